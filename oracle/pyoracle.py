@@ -1,0 +1,227 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  The product never imports it.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+K, KP = 20, 29
+NXCELLS, NSCELLS, NSCELLS_FS = 6, 3, 8
+XC_E, XC_N, XC_J, XC_B, XC_C, XC_SCALE = range(6)
+OK, ERANGE = 0, 16
+ST_NAMES = {1: "M", 2: "D", 3: "I", 4: "S", 5: "N", 6: "B", 7: "E", 8: "C", 9: "T", 10: "J", 11: "X"}
+LOCAL, UNILOCAL = 1, 3
+
+
+class HMM(C.Structure):
+    _fields_ = [("M", C.c_int), ("max_length", C.c_int), ("name", C.c_char * 128), ("acc", C.c_char * 64),
+                ("evparam", C.c_float * 8), ("has_stats_fs3", C.c_int), ("has_stats_fs5", C.c_int),
+                ("fsprob", C.c_float), ("ct", C.c_int), ("compo", C.c_float * K), ("has_compo", C.c_int),
+                ("t", C.POINTER(C.c_float)), ("mat", C.POINTER(C.c_float)), ("ins", C.POINTER(C.c_float)),
+                ("consensus", C.c_char_p)]
+
+
+class BG(C.Structure):
+    _fields_ = [("f", C.c_float * K), ("p1", C.c_float), ("omega", C.c_float),
+                ("fh_t", (C.c_float * 3) * 2), ("fh_e", (C.c_float * K) * 2),
+                ("fh_eo", (C.c_float * KP) * 2), ("fh_pi", C.c_float * 3)]
+
+
+class PROFILE(C.Structure):
+    _fields_ = [("M", C.c_int), ("L", C.c_int), ("mode", C.c_int), ("max_length", C.c_int), ("nj", C.c_float),
+                ("tsc", C.POINTER(C.c_float)), ("rsc", C.POINTER(C.c_float)), ("xsc", (C.c_float * 2) * 4),
+                ("evparam", C.c_float * 8), ("compo", C.c_float * K)]
+
+
+class FS_PROFILE(C.Structure):
+    _fields_ = [("M", C.c_int), ("L", C.c_int), ("mode", C.c_int), ("max_length", C.c_int),
+                ("codon_lengths", C.c_int), ("maxcodons", C.c_int), ("nj", C.c_float), ("fsprob", C.c_float),
+                ("tsc", C.POINTER(C.c_float)), ("rsc", C.POINTER(C.c_float)), ("xsc", (C.c_float * 2) * 4),
+                ("codons", C.POINTER(C.c_uint8)), ("indel_pos", C.POINTER(C.c_uint8)), ("evparam", C.c_float * 8)]
+
+
+class FS_OPROFILE(C.Structure):
+    _fields_ = [("M", C.c_int), ("L", C.c_int), ("mode", C.c_int), ("codon_lengths", C.c_int),
+                ("maxcodons", C.c_int), ("nrows", C.c_int), ("nj", C.c_float),
+                ("rfv", C.POINTER(C.c_float)), ("tfv", C.POINTER(C.c_float)), ("xf", (C.c_float * 2) * 4),
+                ("evparam", C.c_float * 8)]
+
+
+class MX(C.Structure):
+    _fields_ = [("M", C.c_int), ("L", C.c_int), ("allocL", C.c_int), ("nscells", C.c_int),
+                ("dp", C.POINTER(C.c_float)), ("xmx", C.POINTER(C.c_float)), ("totscale", C.c_float),
+                ("has_own_scales", C.c_int)]
+
+
+class TRACE(C.Structure):
+    _fields_ = [("N", C.c_int), ("nalloc", C.c_int), ("M", C.c_int), ("L", C.c_int),
+                ("st", C.POINTER(C.c_char)), ("k", C.POINTER(C.c_int)), ("i", C.POINTER(C.c_int)),
+                ("c", C.POINTER(C.c_int)), ("pp", C.POINTER(C.c_float))]
+
+
+def build(force=False):
+    """Compile oracle/*.c into liboracle.so (gcc).  Building the checker is not using it."""
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-s", "-C", _HERE])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    L = C.CDLL(build())
+    P = C.POINTER
+    u8p, fp = P(C.c_uint8), P(C.c_float)
+    sig = {
+        "bo_hmmfile_read": (C.c_int, [C.c_char_p, C.c_int, P(P(HMM))]),
+        "bo_hmmfile_count": (C.c_int, [C.c_char_p]),
+        "bo_hmm_destroy": (None, [P(HMM)]),
+        "bo_bg_create": (P(BG), []),
+        "bo_bg_destroy": (None, [P(BG)]),
+        "bo_bg_SetLength": (None, [P(BG), C.c_int]),
+        "bo_bg_NullOne": (C.c_float, [P(BG), C.c_int]),
+        "bo_bg_fs_NullOne": (C.c_float, [P(BG), C.c_int]),
+        "bo_profile_config": (P(PROFILE), [P(HMM), P(BG), C.c_int, C.c_int]),
+        "bo_profile_destroy": (None, [P(PROFILE)]),
+        "bo_fs_profile_config": (P(FS_PROFILE), [P(HMM), P(BG), C.c_int, C.c_int, C.c_int, C.c_int]),
+        "bo_fs_profile_destroy": (None, [P(FS_PROFILE)]),
+        "bo_fs_ReconfigLength": (None, [P(FS_PROFILE), C.c_int]),
+        "bo_fs_ReconfigUnihit": (None, [P(FS_PROFILE), C.c_int]),
+        "bo_fs_ReconfigMultihit": (None, [P(FS_PROFILE), C.c_int]),
+        "bo_fs_oprofile_convert": (P(FS_OPROFILE), [P(FS_PROFILE)]),
+        "bo_fs_oprofile_destroy": (None, [P(FS_OPROFILE)]),
+        "bo_fs_oprofile_ReconfigLength": (None, [P(FS_OPROFILE), C.c_int]),
+        "bo_fs_oprofile_ReconfigUnihit": (None, [P(FS_OPROFILE), C.c_int]),
+        "bo_fs_oprofile_ReconfigMultihit": (None, [P(FS_OPROFILE), C.c_int]),
+        "bo_mx_create": (P(MX), [C.c_int, C.c_int, C.c_int]),
+        "bo_mx_destroy": (None, [P(MX)]),
+        "bo_trace_create": (P(TRACE), []),
+        "bo_trace_reuse": (None, [P(TRACE)]),
+        "bo_trace_destroy": (None, [P(TRACE)]),
+        "bo_ForwardParser_Frameshift_3Codons": (C.c_int, [u8p, C.c_int, P(FS_OPROFILE), P(MX), fp]),
+        "bo_BackwardParser_Frameshift_3Codons": (C.c_int, [u8p, C.c_int, P(FS_OPROFILE), P(MX), P(MX), fp]),
+        "bo_Forward_Frameshift": (C.c_int, [u8p, C.c_int, P(FS_OPROFILE), P(MX), fp]),
+        "bo_Backward_Frameshift": (C.c_int, [u8p, C.c_int, P(FS_OPROFILE), P(MX), P(MX), fp]),
+        "bo_Decoding_Frameshift": (C.c_int, [P(FS_OPROFILE), P(MX), P(MX)]),
+        "bo_DomainDecoding_Frameshift": (C.c_int, [fp, P(MX), P(MX), fp, fp, fp]),
+        "bo_OptimalAccuracy_Frameshift": (C.c_int, [P(FS_OPROFILE), P(MX), P(MX), fp]),
+        "bo_OATrace_Frameshift": (C.c_int, [P(FS_OPROFILE), P(MX), P(MX), P(TRACE)]),
+        "bo_Null2_fs_ByExpectation": (C.c_int, [P(FS_OPROFILE), P(MX), fp]),
+        "bo_FLogsum": (C.c_float, [C.c_float, C.c_float]),
+        "bo_FLogsumInit": (None, []),
+        "bo_cephes_expf": (C.c_float, [C.c_float]),
+        "bo_nt_digitize": (C.c_int, [C.c_char]),
+        "bo_aa_digitize": (C.c_int, [C.c_char]),
+        "bo_dna_revcomp": (None, [u8p, C.c_int64]),
+        "bo_gencode_basic": (u8p, [C.c_int]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype, f.argtypes = res, args
+    L.bo_FLogsumInit()
+    _LIB = L
+    return L
+
+
+# ------------------------------------------------------------------ helpers
+
+def u8ptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def fptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def read_fasta(path):
+    """-> list of (name, desc, sequence string)"""
+    out, name, desc, buf = [], None, "", []
+    with open(path) as fh:
+        for line in fh:
+            line = line.rstrip("\n")
+            if line.startswith(">"):
+                if name is not None:
+                    out.append((name, desc, "".join(buf)))
+                hdr = line[1:].split(None, 1)
+                name, desc, buf = hdr[0], (hdr[1] if len(hdr) > 1 else ""), []
+            else:
+                buf.append(line.strip())
+    if name is not None:
+        out.append((name, desc, "".join(buf)))
+    return out
+
+
+_NT = {c: i for i, c in enumerate("ACGT-RYMKSWHBVDN*~")}
+
+
+def digitize_dna(seq):
+    """-> uint8 array, 1-based with sentinels 255 at [0] and [L+1] (ESL_DSQ)"""
+    s = seq.upper().replace("U", "T").replace("X", "N")
+    a = np.full(len(s) + 2, 255, dtype=np.uint8)
+    a[1:-1] = [_NT[c] for c in s]
+    return a
+
+
+def revcomp_dsq(dsq):
+    d = dsq.copy()
+    lib().bo_dna_revcomp(u8ptr(d), len(d) - 2)
+    return d
+
+
+class Model:
+    """One query profile: HMM + bg + gm_fs5/gm_fs3 + om_fs5/om_fs3, as bathsearch
+    sets them up (src/bathsearch.c:794-801: dummy L=100, p7_LOCAL)."""
+
+    def __init__(self, path, index=0, ct=None):
+        L = lib()
+        hp = C.POINTER(HMM)()
+        st = L.bo_hmmfile_read(path.encode(), index, C.byref(hp))
+        if st != OK:
+            raise IOError(f"cannot read model {index} of {path}: status {st}")
+        self.hmm = hp
+        self.M = hp.contents.M
+        self.max_length = hp.contents.max_length
+        self.evparam = list(hp.contents.evparam)
+        self.ct = ct if ct is not None else (hp.contents.ct if hp.contents.ct > 0 else 1)
+        self.bg = L.bo_bg_create()
+        self.gm_fs5 = L.bo_fs_profile_config(self.hmm, self.bg, self.ct, 5, 100, LOCAL)
+        self.gm_fs3 = L.bo_fs_profile_config(self.hmm, self.bg, self.ct, 3, 100, LOCAL)
+        self.om_fs5 = L.bo_fs_oprofile_convert(self.gm_fs5)
+        self.om_fs3 = L.bo_fs_oprofile_convert(self.gm_fs3)
+
+    def rfv(self, which=3):
+        om = (self.om_fs3 if which == 3 else self.om_fs5).contents
+        return np.ctypeslib.as_array(om.rfv, shape=(om.nrows, om.M + 1))
+
+    def tfv(self, which=3):
+        om = (self.om_fs3 if which == 3 else self.om_fs5).contents
+        return np.ctypeslib.as_array(om.tfv, shape=(8, om.M + 1))
+
+    def xf(self, which=3):
+        om = (self.om_fs3 if which == 3 else self.om_fs5).contents
+        return np.array([[om.xf[s][t] for t in range(2)] for s in range(4)], dtype=np.float32)
+
+
+def mx_xmx(mx):
+    m = mx.contents
+    return np.ctypeslib.as_array(m.xmx, shape=(m.allocL + 2, NXCELLS))[: m.L + 1]
+
+
+def mx_dp(mx):
+    m = mx.contents
+    return np.ctypeslib.as_array(m.dp, shape=(m.allocL + 1, m.M + 1, m.nscells))[: m.L + 1]
+
+
+def trace_list(tr):
+    t = tr.contents
+    return [(ST_NAMES[ord(t.st[z])], t.k[z], t.i[z], t.c[z], t.pp[z]) for z in range(t.N)]
