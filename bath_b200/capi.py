@@ -1,0 +1,198 @@
+"""ctypes binding of the C ABI in include/bathgpu.h (the calls a bathsearch build would make)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .build import library_path
+
+OK, EMEM, EINVAL, ERANGE, ENODEVICE, ECUDA = 0, 5, 11, 16, 100, 101
+KP = 29
+
+EXPORTS = [
+    "bathgpu_create", "bathgpu_destroy", "bathgpu_last_error", "bathgpu_device_info",
+    "bathgpu_load_fs_profile", "bathgpu_upload_block", "bathgpu_fs_fwd_windows",
+    "bathgpu_stage_windows", "bathgpu_fs_fwd_staged", "bathgpu_fetch_scores",
+    "bathgpu_fs_bck_decode", "bathgpu_fs_domains", "bathgpu_last_stage_timing",
+]
+
+
+class Window(C.Structure):
+    _fields_ = [("start", C.c_int64), ("L", C.c_int32), ("pmove", C.c_float), ("ploop", C.c_float)]
+
+
+Envelope = Window
+
+window_dtype = np.dtype([("start", "<i8"), ("L", "<i4"), ("pmove", "<f4"), ("ploop", "<f4")], align=True)
+trace_dtype = np.dtype([("i", "<i4"), ("k", "<i2"), ("st", "u1"), ("c", "u1"), ("pp", "<f4")], align=True)
+domain_dtype = np.dtype([("envsc", "<f4"), ("bcksc", "<f4"), ("oasc", "<f4"), ("status", "<i4"),
+                         ("trace_offset", "<i4"), ("trace_len", "<i4"), ("null2", "<f4", (KP,))], align=True)
+
+
+class BathGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"bathgpu status {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load libbathgpu.so.  Fails loudly if it has not been built -- there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `python -m bath_b200.build` "
+                          "(the CUDA library is the product; there is no CPU fallback)")
+    L = C.CDLL(path)
+    vp, fp, ip = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)
+    L.bathgpu_create.restype = C.c_int
+    L.bathgpu_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.bathgpu_destroy.restype = None
+    L.bathgpu_destroy.argtypes = [vp]
+    L.bathgpu_last_error.restype = C.c_char_p
+    L.bathgpu_last_error.argtypes = [vp]
+    L.bathgpu_device_info.restype = C.c_int
+    L.bathgpu_device_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
+    L.bathgpu_load_fs_profile.restype = C.c_int
+    L.bathgpu_load_fs_profile.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp, fp]
+    L.bathgpu_upload_block.restype = C.c_int
+    L.bathgpu_upload_block.argtypes = [vp, C.POINTER(C.c_uint8), C.c_int64]
+    L.bathgpu_fs_fwd_windows.restype = C.c_int
+    L.bathgpu_fs_fwd_windows.argtypes = [vp, vp, C.c_int, fp, fp, ip]
+    L.bathgpu_stage_windows.restype = C.c_int
+    L.bathgpu_stage_windows.argtypes = [vp, vp, C.c_int]
+    L.bathgpu_fs_fwd_staged.restype = C.c_int
+    L.bathgpu_fs_fwd_staged.argtypes = [vp, fp]
+    L.bathgpu_fetch_scores.restype = C.c_int
+    L.bathgpu_fetch_scores.argtypes = [vp, fp, ip, C.c_int]
+    L.bathgpu_fs_bck_decode.restype = C.c_int
+    L.bathgpu_fs_bck_decode.argtypes = [vp, vp, C.c_int, fp, fp, C.POINTER(C.c_int64), fp, fp, fp, fp, fp, ip]
+    L.bathgpu_fs_domains.restype = C.c_int
+    L.bathgpu_fs_domains.argtypes = [vp, vp, C.c_int, fp, vp, vp, C.c_int64]
+    L.bathgpu_last_stage_timing.restype = C.c_int
+    L.bathgpu_last_stage_timing.argtypes = [vp, fp, C.POINTER(C.c_int)]
+    _lib = L
+    return L
+
+
+def _f(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _i(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class Context:
+    """One device context (one stream).  Mirrors the per-worker P7_PIPELINE ownership of the
+    reference (src/bathsearch.c:814-844): one context per worker thread / per GPU."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        st = self.lib.bathgpu_create(device, C.byref(h))
+        if st != OK:
+            raise BathGpuError(st, "bathgpu_create failed (no usable CUDA device?)")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bathgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st != OK:
+            raise BathGpuError(st, self.lib.bathgpu_last_error(self.h).decode())
+
+    def device_info(self):
+        sm, khz, mem = C.c_int(), C.c_int(), C.c_size_t()
+        self._check(self.lib.bathgpu_device_info(self.h, C.byref(sm), C.byref(khz), C.byref(mem)))
+        return {"sm_count": sm.value, "clock_khz": khz.value, "total_mem": mem.value}
+
+    def load_fs_profile(self, which, rfv, tfv):
+        rfv = np.ascontiguousarray(rfv, dtype=np.float32)
+        tfv = np.ascontiguousarray(tfv, dtype=np.float32)
+        nrows, ld = rfv.shape
+        assert tfv.shape == (8, ld)
+        self._check(self.lib.bathgpu_load_fs_profile(self.h, which, ld - 1, nrows, _f(rfv), _f(tfv)))
+
+    def upload_block(self, dsq):
+        dsq = np.ascontiguousarray(dsq, dtype=np.uint8)
+        self._check(self.lib.bathgpu_upload_block(self.h, dsq.ctypes.data_as(C.POINTER(C.c_uint8)), len(dsq) - 2))
+
+    @staticmethod
+    def make_windows(starts, lengths, nj=1.0):
+        """Window descriptors with the length model of p7_fs_oprofile_ReconfigLength(om, L/3)
+        (src/impl_sse/p7_fs_oprofile.c:636-651), computed in float32 as the reference does."""
+        w = np.zeros(len(starts), dtype=window_dtype)
+        w["start"] = starts
+        w["L"] = lengths
+        La = (np.asarray(lengths) // 3).astype(np.float32)
+        njf = np.float32(nj)
+        pmove = (np.float32(2.0) + njf) / (La + np.float32(2.0) + njf)
+        w["pmove"] = pmove.astype(np.float32)
+        w["ploop"] = (np.float32(1.0) - pmove).astype(np.float32)
+        return w
+
+    def fs_fwd_windows(self, wins, xfE=(0.5, 0.5)):
+        n = len(wins)
+        sc = np.empty(n, np.float32)
+        st = np.empty(n, np.int32)
+        xf = np.asarray(xfE, np.float32)
+        self._check(self.lib.bathgpu_fs_fwd_windows(self.h, wins.ctypes.data, n, _f(xf), _f(sc), _i(st)))
+        return sc, st
+
+    def stage_windows(self, wins):
+        self._check(self.lib.bathgpu_stage_windows(self.h, wins.ctypes.data, len(wins)))
+
+    def fs_fwd_staged(self, xfE=(0.5, 0.5)):
+        xf = np.asarray(xfE, np.float32)
+        self._check(self.lib.bathgpu_fs_fwd_staged(self.h, _f(xf)))
+
+    def fetch_scores(self, n):
+        sc = np.empty(n, np.float32)
+        st = np.empty(n, np.int32)
+        self._check(self.lib.bathgpu_fetch_scores(self.h, _f(sc), _i(st), n))
+        return sc, st
+
+    def last_stage_timing(self):
+        ms, nl = C.c_float(), C.c_int()
+        self._check(self.lib.bathgpu_last_stage_timing(self.h, C.byref(ms), C.byref(nl)))
+        return ms.value, nl.value
+
+    def fs_bck_decode(self, wins, xfE, xf5_loop):
+        n = len(wins)
+        Ls = wins["L"].astype(np.int64)
+        off = np.zeros(n, np.int64)
+        off[1:] = np.cumsum(Ls[:-1] + 1)
+        tot = int((Ls + 1).sum())
+        mocc, btot, etot = (np.zeros(tot, np.float32) for _ in range(3))
+        fsc, bsc, st = np.empty(n, np.float32), np.empty(n, np.float32), np.empty(n, np.int32)
+        xf = np.asarray(xfE, np.float32)
+        x5 = np.asarray(xf5_loop, np.float32)
+        self._check(self.lib.bathgpu_fs_bck_decode(self.h, wins.ctypes.data, n, _f(xf), _f(x5),
+                                                   off.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                   _f(mocc), _f(btot), _f(etot), _f(fsc), _f(bsc), _i(st)))
+        split = lambda a: [a[off[w]: off[w] + Ls[w] + 1] for w in range(n)]
+        return split(mocc), split(btot), split(etot), fsc, bsc, st
+
+    def fs_domains(self, envs, xfE5=(1.0, 0.0), max_steps=None):
+        n = len(envs)
+        if max_steps is None:
+            max_steps = int((envs["L"].astype(np.int64) + 8).sum())
+        res = np.zeros(n, dtype=domain_dtype)
+        tr = np.zeros(max_steps, dtype=trace_dtype)
+        xf = np.asarray(xfE5, np.float32)
+        self._check(self.lib.bathgpu_fs_domains(self.h, envs.ctypes.data, n, _f(xf), res.ctypes.data, tr.ctypes.data,
+                                                max_steps))
+        return res, tr

@@ -1,0 +1,382 @@
+// bathgpu.cu -- C-ABI layer of libbathgpu.so (see include/bathgpu.h).
+// Context, device memory, profile images, block upload/packing, stage launchers.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <math.h>
+#include <vector>
+#include <string>
+#include <algorithm>
+
+#include "../../include/bathgpu.h"
+#include "fs_parser.cuh"
+
+using namespace bathgpu;
+
+namespace {
+
+struct DevBuf {
+  void  *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return BATHGPU_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return BATHGPU_EMEM; }
+    cap = want;
+    return BATHGPU_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct FsProfileImage {
+  int   which = 0, M = 0, nrows = 0, J = 0, mpad = 0;
+  DevBuf emis;     // [nrows][mpad]
+  DevBuf cellc;    // forward lane constants
+  DevBuf cellb;    // backward lane constants
+  bool  loaded = false;
+};
+
+}  // namespace
+
+struct bathgpu_ctx {
+  int           device = 0;
+  cudaDeviceProp prop{};
+  cudaStream_t  stream = nullptr;
+  cudaEvent_t   ev0 = nullptr, ev1 = nullptr;
+  std::string   err;
+  FsProfileImage fs3, fs5;
+  DevBuf        dna_bytes, dna4;
+  int64_t       block_n = 0;
+  DevBuf        wins, fwdsc, status, counter;
+  int           nstaged = 0;
+  DevBuf        scratch;
+  float         last_ms = 0.f;
+  int           last_launches = 0;
+};
+
+static int fail(bathgpu_ctx *ctx, int code, const char *fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+#define CUDA_TRY(ctx, call)                                                                      \
+  do { cudaError_t e_ = (call);                                                                  \
+       if (e_ != cudaSuccess) { cudaGetLastError();                                              \
+         return fail(ctx, BATHGPU_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int bathgpu_create(int device, bathgpu_ctx **ret_ctx)
+{
+  if (!ret_ctx) return BATHGPU_EINVAL;
+  *ret_ctx = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return BATHGPU_ENODEVICE; }
+  if (device < 0 || device >= ndev) return BATHGPU_EINVAL;
+  bathgpu_ctx *ctx = new bathgpu_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess) {
+    cudaGetLastError(); delete ctx; return BATHGPU_ENODEVICE;
+  }
+  if (ctx->prop.major < 10) { delete ctx; return BATHGPU_ENODEVICE; }   // sm_100a code only
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+    cudaGetLastError(); delete ctx; return BATHGPU_ECUDA;
+  }
+  *ret_ctx = ctx;
+  return BATHGPU_OK;
+}
+
+extern "C" void bathgpu_destroy(bathgpu_ctx *ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (FsProfileImage *im : { &ctx->fs3, &ctx->fs5 }) { im->emis.release(); im->cellc.release(); im->cellb.release(); }
+  ctx->dna_bytes.release(); ctx->dna4.release(); ctx->wins.release(); ctx->fwdsc.release();
+  ctx->status.release(); ctx->counter.release(); ctx->scratch.release();
+  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char *bathgpu_last_error(const bathgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+extern "C" int bathgpu_device_info(const bathgpu_ctx *ctx, int *sm_count, int *clock_khz, size_t *total_mem)
+{
+  if (!ctx) return BATHGPU_EINVAL;
+  if (sm_count)  *sm_count  = ctx->prop.multiProcessorCount;
+  if (clock_khz) { int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device); *clock_khz = khz; }
+  if (total_mem) *total_mem = ctx->prop.totalGlobalMem;
+  return BATHGPU_OK;
+}
+
+extern "C" int bathgpu_last_stage_timing(const bathgpu_ctx *ctx, float *ms, int *launches)
+{
+  if (!ctx) return BATHGPU_EINVAL;
+  if (ms) *ms = ctx->last_ms;
+  if (launches) *launches = ctx->last_launches;
+  return BATHGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// profile images
+static const int kSupportedJ[] = { 1, 2, 3, 4, 5, 6, 7, 8, 10, 12 };
+
+static int choose_J(int M)
+{
+  for (int J : kSupportedJ) if (32 * J >= M) return J;
+  return 0;
+}
+
+static inline int perm_index(int kk, int J)   // position of node k=kk+1 inside a table row
+{
+  const int VEC = (J % 4 == 0) ? 4 : ((J % 2 == 0) ? 2 : 1);
+  int lane = kk / J, j = kk % J;
+  return (j / VEC) * (32 * VEC) + lane * VEC + (j % VEC);
+}
+
+extern "C" int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int nrows, const float *rfv, const float *tfv)
+{
+  if (!ctx || !rfv || !tfv || M < 1) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_load_fs_profile");
+  if (which != 3 && which != 5)     return fail(ctx, BATHGPU_EINVAL, "codon_lengths must be 3 or 5");
+  const int want_rows = (which == 3 ? 338 : 1367) + BATHGPU_KP;
+  if (nrows != want_rows)           return fail(ctx, BATHGPU_EINVAL, "nrows %d != %d for %d codon lengths", nrows, want_rows, which);
+  const int J = choose_J(M);
+  if (J == 0) return fail(ctx, BATHGPU_EINVAL, "model length %d exceeds the single-warp kernels' limit (%d)", M, 32 * 12);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+
+  FsProfileImage &im = (which == 3) ? ctx->fs3 : ctx->fs5;
+  im.loaded = false;
+  im.which = which; im.M = M; im.nrows = nrows; im.J = J; im.mpad = 32 * J;
+  const int mpad = im.mpad, ld = M + 1;
+
+  // emission table, permuted [c][J/VEC][lane][VEC]
+  std::vector<float> emis((size_t)nrows * mpad, 0.0f);
+  for (int c = 0; c < nrows; ++c)
+    for (int k = 1; k <= M; ++k)
+      emis[(size_t)c * mpad + perm_index(k - 1, J)] = rfv[(size_t)c * ld + k];
+
+  // per-node transition odds, source-node indexed; zero beyond M
+  auto T = [&](int t, int k) -> double { return (k >= 0 && k <= M) ? (double)tfv[(size_t)t * ld + k] : 0.0; };
+  enum { tBM = 0, tMM, tIM, tDM, tMD, tMI, tII, tDD };
+
+  // ---- forward constants
+  {
+    std::vector<float> cc((size_t)(FC_COUNT * J + FL_COUNT) * 32, 0.0f);
+    auto C = [&](int which_c, int j, int lane) -> float & { return cc[(size_t)(which_c * J + j) * 32 + lane]; };
+    std::vector<double> Tsum(mpad + 2, 0.0);       // T_k = sum_{k'>k} prod_{m=k+1}^{k'-1} tDD[m]
+    for (int k = M - 1; k >= 1; --k) Tsum[k] = 1.0 + T(tDD, k + 1) * Tsum[k + 1];
+    std::vector<double> bfull(32, 1.0);
+    for (int lane = 0; lane < 32; ++lane) {
+      double pp = 1.0;
+      for (int j = 0; j < J; ++j) {
+        int k = lane * J + j + 1;
+        C(FC_BM, j, lane) = (float)T(tBM, k - 1);
+        C(FC_MM, j, lane) = (float)T(tMM, k);
+        C(FC_IM, j, lane) = (float)T(tIM, k);
+        C(FC_DM, j, lane) = (float)T(tDM, k);
+        C(FC_MD, j, lane) = (float)T(tMD, k);
+        C(FC_DD, j, lane) = (float)T(tDD, k);
+        C(FC_MI, j, lane) = (float)T(tMI, k);
+        C(FC_II, j, lane) = (float)T(tII, k);
+        C(FC_PP, j, lane) = (float)pp;
+        C(FC_Z,  j, lane) = (k <= M) ? (float)(1.0 + T(tMD, k) * Tsum[k]) : 0.0f;
+        pp *= T(tDD, k);
+      }
+      bfull[lane] = pp;
+    }
+    std::vector<double> b(bfull);
+    for (int s = 0; s < 5; ++s) {
+      int d = 1 << s;
+      std::vector<double> nb(b);
+      for (int lane = 0; lane < 32; ++lane) {
+        cc[(size_t)(FC_COUNT * J + FL_B0 + s) * 32 + lane] = (lane >= d) ? (float)b[lane] : 0.0f;
+        if (lane >= d) nb[lane] = b[lane] * b[lane - d];
+      }
+      b.swap(nb);
+    }
+    if (im.cellc.reserve(cc.size() * sizeof(float)) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
+    CUDA_TRY(ctx, cudaMemcpyAsync(im.cellc.p, cc.data(), cc.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+
+  if (im.emis.reserve(emis.size() * sizeof(float)) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
+  CUDA_TRY(ctx, cudaMemcpyAsync(im.emis.p, emis.data(), emis.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  im.loaded = true;
+  return BATHGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// block upload: ESL_DSQ bytes -> 4-bit packed words, one guard word in front, two behind
+__global__ void pack_dna4_kernel(const uint8_t *__restrict__ dsq, long long n, uint32_t *__restrict__ out, long long nwords)
+{
+  long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nwords) return;
+  uint32_t word = 0;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    long long p = w * 8 + b - 8;          // 0-based nt index
+    uint32_t  code = 15u;
+    if (p >= 0 && p < n) { code = dsq[p + 1]; if (code > 15u) code = 15u; }
+    word |= code << (4 * b);
+  }
+  out[w] = word;
+}
+
+extern "C" int bathgpu_upload_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_t n)
+{
+  if (!ctx || !dsq || n < 1) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_upload_block");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const long long nwords = (n + 8 + 7) / 8 + 2;
+  if (ctx->dna_bytes.reserve((size_t)n + 2) != BATHGPU_OK || ctx->dna4.reserve((size_t)nwords * 4) != BATHGPU_OK)
+    return fail(ctx, BATHGPU_EMEM, "device allocation failed for a %lld-nt block", (long long)n);
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dna_bytes.p, dsq, (size_t)n + 2, cudaMemcpyHostToDevice, ctx->stream));
+  const int threads = 256;
+  const long long blocks = (nwords + threads - 1) / threads;
+  pack_dna4_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(ctx->dna_bytes.as<uint8_t>(), n, ctx->dna4.as<uint32_t>(), nwords);
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->block_n = n;
+  return BATHGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward parser stage
+template <int J, bool XMX>
+static cudaError_t launch_fwd(const FsParserArgs &a, int grid, cudaStream_t s)
+{
+  fs3_forward_parser_kernel<J, XMX><<<grid, 128, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+template <bool XMX>
+static cudaError_t dispatch_fwd(int J, const FsParserArgs &a, int grid, cudaStream_t s)
+{
+  switch (J) {
+  case 1:  return launch_fwd<1, XMX>(a, grid, s);
+  case 2:  return launch_fwd<2, XMX>(a, grid, s);
+  case 3:  return launch_fwd<3, XMX>(a, grid, s);
+  case 4:  return launch_fwd<4, XMX>(a, grid, s);
+  case 5:  return launch_fwd<5, XMX>(a, grid, s);
+  case 6:  return launch_fwd<6, XMX>(a, grid, s);
+  case 7:  return launch_fwd<7, XMX>(a, grid, s);
+  case 8:  return launch_fwd<8, XMX>(a, grid, s);
+  case 10: return launch_fwd<10, XMX>(a, grid, s);
+  case 12: return launch_fwd<12, XMX>(a, grid, s);
+  default: return cudaErrorInvalidValue;
+  }
+}
+
+template <int J, bool XMX>
+static int fwd_occupancy()
+{
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fs3_forward_parser_kernel<J, XMX>, 128, 0);
+  return nb;
+}
+
+static int fwd_blocks_per_sm(int J, bool xmx)
+{
+#define OCC(J_) case J_: return xmx ? fwd_occupancy<J_, true>() : fwd_occupancy<J_, false>();
+  switch (J) { OCC(1) OCC(2) OCC(3) OCC(4) OCC(5) OCC(6) OCC(7) OCC(8) OCC(10) OCC(12) default: return 1; }
+#undef OCC
+}
+
+static int check_windows(bathgpu_ctx *ctx, const bathgpu_window *wins, int n)
+{
+  for (int w = 0; w < n; ++w) {
+    if (wins[w].L < 3 || wins[w].start < 1 || wins[w].start + wins[w].L - 1 > ctx->block_n)
+      return fail(ctx, BATHGPU_EINVAL, "window %d (start %lld, L %d) is outside the uploaded block (n=%lld) or shorter than 3",
+                  w, (long long)wins[w].start, wins[w].L, (long long)ctx->block_n);
+  }
+  return BATHGPU_OK;
+}
+
+extern "C" int bathgpu_stage_windows(bathgpu_ctx *ctx, const bathgpu_window *wins, int n)
+{
+  if (!ctx || !wins || n < 1) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_stage_windows");
+  if (ctx->block_n == 0)      return fail(ctx, BATHGPU_EINVAL, "no block uploaded");
+  int st = check_windows(ctx, wins, n);
+  if (st != BATHGPU_OK) return st;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  static_assert(sizeof(WindowDesc) == sizeof(bathgpu_window), "descriptor layouts must agree");
+  if (ctx->wins.reserve((size_t)n * sizeof(WindowDesc)) != BATHGPU_OK || ctx->fwdsc.reserve((size_t)n * 4) != BATHGPU_OK ||
+      ctx->status.reserve((size_t)n * 4) != BATHGPU_OK || ctx->counter.reserve(64) != BATHGPU_OK)
+    return fail(ctx, BATHGPU_EMEM, "device allocation failed");
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->wins.p, wins, (size_t)n * sizeof(WindowDesc), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->nstaged = n;
+  return BATHGPU_OK;
+}
+
+extern "C" int bathgpu_fs_fwd_staged(bathgpu_ctx *ctx, const float xfE[2])
+{
+  if (!ctx || !xfE)          return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fs_fwd_staged");
+  if (!ctx->fs3.loaded)      return fail(ctx, BATHGPU_EINVAL, "3-codon profile not loaded");
+  if (ctx->nstaged < 1)      return fail(ctx, BATHGPU_EINVAL, "no windows staged");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const FsProfileImage &im = ctx->fs3;
+  FsParserArgs a{};
+  a.emis = im.emis.as<float>(); a.cellc = im.cellc.as<float>(); a.dna4 = ctx->dna4.as<uint32_t>();
+  a.wins = ctx->wins.as<WindowDesc>(); a.nwin = ctx->nstaged; a.mpad = im.mpad;
+  a.tEM = xfE[0]; a.tEL = xfE[1];
+  a.fwdsc = ctx->fwdsc.as<float>(); a.status = ctx->status.as<int>();
+  a.xmx = nullptr; a.xoff = nullptr; a.counter = ctx->counter.as<int>();
+
+  const int per_sm = std::max(1, fwd_blocks_per_sm(im.J, false));
+  const int grid   = std::min((ctx->nstaged + 3) / 4, ctx->prop.multiProcessorCount * per_sm);
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  CUDA_TRY(ctx, dispatch_fwd<false>(im.J, a, grid, ctx->stream));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+  ctx->last_launches = 1;
+  return BATHGPU_OK;
+}
+
+extern "C" int bathgpu_fetch_scores(bathgpu_ctx *ctx, float *fwdsc, int32_t *status, int n)
+{
+  if (!ctx || n < 1 || n > ctx->nstaged) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fetch_scores");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (fwdsc)  CUDA_TRY(ctx, cudaMemcpyAsync(fwdsc,  ctx->fwdsc.p,  (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (status) CUDA_TRY(ctx, cudaMemcpyAsync(status, ctx->status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return BATHGPU_OK;
+}
+
+extern "C" int bathgpu_fs_fwd_windows(bathgpu_ctx *ctx, const bathgpu_window *wins, int n, const float xfE[2],
+                                      float *fwdsc, int32_t *status)
+{
+  int st;
+  if (!fwdsc || !status) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fs_fwd_windows");
+  if ((st = bathgpu_stage_windows(ctx, wins, n)) != BATHGPU_OK) return st;
+  if ((st = bathgpu_fs_fwd_staged(ctx, xfE))     != BATHGPU_OK) return st;
+  return bathgpu_fetch_scores(ctx, fwdsc, status, n);
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int bathgpu_fs_bck_decode(bathgpu_ctx *ctx, const bathgpu_window *wins, int n, const float xfE[2],
+                                     const float xf5_loop[3], const int64_t *out_offset,
+                                     float *mocc, float *btot, float *etot, float *fwdsc, float *bcksc, int32_t *status)
+{
+  return fail(ctx, BATHGPU_EINVAL, "bathgpu_fs_bck_decode: stage not built yet");
+}
+
+extern "C" int bathgpu_fs_domains(bathgpu_ctx *ctx, const bathgpu_envelope *envs, int n, const float xfE5[2],
+                                  bathgpu_domain_result *results, bathgpu_trace_step *traces, int64_t max_steps)
+{
+  return fail(ctx, BATHGPU_EINVAL, "bathgpu_fs_domains: stage not built yet");
+}

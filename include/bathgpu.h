@@ -1,0 +1,141 @@
+/* bathgpu.h -- C ABI of libbathgpu.so: the B200 (sm_100a) engine for the
+ * translated-search hot path of BATH's bathsearch.
+ *
+ * The reference has no FFI today; its replaceable boundary is the "impl" layer
+ * (src/hmmer.h:1044-1052 includes one of impl_{sse,avx,neon}.h; impl_avx already
+ * exposes every kernel as a patchable function pointer, src/impl_avx/fwdback_fs.c:21-22).
+ * One-window-at-a-time calls cannot feed a GPU, so each entry point below is the
+ * BATCHED form of one impl-layer function; the per-item semantics (inputs, outputs,
+ * Easel status codes) are those of the function it replaces:
+ *
+ *   bathgpu_load_fs_profile   <- p7_fs_oprofile_Convert      src/impl_sse/p7_fs_oprofile.c:222-296
+ *   bathgpu_upload_block      <- ESL_SQ block handed to p7_Pipeline_BATH  src/bathsearch.c:1261,1272
+ *   bathgpu_fs_fwd_windows    <- p7_ForwardParser_Frameshift_3Codons      src/impl_sse/impl_sse.h:493
+ *                                (call site src/p7_pipeline.c:1446-1450)
+ *   bathgpu_fs_bck_decode     <- p7_BackwardParser_Frameshift_3Codons + p7_DomainDecoding_Frameshift
+ *                                src/impl_sse/impl_sse.h:494,484 (call sites src/p7_pipeline.c:1470, src/p7_domaindef.c:320)
+ *   bathgpu_fs_domains        <- p7_Forward_Frameshift, p7_Backward_Frameshift, p7_Decoding_Frameshift,
+ *                                p7_OptimalAccuracy_Frameshift, p7_OATrace_Frameshift, p7_Null2_fs_ByExpectation
+ *                                src/impl_sse/impl_sse.h:497-498,483,523-524,516 (call sites src/p7_domaindef.c:1022-1082)
+ *
+ * Plain pointers and sizes only.  All functions return an Easel-style status
+ * (0 = eslOK); per-item status[] carries eslERANGE (16) exactly where the reference
+ * function would have returned it.  There is no CPU fallback: every call fails with
+ * BATHGPU_ENODEVICE if no CUDA device is usable.
+ */
+#ifndef BATHGPU_H
+#define BATHGPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BATHGPU_OK         0
+#define BATHGPU_EMEM       5    /* eslEMEM   */
+#define BATHGPU_EINVAL     11   /* eslEINVAL */
+#define BATHGPU_ERANGE     16   /* eslERANGE */
+#define BATHGPU_ENODEVICE  100
+#define BATHGPU_ECUDA      101
+
+#define BATHGPU_NXCELLS    6    /* E,N,J,B,C,SCALE  (impl_sse.h:324) */
+#define BATHGPU_KP         29
+
+typedef struct bathgpu_ctx bathgpu_ctx;
+
+/* One DNA window of the uploaded block: nucleotides block[start .. start+L-1]
+ * (1-based block coordinates, as dna_window->n / ->length in src/p7_pipeline.c:1376-1380).
+ * pmove/ploop are the N/C/J odds p7_fs_oprofile_ReconfigLength(om_fs3, L/3) would set
+ * (src/impl_sse/p7_fs_oprofile.c:636-651); the caller computes them so the length model
+ * stays host-owned. */
+typedef struct {
+  int64_t start;
+  int32_t L;
+  float   pmove;
+  float   ploop;
+} bathgpu_window;
+
+/* One trace step of an optimal-accuracy alignment (P7_TRACE st/k/i/c/pp; src/hmmer.h P7_TRACE). */
+typedef struct {
+  int32_t i;
+  int16_t k;
+  uint8_t st;
+  uint8_t c;
+  float   pp;
+} bathgpu_trace_step;
+
+/* One envelope to rescore: nucleotides block[start .. start+L-1]; pmove/ploop from
+ * p7_fs_oprofile_ReconfigLength(om_fs5, L/3) in unihit mode (src/p7_domaindef.c:1018). */
+typedef struct {
+  int64_t start;
+  int32_t L;
+  float   pmove;
+  float   ploop;
+} bathgpu_envelope;
+
+/* Per-envelope results of the domain stage (what rescore_isolated_domain_frameshift
+ * reads back, src/p7_domaindef.c:1022-1082). */
+typedef struct {
+  float   envsc;        /* Forward score, nats            */
+  float   bcksc;        /* Backward score, nats           */
+  float   oasc;         /* optimal-accuracy expected score */
+  int32_t status;       /* 0, or eslERANGE from fwd/bck/decoding */
+  int32_t trace_offset; /* first step in the trace buffer  */
+  int32_t trace_len;
+  float   null2[BATHGPU_KP];
+} bathgpu_domain_result;
+
+/* ---- context ---------------------------------------------------------- */
+int         bathgpu_create(int device, bathgpu_ctx **ret_ctx);
+void        bathgpu_destroy(bathgpu_ctx *ctx);
+const char *bathgpu_last_error(const bathgpu_ctx *ctx);
+int         bathgpu_device_info(const bathgpu_ctx *ctx, int *sm_count, int *clock_khz, size_t *total_mem);
+
+/* ---- profile images ---------------------------------------------------- */
+/* which = 3 or 5 codon lengths.  rfv: [nrows][M+1] emission odds ratios, row c as
+ * P7_FS_OPROFILE->rfv[c] un-striped, column 0 unused; tfv: [8][M+1] transition odds,
+ * order BM,MM,IM,DM,MD,MI,II,DD, SOURCE-node indexed (tfv[t][k] = exp(TSC(k,t)), 0 at k=M). */
+int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int nrows, const float *rfv, const float *tfv);
+
+/* ---- target block ------------------------------------------------------ */
+/* dsq: ESL_DSQ codes, dsq[1..n] valid (dsq[0], dsq[n+1] sentinels).  Packed to 4 bits/nt on device. */
+int bathgpu_upload_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_t n);
+
+/* ---- a9: frameshift Forward parser (3 codon lengths) over windows ------- */
+/* xfE = {E->MOVE, E->LOOP} odds (om_fs3->xf[p7O_E]).  Outputs: fwdsc[n] nats, status[n]. */
+int bathgpu_fs_fwd_windows(bathgpu_ctx *ctx, const bathgpu_window *wins, int n, const float xfE[2],
+                           float *fwdsc, int32_t *status);
+
+/* Same stage on descriptors already resident in device memory (set by
+ * bathgpu_stage_windows); results stay on the device until bathgpu_fetch_scores.
+ * Used to time the kernel with inputs resident in HBM. */
+int bathgpu_stage_windows(bathgpu_ctx *ctx, const bathgpu_window *wins, int n);
+int bathgpu_fs_fwd_staged(bathgpu_ctx *ctx, const float xfE[2]);
+int bathgpu_fetch_scores(bathgpu_ctx *ctx, float *fwdsc, int32_t *status, int n);
+
+/* ---- a10+a11: Backward parser + domain decoding ------------------------- */
+/* For each window: re-runs the Forward parser keeping X rows, runs the Backward parser,
+ * then DomainDecoding.  xf5_loop = {N,J,C}->LOOP odds of the profile the reference passes
+ * to p7_DomainDecoding_Frameshift (om_fs5, src/p7_domaindef.c:320).  Outputs are
+ * concatenated per window at out_offset[w] .. +L (L+1 floats each); bcksc[n]; status[n]. */
+int bathgpu_fs_bck_decode(bathgpu_ctx *ctx, const bathgpu_window *wins, int n, const float xfE[2],
+                          const float xf5_loop[3], const int64_t *out_offset,
+                          float *mocc, float *btot, float *etot, float *fwdsc, float *bcksc, int32_t *status);
+
+/* ---- a12-a15: per-envelope Forward/Backward/Decoding/OA/trace/null2 ------ */
+/* xfE5 = {E->MOVE, E->LOOP} odds of om_fs5 (unihit: {1,0}).  traces: caller-allocated buffer
+ * of max_steps steps; results[e].trace_offset/len index into it. */
+int bathgpu_fs_domains(bathgpu_ctx *ctx, const bathgpu_envelope *envs, int n, const float xfE5[2],
+                       bathgpu_domain_result *results, bathgpu_trace_step *traces, int64_t max_steps);
+
+/* ---- measurement helpers ------------------------------------------------ */
+/* Device time (ms) of the kernels launched by the most recent stage call, measured with
+ * CUDA events on the context's stream, and how many kernels that call launched. */
+int bathgpu_last_stage_timing(const bathgpu_ctx *ctx, float *ms, int *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,96 @@
+"""GPU parity: frameshift Forward parser (a9) through the C ABI vs the CPU oracle.
+
+Tolerance: north_star asks Forward/Backward bit scores within 0.01 bit = 0.00693 nat;
+we assert 1e-3 nat (the reference's own SIMD-vs-generic bar with exact logsum,
+src/impl_sse/fwdback_fs.c:3189) on every window.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import common
+
+pytestmark = pytest.mark.gpu
+
+TOL_NATS = 1e-3
+
+
+def oracle_fwd(po, model, dsq, start, L):
+    lib = po.lib()
+    lib.bo_fs_oprofile_ReconfigLength(model.om_fs3, L // 3)
+    ox = lib.bo_mx_create(model.M, L, 0)
+    sc = C.c_float()
+    sub = np.ascontiguousarray(dsq[start - 1: start + L + 1])
+    st = lib.bo_ForwardParser_Frameshift_3Codons(po.u8ptr(sub), L, model.om_fs3, ox, C.byref(sc))
+    xmx = po.mx_xmx(ox).copy()
+    lib.bo_mx_destroy(ox)
+    return st, sc.value, xmx
+
+
+def make_block(rng, model, n_random, n_homolog, lengths):
+    """one block: windows of random DNA and windows holding planted frameshifted homologs"""
+    mat = common.hmm_mat(model)
+    pieces, wins = [], []
+    pos = 1
+    for t in range(n_random + n_homolog):
+        L = int(lengths[t % len(lengths)])
+        if t < n_random:
+            seg = rng.integers(0, 4, L).astype(np.uint8)
+            if t % 7 == 3:
+                seg[rng.integers(0, L, 3)] = 15          # a few N's (degenerate rows)
+        else:
+            ins = common.sample_homolog(rng, mat, fs_rate=0.03, stop_rate=0.01)
+            ins = ins[: max(30, L - 20)]
+            left = (L - len(ins)) // 2
+            seg = np.concatenate([rng.integers(0, 4, left), ins, rng.integers(0, 4, L - left - len(ins))]).astype(np.uint8)
+        gap = rng.integers(0, 4, int(rng.integers(0, 9))).astype(np.uint8)   # unaligned window starts
+        pieces += [gap, seg]
+        pos += len(gap)
+        wins.append((pos, L))
+        pos += L
+    body = np.concatenate(pieces)
+    dsq = np.full(len(body) + 2, 255, np.uint8)
+    dsq[1:-1] = body
+    return dsq, wins
+
+
+@pytest.mark.parametrize("hmmfile,index", [("AMP_N.bhmm", 0), ("2OG-FeII_Oxy_3.bhmm", 0),
+                                           ("tRNA-synthetases.bhmm", 0), ("tRNA-synthetases.bhmm", 2),
+                                           ("PTHR37536.bhmm", 0)])
+def test_forward_parser_matches_oracle(oracle, gpu_ctx, hmmfile, index):
+    po = oracle
+    from bath_b200 import capi
+    model = po.Model(common.golden(hmmfile), index)
+    rng = np.random.default_rng(42 + index)
+    dsq, wins = make_block(rng, model, n_random=24, n_homolog=24,
+                           lengths=[60, 61, 62, 63, 300, 447, 600, 3 * max(model.max_length, 300) + 5])
+    gpu_ctx.load_fs_profile(3, model.rfv(3), model.tfv(3))
+    gpu_ctx.upload_block(dsq)
+    w = capi.Context.make_windows([s for s, _ in wins], [l for _, l in wins], nj=1.0)
+    sc, st = gpu_ctx.fs_fwd_windows(w, xfE=(0.5, 0.5))
+    worst = 0.0
+    for t, (s, L) in enumerate(wins):
+        ost, osc, _ = oracle_fwd(po, model, dsq, s, L)
+        assert st[t] == ost, (t, s, L, st[t], ost)
+        if ost == 0:
+            worst = max(worst, abs(sc[t] - osc))
+            assert abs(sc[t] - osc) <= TOL_NATS, (t, s, L, sc[t], osc)
+    print(f"{hmmfile}[{index}] M={model.M}: {len(wins)} windows, max |dsc| = {worst:.2e} nat")
+
+
+def test_forward_parser_golden_window(oracle, gpu_ctx):
+    """tutorial/target-AMP_N.fa as one window: the score the pinned oracle gives (50.705 nats)."""
+    po = oracle
+    from bath_b200 import capi
+    model = po.Model(common.golden("AMP_N.bhmm"))
+    _, _, seq = po.read_fasta(common.golden("target-AMP_N.fa"))[0]
+    dsq = po.digitize_dna(seq)
+    gpu_ctx.load_fs_profile(3, model.rfv(3), model.tfv(3))
+    gpu_ctx.upload_block(dsq)
+    w = capi.Context.make_windows([1], [len(seq)])
+    sc, st = gpu_ctx.fs_fwd_windows(w)
+    ost, osc, _ = oracle_fwd(po, model, dsq, 1, len(seq))
+    assert st[0] == 0 and ost == 0
+    assert abs(sc[0] - osc) <= TOL_NATS
+    assert abs(sc[0] - 50.70534) <= 2e-3
