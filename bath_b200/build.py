@@ -11,7 +11,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 
 def library_path():
-    return _SO
+    """Path of the built library (BATHGPU_LIB overrides it, for A/B builds while tuning)."""
+    return os.environ.get("BATHGPU_LIB", _SO)
 
 
 def _sources():

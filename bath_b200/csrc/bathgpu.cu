@@ -161,37 +161,47 @@ extern "C" int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int n
   im.which = which; im.M = M; im.nrows = nrows; im.J = J; im.mpad = 32 * J;
   const int mpad = im.mpad, ld = M + 1;
 
-  // emission table, permuted [c][J/VEC][lane][VEC]
-  std::vector<float> emis((size_t)nrows * mpad, 0.0f);
-  for (int c = 0; c < nrows; ++c)
-    for (int k = 1; k <= M; ++k)
-      emis[(size_t)c * mpad + perm_index(k - 1, J)] = rfv[(size_t)c * ld + k];
-
   // per-node transition odds, source-node indexed; zero beyond M
   auto T = [&](int t, int k) -> double { return (k >= 0 && k <= M) ? (double)tfv[(size_t)t * ld + k] : 0.0; };
   enum { tBM = 0, tMM, tIM, tDM, tMD, tMI, tII, tDD };
+
+  // Folding constants (all in double, rounded once):
+  //   s(k) = tBM(k-1): entry odds of node k.  The kernels carry V(k)/s(k), so s(k) must be positive
+  //          (true for every local-mode profile: occ(k) > 0, src/modelconfig.c:90-97).
+  //   Z(k) = 1 + tMD(k) * sum_{k'>k} prod_{m=k+1}^{k'-1} tDD(m): E(i) = sum_k M(i,k) Z(k).
+  std::vector<double> sK(mpad + 2, 1.0), zK(mpad + 2, 0.0), Tsum(mpad + 2, 0.0);
+  for (int k = 1; k <= M; ++k) {
+    sK[k] = T(tBM, k - 1);
+    if (!(sK[k] > 0.0) || !std::isfinite(sK[k]))
+      return fail(ctx, BATHGPU_EINVAL, "node %d has entry odds %g: only local-mode profiles are supported", k, sK[k]);
+  }
+  for (int k = M - 1; k >= 1; --k) Tsum[k] = 1.0 + T(tDD, k + 1) * Tsum[k + 1];
+  for (int k = 1; k <= M; ++k) zK[k] = 1.0 + T(tMD, k) * Tsum[k];
+
+  // emission table, permuted [c][J/VEC][lane][VEC], scaled by s(k) Z(k)
+  std::vector<float> emis((size_t)nrows * mpad, 0.0f);
+  for (int c = 0; c < nrows; ++c)
+    for (int k = 1; k <= M; ++k)
+      emis[(size_t)c * mpad + perm_index(k - 1, J)] = (float)((double)rfv[(size_t)c * ld + k] * sK[k] * zK[k]);
 
   // ---- forward constants
   {
     std::vector<float> cc((size_t)(FC_COUNT * J + FL_COUNT) * 32, 0.0f);
     auto C = [&](int which_c, int j, int lane) -> float & { return cc[(size_t)(which_c * J + j) * 32 + lane]; };
-    std::vector<double> Tsum(mpad + 2, 0.0);       // T_k = sum_{k'>k} prod_{m=k+1}^{k'-1} tDD[m]
-    for (int k = M - 1; k >= 1; --k) Tsum[k] = 1.0 + T(tDD, k + 1) * Tsum[k + 1];
     std::vector<double> bfull(32, 1.0);
     for (int lane = 0; lane < 32; ++lane) {
       double pp = 1.0;
       for (int j = 0; j < J; ++j) {
         int k = lane * J + j + 1;
-        C(FC_BM, j, lane) = (float)T(tBM, k - 1);
-        C(FC_MM, j, lane) = (float)T(tMM, k);
-        C(FC_IM, j, lane) = (float)T(tIM, k);
-        C(FC_DM, j, lane) = (float)T(tDM, k);
-        C(FC_MD, j, lane) = (float)T(tMD, k);
-        C(FC_DD, j, lane) = (float)T(tDD, k);
-        C(FC_MI, j, lane) = (float)T(tMI, k);
-        C(FC_II, j, lane) = (float)T(tII, k);
-        C(FC_PP, j, lane) = (float)pp;
-        C(FC_Z,  j, lane) = (k <= M) ? (float)(1.0 + T(tMD, k) * Tsum[k]) : 0.0f;
+        if (k <= M) {
+          double sn = sK[k + 1];      // s(k+1); 1.0 at k = M where every outgoing transition is 0
+          C(FC_MM, j, lane) = (float)(T(tMM, k) / (zK[k] * sn));
+          C(FC_DM, j, lane) = (float)(T(tDM, k) / sn);
+          C(FC_MD, j, lane) = (float)(T(tMD, k) / zK[k]);
+          C(FC_DD, j, lane) = (float)T(tDD, k);
+          C(FC_MI, j, lane) = (float)(T(tMI, k) * T(tIM, k) / (zK[k] * sn));
+          C(FC_II, j, lane) = (float)T(tII, k);
+        }
         pp *= T(tDD, k);
       }
       bfull[lane] = pp;
@@ -257,7 +267,7 @@ extern "C" int bathgpu_upload_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_
 template <int J, bool XMX>
 static cudaError_t launch_fwd(const FsParserArgs &a, int grid, cudaStream_t s)
 {
-  fs3_forward_parser_kernel<J, XMX><<<grid, 128, 0, s>>>(a);
+  fs3_forward_parser_kernel<J, XMX><<<grid, FwdTune<J>::kThreads, 0, s>>>(a);
   return cudaGetLastError();
 }
 
@@ -283,7 +293,7 @@ template <int J, bool XMX>
 static int fwd_occupancy()
 {
   int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fs3_forward_parser_kernel<J, XMX>, 128, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fs3_forward_parser_kernel<J, XMX>, FwdTune<J>::kThreads, 0);
   return nb;
 }
 
@@ -336,7 +346,8 @@ extern "C" int bathgpu_fs_fwd_staged(bathgpu_ctx *ctx, const float xfE[2])
   a.xmx = nullptr; a.xoff = nullptr; a.counter = ctx->counter.as<int>();
 
   const int per_sm = std::max(1, fwd_blocks_per_sm(im.J, false));
-  const int grid   = std::min((ctx->nstaged + 3) / 4, ctx->prop.multiProcessorCount * per_sm);
+  const int wpb    = 1;   // FwdTune<J>::kThreads / 32
+  const int grid   = std::min((ctx->nstaged + wpb - 1) / wpb, ctx->prop.multiProcessorCount * per_sm);
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   CUDA_TRY(ctx, dispatch_fwd<false>(im.J, a, grid, ctx->stream));

@@ -10,14 +10,16 @@
 //    instead of the reference's 4x3 MDI ring + 3 IVX rows = 15;
 //  * the D->D chain D(k+1) = M(k) tMD(k) + D(k) tDD(k) is a first-order linear recurrence: a serial
 //    pass inside the lane plus a 5-step warp-shuffle scan whose multipliers are profile constants;
-//  * E(i) = sum_k M(i,k)+D(i,k) is taken as a dot product sum_k M(i,k) Z(k) with the profile constant
+//  * E(i) = sum_k M(i,k)+D(i,k) equals sum_k M(i,k) Z(k) with the profile constant
 //    Z(k) = 1 + tMD(k) (1 + tDD(k+1) + tDD(k+1) tDD(k+2) + ...), so E (hence B(i), hence row i+2)
-//    does not wait for the D scan;
+//    does not wait for the D scan; Z(k) and the entry odds tBM(k-1) are folded into the emission
+//    table once per profile, which removes two constants and two multiplies per node and row;
 //  * the three emission rows of a DP row are read with coalesced 128/64/32-bit loads from a table laid
 //    out [codon][J/VEC][lane][VEC]; the table is L1/L2 resident (0.3 MB at M=200);
-//  * target nucleotides are 4-bit packed, fetched one 16-bit quad (4 rows) ahead;
+//  * target nucleotides are 4-bit packed; each lane turns 4 nibbles into the three emission-row indices of
+//    one DP row, 32 rows per step, and rows pick their word up with one shuffle;
 //  * rows are unrolled by 4 so every ring slot is a compile-time register name; the window is entered
-//    at row 0 and the loop may run up to 3 rows past L (their results are discarded).
+//    through 0..3 all-zero pad rows in front so that the last quad ends exactly at row L.
 //
 // Rescaling follows the reference: when E(i) > 1e4 everything live is divided by E(i) and log E(i)
 // is accumulated (fwdback_fs.c:472-496).
@@ -30,7 +32,7 @@ namespace bathgpu {
 constexpr int kWarp = 32;
 
 // lane-constant image: [NC][J][32] floats then [NL][32] floats
-enum FwdCellConst { FC_BM = 0, FC_MM, FC_IM, FC_DM, FC_MD, FC_DD, FC_PP, FC_MI, FC_II, FC_Z, FC_COUNT };
+enum FwdCellConst { FC_MM = 0, FC_DM, FC_MD, FC_DD, FC_MI, FC_II, FC_COUNT };
 enum FwdLaneConst { FL_B0 = 0, FL_B1, FL_B2, FL_B3, FL_B4, FL_COUNT };
 
 struct WindowDesc {      // device copy of bathgpu_window
@@ -63,18 +65,18 @@ __device__ __forceinline__ int codon3_fs3(int v, int w, int x)        { int c = 
 __device__ __forceinline__ int codon4_fs3(int u, int v, int w, int x) { int c = x * 84 + w * 21 + v * 5 + u + 2; return min(c, 337); }
 
 template <int J, int VEC>
-__device__ __forceinline__ void load_emission_row(const float *__restrict__ row, int lane, float (&e)[J])
+__device__ __forceinline__ void load_emission_row(const float *__restrict__ row, float (&e)[J])
 {
 #pragma unroll
   for (int g = 0; g < J / VEC; ++g) {
     if constexpr (VEC == 4) {
-      float4 t = __ldg(reinterpret_cast<const float4 *>(row) + g * kWarp + lane);
+      float4 t = __ldg(reinterpret_cast<const float4 *>(row) + g * kWarp);
       e[4 * g + 0] = t.x; e[4 * g + 1] = t.y; e[4 * g + 2] = t.z; e[4 * g + 3] = t.w;
     } else if constexpr (VEC == 2) {
-      float2 t = __ldg(reinterpret_cast<const float2 *>(row) + g * kWarp + lane);
+      float2 t = __ldg(reinterpret_cast<const float2 *>(row) + g * kWarp);
       e[2 * g + 0] = t.x; e[2 * g + 1] = t.y;
     } else {
-      e[g] = __ldg(row + g * kWarp + lane);
+      e[g] = __ldg(row + g * kWarp);
     }
   }
 }
@@ -98,103 +100,104 @@ __device__ __forceinline__ uint32_t fetch_quad(const uint32_t *__restrict__ dna4
 
 template <int J>
 struct FwdState {
-  float V[4][J];       // V(r) in slot r&3
-  float I[4][J];       // I(r) in slot r&3
+  float W[4][J];       // W(r)[k] = V(r)[k] / s(k), s(k) = tBM(k-1), in slot r&3   (V = the reference's IVX)
+  float I[4][J];       // I~(r)[k] = I(r,k) tIM(k) / s(k+1) in slot r&3
   float xN[4], xJ[4], xC[4];
 };
 
+// Per-node constants with the entry odds s(k) and the E weights Z(k) folded in (see bathgpu.cu):
+//   table T[c][k] = R[c][k] s(k) Z(k)  =>  sum_c W T = M(i,k) Z(k) =: Mz
+//   mm = tMM(k) / (Z(k) s(k+1)),  dm = tDM(k) / s(k+1),  md = tMD(k) / Z(k),  dd = tDD(k),
+//   mi = tMI(k) tIM(k) / (Z(k) s(k+1)),  ii = tII(k)
 template <int J>
 struct FwdConsts {
-  float bm[J], mm[J], im[J], dm[J], md[J], dd[J], pp[J], mi[J], ii[J], z[J];
+  float mm[J], dm[J], md[J], dd[J], mi[J], ii[J];
   float bs[5];
 };
 
-// One DP row i of the Forward parser.  PH = i & 3 (compile time).
-// cend[0..2] capture C(L), C(L-1), C(L-2) because the row loop may run up to 3 rows past L.
+// One DP row of the Forward parser.  r = i + pad is the padded row number (pad rows i<0 in front so
+// that the last quad ends exactly at row L); PH = r & 3 is compile time, so ring slots are register names.
 template <int J, int VEC, int PH, bool XMX>
-__device__ __forceinline__ void fwd_row(int i, int L, int lane, FwdState<J> &S, const FwdConsts<J> &K,
-                                        const float *__restrict__ emis, int mpad, int c2, int c3, int c4,
+__device__ __forceinline__ void fwd_row(int i, int lane, FwdState<J> &S, const FwdConsts<J> &K,
+                                        const char *__restrict__ emis_lane, unsigned rowbytes, uint32_t cw,
                                         float ploop, float pmove, float tEL, float tEM,
-                                        float &totscale, float (&cend)[3], float *__restrict__ xrow)
+                                        float &totscale, float *__restrict__ xrow)
 {
   constexpr int P0 = PH, P1 = (PH + 3) & 3, P2 = (PH + 2) & 3, P3 = (PH + 1) & 3;  // slots of rows i, i-1, i-2, i-3
   float e2[J], e3[J], e4[J], m[J];
-  load_emission_row<J, VEC>(emis + (size_t)c2 * mpad, lane, e2);
-  load_emission_row<J, VEC>(emis + (size_t)c3 * mpad, lane, e3);
-  load_emission_row<J, VEC>(emis + (size_t)c4 * mpad, lane, e4);
+  // cw packs the three emission-row indices of this DP row: c2 | c3 << 9 | c4 << 18
+  load_emission_row<J, VEC>(reinterpret_cast<const float *>(emis_lane + (size_t)(cw & 511u) * rowbytes), e2);
+  load_emission_row<J, VEC>(reinterpret_cast<const float *>(emis_lane + (size_t)((cw >> 9) & 511u) * rowbytes), e3);
+  load_emission_row<J, VEC>(reinterpret_cast<const float *>(emis_lane + (size_t)(cw >> 18) * rowbytes), e4);
 
-  // M(i,k) = V(i) R2 + V(i-1) R3 + V(i-2) R4        (fwdback_fs.c:390-392)
+  // Mz(i,k) = Z(k) M(i,k),  M(i,k) = V(i) R2 + V(i-1) R3 + V(i-2) R4        (fwdback_fs.c:390-392)
+  // E(i)    = sum_k M(i,k) + D(i,k) = sum_k Mz(i,k)                           (:393,456-459)
   float es0 = 0.f, es1 = 0.f;
 #pragma unroll
   for (int j = 0; j < J; ++j) {
-    float t = S.V[P0][j] * e2[j];
-    t = fmaf(S.V[P1][j], e3[j], t);
-    t = fmaf(S.V[P2][j], e4[j], t);
+    float t = S.W[P0][j] * e2[j];
+    t = fmaf(S.W[P1][j], e3[j], t);
+    t = fmaf(S.W[P2][j], e4[j], t);
     m[j] = t;
-    if (j & 1) es1 = fmaf(t, K.z[j], es1); else es0 = fmaf(t, K.z[j], es0);
+    if (j == 0) es0 = t; else if (j == 1) es1 = t; else if (j & 1) es1 += t; else es0 += t;
   }
-  float xE = warp_allsum(es0 + es1);
+  float xE = warp_allsum(J > 1 ? es0 + es1 : es0);
 
-  // D chain: lane-local pass, then warp scan of the lane carries   (:415-453)
-  float dl[J];
-  dl[0] = 0.f;
+  // D chain (:415-453): a(k) = M(k) tMD(k); lane carry-out with zero carry-in, warp scan of carries,
+  // then the lane re-runs the recurrence from its true carry-in.
+  float a[J];
+  float A = 0.f;
 #pragma unroll
-  for (int j = 0; j + 1 < J; ++j) dl[j + 1] = fmaf(dl[j], K.dd[j], m[j] * K.md[j]);
-  float A = fmaf(dl[J - 1], K.dd[J - 1], m[J - 1] * K.md[J - 1]);
+  for (int j = 0; j < J; ++j) { a[j] = m[j] * K.md[j]; A = (j == 0) ? a[0] : fmaf(A, K.dd[j], a[j]); }
 #pragma unroll
   for (int s = 0; s < 5; ++s) {
     float up = __shfl_up_sync(0xffffffffu, A, 1 << s);
     A = fmaf(K.bs[s], up, A);
   }
-  float xin = __shfl_up_sync(0xffffffffu, A, 1);
-  if (lane == 0) xin = 0.f;
+  float d = __shfl_up_sync(0xffffffffu, A, 1);      // D(i, first node of this lane)
+  if (lane == 0) d = 0.f;
 
-  // specials   (:462-465; rows 0..2 hold N at 1.0, :155,279)
-  float xN = (i < 3) ? 1.0f : S.xN[P3] * ploop;
+  // specials   (:462-465; rows 0..2 hold N at 1.0, :155,279; pad rows i<0 hold everything at 0)
+  float xN = (i < 3) ? ((i >= 0) ? 1.0f : 0.0f) : S.xN[P3] * ploop;
   float xJ = fmaf(S.xJ[P3], ploop, xE * tEL);
   float xC = fmaf(S.xC[P3], ploop, xE * tEM);
   float xB = fmaf(xJ, pmove, xN * pmove);
 
-  // outgoing mass O(i)[k] = M tMM + I tIM + D tDM ; V(i+2)[k] = O(i)[k-1] + B(i) tBM[k-1]   (:383-387)
-  // I(i+3)[k] = M(i,k) tMI + I(i,k) tII                                                       (:408-409)
+  // flow into node k+1, per unit of entry odds:  O'(k) = (M tMM + I tIM + D tDM)(k) / s(k+1)
+  // W(i+2)[k+1] = B(i) + O'(k)                                                  (:383-387)
+  // I(i+3)[k]   = M(i,k) tMI + I(i,k) tII                                       (:408-409)
   float o[J];
 #pragma unroll
   for (int j = 0; j < J; ++j) {
-    float d = fmaf(xin, K.pp[j], dl[j]);
-    float t = m[j] * K.mm[j];
-    t = fmaf(S.I[P0][j], K.im[j], t);
-    t = fmaf(d, K.dm[j], t);
-    o[j] = t;
+    float t = fmaf(m[j], K.mm[j], S.I[P0][j]);
+    o[j] = fmaf(d, K.dm[j], t);
+    if (j + 1 < J) d = fmaf(d, K.dd[j], a[j]);
     S.I[P1][j] = fmaf(S.I[P0][j], K.ii[j], m[j] * K.mi[j]);     // slot (i+3)&3 == (i-1)&3
   }
   float oprev = __shfl_up_sync(0xffffffffu, o[J - 1], 1);
   if (lane == 0) oprev = 0.f;
-  S.V[P2][0] = fmaf(xB, K.bm[0], oprev);
+  S.W[P2][0] = xB + oprev;
 #pragma unroll
-  for (int j = 1; j < J; ++j) S.V[P2][j] = fmaf(xB, K.bm[j], o[j - 1]);
+  for (int j = 1; j < J; ++j) S.W[P2][j] = xB + o[j - 1];
 
   float scale = 1.0f;
-  if (xE > 1.0e4f && i <= L) {   // sparse rescaling (:472-496); warp-uniform branch
+  if (xE > 1.0e4f) {             // sparse rescaling (:472-496); warp-uniform branch
     float sf = 1.0f / xE;
     scale = xE;
     xN *= sf; xJ *= sf; xC *= sf; xB *= sf;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
 #pragma unroll
-      for (int j = 0; j < J; ++j) { S.V[r][j] *= sf; S.I[r][j] *= sf; }
+      for (int j = 0; j < J; ++j) { S.W[r][j] *= sf; S.I[r][j] *= sf; }
       S.xN[r] *= sf; S.xJ[r] *= sf; S.xC[r] *= sf;
     }
-    cend[1] *= sf; cend[2] *= sf;
     totscale += logf(xE);
     xE = 1.0f;
   }
   S.xN[P0] = xN; S.xJ[P0] = xJ; S.xC[P0] = xC;
-  if (i == L)     cend[0] = xC;
-  if (i == L - 1) cend[1] = xC;
-  if (i == L - 2) cend[2] = xC;
 
   if constexpr (XMX) {
-    if (lane == 0 && i <= L) {
+    if (lane == 0 && i >= 0) {
       float2 *x2 = reinterpret_cast<float2 *>(xrow + (size_t)i * 6);
       x2[0] = make_float2(xE, xN);
       x2[1] = make_float2(xJ, xB);
@@ -208,29 +211,65 @@ __device__ __forceinline__ void load_fwd_consts(const float *__restrict__ cc, in
 {
 #pragma unroll
   for (int j = 0; j < J; ++j) {
-    K.bm[j] = __ldg(cc + (FC_BM * J + j) * kWarp + lane);
     K.mm[j] = __ldg(cc + (FC_MM * J + j) * kWarp + lane);
-    K.im[j] = __ldg(cc + (FC_IM * J + j) * kWarp + lane);
     K.dm[j] = __ldg(cc + (FC_DM * J + j) * kWarp + lane);
     K.md[j] = __ldg(cc + (FC_MD * J + j) * kWarp + lane);
     K.dd[j] = __ldg(cc + (FC_DD * J + j) * kWarp + lane);
-    K.pp[j] = __ldg(cc + (FC_PP * J + j) * kWarp + lane);
     K.mi[j] = __ldg(cc + (FC_MI * J + j) * kWarp + lane);
     K.ii[j] = __ldg(cc + (FC_II * J + j) * kWarp + lane);
-    K.z[j]  = __ldg(cc + (FC_Z  * J + j) * kWarp + lane);
   }
 #pragma unroll
   for (int s = 0; s < 5; ++s) K.bs[s] = __ldg(cc + FC_COUNT * J * kWarp + (FL_B0 + s) * kWarp + lane);
 }
 
+// One warp per block; kMinBlocks = resident warps per SM the kernel is compiled for (sets the register
+// budget: 65536 / (32 * kMinBlocks)).  Tuned on B200: occupancy beats spill-free slack up to a point.
+#ifndef BATHGPU_WARPS_J6
+#define BATHGPU_WARPS_J6 15
+#endif
+#ifndef BATHGPU_WARPS_J7
+#define BATHGPU_WARPS_J7 13
+#endif
+#ifndef BATHGPU_WARPS_J8
+#define BATHGPU_WARPS_J8 12
+#endif
+#ifndef BATHGPU_WARPS_J5
+#define BATHGPU_WARPS_J5 16
+#endif
+#ifndef BATHGPU_WARPS_J4
+#define BATHGPU_WARPS_J4 18
+#endif
+template <int J> struct FwdTune {
+  static constexpr int kThreads   = 32;
+  static constexpr int kMinBlocks = (J <= 3) ? 20 : (J == 4) ? BATHGPU_WARPS_J4 : (J == 5) ? BATHGPU_WARPS_J5 :
+                                    (J == 6) ? BATHGPU_WARPS_J6 : (J == 7) ? BATHGPU_WARPS_J7 :
+                                    (J == 8) ? BATHGPU_WARPS_J8 : 8;
+};
+
+// Codon words for 32 consecutive padded rows, one per lane: lane l handles padded row r0 + l, i.e.
+// DP row i = r0 + l - pad.  n[p] for p outside 1..L or a degenerate code is the placeholder 338
+// (fwdback_fs.c:176-178,344), which the index clamps turn into the degenerate emission rows (:347-349).
+__device__ __forceinline__ uint32_t codon_word(uint32_t lo, uint32_t hi, int sh, int i, int L)
+{
+  uint32_t bits = __funnelshift_r(lo, hi, sh) & 0xffffu;       // nibbles n[i-3], n[i-2], n[i-1], n[i]
+  int u = (int)(bits & 15u), v = (int)((bits >> 4) & 15u), w = (int)((bits >> 8) & 15u), x = (int)(bits >> 12);
+  u = (u < 4 && i - 3 >= 1 && i - 3 <= L) ? u : 338;
+  v = (v < 4 && i - 2 >= 1 && i - 2 <= L) ? v : 338;
+  w = (w < 4 && i - 1 >= 1 && i - 1 <= L) ? w : 338;
+  x = (x < 4 && i     >= 1 && i     <= L) ? x : 338;
+  return (uint32_t)codon2_fs3(w, x) | ((uint32_t)codon3_fs3(v, w, x) << 9) | ((uint32_t)codon4_fs3(u, v, w, x) << 18);
+}
+
 template <int J, bool XMX>
-__global__ void __launch_bounds__(128) fs3_forward_parser_kernel(FsParserArgs a)
+__global__ void __launch_bounds__(FwdTune<J>::kThreads, FwdTune<J>::kMinBlocks) fs3_forward_parser_kernel(FsParserArgs a)
 {
   constexpr int VEC = VecOf<J>::V;
   const int lane = threadIdx.x & 31;
 
   FwdConsts<J> K;                      // per-lane profile constants -> registers, once per warp
   load_fwd_consts<J>(a.cellc, lane, K);
+  const char    *emis_lane = reinterpret_cast<const char *>(a.emis + lane * VEC);
+  const unsigned rowbytes  = (unsigned)a.mpad * 4u;
 
   for (;;) {
     int w = 0;
@@ -248,38 +287,40 @@ __global__ void __launch_bounds__(128) fs3_forward_parser_kernel(FsParserArgs a)
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
 #pragma unroll
-      for (int j = 0; j < J; ++j) { S.V[r][j] = 0.f; S.I[r][j] = 0.f; }
+      for (int j = 0; j < J; ++j) { S.W[r][j] = 0.f; S.I[r][j] = 0.f; }
       S.xN[r] = 0.f; S.xJ[r] = 0.f; S.xC[r] = 0.f;
     }
     float totscale = 0.f;
-    float cend[3] = { 0.f, 0.f, 0.f };
 
-    // rows 0..4*nq-1 >= L; rows past L run on whatever follows the window and are ignored
-    const int       nq     = (L + 4) >> 2;
-    const long long p_base = wd.start - 1;       // 0-based block index of window position 1
-    int i = 0;
-    int u = 338, v = 338, wn = 338;              // (n[i-3], n[i-2], n[i-1]); 338 = degenerate placeholder (:176)
-    uint32_t quad = fetch_quad(a.dna4, p_base - 1);
+    // padded rows r = 0 .. 4*nq-1 map to DP rows i = r - pad; pad in 0..3 so that the last row is i = L
+    const int nq  = (L + 4) >> 2;                 // ceil((L+1)/4)
+    const int pad = 4 * nq - (L + 1);
+    // nibble index (in the packed block, guard word included) of n[i-3] for this lane's row of chunk 0
+    long long nib = (wd.start - 1) + (long long)(lane - pad - 3) - 1 + 8;
+    uint32_t lo = __ldg(a.dna4 + (nib >> 3)), hi = __ldg(a.dna4 + (nib >> 3) + 1);
+    int i = -pad;
 
+    for (int q0 = 0; q0 < nq; q0 += 8) {
+      const uint32_t cwl = codon_word(lo, hi, (int)(nib & 7) * 4, i + lane, L);
+      nib += 32;
+      if (q0 + 8 < nq) { lo = __ldg(a.dna4 + (nib >> 3)); hi = __ldg(a.dna4 + (nib >> 3) + 1); }   // next chunk, a chunk ahead
+      const int qn = min(8, nq - q0);
+      for (int qq = 0; qq < qn; ++qq) {
 #define BATHGPU_ROW(PH_)                                                                              \
-    {                                                                                                 \
-      int nt = (int)(quad & 15u); quad >>= 4;                                                         \
-      int xn = (i >= 1 && nt < 4) ? nt : 338;                                                         \
-      int c2 = codon2_fs3(wn, xn), c3 = codon3_fs3(v, wn, xn), c4 = codon4_fs3(u, v, wn, xn);         \
-      fwd_row<J, VEC, PH_, XMX>(i, L, lane, S, K, a.emis, a.mpad, c2, c3, c4, ploop, pmove,           \
-                                a.tEL, a.tEM, totscale, cend, xrow);                                  \
-      u = v; v = wn; wn = xn; ++i;                                                                    \
-    }
-    for (int q = 0; q < nq; ++q) {
-      uint32_t next = fetch_quad(a.dna4, p_base + (i + 3));
-      BATHGPU_ROW(0) BATHGPU_ROW(1) BATHGPU_ROW(2) BATHGPU_ROW(3)
-      quad = next;
-    }
+        {                                                                                             \
+          uint32_t cw = __shfl_sync(0xffffffffu, cwl, qq * 4 + PH_);                                  \
+          fwd_row<J, VEC, PH_, XMX>(i, lane, S, K, emis_lane, rowbytes, cw, ploop, pmove,             \
+                                    a.tEL, a.tEM, totscale, xrow);                                    \
+          ++i;                                                                                        \
+        }
+        BATHGPU_ROW(0) BATHGPU_ROW(1) BATHGPU_ROW(2) BATHGPU_ROW(3)
 #undef BATHGPU_ROW
+      }
+    }
 
-    // final score (:513-529): (C(L) + C(L-1) tCL + C(L-2) tCL) tCM
+    // final score (:513-529): (C(L) + C(L-1) tCL + C(L-2) tCL) tCM; row L sits in slot 3
     {
-      float tot = cend[0] + cend[1] * ploop + cend[2] * ploop;
+      float tot = S.xC[3] + S.xC[2] * ploop + S.xC[1] * ploop;
       int   st  = 0;
       float sc;
       if (isnan(tot) || isinf(tot))  { st = 16; sc = tot; }
