@@ -23,6 +23,26 @@ def _sources():
     return out
 
 
+_HOST = os.path.join(_HERE, "host")
+_HOST_SO = os.path.join(_HERE, "libbathhost.so")
+GXX_FLAGS = ["-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-ffp-contract=off", "-fno-fast-math"]
+
+
+def host_library_path():
+    return _HOST_SO
+
+
+def build_host_library(force=False):
+    """libbathhost.so: the host side of the path (model set-up, length models, pipeline logic), g++ only."""
+    srcs = [os.path.join(_HOST, f) for f in sorted(os.listdir(_HOST)) if f.endswith((".cpp", ".h"))]
+    srcs.append(os.path.join(_HERE, "..", "include", "bathhost.h"))
+    if not force and os.path.exists(_HOST_SO) and all(os.path.getmtime(s) <= os.path.getmtime(_HOST_SO) for s in srcs):
+        return _HOST_SO
+    cmd = [os.environ.get("CXX", "g++")] + GXX_FLAGS + ["-o", _HOST_SO] + [s for s in srcs if s.endswith(".cpp")]
+    subprocess.check_call(cmd)
+    return _HOST_SO
+
+
 def build_library(force=False, verbose=False):
     srcs = _sources()
     if not force and os.path.exists(_SO) and all(os.path.getmtime(s) <= os.path.getmtime(_SO) for s in srcs):
@@ -36,4 +56,5 @@ def build_library(force=False, verbose=False):
 
 if __name__ == "__main__":
     import sys
+    print(build_host_library(force="--force" in sys.argv))
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

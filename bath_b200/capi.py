@@ -13,7 +13,8 @@ EXPORTS = [
     "bathgpu_create", "bathgpu_destroy", "bathgpu_last_error", "bathgpu_device_info",
     "bathgpu_load_fs_profile", "bathgpu_upload_block", "bathgpu_fs_fwd_windows",
     "bathgpu_stage_windows", "bathgpu_fs_fwd_staged", "bathgpu_fetch_scores",
-    "bathgpu_fs_bck_decode", "bathgpu_fs_domains", "bathgpu_last_stage_timing",
+    "bathgpu_fs_bck_decode", "bathgpu_fs_domains", "bathgpu_last_stage_timing", "bathgpu_measure_fp32_peak",
+    "bathgpu_host_alloc", "bathgpu_host_free",
 ]
 
 
@@ -75,8 +76,38 @@ def load():
     L.bathgpu_fs_domains.argtypes = [vp, vp, C.c_int, fp, vp, vp, C.c_int64]
     L.bathgpu_last_stage_timing.restype = C.c_int
     L.bathgpu_last_stage_timing.argtypes = [vp, fp, C.POINTER(C.c_int)]
+    L.bathgpu_measure_fp32_peak.restype = C.c_int
+    L.bathgpu_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.bathgpu_host_alloc.restype = vp
+    L.bathgpu_host_alloc.argtypes = [C.c_size_t]
+    L.bathgpu_host_free.restype = None
+    L.bathgpu_host_free.argtypes = [vp]
     _lib = L
     return L
+
+
+def pinned_array(shape, dtype):
+    """numpy array over page-locked memory from bathgpu_host_alloc (kept alive by the returned array's base)."""
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    L = load()
+    p = L.bathgpu_host_alloc(max(n, 1))
+    if not p:
+        raise MemoryError(f"bathgpu_host_alloc({n}) failed")
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                L.bathgpu_host_free(self.ptr)
+            except Exception:
+                pass
+
+    buf = (C.c_uint8 * max(n, 1)).from_address(p)
+    buf._owner = _Owner(p)
+    return np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
 
 
 def _f(a):
@@ -152,6 +183,11 @@ class Context:
         self._check(self.lib.bathgpu_fs_fwd_windows(self.h, wins.ctypes.data, n, _f(xf), _f(sc), _i(st)))
         return sc, st
 
+    def fs_fwd_windows_into(self, wins, xfE, sc, st):
+        """Same call writing into caller-owned (e.g. pinned) score/status arrays."""
+        xf = np.asarray(xfE, np.float32)
+        self._check(self.lib.bathgpu_fs_fwd_windows(self.h, wins.ctypes.data, len(wins), _f(xf), _f(sc), _i(st)))
+
     def stage_windows(self, wins):
         self._check(self.lib.bathgpu_stage_windows(self.h, wins.ctypes.data, len(wins)))
 
@@ -169,6 +205,11 @@ class Context:
         ms, nl = C.c_float(), C.c_int()
         self._check(self.lib.bathgpu_last_stage_timing(self.h, C.byref(ms), C.byref(nl)))
         return ms.value, nl.value
+
+    def measure_fp32_peak(self):
+        tf, mhz = C.c_double(), C.c_double()
+        self._check(self.lib.bathgpu_measure_fp32_peak(self.h, C.byref(tf), C.byref(mhz)))
+        return tf.value, mhz.value
 
     def fs_bck_decode(self, wins, xfE, xf5_loop):
         n = len(wins)

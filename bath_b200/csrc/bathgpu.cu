@@ -12,6 +12,7 @@
 
 #include "../../include/bathgpu.h"
 #include "fs_parser.cuh"
+#include "microbench.cuh"
 
 using namespace bathgpu;
 
@@ -126,6 +127,39 @@ extern "C" int bathgpu_last_stage_timing(const bathgpu_ctx *ctx, float *ms, int 
   if (!ctx) return BATHGPU_EINVAL;
   if (ms) *ms = ctx->last_ms;
   if (launches) *launches = ctx->last_launches;
+  return BATHGPU_OK;
+}
+
+extern "C" void *bathgpu_host_alloc(size_t bytes)
+{
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+
+extern "C" void bathgpu_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" int bathgpu_measure_fp32_peak(bathgpu_ctx *ctx, double *tflops, double *sm_mhz_effective)
+{
+  if (!ctx || !tflops) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_measure_fp32_peak");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (ctx->scratch.reserve(1 << 20) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
+  const int blocks = ctx->prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  const double flop = (double)blocks * threads * (double)iters * 8.0 * 16.0 * 2.0;
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {     // first reps warm the clocks up
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    fp32_fma_probe_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->scratch.as<float>(), iters, 0.999f, 1e-3f);
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (rep >= 2 && ms < best) best = ms;
+  }
+  *tflops = flop / (best * 1e-3) / 1e12;
+  if (sm_mhz_effective)   // clock at which 128 lanes x 2 flop x SMs would give this rate
+    *sm_mhz_effective = *tflops * 1e12 / (2.0 * 128.0 * ctx->prop.multiProcessorCount) / 1e6;
   return BATHGPU_OK;
 }
 

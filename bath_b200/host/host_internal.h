@@ -1,0 +1,59 @@
+// host_internal.h -- types shared by the host-side sources of libbathhost.so.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace bathhost {
+
+constexpr int kK  = 20;   // canonical amino acids
+constexpr int kKp = 29;   // all amino codes: 20 + gap + BJZOUX + '*' + '~'
+
+// core-model transition order (src/hmmer.h:125-131) and profile transition order (:221-231)
+enum { HT_MM = 0, HT_MI, HT_MD, HT_IM, HT_II, HT_DM, HT_DD };
+enum { PT_MM = 0, PT_IM, PT_DM, PT_BM, PT_MD, PT_DD, PT_MI, PT_II };
+enum { PX_E = 0, PX_N, PX_J, PX_C };
+enum { PX_LOOP = 0, PX_MOVE = 1 };
+enum { EV_MMU = 0, EV_MLAMBDA, EV_VMU, EV_VLAMBDA, EV_FTAU, EV_FLAMBDA, EV_FTAUFS3, EV_FTAUFS5 };
+
+struct CoreModel {                 // P7_HMM as read from a BATH3/f file (probabilities)
+  int   M = 0, max_length = -1, ct = -1;
+  float fsprob = -1.0f;
+  float evparam[8] = { -99999.f, -99999.f, -99999.f, -99999.f, -99999.f, -99999.f, -99999.f, -99999.f };
+  bool  has_fs3 = false, has_fs5 = false, has_compo = false;
+  float compo[kK] = { 0 };
+  std::string name, acc;
+  std::vector<float> t, mat, ins;  // [(M+1)][7], [(M+1)][20], [(M+1)][20]
+  std::vector<char>  consensus;    // [M+2], 1..M
+};
+
+struct NullModel {                 // P7_BG
+  float f[kK];
+  float p1, omega;
+  NullModel();
+};
+
+struct FsProfile {                 // P7_FS_PROFILE (log-odds)
+  int   M = 0, codon_lengths = 0, maxcodons = 0;
+  float nj = 1.0f;
+  float xsc[4][2] = { { 0 } };
+  std::vector<float>   rsc;        // [(maxcodons+Kp)][M+1]
+  std::vector<float>   tsc;        // [M][8]
+  std::vector<uint8_t> codons, indel_pos;   // [(M+1)][maxcodons]
+  void configure(const CoreModel &h, const NullModel &bg, const uint8_t gcode[64], int codon_lengths);
+};
+
+struct FsOddsProfile {             // P7_FS_OPROFILE without the SIMD striping
+  int   M = 0, codon_lengths = 0, nrows = 0;
+  float xfE_move = 0.5f, xfE_loop = 0.5f;
+  std::vector<float> rfv;          // [nrows][M+1]
+  std::vector<float> tfv;          // [8][M+1]
+  void convert(const FsProfile &gm);
+};
+
+int   amino_code(char c);
+int   dna_code(char c);
+bool  genetic_code(int ct, uint8_t out[64]);
+float simd_expf(float x);
+
+}  // namespace bathhost

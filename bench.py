@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- frameshift Forward throughput (GCUPS) of the translated-search hot path on B200.
+
+Workload (BASELINE.json configs[2]): a Pfam-sized profile (tutorial tRNA-synthetases.bhmm, model 1,
+M=192) against a 100 Mbp synthetic genome (iid ACGT, a frameshifted back-translated homolog planted
+every 50 kbp, seed 42 + rank), tiled into 1200-nt DNA windows; one step = the frameshift Forward parser
+(p7_ForwardParser_Frameshift_3Codons semantics) over every window of the genome.  Cells = sum Lw * M, the
+reference's own Mc/s definition (src/impl_sse/fwdback_fs.c:3115).
+
+  value  : device-timed (CUDA events on the launching stream), genome and descriptors resident in HBM
+  e2e    : same step through the C ABI with HOST buffers: H2D of the block + window descriptors, 4-bit
+           packing, Forward, D2H of scores/status -- wall clock around the calls
+  roofline: FP32 pipe (the recursion is FMA work): 20 FLOP/cell vs an FFMA probe measured in
+           the same process; an HBM line is given too to show the kernel is nowhere near memory bound
+  cpu_baseline / --impl reference: the restated CPU oracle (the reference itself needs Easel, which is not
+           vendored, so it cannot be compiled) on all host cores, on a bounded sample of the same windows
+
+N > 1: one process per GPU (torchrun), each rank owns its own 100 Mbp shard (weak scaling, no collective
+on the DP path); the only communication is the barrier and the max-over-ranks of the timings.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HMM_FILE = os.path.join(ROOT, "tests", "golden", "tRNA-synthetases.bhmm")
+HMM_INDEX = 1
+FLOP_PER_CELL = 20.0          # 3-codon Forward parser, mul and add counted separately
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mbp", type=float, default=100.0, help="genome size per GPU, Mbp")
+    ap.add_argument("--window", type=int, default=1200, help="DNA window length Lw")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+def make_workload(rank, mbp, window):
+    from bath_b200 import hostapi, synth
+    model = hostapi.QueryModel(HMM_FILE, HMM_INDEX)
+    n = int(mbp * 1e6)
+    rng = np.random.default_rng(42 + rank)
+    dsq, plants = synth.planted_genome(rng, n, model.mat(), every=50000, fs_rate=model.fsprob)
+    starts, lengths = synth.tile_windows(n, window)
+    return model, dsq, starts, lengths, len(plants)
+
+
+def cpu_sample(model_M, dsq, starts, lengths, seconds, nthreads):
+    """Times the CPU oracle (native build, all host threads) on a bounded prefix of the windows.
+    The only place besides tests/ and smoke() where oracle/ is executed -- as the thing compared against."""
+    from oracle import pyoracle as po
+    po.lib(native=True)
+    omodel = po.Model(HMM_FILE, HMM_INDEX)
+    assert omodel.M == model_M
+    probe = min(len(starts), 64 * nthreads)
+    t0 = time.perf_counter()
+    po.batch_forward_parser(omodel, dsq, starts[:probe], lengths[:probe], nthreads)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    n = int(min(len(starts), max(probe, probe * seconds / dt)))
+    t0 = time.perf_counter()
+    sc, st = po.batch_forward_parser(omodel, dsq, starts[:n], lengths[:n], nthreads)
+    dt = time.perf_counter() - t0
+    cells = float(lengths[:n].astype(np.int64).sum()) * model_M
+    return cells / dt / 1e9, n, dt, sc
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  The reference
+    binary cannot be built (Easel not vendored), so this is the restated oracle: kind = "port"."""
+    if rank != 0:
+        return
+    model, dsq, starts, lengths, nplants = make_workload(0, args.mbp, args.window)
+    ncpu = os.cpu_count() or 1
+    per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    from oracle import pyoracle as po
+    po.lib(native=True)
+    omodel = po.Model(HMM_FILE, HMM_INDEX)
+    probe = min(len(starts), 64 * ncpu)
+    t0 = time.perf_counter()
+    po.batch_forward_parser(omodel, dsq, starts[:probe], lengths[:probe], ncpu)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    n = int(min(len(starts), max(probe, probe * per_step / dt)))
+    for _ in range(args.warmup):
+        po.batch_forward_parser(omodel, dsq, starts[:n], lengths[:n], ncpu)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        po.batch_forward_parser(omodel, dsq, starts[:n], lengths[:n], ncpu)
+    dt = time.perf_counter() - t0
+    cells = float(lengths[:n].astype(np.int64).sum()) * model.M
+    value = cells * args.steps / dt / 1e9
+    sample = f"{n} of {len(starts)} windows of {args.window} nt per step ({cells / 1e9:.3f} Gcells), {ncpu} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "frameshift Forward GCUPS", "value": value, "unit": "GCUPS",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, model.M, len(starts)),
+        "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": ncpu, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "restated CPU oracle (scalar C, -O3 -march=native, pthreads over windows); the reference binary needs Easel, "
+                "which is not vendored, so it cannot be compiled here",
+    }))
+
+
+def workload_config(args, M, nwin):
+    return {"workload": f"tRNA-synthetases.bhmm[{HMM_INDEX}] (M={M}) frameshift Forward parser vs {args.mbp:g} Mbp synthetic genome "
+                        f"per GPU, planted frameshifted homologs every 50 kbp, tiled into {args.window}-nt windows",
+            "profile_M": M, "genome_mbp_per_gpu": args.mbp, "window_nt": args.window, "windows_per_gpu": nwin,
+            "l2": "flushed between timed steps (512 MiB device write, untimed)", "sharding": "genome windows per GPU, profile replicated"}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from bath_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    model, dsq_np, starts, lengths, nplants = make_workload(rank, args.mbp, args.window)
+    M, nwin = model.M, len(starts)
+    cells_local = float(lengths.astype(np.int64).sum()) * M
+
+    ctx = capi.Context(local_rank)
+    ctx.load_fs_profile(3, model.rfv(3), model.tfv(3))
+    fp32_peak, eff_mhz = ctx.measure_fp32_peak()
+
+    # host buffers of the e2e leg: pinned, filled once (the copies are what is timed, not the generation)
+    dsq = capi.pinned_array(dsq_np.shape, np.uint8)
+    dsq[:] = dsq_np
+    wins = capi.pinned_array((nwin,), capi.window_dtype)
+    wins[:] = capi.Context.make_windows(starts, lengths, nj=1.0)
+    xfE = (0.5, 0.5)
+
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+
+    # ---- device-resident timing -------------------------------------------------------------
+    ctx.upload_block(dsq)
+    ctx.stage_windows(wins)
+    for _ in range(max(args.warmup, 3)):
+        ctx.fs_fwd_staged(xfE)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    dev_ms, launches = 0.0, 0
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        ctx.fs_fwd_staged(xfE)
+        ms, nl = ctx.last_stage_timing()
+        dev_ms += ms
+        launches += nl
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    dev_ms = max_over_ranks(dev_ms)
+    sc_dev, st_dev = ctx.fetch_scores(nwin)
+
+    # ---- end to end through the C ABI with host buffers -------------------------------------
+    sc = capi.pinned_array((nwin,), np.float32)
+    st = capi.pinned_array((nwin,), np.int32)
+    for _ in range(2):
+        ctx.upload_block(dsq)
+        ctx.fs_fwd_windows_into(wins, xfE, sc, st)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.upload_block(dsq)
+        ctx.fs_fwd_windows_into(wins, xfE, sc, st)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
+    if not np.array_equal(sc, sc_dev) or not np.array_equal(st, st_dev):
+        raise SystemExit("e2e and device-resident runs disagree")
+    n_ok = int((st == 0).sum())
+
+    cells_total = sum_over_ranks(cells_local)
+    value = cells_total * args.steps / (dev_ms * 1e-3) / 1e9
+    e2e_value = cells_total * args.steps / e2e_s / 1e9
+    h2d = int(dsq.nbytes + wins.nbytes)
+    d2h = int(sc.nbytes + st.nbytes)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    per_gpu_cells_s = cells_local * args.steps / (dev_ms * 1e-3)
+    achieved_tf = FLOP_PER_CELL * per_gpu_cells_s / 1e12
+    alg_bytes = float(lengths.astype(np.int64).sum()) / 2 + nwin * (24 + 8)      # packed DNA in, descriptors in, score+status out
+    out = {
+        "metric": "frameshift Forward GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, M, nwin),
+        "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s / args.steps * 1e3},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
+                     "frac": achieved_tf / fp32_peak, "traffic": None,
+                     "kernel": "fs3_forward_parser_kernel", "flop_per_cell": FLOP_PER_CELL,
+                     "peak_source": f"FFMA probe in this process ({eff_mhz:.0f} MHz effective x 148 SM x 128 lanes x 2)",
+                     "hbm": {"achieved": alg_bytes * args.steps / (dev_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": alg_bytes * args.steps / (dev_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                             "algorithmic_bytes_per_step": alg_bytes}},
+        "checks": {"windows": nwin, "status_ok": n_ok, "planted_homologs": nplants, "max_score_nats": float(np.max(sc)),
+                   "wall_ms_timed_loop_incl_flush": wall_ms},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        ncpu = os.cpu_count() or 1
+        v, n, dt, osc = cpu_sample(M, dsq_np, starts, lengths, args.cpu_seconds, ncpu)
+        out["cpu_baseline"] = {"value": v, "unit": "GCUPS", "cores": ncpu, "kind": "port",
+                               "sample": f"first {n} of {nwin} windows ({dt:.1f} s, {ncpu} threads, scalar C oracle -O3 -march=native)"}
+        out["checks"]["max_abs_diff_vs_oracle_nats"] = float(np.max(np.abs(osc - sc[:n])))
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -93,6 +93,11 @@ void        bathgpu_destroy(bathgpu_ctx *ctx);
 const char *bathgpu_last_error(const bathgpu_ctx *ctx);
 int         bathgpu_device_info(const bathgpu_ctx *ctx, int *sm_count, int *clock_khz, size_t *total_mem);
 
+/* Page-locked host buffers for blocks, descriptors and results (so the copies inside the stage calls run at
+ * full PCIe/C2C rate).  Any host pointer is accepted by the stage calls; pinned ones are just faster. */
+void       *bathgpu_host_alloc(size_t bytes);
+void        bathgpu_host_free(void *p);
+
 /* ---- profile images ---------------------------------------------------- */
 /* which = 3 or 5 codon lengths.  rfv: [nrows][M+1] emission odds ratios, row c as
  * P7_FS_OPROFILE->rfv[c] un-striped, column 0 unused; tfv: [8][M+1] transition odds,
@@ -134,6 +139,10 @@ int bathgpu_fs_domains(bathgpu_ctx *ctx, const bathgpu_envelope *envs, int n, co
 /* Device time (ms) of the kernels launched by the most recent stage call, measured with
  * CUDA events on the context's stream, and how many kernels that call launched. */
 int bathgpu_last_stage_timing(const bathgpu_ctx *ctx, float *ms, int *launches);
+
+/* FP32 FMA throughput of the device (TFLOP/s, best of several launches of a register-only FFMA kernel):
+ * the roofline denominator for the frameshift Forward/Backward kernels, which are FP32-pipe bound. */
+int bathgpu_measure_fp32_peak(bathgpu_ctx *ctx, double *tflops, double *sm_mhz_effective);
 
 #ifdef __cplusplus
 }

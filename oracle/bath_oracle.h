@@ -251,6 +251,10 @@ int bo_OATrace_Frameshift(const BO_FS_OPROFILE *om, const BO_MX *pp, const BO_MX
 /* ===== fs_null2.c (impl_sse/null2_fs.c) ===== */
 int bo_Null2_fs_ByExpectation(const BO_FS_OPROFILE *om, BO_MX *pp, float *null2 /* [Kp] */);
 
+/* ===== batch.c (worker-thread pool over windows; src/bathsearch.c:814-844,1224) ===== */
+int bo_batch_ForwardParser_3Codons(const uint8_t *dsq, const int64_t *start, const int32_t *L, int n,
+                                   const BO_FS_OPROFILE *om, int nthreads, float *sc, int32_t *status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,11 +75,17 @@ def build(force=False):
     return so
 
 
-def lib():
+def build_native():
+    """Host-tuned build (-O3 -march=native) for the CPU-baseline legs of bench.py; built on the box that runs it."""
+    subprocess.check_call(["make", "-s", "-B", "-C", _HERE, "native"])   # -B: never trust a copy built on another host
+    return os.path.join(_HERE, "liboracle_native.so")
+
+
+def lib(native=False):
     global _LIB
     if _LIB is not None:
         return _LIB
-    L = C.CDLL(build())
+    L = C.CDLL(build_native() if native else build())
     P = C.POINTER
     u8p, fp = P(C.c_uint8), P(C.c_float)
     sig = {
@@ -117,6 +123,8 @@ def lib():
         "bo_OptimalAccuracy_Frameshift": (C.c_int, [P(FS_OPROFILE), P(MX), P(MX), fp]),
         "bo_OATrace_Frameshift": (C.c_int, [P(FS_OPROFILE), P(MX), P(MX), P(TRACE)]),
         "bo_Null2_fs_ByExpectation": (C.c_int, [P(FS_OPROFILE), P(MX), fp]),
+        "bo_batch_ForwardParser_3Codons": (C.c_int, [u8p, P(C.c_int64), P(C.c_int32), C.c_int, P(FS_OPROFILE),
+                                                     C.c_int, fp, P(C.c_int32)]),
         "bo_FLogsum": (C.c_float, [C.c_float, C.c_float]),
         "bo_FLogsumInit": (None, []),
         "bo_cephes_expf": (C.c_float, [C.c_float]),
@@ -210,6 +218,21 @@ class Model:
     def xf(self, which=3):
         om = (self.om_fs3 if which == 3 else self.om_fs5).contents
         return np.array([[om.xf[s][t] for t in range(2)] for s in range(4)], dtype=np.float32)
+
+
+def batch_forward_parser(model, dsq, starts, lengths, nthreads=1):
+    """Forward parser (3 codon lengths) over windows dsq[start .. start+L-1] with a thread pool."""
+    n = len(starts)
+    st64 = np.ascontiguousarray(starts, np.int64)
+    l32 = np.ascontiguousarray(lengths, np.int32)
+    sc = np.empty(n, np.float32)
+    status = np.empty(n, np.int32)
+    rc = lib().bo_batch_ForwardParser_3Codons(u8ptr(dsq), st64.ctypes.data_as(C.POINTER(C.c_int64)),
+                                              l32.ctypes.data_as(C.POINTER(C.c_int32)), n, model.om_fs3,
+                                              int(nthreads), fptr(sc), status.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc != OK:
+        raise RuntimeError(f"bo_batch_ForwardParser_3Codons: status {rc}")
+    return sc, status
 
 
 def mx_xmx(mx):

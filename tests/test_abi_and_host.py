@@ -1,0 +1,109 @@
+"""CPU-side checks (no GPU): the C-ABI libraries load and export every symbol their headers declare, the
+host-side model set-up is bit-identical to the oracle's, and the synthetic-workload generators are seeded."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import common
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions(header, prefix):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(" + prefix + r"\w+)\s*\(", text)))
+
+
+def test_libbathgpu_exports_every_declared_symbol():
+    from bath_b200 import build, capi
+    build.build_library()
+    lib = C.CDLL(build.library_path())
+    names = declared_functions("bathgpu.h", "bathgpu_")
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/bathgpu.h but not exported"
+    assert sorted(capi.EXPORTS) == names, "capi.EXPORTS must list exactly the header's functions"
+
+
+def test_libbathhost_exports_every_declared_symbol():
+    from bath_b200 import build, hostapi
+    build.build_host_library()
+    lib = C.CDLL(build.host_library_path())
+    names = declared_functions("bathhost.h", "bathhost_")
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/bathhost.h but not exported"
+    assert sorted(hostapi.EXPORTS) == names
+
+
+def test_no_device_is_an_error_not_a_fallback():
+    """Without a CUDA device the product refuses to run (BATHGPU_ENODEVICE); it never computes on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from bath_b200 import capi
+    with pytest.raises(capi.BathGpuError) as e:
+        capi.Context(0)
+    assert e.value.code == capi.ENODEVICE
+
+
+@pytest.mark.parametrize("hmmfile,index", [("AMP_N.bhmm", 0), ("2OG-FeII_Oxy_3.bhmm", 0), ("PTH2.bhmm", 0),
+                                           ("tRNA-synthetases.bhmm", 0), ("tRNA-synthetases.bhmm", 1),
+                                           ("tRNA-synthetases.bhmm", 2), ("PTHR37536.bhmm", 0)])
+def test_host_model_setup_is_bit_identical_to_oracle(oracle, hmmfile, index):
+    from bath_b200 import hostapi
+    o = oracle.Model(common.golden(hmmfile), index)
+    h = hostapi.QueryModel(common.golden(hmmfile), index)
+    assert h.M == o.M and h.max_length == o.max_length
+    assert h.evparam == o.evparam
+    for which in (3, 5):
+        assert np.array_equal(h.rfv(which).view(np.uint32), o.rfv(which).view(np.uint32))
+        assert np.array_equal(h.tfv(which).view(np.uint32), o.tfv(which).view(np.uint32))
+        gm = (o.gm_fs3 if which == 3 else o.gm_fs5).contents
+        mc = gm.maxcodons
+        oc = np.ctypeslib.as_array(gm.codons, shape=((o.M + 1) * (mc + 1),))[: (o.M + 1) * mc].reshape(o.M + 1, mc)
+        oi = np.ctypeslib.as_array(gm.indel_pos, shape=((o.M + 1) * (mc + 1),))[: (o.M + 1) * mc].reshape(o.M + 1, mc)
+        assert np.array_equal(h.codons(which), oc)
+        assert np.array_equal(h.indel_pos(which), oi)
+    assert np.array_equal(h.mat(), common.hmm_mat(o))
+
+
+def test_model_file_errors():
+    from bath_b200 import hostapi
+    with pytest.raises(IOError):
+        hostapi.QueryModel(common.golden("no-such-file.bhmm"))
+    with pytest.raises(IOError):
+        hostapi.QueryModel(common.golden("AMP_N.bhmm"), 1)       # single-model file: index 1 is EOF
+    with pytest.raises(IOError):
+        hostapi.QueryModel(common.golden("target-AMP_N.fa"))     # not a profile file
+    assert hostapi.load().bathhost_model_count(os.fsencode(common.golden("tRNA-synthetases.bhmm"))) == 3
+
+
+def test_length_model_matches_reference_formula():
+    """pmove = (2 + nj) / (L + 2 + nj) in float (src/impl_sse/p7_fs_oprofile.c:636-651)"""
+    from bath_b200 import capi, hostapi
+    for L in (1, 20, 133, 400, 100000):
+        for nj in (0.0, 1.0):
+            pm, pl = hostapi.length_model(L, nj)
+            want = np.float32(np.float32(2.0) + np.float32(nj)) / (np.float32(L) + np.float32(2.0) + np.float32(nj))
+            assert pm == want and pl == np.float32(1.0) - want
+    w = capi.Context.make_windows([1, 5], [399, 1203], nj=1.0)
+    assert w["pmove"][0] == hostapi.length_model(133, 1.0)[0]
+    assert w["ploop"][1] == hostapi.length_model(401, 1.0)[1]
+
+
+def test_synthetic_genome_is_seeded_and_planted():
+    from bath_b200 import hostapi, synth
+    m = hostapi.QueryModel(common.golden("AMP_N.bhmm"))
+    a, pa = synth.planted_genome(np.random.default_rng(42), 200000, m.mat(), every=50000)
+    b, pb = synth.planted_genome(np.random.default_rng(42), 200000, m.mat(), every=50000)
+    c, _ = synth.planted_genome(np.random.default_rng(43), 200000, m.mat(), every=50000)
+    assert np.array_equal(a, b) and pa == pb and not np.array_equal(a, c)
+    assert a[0] == 255 and a[-1] == 255 and a[1:-1].max() <= 3 and len(pa) == 4
+    s, l = synth.tile_windows(200000, 1200)
+    assert s[0] == 1 and s[-1] + l[-1] - 1 == 200000 and np.all(l == 1200)
+    s, l = synth.tile_windows(500, 1200)
+    assert list(s) == [1] and list(l) == [500]
