@@ -14,7 +14,7 @@ EXPORTS = [
     "bathgpu_load_fs_profile", "bathgpu_upload_block", "bathgpu_fs_fwd_windows",
     "bathgpu_stage_windows", "bathgpu_fs_fwd_staged", "bathgpu_fetch_scores",
     "bathgpu_fs_bck_decode", "bathgpu_fs_domains", "bathgpu_last_stage_timing", "bathgpu_measure_fp32_peak",
-    "bathgpu_host_alloc", "bathgpu_host_free",
+    "bathgpu_host_alloc", "bathgpu_host_free", "bathgpu_fs_fetch_xrows",
 ]
 
 
@@ -78,6 +78,8 @@ def load():
     L.bathgpu_last_stage_timing.argtypes = [vp, fp, C.POINTER(C.c_int)]
     L.bathgpu_measure_fp32_peak.restype = C.c_int
     L.bathgpu_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.bathgpu_fs_fetch_xrows.restype = C.c_int
+    L.bathgpu_fs_fetch_xrows.argtypes = [vp, C.c_int, fp, C.c_int64]
     L.bathgpu_host_alloc.restype = vp
     L.bathgpu_host_alloc.argtypes = [C.c_size_t]
     L.bathgpu_host_free.restype = None
@@ -226,6 +228,15 @@ class Context:
                                                    _f(mocc), _f(btot), _f(etot), _f(fsc), _f(bsc), _i(st)))
         split = lambda a: [a[off[w]: off[w] + Ls[w] + 1] for w in range(n)]
         return split(mocc), split(btot), split(etot), fsc, bsc, st
+
+    def fs_fetch_xrows(self, which, wins):
+        """X rows of the Forward (0) / Backward (1) parser for the windows of the last fs_bck_decode call -> list of [L+1][6]"""
+        Ls = wins["L"].astype(np.int64)
+        tot = int((Ls + 1).sum())
+        out = np.empty((tot, 6), np.float32)
+        self._check(self.lib.bathgpu_fs_fetch_xrows(self.h, which, _f(out), tot))
+        off = np.concatenate([[0], np.cumsum(Ls + 1)])
+        return [out[off[w]: off[w + 1]] for w in range(len(wins))]
 
     def fs_domains(self, envs, xfE5=(1.0, 0.0), max_steps=None):
         n = len(envs)

@@ -12,6 +12,7 @@
 
 #include "../../include/bathgpu.h"
 #include "fs_parser.cuh"
+#include "fs_backward.cuh"
 #include "microbench.cuh"
 
 using namespace bathgpu;
@@ -56,6 +57,8 @@ struct bathgpu_ctx {
   DevBuf        wins, fwdsc, status, counter;
   int           nstaged = 0;
   DevBuf        scratch;
+  DevBuf        fxmx, bxmx, lsf, lsb, xoff, dmocc, dbtot, detot, bcksc;
+  int64_t       xrows = 0;          // rows held in fxmx/bxmx by the last bck_decode chunk
   float         last_ms = 0.f;
   int           last_launches = 0;
 };
@@ -106,6 +109,7 @@ extern "C" void bathgpu_destroy(bathgpu_ctx *ctx)
   for (FsProfileImage *im : { &ctx->fs3, &ctx->fs5 }) { im->emis.release(); im->cellc.release(); im->cellb.release(); }
   ctx->dna_bytes.release(); ctx->dna4.release(); ctx->wins.release(); ctx->fwdsc.release();
   ctx->status.release(); ctx->counter.release(); ctx->scratch.release();
+  for (DevBuf *b : { &ctx->fxmx, &ctx->bxmx, &ctx->lsf, &ctx->lsb, &ctx->xoff, &ctx->dmocc, &ctx->dbtot, &ctx->detot, &ctx->bcksc }) b->release();
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -252,6 +256,44 @@ extern "C" int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int n
     }
     if (im.cellc.reserve(cc.size() * sizeof(float)) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
     CUDA_TRY(ctx, cudaMemcpyAsync(im.cellc.p, cc.data(), cc.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+
+  // ---- backward constants (fs_backward.cuh)
+  {
+    std::vector<float> cc((size_t)(BC_COUNT * J + BL_COUNT) * 32, 0.0f);
+    auto C = [&](int which_c, int j, int lane) -> float & { return cc[(size_t)(which_c * J + j) * 32 + lane]; };
+    std::vector<double> bfull(32, 1.0);
+    for (int lane = 0; lane < 32; ++lane) {
+      double pp = 1.0;
+      for (int j = 0; j < J; ++j) {
+        int k = lane * J + j + 1;
+        if (k <= M) {
+          double sn = sK[k + 1];      // entry odds of node k+1 (1.0 at k = M, where every transition out is 0)
+          C(BC_VMM, j, lane) = (float)(T(tMM, k) / (sn * zK[k]));
+          C(BC_VIM, j, lane) = (float)(T(tIM, k) / sn);
+          C(BC_VDM, j, lane) = (float)(T(tDM, k) / sn);
+          C(BC_DD,  j, lane) = (float)T(tDD, k);
+          C(BC_MD,  j, lane) = (float)(T(tMD, k) / zK[k]);
+          C(BC_MI,  j, lane) = (float)(T(tMI, k) / zK[k]);
+          C(BC_II,  j, lane) = (float)T(tII, k);
+        }
+        pp *= T(tDD, k);
+      }
+      bfull[lane] = pp;
+    }
+    std::vector<double> b(bfull);
+    for (int s = 0; s < 5; ++s) {
+      int d = 1 << s;
+      std::vector<double> nb(b);
+      for (int lane = 0; lane < 32; ++lane) {
+        cc[(size_t)(BC_COUNT * J + BL_B0 + s) * 32 + lane] = (lane + d <= 31) ? (float)b[lane] : 0.0f;
+        if (lane + d <= 31) nb[lane] = b[lane] * b[lane + d];
+      }
+      b.swap(nb);
+    }
+    if (im.cellb.reserve(cc.size() * sizeof(float)) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
+    CUDA_TRY(ctx, cudaMemcpyAsync(im.cellb.p, cc.data(), cc.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   }
 
@@ -413,11 +455,131 @@ extern "C" int bathgpu_fs_fwd_windows(bathgpu_ctx *ctx, const bathgpu_window *wi
 }
 
 // ---------------------------------------------------------------------------------------------
+template <int J>
+static cudaError_t launch_bck(const FsBackwardArgs &a, int grid, cudaStream_t s)
+{
+  fs3_backward_parser_kernel<J><<<grid, BckTune<J>::kThreads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+static cudaError_t dispatch_bck(int J, const FsBackwardArgs &a, int sms, cudaStream_t s)
+{
+#define BCK(J_) case J_: { int nb = 0;                                                                          \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fs3_backward_parser_kernel<J_>, BckTune<J_>::kThreads, 0); \
+    return launch_bck<J_>(a, std::min(a.nwin, sms * std::max(nb, 1)), s); }
+  switch (J) { BCK(1) BCK(2) BCK(3) BCK(4) BCK(5) BCK(6) BCK(7) BCK(8) BCK(10) BCK(12) default: return cudaErrorInvalidValue; }
+#undef BCK
+}
+
+// a10 + a11 for one chunk of windows whose descriptors are already in ctx->wins
+static int bck_decode_chunk(bathgpu_ctx *ctx, const bathgpu_window *wins, int n, const float xfE[2], const float xf5_loop[3],
+                            const int64_t *out_offset, float *mocc, float *btot, float *etot,
+                            float *fwdsc, float *bcksc, int32_t *status)
+{
+  const FsProfileImage &im = ctx->fs3;
+  std::vector<long long> xoff(n + 1, 0);
+  for (int w = 0; w < n; ++w) xoff[w + 1] = xoff[w] + wins[w].L + 1;
+  const size_t rows = (size_t)xoff[n];
+
+  if (ctx->wins.reserve((size_t)n * sizeof(WindowDesc)) != BATHGPU_OK || ctx->fwdsc.reserve((size_t)n * 4) != BATHGPU_OK ||
+      ctx->bcksc.reserve((size_t)n * 4) != BATHGPU_OK || ctx->status.reserve((size_t)n * 4) != BATHGPU_OK ||
+      ctx->counter.reserve(64) != BATHGPU_OK || ctx->xoff.reserve((size_t)(n + 1) * 8) != BATHGPU_OK ||
+      ctx->fxmx.reserve(rows * 24) != BATHGPU_OK || ctx->bxmx.reserve(rows * 24) != BATHGPU_OK ||
+      ctx->lsf.reserve((rows + 2 * (size_t)n) * 4) != BATHGPU_OK || ctx->lsb.reserve((rows + 2 * (size_t)n) * 4) != BATHGPU_OK ||
+      ctx->dmocc.reserve(rows * 4) != BATHGPU_OK || ctx->dbtot.reserve(rows * 4) != BATHGPU_OK || ctx->detot.reserve(rows * 4) != BATHGPU_OK)
+    return fail(ctx, BATHGPU_EMEM, "device allocation failed for %d windows (%zu rows)", n, rows);
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->wins.p, wins, (size_t)n * sizeof(WindowDesc), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->xoff.p, xoff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->nstaged = n;
+  ctx->xrows = (int64_t)rows;
+
+  const int sms = ctx->prop.multiProcessorCount;
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+
+  FsParserArgs fa{};
+  fa.emis = im.emis.as<float>(); fa.cellc = im.cellc.as<float>(); fa.dna4 = ctx->dna4.as<uint32_t>();
+  fa.wins = ctx->wins.as<WindowDesc>(); fa.nwin = n; fa.mpad = im.mpad; fa.tEM = xfE[0]; fa.tEL = xfE[1];
+  fa.fwdsc = ctx->fwdsc.as<float>(); fa.status = ctx->status.as<int>();
+  fa.xmx = ctx->fxmx.as<float>(); fa.xoff = ctx->xoff.as<long long>(); fa.counter = ctx->counter.as<int>();
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
+  CUDA_TRY(ctx, dispatch_fwd<true>(im.J, fa, std::min(n, sms * std::max(1, fwd_blocks_per_sm(im.J, true))), ctx->stream));
+
+  FsBackwardArgs ba{};
+  ba.emis = fa.emis; ba.cellb = im.cellb.as<float>(); ba.dna4 = fa.dna4; ba.wins = fa.wins; ba.nwin = n; ba.mpad = im.mpad;
+  ba.tEM = xfE[0]; ba.tEL = xfE[1]; ba.fxmx = ctx->fxmx.as<float>(); ba.bxmx = ctx->bxmx.as<float>(); ba.xoff = fa.xoff;
+  ba.bcksc = ctx->bcksc.as<float>(); ba.status = fa.status; ba.counter = fa.counter;
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
+  CUDA_TRY(ctx, dispatch_bck(im.J, ba, sms, ctx->stream));
+
+  DomainDecodeArgs da{};
+  da.fxmx = ba.fxmx; da.bxmx = ba.bxmx; da.xoff = fa.xoff; da.wins = fa.wins; da.nwin = n;
+  da.tNL = xf5_loop[0]; da.tJL = xf5_loop[1]; da.tCL = xf5_loop[2];
+  da.lsf = ctx->lsf.as<float>(); da.lsb = ctx->lsb.as<float>();
+  da.mocc = ctx->dmocc.as<float>(); da.btot = ctx->dbtot.as<float>(); da.etot = ctx->detot.as<float>();
+  da.ooff = fa.xoff; da.status = fa.status;
+  fs_domain_decoding_kernel<<<(n + 3) / 4, 128, 0, ctx->stream>>>(da);
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+
+  std::vector<float> hm(rows), hb(rows), he(rows);
+  CUDA_TRY(ctx, cudaMemcpyAsync(hm.data(), ctx->dmocc.p, rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(hb.data(), ctx->dbtot.p, rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(he.data(), ctx->detot.p, rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (fwdsc) CUDA_TRY(ctx, cudaMemcpyAsync(fwdsc, ctx->fwdsc.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (bcksc) CUDA_TRY(ctx, cudaMemcpyAsync(bcksc, ctx->bcksc.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(status, ctx->status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  ctx->last_ms += ms;
+  ctx->last_launches += 3;
+  for (int w = 0; w < n; ++w) {
+    const size_t len = (size_t)wins[w].L + 1;
+    memcpy(mocc + out_offset[w], hm.data() + xoff[w], len * 4);
+    memcpy(btot + out_offset[w], hb.data() + xoff[w], len * 4);
+    memcpy(etot + out_offset[w], he.data() + xoff[w], len * 4);
+  }
+  return BATHGPU_OK;
+}
+
 extern "C" int bathgpu_fs_bck_decode(bathgpu_ctx *ctx, const bathgpu_window *wins, int n, const float xfE[2],
                                      const float xf5_loop[3], const int64_t *out_offset,
                                      float *mocc, float *btot, float *etot, float *fwdsc, float *bcksc, int32_t *status)
 {
-  return fail(ctx, BATHGPU_EINVAL, "bathgpu_fs_bck_decode: stage not built yet");
+  if (!ctx || !wins || n < 1 || !xfE || !xf5_loop || !out_offset || !mocc || !btot || !etot || !status)
+    return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fs_bck_decode");
+  if (!ctx->fs3.loaded)  return fail(ctx, BATHGPU_EINVAL, "3-codon profile not loaded");
+  if (ctx->block_n == 0) return fail(ctx, BATHGPU_EINVAL, "no block uploaded");
+  int st = check_windows(ctx, wins, n);
+  if (st != BATHGPU_OK) return st;
+  for (int w = 0; w < n; ++w)
+    if (wins[w].L < 5) return fail(ctx, BATHGPU_EINVAL, "window %d: the Backward parser needs L >= 5 (fwdback_fs.c:600)", w);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ctx->last_ms = 0.f; ctx->last_launches = 0;
+  // chunks bounded by X-row memory: 68 B per row of scratch
+  const size_t max_rows = (size_t)16 << 20;
+  int w0 = 0;
+  while (w0 < n) {
+    size_t rows = 0;
+    int w1 = w0;
+    while (w1 < n && (w1 == w0 || rows + wins[w1].L + 1 <= max_rows)) { rows += wins[w1].L + 1; ++w1; }
+    st = bck_decode_chunk(ctx, wins + w0, w1 - w0, xfE, xf5_loop, out_offset + w0, mocc, btot, etot,
+                          fwdsc ? fwdsc + w0 : nullptr, bcksc ? bcksc + w0 : nullptr, status + w0);
+    if (st != BATHGPU_OK) return st;
+    w0 = w1;
+  }
+  return BATHGPU_OK;
+}
+
+extern "C" int bathgpu_fs_fetch_xrows(bathgpu_ctx *ctx, int which, float *out, int64_t nrows)
+{
+  if (!ctx || !out || nrows < 1 || nrows > ctx->xrows || (which != 0 && which != 1))
+    return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fs_fetch_xrows");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const DevBuf &b = which ? ctx->bxmx : ctx->fxmx;
+  CUDA_TRY(ctx, cudaMemcpyAsync(out, b.p, (size_t)nrows * 24, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return BATHGPU_OK;
 }
 
 extern "C" int bathgpu_fs_domains(bathgpu_ctx *ctx, const bathgpu_envelope *envs, int n, const float xfE5[2],

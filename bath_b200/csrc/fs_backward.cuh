@@ -1,0 +1,397 @@
+// fs_backward.cuh -- frameshift Backward PARSER (3 codon lengths) and domain decoding for sm_100a.
+//
+// Computes p7_BackwardParser_Frameshift_3Codons (reference: src/impl_sse/fwdback_fs.c:565-1013) and
+// p7_DomainDecoding_Frameshift (src/impl_sse/decoding_fs.c:245-359).  Same work decomposition as the
+// Forward parser (fs_parser.cuh): one warp per DNA window, lane l owns J contiguous model nodes, all
+// per-node state in registers, rows walked from L down to 0 in an unroll of 4.
+//
+// Reference recurrence for row i (descending), with v(k) = sum_c R[c][k] M(i+c,k), c = 2,3,4 the length of
+// the quasi-codon starting at nucleotide i+1:
+//     B(i)   = sum_k v(k) tBM(k-1)
+//     D(i,k) = E(i) + v(k+1) tDM(k) + D(i,k+1) tDD(k)
+//     M(i,k) = E(i) + I(i+3,k) tMI(k) + v(k+1) tMM(k) + D(i,k+1) tMD(k)
+//     I(i,k) =        I(i+3,k) tII(k) + v(k+1) tIM(k)
+// What the kernel carries instead:
+//   * Mt(i,k) = M(i,k) / Z(k) with the same profile constant Z(k) = 1 + tMD(k)(1 + tDD(k+1) + ...) the
+//     Forward kernel uses: the E(i) terms of M and of the whole D chain collapse into "E(i) +", so the
+//     emission table (already multiplied by tBM(k-1) Z(k)) is shared with Forward, B(i) is a plain sum, and
+//     nothing that depends on E(i) sits inside the D chain:  Mt(i,k) = E(i) + G(i,k), where G needs only
+//     v, I and the E-free chain D0(i,k) = v(k+1) tDM(k) + D0(i,k+1) tDD(k)  (a downward warp scan);
+//   * 4-slot rings for Mt and I (rows i+1..i+4 live), 4-slot rings for the N/J/C specials.
+// Scaling follows the reference: row i is divided by the Forward row's SCALE(i) unless Backward has
+// switched to its own scales (xB > 1e16; :912-915), the two initialisation rows do not rescale the special
+// buffers (:673-678), row 0 is never rescaled.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "fs_parser.cuh"
+
+namespace bathgpu {
+
+enum BckCellConst { BC_VMM = 0, BC_VIM, BC_VDM, BC_DD, BC_MD, BC_MI, BC_II, BC_COUNT };
+enum BckLaneConst { BL_B0 = 0, BL_B1, BL_B2, BL_B3, BL_B4, BL_COUNT };
+
+struct FsBackwardArgs {
+  const float    *emis;        // same table as Forward: R[c][k] tBM(k-1) Z(k), permuted
+  const float    *cellb;       // backward lane constants [BC_COUNT][J][32] + [BL_COUNT][32]
+  const uint32_t *dna4;
+  const WindowDesc *wins;
+  int             nwin;
+  int             mpad;
+  float           tEM, tEL;
+  const float    *fxmx;        // Forward X rows, window w at fxmx + xoff[w]*6
+  float          *bxmx;        // Backward X rows (out), same offsets
+  const long long *xoff;
+  float          *bcksc;       // [nwin]
+  int            *status;      // [nwin]  (only written when Backward fails: keeps a Forward failure)
+  int            *counter;
+};
+
+template <int J>
+struct BckConsts {
+  float vmm[J], vim[J], vdm[J], dd[J], md[J], mi[J], ii[J];
+  float bs[5];
+};
+
+template <int J>
+struct BckState {
+  float Mt[4][J];
+  float I[4][J];
+  float xN[4], xJ[4], xC[4];
+};
+
+template <int J>
+__device__ __forceinline__ void load_bck_consts(const float *__restrict__ cc, int lane, BckConsts<J> &K)
+{
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    K.vmm[j] = __ldg(cc + (BC_VMM * J + j) * kWarp + lane);
+    K.vim[j] = __ldg(cc + (BC_VIM * J + j) * kWarp + lane);
+    K.vdm[j] = __ldg(cc + (BC_VDM * J + j) * kWarp + lane);
+    K.dd[j]  = __ldg(cc + (BC_DD  * J + j) * kWarp + lane);
+    K.md[j]  = __ldg(cc + (BC_MD  * J + j) * kWarp + lane);
+    K.mi[j]  = __ldg(cc + (BC_MI  * J + j) * kWarp + lane);
+    K.ii[j]  = __ldg(cc + (BC_II  * J + j) * kWarp + lane);
+  }
+#pragma unroll
+  for (int s = 0; s < 5; ++s) K.bs[s] = __ldg(cc + BC_COUNT * J * kWarp + (BL_B0 + s) * kWarp + lane);
+}
+
+// emission-row indices for Backward row i: quasi-codons STARTING at nucleotide i+1 (fwdback_fs.c:806-818)
+__device__ __forceinline__ uint32_t codon_word_bck(uint32_t lo, uint32_t hi, int sh, int i, int L)
+{
+  uint32_t bits = __funnelshift_r(lo, hi, sh) & 0xffffu;       // nibbles n[i+1], n[i+2], n[i+3], n[i+4]
+  int a = (int)(bits & 15u), b = (int)((bits >> 4) & 15u), c = (int)((bits >> 8) & 15u), d = (int)(bits >> 12);
+  a = (a < 4 && i + 1 >= 1 && i + 1 <= L) ? a : 338;
+  b = (b < 4 && i + 2 >= 1 && i + 2 <= L) ? b : 338;
+  c = (c < 4 && i + 3 >= 1 && i + 3 <= L) ? c : 338;
+  d = (d < 4 && i + 4 >= 1 && i + 4 <= L) ? d : 338;
+  return (uint32_t)codon2_fs3(a, b) | ((uint32_t)codon3_fs3(a, b, c) << 9) | ((uint32_t)codon4_fs3(a, b, c, d) << 18);
+}
+
+struct BckRowCtx {
+  int   L;
+  float ploop, pmove, tEL, tEM;
+  float totscale;
+  bool  own_scales;
+};
+
+// One Backward row.  PH = i & 3 (compile time).
+template <int J, int VEC, int PH>
+__device__ __forceinline__ void bck_row(int i, int lane, BckState<J> &S, const BckConsts<J> &K,
+                                        const char *__restrict__ emis_lane, unsigned rowbytes, uint32_t cw,
+                                        float fscale, BckRowCtx &R, float *__restrict__ xrow)
+{
+  constexpr int S0 = PH, S1 = (PH + 1) & 3, S2 = (PH + 2) & 3, S3 = (PH + 3) & 3;   // slots of rows i(=i+4), i+1, i+2, i+3
+  const int L = R.L;
+
+  if (i >= L - 1) {                 // warp-uniform: pad rows above L do nothing, rows L and L-1 initialise (:628-690)
+    if (i <= L) {
+      float xC = (i == L) ? R.pmove : R.ploop * R.pmove;
+      float xE = xC * R.tEM;
+      float sc = fscale;
+      if (sc > 1.0f) {
+        float sf = 1.0f / sc;
+        xC *= sf; xE *= sf;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+          for (int j = 0; j < J; ++j) { S.Mt[r][j] *= sf; S.I[r][j] *= sf; }
+        }
+        R.totscale += logf(sc);
+      }
+#pragma unroll
+      for (int j = 0; j < J; ++j) { S.Mt[S0][j] = xE; S.I[S0][j] = 0.f; }
+      S.xN[S0] = 0.f; S.xJ[S0] = 0.f; S.xC[S0] = xC;
+      if (i == L) S.xC[S1] = R.pmove;     // so that row L-2 reads C = tCL tCM (:815), whatever rows L, L-1 were scaled by
+      if (lane == 0) {
+        float2 *x2 = reinterpret_cast<float2 *>(xrow + (size_t)i * 6);
+        x2[0] = make_float2(xE, 0.f);
+        x2[1] = make_float2(0.f, 0.f);
+        x2[2] = make_float2(xC, sc);
+      }
+    }
+    return;
+  }
+
+  float e2[J], e3[J], e4[J], v[J];
+  load_emission_row<J, VEC>(reinterpret_cast<const float *>(emis_lane + (size_t)(cw & 511u) * rowbytes), e2);
+  load_emission_row<J, VEC>(reinterpret_cast<const float *>(emis_lane + (size_t)((cw >> 9) & 511u) * rowbytes), e3);
+  load_emission_row<J, VEC>(reinterpret_cast<const float *>(emis_lane + (size_t)(cw >> 18) * rowbytes), e4);
+
+  // v'(k) = tBM(k-1) sum_c R[c][k] M(i+c,k);  B(i) = sum_k v'(k)            (:820-835)
+  float bs0 = 0.f, bs1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    float t = S.Mt[S2][j] * e2[j];
+    t = fmaf(S.Mt[S3][j], e3[j], t);
+    t = fmaf(S.Mt[S0][j], e4[j], t);
+    v[j] = t;
+    if (j == 0) bs0 = t; else if (j == 1) bs1 = t; else if (j & 1) bs1 += t; else bs0 += t;
+  }
+  float xB = warp_allsum(J > 1 ? bs0 + bs1 : bs0);
+
+  // vn(k) = v'(k+1): shift down by one node
+  float vn[J];
+  {
+    float up = __shfl_down_sync(0xffffffffu, v[0], 1);
+    if (lane == 31) up = 0.f;
+#pragma unroll
+    for (int j = 0; j + 1 < J; ++j) vn[j] = v[j + 1];
+    vn[J - 1] = up;
+  }
+
+  // E-free D chain, downward: D0(k) = vn(k) vdm(k) + D0(k+1) dd(k)          (:885-909)
+  float a[J];
+  float A = 0.f;
+#pragma unroll
+  for (int j = J - 1; j >= 0; --j) { a[j] = vn[j] * K.vdm[j]; A = (j == J - 1) ? a[j] : fmaf(A, K.dd[j], a[j]); }
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    float dn = __shfl_down_sync(0xffffffffu, A, 1 << s);
+    A = fmaf(K.bs[s], dn, A);
+  }
+  float d = __shfl_down_sync(0xffffffffu, A, 1);     // D0 at the first node of the next lane
+  if (lane == 31) d = 0.f;
+
+  // G(k) = (I(i+3,k) tMI(k) + vn(k) tMM(k) + D0(k+1) tMD(k)) / Z(k);  I(i,k) = I(i+3,k) tII(k) + vn(k) tIM(k)
+  float g[J];
+#pragma unroll
+  for (int j = J - 1; j >= 0; --j) {
+    float t = S.I[S3][j] * K.mi[j];
+    t = fmaf(vn[j], K.vmm[j], t);
+    g[j] = fmaf(d, K.md[j], t);
+    d = fmaf(d, K.dd[j], a[j]);
+    S.I[S0][j] = fmaf(S.I[S3][j], K.ii[j], vn[j] * K.vim[j]);
+  }
+
+  // specials (:837-857)
+  float xC = S.xC[S3] * R.ploop;
+  float xJ = fmaf(S.xJ[S3], R.ploop, xB * R.pmove);
+  float xN = fmaf(S.xN[S3], R.ploop, xB * R.pmove);
+  float xE = fmaf(xJ, R.tEL, xC * R.tEM);
+
+  if (i == 0) {                    // termination (:951-987): only B and N are defined on row 0, no rescaling
+    S.xN[S0] = xN;
+    if (lane == 0) {
+      float2 *x2 = reinterpret_cast<float2 *>(xrow);
+      x2[0] = make_float2(0.f, xN);
+      x2[1] = make_float2(0.f, xB);
+      x2[2] = make_float2(0.f, 1.0f);
+    }
+    return;
+  }
+
+#pragma unroll
+  for (int j = 0; j < J; ++j) S.Mt[S0][j] = xE + g[j];
+
+  float scale = fscale;
+  if (i < L - 2) {                 // (:910-916)
+    if (xB > 1.0e16f) R.own_scales = true;
+    if (R.own_scales) scale = (xB > 1.0e4f) ? xB : 1.0f;
+  }
+  if (scale > 1.0f) {              // warp-uniform
+    float sf = 1.0f / scale;
+    xN *= sf; xJ *= sf; xC *= sf; xB *= sf; xE *= sf;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int j = 0; j < J; ++j) { S.Mt[r][j] *= sf; S.I[r][j] *= sf; }
+      S.xN[r] *= sf; S.xJ[r] *= sf; S.xC[r] *= sf;
+    }
+    R.totscale += logf(scale);
+  }
+  S.xN[S0] = xN; S.xJ[S0] = xJ; S.xC[S0] = xC;
+  if (lane == 0) {
+    float2 *x2 = reinterpret_cast<float2 *>(xrow + (size_t)i * 6);
+    x2[0] = make_float2(xE, xN);
+    x2[1] = make_float2(xJ, xB);
+    x2[2] = make_float2(xC, scale);
+  }
+}
+
+template <int J> struct BckTune {
+  static constexpr int kThreads   = 32;
+  static constexpr int kMinBlocks = (J <= 3) ? 20 : (J == 4) ? 16 : (J == 5) ? 14 : (J == 6) ? 13 : (J == 7) ? 11 : (J == 8) ? 10 : 8;
+};
+
+template <int J>
+__global__ void __launch_bounds__(BckTune<J>::kThreads, BckTune<J>::kMinBlocks) fs3_backward_parser_kernel(FsBackwardArgs a)
+{
+  constexpr int VEC = VecOf<J>::V;
+  const int lane = threadIdx.x & 31;
+
+  BckConsts<J> K;
+  load_bck_consts<J>(a.cellb, lane, K);
+  const char    *emis_lane = reinterpret_cast<const char *>(a.emis + lane * VEC);
+  const unsigned rowbytes  = (unsigned)a.mpad * 4u;
+
+  for (;;) {
+    int w = 0;
+    if (lane == 0) w = atomicAdd(a.counter, 1);
+    w = __shfl_sync(0xffffffffu, w, 0);
+    if (w >= a.nwin) break;
+
+    const WindowDesc wd = a.wins[w];
+    BckRowCtx R;
+    R.L = wd.L; R.ploop = wd.ploop; R.pmove = wd.pmove; R.tEL = a.tEL; R.tEM = a.tEM;
+    R.totscale = 0.f; R.own_scales = false;
+    const float *fx   = a.fxmx + (size_t)a.xoff[w] * 6;
+    float       *xrow = a.bxmx + (size_t)a.xoff[w] * 6;
+    const int L = wd.L;
+
+    BckState<J> S;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int j = 0; j < J; ++j) { S.Mt[r][j] = 0.f; S.I[r][j] = 0.f; }
+      S.xN[r] = 0.f; S.xJ[r] = 0.f; S.xC[r] = 0.f;
+    }
+
+    // rows 4*nq-1 (>= L) down to 0
+    const int nq = (L + 4) >> 2;
+    int i = 4 * nq - 1;
+    for (int q0 = 0; q0 < nq; q0 += 8) {
+      // lane l prepares row i - l: codon word from the nibbles n[i-l+1 .. i-l+4], and the Forward SCALE of that row
+      const int myrow = i - lane;
+      uint32_t cwl = 0;
+      float    fsl = 1.0f;
+      if (myrow >= 0) {
+        long long nib = (wd.start - 1) + (long long)myrow + 8;       // 0-based block index of n[myrow+1], guard word included
+        uint32_t lo = __ldg(a.dna4 + (nib >> 3)), hi = __ldg(a.dna4 + (nib >> 3) + 1);
+        cwl = codon_word_bck(lo, hi, (int)(nib & 7) * 4, myrow, L);
+        if (myrow <= L) fsl = __ldg(fx + (size_t)myrow * 6 + 5);
+      }
+      const int qn = min(8, nq - q0);
+      for (int qq = 0; qq < qn; ++qq) {
+#define BATHGPU_BROW(PH_)                                                                             \
+        {                                                                                             \
+          const int src = qq * 4 + (3 - PH_);                                                         \
+          uint32_t cw = __shfl_sync(0xffffffffu, cwl, src);                                           \
+          float    fs = __shfl_sync(0xffffffffu, fsl, src);                                           \
+          bck_row<J, VEC, PH_>(i, lane, S, K, emis_lane, rowbytes, cw, fs, R, xrow);                  \
+          --i;                                                                                        \
+        }
+        BATHGPU_BROW(3) BATHGPU_BROW(2) BATHGPU_BROW(1) BATHGPU_BROW(0)
+#undef BATHGPU_BROW
+      }
+    }
+
+    // score (:989-1003): N(0) + N(1) + N(2), rows 1 and 2 as left by every later rescale
+    {
+      float tot = S.xN[0] + S.xN[1] + S.xN[2];
+      int   st  = 0;
+      float sc;
+      if (isnan(tot) || isinf(tot)) { st = 16; sc = tot; }
+      else if (tot == 0.0f)         { st = 16; sc = -INFINITY; }
+      else sc = R.totscale + logf(tot);
+      if (lane == 0) { a.bcksc[w] = sc; if (st) a.status[w] = st; }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// p7_FLogsum (src/logsum.c:104-111): table-driven log(e^a + e^b); the table entry is recomputed
+// in double exactly as p7_FLogsumInit fills it (:80-91).
+__device__ __forceinline__ float flogsum_dev(float a, float b)
+{
+  const float mx = (a > b) ? a : b;
+  const float mn = (a > b) ? b : a;
+  if (mn == -INFINITY || (mx - mn) >= 15.7f) return mx;
+  const int idx = (int)((mx - mn) * 1000.f);
+  return mx + (float)log(1. + exp((double)-idx / 1000.));
+}
+
+struct DomainDecodeArgs {
+  const float     *fxmx, *bxmx;      // X rows of both parsers, window w at xoff[w]*6
+  const long long *xoff;
+  const WindowDesc *wins;
+  int              nwin;
+  float            tNL, tJL, tCL;    // {N,J,C}->LOOP odds of the profile the caller passes (om_fs5, src/p7_domaindef.c:320)
+  float           *lsf, *lsb;        // scratch: cumulative log scales, window w at xoff[w] (+1 slot at the end for lsb)
+  float           *mocc, *btot, *etot;     // out, window w at ooff[w], L+1 floats each
+  const long long *ooff;
+  const int       *status;           // windows whose parsers failed are skipped (outputs zeroed)
+};
+
+// One warp per window.  The cumulative sums run serially in one lane in the reference's order (the
+// terms are exact zeros except at the few rescaled rows); everything with an expf in it runs lane-parallel.
+__global__ void __launch_bounds__(128) fs_domain_decoding_kernel(DomainDecodeArgs a)
+{
+  const int lane = threadIdx.x & 31;
+  const int w    = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= a.nwin) return;
+  const int L = a.wins[w].L;
+  const float *xf = a.fxmx + (size_t)a.xoff[w] * 6;
+  const float *xb = a.bxmx + (size_t)a.xoff[w] * 6;
+  float *lsf = a.lsf + (size_t)a.xoff[w] + 2 * (size_t)w;      // L+2 slots per window
+  float *lsb = a.lsb + (size_t)a.xoff[w] + 2 * (size_t)w;
+  float *mocc = a.mocc + a.ooff[w], *btot = a.btot + a.ooff[w], *etot = a.etot + a.ooff[w];
+
+  if (a.status[w] != 0) {
+    for (int i = lane; i <= L; i += 32) { mocc[i] = 0.f; btot[i] = 0.f; etot[i] = 0.f; }
+    return;
+  }
+
+  for (int i = lane; i <= L; i += 32) { lsf[i] = logf(xf[i * 6 + 5]); lsb[i] = logf(xb[i * 6 + 5]); }
+  __syncwarp();
+  if (lane == 0) {                 // log_sfwd[i] = sum_{0..i}, :262-264
+    float acc = lsf[0];
+    for (int i = 1; i <= L; ++i) { acc = acc + lsf[i]; lsf[i] = acc; }
+  } else if (lane == 1) {          // log_sbck[i] = sum_{i..L}, :269-271
+    float acc = 0.0f;
+    lsb[L + 1] = 0.0f;
+    for (int i = L; i >= 0; --i) { acc = acc + lsb[i]; lsb[i] = acc; }
+  }
+  __syncwarp();
+
+  const float liz = -flogsum_dev(logf(xb[0 * 6 + 1]) + lsb[0],
+                                 flogsum_dev(logf(xb[1 * 6 + 1]) + lsb[1], logf(xb[2 * 6 + 1]) + lsb[2]));   // :277-282
+
+  // per-row terms: btot/etot increments parked in the output arrays, mocc final           (:296-352)
+  for (int i = lane; i <= L; i += 32) {
+    if (i < 3) { mocc[i] = 0.f; btot[i] = 0.f; etot[i] = 0.f; continue; }
+    btot[i] = xf[(i - 3) * 6 + 3] * xb[(i - 3) * 6 + 3] * expf(lsf[i - 3] + lsb[i - 3] + liz);
+    etot[i] = xf[i * 6 + 0] * xb[i * 6 + 0] * expf(lsf[i] + lsb[i] + liz);
+    float njcp = 0.f;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {          // s: 0 = N (cell 1), 1 = J (cell 2), 2 = C (cell 4)
+      const int   cell = (s == 0) ? 1 : (s == 1) ? 2 : 4;
+      const float tl   = (s == 0) ? a.tNL : (s == 1) ? a.tJL : a.tCL;
+      njcp += xf[(i - 3) * 6 + cell] * xb[i * 6 + cell] * tl * expf(lsf[i - 3] + lsb[i] + liz);
+      if (i < L)     njcp += xf[(i - 2) * 6 + cell] * xb[(i + 1) * 6 + cell] * tl * expf(lsf[i - 2] + lsb[i + 1] + liz);
+      if (i < L - 1) njcp += xf[(i - 1) * 6 + cell] * xb[(i + 2) * 6 + cell] * tl * expf(lsf[i - 1] + lsb[i + 2] + liz);
+    }
+    mocc[i] = 1.f - njcp;
+  }
+  __syncwarp();
+  if (lane < 3) {                  // three interleaved running sums, stride 3 (:299,305)
+    float bacc = 0.f, eacc = 0.f;
+    for (int i = 3 + lane; i <= L; i += 3) {
+      bacc = bacc + btot[i]; btot[i] = bacc;
+      eacc = eacc + etot[i]; etot[i] = eacc;
+    }
+  }
+}
+
+}  // namespace bathgpu

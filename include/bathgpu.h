@@ -129,6 +129,11 @@ int bathgpu_fs_bck_decode(bathgpu_ctx *ctx, const bathgpu_window *wins, int n, c
                           const float xf5_loop[3], const int64_t *out_offset,
                           float *mocc, float *btot, float *etot, float *fwdsc, float *bcksc, int32_t *status);
 
+/* X rows {E,N,J,B,C,SCALE} x (L+1) per window, windows concatenated in call order, of the Forward (which = 0)
+ * or Backward (which = 1) parser as left on the device by the last bathgpu_fs_bck_decode call (its last chunk):
+ * what P7_OMX->xmx holds after p7_ForwardParser/BackwardParser_Frameshift_3Codons (impl_sse.h:324). */
+int bathgpu_fs_fetch_xrows(bathgpu_ctx *ctx, int which, float *out, int64_t nrows);
+
 /* ---- a12-a15: per-envelope Forward/Backward/Decoding/OA/trace/null2 ------ */
 /* xfE5 = {E->MOVE, E->LOOP} odds of om_fs5 (unihit: {1,0}).  traces: caller-allocated buffer
  * of max_steps steps; results[e].trace_offset/len index into it. */
