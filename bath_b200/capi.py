@@ -15,6 +15,7 @@ EXPORTS = [
     "bathgpu_stage_windows", "bathgpu_fs_fwd_staged", "bathgpu_fetch_scores",
     "bathgpu_fs_bck_decode", "bathgpu_fs_domains", "bathgpu_last_stage_timing", "bathgpu_measure_fp32_peak",
     "bathgpu_host_alloc", "bathgpu_host_free", "bathgpu_fs_fetch_xrows",
+    "bathgpu_fs_fetch_domain_matrices",
 ]
 
 
@@ -80,6 +81,8 @@ def load():
     L.bathgpu_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.bathgpu_fs_fetch_xrows.restype = C.c_int
     L.bathgpu_fs_fetch_xrows.argtypes = [vp, C.c_int, fp, C.c_int64]
+    L.bathgpu_fs_fetch_domain_matrices.restype = C.c_int
+    L.bathgpu_fs_fetch_domain_matrices.argtypes = [vp, C.c_int, fp, fp, fp, fp]
     L.bathgpu_host_alloc.restype = vp
     L.bathgpu_host_alloc.argtypes = [C.c_size_t]
     L.bathgpu_host_free.restype = None
@@ -237,6 +240,14 @@ class Context:
         self._check(self.lib.bathgpu_fs_fetch_xrows(self.h, which, _f(out), tot))
         off = np.concatenate([[0], np.cumsum(Ls + 1)])
         return [out[off[w]: off[w + 1]] for w in range(len(wins))]
+
+    def fs_fetch_domain_matrices(self, e, M, L):
+        pp = np.empty((L + 1, M + 1, 8), np.float32)
+        oa = np.empty((L + 1, M + 1, 3), np.float32)
+        ppx = np.empty((L + 1, 6), np.float32)
+        oax = np.empty((L + 1, 6), np.float32)
+        self._check(self.lib.bathgpu_fs_fetch_domain_matrices(self.h, e, _f(pp), _f(oa), _f(ppx), _f(oax)))
+        return pp, oa, ppx, oax
 
     def fs_domains(self, envs, xfE5=(1.0, 0.0), max_steps=None):
         n = len(envs)

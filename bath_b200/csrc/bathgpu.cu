@@ -13,6 +13,7 @@
 #include "../../include/bathgpu.h"
 #include "fs_parser.cuh"
 #include "fs_backward.cuh"
+#include "fs_domain.cuh"
 #include "microbench.cuh"
 
 using namespace bathgpu;
@@ -40,6 +41,11 @@ struct FsProfileImage {
   DevBuf emis;     // [nrows][mpad]
   DevBuf cellc;    // forward lane constants
   DevBuf cellb;    // backward lane constants
+  DevBuf cellf5;   // 5-codon full-matrix Forward lane constants (fs_domain.cuh)
+  DevBuf amino;    // [20][mpad] amino-acid odds, unfolded, permuted (null2)
+  DevBuf oaflags;  // [mpad] transition-allowed bits per node (optimal accuracy masks)
+  DevBuf oapass;   // [5][32] D pass-through flags of the optimal-accuracy scan
+  DevBuf tfvraw;   // [8][M+1] transition odds as given (traceback)
   bool  loaded = false;
 };
 
@@ -59,6 +65,10 @@ struct bathgpu_ctx {
   DevBuf        scratch;
   DevBuf        fxmx, bxmx, lsf, lsb, xoff, dmocc, dbtot, detot, bcksc;
   int64_t       xrows = 0;          // rows held in fxmx/bxmx by the last bck_decode chunk
+  // domain stage workspace (last chunk stays resident for bathgpu_fs_fetch_domain_matrices)
+  DevBuf        envs, dpp, doa, dfx, dppx, doax, dlsf, dfw, dbk, doasc, dnull2, dstat, dtoff, dtlen, dsteps;
+  std::vector<long long> dom_xoff;
+  std::vector<int>       dom_L;
   float         last_ms = 0.f;
   int           last_launches = 0;
 };
@@ -106,9 +116,14 @@ extern "C" void bathgpu_destroy(bathgpu_ctx *ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (FsProfileImage *im : { &ctx->fs3, &ctx->fs5 }) { im->emis.release(); im->cellc.release(); im->cellb.release(); }
+  for (FsProfileImage *im : { &ctx->fs3, &ctx->fs5 }) {
+    im->emis.release(); im->cellc.release(); im->cellb.release(); im->cellf5.release(); im->amino.release();
+    im->oaflags.release(); im->oapass.release(); im->tfvraw.release();
+  }
   ctx->dna_bytes.release(); ctx->dna4.release(); ctx->wins.release(); ctx->fwdsc.release();
   ctx->status.release(); ctx->counter.release(); ctx->scratch.release();
+  for (DevBuf *b : { &ctx->envs, &ctx->dpp, &ctx->doa, &ctx->dfx, &ctx->dppx, &ctx->doax, &ctx->dlsf, &ctx->dfw, &ctx->dbk, &ctx->doasc,
+                     &ctx->dnull2, &ctx->dstat, &ctx->dtoff, &ctx->dtlen, &ctx->dsteps }) b->release();
   for (DevBuf *b : { &ctx->fxmx, &ctx->bxmx, &ctx->lsf, &ctx->lsb, &ctx->xoff, &ctx->dmocc, &ctx->dbtot, &ctx->detot, &ctx->bcksc }) b->release();
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
@@ -297,6 +312,84 @@ extern "C" int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int n
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   }
 
+  // ---- full-matrix Forward constants, null2 amino rows, optimal-accuracy masks, raw transitions (fs_domain.cuh)
+  {
+    std::vector<float> cc((size_t)(F5_COUNT * J + 5) * 32, 0.0f);
+    auto C = [&](int which_c, int j, int lane) -> float & { return cc[(size_t)(which_c * J + j) * 32 + lane]; };
+    std::vector<double> bfull(32, 1.0);
+    for (int lane = 0; lane < 32; ++lane) {
+      double pp = 1.0;
+      for (int j = 0; j < J; ++j) {
+        int k = lane * J + j + 1;
+        if (k <= M) {
+          double sn = sK[k + 1];
+          C(F5_MM, j, lane) = (float)(T(tMM, k) / (zK[k] * sn));
+          C(F5_IM, j, lane) = (float)(T(tIM, k) / sn);
+          C(F5_DM, j, lane) = (float)(T(tDM, k) / sn);
+          C(F5_MD, j, lane) = (float)(T(tMD, k) / zK[k]);
+          C(F5_DD, j, lane) = (float)T(tDD, k);
+          C(F5_MI, j, lane) = (float)(T(tMI, k) / zK[k]);
+          C(F5_II, j, lane) = (float)T(tII, k);
+        }
+        pp *= T(tDD, k);
+      }
+      bfull[lane] = pp;
+    }
+    std::vector<double> b(bfull);
+    for (int s = 0; s < 5; ++s) {
+      int d = 1 << s;
+      std::vector<double> nb(b);
+      for (int lane = 0; lane < 32; ++lane) {
+        cc[(size_t)(F5_COUNT * J + s) * 32 + lane] = (lane >= d) ? (float)b[lane] : 0.0f;
+        if (lane >= d) nb[lane] = b[lane] * b[lane - d];
+      }
+      b.swap(nb);
+    }
+    const int amino0 = nrows - BATHGPU_KP;
+    std::vector<float> am((size_t)20 * mpad, 0.0f);
+    for (int x = 0; x < 20; ++x)
+      for (int k = 1; k <= M; ++k) am[(size_t)x * mpad + perm_index(k - 1, J)] = rfv[(size_t)(amino0 + x) * ld + k];
+    std::vector<uint32_t> fl(mpad, 0u);
+    std::vector<int> lane_pass(32, 1);
+    for (int k = 1; k <= M; ++k) {
+      uint32_t f = 0;
+      if (T(tBM, k - 1) > 0.0) f |= OF_BM;
+      if (T(tMM, k - 1) > 0.0) f |= OF_MM;
+      if (T(tIM, k - 1) > 0.0) f |= OF_IM;
+      if (T(tDM, k - 1) > 0.0) f |= OF_DM;
+      if (T(tMD, k - 1) > 0.0) f |= OF_MD;
+      if (T(tDD, k - 1) > 0.0) f |= OF_DD;
+      if (T(tMI, k) > 0.0)     f |= OF_MI;
+      if (T(tII, k) > 0.0)     f |= OF_II;
+      fl[k - 1] = f;             // indexed by lane*J + j, NOT permuted
+      if (!(f & OF_DD)) lane_pass[(k - 1) / J] = 0;
+    }
+    // nodes beyond M never pass anything on; they are forced to -inf in the kernel
+    std::vector<float> pass((size_t)5 * 32, 0.0f);
+    {
+      std::vector<int> cur(lane_pass);
+      for (int s = 0; s < 5; ++s) {
+        int d = 1 << s;
+        std::vector<int> nx(cur);
+        for (int lane = 0; lane < 32; ++lane) {
+          pass[(size_t)s * 32 + lane] = (lane >= d && cur[lane]) ? 1.0f : 0.0f;
+          if (lane >= d) nx[lane] = cur[lane] && cur[lane - d];
+        }
+        cur.swap(nx);
+      }
+    }
+    if (im.cellf5.reserve(cc.size() * 4) != BATHGPU_OK || im.amino.reserve(am.size() * 4) != BATHGPU_OK ||
+        im.oaflags.reserve(fl.size() * 4) != BATHGPU_OK || im.oapass.reserve(pass.size() * 4) != BATHGPU_OK ||
+        im.tfvraw.reserve((size_t)8 * ld * 4) != BATHGPU_OK)
+      return fail(ctx, BATHGPU_EMEM, "device allocation failed");
+    CUDA_TRY(ctx, cudaMemcpyAsync(im.cellf5.p, cc.data(), cc.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(im.amino.p, am.data(), am.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(im.oaflags.p, fl.data(), fl.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(im.oapass.p, pass.data(), pass.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(im.tfvraw.p, tfv, (size_t)8 * ld * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+
   if (im.emis.reserve(emis.size() * sizeof(float)) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
   CUDA_TRY(ctx, cudaMemcpyAsync(im.emis.p, emis.data(), emis.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -305,7 +398,7 @@ extern "C" int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int n
 }
 
 // ---------------------------------------------------------------------------------------------
-// block upload: ESL_DSQ bytes -> 4-bit packed words, one guard word in front, two behind
+// block upload: ESL_DSQ bytes -> 4-bit packed words, one guard word in front, eight behind
 __global__ void pack_dna4_kernel(const uint8_t *__restrict__ dsq, long long n, uint32_t *__restrict__ out, long long nwords)
 {
   long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -325,7 +418,7 @@ extern "C" int bathgpu_upload_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_
 {
   if (!ctx || !dsq || n < 1) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_upload_block");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  const long long nwords = (n + 8 + 7) / 8 + 2;
+  const long long nwords = (n + 8 + 7) / 8 + 8;      // kernels prefetch up to 40 nt past a window
   if (ctx->dna_bytes.reserve((size_t)n + 2) != BATHGPU_OK || ctx->dna4.reserve((size_t)nwords * 4) != BATHGPU_OK)
     return fail(ctx, BATHGPU_EMEM, "device allocation failed for a %lld-nt block", (long long)n);
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dna_bytes.p, dsq, (size_t)n + 2, cudaMemcpyHostToDevice, ctx->stream));
@@ -582,8 +675,187 @@ extern "C" int bathgpu_fs_fetch_xrows(bathgpu_ctx *ctx, int which, float *out, i
   return BATHGPU_OK;
 }
 
+template <int J> struct DomLaunch {
+  static cudaError_t run(const DomainArgs &a, const TraceArgs &t, int sms, cudaStream_t s)
+  {
+    int nb = 0;
+    cudaError_t e;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fs5_forward_kernel<J>, 32, 0);
+    if ((e = cudaMemsetAsync(a.counter, 0, 4, s)) != cudaSuccess) return e;
+    fs5_forward_kernel<J><<<std::min(a.nenv, sms * std::max(nb, 1)), 32, 0, s>>>(a);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fs5_backward_decode_kernel<J>, 32, 0);
+    if ((e = cudaMemsetAsync(a.counter, 0, 4, s)) != cudaSuccess) return e;
+    fs5_backward_decode_kernel<J><<<std::min(a.nenv, sms * std::max(nb, 1)), 32, 0, s>>>(a);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fs5_optacc_kernel<J>, 32, 0);
+    if ((e = cudaMemsetAsync(a.counter, 0, 4, s)) != cudaSuccess) return e;
+    fs5_optacc_kernel<J><<<std::min(a.nenv, sms * std::max(nb, 1)), 32, 0, s>>>(a);
+    fs5_oatrace_kernel<<<(a.nenv + 3) / 4, 128, 0, s>>>(a, t);
+    return cudaGetLastError();
+  }
+};
+
+static cudaError_t dispatch_domains(int J, const DomainArgs &a, const TraceArgs &t, int sms, cudaStream_t s)
+{
+#define DOM(J_) case J_: return DomLaunch<J_>::run(a, t, sms, s);
+  switch (J) { DOM(1) DOM(2) DOM(3) DOM(4) DOM(5) DOM(6) DOM(7) DOM(8) DOM(10) DOM(12) default: return cudaErrorInvalidValue; }
+#undef DOM
+}
+
+// p7_trace_fs_Reverse (src/p7_trace.c:2527-2568): pull N/C/J residues back by one, then reverse.
+static void finish_trace(TraceStep *tr, int n)
+{
+  for (int z = 0; z + 1 < n; ++z) {
+    if (tr[z].st == tr[z + 1].st && (tr[z].st == TS_N || tr[z].st == TS_C || tr[z].st == TS_J)) {
+      if (tr[z].i == 0 && tr[z + 1].i > 0) {
+        tr[z].i = tr[z + 1].i;   tr[z + 1].i = 0;
+        tr[z].pp = tr[z + 1].pp; tr[z + 1].pp = 0.0f;
+      }
+    }
+  }
+  std::reverse(tr, tr + n);
+}
+
+static int domains_chunk(bathgpu_ctx *ctx, const bathgpu_envelope *envs, int n, const float xfE5[2],
+                         bathgpu_domain_result *results, bathgpu_trace_step *traces, int64_t max_steps, int64_t &steps_used)
+{
+  const FsProfileImage &im = ctx->fs5;
+  const int M = im.M, mpad = im.mpad;
+  std::vector<long long> xoff(n + 1, 0), toff(n + 1, 0);
+  for (int e = 0; e < n; ++e) { xoff[e + 1] = xoff[e] + envs[e].L + 1; toff[e + 1] = toff[e] + envs[e].L + M + 8; }
+  const size_t rows = (size_t)xoff[n];
+  static_assert(sizeof(EnvelopeDesc) == sizeof(bathgpu_envelope), "descriptor layouts must agree");
+  static_assert(sizeof(TraceStep) == sizeof(bathgpu_trace_step), "trace step layouts must agree");
+
+  if (ctx->envs.reserve((size_t)n * sizeof(EnvelopeDesc)) != BATHGPU_OK || ctx->xoff.reserve((size_t)(n + 1) * 8) != BATHGPU_OK ||
+      ctx->dtoff.reserve((size_t)(n + 1) * 8) != BATHGPU_OK || ctx->dtlen.reserve((size_t)n * 4) != BATHGPU_OK ||
+      ctx->dpp.reserve(rows * kPPCells * mpad * 4) != BATHGPU_OK || ctx->doa.reserve(rows * kOACells * mpad * 4) != BATHGPU_OK ||
+      ctx->dfx.reserve(rows * 24) != BATHGPU_OK || ctx->dppx.reserve(rows * 24) != BATHGPU_OK || ctx->doax.reserve(rows * 24) != BATHGPU_OK ||
+      ctx->dlsf.reserve(rows * 4) != BATHGPU_OK || ctx->dfw.reserve((size_t)n * 4) != BATHGPU_OK || ctx->dbk.reserve((size_t)n * 4) != BATHGPU_OK ||
+      ctx->doasc.reserve((size_t)n * 4) != BATHGPU_OK || ctx->dnull2.reserve((size_t)n * 29 * 4) != BATHGPU_OK ||
+      ctx->dstat.reserve((size_t)n * 4) != BATHGPU_OK || ctx->counter.reserve(64) != BATHGPU_OK ||
+      ctx->dsteps.reserve((size_t)toff[n] * sizeof(TraceStep)) != BATHGPU_OK)
+    return fail(ctx, BATHGPU_EMEM, "device allocation failed for %d envelopes (%zu rows, M=%d)", n, rows, M);
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->envs.p, envs, (size_t)n * sizeof(EnvelopeDesc), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->xoff.p, xoff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dtoff.p, toff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+
+  DomainArgs a{};
+  a.emis = im.emis.as<float>(); a.amino = im.amino.as<float>(); a.cellf = im.cellf5.as<float>(); a.cellb = im.cellb.as<float>();
+  a.oapass = im.oapass.as<float>(); a.oaflags = im.oaflags.as<uint32_t>(); a.dna4 = ctx->dna4.as<uint32_t>();
+  a.envs = ctx->envs.as<EnvelopeDesc>(); a.nenv = n; a.M = M; a.mpad = mpad; a.tEM = xfE5[0]; a.tEL = xfE5[1];
+  a.xoff = ctx->xoff.as<long long>(); a.pp = ctx->dpp.as<float>(); a.oa = ctx->doa.as<float>(); a.fx = ctx->dfx.as<float>();
+  a.ppx = ctx->dppx.as<float>(); a.oax = ctx->doax.as<float>(); a.lsf = ctx->dlsf.as<float>();
+  a.fwdsc = ctx->dfw.as<float>(); a.bcksc = ctx->dbk.as<float>(); a.oasc = ctx->doasc.as<float>();
+  a.null2 = ctx->dnull2.as<float>(); a.status = ctx->dstat.as<int>(); a.counter = ctx->counter.as<int>();
+  TraceArgs t{};
+  t.steps = ctx->dsteps.as<TraceStep>(); t.toff = ctx->dtoff.as<long long>(); t.tlen = ctx->dtlen.as<int>();
+  t.tfv = im.tfvraw.as<float>(); t.J = im.J;
+
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  CUDA_TRY(ctx, dispatch_domains(im.J, a, t, ctx->prop.multiProcessorCount, ctx->stream));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+
+  std::vector<float> fw(n), bk(n), oa(n), n2((size_t)n * 29);
+  std::vector<int> st(n), tl(n);
+  std::vector<TraceStep> steps((size_t)toff[n]);
+  CUDA_TRY(ctx, cudaMemcpyAsync(fw.data(), ctx->dfw.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(bk.data(), ctx->dbk.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(oa.data(), ctx->doasc.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(n2.data(), ctx->dnull2.p, (size_t)n * 29 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(st.data(), ctx->dstat.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(tl.data(), ctx->dtlen.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(steps.data(), ctx->dsteps.p, steps.size() * sizeof(TraceStep), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  ctx->last_ms += ms;
+  ctx->last_launches += 4;
+  ctx->dom_xoff = xoff;
+  ctx->dom_L.assign(n, 0);
+  for (int e = 0; e < n; ++e) ctx->dom_L[e] = envs[e].L;
+
+  for (int e = 0; e < n; ++e) {
+    bathgpu_domain_result &r = results[e];
+    r.envsc = fw[e]; r.bcksc = bk[e]; r.oasc = oa[e]; r.status = st[e];
+    memcpy(r.null2, &n2[(size_t)e * 29], 29 * 4);
+    r.trace_offset = (int32_t)steps_used; r.trace_len = 0;
+    if (st[e] == 0 && tl[e] > 0) {
+      if (steps_used + tl[e] > max_steps)
+        return fail(ctx, BATHGPU_EINVAL, "trace buffer too small: %lld steps needed so far, %lld given", (long long)(steps_used + tl[e]), (long long)max_steps);
+      TraceStep *tr = &steps[(size_t)toff[e]];
+      finish_trace(tr, tl[e]);
+      memcpy(traces + steps_used, tr, (size_t)tl[e] * sizeof(TraceStep));
+      r.trace_len = tl[e];
+      steps_used += tl[e];
+    }
+  }
+  return BATHGPU_OK;
+}
+
 extern "C" int bathgpu_fs_domains(bathgpu_ctx *ctx, const bathgpu_envelope *envs, int n, const float xfE5[2],
                                   bathgpu_domain_result *results, bathgpu_trace_step *traces, int64_t max_steps)
 {
-  return fail(ctx, BATHGPU_EINVAL, "bathgpu_fs_domains: stage not built yet");
+  if (!ctx || !envs || n < 1 || !xfE5 || !results || !traces || max_steps < 1)
+    return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fs_domains");
+  if (!ctx->fs5.loaded)  return fail(ctx, BATHGPU_EINVAL, "5-codon profile not loaded");
+  if (ctx->block_n == 0) return fail(ctx, BATHGPU_EINVAL, "no block uploaded");
+  for (int e = 0; e < n; ++e)
+    if (envs[e].L < 6 || envs[e].start < 1 || envs[e].start + envs[e].L - 1 > ctx->block_n)
+      return fail(ctx, BATHGPU_EINVAL, "envelope %d (start %lld, L %d) is outside the uploaded block (n=%lld) or shorter than 6",
+                  e, (long long)envs[e].start, envs[e].L, (long long)ctx->block_n);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ctx->last_ms = 0.f; ctx->last_launches = 0;
+  // chunks bounded by matrix memory: (7 + 3) * mpad * 4 B per row
+  const size_t row_bytes = (size_t)(kPPCells + kOACells) * ctx->fs5.mpad * 4 + 80;
+  const size_t max_rows = std::max<size_t>(((size_t)8 << 30) / row_bytes, 4096);
+  int64_t steps_used = 0;
+  int e0 = 0;
+  while (e0 < n) {
+    size_t rows = 0;
+    int e1 = e0;
+    while (e1 < n && (e1 == e0 || rows + envs[e1].L + 1 <= max_rows)) { rows += envs[e1].L + 1; ++e1; }
+    int st = domains_chunk(ctx, envs + e0, e1 - e0, xfE5, results + e0, traces, max_steps, steps_used);
+    if (st != BATHGPU_OK) return st;
+    e0 = e1;
+  }
+  return BATHGPU_OK;
+}
+
+// Test/diagnostic access to the matrices of envelope e of the LAST chunk of the last bathgpu_fs_domains call,
+// un-permuted: pp [(L+1)][(M+1)][8] in the reference's cell order {D,I,C0..C5} (impl_sse.h:296-314; D = 0),
+// oa [(L+1)][(M+1)][3] {M,D,I}, ppx / oax [(L+1)][6].
+extern "C" int bathgpu_fs_fetch_domain_matrices(bathgpu_ctx *ctx, int e, float *pp, float *oa, float *ppx, float *oax)
+{
+  if (!ctx || e < 0 || e >= (int)ctx->dom_L.size()) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fs_fetch_domain_matrices");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const FsProfileImage &im = ctx->fs5;
+  const int M = im.M, mpad = im.mpad, J = im.J, L = ctx->dom_L[e];
+  const size_t r0 = (size_t)ctx->dom_xoff[e], nr = (size_t)L + 1;
+  std::vector<float> hp(nr * kPPCells * mpad), ho(nr * kOACells * mpad);
+  CUDA_TRY(ctx, cudaMemcpy(hp.data(), ctx->dpp.as<float>() + r0 * kPPCells * mpad, hp.size() * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(ctx, cudaMemcpy(ho.data(), ctx->doa.as<float>() + r0 * kOACells * mpad, ho.size() * 4, cudaMemcpyDeviceToHost));
+  if (ppx) CUDA_TRY(ctx, cudaMemcpy(ppx, ctx->dppx.as<float>() + r0 * 6, nr * 24, cudaMemcpyDeviceToHost));
+  if (oax) CUDA_TRY(ctx, cudaMemcpy(oax, ctx->doax.as<float>() + r0 * 6, nr * 24, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < nr; ++i)
+    for (int k = 0; k <= M; ++k) {
+      float *pc = pp ? pp + (i * (M + 1) + k) * 8 : nullptr;
+      float *oc = oa ? oa + (i * (M + 1) + k) * 3 : nullptr;
+      if (k == 0) {
+        if (pc) for (int c = 0; c < 8; ++c) pc[c] = 0.f;
+        if (oc) for (int c = 0; c < 3; ++c) oc[c] = -INFINITY;
+        continue;
+      }
+      const int p = perm_index(k - 1, J);
+      if (pc) {
+        pc[0] = 0.f;
+        pc[1] = hp[(i * kPPCells + PP_I) * mpad + p];
+        for (int c = 0; c < 6; ++c) pc[2 + c] = hp[(i * kPPCells + PP_C0 + c) * mpad + p];
+      }
+      if (oc) {
+        oc[0] = ho[(i * kOACells + OA_M) * mpad + p];
+        oc[1] = ho[(i * kOACells + OA_D) * mpad + p];
+        oc[2] = ho[(i * kOACells + OA_I) * mpad + p];
+      }
+    }
+  return BATHGPU_OK;
 }

@@ -140,6 +140,11 @@ int bathgpu_fs_fetch_xrows(bathgpu_ctx *ctx, int which, float *out, int64_t nrow
 int bathgpu_fs_domains(bathgpu_ctx *ctx, const bathgpu_envelope *envs, int n, const float xfE5[2],
                        bathgpu_domain_result *results, bathgpu_trace_step *traces, int64_t max_steps);
 
+/* Test/diagnostic: matrices of envelope e of the last chunk of the last bathgpu_fs_domains call, in the
+ * reference's cell order: pp [(L+1)][(M+1)][8] {D,I,M_C0..M_C5} (impl_sse.h:296-314; D cells are 0 after
+ * decoding), oa [(L+1)][(M+1)][3] {M,D,I}, ppx / oax [(L+1)][6] {E,N,J,B,C,SCALE}.  Any pointer may be NULL. */
+int bathgpu_fs_fetch_domain_matrices(bathgpu_ctx *ctx, int e, float *pp, float *oa, float *ppx, float *oax);
+
 /* ---- measurement helpers ------------------------------------------------ */
 /* Device time (ms) of the kernels launched by the most recent stage call, measured with
  * CUDA events on the context's stream, and how many kernels that call launched. */
