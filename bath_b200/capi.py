@@ -16,6 +16,7 @@ EXPORTS = [
     "bathgpu_fs_bck_decode", "bathgpu_fs_domains", "bathgpu_last_stage_timing", "bathgpu_measure_fp32_peak",
     "bathgpu_host_alloc", "bathgpu_host_free", "bathgpu_fs_fetch_xrows",
     "bathgpu_fs_fetch_domain_matrices",
+    "bathgpu_load_filter_profile", "bathgpu_upload_orfs", "bathgpu_msv_orfs", "bathgpu_ssv_windows", "bathgpu_vit_orfs",
 ]
 
 
@@ -29,6 +30,17 @@ window_dtype = np.dtype([("start", "<i8"), ("L", "<i4"), ("pmove", "<f4"), ("plo
 trace_dtype = np.dtype([("i", "<i4"), ("k", "<i2"), ("st", "u1"), ("c", "u1"), ("pp", "<f4")], align=True)
 domain_dtype = np.dtype([("envsc", "<f4"), ("bcksc", "<f4"), ("oasc", "<f4"), ("status", "<i4"),
                          ("trace_offset", "<i4"), ("trace_len", "<i4"), ("null2", "<f4", (KP,))], align=True)
+
+
+class FilterParams(C.Structure):
+    _fields_ = [("M", C.c_int32), ("tbm_b", C.c_int32), ("tec_b", C.c_int32), ("base_b", C.c_int32), ("bias_b", C.c_int32),
+                ("scale_b", C.c_float), ("base_w", C.c_int32), ("ddbound_w", C.c_int32), ("xw_E_move", C.c_int32),
+                ("xw_E_loop", C.c_int32), ("scale_w", C.c_float), ("cpu_lanes_u8", C.c_int32), ("cpu_lanes_i16", C.c_int32)]
+
+
+orf_dtype = np.dtype([("offset", "<i8"), ("L", "<i4"), ("tjb_b", "u1"), ("ssv_thresh", "u1"), ("xw_move", "<i2"),
+                      ("vit_thresh", "<i2"), ("flags", "<i2"), ("ext_thresh", "<i4")], align=True)
+orf_window_dtype = np.dtype([("orf", "<i4"), ("n", "<i4"), ("k", "<i4"), ("length", "<i4"), ("score", "<f4")], align=True)
 
 
 class BathGpuError(RuntimeError):
@@ -83,6 +95,16 @@ def load():
     L.bathgpu_fs_fetch_xrows.argtypes = [vp, C.c_int, fp, C.c_int64]
     L.bathgpu_fs_fetch_domain_matrices.restype = C.c_int
     L.bathgpu_fs_fetch_domain_matrices.argtypes = [vp, C.c_int, fp, fp, fp, fp]
+    L.bathgpu_load_filter_profile.restype = C.c_int
+    L.bathgpu_load_filter_profile.argtypes = [vp, C.POINTER(FilterParams), C.POINTER(C.c_uint8), C.POINTER(C.c_int16), C.POINTER(C.c_int16)]
+    L.bathgpu_upload_orfs.restype = C.c_int
+    L.bathgpu_upload_orfs.argtypes = [vp, C.POINTER(C.c_uint8), C.c_int64]
+    L.bathgpu_msv_orfs.restype = C.c_int
+    L.bathgpu_msv_orfs.argtypes = [vp, vp, C.c_int, fp, ip]
+    L.bathgpu_ssv_windows.restype = C.c_int
+    L.bathgpu_ssv_windows.argtypes = [vp, vp, C.c_int, vp, C.c_int, ip]
+    L.bathgpu_vit_orfs.restype = C.c_int
+    L.bathgpu_vit_orfs.argtypes = [vp, vp, C.c_int, fp, ip, vp, C.c_int, ip]
     L.bathgpu_host_alloc.restype = vp
     L.bathgpu_host_alloc.argtypes = [C.c_size_t]
     L.bathgpu_host_free.restype = None
@@ -248,6 +270,42 @@ class Context:
         oax = np.empty((L + 1, 6), np.float32)
         self._check(self.lib.bathgpu_fs_fetch_domain_matrices(self.h, e, _f(pp), _f(oa), _f(ppx), _f(oax)))
         return pp, oa, ppx, oax
+
+    def load_filter_profile(self, params, rbv, rwv, twv):
+        """params: dict with the FilterParams fields; rbv [29][M+1] u8, rwv [29][M+1] i16, twv [8][M+1] i16"""
+        prm = FilterParams(**params)
+        rbv = np.ascontiguousarray(rbv, np.uint8)
+        rwv = np.ascontiguousarray(rwv, np.int16)
+        twv = np.ascontiguousarray(twv, np.int16)
+        self._check(self.lib.bathgpu_load_filter_profile(self.h, C.byref(prm), rbv.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                                         rwv.ctypes.data_as(C.POINTER(C.c_int16)),
+                                                         twv.ctypes.data_as(C.POINTER(C.c_int16))))
+
+    def upload_orfs(self, residues):
+        residues = np.ascontiguousarray(residues, np.uint8)
+        self._check(self.lib.bathgpu_upload_orfs(self.h, residues.ctypes.data_as(C.POINTER(C.c_uint8)), len(residues)))
+
+    def msv_orfs(self, orfs):
+        n = len(orfs)
+        sc, st = np.empty(n, np.float32), np.empty(n, np.int32)
+        self._check(self.lib.bathgpu_msv_orfs(self.h, orfs.ctypes.data, n, _f(sc), _i(st)))
+        return sc, st
+
+    def ssv_windows(self, orfs, max_wins=None):
+        max_wins = max_wins or (16 * len(orfs) + 64)
+        w = np.zeros(max_wins, orf_window_dtype)
+        nw = C.c_int32()
+        self._check(self.lib.bathgpu_ssv_windows(self.h, orfs.ctypes.data, len(orfs), w.ctypes.data, max_wins, C.byref(nw)))
+        return w[: nw.value]
+
+    def vit_orfs(self, orfs, max_wins=None):
+        n = len(orfs)
+        max_wins = max_wins or (16 * n + 64)
+        sc, st = np.empty(n, np.float32), np.empty(n, np.int32)
+        w = np.zeros(max_wins, orf_window_dtype)
+        nw = C.c_int32()
+        self._check(self.lib.bathgpu_vit_orfs(self.h, orfs.ctypes.data, n, _f(sc), _i(st), w.ctypes.data, max_wins, C.byref(nw)))
+        return sc, st, w[: nw.value]
 
     def fs_domains(self, envs, xfE5=(1.0, 0.0), max_steps=None):
         n = len(envs)

@@ -14,6 +14,7 @@
 #include "fs_parser.cuh"
 #include "fs_backward.cuh"
 #include "fs_domain.cuh"
+#include "orf_filters.cuh"
 #include "microbench.cuh"
 
 using namespace bathgpu;
@@ -65,6 +66,12 @@ struct bathgpu_ctx {
   DevBuf        scratch;
   DevBuf        fxmx, bxmx, lsf, lsb, xoff, dmocc, dbtot, detot, bcksc;
   int64_t       xrows = 0;          // rows held in fxmx/bxmx by the last bck_decode chunk
+  // ORF-stage filters
+  bool          flt_loaded = false;
+  bathgpu_filter_params flt{};
+  int           flt_W = 0, flt_P = 0;
+  DevBuf        f_rbv, f_rwv, f_twv, f_ddsum, residues, orfs, fsc, fst, fwins, fnw;
+  int64_t       nres = 0;
   // domain stage workspace (last chunk stays resident for bathgpu_fs_fetch_domain_matrices)
   DevBuf        envs, dpp, doa, dfx, dppx, doax, dlsf, dfw, dbk, doasc, dnull2, dstat, dtoff, dtlen, dsteps;
   std::vector<long long> dom_xoff;
@@ -122,6 +129,7 @@ extern "C" void bathgpu_destroy(bathgpu_ctx *ctx)
   }
   ctx->dna_bytes.release(); ctx->dna4.release(); ctx->wins.release(); ctx->fwdsc.release();
   ctx->status.release(); ctx->counter.release(); ctx->scratch.release();
+  for (DevBuf *b : { &ctx->f_rbv, &ctx->f_rwv, &ctx->f_twv, &ctx->f_ddsum, &ctx->residues, &ctx->orfs, &ctx->fsc, &ctx->fst, &ctx->fwins, &ctx->fnw }) b->release();
   for (DevBuf *b : { &ctx->envs, &ctx->dpp, &ctx->doa, &ctx->dfx, &ctx->dppx, &ctx->doax, &ctx->dlsf, &ctx->dfw, &ctx->dbk, &ctx->doasc,
                      &ctx->dnull2, &ctx->dstat, &ctx->dtoff, &ctx->dtlen, &ctx->dsteps }) b->release();
   for (DevBuf *b : { &ctx->fxmx, &ctx->bxmx, &ctx->lsf, &ctx->lsb, &ctx->xoff, &ctx->dmocc, &ctx->dbtot, &ctx->detot, &ctx->bcksc }) b->release();
@@ -857,5 +865,233 @@ extern "C" int bathgpu_fs_fetch_domain_matrices(bathgpu_ctx *ctx, int e, float *
         oc[2] = ho[(i * kOACells + OA_I) * mpad + p];
       }
     }
+  return BATHGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ORF-stage integer filters
+extern "C" int bathgpu_load_filter_profile(bathgpu_ctx *ctx, const bathgpu_filter_params *prm,
+                                           const uint8_t *rbv, const int16_t *rwv, const int16_t *twv)
+{
+  if (!ctx || !prm || !rbv || !rwv || !twv || prm->M < 1) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_load_filter_profile");
+  const int M = prm->M, ld = M + 1;
+  if (M > 384) return fail(ctx, BATHGPU_EINVAL, "model length %d exceeds the single-warp kernels' limit (384)", M);
+  if (prm->cpu_lanes_u8 < 1 || prm->cpu_lanes_i16 < 1) return fail(ctx, BATHGPU_EINVAL, "cpu lane counts must be positive");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ctx->flt_loaded = false;
+  ctx->flt = *prm;
+  const int W = (M + 127) / 128, P = (M + 63) / 64;
+  ctx->flt_W = W; ctx->flt_P = P;
+  const int nb = 128 * W, nw = 64 * P;                 // nodes per padded row
+  std::vector<uint8_t> hb((size_t)29 * nb, 255);
+  std::vector<int16_t> hw((size_t)29 * nw, -32768), ht((size_t)8 * nw, -32768);
+  for (int x = 0; x < 29; ++x)
+    for (int k = 1; k <= M; ++k) {
+      hb[(size_t)x * nb + (k - 1)] = rbv[(size_t)x * ld + k];
+      hw[(size_t)x * nw + (k - 1)] = rwv[(size_t)x * ld + k];
+    }
+  for (int t = 0; t < 8; ++t)
+    for (int k = 1; k <= M; ++k) {
+      // BM,MM,IM,DM act on the way INTO node k: source node k-1; the others are taken at node k itself
+      const int src = (t < 4) ? k - 1 : k;
+      ht[(size_t)t * nw + (k - 1)] = twv[(size_t)t * ld + src];
+    }
+  // lane constants of the D->D closure scan (orf_filters.cuh): nodes per lane = 2P
+  std::vector<int> dds((size_t)6 * 32, 0);
+  {
+    const int n = 2 * P;
+    auto tDD = [&](int k) -> long long { return (k >= 1 && k <= M) ? (long long)twv[(size_t)7 * ld + k] : -32768LL; };
+    std::vector<long long> T0(32, 0);
+    for (int lane = 0; lane < 32; ++lane) {
+      const int first = lane * n + 1;                  // first node of the lane
+      long long t = (lane > 0) ? tDD(first - 1) : 0;
+      for (int j = 0; j + 1 < n; ++j) t += tDD(first + j);
+      T0[lane] = t;
+      dds[(size_t)5 * 32 + lane] = (lane > 0) ? (int)tDD(first - 1) : 0;
+    }
+    std::vector<long long> cur(T0);
+    for (int s = 0; s < 5; ++s) {
+      const int d = 1 << s;
+      std::vector<long long> nx(cur);
+      for (int lane = 0; lane < 32; ++lane) {
+        dds[(size_t)s * 32 + lane] = (int)std::max(cur[lane], -(1LL << 28));
+        if (lane >= d) nx[lane] = cur[lane] + cur[lane - d];
+      }
+      cur.swap(nx);
+    }
+  }
+  if (ctx->f_rbv.reserve(hb.size()) != BATHGPU_OK || ctx->f_rwv.reserve(hw.size() * 2) != BATHGPU_OK ||
+      ctx->f_twv.reserve(ht.size() * 2) != BATHGPU_OK || ctx->f_ddsum.reserve(dds.size() * 4) != BATHGPU_OK)
+    return fail(ctx, BATHGPU_EMEM, "device allocation failed");
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->f_rbv.p, hb.data(), hb.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->f_rwv.p, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->f_twv.p, ht.data(), ht.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->f_ddsum.p, dds.data(), dds.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->flt_loaded = true;
+  return BATHGPU_OK;
+}
+
+extern "C" int bathgpu_upload_orfs(bathgpu_ctx *ctx, const uint8_t *residues, int64_t n)
+{
+  if (!ctx || !residues || n < 1) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_upload_orfs");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (ctx->residues.reserve((size_t)n + 64) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->residues.p, residues, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->nres = n;
+  return BATHGPU_OK;
+}
+
+static int stage_orfs(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n, int max_wins)
+{
+  if (!ctx->flt_loaded) return fail(ctx, BATHGPU_EINVAL, "filter profile not loaded");
+  if (ctx->nres == 0)   return fail(ctx, BATHGPU_EINVAL, "no ORF residues uploaded");
+  for (int o = 0; o < n; ++o)
+    if (orfs[o].L < 1 || orfs[o].offset < 0 || orfs[o].offset + orfs[o].L > ctx->nres)
+      return fail(ctx, BATHGPU_EINVAL, "ORF %d (offset %lld, L %d) is outside the uploaded residues (n=%lld)",
+                  o, (long long)orfs[o].offset, orfs[o].L, (long long)ctx->nres);
+  static_assert(sizeof(OrfDesc) == sizeof(bathgpu_orf), "descriptor layouts must agree");
+  static_assert(sizeof(WindowRec) == sizeof(bathgpu_orf_window), "window layouts must agree");
+  if (ctx->orfs.reserve((size_t)n * sizeof(OrfDesc)) != BATHGPU_OK || ctx->fsc.reserve((size_t)n * 4) != BATHGPU_OK ||
+      ctx->fst.reserve((size_t)n * 4) != BATHGPU_OK || ctx->counter.reserve(64) != BATHGPU_OK || ctx->fnw.reserve(64) != BATHGPU_OK ||
+      ctx->fwins.reserve((size_t)std::max(max_wins, 1) * sizeof(WindowRec)) != BATHGPU_OK)
+    return fail(ctx, BATHGPU_EMEM, "device allocation failed");
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->orfs.p, orfs, (size_t)n * sizeof(OrfDesc), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->fnw.p, 0, 4, ctx->stream));
+  return BATHGPU_OK;
+}
+
+static FilterArgs filter_args(bathgpu_ctx *ctx, int n, int max_wins)
+{
+  FilterArgs a{};
+  const bathgpu_filter_params &p = ctx->flt;
+  a.residues = ctx->residues.as<uint8_t>(); a.orfs = ctx->orfs.as<OrfDesc>(); a.norf = n; a.M = p.M;
+  a.rbv = ctx->f_rbv.as<uint32_t>(); a.rbv_bytes = ctx->f_rbv.as<uint8_t>(); a.rowwords_b = 32 * ctx->flt_W;
+  a.tbm_b = p.tbm_b; a.tec_b = p.tec_b; a.base_b = p.base_b; a.bias_b = p.bias_b; a.scale_b = p.scale_b;
+  a.rwv = ctx->f_rwv.as<uint32_t>(); a.twv = ctx->f_twv.as<uint32_t>(); a.ddsum = ctx->f_ddsum.as<int>(); a.rowwords_w = 32 * ctx->flt_P;
+  a.base_w = p.base_w; a.ddbound_w = p.ddbound_w; a.xw_E_move = p.xw_E_move; a.xw_E_loop = p.xw_E_loop; a.scale_w = p.scale_w;
+  a.lanes_u8 = p.cpu_lanes_u8; a.lanes_i16 = p.cpu_lanes_i16;
+  a.sc = ctx->fsc.as<float>(); a.status = ctx->fst.as<int>(); a.wins = ctx->fwins.as<WindowRec>(); a.nwins = ctx->fnw.as<int>();
+  a.max_wins = max_wins; a.counter = ctx->counter.as<int>();
+  return a;
+}
+
+template <int W, int MODE>
+static cudaError_t launch_msv(const FilterArgs &a, int sms, cudaStream_t s)
+{
+  const size_t smem = (size_t)29 * 32 * W * 4;
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msv_filter_kernel<W, MODE>, 128, smem);
+  const int grid = std::min((a.norf + 3) / 4, sms * std::max(nb, 1));
+  msv_filter_kernel<W, MODE><<<grid, 128, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+template <int MODE>
+static cudaError_t dispatch_msv(int W, const FilterArgs &a, int sms, cudaStream_t s)
+{
+  switch (W) {
+  case 1: return launch_msv<1, MODE>(a, sms, s);
+  case 2: return launch_msv<2, MODE>(a, sms, s);
+  case 3: return launch_msv<3, MODE>(a, sms, s);
+  default: return cudaErrorInvalidValue;
+  }
+}
+
+template <int P>
+static cudaError_t launch_vit(const FilterArgs &a, int sms, cudaStream_t s)
+{
+  const size_t smem = (size_t)(29 + 8) * 32 * P * 4;
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, vit_filter_kernel<P>, 128, smem);
+  const int grid = std::min((a.norf + 3) / 4, sms * std::max(nb, 1));
+  vit_filter_kernel<P><<<grid, 128, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+static cudaError_t dispatch_vit(int P, const FilterArgs &a, int sms, cudaStream_t s)
+{
+  switch (P) {
+  case 1: return launch_vit<1>(a, sms, s);
+  case 2: return launch_vit<2>(a, sms, s);
+  case 3: return launch_vit<3>(a, sms, s);
+  case 4: return launch_vit<4>(a, sms, s);
+  case 5: return launch_vit<5>(a, sms, s);
+  case 6: return launch_vit<6>(a, sms, s);
+  default: return cudaErrorInvalidValue;
+  }
+}
+
+static int fetch_windows(bathgpu_ctx *ctx, bathgpu_orf_window *wins, int max_wins, int *nwins)
+{
+  int nw = 0;
+  CUDA_TRY(ctx, cudaMemcpyAsync(&nw, ctx->fnw.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (nw > max_wins) return fail(ctx, BATHGPU_EINVAL, "window buffer too small: %d windows found, room for %d", nw, max_wins);
+  if (nw > 0) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(wins, ctx->fwins.p, (size_t)nw * sizeof(WindowRec), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    // the reference appends windows ORF by ORF in target order (src/p7_pipeline.c:1669-1680)
+    std::sort(wins, wins + nw, [](const bathgpu_orf_window &x, const bathgpu_orf_window &y) {
+      return x.orf != y.orf ? x.orf < y.orf : x.n < y.n; });
+  }
+  *nwins = nw;
+  return BATHGPU_OK;
+}
+
+static int finish_filter(bathgpu_ctx *ctx, int n, float *sc, int32_t *status, int launches)
+{
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  if (sc)     CUDA_TRY(ctx, cudaMemcpyAsync(sc, ctx->fsc.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (status) CUDA_TRY(ctx, cudaMemcpyAsync(status, ctx->fst.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+  ctx->last_launches = launches;
+  return BATHGPU_OK;
+}
+
+extern "C" int bathgpu_msv_orfs(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n, float *sc, int32_t *status)
+{
+  if (!ctx || !orfs || n < 1 || !sc || !status) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_msv_orfs");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int st = stage_orfs(ctx, orfs, n, 0);
+  if (st != BATHGPU_OK) return st;
+  FilterArgs a = filter_args(ctx, n, 0);
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  CUDA_TRY(ctx, dispatch_msv<0>(ctx->flt_W, a, ctx->prop.multiProcessorCount, ctx->stream));
+  return finish_filter(ctx, n, sc, status, 1);
+}
+
+extern "C" int bathgpu_ssv_windows(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n, bathgpu_orf_window *wins, int max_wins, int *nwins)
+{
+  if (!ctx || !orfs || n < 1 || !wins || max_wins < 1 || !nwins) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_ssv_windows");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int st = stage_orfs(ctx, orfs, n, max_wins);
+  if (st != BATHGPU_OK) return st;
+  FilterArgs a = filter_args(ctx, n, max_wins);
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  CUDA_TRY(ctx, dispatch_msv<1>(ctx->flt_W, a, ctx->prop.multiProcessorCount, ctx->stream));
+  if ((st = finish_filter(ctx, n, nullptr, nullptr, 1)) != BATHGPU_OK) return st;
+  return fetch_windows(ctx, wins, max_wins, nwins);
+}
+
+extern "C" int bathgpu_vit_orfs(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n, float *sc, int32_t *status,
+                                bathgpu_orf_window *wins, int max_wins, int *nwins)
+{
+  if (!ctx || !orfs || n < 1 || !sc || !status) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_vit_orfs");
+  bool any = false;
+  for (int o = 0; o < n; ++o) any = any || (orfs[o].flags & 1);
+  if (any && (!wins || max_wins < 1 || !nwins)) return fail(ctx, BATHGPU_EINVAL, "window output buffers are required when any ORF asks for windows");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int st = stage_orfs(ctx, orfs, n, any ? max_wins : 0);
+  if (st != BATHGPU_OK) return st;
+  FilterArgs a = filter_args(ctx, n, any ? max_wins : 0);
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  CUDA_TRY(ctx, dispatch_vit(ctx->flt_P, a, ctx->prop.multiProcessorCount, ctx->stream));
+  if ((st = finish_filter(ctx, n, sc, status, 1)) != BATHGPU_OK) return st;
+  if (nwins) *nwins = 0;
+  if (any) return fetch_windows(ctx, wins, max_wins, nwins);
   return BATHGPU_OK;
 }

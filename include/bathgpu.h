@@ -104,6 +104,54 @@ void        bathgpu_host_free(void *p);
  * order BM,MM,IM,DM,MD,MI,II,DD, SOURCE-node indexed (tfv[t][k] = exp(TSC(k,t)), 0 at k=M). */
 int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int nrows, const float *rfv, const float *tfv);
 
+/* ---- protein (ORF-stage) filter profile: the integer parts of P7_OPROFILE, un-striped ------------------- */
+/* Replaces reading om->rbv/rwv/twv in p7_MSVFilter / p7_ViterbiFilter (src/impl_sse/impl_sse.h:75-142).
+ * rbv: [29][M+1] uint8 match costs (column 0 unused); rwv: [29][M+1] int16 match scores;
+ * twv: [8][M+1] int16 transition scores, order BM,MM,IM,DM,MD,MI,II,DD, SOURCE-node indexed (0 .. M-1; column M = -32768).
+ * cpu_lanes_u8 / cpu_lanes_i16: bytes / words per SIMD vector of the CPU build whose window tie-breaks are to be
+ * reproduced (16 / 8 for SSE, 32 / 16 for AVX2; src/impl_sse/msvfilter.c:358-366, vitfilter.c:388-396). */
+typedef struct {
+  int32_t M;
+  int32_t tbm_b, tec_b, base_b, bias_b;       /* om->tbm_b, tec_b, base_b, bias_b */
+  float   scale_b;
+  int32_t base_w, ddbound_w;                  /* om->base_w, ddbound_w            */
+  int32_t xw_E_move, xw_E_loop;               /* om->xw[p7O_E][MOVE|LOOP]         */
+  float   scale_w;
+  int32_t cpu_lanes_u8, cpu_lanes_i16;
+} bathgpu_filter_params;
+
+int bathgpu_load_filter_profile(bathgpu_ctx *ctx, const bathgpu_filter_params *prm,
+                                const uint8_t *rbv, const int16_t *rwv, const int16_t *twv);
+
+/* One ORF of the uploaded residue buffer, with the per-length pieces of the score system the reference
+ * re-derives per ORF on the host (p7_oprofile_ReconfigLength, src/impl_sse/p7_oprofile.c:1261-1326) and the
+ * window thresholds (msvfilter.c:313, vitfilter.c:315-321), so that every float->integer rounding stays host-owned. */
+typedef struct {
+  int64_t offset;       /* index of the ORF's first residue in the residue buffer */
+  int32_t L;
+  uint8_t tjb_b;        /* unbiased_byteify(logf(3/(L+3)))                          */
+  uint8_t ssv_thresh;   /* sc_thresh of p7_SSVFilter_BATH (uint8, as the reference stores it) */
+  int16_t xw_move;      /* wordify(logf(pmove)), pmove = (2+nj)/(L+2+nj)            */
+  int16_t vit_thresh;   /* sc_thresh of p7_ViterbiFilter_BATH                       */
+  int16_t flags;        /* bit 0: emit windows from the Viterbi filter              */
+  int32_t ext_thresh;   /* sc_ext_thresh of p7_ViterbiFilter_BATH                   */
+} bathgpu_orf;
+
+/* P7_HMM_WINDOW fields the pipeline reads (src/p7_hmmwindow.c:83): target position n, model position k,
+ * diagonal length, score; orf = index of the ORF in the call. */
+typedef struct { int32_t orf, n, k, length; float score; } bathgpu_orf_window;
+
+/* residues: concatenated amino-acid codes (Easel digital alphabet, 0..28) of all ORFs of a block */
+int bathgpu_upload_orfs(bathgpu_ctx *ctx, const uint8_t *residues, int64_t n);
+
+/* a2: p7_MSVFilter over ORFs.  sc[n] nats (+inf with status eslERANGE on overflow, msvfilter.c:176-180). */
+int bathgpu_msv_orfs(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n, float *sc, int32_t *status);
+/* a3: p7_SSVFilter_BATH over ORFs: windows only (sorted by ORF, then target position). */
+int bathgpu_ssv_windows(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n, bathgpu_orf_window *wins, int max_wins, int *nwins);
+/* a4: p7_ViterbiFilter / p7_ViterbiFilter_BATH over ORFs: sc[n], status[n], and windows for ORFs with flags bit 0. */
+int bathgpu_vit_orfs(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n, float *sc, int32_t *status,
+                     bathgpu_orf_window *wins, int max_wins, int *nwins);
+
 /* ---- target block ------------------------------------------------------ */
 /* dsq: ESL_DSQ codes, dsq[1..n] valid (dsq[0], dsq[n+1] sentinels).  Packed to 4 bits/nt on device. */
 int bathgpu_upload_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_t n);

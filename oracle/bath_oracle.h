@@ -162,6 +162,33 @@ typedef struct {
   float  evparam[8];
 } BO_FS_OPROFILE;
 
+/* ---- "optimized" protein profile, UN-striped (impl_sse.h:75-142): byte costs for MSV/SSV, word scores
+ *      for the Viterbi filter, float odds ratios for Forward/Backward ---- */
+typedef struct {
+  int      M, L, mode, max_length;
+  float    nj;
+  /* MSV/SSV: uint8 costs */
+  uint8_t *rbv;        /* [Kp][M+1] biased match costs, column 0 = 255 */
+  uint8_t  tbm_b, tec_b, tjb_b, base_b, bias_b;
+  float    scale_b;
+  /* Viterbi filter: int16 scores */
+  int16_t *rwv;        /* [Kp][M+1] */
+  int16_t *twv;        /* [8][M+1] BM,MM,IM,DM,MD,MI,II,DD, source-node indexed */
+  int16_t  xw[4][2];   /* [E,N,J,C][MOVE,LOOP] */
+  int16_t  base_w, ddbound_w;
+  float    scale_w;
+  /* Forward/Backward: float odds ratios */
+  float   *rfv;        /* [Kp][M+1] */
+  float   *tfv;        /* [8][M+1] */
+  float    xf[4][2];
+  float    evparam[8];
+  float    compo[BO_K];
+} BO_OPROFILE;
+
+/* P7_HMM_WINDOW / P7_HMM_WINDOWLIST (src/hmmer.h, p7_hmmwindow.c:83) */
+typedef struct { int n, k, length, target_len, id; float score; } BO_WINDOW;
+typedef struct { BO_WINDOW *w; int count, nalloc; } BO_WINDOWLIST;
+
 /* ---- DP matrices ---- */
 typedef struct {
   int    M, L;
@@ -250,6 +277,26 @@ int bo_OATrace_Frameshift(const BO_FS_OPROFILE *om, const BO_MX *pp, const BO_MX
 
 /* ===== fs_null2.c (impl_sse/null2_fs.c) ===== */
 int bo_Null2_fs_ByExpectation(const BO_FS_OPROFILE *om, BO_MX *pp, float *null2 /* [Kp] */);
+
+/* ===== filters.c (impl_sse/p7_oprofile.c, msvfilter.c, ssvfilter.c, vitfilter.c) ===== */
+BO_OPROFILE *bo_oprofile_convert(const BO_PROFILE *gm);
+void   bo_oprofile_destroy(BO_OPROFILE *om);
+void   bo_oprofile_ReconfigLength(BO_OPROFILE *om, int L);
+void   bo_oprofile_ssv_scores(const BO_OPROFILE *om, uint8_t *arr /* [(M+1)*Kp] */);
+int    bo_SSVFilter(const uint8_t *dsq, int L, const BO_OPROFILE *om, float *ret_sc);
+int    bo_MSVFilter(const uint8_t *dsq, int L, const BO_OPROFILE *om, float *ret_sc);
+int    bo_MSVFilter_opt(const uint8_t *dsq, int L, const BO_OPROFILE *om, int use_ssv, float *ret_sc);
+int    bo_SSVFilter_BATH(const uint8_t *dsq, int L, BO_OPROFILE *om, const uint8_t *ssv_scores, float nullsc, double P,
+                         int lanes, BO_WINDOWLIST *wl);
+int    bo_ViterbiFilter(const uint8_t *dsq, int L, const BO_OPROFILE *om, float *ret_sc);
+int    bo_ViterbiFilter_BATH(const uint8_t *dsq, int L, const BO_OPROFILE *om, const uint8_t *ssv_scores, float filtersc, double P,
+                             int lanes, BO_WINDOWLIST *wl, float *ret_sc);
+void   bo_windowlist_reset(BO_WINDOWLIST *wl);
+void   bo_windowlist_free(BO_WINDOWLIST *wl);
+double bo_gumbel_invsurv(double p, double mu, double lambda);
+double bo_gumbel_surv(double x, double mu, double lambda);
+double bo_exp_surv(double x, double mu, double lambda);
+double bo_exp_logsurv(double x, double mu, double lambda);
 
 /* ===== batch.c (worker-thread pool over windows; src/bathsearch.c:814-844,1224) ===== */
 int bo_batch_ForwardParser_3Codons(const uint8_t *dsq, const int64_t *start, const int32_t *L, int n,

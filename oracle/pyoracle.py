@@ -54,6 +54,25 @@ class FS_OPROFILE(C.Structure):
                 ("evparam", C.c_float * 8)]
 
 
+class OPROFILE(C.Structure):
+    _fields_ = [("M", C.c_int), ("L", C.c_int), ("mode", C.c_int), ("max_length", C.c_int), ("nj", C.c_float),
+                ("rbv", C.POINTER(C.c_uint8)), ("tbm_b", C.c_uint8), ("tec_b", C.c_uint8), ("tjb_b", C.c_uint8),
+                ("base_b", C.c_uint8), ("bias_b", C.c_uint8), ("scale_b", C.c_float),
+                ("rwv", C.POINTER(C.c_int16)), ("twv", C.POINTER(C.c_int16)), ("xw", (C.c_int16 * 2) * 4),
+                ("base_w", C.c_int16), ("ddbound_w", C.c_int16), ("scale_w", C.c_float),
+                ("rfv", C.POINTER(C.c_float)), ("tfv", C.POINTER(C.c_float)), ("xf", (C.c_float * 2) * 4),
+                ("evparam", C.c_float * 8), ("compo", C.c_float * K)]
+
+
+class WINDOW(C.Structure):
+    _fields_ = [("n", C.c_int), ("k", C.c_int), ("length", C.c_int), ("target_len", C.c_int), ("id", C.c_int),
+                ("score", C.c_float)]
+
+
+class WINDOWLIST(C.Structure):
+    _fields_ = [("w", C.POINTER(WINDOW)), ("count", C.c_int), ("nalloc", C.c_int)]
+
+
 class MX(C.Structure):
     _fields_ = [("M", C.c_int), ("L", C.c_int), ("allocL", C.c_int), ("nscells", C.c_int),
                 ("dp", C.POINTER(C.c_float)), ("xmx", C.POINTER(C.c_float)), ("totscale", C.c_float),
@@ -123,6 +142,24 @@ def lib(native=False):
         "bo_OptimalAccuracy_Frameshift": (C.c_int, [P(FS_OPROFILE), P(MX), P(MX), fp]),
         "bo_OATrace_Frameshift": (C.c_int, [P(FS_OPROFILE), P(MX), P(MX), P(TRACE)]),
         "bo_Null2_fs_ByExpectation": (C.c_int, [P(FS_OPROFILE), P(MX), fp]),
+        "bo_oprofile_convert": (P(OPROFILE), [P(PROFILE)]),
+        "bo_oprofile_destroy": (None, [P(OPROFILE)]),
+        "bo_oprofile_ReconfigLength": (None, [P(OPROFILE), C.c_int]),
+        "bo_oprofile_ssv_scores": (None, [P(OPROFILE), u8p]),
+        "bo_SSVFilter": (C.c_int, [u8p, C.c_int, P(OPROFILE), fp]),
+        "bo_MSVFilter": (C.c_int, [u8p, C.c_int, P(OPROFILE), fp]),
+        "bo_MSVFilter_opt": (C.c_int, [u8p, C.c_int, P(OPROFILE), C.c_int, fp]),
+        "bo_SSVFilter_BATH": (C.c_int, [u8p, C.c_int, P(OPROFILE), u8p, C.c_float, C.c_double, C.c_int, P(WINDOWLIST)]),
+        "bo_ViterbiFilter": (C.c_int, [u8p, C.c_int, P(OPROFILE), fp]),
+        "bo_ViterbiFilter_BATH": (C.c_int, [u8p, C.c_int, P(OPROFILE), u8p, C.c_float, C.c_double, C.c_int,
+                                            P(WINDOWLIST), fp]),
+        "bo_windowlist_reset": (None, [P(WINDOWLIST)]),
+        "bo_windowlist_free": (None, [P(WINDOWLIST)]),
+        "bo_gumbel_invsurv": (C.c_double, [C.c_double, C.c_double, C.c_double]),
+        "bo_gumbel_surv": (C.c_double, [C.c_double, C.c_double, C.c_double]),
+        "bo_exp_surv": (C.c_double, [C.c_double, C.c_double, C.c_double]),
+        "bo_exp_logsurv": (C.c_double, [C.c_double, C.c_double, C.c_double]),
+        "bo_profile_ReconfigLength": (None, [P(PROFILE), C.c_int]),
         "bo_batch_ForwardParser_3Codons": (C.c_int, [u8p, P(C.c_int64), P(C.c_int32), C.c_int, P(FS_OPROFILE),
                                                      C.c_int, fp, P(C.c_int32)]),
         "bo_FLogsum": (C.c_float, [C.c_float, C.c_float]),
@@ -206,6 +243,11 @@ class Model:
         self.gm_fs3 = L.bo_fs_profile_config(self.hmm, self.bg, self.ct, 3, 100, LOCAL)
         self.om_fs5 = L.bo_fs_oprofile_convert(self.gm_fs5)
         self.om_fs3 = L.bo_fs_oprofile_convert(self.gm_fs3)
+        # protein profile for the ORF filters (src/bathsearch.c:794-796: p7_ProfileConfig(L=100, p7_LOCAL), p7_oprofile_Convert)
+        self.gm = L.bo_profile_config(self.hmm, self.bg, 100, LOCAL)
+        self.om = L.bo_oprofile_convert(self.gm)
+        self._ssv_scores = np.zeros((self.M + 1) * KP, np.uint8)
+        L.bo_oprofile_ssv_scores(self.om, u8ptr(self._ssv_scores))
 
     def rfv(self, which=3):
         om = (self.om_fs3 if which == 3 else self.om_fs5).contents
@@ -214,6 +256,17 @@ class Model:
     def tfv(self, which=3):
         om = (self.om_fs3 if which == 3 else self.om_fs5).contents
         return np.ctypeslib.as_array(om.tfv, shape=(8, om.M + 1))
+
+    def ssv_scores(self):
+        return self._ssv_scores
+
+    def om_tables(self):
+        """un-striped integer/float tables of the protein profile: rbv [Kp][M+1] u8, rwv [Kp][M+1] i16, twv [8][M+1] i16"""
+        o = self.om.contents
+        M = self.M
+        return (np.ctypeslib.as_array(o.rbv, shape=(KP, M + 1)), np.ctypeslib.as_array(o.rwv, shape=(KP, M + 1)),
+                np.ctypeslib.as_array(o.twv, shape=(8, M + 1)), np.ctypeslib.as_array(o.rfv, shape=(KP, M + 1)),
+                np.ctypeslib.as_array(o.tfv, shape=(8, M + 1)))
 
     def xf(self, which=3):
         om = (self.om_fs3 if which == 3 else self.om_fs5).contents
@@ -233,6 +286,19 @@ def batch_forward_parser(model, dsq, starts, lengths, nthreads=1):
     if rc != OK:
         raise RuntimeError(f"bo_batch_ForwardParser_3Codons: status {rc}")
     return sc, status
+
+
+_AA = {c: i for i, c in enumerate("ACDEFGHIKLMNPQRSTVWY-BJZOUX*~")}
+
+
+def digitize_amino(seq):
+    a = np.full(len(seq) + 2, 255, dtype=np.uint8)
+    a[1:-1] = [_AA[c] for c in seq.upper()]
+    return a
+
+
+def windows(wl):
+    return [(wl.w[z].n, wl.w[z].k, wl.w[z].length, wl.w[z].score) for z in range(wl.count)]
 
 
 def mx_xmx(mx):
