@@ -17,6 +17,7 @@ EXPORTS = [
     "bathgpu_host_alloc", "bathgpu_host_free", "bathgpu_fs_fetch_xrows",
     "bathgpu_fs_fetch_domain_matrices",
     "bathgpu_load_filter_profile", "bathgpu_upload_orfs", "bathgpu_msv_orfs", "bathgpu_ssv_windows", "bathgpu_vit_orfs",
+    "bathgpu_fwd_orfs",
 ]
 
 
@@ -105,6 +106,8 @@ def load():
     L.bathgpu_ssv_windows.argtypes = [vp, vp, C.c_int, vp, C.c_int, ip]
     L.bathgpu_vit_orfs.restype = C.c_int
     L.bathgpu_vit_orfs.argtypes = [vp, vp, C.c_int, fp, ip, vp, C.c_int, ip]
+    L.bathgpu_fwd_orfs.restype = C.c_int
+    L.bathgpu_fwd_orfs.argtypes = [vp, vp, C.c_int, C.c_float, fp, fp, ip]
     L.bathgpu_host_alloc.restype = vp
     L.bathgpu_host_alloc.argtypes = [C.c_size_t]
     L.bathgpu_host_free.restype = None
@@ -306,6 +309,13 @@ class Context:
         nw = C.c_int32()
         self._check(self.lib.bathgpu_vit_orfs(self.h, orfs.ctypes.data, n, _f(sc), _i(st), w.ctypes.data, max_wins, C.byref(nw)))
         return sc, st, w[: nw.value]
+
+    def fwd_orfs(self, orfs, nj=1.0, xfE=(0.5, 0.5)):
+        n = len(orfs)
+        sc, st = np.empty(n, np.float32), np.empty(n, np.int32)
+        xf = np.asarray(xfE, np.float32)
+        self._check(self.lib.bathgpu_fwd_orfs(self.h, orfs.ctypes.data, n, nj, _f(xf), _f(sc), _i(st)))
+        return sc, st
 
     def fs_domains(self, envs, xfE5=(1.0, 0.0), max_steps=None):
         n = len(envs)

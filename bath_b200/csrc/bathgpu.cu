@@ -1095,3 +1095,44 @@ extern "C" int bathgpu_vit_orfs(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n
   if (any) return fetch_windows(ctx, wins, max_wins, nwins);
   return BATHGPU_OK;
 }
+
+template <int J>
+static cudaError_t launch_orf_fwd(const OrfFwdArgs &a, int sms, cudaStream_t s)
+{
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, orf_forward_parser_kernel<J>, 32, 0);
+  orf_forward_parser_kernel<J><<<std::min(a.norf, sms * std::max(nb, 1)), 32, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+extern "C" int bathgpu_fwd_orfs(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n, float nj, const float xfE[2], float *fwdsc, int32_t *status)
+{
+  if (!ctx || !orfs || n < 1 || !xfE || !fwdsc || !status) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fwd_orfs");
+  if (!ctx->fs3.loaded) return fail(ctx, BATHGPU_EINVAL, "3-codon profile not loaded");
+  if (ctx->nres == 0)   return fail(ctx, BATHGPU_EINVAL, "no ORF residues uploaded");
+  for (int o = 0; o < n; ++o)
+    if (orfs[o].L < 1 || orfs[o].offset < 0 || orfs[o].offset + orfs[o].L > ctx->nres)
+      return fail(ctx, BATHGPU_EINVAL, "ORF %d is outside the uploaded residues", o);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (ctx->orfs.reserve((size_t)n * sizeof(OrfDesc)) != BATHGPU_OK || ctx->fsc.reserve((size_t)n * 4) != BATHGPU_OK ||
+      ctx->fst.reserve((size_t)n * 4) != BATHGPU_OK || ctx->counter.reserve(64) != BATHGPU_OK)
+    return fail(ctx, BATHGPU_EMEM, "device allocation failed");
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->orfs.p, orfs, (size_t)n * sizeof(OrfDesc), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
+  const FsProfileImage &im = ctx->fs3;
+  OrfFwdArgs a{};
+  a.emis = im.emis.as<float>(); a.cellc = im.cellc.as<float>(); a.residues = ctx->residues.as<uint8_t>();
+  a.orfs = ctx->orfs.p; a.orf_stride = (int)sizeof(OrfDesc); a.norf = n; a.mpad = im.mpad; a.nj = nj;
+  a.tEM = xfE[0]; a.tEL = xfE[1]; a.fwdsc = ctx->fsc.as<float>(); a.status = ctx->fst.as<int>(); a.counter = ctx->counter.as<int>();
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  const int sms = ctx->prop.multiProcessorCount;
+  cudaError_t e;
+  switch (im.J) {
+#define OF(J_) case J_: e = launch_orf_fwd<J_>(a, sms, ctx->stream); break;
+  OF(1) OF(2) OF(3) OF(4) OF(5) OF(6) OF(7) OF(8) OF(10) OF(12)
+#undef OF
+  default: e = cudaErrorInvalidValue;
+  }
+  CUDA_TRY(ctx, e);
+  return finish_filter(ctx, n, fwdsc, status, 1);
+}

@@ -332,3 +332,116 @@ __global__ void __launch_bounds__(FwdTune<J>::kThreads, FwdTune<J>::kMinBlocks) 
 }
 
 }  // namespace bathgpu
+
+// ---------------------------------------------------------------------------------------------
+// Protein Forward parser over ORFs: p7_ForwardParser (reference src/impl_sse/fwdback.c:132, engine :256-466),
+// the F3/F4 gate between the integer filters and the frameshift stage (src/p7_pipeline.c:1774-1789).
+// Same carried quantities as the frameshift parser -- W = entry value / tBM, I~ = I tIM / s(k+1), E = sum M Z --
+// with a one-row look-back; it reads the amino-acid rows (338 + x) of the SAME folded 3-codon emission table
+// and the same lane constants, because the frameshift profile's amino rows and transitions are the protein
+// profile's (src/modelconfig.c:343-352 vs :140-156).
+namespace bathgpu {
+
+struct OrfFwdArgs {
+  const float    *emis;        // 3-codon image; amino rows start at row 338
+  const float    *cellc;
+  const uint8_t  *residues;
+  const void     *orfs;        // OrfDesc[] (orf_filters.cuh): offset, L
+  int             orf_stride;
+  int             norf;
+  int             mpad;
+  float           nj;          // expected J uses of the protein profile (1 in bathsearch: multihit local)
+  float           tEM, tEL;
+  float          *fwdsc;
+  int            *status;
+  int            *counter;
+};
+
+template <int J>
+__global__ void __launch_bounds__(32) orf_forward_parser_kernel(OrfFwdArgs a)
+{
+  constexpr int VEC = VecOf<J>::V;
+  const int lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
+  FwdConsts<J> K;
+  load_fwd_consts<J>(a.cellc, lane, K);
+  const float *emis_lane = a.emis + (size_t)338 * a.mpad + lane * VEC;
+
+  for (;;) {
+    int o = 0;
+    if (lane == 0) o = atomicAdd(a.counter, 1);
+    o = __shfl_sync(full, o, 0);
+    if (o >= a.norf) break;
+    const char *od = reinterpret_cast<const char *>(a.orfs) + (size_t)o * a.orf_stride;
+    const long long off = *reinterpret_cast<const long long *>(od);
+    const int L = *reinterpret_cast<const int *>(od + 8);
+    const float pmove = (2.0f + a.nj) / ((float)L + 2.0f + a.nj);      // p7_oprofile_ReconfigRestLength (p7_oprofile.c:1312-1313)
+    const float ploop = 1.0f - pmove;
+
+    float W[J], It[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) { W[j] = pmove; It[j] = 0.f; }         // row 0: B = tNM, nothing else (:281-285)
+    float xN = 1.0f, xJ = 0.f, xC = 0.f, totscale = 0.f;
+
+    int chunk = -64;
+    unsigned myres = 0;
+    for (int i = 1; i <= L; ++i) {
+      if (i >= chunk + 32) { chunk = i; myres = (i + lane <= L) ? a.residues[off + i + lane - 1] : 0u; }
+      const unsigned x = __shfl_sync(full, myres, i - chunk);
+      float e[J], m[J];
+      load_emission_row<J, VEC>(emis_lane + (size_t)x * a.mpad, e);
+      float es = 0.f;
+#pragma unroll
+      for (int j = 0; j < J; ++j) { m[j] = W[j] * e[j]; es += m[j]; }
+      float xE = warp_allsum(es);
+
+      float av[J];
+      float A = 0.f;
+#pragma unroll
+      for (int j = 0; j < J; ++j) { av[j] = m[j] * K.md[j]; A = (j == 0) ? av[0] : fmaf(A, K.dd[j], av[j]); }
+#pragma unroll
+      for (int s = 0; s < 5; ++s) {
+        float up = __shfl_up_sync(full, A, 1 << s);
+        A = fmaf(K.bs[s], up, A);
+      }
+      float d = __shfl_up_sync(full, A, 1);
+      if (lane == 0) d = 0.f;
+
+      xN = xN * ploop;                                    // (:401-404)
+      xC = fmaf(xC, ploop, xE * a.tEM);
+      xJ = fmaf(xJ, ploop, xE * a.tEL);
+      float xB = fmaf(xJ, pmove, xN * pmove);
+
+      float ov[J];
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        float t = fmaf(m[j], K.mm[j], It[j]);
+        ov[j] = fmaf(d, K.dm[j], t);
+        if (j + 1 < J) d = fmaf(d, K.dd[j], av[j]);
+        It[j] = fmaf(It[j], K.ii[j], m[j] * K.mi[j]);
+      }
+      float oprev = __shfl_up_sync(full, ov[J - 1], 1);
+      if (lane == 0) oprev = 0.f;
+      W[0] = xB + oprev;
+#pragma unroll
+      for (int j = 1; j < J; ++j) W[j] = xB + ov[j - 1];
+
+      if (xE > 1.0e4f) {                                   // sparse rescaling (:407-423)
+        const float sf = 1.0f / xE;
+        xN *= sf; xC *= sf; xJ *= sf;
+#pragma unroll
+        for (int j = 0; j < J; ++j) { W[j] *= sf; It[j] *= sf; }
+        totscale += logf(xE);
+      }
+    }
+    int   st = 0;
+    float sc;
+    if (isnan(xC))                 { st = 16; sc = xC; }                 // (:447-449)
+    else if (L > 0 && xC == 0.0f)  { st = 16; sc = -INFINITY; }
+    else if (isinf(xC))            { st = 16; sc = xC; }
+    else sc = totscale + logf(xC * pmove);
+    if (lane == 0) { a.fwdsc[o] = sc; a.status[o] = st; }
+  }
+}
+
+}  // namespace bathgpu

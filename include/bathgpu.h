@@ -152,6 +152,12 @@ int bathgpu_ssv_windows(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n, bathgp
 int bathgpu_vit_orfs(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n, float *sc, int32_t *status,
                      bathgpu_orf_window *wins, int max_wins, int *nwins);
 
+/* a6: p7_ForwardParser over ORFs (src/impl_sse/impl_sse.h:488; call site src/p7_pipeline.c:1779): the protein
+ * Forward score in nats.  Uses the amino-acid rows and transitions of the loaded 3-codon frameshift profile, which
+ * are the protein profile's own (src/modelconfig.c:343-352); nj = expected J uses of the protein profile (1 for the
+ * multihit local mode bathsearch configures), xfE = {E->MOVE, E->LOOP} odds. */
+int bathgpu_fwd_orfs(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n, float nj, const float xfE[2], float *fwdsc, int32_t *status);
+
 /* ---- target block ------------------------------------------------------ */
 /* dsq: ESL_DSQ codes, dsq[1..n] valid (dsq[0], dsq[n+1] sentinels).  Packed to 4 bits/nt on device. */
 int bathgpu_upload_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_t n);

@@ -298,6 +298,9 @@ double bo_gumbel_surv(double x, double mu, double lambda);
 double bo_exp_surv(double x, double mu, double lambda);
 double bo_exp_logsurv(double x, double mu, double lambda);
 
+/* ===== orf_fwd.c (impl_sse/fwdback.c) ===== */
+int    bo_ForwardParser(const uint8_t *dsq, int L, const BO_OPROFILE *om, float *opt_sc);
+
 /* ===== batch.c (worker-thread pool over windows; src/bathsearch.c:814-844,1224) ===== */
 int bo_batch_ForwardParser_3Codons(const uint8_t *dsq, const int64_t *start, const int32_t *L, int n,
                                    const BO_FS_OPROFILE *om, int nthreads, float *sc, int32_t *status);

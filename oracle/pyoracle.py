@@ -153,6 +153,7 @@ def lib(native=False):
         "bo_ViterbiFilter": (C.c_int, [u8p, C.c_int, P(OPROFILE), fp]),
         "bo_ViterbiFilter_BATH": (C.c_int, [u8p, C.c_int, P(OPROFILE), u8p, C.c_float, C.c_double, C.c_int,
                                             P(WINDOWLIST), fp]),
+        "bo_ForwardParser": (C.c_int, [u8p, C.c_int, P(OPROFILE), fp]),
         "bo_windowlist_reset": (None, [P(WINDOWLIST)]),
         "bo_windowlist_free": (None, [P(WINDOWLIST)]),
         "bo_gumbel_invsurv": (C.c_double, [C.c_double, C.c_double, C.c_double]),

@@ -125,3 +125,33 @@ def test_filters_bit_exact(oracle, gpu_ctx, hmmfile, index, lanes):
     lib.bo_windowlist_free(C.byref(wl))
     assert n_vwin > 0 and n_swin > 0 and n_overflow > 0
     print(f"{hmmfile}[{index}] lanes={lanes}: {len(seqs)} ORFs, {n_overflow} MSV overflows, {n_vwin} Viterbi windows, {n_swin} SSV windows")
+
+
+@pytest.mark.parametrize("hmmfile,index", [("AMP_N.bhmm", 0), ("tRNA-synthetases.bhmm", 1), ("PTHR37536.bhmm", 0)])
+def test_protein_forward_parser(oracle, gpu_ctx, hmmfile, index):
+    """a6: p7_ForwardParser over ORFs, within 1e-3 nat of the oracle; statuses equal"""
+    po = oracle
+    lib = po.lib()
+    model = po.Model(common.golden(hmmfile), index)
+    rng = np.random.default_rng(9 + index)
+    seqs = make_orfs(rng, model, n_random=30, n_homolog=30)
+    gpu_ctx.load_fs_profile(3, model.rfv(3), model.tfv(3))
+    gpu_ctx.upload_orfs(np.concatenate(seqs))
+    from bath_b200 import capi
+    orfs = np.zeros(len(seqs), capi.orf_dtype)
+    off = 0
+    for t, s in enumerate(seqs):
+        orfs[t]["offset"], orfs[t]["L"] = off, len(s)
+        off += len(s)
+    sc, st = gpu_ctx.fwd_orfs(orfs, nj=1.0, xfE=(0.5, 0.5))
+    worst = 0.0
+    for t, s in enumerate(seqs):
+        d = np.concatenate([[255], s, [255]]).astype(np.uint8)
+        lib.bo_oprofile_ReconfigLength(model.om, len(s))
+        v = C.c_float()
+        ost = lib.bo_ForwardParser(po.u8ptr(d), len(s), model.om, C.byref(v))
+        assert st[t] == ost
+        if ost == 0:
+            worst = max(worst, abs(sc[t] - v.value))
+            assert abs(sc[t] - v.value) <= 1e-3, (t, len(s), sc[t], v.value)
+    print(f"{hmmfile}[{index}]: {len(seqs)} ORFs, max |dsc| = {worst:.2e} nat, max score {sc.max():.1f}")
