@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
 #include <vector>
 #include <string>
@@ -12,6 +13,7 @@
 
 #include "../../include/bathgpu.h"
 #include "fs_parser.cuh"
+#include "fs_parser_v3.cuh"
 #include "fs_backward.cuh"
 #include "fs_domain.cuh"
 #include "orf_filters.cuh"
@@ -406,7 +408,7 @@ extern "C" int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int n
 }
 
 // ---------------------------------------------------------------------------------------------
-// block upload: ESL_DSQ bytes -> 4-bit packed words, one guard word in front, eight behind
+// block upload: ESL_DSQ bytes -> 4-bit packed words, one guard word in front, 24 behind
 __global__ void pack_dna4_kernel(const uint8_t *__restrict__ dsq, long long n, uint32_t *__restrict__ out, long long nwords)
 {
   long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -426,7 +428,7 @@ extern "C" int bathgpu_upload_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_
 {
   if (!ctx || !dsq || n < 1) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_upload_block");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  const long long nwords = (n + 8 + 7) / 8 + 8;      // kernels prefetch up to 40 nt past a window
+  const long long nwords = (n + 8 + 7) / 8 + 24;     // kernels prefetch up to ~100 nt past a window
   if (ctx->dna_bytes.reserve((size_t)n + 2) != BATHGPU_OK || ctx->dna4.reserve((size_t)nwords * 4) != BATHGPU_OK)
     return fail(ctx, BATHGPU_EMEM, "device allocation failed for a %lld-nt block", (long long)n);
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dna_bytes.p, dsq, (size_t)n + 2, cudaMemcpyHostToDevice, ctx->stream));
@@ -448,9 +450,48 @@ static cudaError_t launch_fwd(const FsParserArgs &a, int grid, cudaStream_t s)
   return cudaGetLastError();
 }
 
+static int fwd_version()      // BATHGPU_FWD=1|3 picks a kernel generation for A/B runs (1: one row per block of code; default 3: the row-pair schedule)
+{
+  static const int v = [] { const char *e = getenv("BATHGPU_FWD"); int x = e ? atoi(e) : 3; return (x == 1) ? 1 : 3; }();
+  return v;
+}
+static bool use_fwd_v1() { return fwd_version() == 1; }
+
+template <int J, bool XMX>
+static cudaError_t launch_fwd3(const FsParserArgs &a, int grid, cudaStream_t s)
+{
+  fs3_forward_parser_kernel_v3<J, XMX><<<grid, 32, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
 template <bool XMX>
 static cudaError_t dispatch_fwd(int J, const FsParserArgs &a, int grid, cudaStream_t s)
 {
+  if (fwd_version() == 3) {
+    switch (J) {
+    case 1:  return launch_fwd3<1, XMX>(a, grid, s);
+    case 2:  return launch_fwd3<2, XMX>(a, grid, s);
+    case 3:  return launch_fwd3<3, XMX>(a, grid, s);
+    case 4:  return launch_fwd3<4, XMX>(a, grid, s);
+    case 5:  return launch_fwd3<5, XMX>(a, grid, s);
+    case 6:  return launch_fwd3<6, XMX>(a, grid, s);
+    case 7:  return launch_fwd3<7, XMX>(a, grid, s);
+    case 8:  return launch_fwd3<8, XMX>(a, grid, s);
+    case 10: return launch_fwd3<10, XMX>(a, grid, s);
+    case 12: return launch_fwd3<12, XMX>(a, grid, s);
+    default: return cudaErrorInvalidValue;
+    }
+  }
+  switch (J) {
+    case 2:  return launch_fwd2<2, XMX>(a, grid, s);
+    case 4:  return launch_fwd2<4, XMX>(a, grid, s);
+    case 6:  return launch_fwd2<6, XMX>(a, grid, s);
+    case 8:  return launch_fwd2<8, XMX>(a, grid, s);
+    case 10: return launch_fwd2<10, XMX>(a, grid, s);
+    case 12: return launch_fwd2<12, XMX>(a, grid, s);
+    default: return cudaErrorInvalidValue;
+    }
+  }
   switch (J) {
   case 1:  return launch_fwd<1, XMX>(a, grid, s);
   case 2:  return launch_fwd<2, XMX>(a, grid, s);
@@ -470,6 +511,7 @@ template <int J, bool XMX>
 static int fwd_occupancy()
 {
   int nb = 0;
+  if (fwd_version() == 3) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fs3_forward_parser_kernel_v3<J, XMX>, 32, 0); return nb; }
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fs3_forward_parser_kernel<J, XMX>, FwdTune<J>::kThreads, 0);
   return nb;
 }

@@ -1,0 +1,201 @@
+// fs_parser_v3.cuh -- frameshift Forward parser, row-pair schedule.
+//
+// Same recurrence, carried quantities and tables as fs_parser.cuh (read its header first).  What changes is
+// the schedule: DP rows i and i+1 depend only on rows <= i-1 (the quasi-codon look-back starts two rows
+// back: W(i+1) was finished by row i-1), so the two rows are computed in ONE basic block and the compiler
+// interleaves their instruction streams.  The per-row cost of this kernel is latency, not issue slots: each
+// row has two serial shuffle chains (the E sum and the D->D scan, ~140 cycles each); pairing rows overlaps
+// the chains of two rows inside one warp, which is worth more than the warps the extra registers cost.
+// The rescale test (xE > 1e4, fwdback_fs.c:472-496) is taken once per pair: if row i rescales, row i+1's
+// freshly computed values are scaled with everything else (they are linear in the state they were computed
+// from), then row i+1 is tested on its scaled xE exactly as the reference would see it.
+#pragma once
+#include "fs_parser.cuh"
+
+namespace bathgpu {
+
+struct RowOut { float xE, xN, xJ, xC, xB, scale; };
+
+// Row i without the rescale test and without the X-row store.
+template <int J, int VEC, int PH>
+__device__ __forceinline__ void fwd_row_compute(int i, int lane, FwdState<J> &S, const FwdConsts<J> &K,
+                                                const char *__restrict__ emis_lane, unsigned rowbytes, uint32_t cw,
+                                                float ploop, float pmove, float tEL, float tEM, RowOut &R)
+{
+  constexpr int P0 = PH, P1 = (PH + 3) & 3, P2 = (PH + 2) & 3, P3 = (PH + 1) & 3;
+  float e2[J], e3[J], e4[J], m[J];
+  load_emission_row<J, VEC>(reinterpret_cast<const float *>(emis_lane + (size_t)(cw & 511u) * rowbytes), e2);
+  load_emission_row<J, VEC>(reinterpret_cast<const float *>(emis_lane + (size_t)((cw >> 9) & 511u) * rowbytes), e3);
+  load_emission_row<J, VEC>(reinterpret_cast<const float *>(emis_lane + (size_t)(cw >> 18) * rowbytes), e4);
+
+  float es0 = 0.f, es1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    float t = S.W[P0][j] * e2[j];
+    t = fmaf(S.W[P1][j], e3[j], t);
+    t = fmaf(S.W[P2][j], e4[j], t);
+    m[j] = t;
+    if (j == 0) es0 = t; else if (j == 1) es1 = t; else if (j & 1) es1 += t; else es0 += t;
+  }
+  float xE = warp_allsum(J > 1 ? es0 + es1 : es0);
+
+  float a[J];
+  float A = 0.f;
+#pragma unroll
+  for (int j = 0; j < J; ++j) { a[j] = m[j] * K.md[j]; A = (j == 0) ? a[0] : fmaf(A, K.dd[j], a[j]); }
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    float up = __shfl_up_sync(0xffffffffu, A, 1 << s);
+    A = fmaf(K.bs[s], up, A);
+  }
+  float d = __shfl_up_sync(0xffffffffu, A, 1);
+  if (lane == 0) d = 0.f;
+
+  float xN = (i < 3) ? ((i >= 0) ? 1.0f : 0.0f) : S.xN[P3] * ploop;
+  float xJ = fmaf(S.xJ[P3], ploop, xE * tEL);
+  float xC = fmaf(S.xC[P3], ploop, xE * tEM);
+  float xB = fmaf(xJ, pmove, xN * pmove);
+
+  float o[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    float t = fmaf(m[j], K.mm[j], S.I[P0][j]);
+    o[j] = fmaf(d, K.dm[j], t);
+    if (j + 1 < J) d = fmaf(d, K.dd[j], a[j]);
+    S.I[P1][j] = fmaf(S.I[P0][j], K.ii[j], m[j] * K.mi[j]);
+  }
+  float oprev = __shfl_up_sync(0xffffffffu, o[J - 1], 1);
+  if (lane == 0) oprev = 0.f;
+  S.W[P2][0] = xB + oprev;
+#pragma unroll
+  for (int j = 1; j < J; ++j) S.W[P2][j] = xB + o[j - 1];
+  S.xN[P0] = xN; S.xJ[P0] = xJ; S.xC[P0] = xC;
+  R.xE = xE; R.xN = xN; R.xJ = xJ; R.xC = xC; R.xB = xB; R.scale = 1.0f;
+}
+
+template <int J>
+__device__ __forceinline__ void scale_state(FwdState<J> &S, float sf)
+{
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+#pragma unroll
+    for (int j = 0; j < J; ++j) { S.W[r][j] *= sf; S.I[r][j] *= sf; }
+    S.xN[r] *= sf; S.xJ[r] *= sf; S.xC[r] *= sf;
+  }
+}
+
+template <bool XMX>
+__device__ __forceinline__ void store_xrow(int i, int lane, const RowOut &R, float *__restrict__ xrow)
+{
+  if constexpr (XMX) {
+    if (lane == 0 && i >= 0) {
+      float2 *x2 = reinterpret_cast<float2 *>(xrow + (size_t)i * 6);
+      x2[0] = make_float2(R.xE, R.xN);
+      x2[1] = make_float2(R.xJ, R.xB);
+      x2[2] = make_float2(R.xC, R.scale);
+    }
+  }
+}
+
+// Rows i (phase PH) and i+1 (phase PH+1) in one block, then the rescale logic for both in order.
+template <int J, int VEC, int PH, bool XMX>
+__device__ __forceinline__ void fwd_row_pair(int i, int lane, FwdState<J> &S, const FwdConsts<J> &K,
+                                             const char *__restrict__ emis_lane, unsigned rowbytes, uint32_t cwA, uint32_t cwB,
+                                             float ploop, float pmove, float tEL, float tEM,
+                                             float &totscale, float *__restrict__ xrow)
+{
+  RowOut A, B;
+  fwd_row_compute<J, VEC, PH>(i, lane, S, K, emis_lane, rowbytes, cwA, ploop, pmove, tEL, tEM, A);
+  fwd_row_compute<J, VEC, PH + 1>(i + 1, lane, S, K, emis_lane, rowbytes, cwB, ploop, pmove, tEL, tEM, B);
+  if (A.xE > 1.0e4f || B.xE > 1.0e4f) {          // rare, warp-uniform
+    if (A.xE > 1.0e4f) {
+      const float sf = 1.0f / A.xE;
+      scale_state<J>(S, sf);                     // includes what row i+1 has just written
+      A.scale = A.xE; A.xN *= sf; A.xJ *= sf; A.xC *= sf; A.xB *= sf;
+      B.xE *= sf; B.xN *= sf; B.xJ *= sf; B.xC *= sf; B.xB *= sf;
+      totscale += logf(A.xE);
+      A.xE = 1.0f;
+    }
+    if (B.xE > 1.0e4f) {
+      const float sf = 1.0f / B.xE;
+      scale_state<J>(S, sf);
+      B.scale = B.xE; B.xN *= sf; B.xJ *= sf; B.xC *= sf; B.xB *= sf;
+      totscale += logf(B.xE);
+      B.xE = 1.0f;
+    }
+  }
+  store_xrow<XMX>(i, lane, A, xrow);
+  store_xrow<XMX>(i + 1, lane, B, xrow);
+}
+
+#ifndef BATHGPU_V3_WARPS
+// resident warps per SM the kernel is compiled for (register budget 65536/(32 n)); measured on B200 per J
+#define BATHGPU_V3_WARPS(J) ((J) <= 2 ? 20 : (J) == 3 ? 18 : (J) == 4 ? 16 : (J) == 5 ? 14 : (J) == 6 ? 11 : (J) == 7 ? 10 : (J) == 8 ? 9 : 8)
+#endif
+
+template <int J, bool XMX>
+__global__ void __launch_bounds__(32, BATHGPU_V3_WARPS(J)) fs3_forward_parser_kernel_v3(FsParserArgs a)
+{
+  constexpr int VEC = VecOf<J>::V;
+  const int lane = threadIdx.x & 31;
+
+  FwdConsts<J> K;
+  load_fwd_consts<J>(a.cellc, lane, K);
+  const char    *emis_lane = reinterpret_cast<const char *>(a.emis + lane * VEC);
+  const unsigned rowbytes  = (unsigned)a.mpad * 4u;
+
+  for (;;) {
+    int w = 0;
+    if (lane == 0) w = atomicAdd(a.counter, 1);
+    w = __shfl_sync(0xffffffffu, w, 0);
+    if (w >= a.nwin) break;
+
+    const WindowDesc wd = a.wins[w];
+    const int   L     = wd.L;
+    const float pmove = wd.pmove, ploop = wd.ploop;
+    float *xrow = nullptr;
+    if constexpr (XMX) xrow = a.xmx + (size_t)a.xoff[w] * 6;
+
+    FwdState<J> S;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int j = 0; j < J; ++j) { S.W[r][j] = 0.f; S.I[r][j] = 0.f; }
+      S.xN[r] = 0.f; S.xJ[r] = 0.f; S.xC[r] = 0.f;
+    }
+    float totscale = 0.f;
+
+    const int nq  = (L + 4) >> 2;
+    const int pad = 4 * nq - (L + 1);
+    long long nib = (wd.start - 1) + (long long)(lane - pad - 3) - 1 + 8;
+    uint32_t lo = __ldg(a.dna4 + (nib >> 3)), hi = __ldg(a.dna4 + (nib >> 3) + 1);
+    int i = -pad;
+
+    for (int q0 = 0; q0 < nq; q0 += 8) {
+      const uint32_t cwl = codon_word(lo, hi, (int)(nib & 7) * 4, i + lane, L);
+      nib += 32;
+      if (q0 + 8 < nq) { lo = __ldg(a.dna4 + (nib >> 3)); hi = __ldg(a.dna4 + (nib >> 3) + 1); }
+      const int qn = min(8, nq - q0);
+      for (int qq = 0; qq < qn; ++qq) {
+        const uint32_t c0 = __shfl_sync(0xffffffffu, cwl, qq * 4 + 0);
+        const uint32_t c1 = __shfl_sync(0xffffffffu, cwl, qq * 4 + 1);
+        const uint32_t c2 = __shfl_sync(0xffffffffu, cwl, qq * 4 + 2);
+        const uint32_t c3 = __shfl_sync(0xffffffffu, cwl, qq * 4 + 3);
+        fwd_row_pair<J, VEC, 0, XMX>(i, lane, S, K, emis_lane, rowbytes, c0, c1, ploop, pmove, a.tEL, a.tEM, totscale, xrow); i += 2;
+        fwd_row_pair<J, VEC, 2, XMX>(i, lane, S, K, emis_lane, rowbytes, c2, c3, ploop, pmove, a.tEL, a.tEM, totscale, xrow); i += 2;
+      }
+    }
+
+    {
+      float tot = S.xC[3] + S.xC[2] * ploop + S.xC[1] * ploop;
+      int   st  = 0;
+      float sc;
+      if (isnan(tot) || isinf(tot))  { st = 16; sc = tot; }
+      else if (L > 2 && tot == 0.0f) { st = 16; sc = -INFINITY; }
+      else sc = totscale + logf(tot * pmove);
+      if (lane == 0) { a.fwdsc[w] = sc; a.status[w] = st; }
+    }
+  }
+}
+
+}  // namespace bathgpu

@@ -11,7 +11,7 @@ for hmmfile, idx in [("AMP_N.bhmm",0), ("tRNA-synthetases.bhmm",0), ("tRNA-synth
     model = po.Model(common.golden(hmmfile), idx)
     ctx.load_fs_profile(3, model.rfv(3), model.tfv(3))
     rng = np.random.default_rng(1)
-    for Lw in (600, 1200):
+    for Lw in (1200,):
         nwin = 16384
         dsq = common.random_dna(rng, nwin * Lw)
         ctx.upload_block(dsq)
