@@ -483,16 +483,6 @@ static cudaError_t dispatch_fwd(int J, const FsParserArgs &a, int grid, cudaStre
     }
   }
   switch (J) {
-    case 2:  return launch_fwd2<2, XMX>(a, grid, s);
-    case 4:  return launch_fwd2<4, XMX>(a, grid, s);
-    case 6:  return launch_fwd2<6, XMX>(a, grid, s);
-    case 8:  return launch_fwd2<8, XMX>(a, grid, s);
-    case 10: return launch_fwd2<10, XMX>(a, grid, s);
-    case 12: return launch_fwd2<12, XMX>(a, grid, s);
-    default: return cudaErrorInvalidValue;
-    }
-  }
-  switch (J) {
   case 1:  return launch_fwd<1, XMX>(a, grid, s);
   case 2:  return launch_fwd<2, XMX>(a, grid, s);
   case 3:  return launch_fwd<3, XMX>(a, grid, s);
