@@ -51,6 +51,33 @@ struct FsOddsProfile {             // P7_FS_OPROFILE without the SIMD striping
   void convert(const FsProfile &gm);
 };
 
+// P7_OPROFILE's integer and float parts for the ORF stage, un-striped (src/impl_sse/p7_oprofile.c:667-985),
+// plus the P7_SCOREDATA pieces the pipeline reads (src/p7_scoredata.c:60-70, :296-375)
+struct ProteinProfile {
+  int   M = 0, max_length = -1;
+  float nj = 1.0f;
+  // generic profile (src/modelconfig.c:48-196): match log-odds and the specials that never change
+  std::vector<float> msc;          // [Kp][M+1]
+  float xsc_E_move = 0, xsc_E_loop = 0;
+  // bytes
+  float scale_b = 0;
+  int   base_b = 190, bias_b = 0, tbm_b = 0, tec_b = 0;
+  std::vector<uint8_t> rbv;        // [Kp][M+1]
+  // words
+  float scale_w = 0;
+  int   base_w = 12000, ddbound_w = -32768, xw_E_move = 0, xw_E_loop = 0;
+  std::vector<int16_t> rwv;        // [Kp][M+1]
+  std::vector<int16_t> twv;        // [8][M+1]
+  // score data
+  std::vector<float> prefix_lengths, suffix_lengths;   // [M+1]
+  void configure(const CoreModel &h, const NullModel &bg, const FsProfile &gm_fs, const FsOddsProfile &om_fs);
+  uint8_t unbiased_byteify(float sc) const;
+  uint8_t biased_byteify(float sc) const;
+  int16_t wordify(float sc) const;
+  uint8_t tjb_for_length(int L) const;      // p7_oprofile_ReconfigMSVLength
+  int16_t xw_move_for_length(int L) const;  // p7_oprofile_ReconfigRestLength
+};
+
 int   amino_code(char c);
 int   dna_code(char c);
 bool  genetic_code(int ct, uint8_t out[64]);

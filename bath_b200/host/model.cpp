@@ -17,6 +17,7 @@
 
 #include "../../include/bathhost.h"
 #include "host_internal.h"
+#include "model_internal.h"
 
 namespace bathhost {
 
@@ -436,6 +437,102 @@ void FsOddsProfile::convert(const FsProfile &gm)
   xfE_loop = expf(gm.xsc[PX_E][PX_LOOP]);
 }
 
+// ------------------------------------------------------------------------------------------
+// protein profile for the ORF filters
+
+uint8_t ProteinProfile::unbiased_byteify(float sc) const
+{
+  sc = -1.0f * roundf(scale_b * sc);
+  return (sc > 255.) ? 255 : (uint8_t) sc;
+}
+uint8_t ProteinProfile::biased_byteify(float sc) const
+{
+  sc = -1.0f * roundf(scale_b * sc);
+  uint8_t b = (sc > 255 - bias_b) ? 255 : (uint8_t) sc + bias_b;
+  return b;
+}
+int16_t ProteinProfile::wordify(float sc) const
+{
+  sc = roundf(scale_w * sc);
+  if (sc >= 32767.0) return 32767;
+  if (sc <= -32768.0) return -32768;
+  return (int16_t) sc;
+}
+uint8_t ProteinProfile::tjb_for_length(int L) const { return unbiased_byteify(logf(3.0f / (float) (L + 3))); }
+int16_t ProteinProfile::xw_move_for_length(int L) const
+{
+  const float pmove = (2.0f + nj) / ((float) L + 2.0f + nj);
+  return wordify(logf(pmove));
+}
+
+// The protein profile's match scores and transitions are the frameshift profile's amino rows and
+// transitions (same arithmetic, src/modelconfig.c:140-156 vs :343-352), so they are taken from there.
+void ProteinProfile::configure(const CoreModel &h, const NullModel &bg, const FsProfile &gm_fs, const FsOddsProfile &om_fs)
+{
+  (void) bg;
+  M = h.M; max_length = h.max_length; nj = 1.0f;
+  const size_t ld = (size_t) M + 1;
+  msc.assign((size_t) kKp * ld, kNegInf);
+  for (int x = 0; x < kKp; ++x)
+    for (int k = 1; k <= M; ++k) msc[(size_t) x * ld + k] = gm_fs.rsc[(size_t) (gm_fs.maxcodons + x) * ld + k];
+  xsc_E_move = gm_fs.xsc[PX_E][PX_MOVE];
+  xsc_E_loop = gm_fs.xsc[PX_E][PX_LOOP];
+
+  // bytes (mf_conversion, :773-812): the bias is the highest score of a canonical residue; insert scores are 0
+  float max = 0.0;
+  for (int x = 0; x < kK; ++x)
+    for (int k = 1; k <= M; ++k) if (msc[(size_t) x * ld + k] > max) max = msc[(size_t) x * ld + k];
+  scale_b = 3.0 / 0.69314718055994529;
+  base_b  = 190;
+  bias_b  = unbiased_byteify(-1.0 * max);
+  rbv.assign((size_t) kKp * ld, 255);
+  for (int x = 0; x < kKp; ++x)
+    for (int k = 1; k <= M; ++k) rbv[(size_t) x * ld + k] = biased_byteify(msc[(size_t) x * ld + k]);
+  tbm_b = unbiased_byteify(logf(2.0f / ((float) M * (float) (M + 1))));
+  tec_b = unbiased_byteify(logf(0.5f));
+
+  // words (vf_conversion, :826-921)
+  scale_w = 500.0 / 0.69314718055994529;
+  base_w  = 12000;
+  rwv.assign((size_t) kKp * ld, -32768);
+  for (int x = 0; x < kKp; ++x)
+    for (int k = 1; k <= M; ++k) rwv[(size_t) x * ld + k] = wordify(msc[(size_t) x * ld + k]);
+  static const int from[8] = { PT_BM, PT_MM, PT_IM, PT_DM, PT_MD, PT_MI, PT_II, PT_DD };
+  twv.assign(8 * ld, -32768);
+  for (int t = 0; t < 8; ++t)
+    for (int k = (t < 4 ? 0 : 1); k < M; ++k) {
+      int16_t v = wordify(gm_fs.tsc[(size_t) k * 8 + from[t]]);
+      const int16_t cap = (t == 6) ? -1 : 0;            // II may not cost 0 (:872-877)
+      if (t != 7 && v > cap) v = cap;
+      twv[(size_t) t * ld + k] = v;
+    }
+  xw_E_loop = wordify(xsc_E_loop);
+  xw_E_move = wordify(xsc_E_move);
+  ddbound_w = -32768;
+  for (int k = 2; k < M - 1; ++k) {
+    int dd = (int) wordify(gm_fs.tsc[(size_t) k * 8 + PT_DD]);
+    dd    += (int) wordify(gm_fs.tsc[(size_t) (k + 1) * 8 + PT_DM]);
+    dd    -= (int) wordify(gm_fs.tsc[(size_t) (k + 1) * 8 + PT_BM]);
+    if (dd > ddbound_w) ddbound_w = dd;
+  }
+
+  // prefix / suffix lengths (p7_scoredata.c:358-375) from the odds-ratio MI and II transitions
+  prefix_lengths.assign(ld, 0.0f);
+  suffix_lengths.assign(ld, 0.0f);
+  const float *t_mis = &om_fs.tfv[5 * ld], *t_iis = &om_fs.tfv[6 * ld];
+  float sum = 0;
+  for (int k = 1; k < M; ++k) {
+    if (t_mis[k] == 0) prefix_lengths[k] = 1;
+    else               prefix_lengths[k] = 1 + (int) (log(1e-7 / t_mis[k]) / log(t_iis[k]));
+    sum += prefix_lengths[k];
+  }
+  prefix_lengths[0] = prefix_lengths[M] = 0;
+  for (int k = 1; k < M; ++k) prefix_lengths[k] /= sum;
+  suffix_lengths[M] = prefix_lengths[M - 1];
+  for (int k = M - 1; k >= 1; --k) suffix_lengths[k] = suffix_lengths[k + 1] + prefix_lengths[k - 1];
+  for (int k = 2; k < M; ++k) prefix_lengths[k] += prefix_lengths[k - 1];
+}
+
 }  // namespace bathhost
 
 // ------------------------------------------------------------------------------------------
@@ -443,13 +540,6 @@ void FsOddsProfile::convert(const FsProfile &gm)
 
 using namespace bathhost;
 
-struct bathhost_model {
-  CoreModel     hmm;
-  NullModel     bg;
-  int           ct = 1;
-  FsProfile     gm3, gm5;
-  FsOddsProfile om3, om5;
-};
 
 static int open_nth(const char *path, int index, CoreModel &h)
 {
@@ -476,6 +566,7 @@ extern "C" int bathhost_model_read(const char *path, int index, int ct, bathhost
   m->gm5.configure(m->hmm, m->bg, gcode, 5);
   m->om3.convert(m->gm3);
   m->om5.convert(m->gm5);
+  m->prot.configure(m->hmm, m->bg, m->gm5, m->om5);
   *ret_model = m;
   return BATHHOST_OK;
 }
@@ -524,4 +615,22 @@ extern "C" void bathhost_length_model(int L_amino, float nj, float *pmove, float
   const float pm = (2.0f + nj) / ((float) L_amino + 2.0f + nj);
   if (pmove) *pmove = pm;
   if (ploop) *ploop = 1.0f - pm;
+}
+
+extern "C" int bathhost_model_filter_params(const bathhost_model *m, bathhost_filter_params *p)
+{
+  if (!m || !p) return BATHHOST_EINVAL;
+  const ProteinProfile &q = m->prot;
+  p->M = q.M; p->tbm_b = q.tbm_b; p->tec_b = q.tec_b; p->base_b = q.base_b; p->bias_b = q.bias_b; p->scale_b = q.scale_b;
+  p->base_w = q.base_w; p->ddbound_w = q.ddbound_w; p->xw_E_move = q.xw_E_move; p->xw_E_loop = q.xw_E_loop; p->scale_w = q.scale_w;
+  return BATHHOST_OK;
+}
+extern "C" const uint8_t *bathhost_model_rbv(const bathhost_model *m) { return m ? m->prot.rbv.data() : nullptr; }
+extern "C" const int16_t *bathhost_model_rwv(const bathhost_model *m) { return m ? m->prot.rwv.data() : nullptr; }
+extern "C" const int16_t *bathhost_model_twv(const bathhost_model *m) { return m ? m->prot.twv.data() : nullptr; }
+extern "C" void bathhost_orf_length_params(const bathhost_model *m, int L, uint8_t *tjb_b, int16_t *xw_move)
+{
+  if (!m) return;
+  if (tjb_b)   *tjb_b   = m->prot.tjb_for_length(L);
+  if (xw_move) *xw_move = m->prot.xw_move_for_length(L);
 }

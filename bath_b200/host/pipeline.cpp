@@ -1,0 +1,1060 @@
+// pipeline.cpp -- host side of the translated-search path: the stage-batched frameshift pipeline (libbathhost.so).
+//
+// Restates the control flow of p7_Pipeline_BATH / p7_pli_Frameshift (src/p7_pipeline.c:1583-1821, :1339-1522),
+// p7_domaindef_ByPosteriorHeuristics_Frameshift_BATH and rescore_isolated_domain_frameshift
+// (src/p7_domaindef.c:301-473, :993-1191), p7_pli_postDomainDef_Frameshift_BATH (src/p7_pipeline.c:1005-1144)
+// and the hit post-processing of bathsearch (src/bathsearch.c:869-921; src/p7_tophits.c:789-960), with every DP
+// call replaced by ONE batched call per stage into the device library (include/bathgpu.h) through a table
+// of function pointers.  P-values, thresholds, window merging, region heuristics, coordinates and hit records
+// are computed here exactly as the reference computes them; nothing in this file does dynamic programming
+// over model nodes except the 2-state bias filter (p7_bg_FilterScore), which the reference also runs on the host.
+//
+// Not restated yet ("next" rows): the standard-translation branch for windows the frameshift
+// arbitration rejects (src/p7_pipeline.c:1480-1511), and the stochastic-trace clustering of multi-domain regions
+// (src/p7_domaindef.c:411-451) -- such regions are rescored as one envelope and counted in the statistics.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/bathhost.h"
+#include "../../include/bathgpu.h"
+#include "host_internal.h"
+#include "model_internal.h"
+
+namespace bathhost {
+
+static const double kLog2 = 0.69314718055994529;
+static const float  kNegInfF = -std::numeric_limits<float>::infinity();
+
+// ------------------------------------------------------------------------------------------
+// p7_FLogsum (src/logsum.c:58-111)
+static float g_logsum[16000];
+static bool  g_logsum_ready = false;
+static void flogsum_init()
+{
+  if (g_logsum_ready) return;
+  for (int i = 0; i < 16000; ++i) g_logsum[i] = log(1. + exp((double) -i / 1000.f));
+  g_logsum_ready = true;
+}
+static float flogsum(float a, float b)
+{
+  const float mx = (a > b) ? a : b, mn = (a > b) ? b : a;
+  return (mn == kNegInfF || (mx - mn) >= 15.7f) ? mx : mx + g_logsum[(int) ((mx - mn) * 1000.f)];
+}
+
+// Easel statistics (esl_gumbel.c, esl_exponential.c; public Easel definitions)
+static double gumbel_surv(double x, double mu, double lambda)
+{
+  const double y = lambda * (x - mu), ey = -exp(-y);
+  return (fabs(ey) < 5e-9) ? -ey : 1 - exp(ey);
+}
+static double gumbel_invsurv(double p, double mu, double lambda)
+{
+  const double lp = (p < 5e-9) ? log(p) : log(-1. * log1p(-p));
+  return mu - (lp / lambda);
+}
+static double exp_surv(double x, double mu, double lambda)    { return (x < mu) ? 1.0 : exp(-lambda * (x - mu)); }
+static double exp_logsurv(double x, double mu, double lambda) { return (x < mu) ? 0.0 : -lambda * (x - mu); }
+
+// ------------------------------------------------------------------------------------------
+// null model with the 2-state bias filter (src/p7_bg.c:189-197, :356-384, :449-573; Easel esl_hmm.c)
+struct Background {
+  float f[kK];
+  float p1, omega;
+  float t[2][3], e[2][kK], eo[kKp][2], pi[2];
+
+  explicit Background(const NullModel &n) { for (int x = 0; x < kK; ++x) f[x] = n.f[x]; p1 = n.p1; omega = n.omega; }
+  void set_length(int L) { p1 = (float) L / (float) (L + 1); t[0][0] = p1; t[0][1] = 1.0f - p1; }
+  float null_one(int L) const { return (float) L * log(p1) + log(1. - p1); }
+  float fs_null_one(int La) const { float per_frame = (float) La * log(p1) + log(1. - p1); return per_frame + log(3.0); }
+
+  void set_filter(int M, const float *compo)
+  {
+    const float L0 = 400.0, L1 = (float) M / 8.0;
+    t[0][0] = L0 / (L0 + 1.0f); t[0][1] = 1.0f / (L0 + 1.0f); t[0][2] = 1.0f;
+    t[1][0] = 1.0f / (L1 + 1.0f); t[1][1] = L1 / (L1 + 1.0f); t[1][2] = 1.0f;
+    for (int x = 0; x < kK; ++x) { e[0][x] = f[x]; e[1][x] = compo[x]; }
+    pi[0] = 0.999; pi[1] = 0.001;
+    // esl_hmm_Configure: emission odds against the background; gap/'*'/'~' = 1; degenerates = summed e over summed f
+    for (int x = 0; x < kK; ++x) for (int k = 0; k < 2; ++k) eo[x][k] = e[k][x] / f[x];
+    for (int k = 0; k < 2; ++k) { eo[kK][k] = 1.0; eo[kKp - 2][k] = 1.0; eo[kKp - 1][k] = 1.0; }
+    static const int members[6][2] = { { 2, 11 }, { 7, 9 }, { 3, 13 }, { 8, 8 }, { 1, 1 }, { -1, -1 } };
+    for (int x = kK + 1; x <= kKp - 3; ++x)
+      for (int k = 0; k < 2; ++k) {
+        float num = 0.0f, den = 0.0f;
+        for (int y = 0; y < kK; ++y) {
+          const int *mb = members[x - kK - 1];
+          const bool in = (mb[0] < 0) || y == mb[0] || y == mb[1];
+          if (in) { num += e[k][y]; den += f[y]; }
+        }
+        eo[x][k] = (den > 0.0f) ? num / den : 0.0f;
+      }
+  }
+
+  // esl_hmm_Forward, 2 states, per-row rescaling by the row maximum
+  float hmm_forward(const uint8_t *dsq, int L) const
+  {
+    if (L == 0) return 0.0f;           // pi[M] is 0 in this model: log(0); never reached (L >= 1 everywhere it is called)
+    float prev[2], cur[2], logsc = 0;
+    float mx = 0.0;
+    for (int k = 0; k < 2; ++k) { prev[k] = eo[dsq[1]][k] * pi[k]; mx = std::max(prev[k], mx); }
+    for (int k = 0; k < 2; ++k) prev[k] /= mx;
+    logsc += log(mx);                  // accumulated in float as esl_hmm_Forward sums fwd->sc[]
+    std::vector<float> sc;
+    sc.reserve((size_t) L + 2);
+    sc.push_back((float) log(mx));
+    for (int i = 2; i <= L; ++i) {
+      mx = 0.0;
+      for (int k = 0; k < 2; ++k) {
+        cur[k] = 0.0;
+        for (int m = 0; m < 2; ++m) cur[k] += prev[m] * t[m][k];
+        cur[k] *= eo[dsq[i]][k];
+        mx = std::max(cur[k], mx);
+      }
+      for (int k = 0; k < 2; ++k) prev[k] = cur[k] / mx;
+      sc.push_back((float) log(mx));
+    }
+    float last = 0.0;
+    for (int m = 0; m < 2; ++m) last += prev[m] * t[m][2];
+    sc.push_back((float) log(last));
+    logsc = 0.0;
+    for (float v : sc) logsc += v;
+    return logsc;
+  }
+  float filter_score(const uint8_t *dsq, int L) const { return hmm_forward(dsq, L) + (float) L * logf(p1) + logf(1. - p1); }
+
+  // p7_bg_fs_FilterScore: three frames of the DNA window, canonical residues only
+  float fs_filter_score(const uint8_t *dna, int L, const uint8_t gcode[64]) const
+  {
+    std::vector<uint8_t> orf((size_t) L + 2);
+    float sum = kNegInfF;
+    for (int fr = 1; fr <= 3; ++fr) {
+      int j = 1;
+      for (int i = fr; i <= L - 2; i += 3) {
+        const uint8_t a = dna[i], b = dna[i + 1], c = dna[i + 2];
+        if (a < 4 && b < 4 && c < 4) {
+          const uint8_t aa = gcode[16 * a + 4 * b + c];
+          if (aa < kK) orf[j++] = aa;
+        }
+      }
+      const float sc = hmm_forward(orf.data(), j - 1);
+      sum = flogsum(sum, sc);
+    }
+    return sum + ((float) (L / 3) * logf(p1) + logf(1. - p1) + log(3.0));
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+struct Orf {
+  int start, end;            // nucleotide coordinates in the ORIENTED block, start < end
+  int frame;
+  long long offset;          // first residue in the block's residue buffer
+  int n;                     // residues
+  int window_idx = -1;       // orfsq->idx
+};
+
+struct OrfWin { int id, n, k, length; float score; };      // P7_HMM_WINDOW fields the pipeline reads
+struct DnaWin { long long n; int k, length; };
+
+struct Domain {
+  int   ienv, jenv, iali, jali, ihmm, jhmm;   // window-relative until post-processing
+  float envsc, oasc, domcorrection;
+  std::vector<bathgpu_trace_step> tr;          // positions relative to the window
+};
+
+struct Hit {
+  bathhost_hit pub;
+  double sortkey;
+  bool duplicate = false, reported = false;
+};
+
+struct Options {
+  double F1 = 0.02, F2 = 1e-3, F3 = 1e-5, F4 = 5e-4, E = 10.0;
+  int    min_orf = 20, block_length = 262144, lanes_u8 = 16, lanes_i16 = 8;
+  bool   do_bias = true, do_null2 = true, top = true, bottom = true;
+};
+
+}  // namespace bathhost
+
+using namespace bathhost;
+
+struct bathhost_search {
+  const bathhost_model *model;
+  bathhost_backend      be;
+  Options               opt;
+  Background            bg;
+  std::vector<float>    compo;
+  uint8_t               gcode[64];
+  bathhost_stats        st{};
+  std::vector<Hit>      hits;
+  std::string           err;
+  // the length model left in om_fs5 by the last thing that reconfigured it (src/p7_domaindef.c:324, :1018):
+  // p7_DomainDecoding_Frameshift reads its N/J/C loop odds (decoding_fs.c:309-349)
+  float                 om5_nj = 1.0f;
+  int                   om5_L = 100;
+  int64_t               nseqs = 0;
+
+  bathhost_search(const bathhost_model *m, const bathhost_backend &b) : model(m), be(b), bg(m->bg) {}
+};
+
+namespace {
+
+int fail(bathhost_search *s, int code, const std::string &msg) { s->err = msg; return code; }
+
+#define BE_TRY(s, call, what)                                                                   \
+  do { int st_ = (call); if (st_ != 0) return fail(s, st_, std::string(what) + " failed: " +    \
+       (s->be.last_error ? s->be.last_error(s->be.ctx) : "?")); } while (0)
+
+// Six-frame translation is done three frames at a time on the oriented block (bathsearch reverse-complements the
+// block itself, src/bathsearch.c:1087-1096).  ORFs are maximal stop-free runs of whole codons of at least min_len
+// residues, any codon may start one (Easel esl_gencode_ProcessStart/Piece/End with default options); a codon holding
+// a degenerate nucleotide translates to X.  Emitted in order of their last nucleotide, as a left-to-right scan ends them.
+void find_orfs(const uint8_t *dsq, int n, const uint8_t gcode[64], int min_len, std::vector<Orf> &orfs, std::vector<uint8_t> &res)
+{
+  orfs.clear(); res.clear();
+  struct Open { int start; std::vector<uint8_t> aa; };
+  Open fr[3];
+  for (int f = 0; f < 3; ++f) fr[f].start = -1;
+  auto close = [&](int f, int end) {
+    Open &o = fr[f];
+    if (o.start > 0 && (int) o.aa.size() >= min_len) {
+      Orf r; r.start = o.start; r.end = end; r.frame = f; r.offset = (long long) res.size(); r.n = (int) o.aa.size();
+      res.insert(res.end(), o.aa.begin(), o.aa.end());
+      orfs.push_back(r);
+    }
+    o.start = -1; o.aa.clear();
+  };
+  for (int i = 1; i + 2 <= n; ++i) {
+    const int f = (i - 1) % 3;
+    const uint8_t a = dsq[i], b = dsq[i + 1], c = dsq[i + 2];
+    uint8_t aa = 26;                                   // X
+    if (a < 4 && b < 4 && c < 4) aa = gcode[16 * a + 4 * b + c];
+    if (aa == kKp - 2) close(f, i - 1);                // stop codon ends the run before it
+    else { if (fr[f].start < 0) fr[f].start = i; fr[f].aa.push_back(aa); }
+  }
+  // runs still open at the end of the block end at their last whole codon, in frame order of their last nucleotide
+  int order[3] = { 0, 1, 2 };
+  auto last_end = [&](int f) { return fr[f].start < 0 ? -1 : fr[f].start + 3 * (int) fr[f].aa.size() - 1; };
+  std::sort(order, order + 3, [&](int x, int y) { return last_end(x) < last_end(y); });
+  for (int z = 0; z < 3; ++z) if (fr[order[z]].start > 0) close(order[z], last_end(order[z]));
+}
+
+void revcomp(std::vector<uint8_t> &d, int n)
+{
+  static const uint8_t comp[18] = { 3, 2, 1, 0, 4, 6, 5, 8, 7, 9, 10, 14, 13, 12, 11, 15, 16, 17 };
+  for (int i = 1, j = n; i <= j; ++i, --j) {
+    const uint8_t a = d[i], b = d[j];
+    d[i] = (b < 18) ? comp[b] : b;
+    d[j] = (a < 18) ? comp[a] : a;
+  }
+}
+
+// p7_pli_ComputeLocalCompo (src/p7_pipeline.c:427-458)
+void local_compo(const bathhost_model *m, const Background &bg, int k_start, int k_end, float *compo)
+{
+  const ProteinProfile &q = m->prot;
+  const int M = q.M;
+  int k_len = k_end - k_start + 1;
+  if (k_len < 20) { k_start -= (20 - k_len) / 2; k_end += (20 - k_len) / 2; }
+  k_start = std::max(1, k_start);
+  k_end   = std::min(M, k_end);
+  for (int x = 0; x < kK; ++x) compo[x] = 0.0f;
+  for (int k = k_start; k <= k_end; ++k)
+    for (int x = 0; x < kK; ++x) {
+      const float log_odds = ((float) q.base_b - (float) q.rbv[(size_t) x * (M + 1) + k]) / q.scale_b;
+      compo[x] += bg.f[x] * expf(log_odds);
+    }
+  float sum = 0.0f;                                  // esl_vec_FNorm
+  for (int x = 0; x < kK; ++x) sum += compo[x];
+  if (sum != 0.0f) for (int x = 0; x < kK; ++x) compo[x] /= sum;
+  else             for (int x = 0; x < kK; ++x) compo[x] = 1.0f / (float) kK;
+}
+
+int codon_index5(const uint8_t *dsq, int i, int c)      // quasi-codon of length c ending at i (src/p7_pipeline.c:819-871)
+{
+  for (int b = 0; b < c; ++b) if (dsq[i - b] >= 4) return c == 3 ? 1364 : (c == 2 || c == 4) ? 1365 : 1366;
+  const int x = dsq[i];
+  if (c == 1) return x * 341;
+  const int w = dsq[i - 1];
+  if (c == 2) return x * 341 + w * 85 + 1;
+  const int v = dsq[i - 2];
+  if (c == 3) return x * 341 + w * 85 + v * 21 + 2;
+  const int u = dsq[i - 3];
+  if (c == 4) return x * 341 + w * 85 + v * 21 + u * 5 + 3;
+  const int t = dsq[i - 4];
+  return x * 341 + w * 85 + v * 21 + u * 5 + t + 4;
+}
+
+enum { PXXx = 6, PXxX = 7, PxXX = 8 };
+enum { P__X = 0, PX__ = 1, PXX_ = 2, PX_X = 3, P_XX = 4, PXXxX = 10, PXxXX = 11, PxXXX = 12, PXXxxX = 13, PXxxXX = 14, PxxXXX = 15 };
+enum { TS_M = 1, TS_D = 2, TS_I = 3, TS_N = 5, TS_B = 6, TS_E = 7, TS_C = 8, TS_J = 10 };
+
+// p7_pli_computeAliScores_BATH (src/p7_pipeline.c:781-985): sum of emission and transition log-odds along the core of the trace
+float ali_score(const bathhost_model *m, const std::vector<bathgpu_trace_step> &tr, const uint8_t *dsq)
+{
+  const FsProfile &gm = m->gm5;
+  const int M = gm.M;
+  const size_t ld = (size_t) M + 1;
+  int z1 = 0, z2 = (int) tr.size() - 1;
+  while (z1 < (int) tr.size() && tr[z1].st != TS_M) ++z1;
+  while (z2 >= 0 && tr[z2].st != TS_M) --z2;
+  if (z1 > z2) return 0.0f;
+  auto amino_sc = [&](int k, int i, int c) {
+    const int ci = codon_index5(dsq, i, c);
+    const int aa = gm.codons[(size_t) k * gm.maxcodons + ci];
+    return gm.rsc[(size_t) (gm.maxcodons + aa) * ld + k];
+  };
+  auto tsc = [&](int k, int t) { return gm.tsc[(size_t) k * 8 + t]; };
+  std::vector<float> per;
+  int k = 0;
+  while (z1 <= z2) {
+    k = tr[z1].k;
+    if (tr[z1].st == TS_M) {
+      float v = amino_sc(k, tr[z1].i, tr[z1].c);
+      if (z1 > 0 && tr[z1 - 1].st == TS_I)      v += tsc(k - 1, PT_IM);
+      else if (z1 > 0 && tr[z1 - 1].st == TS_D) v += tsc(k - 1, PT_DM);
+      per.push_back(v);
+      k++; z1++;
+      while (z1 < z2 && tr[z1].st == TS_M) {
+        per.push_back(amino_sc(k, tr[z1].i, tr[z1].c) + tsc(k - 1, PT_MM));
+        k++; z1++;
+      }
+    } else if (tr[z1].st == TS_I) {
+      per.push_back(tsc(k, PT_MI));
+      z1++;
+      while (z1 < z2 && tr[z1].st == TS_I) { per.push_back(tsc(k, PT_II)); z1++; }
+    } else if (tr[z1].st == TS_D) {
+      per.push_back(tsc(k - 1, PT_MD));
+      k++; z1++;
+      while (z1 < z2 && tr[z1].st == TS_D) { per.push_back(tsc(k - 1, PT_DD)); k++; z1++; }
+    } else break;
+  }
+  float s = 0.0f;
+  for (float v : per) s += v;
+  return s;
+}
+
+// the alignment summary p7_alidisplay_fs_Create derives from a trace (src/p7_alidisplay.c:696-895): frameshifts,
+// stop codons, percent identity and the CIGAR string
+void summarize_alignment(const bathhost_model *m, const std::vector<bathgpu_trace_step> &tr, const uint8_t *dsq, bathhost_hit &h)
+{
+  const FsProfile &gm = m->gm5;
+  std::vector<const bathgpu_trace_step *> core;
+  for (const auto &s : tr) if (s.st == TS_M || s.st == TS_D || s.st == TS_I) core.push_back(&s);
+  std::string cigar;
+  int shifts = 0, stops = 0, exact = 0, n_count = 0;
+  char buf[32];
+  for (size_t z = 0; z < core.size(); ++z) {
+    const bathgpu_trace_step &s = *core[z];
+    const int nxt = (z + 1 < core.size()) ? core[z + 1]->st : TS_E;
+    if (s.st == TS_M) {
+      const int ci = codon_index5(dsq, s.i, s.c);
+      const int aa = gm.codons[(size_t) s.k * gm.maxcodons + ci];
+      const int indel = gm.indel_pos[(size_t) s.k * gm.maxcodons + ci];
+      if (aa == amino_code(m->hmm.consensus[s.k])) exact++;
+      if (s.c != 3) shifts++;
+      else if (indel == PXXx || indel == PXxX || indel == PxXX) stops++;
+      if (nxt != TS_M || s.c != 3) {
+        if (s.c == 3) n_count += 3;
+        else if (indel == PXX_ || indel == PXXxX || indel == PXXxxX) n_count += 2;
+        else if (indel == PX_X || indel == PX__ || indel == PXxXX || indel == PXxxXX) n_count += 1;
+        snprintf(buf, sizeof buf, "%dM", n_count); cigar += buf;
+        n_count = 0;
+        if (s.c == 1) cigar += "2B"; else if (s.c == 2) cigar += "1B"; else if (s.c == 4) cigar += "1F"; else if (s.c == 5) cigar += "2F";
+        if (indel == P__X || indel == PX_X || indel == PXXxX || indel == PXXxxX) n_count = 1;
+        if (indel == P_XX || indel == PXxXX || indel == PXxxXX) n_count = 2;
+        if (indel == PxXXX || indel == PxxXXX) n_count = 3;
+        if (nxt != TS_M && n_count > 0) { snprintf(buf, sizeof buf, "%dM", n_count); cigar += buf; n_count = 0; }
+      } else n_count += 3;
+    } else if (s.st == TS_I) {
+      const int ci = codon_index5(dsq, s.i, 3);
+      const int indel = gm.indel_pos[(size_t) s.k * gm.maxcodons + ci];
+      if (indel == PXXx || indel == PXxX || indel == PxXX) stops++;
+      n_count += 3;
+      if (nxt != TS_I) { snprintf(buf, sizeof buf, "%dI", n_count); cigar += buf; n_count = 0; }
+    } else {
+      n_count += 3;
+      if (nxt != TS_D) { snprintf(buf, sizeof buf, "%dD", n_count); cigar += buf; n_count = 0; }
+    }
+  }
+  h.shifts = shifts; h.stops = stops;
+  h.pid = core.empty() ? 0.0f : ((float) exact / (float) core.size()) * 100;
+  snprintf(h.cigar, sizeof h.cigar, "%s", cigar.c_str());
+}
+
+// ---- one oriented block ----------------------------------------------------------------------------------
+struct Block {
+  const uint8_t *dsq;        // oriented, 1..n with sentinels
+  int       n;               // dnasq->n
+  int       C;               // context carried over from the previous block (dnasq->C)
+  long long start;           // dnasq->start: original coordinate of oriented position 1
+  bool      complement;
+  int64_t   seqidx;
+  const char *name;
+  long long sq_len;          // full length of the source sequence
+};
+
+int run_block(bathhost_search *s, const Block &blk)
+{
+  const bathhost_model *m = s->model;
+  const ProteinProfile &q = m->prot;
+  const Options &opt = s->opt;
+  const int M = q.M;
+  const float *ev = m->hmm.evparam;
+  Background &bg = s->bg;
+  if (blk.n < 15) return 0;
+
+  std::vector<Orf> orfs;
+  std::vector<uint8_t> residues;
+  find_orfs(blk.dsq, blk.n, s->gcode, opt.min_orf, orfs, residues);
+  if (orfs.empty()) return 0;
+  s->st.n_orfs += (int64_t) orfs.size();
+  const int norf = (int) orfs.size();
+
+  BE_TRY(s, s->be.upload_block(s->be.ctx, blk.dsq, blk.n), "bathgpu_upload_block");
+  BE_TRY(s, s->be.upload_orfs(s->be.ctx, residues.data(), (int64_t) residues.size()), "bathgpu_upload_orfs");
+
+  auto orf_dsq = [&](const Orf &o, std::vector<uint8_t> &buf) {      // 1-based with sentinels, for the bias filter
+    buf.assign((size_t) o.n + 2, 255);
+    memcpy(buf.data() + 1, residues.data() + o.offset, (size_t) o.n);
+  };
+
+  // ---- stage 1: MSV over every ORF not wholly inside the overlap context (:1632-1652)
+  std::vector<int> live;
+  for (int i = 0; i < norf; ++i) {
+    const Orf &o = orfs[i];
+    const bool in_context = blk.complement ? ((blk.n - o.start + 1) < blk.C) : (o.end < blk.C);
+    if (!in_context && o.n > 0) live.push_back(i);
+  }
+  if (live.empty()) return 0;
+  std::vector<bathgpu_orf> desc(live.size());
+  for (size_t t = 0; t < live.size(); ++t) {
+    const Orf &o = orfs[live[t]];
+    bathgpu_orf &d = desc[t];
+    memset(&d, 0, sizeof d);
+    d.offset = o.offset; d.L = o.n;
+    d.tjb_b = q.tjb_for_length(o.n); d.xw_move = q.xw_move_for_length(o.n);
+  }
+  std::vector<float> usc(live.size());
+  std::vector<int32_t> ust(live.size());
+  BE_TRY(s, s->be.msv_orfs(s->be.ctx, desc.data(), (int) desc.size(), usc.data(), ust.data()), "bathgpu_msv_orfs");
+
+  struct Cand { int orf; float nullsc, usc, filtersc, vfsc; double P; bool need_vit; };
+  std::vector<Cand> cand;
+  std::vector<uint8_t> buf;
+  for (size_t t = 0; t < live.size(); ++t) {
+    const Orf &o = orfs[live[t]];
+    bg.set_length(o.n);
+    const float nullsc = bg.null_one(o.n);
+    float seqsc = (usc[t] - nullsc) / kLog2;
+    double P = gumbel_surv(seqsc, ev[EV_MMU], ev[EV_MLAMBDA]);
+    if (P > opt.F1) continue;
+    s->st.pos_past_msv += (int64_t) o.n * 3;
+    float filtersc = nullsc;
+    if (opt.do_bias) {                                  // (:1657-1663)
+      orf_dsq(o, buf);
+      filtersc = bg.filter_score(buf.data(), o.n);
+      seqsc = (usc[t] - filtersc) / kLog2;
+      P = gumbel_surv(seqsc, ev[EV_MMU], ev[EV_MLAMBDA]);
+      if (P > opt.F1) continue;
+    }
+    s->st.pos_past_bias += (int64_t) o.n * 3;
+    Cand c; c.orf = live[t]; c.nullsc = nullsc; c.usc = usc[t]; c.filtersc = filtersc; c.vfsc = kNegInfF; c.P = P; c.need_vit = (P > opt.F2);
+    cand.push_back(c);
+  }
+  if (cand.empty()) return 0;
+
+  // ---- stage 2: Viterbi filter with windows, or the SSV window finder for ORFs already below F2 (:1666-1680)
+  std::vector<OrfWin> hit_windows;                       // grouped by ORF in candidate order, target order inside
+  auto make_desc = [&](const Cand &c, bool windows) {
+    const Orf &o = orfs[c.orf];
+    bathgpu_orf d; memset(&d, 0, sizeof d);
+    d.offset = o.offset; d.L = o.n; d.tjb_b = q.tjb_for_length(o.n); d.xw_move = q.xw_move_for_length(o.n);
+    if (windows) {
+      float invP = gumbel_invsurv(opt.F2, ev[EV_VMU], ev[EV_VLAMBDA]);          // vitfilter.c:313-321
+      d.vit_thresh = (int16_t) ceil(((c.filtersc + kLog2 * invP + 3.0) * q.scale_w) - (float) q.xw_E_move - (float) d.xw_move + (float) q.base_w);
+      invP = gumbel_invsurv(opt.F2, ev[EV_MMU], ev[EV_MLAMBDA]);
+      d.ext_thresh = (int) ceil(((c.filtersc + kLog2 * invP + 3.0) * q.scale_b) + q.base_b + q.tec_b + d.tjb_b);
+      d.flags = 1;
+    } else {
+      // p7_SSVFilter_BATH recomputes null1 for the ORF and inverts F1 (msvfilter.c:302-314)
+      const float invP = gumbel_invsurv(opt.F1, ev[EV_MMU], ev[EV_MLAMBDA]);
+      d.ssv_thresh = (uint8_t) (int) ceil(((c.nullsc + (invP * kLog2) + 3.0) * q.scale_b) + q.base_b + q.tec_b + d.tjb_b);
+    }
+    return d;
+  };
+  std::vector<int> vit_idx, ssv_idx;
+  for (size_t t = 0; t < cand.size(); ++t) (cand[t].need_vit ? vit_idx : ssv_idx).push_back((int) t);
+  std::vector<std::vector<OrfWin>> wins_of(cand.size());
+  if (!vit_idx.empty()) {
+    std::vector<bathgpu_orf> d(vit_idx.size());
+    for (size_t z = 0; z < vit_idx.size(); ++z) d[z] = make_desc(cand[vit_idx[z]], true);
+    std::vector<float> vsc(d.size());
+    std::vector<int32_t> vst(d.size());
+    int max_w = 0; for (auto &x : d) max_w += x.L / 2 + 4;
+    std::vector<bathgpu_orf_window> w((size_t) max_w);
+    int nw = 0;
+    BE_TRY(s, s->be.vit_orfs(s->be.ctx, d.data(), (int) d.size(), vsc.data(), vst.data(), w.data(), max_w, &nw), "bathgpu_vit_orfs");
+    for (size_t z = 0; z < vit_idx.size(); ++z) cand[vit_idx[z]].vfsc = vsc[z];
+    for (int x = 0; x < nw; ++x) wins_of[vit_idx[w[x].orf]].push_back(OrfWin{ 0, w[x].n, w[x].k, w[x].length, w[x].score });
+  }
+  if (!ssv_idx.empty()) {
+    std::vector<bathgpu_orf> d(ssv_idx.size());
+    for (size_t z = 0; z < ssv_idx.size(); ++z) d[z] = make_desc(cand[ssv_idx[z]], false);
+    int max_w = 0; for (auto &x : d) max_w += x.L / 2 + 4;
+    std::vector<bathgpu_orf_window> w((size_t) max_w);
+    int nw = 0;
+    BE_TRY(s, s->be.ssv_windows(s->be.ctx, d.data(), (int) d.size(), w.data(), max_w, &nw), "bathgpu_ssv_windows");
+    for (int x = 0; x < nw; ++x) wins_of[ssv_idx[w[x].orf]].push_back(OrfWin{ 0, w[x].n, w[x].k, w[x].length, w[x].score });
+  }
+
+  // ---- Viterbi decision, local-composition bias re-check (:1669-1718); ORFs that need a plain Viterbi re-run are batched
+  std::vector<int> keep;                                  // candidate indices that go on to Forward
+  std::vector<int> rerun;                                 // candidates needing p7_ViterbiFilter after the local bias raised filtersc
+  float lcompo[kK];
+  for (size_t t = 0; t < cand.size(); ++t) {
+    Cand &c = cand[t];
+    const Orf &o = orfs[c.orf];
+    if (c.need_vit) {
+      const float seqsc = (c.vfsc - c.filtersc) / kLog2;
+      c.P = gumbel_surv(seqsc, ev[EV_VMU], ev[EV_VLAMBDA]);
+      if (c.P > opt.F2) { wins_of[t].clear(); continue; }
+    }
+    s->st.pos_past_vit += (int64_t) o.n * 3;
+    bool dropped = false, need_rerun = false;
+    if (opt.do_bias && !wins_of[t].empty()) {
+      int k_max = wins_of[t][0].k, k_min = k_max - wins_of[t][0].length + 1;
+      for (size_t w = 1; w < wins_of[t].size(); ++w) {
+        k_max = std::max(k_max, wins_of[t][w].k);
+        k_min = std::min(k_min, wins_of[t][w].k - wins_of[t][w].length + 1);
+      }
+      local_compo(m, bg, k_min, k_max, lcompo);
+      bg.set_filter(M, lcompo);
+      bg.set_length(o.n);
+      orf_dsq(o, buf);
+      const float local_filtersc = bg.filter_score(buf.data(), o.n);
+      if (local_filtersc > c.filtersc) {
+        c.filtersc = local_filtersc;
+        if (c.vfsc == kNegInfF) {
+          const float seqsc = (c.usc - c.filtersc) / kLog2;
+          c.P = gumbel_surv(seqsc, ev[EV_MMU], ev[EV_MLAMBDA]);
+          if (c.P > opt.F2) need_rerun = true;
+        } else {
+          const float seqsc = (c.vfsc - c.filtersc) / kLog2;
+          c.P = gumbel_surv(seqsc, ev[EV_VMU], ev[EV_VLAMBDA]);
+          if (c.P > opt.F2) dropped = true;
+        }
+      }
+      bg.set_filter(M, s->compo.data());
+      bg.set_length(o.n);
+    }
+    if (dropped) { wins_of[t].clear(); continue; }
+    if (need_rerun) rerun.push_back((int) t); else keep.push_back((int) t);
+  }
+  if (!rerun.empty()) {
+    std::vector<bathgpu_orf> d(rerun.size());
+    for (size_t z = 0; z < rerun.size(); ++z) { d[z] = make_desc(cand[rerun[z]], true); d[z].flags = 0; }
+    std::vector<float> vsc(d.size());
+    std::vector<int32_t> vst(d.size());
+    int nw = 0;
+    BE_TRY(s, s->be.vit_orfs(s->be.ctx, d.data(), (int) d.size(), vsc.data(), vst.data(), nullptr, 0, &nw), "bathgpu_vit_orfs");
+    for (size_t z = 0; z < rerun.size(); ++z) {
+      Cand &c = cand[rerun[z]];
+      c.vfsc = vsc[z];
+      const float seqsc = (c.vfsc - c.filtersc) / kLog2;
+      c.P = gumbel_surv(seqsc, ev[EV_VMU], ev[EV_VLAMBDA]);
+      if (c.P > opt.F2) wins_of[rerun[z]].clear(); else keep.push_back(rerun[z]);
+    }
+    std::sort(keep.begin(), keep.end());
+  }
+  if (keep.empty()) return 0;
+
+  // ---- stage 3: protein Forward over the survivors (:1774-1789)
+  std::vector<double> P_orf((size_t) norf, 1.0);
+  std::vector<float>  fwdsc_orf((size_t) norf, kNegInfF);
+  {
+    std::vector<bathgpu_orf> d(keep.size());
+    for (size_t z = 0; z < keep.size(); ++z) d[z] = make_desc(cand[keep[z]], true);
+    std::vector<float> fsc(d.size());
+    std::vector<int32_t> fst(d.size());
+    const float xfE[2] = { expf(q.xsc_E_move), expf(q.xsc_E_loop) };
+    BE_TRY(s, s->be.fwd_orfs(s->be.ctx, d.data(), (int) d.size(), q.nj, xfE, fsc.data(), fst.data()), "bathgpu_fwd_orfs");
+    for (size_t z = 0; z < keep.size(); ++z) {
+      const Cand &c = cand[keep[z]];
+      const float seqsc = (fsc[z] - c.filtersc) / kLog2;
+      P_orf[c.orf] = exp_surv(seqsc, ev[EV_FTAU], ev[EV_FLAMBDA]);
+      fwdsc_orf[c.orf] = fsc[z] - c.nullsc;
+      for (const OrfWin &w : wins_of[keep[z]]) { OrfWin x = w; x.id = c.orf; hit_windows.push_back(x); }
+    }
+  }
+
+  // ---- p7_pli_BuildDNAWindows (:462-572)
+  std::vector<DnaWin> dwin;
+  for (int f = 0; f < norf; ++f) {
+    if (P_orf[f] > opt.F4) continue;
+    Orf &o = orfs[f];
+    int best = -1; float best_score = kNegInfF;
+    for (size_t w = 0; w < hit_windows.size(); ++w) {
+      if (hit_windows[w].id != f) continue;
+      if (hit_windows[w].score > best_score ||
+          (hit_windows[w].score == best_score && hit_windows[w].length > (best >= 0 ? hit_windows[best].length : 0))) {
+        best_score = hit_windows[w].score; best = (int) w;
+      }
+    }
+    OrfWin cw;
+    if (best >= 0) cw = hit_windows[best];
+    else if (o.n >= M) { cw.n = (o.n - M) / 2 + 1; cw.k = M; cw.length = M; }
+    else               { cw.n = 1; cw.k = M - ((M - o.n) / 2); cw.length = o.n; }
+    long long ws = cw.n - (q.max_length * (0.1 + q.prefix_lengths[cw.k - cw.length + 1])) + 1;
+    long long we = cw.n + cw.length + (q.max_length * (0.1 + q.suffix_lengths[cw.k])) - 2;
+    ws = std::min<long long>(0, ws);
+    we = std::max<long long>(o.n, we);
+    ws = std::max<long long>(1, o.start + ws * 3);       // (n - start_ref + 1) == o.start on the bottom strand
+    we = std::min<long long>(blk.n, o.start + we * 3);
+    dwin.push_back(DnaWin{ ws, cw.k, (int) (we - ws + 1) });
+    o.window_idx = (int) dwin.size() - 1;
+  }
+  if (dwin.empty()) return 0;
+  std::stable_sort(dwin.begin(), dwin.end(), [](const DnaWin &a, const DnaWin &b) { return a.n < b.n; });
+  {
+    size_t nh = 0;
+    for (size_t i = 1; i < dwin.size(); ++i) {
+      DnaWin &pw = dwin[nh];
+      const DnaWin &cw = dwin[i];
+      const long long ov_s = std::max(pw.n, cw.n), ov_e = std::min(pw.n + pw.length - 1, cw.n + cw.length - 1);
+      const long long ov_len = ov_e - ov_s + 1;
+      const long long w_s = std::min(pw.n, cw.n), w_e = std::max(pw.n + pw.length - 1, cw.n + cw.length - 1);
+      const long long w_len = w_e - w_s + 1;
+      if (((float) ov_len / std::min(pw.length, cw.length) > 0.0f) && w_len < (2 * (q.max_length * 3))) { pw.n = w_s; pw.length = (int) w_len; }
+      else { nh++; dwin[nh] = dwin[i]; }
+    }
+    dwin.resize(nh + 1);
+  }
+
+  // ---- stage 4: frameshift Forward parser over every DNA window (:1392-1454)
+  const int nwin = (int) dwin.size();
+  std::vector<bathgpu_window> gw((size_t) nwin);
+  for (int w = 0; w < nwin; ++w) {
+    gw[w].start = dwin[w].n; gw[w].L = dwin[w].length;
+    bathhost_length_model(dwin[w].length / 3, 1.0f, &gw[w].pmove, &gw[w].ploop);
+  }
+  const float xfE3[2] = { m->om3.xfE_move, m->om3.xfE_loop };
+  std::vector<float> fs_fwd((size_t) nwin);
+  std::vector<int32_t> fs_st((size_t) nwin);
+  BE_TRY(s, s->be.fs_fwd_windows(s->be.ctx, gw.data(), nwin, xfE3, fs_fwd.data(), fs_st.data()), "bathgpu_fs_fwd_windows");
+  s->st.n_windows += nwin;
+
+  for (int w = 0; w < nwin; ++w) {
+    const DnaWin &dw = dwin[w];
+    const uint8_t *wdsq = blk.dsq + dw.n - 1;            // window position p is wdsq[p]
+    int orf_cnt = 0, k_min = M, k_max = 0;
+    float tot_orfsc = kNegInfF;
+    double P_tot, P_min = std::numeric_limits<double>::infinity();
+    size_t last_h = 0;
+    for (int i = 0; i < norf; ++i) {
+      if (P_orf[i] > opt.F4) continue;
+      const Orf &o = orfs[i];
+      const bool inside = blk.complement ? (o.start >= dw.n && o.end <= dw.n + dw.length + 1)
+                                         : (o.start >= dw.n && o.end <= dw.n + dw.length - 1);
+      if (!inside) continue;
+      orfs[i].window_idx = w;
+      P_min = std::min(P_min, P_orf[i]);
+      tot_orfsc = flogsum(tot_orfsc, fwdsc_orf[i]);
+      orf_cnt++;
+      size_t h = last_h;
+      while (h < hit_windows.size() && hit_windows[h].id != i) h++;
+      if (h < hit_windows.size()) {
+        while (h < hit_windows.size() && hit_windows[h].id == i) {
+          k_min = std::min(k_min, hit_windows[h].k - hit_windows[h].length + 1);
+          k_max = std::max(k_max, hit_windows[h].k);
+          h++;
+        }
+        last_h = h;
+      }
+    }
+    P_tot = exp_surv(tot_orfsc / kLog2, ev[EV_FTAU], ev[EV_FLAMBDA]);
+
+    bg.set_length(dw.length / 3);
+    const float nullsc = bg.fs_null_one(dw.length / 3);
+    float filtersc = nullsc;
+    if (opt.do_bias) {
+      filtersc = bg.fs_filter_score(wdsq, dw.length, s->gcode);
+      if (k_min <= k_max) {
+        local_compo(m, bg, k_min, k_max, lcompo);
+        bg.set_filter(M, lcompo);
+        bg.set_length(dw.length / 3);
+        const float lf = bg.fs_filter_score(wdsq, dw.length, s->gcode);
+        if (lf > filtersc) filtersc = lf;
+        bg.set_filter(M, s->compo.data());
+        bg.set_length(dw.length / 3);
+      }
+    }
+    if (fs_st[w] != 0) continue;                          // eslERANGE from the Forward parser: treated as no score
+    const float fwdsc = fs_fwd[w];
+    const float seqscore = (fwdsc - filtersc) / kLog2;
+    const double P_fs   = exp_surv(seqscore, ev[EV_FTAUFS3], ev[EV_FLAMBDA]);
+    const double P_null = exp_surv((fwdsc - nullsc) / kLog2, ev[EV_FTAUFS3], ev[EV_FLAMBDA]);
+
+    if (P_fs <= opt.F3 && (P_null < P_tot || (P_null == P_tot && orf_cnt > 1) || P_min > opt.F3)) {
+      // ---- frameshift branch (:1465-1477)
+      s->st.pos_past_fwd += dw.length;
+      const float xf5_loop = 1.0f - (2.0f + s->om5_nj) / ((float) s->om5_L + 2.0f + s->om5_nj);
+      const float xf5[3] = { xf5_loop, xf5_loop, xf5_loop };
+      const int64_t off0 = 0;
+      std::vector<float> mocc((size_t) dw.length + 1), btot((size_t) dw.length + 1), etot((size_t) dw.length + 1);
+      float f2 = 0, b2 = 0; int32_t st2 = 0;
+      BE_TRY(s, s->be.fs_bck_decode(s->be.ctx, &gw[w], 1, xfE3, xf5, &off0, mocc.data(), btot.data(), etot.data(), &f2, &b2, &st2), "bathgpu_fs_bck_decode");
+      if (st2 != 0) continue;                             // backward underflow: skip domain definition (:1471)
+
+      // region finding (src/p7_domaindef.c:324-383).  The profile is switched to unihit at the saved length first.
+      const int saveL = 100;                              // gm_fs5->L: the dummy length bathsearch configures and never changes (src/bathsearch.c:797)
+      s->om5_nj = 0.0f; s->om5_L = saveL / 3;             // p7_fs_oprofile_ReconfigUnihit(om_fs5, saveL/3)
+      const int Lw = dw.length;
+      const float rt1 = 0.25f, rt2 = 0.10f, rt3 = 0.20f;
+      std::vector<std::pair<int, int>> envs;
+      {
+        int i = -1, d = 0; bool triggered = false, start = false, end = false;
+        for (int j = 1; j < Lw; ++j) {
+          if (!triggered) { if (mocc[j] >= rt1) triggered = true; d = j; }
+          else {
+            while (d > 1 && !start) {
+              d--;
+              if (d > 3 && mocc[d] - (btot[d] - btot[d - 3]) < rt2) { d--;
+                if (d > 3 && mocc[d] - (btot[d] - btot[d - 3]) < rt2) { d--;
+                  if (d > 3 && mocc[d] - (btot[d] - btot[d - 3]) < rt2) { d--; start = true; } } }
+            }
+            i = std::max(1, d - 3);
+            d = j + 1;
+            while (d < Lw && !end) {
+              d++;
+              if (d < Lw && mocc[d] - (etot[d] - etot[d - 3]) < rt2) { d++;
+                if (d < Lw && mocc[d] - (etot[d] - etot[d - 3]) < rt2) { d++;
+                  if (d < Lw && mocc[d] - (etot[d] - etot[d - 3]) < rt2) { d++; end = true; } } }
+            }
+            j = std::min(Lw, d + 3);
+            if (j - i + 1 >= 12) {
+              s->st.n_regions++;
+              // is_multidomain_region_frameshift (:684-714)
+              float mx = -1.0f;
+              auto scan = [&](int z0, int eoff, int f) {
+                for (int z = z0; z <= j - f; z += 3) {
+                  const float en = std::min(etot[z] - etot[i + eoff], btot[j - f] - btot[z - 3]);
+                  mx = std::max(mx, en);
+                }
+              };
+              scan(i + 2, -1, (j - i + 1) % 3);
+              scan(i + 3, 0, (j - i) % 3);
+              scan(i + 4, 1, (j - i - 1) % 3);
+              if (mx >= rt3) s->st.n_multidomain_regions++;      // rescored as ONE envelope (see the file header)
+              envs.emplace_back(i, j);
+            }
+            i = -1; triggered = false; start = false; end = false;
+          }
+        }
+      }
+      if (envs.empty()) continue;
+
+      // ---- per-envelope rescoring (rescore_isolated_domain_frameshift, :993-1191): one batched call
+      std::vector<bathgpu_envelope> ge;
+      std::vector<std::pair<int, int>> used;
+      for (auto &e : envs) {
+        const int Ld = e.second - e.first + 1;
+        if (Ld < 15) continue;
+        bathgpu_envelope g;
+        g.start = dw.n + e.first - 1; g.L = Ld;
+        bathhost_length_model(Ld / 3, 0.0f, &g.pmove, &g.ploop);
+        ge.push_back(g); used.push_back(e);
+        s->om5_nj = 0.0f; s->om5_L = Ld / 3;               // p7_fs_oprofile_ReconfigLength(om_fs5, Ld/3) (:1018)
+      }
+      if (ge.empty()) continue;
+      std::vector<bathgpu_domain_result> res(ge.size());
+      int64_t max_steps = 0; for (auto &g : ge) max_steps += g.L + M + 8;
+      std::vector<bathgpu_trace_step> traces((size_t) max_steps);
+      const float xfE5[2] = { 1.0f, 0.0f };
+      BE_TRY(s, s->be.fs_domains(s->be.ctx, ge.data(), (int) ge.size(), xfE5, res.data(), traces.data(), max_steps), "bathgpu_fs_domains");
+      s->st.n_envelopes += (int64_t) ge.size();
+
+      for (size_t e = 0; e < ge.size(); ++e) {
+        const int i = used[e].first, j = used[e].second, Ld = ge[e].L;
+        const bathgpu_domain_result &r = res[e];
+        if (r.status != 0 && r.trace_len == 0) continue;   // Forward/Backward range error: envelope dropped (:1022,1041)
+        bg.set_length(Ld / 3);
+        const float env_null = bg.fs_null_one(Ld / 3);
+        const float seqsc = (r.envsc - env_null) / kLog2;
+        const double P = exp_surv(seqsc, ev[EV_FTAUFS5], ev[EV_FLAMBDA]);
+        const double Z = (float) s->st.nres / (float) q.max_length;
+        if (P * Z > opt.E) continue;                         // early cut on the residues seen so far (:1033-1037)
+        if (r.status != 0) continue;
+
+        Domain dom;
+        dom.tr.assign(traces.begin() + r.trace_offset, traces.begin() + r.trace_offset + r.trace_len);
+        for (auto &ts : dom.tr) ts.i += i - 1;               // window coordinates (:1050-1051; every i >= 0 is shifted)
+        const float aliscore = ali_score(m, dom.tr, wdsq);
+        if (aliscore < 0.0f) continue;
+
+        // null2 correction along the trace (:1084-1142)
+        float domcorrection = 0.0f;
+        {
+          std::vector<float> n2((size_t) Lw + 2, 0.0f);
+          int t5 = -1, u5 = -1, v5 = -1, w5 = -1, x5 = -1;
+          size_t z = 0;
+          int pos = i;
+          auto cidx = [&](int c) {
+            long long ci;
+            if (c == 1)      { ci = (long long) x5 * 341;                                              return (int) std::min<long long>(ci, 1366); }
+            else if (c == 2) { ci = (long long) x5 * 341 + w5 * 85 + 1;                                return (int) std::min<long long>(ci, 1365); }
+            else if (c == 3) { ci = (long long) x5 * 341 + w5 * 85 + v5 * 21 + 2;                      return (int) std::min<long long>(ci, 1364); }
+            else if (c == 4) { ci = (long long) x5 * 341 + w5 * 85 + v5 * 21 + u5 * 5 + 3;             return (int) std::min<long long>(ci, 1365); }
+            ci = (long long) x5 * 341 + w5 * 85 + v5 * 21 + u5 * 5 + t5 + 4;                           return (int) std::min<long long>(ci, 1366);
+          };
+          const FsProfile &gm = m->gm5;
+          while (pos <= j && z < dom.tr.size()) {
+            x5 = (wdsq[pos] < 4) ? wdsq[pos] : 1367;
+            const bathgpu_trace_step &ts = dom.tr[z];
+            switch (ts.st) {
+            case TS_N: case TS_C: case TS_J:
+              n2[pos] = 0.0f;
+              if (ts.i == pos && pos > i + 1) pos++;
+              z++; break;
+            case TS_M:
+              if (ts.i == pos) {
+                int ci = cidx(ts.c);
+                if (ci < 0) ci = 0;                          // a look-back before the envelope start holds -1 in the reference too
+                n2[pos] = logf(r.null2[gm.codons[(size_t) ts.k * gm.maxcodons + ci]]);
+                if (n2[pos] == kNegInfF) n2[pos] = 0.0f;
+                z++;
+              } else n2[pos] = 0.0f;
+              pos++; break;
+            case TS_I:
+              if (ts.i == pos) {
+                int ci = cidx(3);
+                if (ci < 0) ci = 0;
+                n2[pos] = logf(r.null2[gm.codons[(size_t) ts.k * gm.maxcodons + ci]]);
+                if (n2[pos] == kNegInfF) n2[pos] = 0.0f;
+                z++;
+              } else n2[pos] = 0.0f;
+              pos++; break;
+            default: z++; break;
+            }
+            t5 = u5; u5 = v5; v5 = w5; w5 = x5;
+          }
+          for (pos = i; pos <= j; ++pos) domcorrection += n2[pos];
+        }
+        dom.domcorrection = std::max(0.f, domcorrection);
+        int z1 = 0, z2 = (int) dom.tr.size() - 1;
+        while (z1 < (int) dom.tr.size() && dom.tr[z1].st != TS_M) ++z1;
+        while (z2 >= 0 && dom.tr[z2].st != TS_M) --z2;
+        if (z1 > z2) continue;
+        dom.iali = dom.tr[z1].i - (dom.tr[z1].c - 1);
+        dom.jali = dom.tr[z2].i;
+        dom.ienv = i; dom.jenv = j;
+        dom.ihmm = dom.tr[z1].k; dom.jhmm = dom.tr[z2].k;
+        dom.envsc = r.envsc; dom.oasc = r.oasc;
+
+        // ---- p7_pli_postDomainDef_Frameshift_BATH (src/p7_pipeline.c:1005-1144)
+        const int ali_len = dom.jali - dom.iali + 1;
+        if (ali_len < 12) continue;
+        const int env_len = dom.jenv - dom.ienv + 1;
+        const int ml = q.max_length;
+        float bitscore = dom.envsc;
+        bitscore -= 2 * log(2. / ((env_len / 3.) + 2));
+        bitscore += 2 * log(2. / (ml + 2));
+        bitscore -= ((env_len - ali_len) / 3.) * log((float) (env_len / 3.) / (float) ((env_len / 3.) + 2));
+        bitscore += ((std::max(env_len, ml * 3) - ali_len) / 3.) * log((float) ml / (float) (ml + 2));
+        const float dom_bias = opt.do_null2 ? flogsum(0.0, log(bg.omega) + dom.domcorrection) : 0.0f;
+        const int nl = std::max(env_len / 3, ml);
+        bg.set_length(nl);
+        const float hit_null = bg.fs_null_one(nl);
+        const float dom_score = (bitscore - (hit_null + dom_bias)) / kLog2;
+        const double dom_lnP = exp_logsurv(dom_score, ev[EV_FTAUFS5], ev[EV_FLAMBDA]);
+        const double Z2 = (float) s->st.nres / (float) ml;
+        if (!(exp(dom_lnP) * Z2 <= opt.E)) continue;
+
+        Hit h;
+        memset(&h.pub, 0, sizeof h.pub);
+        auto orig = [&](int wpos) -> long long {            // window position -> coordinate on the source sequence
+          return blk.complement ? blk.start - (dw.n + wpos) + 2 : blk.start + dw.n + wpos - 2;
+        };
+        h.pub.seqidx = s->nseqs;
+        snprintf(h.pub.name, sizeof h.pub.name, "%s", blk.name ? blk.name : "");
+        h.pub.strand = blk.complement ? -1 : 1;
+        h.pub.env_from = orig(dom.ienv); h.pub.env_to = orig(dom.jenv);
+        h.pub.ali_from = orig(dom.iali); h.pub.ali_to = orig(dom.jali);
+        h.pub.hmm_from = dom.ihmm; h.pub.hmm_to = dom.jhmm;
+        h.pub.sq_len = blk.sq_len;
+        h.pub.score = dom_score; h.pub.bias = dom_bias; h.pub.lnP = dom_lnP;
+        h.pub.pre_score = bitscore / kLog2;
+        h.pub.envsc = dom.envsc; h.pub.oasc = dom.oasc;
+        h.pub.trace_len = (int32_t) dom.tr.size();
+        summarize_alignment(m, dom.tr, wdsq, h.pub);
+        h.sortkey = -dom_lnP;
+        s->hits.push_back(h);
+      }
+    } else {
+      s->st.n_std_windows++;      // standard-translation branch (:1480-1511): not restated yet
+    }
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+extern "C" int bathhost_search_create(const bathhost_model *m, const bathhost_backend *be, const bathhost_options *o, bathhost_search **ret)
+{
+  if (!m || !be || !ret) return BATHHOST_EINVAL;
+  *ret = nullptr;
+  if (!m->hmm.has_fs3 || !m->hmm.has_fs5 || !(m->hmm.fsprob > 0) || m->hmm.max_length < 1) return BATHHOST_EINVAL;   // src/bathsearch.c:747-759
+  flogsum_init();
+  bathhost_search *s = new (std::nothrow) bathhost_search(m, *be);
+  if (!s) return BATHHOST_EMEM;
+  if (o) {
+    if (o->F1 > 0) s->opt.F1 = o->F1;
+    if (o->F2 > 0) s->opt.F2 = o->F2;
+    if (o->F3 > 0) s->opt.F3 = o->F3;
+    if (o->F4 > 0) s->opt.F4 = o->F4;
+    if (o->E > 0)  s->opt.E = o->E;
+    if (o->min_orf_len > 0) s->opt.min_orf = o->min_orf_len;
+    if (o->block_length > 0) s->opt.block_length = o->block_length;
+    if (o->cpu_lanes_u8 > 0) s->opt.lanes_u8 = o->cpu_lanes_u8;
+    if (o->cpu_lanes_i16 > 0) s->opt.lanes_i16 = o->cpu_lanes_i16;
+    s->opt.do_bias = !o->no_bias; s->opt.do_null2 = !o->no_null2;
+    s->opt.top = !o->bottom_only; s->opt.bottom = !o->top_only;
+  }
+  if (!genetic_code(m->ct, s->gcode)) { delete s; return BATHHOST_EINVAL; }
+  s->compo.assign(m->hmm.compo, m->hmm.compo + kK);
+  s->bg.set_filter(m->hmm.M, s->compo.data());           // p7_pli_NewModel -> p7_bg_SetFilter(bg, om->M, om->compo)
+
+  // device images: the three profiles of a query
+  const int M = m->hmm.M;
+  int st;
+  if ((st = be->load_fs_profile(be->ctx, 3, M, m->om3.nrows, m->om3.rfv.data(), m->om3.tfv.data())) != 0 ||
+      (st = be->load_fs_profile(be->ctx, 5, M, m->om5.nrows, m->om5.rfv.data(), m->om5.tfv.data())) != 0) { delete s; return st; }
+  bathgpu_filter_params fp;
+  const ProteinProfile &q = m->prot;
+  fp.M = M; fp.tbm_b = q.tbm_b; fp.tec_b = q.tec_b; fp.base_b = q.base_b; fp.bias_b = q.bias_b; fp.scale_b = q.scale_b;
+  fp.base_w = q.base_w; fp.ddbound_w = q.ddbound_w; fp.xw_E_move = q.xw_E_move; fp.xw_E_loop = q.xw_E_loop; fp.scale_w = q.scale_w;
+  fp.cpu_lanes_u8 = s->opt.lanes_u8; fp.cpu_lanes_i16 = s->opt.lanes_i16;
+  if ((st = be->load_filter_profile(be->ctx, &fp, q.rbv.data(), q.rwv.data(), q.twv.data())) != 0) { delete s; return st; }
+  *ret = s;
+  return BATHHOST_OK;
+}
+
+extern "C" void bathhost_search_destroy(bathhost_search *s) { delete s; }
+extern "C" const char *bathhost_search_last_error(const bathhost_search *s) { return s ? s->err.c_str() : "no search"; }
+
+// One target sequence: dsq[1..n] (sentinels at 0 and n+1).  Read in blocks of block_length nucleotides that carry
+// max_length*3 nucleotides of left context (src/bathsearch.c:1060-1105), each searched on both strands.
+extern "C" int bathhost_search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, int64_t n)
+{
+  if (!s || !dsq || n < 1) return BATHHOST_EINVAL;
+  const int C = s->model->prot.max_length * 3;
+  const int W = s->opt.block_length;
+  int64_t pos = 1;                                         // first NEW residue of the next block
+  bool first = true;
+  while (pos <= n) {
+    const int64_t ctx = first ? 0 : std::min<int64_t>(C, pos - 1);
+    const int64_t b0 = pos - ctx, b1 = std::min<int64_t>(n, pos + W - 1);
+    const int bn = (int) (b1 - b0 + 1), bw = (int) (b1 - pos + 1);
+    if (bn >= 15) {
+      std::vector<uint8_t> blk((size_t) bn + 2, 255);
+      memcpy(blk.data() + 1, dsq + b0, (size_t) bn);
+      Block b; b.dsq = blk.data(); b.n = bn; b.C = (int) ctx; b.seqidx = s->nseqs; b.name = name; b.sq_len = n;
+      if (s->opt.top) {
+        s->st.nres += bw;
+        b.start = b0; b.complement = false;
+        int st = run_block(s, b);
+        if (st != 0) return st;
+      }
+      if (s->opt.bottom) {
+        s->st.nres += bw;
+        revcomp(blk, bn);
+        b.start = b1; b.complement = true;
+        int st = run_block(s, b);
+        if (st != 0) return st;
+      }
+    }
+    pos = b1 + 1;
+    first = false;
+  }
+  s->nseqs++;
+  s->st.nseqs = s->nseqs;
+  return BATHHOST_OK;
+}
+
+// E-values over the whole search space, duplicate removal, final ordering and reporting threshold
+// (src/bathsearch.c:869-921; src/p7_tophits.c:262-309, :789-960; src/p7_pipeline.c:584-602)
+extern "C" int bathhost_search_finish(bathhost_search *s)
+{
+  if (!s) return BATHHOST_EINVAL;
+  const int Wn = s->model->prot.max_length * 3;
+  for (Hit &h : s->hits) {
+    h.pub.lnP += log((float) s->st.nres / (float) Wn);
+    h.sortkey = -1.0 * h.pub.lnP;
+    h.pub.evalue = exp(h.pub.lnP);
+  }
+  // p7_tophits_SortBySeqidxAndAlipos: seqidx, plus strand first, start ascending, end descending
+  std::stable_sort(s->hits.begin(), s->hits.end(), [](const Hit &a, const Hit &b) {
+    if (a.pub.seqidx != b.pub.seqidx) return a.pub.seqidx < b.pub.seqidx;
+    const int da = a.pub.ali_from < a.pub.ali_to ? 1 : -1, db = b.pub.ali_from < b.pub.ali_to ? 1 : -1;
+    if (da != db) return da > db;
+    if (a.pub.ali_from != b.pub.ali_from) return a.pub.ali_from < b.pub.ali_from;
+    return a.pub.ali_to > b.pub.ali_to;
+  });
+  if (s->hits.size() > 1) {                                 // p7_tophits_RemoveDuplicates
+    size_t j = 0;
+    for (size_t i = 1; i < s->hits.size(); ++i) {
+      Hit &hj = s->hits[j], &hi = s->hits[i];
+      long long s_j = hj.pub.ali_from, e_j = hj.pub.ali_to, s_i = hi.pub.ali_from, e_i = hi.pub.ali_to;
+      const int dir_j = s_j < e_j ? 1 : -1, dir_i = s_i < e_i ? 1 : -1;
+      if (dir_j == -1) std::swap(s_j, e_j);
+      if (dir_i == -1) std::swap(s_i, e_i);
+      const long long len_j = e_j - s_j + 1, len_i = e_i - s_i + 1;
+      const long long is = std::max(s_i, s_j), ie = std::min(e_i, e_j), ilen = ie - is + 1;
+      const int hs = std::max(hi.pub.hmm_from, hj.pub.hmm_from), he = std::min(hi.pub.hmm_to, hj.pub.hmm_to), hlen = he - hs + 1;
+      const Hit &hp = s->hits[i - 1];
+      if (hi.pub.seqidx == hp.pub.seqidx && dir_i == dir_j && hlen > 0 &&
+          ((s_i >= s_j - 3 && s_i <= s_j + 3) || (e_i >= e_j - 3 && e_i <= e_j + 3) || (ilen >= len_i * 0.95) || (ilen >= len_j * 0.95))) {
+        const size_t remove = hi.pub.lnP < hj.pub.lnP ? j : i;
+        s->hits[remove].duplicate = true;
+        j = (remove == j ? i : j);
+      } else j = i;
+    }
+  }
+  // p7_tophits_SortBySortkey: sortkey descending, then name, strand, position
+  std::stable_sort(s->hits.begin(), s->hits.end(), [](const Hit &a, const Hit &b) {
+    if (a.sortkey != b.sortkey) return a.sortkey > b.sortkey;
+    const int c = strcmp(a.pub.name, b.pub.name);
+    if (c != 0) return c < 0;
+    const int da = a.pub.ali_from < a.pub.ali_to ? 1 : -1, db = b.pub.ali_from < b.pub.ali_to ? 1 : -1;
+    if (da != db) return da > db;
+    return a.pub.ali_from < b.pub.ali_from;
+  });
+  s->st.n_hits_reported = 0;
+  for (Hit &h : s->hits) {
+    h.reported = !h.duplicate && (exp(h.pub.lnP) <= s->opt.E);      // Z forced to 1 for reporting (src/bathsearch.c:920)
+    if (h.reported) s->st.n_hits_reported++;
+  }
+  return BATHHOST_OK;
+}
+
+extern "C" int bathhost_search_nhits(const bathhost_search *s) { return s ? (int) s->st.n_hits_reported : 0; }
+
+extern "C" int bathhost_search_get_hit(const bathhost_search *s, int idx, bathhost_hit *hit)
+{
+  if (!s || !hit || idx < 0) return BATHHOST_EINVAL;
+  int z = 0;
+  for (const Hit &h : s->hits) if (h.reported) { if (z == idx) { *hit = h.pub; return BATHHOST_OK; } ++z; }
+  return BATHHOST_EINVAL;
+}
+
+extern "C" int bathhost_search_get_stats(const bathhost_search *s, bathhost_stats *st)
+{
+  if (!s || !st) return BATHHOST_EINVAL;
+  *st = s->st;
+  return BATHHOST_OK;
+}

@@ -11,6 +11,10 @@ EXPORTS = [
     "bathhost_model_read", "bathhost_model_count", "bathhost_model_destroy", "bathhost_model_get_info",
     "bathhost_model_nrows", "bathhost_model_rfv", "bathhost_model_tfv", "bathhost_model_codons",
     "bathhost_model_indel_pos", "bathhost_model_mat", "bathhost_model_consensus", "bathhost_length_model",
+    "bathhost_model_filter_params", "bathhost_model_rbv", "bathhost_model_rwv", "bathhost_model_twv",
+    "bathhost_orf_length_params",
+    "bathhost_search_create", "bathhost_search_destroy", "bathhost_search_last_error", "bathhost_search_sequence",
+    "bathhost_search_finish", "bathhost_search_nhits", "bathhost_search_get_hit", "bathhost_search_get_stats",
 ]
 
 
@@ -18,6 +22,39 @@ class ModelInfo(C.Structure):
     _fields_ = [("M", C.c_int32), ("max_length", C.c_int32), ("codon_table", C.c_int32), ("fsprob", C.c_float),
                 ("evparam", C.c_float * 8), ("has_fs3_stats", C.c_int32), ("has_fs5_stats", C.c_int32),
                 ("name", C.c_char * 128), ("acc", C.c_char * 64)]
+
+
+class FilterParams(C.Structure):
+    _fields_ = [("M", C.c_int32), ("tbm_b", C.c_int32), ("tec_b", C.c_int32), ("base_b", C.c_int32), ("bias_b", C.c_int32),
+                ("scale_b", C.c_float), ("base_w", C.c_int32), ("ddbound_w", C.c_int32), ("xw_E_move", C.c_int32),
+                ("xw_E_loop", C.c_int32), ("scale_w", C.c_float)]
+
+
+class Backend(C.Structure):
+    """bathhost_backend: the device library as a table of function pointers (include/bathhost.h)"""
+    _names = ["last_error", "load_fs_profile", "load_filter_profile", "upload_block", "upload_orfs", "msv_orfs", "ssv_windows",
+              "vit_orfs", "fwd_orfs", "fs_fwd_windows", "fs_bck_decode", "fs_domains"]
+    _fields_ = [("ctx", C.c_void_p)] + [(n, C.c_void_p) for n in _names]
+
+
+class Options(C.Structure):
+    _fields_ = [("F1", C.c_double), ("F2", C.c_double), ("F3", C.c_double), ("F4", C.c_double), ("E", C.c_double),
+                ("min_orf_len", C.c_int32), ("block_length", C.c_int32), ("cpu_lanes_u8", C.c_int32), ("cpu_lanes_i16", C.c_int32),
+                ("no_bias", C.c_int32), ("no_null2", C.c_int32), ("top_only", C.c_int32), ("bottom_only", C.c_int32)]
+
+
+class Hit(C.Structure):
+    _fields_ = [("seqidx", C.c_int64), ("name", C.c_char * 64), ("strand", C.c_int32),
+                ("ali_from", C.c_int64), ("ali_to", C.c_int64), ("env_from", C.c_int64), ("env_to", C.c_int64), ("sq_len", C.c_int64),
+                ("hmm_from", C.c_int32), ("hmm_to", C.c_int32), ("evalue", C.c_double), ("lnP", C.c_double),
+                ("score", C.c_float), ("bias", C.c_float), ("pre_score", C.c_float), ("envsc", C.c_float), ("oasc", C.c_float),
+                ("pid", C.c_float), ("shifts", C.c_int32), ("stops", C.c_int32), ("trace_len", C.c_int32), ("cigar", C.c_char * 1024)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("nseqs", "nres", "pos_past_msv", "pos_past_bias", "pos_past_vit", "pos_past_fwd", "n_orfs",
+                                         "n_windows", "n_std_windows", "n_regions", "n_multidomain_regions", "n_envelopes",
+                                         "n_hits_reported")]
 
 
 _lib = None
@@ -50,6 +87,32 @@ def load():
     L.bathhost_model_mat.argtypes = [vp]
     L.bathhost_model_consensus.restype = C.c_char_p
     L.bathhost_model_consensus.argtypes = [vp]
+    L.bathhost_model_filter_params.restype = C.c_int
+    L.bathhost_model_filter_params.argtypes = [vp, C.POINTER(FilterParams)]
+    L.bathhost_model_rbv.restype = u8p
+    L.bathhost_model_rbv.argtypes = [vp]
+    L.bathhost_model_rwv.restype = C.POINTER(C.c_int16)
+    L.bathhost_model_rwv.argtypes = [vp]
+    L.bathhost_model_twv.restype = C.POINTER(C.c_int16)
+    L.bathhost_model_twv.argtypes = [vp]
+    L.bathhost_orf_length_params.restype = None
+    L.bathhost_orf_length_params.argtypes = [vp, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_int16)]
+    L.bathhost_search_create.restype = C.c_int
+    L.bathhost_search_create.argtypes = [vp, C.POINTER(Backend), C.POINTER(Options), C.POINTER(vp)]
+    L.bathhost_search_destroy.restype = None
+    L.bathhost_search_destroy.argtypes = [vp]
+    L.bathhost_search_last_error.restype = C.c_char_p
+    L.bathhost_search_last_error.argtypes = [vp]
+    L.bathhost_search_sequence.restype = C.c_int
+    L.bathhost_search_sequence.argtypes = [vp, C.c_char_p, u8p, C.c_int64]
+    L.bathhost_search_finish.restype = C.c_int
+    L.bathhost_search_finish.argtypes = [vp]
+    L.bathhost_search_nhits.restype = C.c_int
+    L.bathhost_search_nhits.argtypes = [vp]
+    L.bathhost_search_get_hit.restype = C.c_int
+    L.bathhost_search_get_hit.argtypes = [vp, C.c_int, C.POINTER(Hit)]
+    L.bathhost_search_get_stats.restype = C.c_int
+    L.bathhost_search_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.bathhost_length_model.restype = None
     L.bathhost_length_model.argtypes = [C.c_int, C.c_float, fp, fp]
     _lib = L
@@ -106,6 +169,25 @@ class QueryModel:
         flat = np.ctypeslib.as_array(self.lib.bathhost_model_indel_pos(self.h, which), shape=((self.M + 1) * (mc + 1),))
         return flat[: (self.M + 1) * mc].reshape(self.M + 1, mc)
 
+    def filter_params(self, cpu_lanes_u8=16, cpu_lanes_i16=8):
+        """dict in the shape capi.Context.load_filter_profile takes"""
+        p = FilterParams()
+        self.lib.bathhost_model_filter_params(self.h, C.byref(p))
+        d = {name: getattr(p, name) for name, _ in FilterParams._fields_}
+        d.update(cpu_lanes_u8=cpu_lanes_u8, cpu_lanes_i16=cpu_lanes_i16)
+        return d
+
+    def filter_tables(self):
+        M = self.M
+        return (np.ctypeslib.as_array(self.lib.bathhost_model_rbv(self.h), shape=(29, M + 1)),
+                np.ctypeslib.as_array(self.lib.bathhost_model_rwv(self.h), shape=(29, M + 1)),
+                np.ctypeslib.as_array(self.lib.bathhost_model_twv(self.h), shape=(8, M + 1)))
+
+    def orf_length_params(self, L):
+        a, b = C.c_uint8(), C.c_int16()
+        self.lib.bathhost_orf_length_params(self.h, int(L), C.byref(a), C.byref(b))
+        return a.value, b.value
+
     def mat(self):
         return np.ctypeslib.as_array(self.lib.bathhost_model_mat(self.h), shape=(self.M + 1, 20))
 
@@ -114,3 +196,88 @@ def length_model(L_amino, nj=1.0):
     pm, pl = C.c_float(), C.c_float()
     load().bathhost_length_model(int(L_amino), float(nj), C.byref(pm), C.byref(pl))
     return pm.value, pl.value
+
+
+_DNA = {c: i for i, c in enumerate("ACGT-RYMKSWHBVDN*~")}
+
+
+def digitize_dna(seq):
+    """Easel digital DNA: codes at [1..L], sentinel 255 at [0] and [L+1]"""
+    s = seq.upper().replace("U", "T").replace("X", "N")
+    a = np.full(len(s) + 2, 255, dtype=np.uint8)
+    a[1:-1] = [_DNA[c] for c in s]
+    return a
+
+
+def read_fasta(path):
+    out, name, buf = [], None, []
+    with open(path) as fh:
+        for line in fh:
+            line = line.rstrip("\n")
+            if line.startswith(">"):
+                if name is not None:
+                    out.append((name, "".join(buf)))
+                name, buf = line[1:].split(None, 1)[0], []
+            else:
+                buf.append(line.strip())
+    if name is not None:
+        out.append((name, "".join(buf)))
+    return out
+
+
+def backend_from(gpu_lib, ctx_handle):
+    """bathhost_backend over a loaded libbathgpu.so (ctypes CDLL) and a bathgpu_ctx handle"""
+    be = Backend()
+    be.ctx = ctx_handle
+    for n in Backend._names:
+        setattr(be, n, C.cast(getattr(gpu_lib, "bathgpu_" + n), C.c_void_p))
+    return be
+
+
+class Search:
+    """One query against target sequences: the stage-batched pipeline of bathsearch --fs (pipeline.cpp)."""
+
+    def __init__(self, model, gpu_ctx, **options):
+        self.lib = load()
+        self.model = model
+        self.gpu_ctx = gpu_ctx                       # keeps the device context alive
+        self.backend = backend_from(gpu_ctx.lib, gpu_ctx.h)
+        opt = Options(**options)
+        h = C.c_void_p()
+        st = self.lib.bathhost_search_create(model.h, C.byref(self.backend), C.byref(opt), C.byref(h))
+        if st != OK:
+            raise RuntimeError(f"bathhost_search_create: status {st}")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bathhost_search_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_sequence(self, name, dsq):
+        dsq = np.ascontiguousarray(dsq, np.uint8)
+        st = self.lib.bathhost_search_sequence(self.h, name.encode(), dsq.ctypes.data_as(C.POINTER(C.c_uint8)), len(dsq) - 2)
+        if st != OK:
+            raise RuntimeError(f"bathhost_search_sequence: status {st}: {self.lib.bathhost_search_last_error(self.h).decode()}")
+
+    def finish(self):
+        st = self.lib.bathhost_search_finish(self.h)
+        if st != OK:
+            raise RuntimeError(f"bathhost_search_finish: status {st}")
+        hits = []
+        for i in range(self.lib.bathhost_search_nhits(self.h)):
+            h = Hit()
+            self.lib.bathhost_search_get_hit(self.h, i, C.byref(h))
+            hits.append({n: (getattr(h, n).decode() if isinstance(getattr(h, n), bytes) else getattr(h, n)) for n, _ in Hit._fields_})
+        return hits
+
+    def stats(self):
+        s = Stats()
+        self.lib.bathhost_search_get_stats(self.h, C.byref(s))
+        return {n: getattr(s, n) for n, _ in Stats._fields_}

@@ -64,9 +64,87 @@ const uint8_t *bathhost_model_indel_pos(const bathhost_model *m, int which);
 const float *bathhost_model_mat(const bathhost_model *m);
 const char  *bathhost_model_consensus(const bathhost_model *m);
 
+/* Integer filter score systems of the protein profile (P7_OPROFILE, src/impl_sse/p7_oprofile.c:773-921), in the
+ * layout bathgpu_load_filter_profile takes: rbv [29][M+1] uint8, rwv [29][M+1] int16, twv [8][M+1] int16. */
+typedef struct {
+  int32_t M, tbm_b, tec_b, base_b, bias_b;
+  float   scale_b;
+  int32_t base_w, ddbound_w, xw_E_move, xw_E_loop;
+  float   scale_w;
+} bathhost_filter_params;
+int            bathhost_model_filter_params(const bathhost_model *m, bathhost_filter_params *p);
+const uint8_t *bathhost_model_rbv(const bathhost_model *m);
+const int16_t *bathhost_model_rwv(const bathhost_model *m);
+const int16_t *bathhost_model_twv(const bathhost_model *m);
+/* per-ORF-length integers: tjb_b = unbiased_byteify(logf(3/(L+3))), xw_move = wordify(logf((2+nj)/(L+2+nj)))
+ * (p7_oprofile_ReconfigLength, src/impl_sse/p7_oprofile.c:1261-1326) */
+void           bathhost_orf_length_params(const bathhost_model *m, int L, uint8_t *tjb_b, int16_t *xw_move);
+
 /* N/C/J move and loop odds for a target of L_amino residues with nj expected J uses
  * (multihit local: nj = 1; unihit: nj = 0), in float as the reference computes them. */
 void bathhost_length_model(int L_amino, float nj, float *pmove, float *ploop);
+
+/* ---- the stage-batched translated search (pipeline.cpp) -------------------------------------------------
+ * Restates p7_Pipeline_BATH + p7_pli_Frameshift + frameshift domain definition + hit post-processing
+ * (src/p7_pipeline.c:1583-1821, :1339-1522, :1005-1144; src/p7_domaindef.c:301-473, :993-1191;
+ * src/p7_tophits.c:789-960) around batched calls into the device library.  The device library is handed in as a
+ * table of function pointers with the signatures of include/bathgpu.h, so this library has no link-time dependency
+ * on CUDA. */
+
+typedef struct {
+  void *ctx;                                      /* bathgpu_ctx* */
+  const char *(*last_error)(const void *ctx);
+  int (*load_fs_profile)(void *ctx, int which, int M, int nrows, const float *rfv, const float *tfv);
+  int (*load_filter_profile)(void *ctx, const void *prm, const uint8_t *rbv, const int16_t *rwv, const int16_t *twv);
+  int (*upload_block)(void *ctx, const uint8_t *dsq, int64_t n);
+  int (*upload_orfs)(void *ctx, const uint8_t *residues, int64_t n);
+  int (*msv_orfs)(void *ctx, const void *orfs, int n, float *sc, int32_t *status);
+  int (*ssv_windows)(void *ctx, const void *orfs, int n, void *wins, int max_wins, int *nwins);
+  int (*vit_orfs)(void *ctx, const void *orfs, int n, float *sc, int32_t *status, void *wins, int max_wins, int *nwins);
+  int (*fwd_orfs)(void *ctx, const void *orfs, int n, float nj, const float xfE[2], float *fwdsc, int32_t *status);
+  int (*fs_fwd_windows)(void *ctx, const void *wins, int n, const float xfE[2], float *fwdsc, int32_t *status);
+  int (*fs_bck_decode)(void *ctx, const void *wins, int n, const float xfE[2], const float xf5_loop[3], const int64_t *out_offset,
+                       float *mocc, float *btot, float *etot, float *fwdsc, float *bcksc, int32_t *status);
+  int (*fs_domains)(void *ctx, const void *envs, int n, const float xfE5[2], void *results, void *traces, int64_t max_steps);
+} bathhost_backend;
+
+/* 0 / unset fields take bathsearch's defaults (src/p7_pipeline.c:145-214; src/bathsearch.c:94) */
+typedef struct {
+  double  F1, F2, F3, F4, E;
+  int32_t min_orf_len;        /* -l, 20 */
+  int32_t block_length;       /* 262144 */
+  int32_t cpu_lanes_u8, cpu_lanes_i16;   /* stripe geometry of the CPU build to match: 16/8 (SSE) */
+  int32_t no_bias, no_null2, top_only, bottom_only;
+} bathhost_options;
+
+typedef struct {
+  int64_t seqidx;
+  char    name[64];
+  int32_t strand;             /* +1 top, -1 bottom */
+  int64_t ali_from, ali_to, env_from, env_to, sq_len;
+  int32_t hmm_from, hmm_to;
+  double  evalue, lnP;
+  float   score, bias, pre_score, envsc, oasc, pid;
+  int32_t shifts, stops, trace_len;
+  char    cigar[1024];
+} bathhost_hit;
+
+typedef struct {
+  int64_t nseqs, nres;                                      /* "Target sequence(s)", "residues searched"      */
+  int64_t pos_past_msv, pos_past_bias, pos_past_vit, pos_past_fwd;   /* the footer's filter counters          */
+  int64_t n_orfs, n_windows, n_std_windows, n_regions, n_multidomain_regions, n_envelopes, n_hits_reported;
+} bathhost_stats;
+
+typedef struct bathhost_search bathhost_search;
+int  bathhost_search_create(const bathhost_model *m, const bathhost_backend *be, const bathhost_options *opt, bathhost_search **ret);
+void bathhost_search_destroy(bathhost_search *s);
+const char *bathhost_search_last_error(const bathhost_search *s);
+/* dsq[1..n] Easel digital nucleotides with sentinels at [0] and [n+1]; both strands unless restricted */
+int  bathhost_search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, int64_t n);
+int  bathhost_search_finish(bathhost_search *s);
+int  bathhost_search_nhits(const bathhost_search *s);
+int  bathhost_search_get_hit(const bathhost_search *s, int idx, bathhost_hit *hit);
+int  bathhost_search_get_stats(const bathhost_search *s, bathhost_stats *st);
 
 #ifdef __cplusplus
 }
