@@ -78,6 +78,7 @@ struct ProteinProfile {
   int16_t xw_move_for_length(int L) const;  // p7_oprofile_ReconfigRestLength
 };
 
+int   builder_max_length(const CoreModel &h, double emit_thresh);
 int   amino_code(char c);
 int   dna_code(char c);
 bool  genetic_code(int ct, uint8_t out[64]);

@@ -235,6 +235,50 @@ static int read_record(std::istream &in, CoreModel &h)
   return BATHHOST_OK;
 }
 
+// p7_Builder_MaxLength (src/p7_builder.c): the sequence length beyond which only a fraction <emit_thresh> of the
+// model's emitted sequences fall; bathsearch computes it when the file has no MAXL line (src/bathsearch.c:761-762).
+int builder_max_length(const CoreModel &h, double emit_thresh)
+{
+  const int M = h.M;
+  if (M == 1) return 1;
+  const int bound = std::max(M, std::min(20 * M, 100000));
+  auto T = [&](int k, int t) -> double { return h.t[(size_t) k * 7 + t]; };
+  std::vector<double> Mx[2], Ix[2], Dx[2];
+  for (int c = 0; c < 2; ++c) { Mx[c].assign(M + 2, 0.0); Ix[c].assign(M + 2, 0.0); Dx[c].assign(M + 2, 0.0); }
+  // column 1 (one residue emitted) in slot 0, column 2 in slot 1
+  Mx[0][1] = 1.0;
+  if (M >= 2) Dx[0][2] = T(1, HT_MD);
+  for (int k = 3; k <= M; ++k) Dx[0][k] = T(k - 1, HT_DD) * Dx[0][k - 1];
+  Ix[1][1] = T(1, HT_MI) * Mx[0][1];
+  if (M >= 2) Mx[1][2] = T(1, HT_MM) * Mx[0][1];
+  for (int k = 3; k <= M; ++k) {
+    Mx[1][k] = T(k - 1, HT_DM) * Dx[0][k - 1];
+    Ix[1][k] = 0;
+    Dx[1][k] = T(k - 1, HT_MD) * Mx[1][k - 1] + T(k - 1, HT_DD) * Dx[1][k - 1];
+  }
+  double p_sum = Mx[0][M] + Mx[1][M] + Dx[0][M] + Dx[1][M];
+  int cur = 0;
+  for (int col = 3; col <= bound; ++col) {
+    const int prev = 1 - cur;
+    double surv = 0.0;
+    Mx[cur][1] = Dx[cur][1] = 0;
+    Ix[cur][1] = T(1, HT_II) * Ix[prev][1];
+    surv += Ix[cur][1];
+    for (int k = 2; k <= M; ++k) {
+      Mx[cur][k] = T(k - 1, HT_MM) * Mx[prev][k - 1] + T(k - 1, HT_DM) * Dx[prev][k - 1] + T(k - 1, HT_IM) * Ix[prev][k - 1];
+      Ix[cur][k] = T(k, HT_MI) * Mx[prev][k] + T(k, HT_II) * Ix[prev][k];
+      Dx[cur][k] = T(k - 1, HT_MD) * Mx[cur][k - 1] + T(k - 1, HT_DD) * Dx[cur][k - 1];
+      surv += Ix[cur][k] + Mx[cur][k] * (1 - T(k, HT_MD)) + Dx[cur][k] * (1 - T(k, HT_DD));
+    }
+    surv += Mx[cur][M] * T(M, HT_MD) + Dx[cur][M] * T(M, HT_DD) - Ix[cur][M];
+    p_sum += Mx[cur][M] + Dx[cur][M];
+    surv /= surv + p_sum;
+    if (surv < emit_thresh) return col;
+    cur = 1 - cur;
+  }
+  return bound;
+}
+
 // ------------------------------------------------------------------------------------------
 // null model (src/p7_bg.c:52-82; frequencies src/hmmer.c:163-182)
 
@@ -559,6 +603,8 @@ extern "C" int bathhost_model_read(const char *path, int index, int ct, bathhost
   if (!m) return BATHHOST_EMEM;
   int st = open_nth(path, index, m->hmm);
   if (st != BATHHOST_OK) { delete m; return st; }
+  m->maxl_in_file = m->hmm.max_length;
+  if (m->hmm.max_length == -1) m->hmm.max_length = builder_max_length(m->hmm, 1e-7);      // src/bathsearch.c:761-762
   m->ct = (ct > 0) ? ct : (m->hmm.ct > 0 ? m->hmm.ct : 1);
   uint8_t gcode[64];
   if (!genetic_code(m->ct, gcode) || !(m->hmm.fsprob > 0.0f)) { delete m; return BATHHOST_EINVAL; }
@@ -633,4 +679,9 @@ extern "C" void bathhost_orf_length_params(const bathhost_model *m, int L, uint8
   if (!m) return;
   if (tjb_b)   *tjb_b   = m->prot.tjb_for_length(L);
   if (xw_move) *xw_move = m->prot.xw_move_for_length(L);
+}
+
+extern "C" int bathhost_model_computed_max_length(const bathhost_model *m)
+{
+  return m ? bathhost::builder_max_length(m->hmm, 1e-7) : -1;
 }

@@ -6,6 +6,7 @@ struct bathhost_model {
   bathhost::CoreModel      hmm;
   bathhost::NullModel      bg;
   int                      ct = 1;
+  int                      maxl_in_file = -1;
   bathhost::FsProfile      gm3, gm5;
   bathhost::FsOddsProfile  om3, om5;
   bathhost::ProteinProfile prot;

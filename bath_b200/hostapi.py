@@ -12,7 +12,7 @@ EXPORTS = [
     "bathhost_model_nrows", "bathhost_model_rfv", "bathhost_model_tfv", "bathhost_model_codons",
     "bathhost_model_indel_pos", "bathhost_model_mat", "bathhost_model_consensus", "bathhost_length_model",
     "bathhost_model_filter_params", "bathhost_model_rbv", "bathhost_model_rwv", "bathhost_model_twv",
-    "bathhost_orf_length_params",
+    "bathhost_orf_length_params", "bathhost_model_computed_max_length",
     "bathhost_search_create", "bathhost_search_destroy", "bathhost_search_last_error", "bathhost_search_sequence",
     "bathhost_search_finish", "bathhost_search_nhits", "bathhost_search_get_hit", "bathhost_search_get_stats",
 ]
@@ -113,6 +113,8 @@ def load():
     L.bathhost_search_get_hit.argtypes = [vp, C.c_int, C.POINTER(Hit)]
     L.bathhost_search_get_stats.restype = C.c_int
     L.bathhost_search_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.bathhost_model_computed_max_length.restype = C.c_int
+    L.bathhost_model_computed_max_length.argtypes = [vp]
     L.bathhost_length_model.restype = None
     L.bathhost_length_model.argtypes = [C.c_int, C.c_float, fp, fp]
     _lib = L

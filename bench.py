@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--window", type=int, default=1200, help="DNA window length Lw")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--search-mbp", type=float, default=20.0,
+                    help="also run the whole stage-batched bathsearch --fs pipeline over this many Mbp of the genome (0 = skip)")
     return ap.parse_args()
 
 
@@ -106,7 +108,7 @@ def make_workload(rank, mbp, window):
     rng = np.random.default_rng(42 + rank)
     dsq, plants = synth.planted_genome(rng, n, model.mat(), every=50000, fs_rate=model.fsprob)
     starts, lengths = synth.tile_windows(n, window)
-    return model, dsq, starts, lengths, len(plants)
+    return model, dsq, starts, lengths, plants
 
 
 def cpu_sample(model_M, dsq, starts, lengths, seconds, nthreads):
@@ -133,7 +135,7 @@ def run_reference(args, rank, world):
     binary cannot be built (Easel not vendored), so this is the restated oracle: kind = "port"."""
     if rank != 0:
         return
-    model, dsq, starts, lengths, nplants = make_workload(0, args.mbp, args.window)
+    model, dsq, starts, lengths, _ = make_workload(0, args.mbp, args.window)
     ncpu = os.cpu_count() or 1
     per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     from oracle import pyoracle as po
@@ -163,6 +165,35 @@ def run_reference(args, rank, world):
         "note": "restated CPU oracle (scalar C, -O3 -march=native, pthreads over windows); the reference binary needs Easel, "
                 "which is not vendored, so it cannot be compiled here",
     }))
+
+
+def search_leg(ctx, model, dsq, mbp, plants):
+    """BASELINE.json's second metric on rank 0's shard: bathsearch --fs end to end (ORF translation, MSV/bias/Viterbi/Forward
+    filters, DNA windows, frameshift Forward/Backward, domain definition, rescoring, hit list) through the host pipeline
+    (bath_b200/host/pipeline.cpp) and the C ABI, host buffers in, hit records out.  Mbp/s = target nucleotides (one strand
+    counted, both searched) / wall seconds.  Planted homologs recovered = hits overlapping a planted interval."""
+    from bath_b200 import hostapi
+    n = int(min(mbp * 1e6, len(dsq) - 2))
+    sub = np.full(n + 2, 255, np.uint8)
+    sub[1:-1] = dsq[1:n + 1]
+    search = hostapi.Search(model, ctx)
+    t0 = time.perf_counter()
+    search.add_sequence("synthetic", sub)
+    hits = search.finish()
+    dt = time.perf_counter() - t0
+    st = search.stats()
+    planted = [(a, b) for (a, b, strand) in plants if b <= n]
+    found = 0
+    for a, b in planted:
+        for h in hits:
+            lo, hi = min(h["ali_from"], h["ali_to"]), max(h["ali_from"], h["ali_to"])
+            if lo <= b and hi >= a:
+                found += 1
+                break
+    search.close()
+    return {"metric": "bathsearch --fs Mbp/s", "value": n / dt / 1e6, "unit": "Mbp/s", "seconds": dt, "target_mbp": n / 1e6,
+            "hits": len(hits), "planted": len(planted), "planted_recovered": found, "stats": st,
+            "note": "standard-translation branch and multi-domain clustering not restated yet (windows routed there are counted in stats.n_std_windows)"}
 
 
 def workload_config(args, M, nwin):
@@ -198,21 +229,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from bath_b200 import shard
+
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return shard.reduce_scalar(x, "max", device="cuda")
 
     def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return shard.reduce_scalar(x, "sum", device="cuda")
 
-    model, dsq_np, starts, lengths, nplants = make_workload(rank, args.mbp, args.window)
+    model, dsq_np, starts, lengths, plants = make_workload(rank, args.mbp, args.window)
+    nplants = len(plants)
     M, nwin = model.M, len(starts)
     cells_local = float(lengths.astype(np.int64).sum()) * M
 
@@ -310,6 +336,8 @@ def main():
         "checks": {"windows": nwin, "status_ok": n_ok, "planted_homologs": nplants, "max_score_nats": float(np.max(sc)),
                    "wall_ms_timed_loop_incl_flush": wall_ms},
     }
+    if args.search_mbp > 0:
+        out["search"] = search_leg(ctx, model, dsq_np, args.search_mbp, plants)
     if world == 1 and not args.no_cpu_baseline:
         ncpu = os.cpu_count() or 1
         v, n, dt, osc = cpu_sample(M, dsq_np, starts, lengths, args.cpu_seconds, ncpu)

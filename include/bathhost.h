@@ -51,6 +51,10 @@ int  bathhost_model_count(const char *path);
 void bathhost_model_destroy(bathhost_model *m);
 int  bathhost_model_get_info(const bathhost_model *m, bathhost_model_info *info);
 
+/* p7_Builder_MaxLength(hmm, 1e-7) recomputed from the core model (what bathsearch uses when the file has no MAXL line,
+ * src/bathsearch.c:761-762; bathhost_model_read already applies it) */
+int  bathhost_model_computed_max_length(const bathhost_model *m);
+
 /* Un-striped odds-ratio tables in the layout bathgpu_load_fs_profile takes.
  * which = 3 | 5.  rfv: [nrows][M+1], tfv: [8][M+1] (BM,MM,IM,DM,MD,MI,II,DD; source-node indexed). */
 int          bathhost_model_nrows(const bathhost_model *m, int which);

@@ -57,7 +57,12 @@ def test_host_model_setup_is_bit_identical_to_oracle(oracle, hmmfile, index):
     from bath_b200 import hostapi
     o = oracle.Model(common.golden(hmmfile), index)
     h = hostapi.QueryModel(common.golden(hmmfile), index)
-    assert h.M == o.M and h.max_length == o.max_length
+    assert h.M == o.M
+    if o.max_length > 0:
+        assert h.max_length == o.max_length
+    # p7_Builder_MaxLength restated: reproduces the MAXL line of every shipped model that has one (known-answer test),
+    # and supplies it for the models that lack one, as bathsearch does (src/bathsearch.c:761-762)
+    assert h.lib.bathhost_model_computed_max_length(h.h) == h.max_length
     assert h.evparam == o.evparam
     for which in (3, 5):
         assert np.array_equal(h.rfv(which).view(np.uint32), o.rfv(which).view(np.uint32))
@@ -107,3 +112,45 @@ def test_synthetic_genome_is_seeded_and_planted():
     assert s[0] == 1 and s[-1] + l[-1] - 1 == 200000 and np.all(l == 1200)
     s, l = synth.tile_windows(500, 1200)
     assert list(s) == [1] and list(l) == [500]
+
+
+def test_host_integer_filter_tables_match_oracle(oracle):
+    """a1: byte/word score systems of the protein profile (mf_conversion / vf_conversion) and the per-length integers"""
+    from bath_b200 import hostapi
+    lib = oracle.lib()
+    for hmmfile, index in [("AMP_N.bhmm", 0), ("tRNA-synthetases.bhmm", 1), ("PTHR37536.bhmm", 0)]:
+        o = oracle.Model(common.golden(hmmfile), index)
+        h = hostapi.QueryModel(common.golden(hmmfile), index)
+        rbv, rwv, twv, _, _ = o.om_tables()
+        hb, hw, ht = h.filter_tables()
+        assert np.array_equal(rbv[:, 1:], hb[:, 1:]) and np.array_equal(rwv[:, 1:], hw[:, 1:]) and np.array_equal(twv, ht)
+        oc, p = o.om.contents, h.filter_params()
+        assert (p["tbm_b"], p["tec_b"], p["base_b"], p["bias_b"], p["base_w"], p["ddbound_w"], p["xw_E_move"], p["xw_E_loop"]) == \
+               (oc.tbm_b, oc.tec_b, oc.base_b, oc.bias_b, oc.base_w, oc.ddbound_w, oc.xw[0][0], oc.xw[0][1])
+        assert p["scale_b"] == oc.scale_b and p["scale_w"] == oc.scale_w
+        for L in (20, 57, 133, 400, 1234, 100000):
+            lib.bo_oprofile_ReconfigLength(o.om, L)
+            assert h.orf_length_params(L) == (oc.tjb_b, oc.xw[1][0])
+
+
+def test_msv_shortcut_equivalence(oracle):
+    """The GPU runs the J-state MSV recursion only; the reference tries the J-less SSV shortcut first.  Both must give the
+    same score and status whenever the shortcut answers (src/impl_sse/ssvfilter.c:14-210): checked on the oracle's two paths."""
+    import ctypes as C
+    lib = oracle.lib()
+    model = oracle.Model(common.golden("AMP_N.bhmm"))
+    mat = common.hmm_mat(model)
+    rng = np.random.default_rng(0)
+    p = mat[1:] / mat[1:].sum(axis=1, keepdims=True)
+    for t in range(120):
+        if t % 3 == 0:
+            s = np.array([rng.choice(20, p=p[k]) for k in range(model.M)])
+            s = np.concatenate([rng.integers(0, 20, int(rng.integers(0, 30))), s[int(rng.integers(0, 60)):]])
+        else:
+            s = rng.integers(0, 20, int(rng.integers(20, 400)))
+        d = np.concatenate([[255], s, [255]]).astype(np.uint8)
+        lib.bo_oprofile_ReconfigLength(model.om, len(s))
+        a, b = C.c_float(), C.c_float()
+        s1 = lib.bo_MSVFilter_opt(oracle.u8ptr(d), len(s), model.om, 1, C.byref(a))
+        s2 = lib.bo_MSVFilter_opt(oracle.u8ptr(d), len(s), model.om, 0, C.byref(b))
+        assert s1 == s2 and (a.value == b.value or (np.isinf(a.value) and np.isinf(b.value)))

@@ -44,3 +44,16 @@ def test_amp_n_fs_matches_golden_table(gpu_ctx):
             ("Residues passing SSV filter", "Residues passing bias filter", "Residues passing Vit filter", "Residues passing Fwd filter")}
     assert st["nres"] == 822
     assert (st["pos_past_msv"], st["pos_past_bias"], st["pos_past_vit"], st["pos_past_fwd"]) == tuple(want.values())
+
+
+def test_pth2_filter_cascade_counters_match_golden(gpu_ctx):
+    """tutorial/PTH2.out is a run WITHOUT --fs; the ORF finder and the MSV -> bias -> Viterbi cascade are the same code
+    path in both modes (src/p7_pipeline.c:1632-1718), so its footer pins them: 6000 residues searched, 1503 / 1503 / 1401
+    residues past the SSV, bias and Viterbi filters."""
+    hits, st = run_search(gpu_ctx, "PTH2.bhmm", "target-PTH2.fa")
+    out = open(common.golden("PTH2.out")).read()
+    want = [int(re.search(k + r":\s+(\d+)", out).group(1)) for k in
+            ("Residues passing SSV filter", "Residues passing bias filter", "Residues passing Vit filter")]
+    assert st["nres"] == 6000
+    assert [st["pos_past_msv"], st["pos_past_bias"], st["pos_past_vit"]] == want
+    print(hits, st)
