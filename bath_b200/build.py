@@ -25,7 +25,7 @@ def _sources():
 
 _HOST = os.path.join(_HERE, "host")
 _HOST_SO = os.path.join(_HERE, "libbathhost.so")
-GXX_FLAGS = ["-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-ffp-contract=off", "-fno-fast-math"]
+GXX_FLAGS = ["-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-ffp-contract=off", "-fno-fast-math", "-pthread"]
 
 
 def host_library_path():

@@ -17,7 +17,7 @@ EXPORTS = [
     "bathgpu_host_alloc", "bathgpu_host_free", "bathgpu_fs_fetch_xrows",
     "bathgpu_fs_fetch_domain_matrices",
     "bathgpu_load_filter_profile", "bathgpu_upload_orfs", "bathgpu_msv_orfs", "bathgpu_ssv_windows", "bathgpu_vit_orfs",
-    "bathgpu_fwd_orfs",
+    "bathgpu_fwd_orfs", "bathgpu_fs_fwd_bck_xrows", "bathgpu_select_slot",
 ]
 
 
@@ -108,6 +108,10 @@ def load():
     L.bathgpu_vit_orfs.argtypes = [vp, vp, C.c_int, fp, ip, vp, C.c_int, ip]
     L.bathgpu_fwd_orfs.restype = C.c_int
     L.bathgpu_fwd_orfs.argtypes = [vp, vp, C.c_int, C.c_float, fp, fp, ip]
+    L.bathgpu_fs_fwd_bck_xrows.restype = C.c_int
+    L.bathgpu_fs_fwd_bck_xrows.argtypes = [vp, vp, C.c_int, fp, fp, fp, fp, fp, ip]
+    L.bathgpu_select_slot.restype = C.c_int
+    L.bathgpu_select_slot.argtypes = [vp, C.c_int]
     L.bathgpu_host_alloc.restype = vp
     L.bathgpu_host_alloc.argtypes = [C.c_size_t]
     L.bathgpu_host_free.restype = None
@@ -186,6 +190,9 @@ class Context:
         nrows, ld = rfv.shape
         assert tfv.shape == (8, ld)
         self._check(self.lib.bathgpu_load_fs_profile(self.h, which, ld - 1, nrows, _f(rfv), _f(tfv)))
+
+    def select_slot(self, slot):
+        self._check(self.lib.bathgpu_select_slot(self.h, slot))
 
     def upload_block(self, dsq):
         dsq = np.ascontiguousarray(dsq, dtype=np.uint8)
@@ -316,6 +323,17 @@ class Context:
         xf = np.asarray(xfE, np.float32)
         self._check(self.lib.bathgpu_fwd_orfs(self.h, orfs.ctypes.data, n, nj, _f(xf), _f(sc), _i(st)))
         return sc, st
+
+    def fs_fwd_bck_xrows(self, wins, xfE=(0.5, 0.5)):
+        n = len(wins)
+        Ls = wins["L"].astype(np.int64)
+        tot = int((Ls + 1).sum())
+        fx, bx = np.empty((tot, 6), np.float32), np.empty((tot, 6), np.float32)
+        fsc, bsc, st = np.empty(n, np.float32), np.empty(n, np.float32), np.empty(n, np.int32)
+        xf = np.asarray(xfE, np.float32)
+        self._check(self.lib.bathgpu_fs_fwd_bck_xrows(self.h, wins.ctypes.data, n, _f(xf), _f(fx), _f(bx), _f(fsc), _f(bsc), _i(st)))
+        off = np.concatenate([[0], np.cumsum(Ls + 1)])
+        return [fx[off[w]: off[w + 1]] for w in range(n)], [bx[off[w]: off[w + 1]] for w in range(n)], fsc, bsc, st
 
     def fs_domains(self, envs, xfE5=(1.0, 0.0), max_steps=None):
         n = len(envs)

@@ -54,6 +54,11 @@ struct FsProfileImage {
 
 }  // namespace
 
+struct TargetSlot {          // one resident target: packed DNA block + ORF residues (two slots: one per strand)
+  DevBuf  dna_bytes, dna4, residues;
+  int64_t block_n = 0, nres = 0;
+};
+
 struct bathgpu_ctx {
   int           device = 0;
   cudaDeviceProp prop{};
@@ -61,8 +66,9 @@ struct bathgpu_ctx {
   cudaEvent_t   ev0 = nullptr, ev1 = nullptr;
   std::string   err;
   FsProfileImage fs3, fs5;
-  DevBuf        dna_bytes, dna4;
-  int64_t       block_n = 0;
+  TargetSlot    slot[2];
+  int           cur = 0;
+  TargetSlot   &S() { return slot[cur]; }
   DevBuf        wins, fwdsc, status, counter;
   int           nstaged = 0;
   DevBuf        scratch;
@@ -72,8 +78,7 @@ struct bathgpu_ctx {
   bool          flt_loaded = false;
   bathgpu_filter_params flt{};
   int           flt_W = 0, flt_P = 0;
-  DevBuf        f_rbv, f_rwv, f_twv, f_ddsum, residues, orfs, fsc, fst, fwins, fnw;
-  int64_t       nres = 0;
+  DevBuf        f_rbv, f_rwv, f_twv, f_ddsum, orfs, fsc, fst, fwins, fnw;
   // domain stage workspace (last chunk stays resident for bathgpu_fs_fetch_domain_matrices)
   DevBuf        envs, dpp, doa, dfx, dppx, doax, dlsf, dfw, dbk, doasc, dnull2, dstat, dtoff, dtlen, dsteps;
   std::vector<long long> dom_xoff;
@@ -129,9 +134,10 @@ extern "C" void bathgpu_destroy(bathgpu_ctx *ctx)
     im->emis.release(); im->cellc.release(); im->cellb.release(); im->cellf5.release(); im->amino.release();
     im->oaflags.release(); im->oapass.release(); im->tfvraw.release();
   }
-  ctx->dna_bytes.release(); ctx->dna4.release(); ctx->wins.release(); ctx->fwdsc.release();
+  for (TargetSlot &t : ctx->slot) { t.dna_bytes.release(); t.dna4.release(); t.residues.release(); }
+  ctx->wins.release(); ctx->fwdsc.release();
   ctx->status.release(); ctx->counter.release(); ctx->scratch.release();
-  for (DevBuf *b : { &ctx->f_rbv, &ctx->f_rwv, &ctx->f_twv, &ctx->f_ddsum, &ctx->residues, &ctx->orfs, &ctx->fsc, &ctx->fst, &ctx->fwins, &ctx->fnw }) b->release();
+  for (DevBuf *b : { &ctx->f_rbv, &ctx->f_rwv, &ctx->f_twv, &ctx->f_ddsum, &ctx->orfs, &ctx->fsc, &ctx->fst, &ctx->fwins, &ctx->fnw }) b->release();
   for (DevBuf *b : { &ctx->envs, &ctx->dpp, &ctx->doa, &ctx->dfx, &ctx->dppx, &ctx->doax, &ctx->dlsf, &ctx->dfw, &ctx->dbk, &ctx->doasc,
                      &ctx->dnull2, &ctx->dstat, &ctx->dtoff, &ctx->dtlen, &ctx->dsteps }) b->release();
   for (DevBuf *b : { &ctx->fxmx, &ctx->bxmx, &ctx->lsf, &ctx->lsb, &ctx->xoff, &ctx->dmocc, &ctx->dbtot, &ctx->detot, &ctx->bcksc }) b->release();
@@ -424,20 +430,27 @@ __global__ void pack_dna4_kernel(const uint8_t *__restrict__ dsq, long long n, u
   out[w] = word;
 }
 
+extern "C" int bathgpu_select_slot(bathgpu_ctx *ctx, int slot)
+{
+  if (!ctx || slot < 0 || slot > 1) return fail(ctx, BATHGPU_EINVAL, "slot must be 0 or 1");
+  ctx->cur = slot;
+  return BATHGPU_OK;
+}
+
 extern "C" int bathgpu_upload_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_t n)
 {
   if (!ctx || !dsq || n < 1) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_upload_block");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   const long long nwords = (n + 8 + 7) / 8 + 24;     // kernels prefetch up to ~100 nt past a window
-  if (ctx->dna_bytes.reserve((size_t)n + 2) != BATHGPU_OK || ctx->dna4.reserve((size_t)nwords * 4) != BATHGPU_OK)
+  if (ctx->S().dna_bytes.reserve((size_t)n + 2) != BATHGPU_OK || ctx->S().dna4.reserve((size_t)nwords * 4) != BATHGPU_OK)
     return fail(ctx, BATHGPU_EMEM, "device allocation failed for a %lld-nt block", (long long)n);
-  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dna_bytes.p, dsq, (size_t)n + 2, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->S().dna_bytes.p, dsq, (size_t)n + 2, cudaMemcpyHostToDevice, ctx->stream));
   const int threads = 256;
   const long long blocks = (nwords + threads - 1) / threads;
-  pack_dna4_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(ctx->dna_bytes.as<uint8_t>(), n, ctx->dna4.as<uint32_t>(), nwords);
+  pack_dna4_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(ctx->S().dna_bytes.as<uint8_t>(), n, ctx->S().dna4.as<uint32_t>(), nwords);
   CUDA_TRY(ctx, cudaGetLastError());
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  ctx->block_n = n;
+  ctx->S().block_n = n;
   return BATHGPU_OK;
 }
 
@@ -455,7 +468,6 @@ static int fwd_version()      // BATHGPU_FWD=1|3 picks a kernel generation for A
   static const int v = [] { const char *e = getenv("BATHGPU_FWD"); int x = e ? atoi(e) : 3; return (x == 1) ? 1 : 3; }();
   return v;
 }
-static bool use_fwd_v1() { return fwd_version() == 1; }
 
 template <int J, bool XMX>
 static cudaError_t launch_fwd3(const FsParserArgs &a, int grid, cudaStream_t s)
@@ -467,7 +479,7 @@ static cudaError_t launch_fwd3(const FsParserArgs &a, int grid, cudaStream_t s)
 template <bool XMX>
 static cudaError_t dispatch_fwd(int J, const FsParserArgs &a, int grid, cudaStream_t s)
 {
-  if (fwd_version() == 3) {
+  if (fwd_version() >= 3) {
     switch (J) {
     case 1:  return launch_fwd3<1, XMX>(a, grid, s);
     case 2:  return launch_fwd3<2, XMX>(a, grid, s);
@@ -501,7 +513,7 @@ template <int J, bool XMX>
 static int fwd_occupancy()
 {
   int nb = 0;
-  if (fwd_version() == 3) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fs3_forward_parser_kernel_v3<J, XMX>, 32, 0); return nb; }
+  if (fwd_version() >= 3) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fs3_forward_parser_kernel_v3<J, XMX>, 32, 0); return nb; }
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fs3_forward_parser_kernel<J, XMX>, FwdTune<J>::kThreads, 0);
   return nb;
 }
@@ -516,9 +528,9 @@ static int fwd_blocks_per_sm(int J, bool xmx)
 static int check_windows(bathgpu_ctx *ctx, const bathgpu_window *wins, int n)
 {
   for (int w = 0; w < n; ++w) {
-    if (wins[w].L < 3 || wins[w].start < 1 || wins[w].start + wins[w].L - 1 > ctx->block_n)
+    if (wins[w].L < 3 || wins[w].start < 1 || wins[w].start + wins[w].L - 1 > ctx->S().block_n)
       return fail(ctx, BATHGPU_EINVAL, "window %d (start %lld, L %d) is outside the uploaded block (n=%lld) or shorter than 3",
-                  w, (long long)wins[w].start, wins[w].L, (long long)ctx->block_n);
+                  w, (long long)wins[w].start, wins[w].L, (long long)ctx->S().block_n);
   }
   return BATHGPU_OK;
 }
@@ -526,7 +538,7 @@ static int check_windows(bathgpu_ctx *ctx, const bathgpu_window *wins, int n)
 extern "C" int bathgpu_stage_windows(bathgpu_ctx *ctx, const bathgpu_window *wins, int n)
 {
   if (!ctx || !wins || n < 1) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_stage_windows");
-  if (ctx->block_n == 0)      return fail(ctx, BATHGPU_EINVAL, "no block uploaded");
+  if (ctx->S().block_n == 0)      return fail(ctx, BATHGPU_EINVAL, "no block uploaded");
   int st = check_windows(ctx, wins, n);
   if (st != BATHGPU_OK) return st;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -548,7 +560,7 @@ extern "C" int bathgpu_fs_fwd_staged(bathgpu_ctx *ctx, const float xfE[2])
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   const FsProfileImage &im = ctx->fs3;
   FsParserArgs a{};
-  a.emis = im.emis.as<float>(); a.cellc = im.cellc.as<float>(); a.dna4 = ctx->dna4.as<uint32_t>();
+  a.emis = im.emis.as<float>(); a.cellc = im.cellc.as<float>(); a.dna4 = ctx->S().dna4.as<uint32_t>();
   a.wins = ctx->wins.as<WindowDesc>(); a.nwin = ctx->nstaged; a.mpad = im.mpad;
   a.tEM = xfE[0]; a.tEL = xfE[1];
   a.fwdsc = ctx->fwdsc.as<float>(); a.status = ctx->status.as<int>();
@@ -605,10 +617,14 @@ static cudaError_t dispatch_bck(int J, const FsBackwardArgs &a, int sms, cudaStr
 }
 
 // a10 + a11 for one chunk of windows whose descriptors are already in ctx->wins
+// x_off0 / fx_out / bx_out: when given, the X rows of both parsers are returned (rows of this chunk start at x_off0)
+// and the decoding kernel is skipped (xf5_loop == nullptr)
 static int bck_decode_chunk(bathgpu_ctx *ctx, const bathgpu_window *wins, int n, const float xfE[2], const float xf5_loop[3],
                             const int64_t *out_offset, float *mocc, float *btot, float *etot,
-                            float *fwdsc, float *bcksc, int32_t *status)
+                            float *fwdsc, float *bcksc, int32_t *status,
+                            int64_t x_off0 = 0, float *fx_out = nullptr, float *bx_out = nullptr)
 {
+  const bool decode = (xf5_loop != nullptr);
   const FsProfileImage &im = ctx->fs3;
   std::vector<long long> xoff(n + 1, 0);
   for (int w = 0; w < n; ++w) xoff[w + 1] = xoff[w] + wins[w].L + 1;
@@ -630,7 +646,7 @@ static int bck_decode_chunk(bathgpu_ctx *ctx, const bathgpu_window *wins, int n,
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
 
   FsParserArgs fa{};
-  fa.emis = im.emis.as<float>(); fa.cellc = im.cellc.as<float>(); fa.dna4 = ctx->dna4.as<uint32_t>();
+  fa.emis = im.emis.as<float>(); fa.cellc = im.cellc.as<float>(); fa.dna4 = ctx->S().dna4.as<uint32_t>();
   fa.wins = ctx->wins.as<WindowDesc>(); fa.nwin = n; fa.mpad = im.mpad; fa.tEM = xfE[0]; fa.tEL = xfE[1];
   fa.fwdsc = ctx->fwdsc.as<float>(); fa.status = ctx->status.as<int>();
   fa.xmx = ctx->fxmx.as<float>(); fa.xoff = ctx->xoff.as<long long>(); fa.counter = ctx->counter.as<int>();
@@ -644,20 +660,27 @@ static int bck_decode_chunk(bathgpu_ctx *ctx, const bathgpu_window *wins, int n,
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
   CUDA_TRY(ctx, dispatch_bck(im.J, ba, sms, ctx->stream));
 
-  DomainDecodeArgs da{};
-  da.fxmx = ba.fxmx; da.bxmx = ba.bxmx; da.xoff = fa.xoff; da.wins = fa.wins; da.nwin = n;
-  da.tNL = xf5_loop[0]; da.tJL = xf5_loop[1]; da.tCL = xf5_loop[2];
-  da.lsf = ctx->lsf.as<float>(); da.lsb = ctx->lsb.as<float>();
-  da.mocc = ctx->dmocc.as<float>(); da.btot = ctx->dbtot.as<float>(); da.etot = ctx->detot.as<float>();
-  da.ooff = fa.xoff; da.status = fa.status;
-  fs_domain_decoding_kernel<<<(n + 3) / 4, 128, 0, ctx->stream>>>(da);
-  CUDA_TRY(ctx, cudaGetLastError());
+  std::vector<float> hm, hb, he;
+  if (decode) {
+    DomainDecodeArgs da{};
+    da.fxmx = ba.fxmx; da.bxmx = ba.bxmx; da.xoff = fa.xoff; da.wins = fa.wins; da.nwin = n;
+    da.tNL = xf5_loop[0]; da.tJL = xf5_loop[1]; da.tCL = xf5_loop[2];
+    da.lsf = ctx->lsf.as<float>(); da.lsb = ctx->lsb.as<float>();
+    da.mocc = ctx->dmocc.as<float>(); da.btot = ctx->dbtot.as<float>(); da.etot = ctx->detot.as<float>();
+    da.ooff = fa.xoff; da.status = fa.status;
+    fs_domain_decoding_kernel<<<(n + 3) / 4, 128, 0, ctx->stream>>>(da);
+    CUDA_TRY(ctx, cudaGetLastError());
+  }
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
 
-  std::vector<float> hm(rows), hb(rows), he(rows);
-  CUDA_TRY(ctx, cudaMemcpyAsync(hm.data(), ctx->dmocc.p, rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaMemcpyAsync(hb.data(), ctx->dbtot.p, rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaMemcpyAsync(he.data(), ctx->detot.p, rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (decode) {
+    hm.resize(rows); hb.resize(rows); he.resize(rows);
+    CUDA_TRY(ctx, cudaMemcpyAsync(hm.data(), ctx->dmocc.p, rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(hb.data(), ctx->dbtot.p, rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(he.data(), ctx->detot.p, rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (fx_out) CUDA_TRY(ctx, cudaMemcpyAsync(fx_out + (size_t)x_off0 * 6, ctx->fxmx.p, rows * 24, cudaMemcpyDeviceToHost, ctx->stream));
+  if (bx_out) CUDA_TRY(ctx, cudaMemcpyAsync(bx_out + (size_t)x_off0 * 6, ctx->bxmx.p, rows * 24, cudaMemcpyDeviceToHost, ctx->stream));
   if (fwdsc) CUDA_TRY(ctx, cudaMemcpyAsync(fwdsc, ctx->fwdsc.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (bcksc) CUDA_TRY(ctx, cudaMemcpyAsync(bcksc, ctx->bcksc.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(status, ctx->status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -665,13 +688,14 @@ static int bck_decode_chunk(bathgpu_ctx *ctx, const bathgpu_window *wins, int n,
   float ms = 0.f;
   CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   ctx->last_ms += ms;
-  ctx->last_launches += 3;
-  for (int w = 0; w < n; ++w) {
-    const size_t len = (size_t)wins[w].L + 1;
-    memcpy(mocc + out_offset[w], hm.data() + xoff[w], len * 4);
-    memcpy(btot + out_offset[w], hb.data() + xoff[w], len * 4);
-    memcpy(etot + out_offset[w], he.data() + xoff[w], len * 4);
-  }
+  ctx->last_launches += decode ? 3 : 2;
+  if (decode)
+    for (int w = 0; w < n; ++w) {
+      const size_t len = (size_t)wins[w].L + 1;
+      memcpy(mocc + out_offset[w], hm.data() + xoff[w], len * 4);
+      memcpy(btot + out_offset[w], hb.data() + xoff[w], len * 4);
+      memcpy(etot + out_offset[w], he.data() + xoff[w], len * 4);
+    }
   return BATHGPU_OK;
 }
 
@@ -682,7 +706,7 @@ extern "C" int bathgpu_fs_bck_decode(bathgpu_ctx *ctx, const bathgpu_window *win
   if (!ctx || !wins || n < 1 || !xfE || !xf5_loop || !out_offset || !mocc || !btot || !etot || !status)
     return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fs_bck_decode");
   if (!ctx->fs3.loaded)  return fail(ctx, BATHGPU_EINVAL, "3-codon profile not loaded");
-  if (ctx->block_n == 0) return fail(ctx, BATHGPU_EINVAL, "no block uploaded");
+  if (ctx->S().block_n == 0) return fail(ctx, BATHGPU_EINVAL, "no block uploaded");
   int st = check_windows(ctx, wins, n);
   if (st != BATHGPU_OK) return st;
   for (int w = 0; w < n; ++w)
@@ -699,6 +723,38 @@ extern "C" int bathgpu_fs_bck_decode(bathgpu_ctx *ctx, const bathgpu_window *win
     st = bck_decode_chunk(ctx, wins + w0, w1 - w0, xfE, xf5_loop, out_offset + w0, mocc, btot, etot,
                           fwdsc ? fwdsc + w0 : nullptr, bcksc ? bcksc + w0 : nullptr, status + w0);
     if (st != BATHGPU_OK) return st;
+    w0 = w1;
+  }
+  return BATHGPU_OK;
+}
+
+// a10 alone: Forward (keeping X rows) + Backward parsers over windows; X rows of both come back to the host, which
+// runs p7_DomainDecoding_Frameshift itself (it needs a length-model value that depends on the previous window's
+// envelopes, src/p7_domaindef.c:320-325, :1018 -- an O(L) scalar pass the reference also does per window).
+extern "C" int bathgpu_fs_fwd_bck_xrows(bathgpu_ctx *ctx, const bathgpu_window *wins, int n, const float xfE[2],
+                                        float *fwd_xrows, float *bck_xrows, float *fwdsc, float *bcksc, int32_t *status)
+{
+  if (!ctx || !wins || n < 1 || !xfE || !fwd_xrows || !bck_xrows || !status)
+    return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fs_fwd_bck_xrows");
+  if (!ctx->fs3.loaded)  return fail(ctx, BATHGPU_EINVAL, "3-codon profile not loaded");
+  if (ctx->S().block_n == 0) return fail(ctx, BATHGPU_EINVAL, "no block uploaded");
+  int st = check_windows(ctx, wins, n);
+  if (st != BATHGPU_OK) return st;
+  for (int w = 0; w < n; ++w)
+    if (wins[w].L < 5) return fail(ctx, BATHGPU_EINVAL, "window %d: the Backward parser needs L >= 5 (fwdback_fs.c:600)", w);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ctx->last_ms = 0.f; ctx->last_launches = 0;
+  const size_t max_rows = (size_t)16 << 20;
+  int w0 = 0;
+  int64_t x0 = 0;
+  while (w0 < n) {
+    size_t rows = 0;
+    int w1 = w0;
+    while (w1 < n && (w1 == w0 || rows + wins[w1].L + 1 <= max_rows)) { rows += wins[w1].L + 1; ++w1; }
+    st = bck_decode_chunk(ctx, wins + w0, w1 - w0, xfE, nullptr, nullptr, nullptr, nullptr, nullptr,
+                          fwdsc ? fwdsc + w0 : nullptr, bcksc ? bcksc + w0 : nullptr, status + w0, x0, fwd_xrows, bck_xrows);
+    if (st != BATHGPU_OK) return st;
+    x0 += (int64_t)rows;
     w0 = w1;
   }
   return BATHGPU_OK;
@@ -781,7 +837,7 @@ static int domains_chunk(bathgpu_ctx *ctx, const bathgpu_envelope *envs, int n, 
 
   DomainArgs a{};
   a.emis = im.emis.as<float>(); a.amino = im.amino.as<float>(); a.cellf = im.cellf5.as<float>(); a.cellb = im.cellb.as<float>();
-  a.oapass = im.oapass.as<float>(); a.oaflags = im.oaflags.as<uint32_t>(); a.dna4 = ctx->dna4.as<uint32_t>();
+  a.oapass = im.oapass.as<float>(); a.oaflags = im.oaflags.as<uint32_t>(); a.dna4 = ctx->S().dna4.as<uint32_t>();
   a.envs = ctx->envs.as<EnvelopeDesc>(); a.nenv = n; a.M = M; a.mpad = mpad; a.tEM = xfE5[0]; a.tEL = xfE5[1];
   a.xoff = ctx->xoff.as<long long>(); a.pp = ctx->dpp.as<float>(); a.oa = ctx->doa.as<float>(); a.fx = ctx->dfx.as<float>();
   a.ppx = ctx->dppx.as<float>(); a.oax = ctx->doax.as<float>(); a.lsf = ctx->dlsf.as<float>();
@@ -838,11 +894,11 @@ extern "C" int bathgpu_fs_domains(bathgpu_ctx *ctx, const bathgpu_envelope *envs
   if (!ctx || !envs || n < 1 || !xfE5 || !results || !traces || max_steps < 1)
     return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fs_domains");
   if (!ctx->fs5.loaded)  return fail(ctx, BATHGPU_EINVAL, "5-codon profile not loaded");
-  if (ctx->block_n == 0) return fail(ctx, BATHGPU_EINVAL, "no block uploaded");
+  if (ctx->S().block_n == 0) return fail(ctx, BATHGPU_EINVAL, "no block uploaded");
   for (int e = 0; e < n; ++e)
-    if (envs[e].L < 6 || envs[e].start < 1 || envs[e].start + envs[e].L - 1 > ctx->block_n)
+    if (envs[e].L < 6 || envs[e].start < 1 || envs[e].start + envs[e].L - 1 > ctx->S().block_n)
       return fail(ctx, BATHGPU_EINVAL, "envelope %d (start %lld, L %d) is outside the uploaded block (n=%lld) or shorter than 6",
-                  e, (long long)envs[e].start, envs[e].L, (long long)ctx->block_n);
+                  e, (long long)envs[e].start, envs[e].L, (long long)ctx->S().block_n);
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   ctx->last_ms = 0.f; ctx->last_launches = 0;
   // chunks bounded by matrix memory: (7 + 3) * mpad * 4 B per row
@@ -968,21 +1024,21 @@ extern "C" int bathgpu_upload_orfs(bathgpu_ctx *ctx, const uint8_t *residues, in
 {
   if (!ctx || !residues || n < 1) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_upload_orfs");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  if (ctx->residues.reserve((size_t)n + 64) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
-  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->residues.p, residues, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  if (ctx->S().residues.reserve((size_t)n + 64) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->S().residues.p, residues, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  ctx->nres = n;
+  ctx->S().nres = n;
   return BATHGPU_OK;
 }
 
 static int stage_orfs(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n, int max_wins)
 {
   if (!ctx->flt_loaded) return fail(ctx, BATHGPU_EINVAL, "filter profile not loaded");
-  if (ctx->nres == 0)   return fail(ctx, BATHGPU_EINVAL, "no ORF residues uploaded");
+  if (ctx->S().nres == 0)   return fail(ctx, BATHGPU_EINVAL, "no ORF residues uploaded");
   for (int o = 0; o < n; ++o)
-    if (orfs[o].L < 1 || orfs[o].offset < 0 || orfs[o].offset + orfs[o].L > ctx->nres)
+    if (orfs[o].L < 1 || orfs[o].offset < 0 || orfs[o].offset + orfs[o].L > ctx->S().nres)
       return fail(ctx, BATHGPU_EINVAL, "ORF %d (offset %lld, L %d) is outside the uploaded residues (n=%lld)",
-                  o, (long long)orfs[o].offset, orfs[o].L, (long long)ctx->nres);
+                  o, (long long)orfs[o].offset, orfs[o].L, (long long)ctx->S().nres);
   static_assert(sizeof(OrfDesc) == sizeof(bathgpu_orf), "descriptor layouts must agree");
   static_assert(sizeof(WindowRec) == sizeof(bathgpu_orf_window), "window layouts must agree");
   if (ctx->orfs.reserve((size_t)n * sizeof(OrfDesc)) != BATHGPU_OK || ctx->fsc.reserve((size_t)n * 4) != BATHGPU_OK ||
@@ -999,7 +1055,7 @@ static FilterArgs filter_args(bathgpu_ctx *ctx, int n, int max_wins)
 {
   FilterArgs a{};
   const bathgpu_filter_params &p = ctx->flt;
-  a.residues = ctx->residues.as<uint8_t>(); a.orfs = ctx->orfs.as<OrfDesc>(); a.norf = n; a.M = p.M;
+  a.residues = ctx->S().residues.as<uint8_t>(); a.orfs = ctx->orfs.as<OrfDesc>(); a.norf = n; a.M = p.M;
   a.rbv = ctx->f_rbv.as<uint32_t>(); a.rbv_bytes = ctx->f_rbv.as<uint8_t>(); a.rowwords_b = 32 * ctx->flt_W;
   a.tbm_b = p.tbm_b; a.tec_b = p.tec_b; a.base_b = p.base_b; a.bias_b = p.bias_b; a.scale_b = p.scale_b;
   a.rwv = ctx->f_rwv.as<uint32_t>(); a.twv = ctx->f_twv.as<uint32_t>(); a.ddsum = ctx->f_ddsum.as<int>(); a.rowwords_w = 32 * ctx->flt_P;
@@ -1141,9 +1197,9 @@ extern "C" int bathgpu_fwd_orfs(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n
 {
   if (!ctx || !orfs || n < 1 || !xfE || !fwdsc || !status) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fwd_orfs");
   if (!ctx->fs3.loaded) return fail(ctx, BATHGPU_EINVAL, "3-codon profile not loaded");
-  if (ctx->nres == 0)   return fail(ctx, BATHGPU_EINVAL, "no ORF residues uploaded");
+  if (ctx->S().nres == 0)   return fail(ctx, BATHGPU_EINVAL, "no ORF residues uploaded");
   for (int o = 0; o < n; ++o)
-    if (orfs[o].L < 1 || orfs[o].offset < 0 || orfs[o].offset + orfs[o].L > ctx->nres)
+    if (orfs[o].L < 1 || orfs[o].offset < 0 || orfs[o].offset + orfs[o].L > ctx->S().nres)
       return fail(ctx, BATHGPU_EINVAL, "ORF %d is outside the uploaded residues", o);
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   if (ctx->orfs.reserve((size_t)n * sizeof(OrfDesc)) != BATHGPU_OK || ctx->fsc.reserve((size_t)n * 4) != BATHGPU_OK ||
@@ -1153,7 +1209,7 @@ extern "C" int bathgpu_fwd_orfs(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
   const FsProfileImage &im = ctx->fs3;
   OrfFwdArgs a{};
-  a.emis = im.emis.as<float>(); a.cellc = im.cellc.as<float>(); a.residues = ctx->residues.as<uint8_t>();
+  a.emis = im.emis.as<float>(); a.cellc = im.cellc.as<float>(); a.residues = ctx->S().residues.as<uint8_t>();
   a.orfs = ctx->orfs.p; a.orf_stride = (int)sizeof(OrfDesc); a.norf = n; a.mpad = im.mpad; a.nj = nj;
   a.tEM = xfE[0]; a.tEL = xfE[1]; a.fwdsc = ctx->fsc.as<float>(); a.status = ctx->fst.as<int>(); a.counter = ctx->counter.as<int>();
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));

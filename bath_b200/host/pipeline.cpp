@@ -13,11 +13,13 @@
 // arbitration rejects (src/p7_pipeline.c:1480-1511), and the stochastic-trace clustering of multi-domain regions
 // (src/p7_domaindef.c:411-451) -- such regions are rescored as one envelope and counted in the statistics.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/bathhost.h"
@@ -205,6 +207,15 @@ namespace {
 
 int fail(bathhost_search *s, int code, const std::string &msg) { s->err = msg; return code; }
 
+struct StageTimer {              // adds the time since construction / last lap to a stats counter
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void lap(int64_t &acc) {
+    auto t1 = std::chrono::steady_clock::now();
+    acc += std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+    t0 = t1;
+  }
+};
+
 #define BE_TRY(s, call, what)                                                                   \
   do { int st_ = (call); if (st_ != 0) return fail(s, st_, std::string(what) + " failed: " +    \
        (s->be.last_error ? s->be.last_error(s->be.ctx) : "?")); } while (0)
@@ -216,31 +227,30 @@ int fail(bathhost_search *s, int code, const std::string &msg) { s->err = msg; r
 void find_orfs(const uint8_t *dsq, int n, const uint8_t gcode[64], int min_len, std::vector<Orf> &orfs, std::vector<uint8_t> &res)
 {
   orfs.clear(); res.clear();
-  struct Open { int start; std::vector<uint8_t> aa; };
-  Open fr[3];
-  for (int f = 0; f < 3; ++f) fr[f].start = -1;
-  auto close = [&](int f, int end) {
-    Open &o = fr[f];
-    if (o.start > 0 && (int) o.aa.size() >= min_len) {
-      Orf r; r.start = o.start; r.end = end; r.frame = f; r.offset = (long long) res.size(); r.n = (int) o.aa.size();
-      res.insert(res.end(), o.aa.begin(), o.aa.end());
-      orfs.push_back(r);
+  res.reserve((size_t) n);
+  for (int f = 0; f < 3; ++f) {
+    int run_start = -1;
+    size_t run_res = res.size();
+    auto close = [&](int end) {
+      const int len = (int) (res.size() - run_res);
+      if (run_start > 0 && len >= min_len) {
+        Orf r; r.start = run_start; r.end = end; r.frame = f; r.offset = (long long) run_res; r.n = len;
+        orfs.push_back(r);
+      } else res.resize(run_res);              // too short: its residues are dropped
+      run_start = -1; run_res = res.size();
+    };
+    int i = f + 1;
+    for (; i + 2 <= n; i += 3) {
+      const uint8_t a = dsq[i], b = dsq[i + 1], c = dsq[i + 2];
+      uint8_t aa = 26;                                   // X
+      if (a < 4 && b < 4 && c < 4) aa = gcode[16 * a + 4 * b + c];
+      if (aa == kKp - 2) close(i - 1);                   // a stop codon ends the run before it
+      else { if (run_start < 0) { run_start = i; run_res = res.size(); } res.push_back(aa); }
     }
-    o.start = -1; o.aa.clear();
-  };
-  for (int i = 1; i + 2 <= n; ++i) {
-    const int f = (i - 1) % 3;
-    const uint8_t a = dsq[i], b = dsq[i + 1], c = dsq[i + 2];
-    uint8_t aa = 26;                                   // X
-    if (a < 4 && b < 4 && c < 4) aa = gcode[16 * a + 4 * b + c];
-    if (aa == kKp - 2) close(f, i - 1);                // stop codon ends the run before it
-    else { if (fr[f].start < 0) fr[f].start = i; fr[f].aa.push_back(aa); }
+    if (run_start > 0) close(run_start + 3 * (int) (res.size() - run_res) - 1);     // open at the end: ends at its last whole codon
   }
-  // runs still open at the end of the block end at their last whole codon, in frame order of their last nucleotide
-  int order[3] = { 0, 1, 2 };
-  auto last_end = [&](int f) { return fr[f].start < 0 ? -1 : fr[f].start + 3 * (int) fr[f].aa.size() - 1; };
-  std::sort(order, order + 3, [&](int x, int y) { return last_end(x) < last_end(y); });
-  for (int z = 0; z < 3; ++z) if (fr[order[z]].start > 0) close(order[z], last_end(order[z]));
+  // a left-to-right scan over the three interleaved frames finishes ORFs in order of their last nucleotide
+  std::sort(orfs.begin(), orfs.end(), [](const Orf &x, const Orf &y) { return x.end < y.end; });
 }
 
 void revcomp(std::vector<uint8_t> &d, int n)
@@ -386,19 +396,54 @@ void summarize_alignment(const bathhost_model *m, const std::vector<bathgpu_trac
   snprintf(h.cigar, sizeof h.cigar, "%s", cigar.c_str());
 }
 
-// ---- one oriented block ----------------------------------------------------------------------------------
-struct Block {
-  const uint8_t *dsq;        // oriented, 1..n with sentinels
-  int       n;               // dnasq->n
-  int       C;               // context carried over from the previous block (dnasq->C)
-  long long start;           // dnasq->start: original coordinate of oriented position 1
-  bool      complement;
-  int64_t   seqidx;
-  const char *name;
-  long long sq_len;          // full length of the source sequence
+// ---- one target sequence, both strands, stage-batched ------------------------------------------------------
+// The reference walks the sequence in blocks of block_length nucleotides carrying max_length*3 nucleotides of left
+// context, top strand then bottom strand of each block (src/bathsearch.c:1060-1105).  Here every DP stage runs ONCE PER
+// STRAND over the work of all blocks (the two strands sit in the device library's two target slots), and everything
+// whose result depends on the order the reference visits blocks in is done on the host in exactly that order:
+//   * hit_windows is never reset between blocks or strands in the reference (info->hw, src/bathsearch.c:817,1076,1090),
+//     so the window picked for an ORF (p7_pli_BuildDNAWindows) and the k-range scan of p7_pli_Frameshift see every
+//     window stamped with the same ORF index by EARLIER blocks -- reproduced by appending in reference order;
+//   * the length model left in om_fs5 by the previous window's rescoring feeds p7_DomainDecoding_Frameshift;
+//   * the early E-value cuts use the residue count at the time the block is processed.
+struct BlockInfo {
+  long long b0, b1;          // original coordinates of the block (context included)
+  int       n, C, bw;        // dnasq->n, dnasq->C, dnasq->W
+  long long nres_at[2];      // pli->nres when the top / bottom strand of this block is processed
 };
 
-int run_block(bathhost_search *s, const Block &blk)
+struct Strand {
+  bool complement = false;
+  std::vector<uint8_t> dsq;                 // the whole sequence in this orientation, 1..n with sentinels
+  std::vector<Orf> orfs;                    // of all blocks, block-local coordinates
+  std::vector<int> orf_blk;                 // block of each ORF
+  std::vector<int> orf_begin;               // [nblocks+1] range of each block's ORFs
+  std::vector<uint8_t> residues;
+  std::vector<double> P_orf;
+  std::vector<float>  fwdsc_orf;
+  std::vector<std::vector<OrfWin>> wins_of_orf;     // windows of ORFs that reached the Forward stage, id = block-local ORF index
+  std::vector<DnaWin> dwin;                 // DNA windows of all blocks, block-local coordinates
+  std::vector<int>    dwin_blk;
+  std::vector<int>    dwin_begin;           // [nblocks+1]
+  std::vector<size_t> hw_count;             // [nblocks] length of the accumulated hit_windows list after this block-strand
+  std::vector<bathgpu_window> gw;
+  std::vector<float>   fs_fwd;
+  std::vector<int32_t> fs_st;
+  std::vector<int>     fsw;                 // windows that go down the frameshift branch
+  std::vector<size_t>  xoff;
+  std::vector<float>   fxr, bxr;
+  std::vector<int32_t> st2;
+  struct Env { int win, i, j; };
+  std::vector<Env> envs;
+  std::vector<bathgpu_envelope> ge;
+  std::vector<bathgpu_domain_result> res;
+  std::vector<bathgpu_trace_step> traces;
+  long long goff(const BlockInfo &b, long long n_total) const { return complement ? n_total - b.b1 : b.b0 - 1; }   // device coordinate = goff + block-local
+  long long start_of(const BlockInfo &b) const { return complement ? b.b1 : b.b0; }                               // dnasq->start
+};
+
+// stages 1-3 for one strand: ORFs of every block, MSV, bias, Viterbi/SSV windows, local-composition re-check, protein Forward
+int filter_strand(bathhost_search *s, Strand &S, const std::vector<BlockInfo> &blocks, long long n_total, int slot)
 {
   const bathhost_model *m = s->model;
   const ProteinProfile &q = m->prot;
@@ -406,18 +451,47 @@ int run_block(bathhost_search *s, const Block &blk)
   const int M = q.M;
   const float *ev = m->hmm.evparam;
   Background &bg = s->bg;
-  if (blk.n < 15) return 0;
+  StageTimer tm;
 
-  std::vector<Orf> orfs;
-  std::vector<uint8_t> residues;
-  find_orfs(blk.dsq, blk.n, s->gcode, opt.min_orf, orfs, residues);
-  if (orfs.empty()) return 0;
-  s->st.n_orfs += (int64_t) orfs.size();
-  const int norf = (int) orfs.size();
+  S.orf_begin.assign(blocks.size() + 1, 0);
+  {
+    // blocks are independent: translate them on all host cores, then concatenate in block order
+    const size_t nblk = blocks.size();
+    std::vector<std::vector<Orf>> bo(nblk);
+    std::vector<std::vector<uint8_t>> br(nblk);
+    const unsigned nthr = (unsigned) std::max<size_t>(1, std::min<size_t>({ nblk, (size_t) std::thread::hardware_concurrency(), (size_t) 32 }));
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nthr; ++t)
+      pool.emplace_back([&, t]() {
+        for (size_t b = t; b < nblk; b += nthr)
+          if (blocks[b].n >= 15) find_orfs(S.dsq.data() + S.goff(blocks[b], n_total), blocks[b].n, s->gcode, opt.min_orf, bo[b], br[b]);
+      });
+    for (auto &th : pool) th.join();
+    size_t tot_o = 0, tot_r = 0;
+    for (size_t b = 0; b < nblk; ++b) { tot_o += bo[b].size(); tot_r += br[b].size(); }
+    S.orfs.reserve(tot_o); S.orf_blk.reserve(tot_o); S.residues.reserve(tot_r);
+    for (size_t b = 0; b < nblk; ++b) {
+      S.orf_begin[b] = (int) S.orfs.size();
+      for (Orf &o : bo[b]) { o.offset += (long long) S.residues.size(); S.orfs.push_back(o); S.orf_blk.push_back((int) b); }
+      S.residues.insert(S.residues.end(), br[b].begin(), br[b].end());
+    }
+    S.orf_begin[nblk] = (int) S.orfs.size();
+  }
+  const int norf = (int) S.orfs.size();
+  s->st.n_orfs += norf;
+  S.P_orf.assign((size_t) norf, 1.0);
+  S.fwdsc_orf.assign((size_t) norf, kNegInfF);
+  S.wins_of_orf.assign((size_t) norf, {});
+  tm.lap(s->st.us_orfs);
 
-  BE_TRY(s, s->be.upload_block(s->be.ctx, blk.dsq, blk.n), "bathgpu_upload_block");
-  BE_TRY(s, s->be.upload_orfs(s->be.ctx, residues.data(), (int64_t) residues.size()), "bathgpu_upload_orfs");
+  BE_TRY(s, s->be.select_slot(s->be.ctx, slot), "bathgpu_select_slot");
+  BE_TRY(s, s->be.upload_block(s->be.ctx, S.dsq.data(), n_total), "bathgpu_upload_block");
+  if (norf == 0) return 0;
+  BE_TRY(s, s->be.upload_orfs(s->be.ctx, S.residues.data(), (int64_t) S.residues.size()), "bathgpu_upload_orfs");
+  tm.lap(s->st.us_upload);
 
+  std::vector<Orf> &orfs = S.orfs;
+  const std::vector<uint8_t> &residues = S.residues;
   auto orf_dsq = [&](const Orf &o, std::vector<uint8_t> &buf) {      // 1-based with sentinels, for the bias filter
     buf.assign((size_t) o.n + 2, 255);
     memcpy(buf.data() + 1, residues.data() + o.offset, (size_t) o.n);
@@ -427,32 +501,47 @@ int run_block(bathhost_search *s, const Block &blk)
   std::vector<int> live;
   for (int i = 0; i < norf; ++i) {
     const Orf &o = orfs[i];
-    const bool in_context = blk.complement ? ((blk.n - o.start + 1) < blk.C) : (o.end < blk.C);
+    const BlockInfo &blk = blocks[S.orf_blk[i]];
+    const bool in_context = S.complement ? ((blk.n - o.start + 1) < blk.C) : (o.end < blk.C);
     if (!in_context && o.n > 0) live.push_back(i);
   }
   if (live.empty()) return 0;
+  // per-length integers and null1 scores depend on the ORF length only: tabulate them once per strand
+  int maxlen = 0;
+  for (int i : live) maxlen = std::max(maxlen, orfs[i].n);
+  std::vector<uint8_t> tjb_of((size_t) maxlen + 1);
+  std::vector<int16_t> xw_of((size_t) maxlen + 1);
+  std::vector<float>   null_of((size_t) maxlen + 1);
+  for (int L = 1; L <= maxlen; ++L) {
+    tjb_of[L] = q.tjb_for_length(L); xw_of[L] = q.xw_move_for_length(L);
+    bg.set_length(L); null_of[L] = bg.null_one(L);
+  }
   std::vector<bathgpu_orf> desc(live.size());
   for (size_t t = 0; t < live.size(); ++t) {
     const Orf &o = orfs[live[t]];
     bathgpu_orf &d = desc[t];
     memset(&d, 0, sizeof d);
     d.offset = o.offset; d.L = o.n;
-    d.tjb_b = q.tjb_for_length(o.n); d.xw_move = q.xw_move_for_length(o.n);
+    d.tjb_b = tjb_of[o.n]; d.xw_move = xw_of[o.n];
   }
   std::vector<float> usc(live.size());
   std::vector<int32_t> ust(live.size());
   BE_TRY(s, s->be.msv_orfs(s->be.ctx, desc.data(), (int) desc.size(), usc.data(), ust.data()), "bathgpu_msv_orfs");
-
+  tm.lap(s->st.us_msv);
   struct Cand { int orf; float nullsc, usc, filtersc, vfsc; double P; bool need_vit; };
   std::vector<Cand> cand;
   std::vector<uint8_t> buf;
+  // the Gumbel tail is monotone: P > F1 exactly when the bit score is below x1 = invsurv(F1); the tail is only evaluated
+  // for scores within a margin of x1 (where rounding could matter) or above it
+  const double x1 = gumbel_invsurv(opt.F1, ev[EV_MMU], ev[EV_MLAMBDA]);
   for (size_t t = 0; t < live.size(); ++t) {
     const Orf &o = orfs[live[t]];
-    bg.set_length(o.n);
-    const float nullsc = bg.null_one(o.n);
+    const float nullsc = null_of[o.n];
     float seqsc = (usc[t] - nullsc) / kLog2;
+    if (seqsc < x1 - 0.01) continue;
     double P = gumbel_surv(seqsc, ev[EV_MMU], ev[EV_MLAMBDA]);
     if (P > opt.F1) continue;
+    bg.set_length(o.n);
     s->st.pos_past_msv += (int64_t) o.n * 3;
     float filtersc = nullsc;
     if (opt.do_bias) {                                  // (:1657-1663)
@@ -466,10 +555,10 @@ int run_block(bathhost_search *s, const Block &blk)
     Cand c; c.orf = live[t]; c.nullsc = nullsc; c.usc = usc[t]; c.filtersc = filtersc; c.vfsc = kNegInfF; c.P = P; c.need_vit = (P > opt.F2);
     cand.push_back(c);
   }
+  tm.lap(s->st.us_bias);
   if (cand.empty()) return 0;
 
   // ---- stage 2: Viterbi filter with windows, or the SSV window finder for ORFs already below F2 (:1666-1680)
-  std::vector<OrfWin> hit_windows;                       // grouped by ORF in candidate order, target order inside
   auto make_desc = [&](const Cand &c, bool windows) {
     const Orf &o = orfs[c.orf];
     bathgpu_orf d; memset(&d, 0, sizeof d);
@@ -571,11 +660,10 @@ int run_block(bathhost_search *s, const Block &blk)
     }
     std::sort(keep.begin(), keep.end());
   }
+  tm.lap(s->st.us_vit);
   if (keep.empty()) return 0;
 
   // ---- stage 3: protein Forward over the survivors (:1774-1789)
-  std::vector<double> P_orf((size_t) norf, 1.0);
-  std::vector<float>  fwdsc_orf((size_t) norf, kNegInfF);
   {
     std::vector<bathgpu_orf> d(keep.size());
     for (size_t z = 0; z < keep.size(); ++z) d[z] = make_desc(cand[keep[z]], true);
@@ -586,17 +674,27 @@ int run_block(bathhost_search *s, const Block &blk)
     for (size_t z = 0; z < keep.size(); ++z) {
       const Cand &c = cand[keep[z]];
       const float seqsc = (fsc[z] - c.filtersc) / kLog2;
-      P_orf[c.orf] = exp_surv(seqsc, ev[EV_FTAU], ev[EV_FLAMBDA]);
-      fwdsc_orf[c.orf] = fsc[z] - c.nullsc;
-      for (const OrfWin &w : wins_of[keep[z]]) { OrfWin x = w; x.id = c.orf; hit_windows.push_back(x); }
+      S.P_orf[c.orf] = exp_surv(seqsc, ev[EV_FTAU], ev[EV_FLAMBDA]);
+      S.fwdsc_orf[c.orf] = fsc[z] - c.nullsc;
+      for (const OrfWin &w : wins_of[keep[z]]) { OrfWin x = w; x.id = c.orf - S.orf_begin[S.orf_blk[c.orf]]; S.wins_of_orf[c.orf].push_back(x); }
     }
   }
 
-  // ---- p7_pli_BuildDNAWindows (:462-572)
+  tm.lap(s->st.us_fwd);
+  return 0;
+}
+
+// p7_pli_BuildDNAWindows (src/p7_pipeline.c:462-572) for one block-strand, against the accumulated hit_windows list
+void build_dna_windows(bathhost_search *s, Strand &S, const BlockInfo &blk, int b, const std::vector<OrfWin> &hit_windows)
+{
+  const ProteinProfile &q = s->model->prot;
+  const Options &opt = s->opt;
+  const int M = q.M;
   std::vector<DnaWin> dwin;
-  for (int f = 0; f < norf; ++f) {
-    if (P_orf[f] > opt.F4) continue;
-    Orf &o = orfs[f];
+  for (int gi = S.orf_begin[b]; gi < S.orf_begin[b + 1]; ++gi) {
+    const int f = gi - S.orf_begin[b];
+    if (S.P_orf[gi] > opt.F4) continue;
+    Orf &o = S.orfs[gi];
     int best = -1; float best_score = kNegInfF;
     for (size_t w = 0; w < hit_windows.size(); ++w) {
       if (hit_windows[w].id != f) continue;
@@ -616,11 +714,9 @@ int run_block(bathhost_search *s, const Block &blk)
     ws = std::max<long long>(1, o.start + ws * 3);       // (n - start_ref + 1) == o.start on the bottom strand
     we = std::min<long long>(blk.n, o.start + we * 3);
     dwin.push_back(DnaWin{ ws, cw.k, (int) (we - ws + 1) });
-    o.window_idx = (int) dwin.size() - 1;
   }
-  if (dwin.empty()) return 0;
-  std::stable_sort(dwin.begin(), dwin.end(), [](const DnaWin &a, const DnaWin &b) { return a.n < b.n; });
-  {
+  if (!dwin.empty()) {
+    std::stable_sort(dwin.begin(), dwin.end(), [](const DnaWin &x, const DnaWin &y) { return x.n < y.n; });
     size_t nh = 0;
     for (size_t i = 1; i < dwin.size(); ++i) {
       DnaWin &pw = dwin[nh];
@@ -634,159 +730,302 @@ int run_block(bathhost_search *s, const Block &blk)
     }
     dwin.resize(nh + 1);
   }
+  for (const DnaWin &d : dwin) { S.dwin.push_back(d); S.dwin_blk.push_back(b); }
+}
 
-  // ---- stage 4: frameshift Forward parser over every DNA window (:1392-1454)
-  const int nwin = (int) dwin.size();
-  std::vector<bathgpu_window> gw((size_t) nwin);
-  for (int w = 0; w < nwin; ++w) {
-    gw[w].start = dwin[w].n; gw[w].L = dwin[w].length;
-    bathhost_length_model(dwin[w].length / 3, 1.0f, &gw[w].pmove, &gw[w].ploop);
+int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, int64_t n)
+{
+  const bathhost_model *m = s->model;
+  const ProteinProfile &q = m->prot;
+  const Options &opt = s->opt;
+  const int M = q.M;
+  const float *ev = m->hmm.evparam;
+  Background &bg = s->bg;
+
+  // ---- the reference's blocks (src/bathsearch.c:1060-1105) and the residue count as each block-strand is reached
+  std::vector<BlockInfo> blocks;
+  {
+    const int C = q.max_length * 3, W = opt.block_length;
+    int64_t pos = 1;
+    bool first = true;
+    long long nres = s->st.nres;
+    while (pos <= n) {
+      const int64_t ctx = first ? 0 : std::min<int64_t>(C, pos - 1);
+      BlockInfo b;
+      b.b0 = pos - ctx; b.b1 = std::min<int64_t>(n, pos + W - 1);
+      b.n = (int) (b.b1 - b.b0 + 1); b.C = (int) ctx; b.bw = (int) (b.b1 - pos + 1);
+      b.nres_at[0] = b.nres_at[1] = nres;
+      if (b.n >= 15) {
+        if (opt.top)    { nres += b.bw; b.nres_at[0] = nres; }
+        if (opt.bottom) { nres += b.bw; b.nres_at[1] = nres; }
+      }
+      blocks.push_back(b);
+      pos = b.b1 + 1;
+      first = false;
+    }
+    s->st.nres = nres;
   }
+  const size_t nb = blocks.size();
+
+  Strand strands[2];
+  std::vector<int> active;
+  if (opt.top)    active.push_back(0);
+  if (opt.bottom) active.push_back(1);
+  for (int sidx : active) {
+    Strand &S = strands[sidx];
+    S.complement = (sidx == 1);
+    S.dsq.assign((size_t) n + 2, 255);
+    memcpy(S.dsq.data() + 1, dsq + 1, (size_t) n);
+    if (S.complement) revcomp(S.dsq, (int) n);
+    int st = filter_strand(s, S, blocks, n, sidx);
+    if (st != 0) return st;
+  }
+
+  // ---- DNA windows, block by block in the reference's order, against the ever-growing hit_windows list
+  StageTimer tm;
+  std::vector<OrfWin> hit_windows;
+  for (int sidx : active) { strands[sidx].dwin_begin.assign(nb + 1, 0); strands[sidx].hw_count.assign(nb, 0); }
+  for (size_t b = 0; b < nb; ++b)
+    for (int sidx : active) {
+      Strand &S = strands[sidx];
+      S.dwin_begin[b] = (int) S.dwin.size();
+      if (blocks[b].n >= 15) {
+        for (int gi = S.orf_begin[b]; gi < S.orf_begin[b + 1]; ++gi)
+          for (const OrfWin &w : S.wins_of_orf[gi]) hit_windows.push_back(w);
+        S.hw_count[b] = hit_windows.size();
+        build_dna_windows(s, S, blocks[b], (int) b, hit_windows);
+      } else S.hw_count[b] = hit_windows.size();
+      S.dwin_begin[b + 1] = (int) S.dwin.size();
+    }
+  for (int sidx : active) for (size_t b = 0; b + 1 <= nb; ++b) strands[sidx].dwin_begin[b + 1] = std::max(strands[sidx].dwin_begin[b + 1], strands[sidx].dwin_begin[b]);
+  tm.lap(s->st.us_windows);
+
+  // ---- stage 4: frameshift Forward parser over every DNA window, one call per strand (:1446-1450)
   const float xfE3[2] = { m->om3.xfE_move, m->om3.xfE_loop };
-  std::vector<float> fs_fwd((size_t) nwin);
-  std::vector<int32_t> fs_st((size_t) nwin);
-  BE_TRY(s, s->be.fs_fwd_windows(s->be.ctx, gw.data(), nwin, xfE3, fs_fwd.data(), fs_st.data()), "bathgpu_fs_fwd_windows");
-  s->st.n_windows += nwin;
+  for (int sidx : active) {
+    Strand &S = strands[sidx];
+    const int nwin = (int) S.dwin.size();
+    if (nwin == 0) continue;
+    S.gw.resize((size_t) nwin);
+    for (int w = 0; w < nwin; ++w) {
+      S.gw[w].start = S.goff(blocks[S.dwin_blk[w]], n) + S.dwin[w].n; S.gw[w].L = S.dwin[w].length;
+      bathhost_length_model(S.dwin[w].length / 3, 1.0f, &S.gw[w].pmove, &S.gw[w].ploop);
+    }
+    S.fs_fwd.resize((size_t) nwin); S.fs_st.resize((size_t) nwin);
+    BE_TRY(s, s->be.select_slot(s->be.ctx, sidx), "bathgpu_select_slot");
+    BE_TRY(s, s->be.fs_fwd_windows(s->be.ctx, S.gw.data(), nwin, xfE3, S.fs_fwd.data(), S.fs_st.data()), "bathgpu_fs_fwd_windows");
+    s->st.n_windows += nwin;
+  }
+  tm.lap(s->st.us_fs_fwd);
 
-  for (int w = 0; w < nwin; ++w) {
-    const DnaWin &dw = dwin[w];
-    const uint8_t *wdsq = blk.dsq + dw.n - 1;            // window position p is wdsq[p]
-    int orf_cnt = 0, k_min = M, k_max = 0;
-    float tot_orfsc = kNegInfF;
-    double P_tot, P_min = std::numeric_limits<double>::infinity();
-    size_t last_h = 0;
-    for (int i = 0; i < norf; ++i) {
-      if (P_orf[i] > opt.F4) continue;
-      const Orf &o = orfs[i];
-      const bool inside = blk.complement ? (o.start >= dw.n && o.end <= dw.n + dw.length + 1)
+  // ---- arbitration per window (:1392-1465)
+  float lcompo[kK];
+  for (int sidx : active) {
+    Strand &S = strands[sidx];
+    for (int w = 0; w < (int) S.dwin.size(); ++w) {
+      const int b = S.dwin_blk[w];
+      const BlockInfo &blk = blocks[b];
+      const DnaWin &dw = S.dwin[w];
+      const uint8_t *wdsq = S.dsq.data() + S.goff(blk, n) + dw.n - 1;        // window position p is wdsq[p]
+      int orf_cnt = 0, k_min = M, k_max = 0;
+      float tot_orfsc = kNegInfF;
+      double P_tot, P_min = std::numeric_limits<double>::infinity();
+      size_t last_h = 0;
+      const size_t hw_n = S.hw_count[b];
+      for (int gi = S.orf_begin[b]; gi < S.orf_begin[b + 1]; ++gi) {
+        if (S.P_orf[gi] > opt.F4) continue;
+        const int i = gi - S.orf_begin[b];
+        const Orf &o = S.orfs[gi];
+        const bool inside = S.complement ? (o.start >= dw.n && o.end <= dw.n + dw.length + 1)
                                          : (o.start >= dw.n && o.end <= dw.n + dw.length - 1);
-      if (!inside) continue;
-      orfs[i].window_idx = w;
-      P_min = std::min(P_min, P_orf[i]);
-      tot_orfsc = flogsum(tot_orfsc, fwdsc_orf[i]);
-      orf_cnt++;
-      size_t h = last_h;
-      while (h < hit_windows.size() && hit_windows[h].id != i) h++;
-      if (h < hit_windows.size()) {
-        while (h < hit_windows.size() && hit_windows[h].id == i) {
-          k_min = std::min(k_min, hit_windows[h].k - hit_windows[h].length + 1);
-          k_max = std::max(k_max, hit_windows[h].k);
-          h++;
+        if (!inside) continue;
+        P_min = std::min(P_min, S.P_orf[gi]);
+        tot_orfsc = flogsum(tot_orfsc, S.fwdsc_orf[gi]);
+        orf_cnt++;
+        size_t h = last_h;
+        while (h < hw_n && hit_windows[h].id != i) h++;
+        if (h < hw_n) {
+          while (h < hw_n && hit_windows[h].id == i) {
+            k_min = std::min(k_min, hit_windows[h].k - hit_windows[h].length + 1);
+            k_max = std::max(k_max, hit_windows[h].k);
+            h++;
+          }
+          last_h = h;
         }
-        last_h = h;
       }
-    }
-    P_tot = exp_surv(tot_orfsc / kLog2, ev[EV_FTAU], ev[EV_FLAMBDA]);
+      P_tot = exp_surv(tot_orfsc / kLog2, ev[EV_FTAU], ev[EV_FLAMBDA]);
 
-    bg.set_length(dw.length / 3);
-    const float nullsc = bg.fs_null_one(dw.length / 3);
-    float filtersc = nullsc;
-    if (opt.do_bias) {
-      filtersc = bg.fs_filter_score(wdsq, dw.length, s->gcode);
-      if (k_min <= k_max) {
-        local_compo(m, bg, k_min, k_max, lcompo);
-        bg.set_filter(M, lcompo);
-        bg.set_length(dw.length / 3);
-        const float lf = bg.fs_filter_score(wdsq, dw.length, s->gcode);
-        if (lf > filtersc) filtersc = lf;
-        bg.set_filter(M, s->compo.data());
-        bg.set_length(dw.length / 3);
+      bg.set_length(dw.length / 3);
+      const float nullsc = bg.fs_null_one(dw.length / 3);
+      float filtersc = nullsc;
+      if (opt.do_bias) {
+        filtersc = bg.fs_filter_score(wdsq, dw.length, s->gcode);
+        if (k_min <= k_max) {
+          local_compo(m, bg, k_min, k_max, lcompo);
+          bg.set_filter(M, lcompo);
+          bg.set_length(dw.length / 3);
+          const float lf = bg.fs_filter_score(wdsq, dw.length, s->gcode);
+          if (lf > filtersc) filtersc = lf;
+          bg.set_filter(M, s->compo.data());
+          bg.set_length(dw.length / 3);
+        }
       }
+      if (S.fs_st[w] != 0) continue;                        // eslERANGE from the Forward parser: treated as no score
+      const float fwdsc = S.fs_fwd[w];
+      const float seqscore = (fwdsc - filtersc) / kLog2;
+      const double P_fs   = exp_surv(seqscore, ev[EV_FTAUFS3], ev[EV_FLAMBDA]);
+      const double P_null = exp_surv((fwdsc - nullsc) / kLog2, ev[EV_FTAUFS3], ev[EV_FLAMBDA]);
+      if (P_fs <= opt.F3 && (P_null < P_tot || (P_null == P_tot && orf_cnt > 1) || P_min > opt.F3)) {
+        s->st.pos_past_fwd += dw.length;
+        S.fsw.push_back(w);
+      } else s->st.n_std_windows++;                         // standard-translation branch (:1480-1511): not restated yet
     }
-    if (fs_st[w] != 0) continue;                          // eslERANGE from the Forward parser: treated as no score
-    const float fwdsc = fs_fwd[w];
-    const float seqscore = (fwdsc - filtersc) / kLog2;
-    const double P_fs   = exp_surv(seqscore, ev[EV_FTAUFS3], ev[EV_FLAMBDA]);
-    const double P_null = exp_surv((fwdsc - nullsc) / kLog2, ev[EV_FTAUFS3], ev[EV_FLAMBDA]);
+  }
+  tm.lap(s->st.us_bias);
 
-    if (P_fs <= opt.F3 && (P_null < P_tot || (P_null == P_tot && orf_cnt > 1) || P_min > opt.F3)) {
-      // ---- frameshift branch (:1465-1477)
-      s->st.pos_past_fwd += dw.length;
-      const float xf5_loop = 1.0f - (2.0f + s->om5_nj) / ((float) s->om5_L + 2.0f + s->om5_nj);
-      const float xf5[3] = { xf5_loop, xf5_loop, xf5_loop };
-      const int64_t off0 = 0;
-      std::vector<float> mocc((size_t) dw.length + 1), btot((size_t) dw.length + 1), etot((size_t) dw.length + 1);
-      float f2 = 0, b2 = 0; int32_t st2 = 0;
-      BE_TRY(s, s->be.fs_bck_decode(s->be.ctx, &gw[w], 1, xfE3, xf5, &off0, mocc.data(), btot.data(), etot.data(), &f2, &b2, &st2), "bathgpu_fs_bck_decode");
-      if (st2 != 0) continue;                             // backward underflow: skip domain definition (:1471)
+  // ---- stage 5: Forward (X rows kept) + Backward parsers over the frameshift-branch windows, one call per strand (:1469-1470)
+  for (int sidx : active) {
+    Strand &S = strands[sidx];
+    if (S.fsw.empty()) continue;
+    std::vector<bathgpu_window> gf(S.fsw.size());
+    S.xoff.assign(S.fsw.size() + 1, 0);
+    for (size_t z = 0; z < S.fsw.size(); ++z) { gf[z] = S.gw[S.fsw[z]]; S.xoff[z + 1] = S.xoff[z] + (size_t) gf[z].L + 1; }
+    S.fxr.resize(S.xoff.back() * 6); S.bxr.resize(S.xoff.back() * 6); S.st2.resize(S.fsw.size());
+    std::vector<float> f2(S.fsw.size()), b2(S.fsw.size());
+    BE_TRY(s, s->be.select_slot(s->be.ctx, sidx), "bathgpu_select_slot");
+    BE_TRY(s, s->be.fs_fwd_bck_xrows(s->be.ctx, gf.data(), (int) gf.size(), xfE3, S.fxr.data(), S.bxr.data(), f2.data(), b2.data(), S.st2.data()),
+           "bathgpu_fs_fwd_bck_xrows");
+  }
+  tm.lap(s->st.us_fs_fwd);
 
-      // region finding (src/p7_domaindef.c:324-383).  The profile is switched to unihit at the saved length first.
-      const int saveL = 100;                              // gm_fs5->L: the dummy length bathsearch configures and never changes (src/bathsearch.c:797)
-      s->om5_nj = 0.0f; s->om5_L = saveL / 3;             // p7_fs_oprofile_ReconfigUnihit(om_fs5, saveL/3)
-      const int Lw = dw.length;
-      const float rt1 = 0.25f, rt2 = 0.10f, rt3 = 0.20f;
-      std::vector<std::pair<int, int>> envs;
-      {
-        int i = -1, d = 0; bool triggered = false, start = false, end = false;
-        for (int j = 1; j < Lw; ++j) {
-          if (!triggered) { if (mocc[j] >= rt1) triggered = true; d = j; }
-          else {
-            while (d > 1 && !start) {
-              d--;
-              if (d > 3 && mocc[d] - (btot[d] - btot[d - 3]) < rt2) { d--;
+  // ---- domain decoding and region finding on the host, in the reference's order (block, then strand, then window):
+  // the length model of om_fs5 that p7_DomainDecoding_Frameshift reads is whatever the previous window's rescoring left
+  // (src/p7_domaindef.c:320-325, :1018)
+  const float rt1 = 0.25f, rt2 = 0.10f, rt3 = 0.20f;
+  const int saveL = 100;                                    // gm_fs5->L: the dummy length bathsearch configures and never changes (src/bathsearch.c:797)
+  {
+    size_t zpos[2] = { 0, 0 };
+    for (size_t b = 0; b < nb; ++b)
+      for (int sidx : active) {
+        Strand &S = strands[sidx];
+        for (; zpos[sidx] < S.fsw.size() && S.dwin_blk[S.fsw[zpos[sidx]]] == (int) b; ++zpos[sidx]) {
+          const size_t z = zpos[sidx];
+          if (S.st2[z] != 0) continue;                      // backward underflow: skip domain definition for this window (:1471)
+          const int w = S.fsw[z];
+          const int Lw = S.dwin[w].length;
+          const float *xf = &S.fxr[S.xoff[z] * 6], *xb = &S.bxr[S.xoff[z] * 6];
+          const float tL = 1.0f - (2.0f + s->om5_nj) / ((float) s->om5_L + 2.0f + s->om5_nj);
+          std::vector<float> mocc((size_t) Lw + 1, 0.f), btot((size_t) Lw + 1, 0.f), etot((size_t) Lw + 1, 0.f);
+          {   // p7_DomainDecoding_Frameshift (src/impl_sse/decoding_fs.c:245-359)
+            std::vector<float> lsf((size_t) Lw + 2), lsb((size_t) Lw + 2);
+            lsf[0] = logf(xf[5]);
+            for (int i = 1; i <= Lw; ++i) lsf[i] = lsf[i - 1] + logf(xf[(size_t) i * 6 + 5]);
+            lsb[Lw + 1] = 0.0f;
+            for (int i = Lw; i >= 0; --i) lsb[i] = lsb[i + 1] + logf(xb[(size_t) i * 6 + 5]);
+            const float liz = -flogsum(logf(xb[0 * 6 + 1]) + lsb[0], flogsum(logf(xb[1 * 6 + 1]) + lsb[1], logf(xb[2 * 6 + 1]) + lsb[2]));
+            auto F = [&](int i, int c) { return xf[(size_t) i * 6 + c]; };
+            auto B = [&](int i, int c) { return xb[(size_t) i * 6 + c]; };
+            for (int i = 3; i <= Lw; ++i) {
+              btot[i] = btot[i - 3] + F(i - 3, 3) * B(i - 3, 3) * expf(lsf[i - 3] + lsb[i - 3] + liz);
+              etot[i] = etot[i - 3] + F(i, 0) * B(i, 0) * expf(lsf[i] + lsb[i] + liz);
+              float njcp = 0.;
+              static const int cells[3] = { 1, 2, 4 };      // N, J, C
+              for (int c : cells) {
+                njcp += F(i - 3, c) * B(i, c) * tL * expf(lsf[i - 3] + lsb[i] + liz);
+                if (i < Lw)     njcp += F(i - 2, c) * B(i + 1, c) * tL * expf(lsf[i - 2] + lsb[i + 1] + liz);
+                if (i < Lw - 1) njcp += F(i - 1, c) * B(i + 2, c) * tL * expf(lsf[i - 1] + lsb[i + 2] + liz);
+              }
+              mocc[i] = 1. - njcp;
+            }
+          }
+          s->om5_nj = 0.0f; s->om5_L = saveL / 3;           // p7_fs_oprofile_ReconfigUnihit(om_fs5, saveL/3) (:325)
+          // region finding (src/p7_domaindef.c:332-383)
+          int i = -1, d = 0; bool triggered = false, start = false, end = false;
+          for (int j = 1; j < Lw; ++j) {
+            if (!triggered) { if (mocc[j] >= rt1) triggered = true; d = j; }
+            else {
+              while (d > 1 && !start) {
+                d--;
                 if (d > 3 && mocc[d] - (btot[d] - btot[d - 3]) < rt2) { d--;
-                  if (d > 3 && mocc[d] - (btot[d] - btot[d - 3]) < rt2) { d--; start = true; } } }
-            }
-            i = std::max(1, d - 3);
-            d = j + 1;
-            while (d < Lw && !end) {
-              d++;
-              if (d < Lw && mocc[d] - (etot[d] - etot[d - 3]) < rt2) { d++;
+                  if (d > 3 && mocc[d] - (btot[d] - btot[d - 3]) < rt2) { d--;
+                    if (d > 3 && mocc[d] - (btot[d] - btot[d - 3]) < rt2) { d--; start = true; } } }
+              }
+              i = std::max(1, d - 3);
+              d = j + 1;
+              while (d < Lw && !end) {
+                d++;
                 if (d < Lw && mocc[d] - (etot[d] - etot[d - 3]) < rt2) { d++;
-                  if (d < Lw && mocc[d] - (etot[d] - etot[d - 3]) < rt2) { d++; end = true; } } }
-            }
-            j = std::min(Lw, d + 3);
-            if (j - i + 1 >= 12) {
-              s->st.n_regions++;
-              // is_multidomain_region_frameshift (:684-714)
-              float mx = -1.0f;
-              auto scan = [&](int z0, int eoff, int f) {
-                for (int z = z0; z <= j - f; z += 3) {
-                  const float en = std::min(etot[z] - etot[i + eoff], btot[j - f] - btot[z - 3]);
-                  mx = std::max(mx, en);
+                  if (d < Lw && mocc[d] - (etot[d] - etot[d - 3]) < rt2) { d++;
+                    if (d < Lw && mocc[d] - (etot[d] - etot[d - 3]) < rt2) { d++; end = true; } } }
+              }
+              j = std::min(Lw, d + 3);
+              if (j - i + 1 >= 12) {
+                s->st.n_regions++;
+                float mx = -1.0f;                           // is_multidomain_region_frameshift (:684-714)
+                auto scan = [&](int z0, int eoff, int f) {
+                  for (int zz = z0; zz <= j - f; zz += 3) {
+                    const float en = std::min(etot[zz] - etot[i + eoff], btot[j - f] - btot[zz - 3]);
+                    mx = std::max(mx, en);
+                  }
+                };
+                scan(i + 2, -1, (j - i + 1) % 3);
+                scan(i + 3, 0, (j - i) % 3);
+                scan(i + 4, 1, (j - i - 1) % 3);
+                if (mx >= rt3) s->st.n_multidomain_regions++;   // rescored as ONE envelope (see the file header)
+                const int Ld = j - i + 1;
+                if (Ld >= 15) {                              // rescore_isolated_domain_frameshift returns at once below 15 (:1012)
+                  bathgpu_envelope g;
+                  g.start = S.gw[w].start + i - 1; g.L = Ld;
+                  bathhost_length_model(Ld / 3, 0.0f, &g.pmove, &g.ploop);
+                  S.ge.push_back(g); S.envs.push_back(Strand::Env{ w, i, j });
+                  s->om5_nj = 0.0f; s->om5_L = Ld / 3;       // p7_fs_oprofile_ReconfigLength(om_fs5, Ld/3) (:1018)
                 }
-              };
-              scan(i + 2, -1, (j - i + 1) % 3);
-              scan(i + 3, 0, (j - i) % 3);
-              scan(i + 4, 1, (j - i - 1) % 3);
-              if (mx >= rt3) s->st.n_multidomain_regions++;      // rescored as ONE envelope (see the file header)
-              envs.emplace_back(i, j);
+              }
+              i = -1; triggered = false; start = false; end = false;
             }
-            i = -1; triggered = false; start = false; end = false;
           }
         }
       }
-      if (envs.empty()) continue;
+  }
+  tm.lap(s->st.us_windows);
 
-      // ---- per-envelope rescoring (rescore_isolated_domain_frameshift, :993-1191): one batched call
-      std::vector<bathgpu_envelope> ge;
-      std::vector<std::pair<int, int>> used;
-      for (auto &e : envs) {
-        const int Ld = e.second - e.first + 1;
-        if (Ld < 15) continue;
-        bathgpu_envelope g;
-        g.start = dw.n + e.first - 1; g.L = Ld;
-        bathhost_length_model(Ld / 3, 0.0f, &g.pmove, &g.ploop);
-        ge.push_back(g); used.push_back(e);
-        s->om5_nj = 0.0f; s->om5_L = Ld / 3;               // p7_fs_oprofile_ReconfigLength(om_fs5, Ld/3) (:1018)
-      }
-      if (ge.empty()) continue;
-      std::vector<bathgpu_domain_result> res(ge.size());
-      int64_t max_steps = 0; for (auto &g : ge) max_steps += g.L + M + 8;
-      std::vector<bathgpu_trace_step> traces((size_t) max_steps);
-      const float xfE5[2] = { 1.0f, 0.0f };
-      BE_TRY(s, s->be.fs_domains(s->be.ctx, ge.data(), (int) ge.size(), xfE5, res.data(), traces.data(), max_steps), "bathgpu_fs_domains");
-      s->st.n_envelopes += (int64_t) ge.size();
+  // ---- stage 6: every envelope of a strand rescored in one batched call (rescore_isolated_domain_frameshift, :993-1191)
+  const float xfE5[2] = { 1.0f, 0.0f };
+  for (int sidx : active) {
+    Strand &S = strands[sidx];
+    if (S.ge.empty()) continue;
+    S.res.resize(S.ge.size());
+    int64_t max_steps = 0; for (auto &g : S.ge) max_steps += g.L + M + 8;
+    S.traces.resize((size_t) max_steps);
+    BE_TRY(s, s->be.select_slot(s->be.ctx, sidx), "bathgpu_select_slot");
+    BE_TRY(s, s->be.fs_domains(s->be.ctx, S.ge.data(), (int) S.ge.size(), xfE5, S.res.data(), S.traces.data(), max_steps), "bathgpu_fs_domains");
+    s->st.n_envelopes += (int64_t) S.ge.size();
+  }
 
-      for (size_t e = 0; e < ge.size(); ++e) {
-        const int i = used[e].first, j = used[e].second, Ld = ge[e].L;
+  // ---- scoring and hit records, in the reference's order
+  {
+    size_t epos[2] = { 0, 0 };
+    for (size_t b = 0; b < nb; ++b)
+      for (int sidx : active) {
+        Strand &S = strands[sidx];
+        const std::vector<bathgpu_domain_result> &res = S.res;
+        const std::vector<bathgpu_trace_step> &traces = S.traces;
+        for (; epos[sidx] < S.envs.size() && S.dwin_blk[S.envs[epos[sidx]].win] == (int) b; ++epos[sidx]) {
+          const size_t e = epos[sidx];
+          const BlockInfo &binfo = blocks[b];
+          const DnaWin &dw = S.dwin[S.envs[e].win];
+          const uint8_t *wdsq = S.dsq.data() + S.goff(binfo, n) + dw.n - 1;
+          const int Lw = dw.length;
+          const long long nres_now = binfo.nres_at[sidx];
+          struct { bool complement; long long start; const char *name; long long sq_len; } blk = { S.complement, S.start_of(binfo), name, (long long) n };
+          const int i = S.envs[e].i, j = S.envs[e].j, Ld = S.ge[e].L;
         const bathgpu_domain_result &r = res[e];
         if (r.status != 0 && r.trace_len == 0) continue;   // Forward/Backward range error: envelope dropped (:1022,1041)
         bg.set_length(Ld / 3);
         const float env_null = bg.fs_null_one(Ld / 3);
         const float seqsc = (r.envsc - env_null) / kLog2;
         const double P = exp_surv(seqsc, ev[EV_FTAUFS5], ev[EV_FLAMBDA]);
-        const double Z = (float) s->st.nres / (float) q.max_length;
+        const double Z = (float) nres_now / (float) q.max_length;
         if (P * Z > opt.E) continue;                         // early cut on the residues seen so far (:1033-1037)
         if (r.status != 0) continue;
 
@@ -871,7 +1110,7 @@ int run_block(bathhost_search *s, const Block &blk)
         const float hit_null = bg.fs_null_one(nl);
         const float dom_score = (bitscore - (hit_null + dom_bias)) / kLog2;
         const double dom_lnP = exp_logsurv(dom_score, ev[EV_FTAUFS5], ev[EV_FLAMBDA]);
-        const double Z2 = (float) s->st.nres / (float) ml;
+        const double Z2 = (float) nres_now / (float) ml;
         if (!(exp(dom_lnP) * Z2 <= opt.E)) continue;
 
         Hit h;
@@ -893,11 +1132,12 @@ int run_block(bathhost_search *s, const Block &blk)
         summarize_alignment(m, dom.tr, wdsq, h.pub);
         h.sortkey = -dom_lnP;
         s->hits.push_back(h);
+        }
       }
-    } else {
-      s->st.n_std_windows++;      // standard-translation branch (:1480-1511): not restated yet
-    }
   }
+  tm.lap(s->st.us_fs_domains);
+  s->nseqs++;
+  s->st.nseqs = s->nseqs;
   return 0;
 }
 
@@ -947,43 +1187,11 @@ extern "C" int bathhost_search_create(const bathhost_model *m, const bathhost_ba
 extern "C" void bathhost_search_destroy(bathhost_search *s) { delete s; }
 extern "C" const char *bathhost_search_last_error(const bathhost_search *s) { return s ? s->err.c_str() : "no search"; }
 
-// One target sequence: dsq[1..n] (sentinels at 0 and n+1).  Read in blocks of block_length nucleotides that carry
-// max_length*3 nucleotides of left context (src/bathsearch.c:1060-1105), each searched on both strands.
+// One target sequence: dsq[1..n] (sentinels at 0 and n+1), both strands unless restricted.
 extern "C" int bathhost_search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, int64_t n)
 {
   if (!s || !dsq || n < 1) return BATHHOST_EINVAL;
-  const int C = s->model->prot.max_length * 3;
-  const int W = s->opt.block_length;
-  int64_t pos = 1;                                         // first NEW residue of the next block
-  bool first = true;
-  while (pos <= n) {
-    const int64_t ctx = first ? 0 : std::min<int64_t>(C, pos - 1);
-    const int64_t b0 = pos - ctx, b1 = std::min<int64_t>(n, pos + W - 1);
-    const int bn = (int) (b1 - b0 + 1), bw = (int) (b1 - pos + 1);
-    if (bn >= 15) {
-      std::vector<uint8_t> blk((size_t) bn + 2, 255);
-      memcpy(blk.data() + 1, dsq + b0, (size_t) bn);
-      Block b; b.dsq = blk.data(); b.n = bn; b.C = (int) ctx; b.seqidx = s->nseqs; b.name = name; b.sq_len = n;
-      if (s->opt.top) {
-        s->st.nres += bw;
-        b.start = b0; b.complement = false;
-        int st = run_block(s, b);
-        if (st != 0) return st;
-      }
-      if (s->opt.bottom) {
-        s->st.nres += bw;
-        revcomp(blk, bn);
-        b.start = b1; b.complement = true;
-        int st = run_block(s, b);
-        if (st != 0) return st;
-      }
-    }
-    pos = b1 + 1;
-    first = false;
-  }
-  s->nseqs++;
-  s->st.nseqs = s->nseqs;
-  return BATHHOST_OK;
+  return search_sequence(s, name, dsq, n);
 }
 
 // E-values over the whole search space, duplicate removal, final ordering and reporting threshold

@@ -159,6 +159,10 @@ int bathgpu_vit_orfs(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n, float *sc
 int bathgpu_fwd_orfs(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n, float nj, const float xfE[2], float *fwdsc, int32_t *status);
 
 /* ---- target block ------------------------------------------------------ */
+/* Two resident targets (slot 0 / 1), e.g. the two strands of a sequence: uploads and every stage call act on the
+ * selected slot, so the stages of both strands can be batched without re-uploading.  Slot 0 is selected at creation. */
+int bathgpu_select_slot(bathgpu_ctx *ctx, int slot);
+
 /* dsq: ESL_DSQ codes, dsq[1..n] valid (dsq[0], dsq[n+1] sentinels).  Packed to 4 bits/nt on device. */
 int bathgpu_upload_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_t n);
 
@@ -182,6 +186,12 @@ int bathgpu_fetch_scores(bathgpu_ctx *ctx, float *fwdsc, int32_t *status, int n)
 int bathgpu_fs_bck_decode(bathgpu_ctx *ctx, const bathgpu_window *wins, int n, const float xfE[2],
                           const float xf5_loop[3], const int64_t *out_offset,
                           float *mocc, float *btot, float *etot, float *fwdsc, float *bcksc, int32_t *status);
+
+/* a10 without a11: Forward (X rows kept) + Backward parsers over windows.  fwd_xrows / bck_xrows: {E,N,J,B,C,SCALE} x (L+1)
+ * per window, windows concatenated in call order (what P7_OMX->xmx holds, impl_sse.h:324), for a caller that runs
+ * p7_DomainDecoding_Frameshift itself. */
+int bathgpu_fs_fwd_bck_xrows(bathgpu_ctx *ctx, const bathgpu_window *wins, int n, const float xfE[2],
+                             float *fwd_xrows, float *bck_xrows, float *fwdsc, float *bcksc, int32_t *status);
 
 /* X rows {E,N,J,B,C,SCALE} x (L+1) per window, windows concatenated in call order, of the Forward (which = 0)
  * or Backward (which = 1) parser as left on the device by the last bathgpu_fs_bck_decode call (its last chunk):

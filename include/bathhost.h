@@ -100,6 +100,7 @@ typedef struct {
   const char *(*last_error)(const void *ctx);
   int (*load_fs_profile)(void *ctx, int which, int M, int nrows, const float *rfv, const float *tfv);
   int (*load_filter_profile)(void *ctx, const void *prm, const uint8_t *rbv, const int16_t *rwv, const int16_t *twv);
+  int (*select_slot)(void *ctx, int slot);
   int (*upload_block)(void *ctx, const uint8_t *dsq, int64_t n);
   int (*upload_orfs)(void *ctx, const uint8_t *residues, int64_t n);
   int (*msv_orfs)(void *ctx, const void *orfs, int n, float *sc, int32_t *status);
@@ -107,6 +108,8 @@ typedef struct {
   int (*vit_orfs)(void *ctx, const void *orfs, int n, float *sc, int32_t *status, void *wins, int max_wins, int *nwins);
   int (*fwd_orfs)(void *ctx, const void *orfs, int n, float nj, const float xfE[2], float *fwdsc, int32_t *status);
   int (*fs_fwd_windows)(void *ctx, const void *wins, int n, const float xfE[2], float *fwdsc, int32_t *status);
+  int (*fs_fwd_bck_xrows)(void *ctx, const void *wins, int n, const float xfE[2], float *fwd_xrows, float *bck_xrows,
+                          float *fwdsc, float *bcksc, int32_t *status);
   int (*fs_bck_decode)(void *ctx, const void *wins, int n, const float xfE[2], const float xf5_loop[3], const int64_t *out_offset,
                        float *mocc, float *btot, float *etot, float *fwdsc, float *bcksc, int32_t *status);
   int (*fs_domains)(void *ctx, const void *envs, int n, const float xfE5[2], void *results, void *traces, int64_t max_steps);
@@ -137,6 +140,8 @@ typedef struct {
   int64_t nseqs, nres;                                      /* "Target sequence(s)", "residues searched"      */
   int64_t pos_past_msv, pos_past_bias, pos_past_vit, pos_past_fwd;   /* the footer's filter counters          */
   int64_t n_orfs, n_windows, n_std_windows, n_regions, n_multidomain_regions, n_envelopes, n_hits_reported;
+  /* wall time per stage of the host pipeline, microseconds (host work + the device calls made from it) */
+  int64_t us_orfs, us_upload, us_msv, us_bias, us_vit, us_fwd, us_windows, us_fs_fwd, us_fs_domains;
 } bathhost_stats;
 
 typedef struct bathhost_search bathhost_search;
