@@ -240,11 +240,17 @@ def backend_from(gpu_lib, ctx_handle):
 class Search:
     """One query against target sequences: the stage-batched pipeline of bathsearch --fs (pipeline.cpp)."""
 
-    def __init__(self, model, gpu_ctx, **options):
+    def __init__(self, model, gpu_ctx=None, backend=None, **options):
+        """gpu_ctx: a capi.Context (the product path).  backend: a ready bathhost_backend table instead -- used by the tests
+        and the CPU-baseline legs of bench.py to put the CPU oracle behind the same pipeline."""
         self.lib = load()
         self.model = model
         self.gpu_ctx = gpu_ctx                       # keeps the device context alive
-        self.backend = backend_from(gpu_ctx.lib, gpu_ctx.h)
+        if backend is None:
+            if gpu_ctx is None:
+                raise ValueError("a device context is required: the product has no CPU path")
+            backend = backend_from(gpu_ctx.lib, gpu_ctx.h)
+        self.backend = backend
         opt = Options(**options)
         h = C.c_void_p()
         st = self.lib.bathhost_search_create(model.h, C.byref(self.backend), C.byref(opt), C.byref(h))

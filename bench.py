@@ -46,7 +46,8 @@ def parse_args():
     ap.add_argument("--window", type=int, default=1200, help="DNA window length Lw")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--search-mbp", type=float, default=20.0,
+    ap.add_argument("--search-cpu-mbp", type=float, default=4.0, help="size of the CPU-baseline sample of the search leg, Mbp")
+    ap.add_argument("--search-mbp", type=float, default=100.0,
                     help="also run the whole stage-batched bathsearch --fs pipeline over this many Mbp of the genome (0 = skip)")
     return ap.parse_args()
 
@@ -155,6 +156,7 @@ def run_reference(args, rank, world):
     cells = float(lengths[:n].astype(np.int64).sum()) * model.M
     value = cells * args.steps / dt / 1e9
     sample = f"{n} of {len(starts)} windows of {args.window} nt per step ({cells / 1e9:.3f} Gcells), {ncpu} threads"
+    search = search_leg_cpu(model, dsq, args.search_cpu_mbp, ncpu) if args.search_mbp > 0 else None
     print(json.dumps({
         "impl": "reference", "metric": "frameshift Forward GCUPS", "value": value, "unit": "GCUPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
@@ -162,6 +164,7 @@ def run_reference(args, rank, world):
         "config": workload_config(args, model.M, len(starts)),
         "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": ncpu, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "search": ({"metric": "bathsearch --fs Mbp/s", **search} if search else None),
         "note": "restated CPU oracle (scalar C, -O3 -march=native, pthreads over windows); the reference binary needs Easel, "
                 "which is not vendored, so it cannot be compiled here",
     }))
@@ -194,6 +197,28 @@ def search_leg(ctx, model, dsq, mbp, plants):
     return {"metric": "bathsearch --fs Mbp/s", "value": n / dt / 1e6, "unit": "Mbp/s", "seconds": dt, "target_mbp": n / 1e6,
             "hits": len(hits), "planted": len(planted), "planted_recovered": found, "stats": st,
             "note": "standard-translation branch and multi-domain clustering not restated yet (windows routed there are counted in stats.n_std_windows)"}
+
+
+def search_leg_cpu(model, dsq, mbp, nthreads):
+    """The same pipeline (bath_b200/host/pipeline.cpp) with the CPU oracle behind the stage calls (oracle/cpu_backend.c) on all
+    host threads, on a bounded prefix of the genome: the CPU baseline of the Mbp/s metric.  Oracle code is the thing timed here,
+    never part of the product path."""
+    from bath_b200 import hostapi
+    from oracle import pyoracle as po
+    po.lib(native=True)
+    be, keep = po.cpu_backend(nthreads)
+    n = int(min(mbp * 1e6, len(dsq) - 2))
+    sub = np.full(n + 2, 255, np.uint8)
+    sub[1:-1] = dsq[1:n + 1]
+    search = hostapi.Search(model, backend=be)
+    t0 = time.perf_counter()
+    search.add_sequence("synthetic", sub)
+    hits = search.finish()
+    dt = time.perf_counter() - t0
+    search.close()
+    del keep
+    return {"value": n / dt / 1e6, "unit": "Mbp/s", "cores": nthreads, "kind": "port", "hits": len(hits),
+            "sample": f"first {n / 1e6:g} Mbp of the genome ({dt:.1f} s, {nthreads} threads, scalar C oracle behind the same host pipeline)"}
 
 
 def workload_config(args, M, nwin):
@@ -337,7 +362,9 @@ def main():
                    "wall_ms_timed_loop_incl_flush": wall_ms},
     }
     if args.search_mbp > 0:
-        out["search"] = search_leg(ctx, model, dsq_np, args.search_mbp, plants)
+        out["search"] = search_leg(ctx, model, dsq_np, min(args.search_mbp, args.mbp), plants)
+        if world == 1 and not args.no_cpu_baseline:
+            out["search"]["cpu_baseline"] = search_leg_cpu(model, dsq_np, min(args.search_mbp, args.search_cpu_mbp), os.cpu_count() or 1)
     if world == 1 and not args.no_cpu_baseline:
         ncpu = os.cpu_count() or 1
         v, n, dt, osc = cpu_sample(M, dsq_np, starts, lengths, args.cpu_seconds, ncpu)

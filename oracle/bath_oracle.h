@@ -291,6 +291,10 @@ int    bo_SSVFilter_BATH(const uint8_t *dsq, int L, BO_OPROFILE *om, const uint8
 int    bo_ViterbiFilter(const uint8_t *dsq, int L, const BO_OPROFILE *om, float *ret_sc);
 int    bo_ViterbiFilter_BATH(const uint8_t *dsq, int L, const BO_OPROFILE *om, const uint8_t *ssv_scores, float filtersc, double P,
                              int lanes, BO_WINDOWLIST *wl, float *ret_sc);
+int    bo_SSVFilter_BATH_thresh(const uint8_t *dsq, int L, const BO_OPROFILE *om, const uint8_t *ssv_scores, uint8_t sc_thresh,
+                                int lanes, BO_WINDOWLIST *wl);
+int    bo_ViterbiFilter_BATH_thresh(const uint8_t *dsq, int L, const BO_OPROFILE *om, const uint8_t *ssv_scores, int16_t sc_thresh,
+                                    int sc_ext_thresh, int lanes, BO_WINDOWLIST *wl, float *ret_sc);
 void   bo_windowlist_reset(BO_WINDOWLIST *wl);
 void   bo_windowlist_free(BO_WINDOWLIST *wl);
 double bo_gumbel_invsurv(double p, double mu, double lambda);

@@ -1,0 +1,350 @@
+/* cpu_backend.c -- ORACLE (test infrastructure only; see bath_oracle.h).
+ *
+ * The batched stage calls of include/bathgpu.h implemented on the CPU with the oracle's scalar functions and a
+ * pool of POSIX threads -- the way the reference runs the same stages on its worker threads.  It exists so that
+ *   (1) the host pipeline (bath_b200/host/pipeline.cpp) can be checked against the reference's golden outputs on a
+ *       machine without a GPU (tests/test_host_pipeline_cpu.py), and
+ *   (2) bench.py's cpu_baseline / --impl reference legs can time the whole translated search on the host cores.
+ * It is handed to the host pipeline as a bathhost_backend table by TESTS AND BENCH ONLY; the product never loads it.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include <math.h>
+#include <pthread.h>
+#include "bath_oracle.h"
+#include "../include/bathgpu.h"
+
+typedef struct {
+  int             nthreads;
+  char            err[256];
+  BO_FS_OPROFILE *om3, *om5;
+  BO_OPROFILE    *om;             /* integer tables from load_filter_profile; float tables from the 3-codon image */
+  uint8_t        *ssv_scores;
+  int             lanes_u8, lanes_i16;
+  int             cur;
+  uint8_t        *dsq[2];   int64_t n[2];
+  uint8_t        *res[2];   int64_t nres[2];
+} bo_backend;
+
+bo_backend *bo_backend_create(int nthreads)
+{
+  bo_backend *b = calloc(1, sizeof(bo_backend));
+  if (b) b->nthreads = nthreads > 0 ? nthreads : 1;
+  bo_FLogsumInit();
+  return b;
+}
+
+void bo_backend_destroy(bo_backend *b)
+{
+  int s;
+  if (!b) return;
+  bo_fs_oprofile_destroy(b->om3); bo_fs_oprofile_destroy(b->om5); bo_oprofile_destroy(b->om);
+  free(b->ssv_scores);
+  for (s = 0; s < 2; s++) { free(b->dsq[s]); free(b->res[s]); }
+  free(b);
+}
+
+const char *bo_backend_last_error(const void *ctx) { return ctx ? ((const bo_backend *) ctx)->err : "no context"; }
+
+/* ---- parallel for over items ---- */
+typedef void (*item_fn)(bo_backend *b, void *arg, int item);
+typedef struct { bo_backend *b; void *arg; item_fn fn; int n, next; pthread_mutex_t mu; } pf_job;
+static void *pf_worker(void *p)
+{
+  pf_job *j = p;
+  for (;;) {
+    int i0, i1, i;
+    pthread_mutex_lock(&j->mu); i0 = j->next; j->next += 16; pthread_mutex_unlock(&j->mu);
+    if (i0 >= j->n) break;
+    i1 = i0 + 16 < j->n ? i0 + 16 : j->n;
+    for (i = i0; i < i1; i++) j->fn(j->b, j->arg, i);
+  }
+  return NULL;
+}
+static void parallel_for(bo_backend *b, int n, item_fn fn, void *arg)
+{
+  pf_job j; pthread_t th[64]; int t, nt = b->nthreads > 64 ? 64 : b->nthreads;
+  if (nt > n) nt = n > 0 ? n : 1;
+  j.b = b; j.arg = arg; j.fn = fn; j.n = n; j.next = 0; pthread_mutex_init(&j.mu, NULL);
+  for (t = 0; t < nt; t++) pthread_create(&th[t], NULL, pf_worker, &j);
+  for (t = 0; t < nt; t++) pthread_join(th[t], NULL);
+  pthread_mutex_destroy(&j.mu);
+}
+
+/* ---- profiles ---- */
+int bo_backend_load_fs_profile(void *ctx, int which, int M, int nrows, const float *rfv, const float *tfv)
+{
+  bo_backend *b = ctx;
+  BO_FS_OPROFILE *om = calloc(1, sizeof(BO_FS_OPROFILE));
+  if (!om) return BO_EMEM;
+  om->M = M; om->L = 100; om->mode = BO_LOCAL; om->codon_lengths = which; om->nrows = nrows; om->maxcodons = nrows - BO_KP; om->nj = 1.0f;
+  om->rfv = malloc(sizeof(float) * (size_t) nrows * (M + 1));
+  om->tfv = malloc(sizeof(float) * (size_t) 8 * (M + 1));
+  memcpy(om->rfv, rfv, sizeof(float) * (size_t) nrows * (M + 1));
+  memcpy(om->tfv, tfv, sizeof(float) * (size_t) 8 * (M + 1));
+  om->xf[BO_X_E][BO_O_MOVE] = 0.5f; om->xf[BO_X_E][BO_O_LOOP] = 0.5f;
+  if (which == 3) { bo_fs_oprofile_destroy(b->om3); b->om3 = om; } else { bo_fs_oprofile_destroy(b->om5); b->om5 = om; }
+  return BO_OK;
+}
+
+int bo_backend_load_filter_profile(void *ctx, const void *prm_, const uint8_t *rbv, const int16_t *rwv, const int16_t *twv)
+{
+  bo_backend *b = ctx;
+  const bathgpu_filter_params *p = prm_;
+  int M = p->M, x, k;
+  BO_OPROFILE *om;
+  if (!b->om3 || b->om3->M != M) { snprintf(b->err, sizeof b->err, "load the 3-codon profile first"); return BO_EINVAL; }
+  om = calloc(1, sizeof(BO_OPROFILE));
+  om->M = M; om->L = 100; om->mode = BO_LOCAL; om->nj = 1.0f;
+  om->tbm_b = p->tbm_b; om->tec_b = p->tec_b; om->base_b = p->base_b; om->bias_b = p->bias_b; om->scale_b = p->scale_b;
+  om->base_w = p->base_w; om->ddbound_w = p->ddbound_w; om->scale_w = p->scale_w;
+  om->xw[BO_X_E][BO_O_MOVE] = p->xw_E_move; om->xw[BO_X_E][BO_O_LOOP] = p->xw_E_loop;
+  om->rbv = malloc((size_t) BO_KP * (M + 1));                       memcpy(om->rbv, rbv, (size_t) BO_KP * (M + 1));
+  om->rwv = malloc(sizeof(int16_t) * (size_t) BO_KP * (M + 1));     memcpy(om->rwv, rwv, sizeof(int16_t) * (size_t) BO_KP * (M + 1));
+  om->twv = malloc(sizeof(int16_t) * (size_t) 8 * (M + 1));         memcpy(om->twv, twv, sizeof(int16_t) * (size_t) 8 * (M + 1));
+  /* float tables: the amino rows and transitions of the 3-codon image are the protein profile's (modelconfig.c:343-352) */
+  om->rfv = malloc(sizeof(float) * (size_t) BO_KP * (M + 1));
+  om->tfv = malloc(sizeof(float) * (size_t) 8 * (M + 1));
+  for (x = 0; x < BO_KP; x++) for (k = 0; k <= M; k++) om->rfv[(size_t) x * (M + 1) + k] = b->om3->rfv[(size_t)(b->om3->maxcodons + x) * (M + 1) + k];
+  memcpy(om->tfv, b->om3->tfv, sizeof(float) * (size_t) 8 * (M + 1));
+  om->xf[BO_X_E][BO_O_MOVE] = 0.5f; om->xf[BO_X_E][BO_O_LOOP] = 0.5f;
+  bo_oprofile_destroy(b->om); b->om = om;
+  free(b->ssv_scores);
+  b->ssv_scores = malloc((size_t)(M + 1) * BO_KP);
+  bo_oprofile_ssv_scores(om, b->ssv_scores);
+  b->lanes_u8 = p->cpu_lanes_u8; b->lanes_i16 = p->cpu_lanes_i16;
+  return BO_OK;
+}
+
+/* ---- targets ---- */
+int bo_backend_select_slot(void *ctx, int slot) { bo_backend *b = ctx; if (slot < 0 || slot > 1) return BO_EINVAL; b->cur = slot; return BO_OK; }
+
+int bo_backend_upload_block(void *ctx, const uint8_t *dsq, int64_t n)
+{
+  bo_backend *b = ctx;
+  free(b->dsq[b->cur]);
+  b->dsq[b->cur] = malloc((size_t) n + 2);
+  memcpy(b->dsq[b->cur], dsq, (size_t) n + 2);
+  b->n[b->cur] = n;
+  return BO_OK;
+}
+
+int bo_backend_upload_orfs(void *ctx, const uint8_t *residues, int64_t n)
+{
+  bo_backend *b = ctx;
+  free(b->res[b->cur]);
+  b->res[b->cur] = malloc((size_t) n);
+  memcpy(b->res[b->cur], residues, (size_t) n);
+  b->nres[b->cur] = n;
+  return BO_OK;
+}
+
+static uint8_t *orf_dsq(const bo_backend *b, const bathgpu_orf *o)
+{
+  uint8_t *d = malloc((size_t) o->L + 2);
+  d[0] = d[o->L + 1] = BO_DSQ_SENTINEL;
+  memcpy(d + 1, b->res[b->cur] + o->offset, (size_t) o->L);
+  return d;
+}
+
+/* ---- ORF stages ---- */
+typedef struct { const bathgpu_orf *orfs; float *sc; int32_t *st; BO_WINDOWLIST *wl; float nj; const float *xfE; int mode; } orf_args;
+
+static void orf_item(bo_backend *b, void *arg, int i)
+{
+  orf_args *a = arg;
+  const bathgpu_orf *o = &a->orfs[i];
+  BO_OPROFILE om = *b->om;                      /* private per-length pieces; tables shared */
+  uint8_t *d = orf_dsq(b, o);
+  om.tjb_b = o->tjb_b;
+  om.xw[BO_X_N][BO_O_MOVE] = om.xw[BO_X_C][BO_O_MOVE] = om.xw[BO_X_J][BO_O_MOVE] = o->xw_move;
+  om.xw[BO_X_N][BO_O_LOOP] = om.xw[BO_X_C][BO_O_LOOP] = om.xw[BO_X_J][BO_O_LOOP] = 0;
+  switch (a->mode) {
+  case 0: a->st[i] = bo_MSVFilter(d, o->L, &om, &a->sc[i]); break;
+  case 1: bo_SSVFilter_BATH_thresh(d, o->L, &om, b->ssv_scores, o->ssv_thresh, b->lanes_u8, &a->wl[i]); break;
+  case 2: a->st[i] = bo_ViterbiFilter_BATH_thresh(d, o->L, &om, b->ssv_scores, o->vit_thresh, o->ext_thresh, b->lanes_i16,
+                                                  (o->flags & 1) ? &a->wl[i] : NULL, &a->sc[i]); break;
+  case 3: {
+    float pmove = (2.0f + a->nj) / ((float) o->L + 2.0f + a->nj), ploop = 1.0f - pmove;
+    om.xf[BO_X_N][BO_O_LOOP] = om.xf[BO_X_C][BO_O_LOOP] = om.xf[BO_X_J][BO_O_LOOP] = ploop;
+    om.xf[BO_X_N][BO_O_MOVE] = om.xf[BO_X_C][BO_O_MOVE] = om.xf[BO_X_J][BO_O_MOVE] = pmove;
+    om.xf[BO_X_E][BO_O_MOVE] = a->xfE[0]; om.xf[BO_X_E][BO_O_LOOP] = a->xfE[1];
+    a->sc[i] = 0.0f;
+    a->st[i] = bo_ForwardParser(d, o->L, &om, &a->sc[i]);
+    break; }
+  }
+  free(d);
+}
+
+static int collect_windows(BO_WINDOWLIST *wl, int n, bathgpu_orf_window *out, int max_wins, int *nwins)
+{
+  int i, z, tot = 0, rc = BO_OK;
+  for (i = 0; i < n; i++) {
+    for (z = 0; z < wl[i].count; z++) {
+      if (tot < max_wins) { out[tot].orf = i; out[tot].n = wl[i].w[z].n; out[tot].k = wl[i].w[z].k; out[tot].length = wl[i].w[z].length; out[tot].score = wl[i].w[z].score; }
+      else rc = BO_EINVAL;
+      tot++;
+    }
+    bo_windowlist_free(&wl[i]);
+  }
+  *nwins = tot;
+  return rc;
+}
+
+int bo_backend_msv_orfs(void *ctx, const void *orfs, int n, float *sc, int32_t *status)
+{
+  orf_args a = { orfs, sc, status, NULL, 0, NULL, 0 };
+  parallel_for(ctx, n, orf_item, &a);
+  return BO_OK;
+}
+
+int bo_backend_ssv_windows(void *ctx, const void *orfs, int n, void *wins, int max_wins, int *nwins)
+{
+  BO_WINDOWLIST *wl = calloc((size_t) n, sizeof(BO_WINDOWLIST));
+  orf_args a = { orfs, NULL, NULL, wl, 0, NULL, 1 };
+  int rc;
+  parallel_for(ctx, n, orf_item, &a);
+  rc = collect_windows(wl, n, wins, max_wins, nwins);
+  free(wl);
+  return rc;
+}
+
+int bo_backend_vit_orfs(void *ctx, const void *orfs, int n, float *sc, int32_t *status, void *wins, int max_wins, int *nwins)
+{
+  BO_WINDOWLIST *wl = calloc((size_t) n, sizeof(BO_WINDOWLIST));
+  orf_args a = { orfs, sc, status, wl, 0, NULL, 2 };
+  int rc, nw = 0;
+  parallel_for(ctx, n, orf_item, &a);
+  rc = collect_windows(wl, n, wins, wins ? max_wins : 0, &nw);
+  if (nwins) *nwins = nw;
+  free(wl);
+  return (wins || nw == 0) ? rc : BO_OK;
+}
+
+int bo_backend_fwd_orfs(void *ctx, const void *orfs, int n, float nj, const float xfE[2], float *fwdsc, int32_t *status)
+{
+  orf_args a = { orfs, fwdsc, status, NULL, nj, xfE, 3 };
+  parallel_for(ctx, n, orf_item, &a);
+  return BO_OK;
+}
+
+/* ---- window stages ---- */
+typedef struct { const bathgpu_window *w; const float *xfE; float *fsc, *bsc; int32_t *st; float *fx, *bx; const int64_t *xoff; int do_bck; } win_args;
+
+static void win_item(bo_backend *b, void *arg, int i)
+{
+  win_args *a = arg;
+  const bathgpu_window *w = &a->w[i];
+  BO_FS_OPROFILE om = *b->om3;
+  int L = w->L, st;
+  uint8_t *sub = malloc((size_t) L + 2);
+  BO_MX *oxf = bo_mx_create(om.M, L, 0), *oxb = NULL;
+  float fsc = 0.0f, bsc = 0.0f;
+  sub[0] = sub[L + 1] = BO_DSQ_SENTINEL;
+  memcpy(sub + 1, b->dsq[b->cur] + w->start, (size_t) L);
+  om.xf[BO_X_N][BO_O_LOOP] = om.xf[BO_X_C][BO_O_LOOP] = om.xf[BO_X_J][BO_O_LOOP] = w->ploop;
+  om.xf[BO_X_N][BO_O_MOVE] = om.xf[BO_X_C][BO_O_MOVE] = om.xf[BO_X_J][BO_O_MOVE] = w->pmove;
+  om.xf[BO_X_E][BO_O_MOVE] = a->xfE[0]; om.xf[BO_X_E][BO_O_LOOP] = a->xfE[1];
+  st = bo_ForwardParser_Frameshift_3Codons(sub, L, &om, oxf, &fsc);
+  if (a->do_bck && st == BO_OK) {
+    oxb = bo_mx_create(om.M, L, 0);
+    st = bo_BackwardParser_Frameshift_3Codons(sub, L, &om, oxf, oxb, &bsc);
+    memcpy(a->fx + a->xoff[i] * 6, oxf->xmx, sizeof(float) * (size_t)(L + 1) * 6);
+    memcpy(a->bx + a->xoff[i] * 6, oxb->xmx, sizeof(float) * (size_t)(L + 1) * 6);
+  }
+  if (a->fsc) a->fsc[i] = fsc;
+  if (a->bsc) a->bsc[i] = bsc;
+  a->st[i] = st;
+  bo_mx_destroy(oxf); bo_mx_destroy(oxb); free(sub);
+}
+
+int bo_backend_fs_fwd_windows(void *ctx, const void *wins, int n, const float xfE[2], float *fwdsc, int32_t *status)
+{
+  win_args a = { wins, xfE, fwdsc, NULL, status, NULL, NULL, NULL, 0 };
+  parallel_for(ctx, n, win_item, &a);
+  return BO_OK;
+}
+
+int bo_backend_fs_fwd_bck_xrows(void *ctx, const void *wins, int n, const float xfE[2], float *fwd_xrows, float *bck_xrows,
+                                float *fwdsc, float *bcksc, int32_t *status)
+{
+  const bathgpu_window *w = wins;
+  int64_t *xoff = malloc(sizeof(int64_t) * (size_t)(n + 1));
+  int i;
+  win_args a = { wins, xfE, fwdsc, bcksc, status, fwd_xrows, bck_xrows, xoff, 1 };
+  xoff[0] = 0;
+  for (i = 0; i < n; i++) xoff[i + 1] = xoff[i] + w[i].L + 1;
+  parallel_for(ctx, n, win_item, &a);
+  free(xoff);
+  return BO_OK;
+}
+
+int bo_backend_fs_bck_decode(void *ctx, const void *wins, int n, const float xfE[2], const float xf5_loop[3], const int64_t *out_offset,
+                             float *mocc, float *btot, float *etot, float *fwdsc, float *bcksc, int32_t *status)
+{
+  bo_backend *b = ctx;
+  snprintf(b->err, sizeof b->err, "fs_bck_decode is not used by the host pipeline; not provided by the CPU backend");
+  return BO_EINVAL;
+}
+
+/* ---- envelope stage ---- */
+typedef struct { const bathgpu_envelope *e; const float *xfE5; bathgpu_domain_result *res; BO_TRACE **tr; } env_args;
+
+static void env_item(bo_backend *b, void *arg, int i)
+{
+  env_args *a = arg;
+  const bathgpu_envelope *e = &a->e[i];
+  bathgpu_domain_result *r = &a->res[i];
+  BO_FS_OPROFILE om = *b->om5;
+  int L = e->L, st, M = om.M;
+  uint8_t *sub = malloc((size_t) L + 2);
+  BO_MX *fwd = bo_mx_create(M, L, 8), *bck = bo_mx_create(M, L, 3), *oa = bo_mx_create(M, L, 3);
+  sub[0] = sub[L + 1] = BO_DSQ_SENTINEL;
+  memcpy(sub + 1, b->dsq[b->cur] + e->start, (size_t) L);
+  om.nj = 0.0f;
+  om.xf[BO_X_N][BO_O_LOOP] = om.xf[BO_X_C][BO_O_LOOP] = om.xf[BO_X_J][BO_O_LOOP] = e->ploop;
+  om.xf[BO_X_N][BO_O_MOVE] = om.xf[BO_X_C][BO_O_MOVE] = om.xf[BO_X_J][BO_O_MOVE] = e->pmove;
+  om.xf[BO_X_E][BO_O_MOVE] = a->xfE5[0]; om.xf[BO_X_E][BO_O_LOOP] = a->xfE5[1];
+  memset(r, 0, sizeof *r);
+  a->tr[i] = NULL;
+  st = bo_Forward_Frameshift(sub, L, &om, fwd, &r->envsc);
+  if (st == BO_OK) st = bo_Backward_Frameshift(sub, L, &om, fwd, bck, &r->bcksc);
+  if (st == BO_OK) st = bo_Decoding_Frameshift(&om, fwd, bck);
+  if (st == BO_OK) {
+    BO_TRACE *tr = bo_trace_create();
+    bo_OptimalAccuracy_Frameshift(&om, fwd, oa, &r->oasc);
+    if (bo_OATrace_Frameshift(&om, fwd, oa, tr) == BO_OK) a->tr[i] = tr; else { bo_trace_destroy(tr); st = BO_EINVAL; }
+    bo_Null2_fs_ByExpectation(&om, fwd, r->null2);
+  }
+  r->status = st;
+  bo_mx_destroy(fwd); bo_mx_destroy(bck); bo_mx_destroy(oa); free(sub);
+}
+
+int bo_backend_fs_domains(void *ctx, const void *envs, int n, const float xfE5[2], void *results, void *traces, int64_t max_steps)
+{
+  bo_backend *b = ctx;
+  BO_TRACE **tr = calloc((size_t) n, sizeof(BO_TRACE *));
+  bathgpu_domain_result *res = results;
+  bathgpu_trace_step *out = traces;
+  env_args a = { envs, xfE5, res, tr };
+  int64_t used = 0;
+  int i, z, rc = BO_OK;
+  parallel_for(b, n, env_item, &a);
+  for (i = 0; i < n; i++) {
+    res[i].trace_offset = (int32_t) used; res[i].trace_len = 0;
+    if (!tr[i]) continue;
+    if (used + tr[i]->N > max_steps) { snprintf(b->err, sizeof b->err, "trace buffer too small"); rc = BO_EINVAL; }
+    else {
+      for (z = 0; z < tr[i]->N; z++) {
+        out[used + z].i = tr[i]->i[z]; out[used + z].k = (int16_t) tr[i]->k[z]; out[used + z].st = (uint8_t) tr[i]->st[z];
+        out[used + z].c = (uint8_t) tr[i]->c[z]; out[used + z].pp = tr[i]->pp[z];
+      }
+      res[i].trace_len = tr[i]->N;
+      used += tr[i]->N;
+    }
+    bo_trace_destroy(tr[i]);
+  }
+  free(tr);
+  return rc;
+}

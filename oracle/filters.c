@@ -300,16 +300,25 @@ static int windowlist_add(BO_WINDOWLIST *wl, int n, int k, int length, float sco
 int bo_SSVFilter_BATH(const uint8_t *dsq, int L, BO_OPROFILE *om, const uint8_t *ssv_scores, float nullsc, double P,
                       int lanes, BO_WINDOWLIST *wl)
 {
+  float   invP = bo_gumbel_invsurv(P, om->evparam[BO_MMU], om->evparam[BO_MLAMBDA]);
+  uint8_t sc_thresh;
+  bo_oprofile_ReconfigLength(om, L);      /* p7_oprofile_ReconfigMSVLength (:308); the caller passes NullOne for L */
+  sc_thresh = (uint8_t)(int) ceil(((nullsc + (invP * LOG2) + 3.0) * om->scale_b) + om->base_b + om->tec_b + om->tjb_b);
+  return bo_SSVFilter_BATH_thresh(dsq, L, om, ssv_scores, sc_thresh, lanes, wl);
+}
+
+/* the same with sc_thresh (:313) given and om->tjb_b already set for L */
+int bo_SSVFilter_BATH_thresh(const uint8_t *dsq, int L, const BO_OPROFILE *om, const uint8_t *ssv_scores, uint8_t sc_thresh,
+                             int lanes, BO_WINDOWLIST *wl)
+{
   int      M = om->M, i, k, q, z;
-  int      Q = (M - 1) / lanes + 1; if (Q < 2) Q = 2;
+  int      Q = (M - 1) / lanes + 1;
   uint8_t *prev = calloc((size_t) M + 2, 1), *cur = calloc((size_t) M + 2, 1), *tmp;
-  uint8_t  xB, xE, sc_thresh;
-  float    invP = bo_gumbel_invsurv(P, om->evparam[BO_MMU], om->evparam[BO_MLAMBDA]);
+  uint8_t  xB, xE;
   uint8_t  tjbm;
 
-  bo_oprofile_ReconfigLength(om, L);      /* p7_oprofile_ReconfigMSVLength (:308); the caller passes NullOne for L */
+  if (Q < 2) Q = 2;
   tjbm = (uint8_t)((int8_t) om->tjb_b + (int8_t) om->tbm_b);
-  sc_thresh = (uint8_t)(int) ceil(((nullsc + (invP * LOG2) + 3.0) * om->scale_b) + om->base_b + om->tec_b + om->tjb_b);
   xB = u8_subs(om->base_b, tjbm);
 
   for (i = 1; i <= L; i++) {
@@ -420,14 +429,8 @@ static void vf_free(vf_row *a, vf_row *b) { free(a->m); free(a->d); free(a->i); 
 int bo_ViterbiFilter_BATH(const uint8_t *dsq, int L, const BO_OPROFILE *om, const uint8_t *ssv_scores, float filtersc, double P,
                           int lanes, BO_WINDOWLIST *wl, float *ret_sc)
 {
-  int     M = om->M, i, k, q, z;
-  int     Q = (M - 1) / lanes + 1;
-  vf_row  ra, rb, *prev = &ra, *cur = &rb, *tmp;
-  int16_t xE, xB, xC, xJ, xN, Dmax;
   int16_t sc_thresh = 0;
-  int     sc_ext_thresh = 0, skip_until = 0;
-
-  if (Q < 2) Q = 2;
+  int     sc_ext_thresh = 0;
   if (wl) {
     float invP = bo_gumbel_invsurv(P, om->evparam[BO_VMU], om->evparam[BO_VLAMBDA]);
     sc_thresh = (int16_t) ceil(((filtersc + LOG2 * invP + 3.0) * om->scale_w)
@@ -435,6 +438,20 @@ int bo_ViterbiFilter_BATH(const uint8_t *dsq, int L, const BO_OPROFILE *om, cons
     invP = bo_gumbel_invsurv(P, om->evparam[BO_MMU], om->evparam[BO_MLAMBDA]);
     sc_ext_thresh = (int) ceil(((filtersc + LOG2 * invP + 3.0) * om->scale_b) + om->base_b + om->tec_b + om->tjb_b);
   }
+  return bo_ViterbiFilter_BATH_thresh(dsq, L, om, ssv_scores, sc_thresh, sc_ext_thresh, lanes, wl, ret_sc);
+}
+
+/* the same with both thresholds (:315-321) given */
+int bo_ViterbiFilter_BATH_thresh(const uint8_t *dsq, int L, const BO_OPROFILE *om, const uint8_t *ssv_scores, int16_t sc_thresh,
+                                 int sc_ext_thresh, int lanes, BO_WINDOWLIST *wl, float *ret_sc)
+{
+  int     M = om->M, i, k, q, z;
+  int     Q = (M - 1) / lanes + 1;
+  vf_row  ra, rb, *prev = &ra, *cur = &rb, *tmp;
+  int16_t xE, xB, xC, xJ, xN, Dmax;
+  int     skip_until = 0;
+
+  if (Q < 2) Q = 2;
   if (vf_alloc(M, &ra, &rb) != BO_OK) return BO_EMEM;
   xN = om->base_w;
   xB = xN + om->xw[BO_X_N][BO_O_MOVE];

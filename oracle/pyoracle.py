@@ -302,6 +302,33 @@ def windows(wl):
     return [(wl.w[z].n, wl.w[z].k, wl.w[z].length, wl.w[z].score) for z in range(wl.count)]
 
 
+def cpu_backend(nthreads=1):
+    """The batched stage calls of include/bathgpu.h on the CPU (oracle/cpu_backend.c), as a bathhost_backend table for the
+    host pipeline.  TESTS AND BENCH ONLY.  Returns (backend struct, keep-alive handle)."""
+    from bath_b200 import hostapi
+    L = lib()
+    L.bo_backend_create.restype = C.c_void_p
+    L.bo_backend_create.argtypes = [C.c_int]
+    L.bo_backend_destroy.argtypes = [C.c_void_p]
+    h = L.bo_backend_create(int(nthreads))
+    be = hostapi.Backend()
+    be.ctx = h
+    for n in hostapi.Backend._names:
+        setattr(be, n, C.cast(getattr(L, "bo_backend_" + n), C.c_void_p))
+
+    class _Handle:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                L.bo_backend_destroy(self.ptr)
+            except Exception:
+                pass
+
+    return be, _Handle(h)
+
+
 def mx_xmx(mx):
     m = mx.contents
     return np.ctypeslib.as_array(m.xmx, shape=(m.allocL + 2, NXCELLS))[: m.L + 1]

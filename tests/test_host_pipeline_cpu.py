@@ -1,0 +1,73 @@
+"""The host pipeline (bath_b200/host/pipeline.cpp) behind the CPU oracle's implementation of the stage calls
+(oracle/cpu_backend.c): end-to-end parity with the reference's golden outputs WITHOUT a GPU.  The same assertions run
+against the GPU stages in tests/test_gpu_pipeline.py."""
+import re
+
+import common
+
+
+def run_search_cpu(oracle, hmm, fasta, nthreads=4, **opt):
+    from bath_b200 import hostapi
+    be, keep = oracle.cpu_backend(nthreads)
+    model = hostapi.QueryModel(common.golden(hmm))
+    search = hostapi.Search(model, backend=be, **opt)
+    for name, seq in hostapi.read_fasta(common.golden(fasta)):
+        search.add_sequence(name, hostapi.digitize_dna(seq))
+    hits = search.finish()
+    st = search.stats()
+    search.close()
+    del keep
+    return hits, st
+
+
+def footer_counts(path, keys):
+    out = open(path).read()
+    return [int(re.search(k + r":\s+(\d+)", out).group(1)) for k in keys]
+
+
+def test_amp_n_fs_table_and_footer(oracle):
+    hits, st = run_search_cpu(oracle, "AMP_N.bhmm", "target-AMP_N.fa")
+    tbl = [l for l in open(common.golden("AMP_N-fs.tbl")) if not l.startswith("#")]
+    assert len(hits) == len(tbl) == 1
+    f, h = tbl[0].split(), hits[0]
+    assert h["name"] == f[1] and h["sq_len"] == int(f[8])
+    assert (h["hmm_from"], h["hmm_to"], h["ali_from"], h["ali_to"]) == (int(f[6]), int(f[7]), int(f[9]), int(f[10]))
+    assert f"{h['evalue']:.2g}" == f"{float(f[11]):.2g}"          # 1.9e-27
+    assert f"{h['score']:.1f}" == f[12] and f"{h['bias']:.1f}" == f[13] and f"{h['pid']:.2f}" == f[14]
+    assert (h["shifts"], h["stops"]) == (int(f[15]), int(f[16])) and h["cigar"] == f[17]
+    want = footer_counts(common.golden("AMP_N-fs.out"), ("Residues passing SSV filter", "Residues passing bias filter",
+                                                          "Residues passing Vit filter", "Residues passing Fwd filter"))
+    assert st["nres"] == 822
+    assert [st["pos_past_msv"], st["pos_past_bias"], st["pos_past_vit"], st["pos_past_fwd"]] == want
+
+
+def test_pth2_filter_counters(oracle):
+    hits, st = run_search_cpu(oracle, "PTH2.bhmm", "target-PTH2.fa")
+    want = footer_counts(common.golden("PTH2.out"), ("Residues passing SSV filter", "Residues passing bias filter",
+                                                      "Residues passing Vit filter"))
+    assert st["nres"] == 6000
+    assert [st["pos_past_msv"], st["pos_past_bias"], st["pos_past_vit"]] == want
+    # the frameshift-aware run finds the non-frameshift run's alignments 2 and 4 (tutorial/PTH2.tbl) as well
+    spans = {(min(h["ali_from"], h["ali_to"]), max(h["ali_from"], h["ali_to"])) for h in hits}
+    assert any(abs(a - 1486) <= 3 and abs(b - 1731) <= 3 for a, b in spans)
+    assert any(abs(a - 1273) <= 3 for a, b in spans)
+
+
+def test_strand_restriction_and_blocks(oracle):
+    """top-only / bottom-only searches partition the hits; a tiny block length (many blocks with overlap context) finds the same
+    alignments after duplicate removal"""
+    both, st = run_search_cpu(oracle, "PTH2.bhmm", "target-PTH2.fa")
+    top, _ = run_search_cpu(oracle, "PTH2.bhmm", "target-PTH2.fa", top_only=1)
+    bot, _ = run_search_cpu(oracle, "PTH2.bhmm", "target-PTH2.fa", bottom_only=1)
+    assert all(h["strand"] == 1 for h in top) and all(h["strand"] == -1 for h in bot)
+    assert len(top) + len(bot) == len(both)
+    small, st2 = run_search_cpu(oracle, "PTH2.bhmm", "target-PTH2.fa", block_length=1500)
+    assert st2["nres"] == st["nres"]
+    # a block boundary may cut a window short (the reference keeps the better of the overlapping duplicates,
+    # src/p7_tophits.c:816-900), so alignments are matched by overlap on the target, not by exact ends
+    def span(h):
+        return h["strand"], min(h["ali_from"], h["ali_to"]), max(h["ali_from"], h["ali_to"])
+    assert len(small) == len(both)
+    for h in both:
+        s0, a0, b0 = span(h)
+        assert any(s1 == s0 and a1 <= b0 and b1 >= a0 for s1, a1, b1 in map(span, small)), h
