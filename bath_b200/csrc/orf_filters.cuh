@@ -16,8 +16,9 @@
 // with `lanes` the lanes per vector of the CPU build being matched (16/8 SSE, 32/16 AVX2).
 //
 // MSV: the reference first tries the J-less SSV shortcut and falls back to the full recursion when the J
-// state could matter; both give the same score and status whenever the shortcut answers (ssvfilter.c:14-210),
-// so this kernel runs the full recursion only.
+// state could matter (ssvfilter.c:14-210).  The shortcut's cells equal max(MSV cell, begin score), so its answer
+// is the full recursion's with the row maximum floored at the begin score; this kernel runs the full recursion
+// and applies that floor when the shortcut would have answered.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -199,6 +200,11 @@ __global__ void __launch_bounds__(128) msv_filter_kernel(FilterArgs a)
         float sc;
         if (st) sc = INFINITY;
         else {                                               // (:203-205)
+          // When the J state was never reachable the reference's answer comes from the SSV shortcut, whose cells are
+          // floored at the begin score instead of at 0 (cellwise max(MSV cell, xB0): ssvfilter.c:130-170), so an ORF
+          // with no cell above the begin score reports the begin score itself.  Same preconditions as the shortcut (:882-917).
+          const int floorJ = a.base_b - (int)od.tjb_b - a.tbm_b - a.tec_b;
+          if ((int)od.tjb_b + a.tbm_b + a.tec_b + a.bias_b < 127 && xJ <= a.base_b && floorJ >= 0) xJ = max(xJ, floorJ);
           sc = ((float)(xJ - (int)od.tjb_b) - (float)a.base_b);
           sc /= a.scale_b;
           sc -= 3.0f;

@@ -207,6 +207,21 @@ namespace {
 
 int fail(bathhost_search *s, int code, const std::string &msg) { s->err = msg; return code; }
 
+// static partition of [0,n) over the host cores
+template <class F> void parallel_chunks(size_t n, size_t min_chunk, F &&fn)
+{
+  const size_t hw = std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), 32));
+  const size_t nthr = std::max<size_t>(1, std::min(hw, n / std::max<size_t>(1, min_chunk)));
+  if (nthr <= 1) { fn((size_t) 0, n); return; }
+  std::vector<std::thread> pool;
+  const size_t step = (n + nthr - 1) / nthr;
+  for (size_t t = 0; t < nthr; ++t) {
+    const size_t a = t * step, b = std::min(n, a + step);
+    if (a < b) pool.emplace_back([&fn, a, b]() { fn(a, b); });
+  }
+  for (auto &th : pool) th.join();
+}
+
 struct StageTimer {              // adds the time since construction / last lap to a stats counter
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
   void lap(int64_t &acc) {
@@ -251,16 +266,6 @@ void find_orfs(const uint8_t *dsq, int n, const uint8_t gcode[64], int min_len, 
   }
   // a left-to-right scan over the three interleaved frames finishes ORFs in order of their last nucleotide
   std::sort(orfs.begin(), orfs.end(), [](const Orf &x, const Orf &y) { return x.end < y.end; });
-}
-
-void revcomp(std::vector<uint8_t> &d, int n)
-{
-  static const uint8_t comp[18] = { 3, 2, 1, 0, 4, 6, 5, 8, 7, 9, 10, 14, 13, 12, 11, 15, 16, 17 };
-  for (int i = 1, j = n; i <= j; ++i, --j) {
-    const uint8_t a = d[i], b = d[j];
-    d[i] = (b < 18) ? comp[b] : b;
-    d[j] = (a < 18) ? comp[a] : a;
-  }
 }
 
 // p7_pli_ComputeLocalCompo (src/p7_pipeline.c:427-458)
@@ -467,15 +472,19 @@ int filter_strand(bathhost_search *s, Strand &S, const std::vector<BlockInfo> &b
           if (blocks[b].n >= 15) find_orfs(S.dsq.data() + S.goff(blocks[b], n_total), blocks[b].n, s->gcode, opt.min_orf, bo[b], br[b]);
       });
     for (auto &th : pool) th.join();
-    size_t tot_o = 0, tot_r = 0;
-    for (size_t b = 0; b < nblk; ++b) { tot_o += bo[b].size(); tot_r += br[b].size(); }
-    S.orfs.reserve(tot_o); S.orf_blk.reserve(tot_o); S.residues.reserve(tot_r);
-    for (size_t b = 0; b < nblk; ++b) {
-      S.orf_begin[b] = (int) S.orfs.size();
-      for (Orf &o : bo[b]) { o.offset += (long long) S.residues.size(); S.orfs.push_back(o); S.orf_blk.push_back((int) b); }
-      S.residues.insert(S.residues.end(), br[b].begin(), br[b].end());
-    }
-    S.orf_begin[nblk] = (int) S.orfs.size();
+    std::vector<size_t> o0(nblk + 1, 0), r0(nblk + 1, 0);
+    for (size_t b = 0; b < nblk; ++b) { o0[b + 1] = o0[b] + bo[b].size(); r0[b + 1] = r0[b] + br[b].size(); }
+    S.orfs.resize(o0[nblk]); S.orf_blk.resize(o0[nblk]); S.residues.resize(r0[nblk]);
+    for (size_t b = 0; b <= nblk; ++b) S.orf_begin[b] = (int) o0[b];
+    parallel_chunks(nblk, 1, [&](size_t ba, size_t bb) {
+      for (size_t b = ba; b < bb; ++b) {
+        for (size_t z = 0; z < bo[b].size(); ++z) {
+          Orf o = bo[b][z]; o.offset += (long long) r0[b];
+          S.orfs[o0[b] + z] = o; S.orf_blk[o0[b] + z] = (int) b;
+        }
+        if (!br[b].empty()) memcpy(S.residues.data() + r0[b], br[b].data(), br[b].size());
+      }
+    });
   }
   const int norf = (int) S.orfs.size();
   s->st.n_orfs += norf;
@@ -774,9 +783,17 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
   for (int sidx : active) {
     Strand &S = strands[sidx];
     S.complement = (sidx == 1);
-    S.dsq.assign((size_t) n + 2, 255);
-    memcpy(S.dsq.data() + 1, dsq + 1, (size_t) n);
-    if (S.complement) revcomp(S.dsq, (int) n);
+    S.dsq.resize((size_t) n + 2);
+    S.dsq[0] = S.dsq[(size_t) n + 1] = 255;
+    {
+      static const uint8_t comp[18] = { 3, 2, 1, 0, 4, 6, 5, 8, 7, 9, 10, 14, 13, 12, 11, 15, 16, 17 };
+      const bool rc = S.complement;
+      uint8_t *out = S.dsq.data();
+      parallel_chunks((size_t) n, 1 << 20, [&](size_t a, size_t b) {
+        if (!rc) memcpy(out + 1 + a, dsq + 1 + a, b - a);
+        else for (size_t p = a; p < b; ++p) { const uint8_t c = dsq[(size_t) n - p]; out[1 + p] = (c < 18) ? comp[c] : c; }   // oriented p+1 <- original n-p
+      });
+    }
     int st = filter_strand(s, S, blocks, n, sidx);
     if (st != 0) return st;
   }
@@ -901,6 +918,47 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
   // ---- domain decoding and region finding on the host, in the reference's order (block, then strand, then window):
   // the length model of om_fs5 that p7_DomainDecoding_Frameshift reads is whatever the previous window's rescoring left
   // (src/p7_domaindef.c:320-325, :1018)
+  // The transcendental part of p7_DomainDecoding_Frameshift does not depend on that length model: it is precomputed for
+  // all windows on all host cores (cumulative log scales, Z, the btot/etot sums, the nine forward x backward products and
+  // their scale factors per row); the sequential walk below only applies the loop odds, in the reference's operation order.
+  struct Decoded { std::vector<float> btot, etot, fb, ex; };   // fb, ex: [L+1][9]
+  std::vector<Decoded> dec[2];
+  for (int sidx : active) {
+    Strand &S = strands[sidx];
+    dec[sidx].resize(S.fsw.size());
+    parallel_chunks(S.fsw.size(), 1, [&](size_t za, size_t zb) {
+      for (size_t z = za; z < zb; ++z) {
+        if (S.st2[z] != 0) continue;
+        const int Lw = S.dwin[S.fsw[z]].length;
+        const float *xf = &S.fxr[S.xoff[z] * 6], *xb = &S.bxr[S.xoff[z] * 6];
+        Decoded &D = dec[sidx][z];
+        D.btot.assign((size_t) Lw + 1, 0.f); D.etot.assign((size_t) Lw + 1, 0.f);
+        D.fb.assign(((size_t) Lw + 1) * 9, 0.f); D.ex.assign(((size_t) Lw + 1) * 9, 0.f);
+        std::vector<float> lsf((size_t) Lw + 2), lsb((size_t) Lw + 2);
+        lsf[0] = logf(xf[5]);
+        for (int i = 1; i <= Lw; ++i) lsf[i] = lsf[i - 1] + logf(xf[(size_t) i * 6 + 5]);
+        lsb[Lw + 1] = 0.0f;
+        for (int i = Lw; i >= 0; --i) lsb[i] = lsb[i + 1] + logf(xb[(size_t) i * 6 + 5]);
+        const float liz = -flogsum(logf(xb[0 * 6 + 1]) + lsb[0], flogsum(logf(xb[1 * 6 + 1]) + lsb[1], logf(xb[2 * 6 + 1]) + lsb[2]));
+        auto F = [&](int i, int c) { return xf[(size_t) i * 6 + c]; };
+        auto B = [&](int i, int c) { return xb[(size_t) i * 6 + c]; };
+        static const int cells[3] = { 1, 2, 4 };          // N, J, C
+        for (int i = 3; i <= Lw; ++i) {
+          D.btot[i] = D.btot[i - 3] + F(i - 3, 3) * B(i - 3, 3) * expf(lsf[i - 3] + lsb[i - 3] + liz);
+          D.etot[i] = D.etot[i - 3] + F(i, 0) * B(i, 0) * expf(lsf[i] + lsb[i] + liz);
+          const float e0 = expf(lsf[i - 3] + lsb[i] + liz);
+          const float e1 = (i < Lw)     ? expf(lsf[i - 2] + lsb[i + 1] + liz) : 0.f;
+          const float e2 = (i < Lw - 1) ? expf(lsf[i - 1] + lsb[i + 2] + liz) : 0.f;
+          for (int c = 0; c < 3; ++c) {
+            float *fb = &D.fb[(size_t) i * 9 + 3 * c], *ex = &D.ex[(size_t) i * 9 + 3 * c];
+            fb[0] = F(i - 3, cells[c]) * B(i, cells[c]); ex[0] = e0;
+            if (i < Lw)     { fb[1] = F(i - 2, cells[c]) * B(i + 1, cells[c]); ex[1] = e1; }
+            if (i < Lw - 1) { fb[2] = F(i - 1, cells[c]) * B(i + 2, cells[c]); ex[2] = e2; }
+          }
+        }
+      }
+    });
+  }
   const float rt1 = 0.25f, rt2 = 0.10f, rt3 = 0.20f;
   const int saveL = 100;                                    // gm_fs5->L: the dummy length bathsearch configures and never changes (src/bathsearch.c:797)
   {
@@ -913,30 +971,20 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
           if (S.st2[z] != 0) continue;                      // backward underflow: skip domain definition for this window (:1471)
           const int w = S.fsw[z];
           const int Lw = S.dwin[w].length;
-          const float *xf = &S.fxr[S.xoff[z] * 6], *xb = &S.bxr[S.xoff[z] * 6];
           const float tL = 1.0f - (2.0f + s->om5_nj) / ((float) s->om5_L + 2.0f + s->om5_nj);
-          std::vector<float> mocc((size_t) Lw + 1, 0.f), btot((size_t) Lw + 1, 0.f), etot((size_t) Lw + 1, 0.f);
-          {   // p7_DomainDecoding_Frameshift (src/impl_sse/decoding_fs.c:245-359)
-            std::vector<float> lsf((size_t) Lw + 2), lsb((size_t) Lw + 2);
-            lsf[0] = logf(xf[5]);
-            for (int i = 1; i <= Lw; ++i) lsf[i] = lsf[i - 1] + logf(xf[(size_t) i * 6 + 5]);
-            lsb[Lw + 1] = 0.0f;
-            for (int i = Lw; i >= 0; --i) lsb[i] = lsb[i + 1] + logf(xb[(size_t) i * 6 + 5]);
-            const float liz = -flogsum(logf(xb[0 * 6 + 1]) + lsb[0], flogsum(logf(xb[1 * 6 + 1]) + lsb[1], logf(xb[2 * 6 + 1]) + lsb[2]));
-            auto F = [&](int i, int c) { return xf[(size_t) i * 6 + c]; };
-            auto B = [&](int i, int c) { return xb[(size_t) i * 6 + c]; };
-            for (int i = 3; i <= Lw; ++i) {
-              btot[i] = btot[i - 3] + F(i - 3, 3) * B(i - 3, 3) * expf(lsf[i - 3] + lsb[i - 3] + liz);
-              etot[i] = etot[i - 3] + F(i, 0) * B(i, 0) * expf(lsf[i] + lsb[i] + liz);
-              float njcp = 0.;
-              static const int cells[3] = { 1, 2, 4 };      // N, J, C
-              for (int c : cells) {
-                njcp += F(i - 3, c) * B(i, c) * tL * expf(lsf[i - 3] + lsb[i] + liz);
-                if (i < Lw)     njcp += F(i - 2, c) * B(i + 1, c) * tL * expf(lsf[i - 2] + lsb[i + 1] + liz);
-                if (i < Lw - 1) njcp += F(i - 1, c) * B(i + 2, c) * tL * expf(lsf[i - 1] + lsb[i + 2] + liz);
-              }
-              mocc[i] = 1. - njcp;
+          // mocc[i] = 1 - sum over N,J,C and the three codon offsets of fwd * bck * loop odds * scale (decoding_fs.c:309-352)
+          const Decoded &D = dec[sidx][z];
+          const std::vector<float> &btot = D.btot, &etot = D.etot;
+          std::vector<float> mocc((size_t) Lw + 1, 0.f);
+          for (int i = 3; i <= Lw; ++i) {
+            float njcp = 0.;
+            const float *fb = &D.fb[(size_t) i * 9], *ex = &D.ex[(size_t) i * 9];
+            for (int c = 0; c < 3; ++c) {
+              njcp += fb[3 * c] * tL * ex[3 * c];
+              if (i < Lw)     njcp += fb[3 * c + 1] * tL * ex[3 * c + 1];
+              if (i < Lw - 1) njcp += fb[3 * c + 2] * tL * ex[3 * c + 2];
             }
+            mocc[i] = 1. - njcp;
           }
           s->om5_nj = 0.0f; s->om5_L = saveL / 3;           // p7_fs_oprofile_ReconfigUnihit(om_fs5, saveL/3) (:325)
           // region finding (src/p7_domaindef.c:332-383)

@@ -7,7 +7,7 @@ m = hostapi.QueryModel('tests/golden/tRNA-synthetases.bhmm', 1)
 rng = np.random.default_rng(42)
 d, plants = synth.planted_genome(rng, int(mbp * 1e6), m.mat(), every=50000, fs_rate=m.fsprob)
 ctx = capi.Context(0)
-for rep in range(2):
+for rep in range(int(sys.argv[2]) if len(sys.argv) > 2 else 2):
     s = hostapi.Search(m, ctx)
     t = time.perf_counter(); s.add_sequence('g', d); hits = s.finish(); dt = time.perf_counter() - t
     st = s.stats()

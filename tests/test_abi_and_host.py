@@ -134,8 +134,10 @@ def test_host_integer_filter_tables_match_oracle(oracle):
 
 
 def test_msv_shortcut_equivalence(oracle):
-    """The GPU runs the J-state MSV recursion only; the reference tries the J-less SSV shortcut first.  Both must give the
-    same score and status whenever the shortcut answers (src/impl_sse/ssvfilter.c:14-210): checked on the oracle's two paths."""
+    """The GPU runs the J-state MSV recursion only; the reference tries the J-less SSV shortcut first.  Whenever some cell
+    beats the begin score the two give the same score and status (src/impl_sse/ssvfilter.c:14-210): checked on the oracle's two
+    paths.  (When no cell does -- e.g. an all-X ORF -- the shortcut reports the begin score; the kernel applies that floor, see
+    tests/test_gpu_edge_cases.py.)"""
     import ctypes as C
     lib = oracle.lib()
     model = oracle.Model(common.golden("AMP_N.bhmm"))
