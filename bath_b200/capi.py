@@ -18,6 +18,7 @@ EXPORTS = [
     "bathgpu_fs_fetch_domain_matrices",
     "bathgpu_load_filter_profile", "bathgpu_upload_orfs", "bathgpu_msv_orfs", "bathgpu_ssv_windows", "bathgpu_vit_orfs",
     "bathgpu_fwd_orfs", "bathgpu_fs_fwd_bck_xrows", "bathgpu_select_slot",
+    "bathgpu_orf_fwd_bck_xrows", "bathgpu_orf_domains", "bathgpu_orf_fetch_domain_matrices",
 ]
 
 
@@ -110,6 +111,12 @@ def load():
     L.bathgpu_fwd_orfs.argtypes = [vp, vp, C.c_int, C.c_float, fp, fp, ip]
     L.bathgpu_fs_fwd_bck_xrows.restype = C.c_int
     L.bathgpu_fs_fwd_bck_xrows.argtypes = [vp, vp, C.c_int, fp, fp, fp, fp, fp, ip]
+    L.bathgpu_orf_fwd_bck_xrows.restype = C.c_int
+    L.bathgpu_orf_fwd_bck_xrows.argtypes = [vp, vp, C.c_int, C.c_float, fp, fp, fp, fp, fp, ip]
+    L.bathgpu_orf_domains.restype = C.c_int
+    L.bathgpu_orf_domains.argtypes = [vp, vp, C.c_int, fp, vp, vp, C.c_int64]
+    L.bathgpu_orf_fetch_domain_matrices.restype = C.c_int
+    L.bathgpu_orf_fetch_domain_matrices.argtypes = [vp, C.c_int, fp, fp, fp, fp]
     L.bathgpu_select_slot.restype = C.c_int
     L.bathgpu_select_slot.argtypes = [vp, C.c_int]
     L.bathgpu_host_alloc.restype = vp
@@ -334,6 +341,35 @@ class Context:
         self._check(self.lib.bathgpu_fs_fwd_bck_xrows(self.h, wins.ctypes.data, n, _f(xf), _f(fx), _f(bx), _f(fsc), _f(bsc), _i(st)))
         off = np.concatenate([[0], np.cumsum(Ls + 1)])
         return [fx[off[w]: off[w + 1]] for w in range(n)], [bx[off[w]: off[w + 1]] for w in range(n)], fsc, bsc, st
+
+    def orf_fwd_bck_xrows(self, orfs, nj=1.0, xfE=(0.5, 0.5)):
+        n = len(orfs)
+        Ls = orfs["L"].astype(np.int64)
+        tot = int((Ls + 1).sum())
+        fx, bx = np.empty((tot, 6), np.float32), np.empty((tot, 6), np.float32)
+        fsc, bsc, st = np.empty(n, np.float32), np.empty(n, np.float32), np.empty(n, np.int32)
+        xf = np.asarray(xfE, np.float32)
+        self._check(self.lib.bathgpu_orf_fwd_bck_xrows(self.h, orfs.ctypes.data, n, C.c_float(nj), _f(xf), _f(fx), _f(bx), _f(fsc), _f(bsc), _i(st)))
+        off = np.concatenate([[0], np.cumsum(Ls + 1)])
+        return [fx[off[w]: off[w + 1]] for w in range(n)], [bx[off[w]: off[w + 1]] for w in range(n)], fsc, bsc, st
+
+    def orf_domains(self, envs, xfE=(1.0, 0.0), max_steps=None, M=0):
+        n = len(envs)
+        if max_steps is None:
+            max_steps = int((envs["L"].astype(np.int64) + M + 8).sum())
+        res = np.zeros(n, dtype=domain_dtype)
+        tr = np.zeros(max_steps, dtype=trace_dtype)
+        xf = np.asarray(xfE, np.float32)
+        self._check(self.lib.bathgpu_orf_domains(self.h, envs.ctypes.data, n, _f(xf), res.ctypes.data, tr.ctypes.data, C.c_int64(max_steps)))
+        return res, tr
+
+    def orf_fetch_domain_matrices(self, e, L, M):
+        pp = np.empty((L + 1, M + 1, 3), np.float32)
+        oa = np.empty((L + 1, M + 1, 3), np.float32)
+        ppx = np.empty((L + 1, 6), np.float32)
+        oax = np.empty((L + 1, 6), np.float32)
+        self._check(self.lib.bathgpu_orf_fetch_domain_matrices(self.h, e, _f(pp), _f(oa), _f(ppx), _f(oax)))
+        return pp, oa, ppx, oax
 
     def fs_domains(self, envs, xfE5=(1.0, 0.0), max_steps=None):
         n = len(envs)

@@ -16,6 +16,7 @@
 #include "fs_parser_v3.cuh"
 #include "fs_backward.cuh"
 #include "fs_domain.cuh"
+#include "orf_domain.cuh"
 #include "orf_filters.cuh"
 #include "microbench.cuh"
 
@@ -1223,4 +1224,227 @@ extern "C" int bathgpu_fwd_orfs(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n
   }
   CUDA_TRY(ctx, e);
   return finish_filter(ctx, n, fwdsc, status, 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Standard-translation branch: protein Forward/Backward over ORFs and the per-envelope domain stage (orf_domain.cuh)
+template <int J> struct OrfDomLaunch {
+  template <class K> static int grid_for(K kernel, int n, int sms)
+  {
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 32, 0);
+    return std::min(n, sms * std::max(nb, 1));
+  }
+  static cudaError_t parsers(const OrfDomainArgs &a, int sms, cudaStream_t s)
+  {
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(a.counter, 0, 4, s)) != cudaSuccess) return e;
+    orf_forward_kernel<J, false><<<grid_for(orf_forward_kernel<J, false>, a.nenv, sms), 32, 0, s>>>(a);
+    if ((e = cudaMemsetAsync(a.counter, 0, 4, s)) != cudaSuccess) return e;
+    orf_backward_kernel<J, false><<<grid_for(orf_backward_kernel<J, false>, a.nenv, sms), 32, 0, s>>>(a);
+    return cudaGetLastError();
+  }
+  static cudaError_t domains(const OrfDomainArgs &a, const TraceArgs &t, int sms, cudaStream_t s)
+  {
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(a.counter, 0, 4, s)) != cudaSuccess) return e;
+    orf_forward_kernel<J, true><<<grid_for(orf_forward_kernel<J, true>, a.nenv, sms), 32, 0, s>>>(a);
+    if ((e = cudaMemsetAsync(a.counter, 0, 4, s)) != cudaSuccess) return e;
+    orf_backward_kernel<J, true><<<grid_for(orf_backward_kernel<J, true>, a.nenv, sms), 32, 0, s>>>(a);
+    if ((e = cudaMemsetAsync(a.counter, 0, 4, s)) != cudaSuccess) return e;
+    orf_optacc_kernel<J><<<grid_for(orf_optacc_kernel<J>, a.nenv, sms), 32, 0, s>>>(a);
+    orf_oatrace_kernel<<<(a.nenv + 3) / 4, 128, 0, s>>>(a, t);
+    return cudaGetLastError();
+  }
+};
+
+static cudaError_t dispatch_orf_domains(int J, bool full, const OrfDomainArgs &a, const TraceArgs &t, int sms, cudaStream_t s)
+{
+#define DOM(J_) case J_: return full ? OrfDomLaunch<J_>::domains(a, t, sms, s) : OrfDomLaunch<J_>::parsers(a, sms, s);
+  switch (J) { DOM(1) DOM(2) DOM(3) DOM(4) DOM(5) DOM(6) DOM(7) DOM(8) DOM(10) DOM(12) default: return cudaErrorInvalidValue; }
+#undef DOM
+}
+
+static const FsProfileImage *orf_image(bathgpu_ctx *ctx) { return ctx->fs3.loaded ? &ctx->fs3 : (ctx->fs5.loaded ? &ctx->fs5 : nullptr); }
+
+// One chunk of ORFs / envelopes.  full == false: X rows of both parsers to the host; full == true: results + traces.
+static int orf_chunk(bathgpu_ctx *ctx, const EnvelopeDesc *envs, int n, const float xfE[2], bool full,
+                     float *fwd_xrows, float *bck_xrows, float *fwdsc, float *bcksc, int32_t *status, int64_t x_off0,
+                     bathgpu_domain_result *results, bathgpu_trace_step *traces, int64_t max_steps, int64_t *steps_used)
+{
+  const FsProfileImage &im = *orf_image(ctx);
+  const int M = im.M, mpad = im.mpad;
+  std::vector<long long> xoff(n + 1, 0), toff(n + 1, 0);
+  for (int e = 0; e < n; ++e) { xoff[e + 1] = xoff[e] + envs[e].L + 1; toff[e + 1] = toff[e] + envs[e].L + M + 8; }
+  const size_t rows = (size_t)xoff[n];
+  if (ctx->envs.reserve((size_t)n * sizeof(EnvelopeDesc)) != BATHGPU_OK || ctx->xoff.reserve((size_t)(n + 1) * 8) != BATHGPU_OK ||
+      ctx->dfx.reserve(rows * 24) != BATHGPU_OK || ctx->bxmx.reserve(rows * 24) != BATHGPU_OK || ctx->dlsf.reserve(rows * 4) != BATHGPU_OK ||
+      ctx->dfw.reserve((size_t)n * 4) != BATHGPU_OK || ctx->dbk.reserve((size_t)n * 4) != BATHGPU_OK ||
+      ctx->dstat.reserve((size_t)n * 4) != BATHGPU_OK || ctx->counter.reserve(64) != BATHGPU_OK)
+    return fail(ctx, BATHGPU_EMEM, "device allocation failed for %d ORFs (%zu rows)", n, rows);
+  if (full && (ctx->dtoff.reserve((size_t)(n + 1) * 8) != BATHGPU_OK || ctx->dtlen.reserve((size_t)n * 4) != BATHGPU_OK ||
+               ctx->dpp.reserve(rows * kPPCellsP * mpad * 4) != BATHGPU_OK || ctx->doa.reserve(rows * kOACells * mpad * 4) != BATHGPU_OK ||
+               ctx->dppx.reserve(rows * 24) != BATHGPU_OK || ctx->doax.reserve(rows * 24) != BATHGPU_OK ||
+               ctx->doasc.reserve((size_t)n * 4) != BATHGPU_OK || ctx->dnull2.reserve((size_t)n * 29 * 4) != BATHGPU_OK ||
+               ctx->dsteps.reserve((size_t)toff[n] * sizeof(TraceStep)) != BATHGPU_OK))
+    return fail(ctx, BATHGPU_EMEM, "device allocation failed for %d envelopes (%zu rows, M=%d)", n, rows, M);
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->envs.p, envs, (size_t)n * sizeof(EnvelopeDesc), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->xoff.p, xoff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (full) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dtoff.p, toff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+
+  OrfDomainArgs a{};
+  a.emis = im.emis.as<float>(); a.amino0 = im.nrows - BATHGPU_KP; a.amino = im.amino.as<float>();
+  a.cellf = im.cellf5.as<float>(); a.cellb = im.cellb.as<float>(); a.oapass = im.oapass.as<float>(); a.oaflags = im.oaflags.as<uint32_t>();
+  a.residues = ctx->S().residues.as<uint8_t>(); a.envs = ctx->envs.as<EnvelopeDesc>(); a.nenv = n; a.M = M; a.mpad = mpad;
+  a.tEM = xfE[0]; a.tEL = xfE[1]; a.xoff = ctx->xoff.as<long long>();
+  a.pp = ctx->dpp.as<float>(); a.oa = ctx->doa.as<float>(); a.fx = ctx->dfx.as<float>(); a.bx = ctx->bxmx.as<float>();
+  a.ppx = ctx->dppx.as<float>(); a.oax = ctx->doax.as<float>(); a.lsf = ctx->dlsf.as<float>();
+  a.fwdsc = ctx->dfw.as<float>(); a.bcksc = ctx->dbk.as<float>(); a.oasc = ctx->doasc.as<float>();
+  a.null2 = ctx->dnull2.as<float>(); a.status = ctx->dstat.as<int>(); a.counter = ctx->counter.as<int>();
+  a.lanes_f32 = ctx->flt_loaded ? std::max(1, ctx->flt.cpu_lanes_u8 / 4) : 4;
+  TraceArgs t{};
+  t.steps = ctx->dsteps.as<TraceStep>(); t.toff = ctx->dtoff.as<long long>(); t.tlen = ctx->dtlen.as<int>();
+  t.tfv = im.tfvraw.as<float>(); t.J = im.J;
+
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  CUDA_TRY(ctx, dispatch_orf_domains(im.J, full, a, t, ctx->prop.multiProcessorCount, ctx->stream));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+
+  std::vector<float> fw(n), bk(n);
+  std::vector<int> st(n);
+  CUDA_TRY(ctx, cudaMemcpyAsync(fw.data(), ctx->dfw.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(bk.data(), ctx->dbk.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(st.data(), ctx->dstat.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (!full) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(fwd_xrows + (size_t)x_off0 * 6, ctx->dfx.p, rows * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(bck_xrows + (size_t)x_off0 * 6, ctx->bxmx.p, rows * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_ms += ms; ctx->last_launches += 2;
+    for (int e = 0; e < n; ++e) { if (fwdsc) fwdsc[e] = fw[e]; if (bcksc) bcksc[e] = bk[e]; status[e] = st[e]; }
+    return BATHGPU_OK;
+  }
+  std::vector<float> oa(n), n2((size_t)n * 29);
+  std::vector<int> tl(n);
+  std::vector<TraceStep> steps((size_t)toff[n]);
+  CUDA_TRY(ctx, cudaMemcpyAsync(oa.data(), ctx->doasc.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(n2.data(), ctx->dnull2.p, (size_t)n * 29 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(tl.data(), ctx->dtlen.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(steps.data(), ctx->dsteps.p, steps.size() * sizeof(TraceStep), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  ctx->last_ms += ms; ctx->last_launches += 4;
+  ctx->dom_xoff = xoff;
+  ctx->dom_L.assign(n, 0);
+  for (int e = 0; e < n; ++e) ctx->dom_L[e] = envs[e].L;
+  for (int e = 0; e < n; ++e) {
+    bathgpu_domain_result &r = results[e];
+    r.envsc = fw[e]; r.bcksc = bk[e]; r.oasc = oa[e]; r.status = st[e];
+    memcpy(r.null2, &n2[(size_t)e * 29], 29 * 4);
+    r.trace_offset = (int32_t)*steps_used; r.trace_len = 0;
+    if (st[e] == 0 && tl[e] > 0) {
+      if (*steps_used + tl[e] > max_steps)
+        return fail(ctx, BATHGPU_EINVAL, "trace buffer too small: %lld steps needed so far, %lld given", (long long)(*steps_used + tl[e]), (long long)max_steps);
+      TraceStep *tr = &steps[(size_t)toff[e]];
+      finish_trace(tr, tl[e]);
+      memcpy(traces + *steps_used, tr, (size_t)tl[e] * sizeof(TraceStep));
+      r.trace_len = tl[e];
+      *steps_used += tl[e];
+    }
+  }
+  return BATHGPU_OK;
+}
+
+extern "C" int bathgpu_orf_fwd_bck_xrows(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n, float nj, const float xfE[2],
+                                         float *fwd_xrows, float *bck_xrows, float *fwdsc, float *bcksc, int32_t *status)
+{
+  if (!ctx || !orfs || n < 1 || !xfE || !fwd_xrows || !bck_xrows || !status)
+    return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_orf_fwd_bck_xrows");
+  if (!orf_image(ctx))    return fail(ctx, BATHGPU_EINVAL, "no frameshift profile loaded (its amino-acid rows are the protein profile)");
+  if (ctx->S().nres == 0) return fail(ctx, BATHGPU_EINVAL, "no ORF residues uploaded");
+  std::vector<EnvelopeDesc> ed((size_t)n);
+  for (int o = 0; o < n; ++o) {
+    if (orfs[o].L < 1 || orfs[o].offset < 0 || orfs[o].offset + orfs[o].L > ctx->S().nres)
+      return fail(ctx, BATHGPU_EINVAL, "ORF %d is outside the uploaded residues", o);
+    ed[o].start = orfs[o].offset; ed[o].L = orfs[o].L;
+    ed[o].pmove = (2.0f + nj) / ((float)orfs[o].L + 2.0f + nj);      // p7_oprofile_ReconfigRestLength (p7_oprofile.c:1312-1313)
+    ed[o].ploop = 1.0f - ed[o].pmove;
+  }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ctx->last_ms = 0.f; ctx->last_launches = 0;
+  const size_t max_rows = (size_t)16 << 20;
+  int o0 = 0;
+  int64_t x0 = 0;
+  while (o0 < n) {
+    size_t rows = 0;
+    int o1 = o0;
+    while (o1 < n && (o1 == o0 || rows + ed[o1].L + 1 <= max_rows)) { rows += ed[o1].L + 1; ++o1; }
+    int st = orf_chunk(ctx, ed.data() + o0, o1 - o0, xfE, false, fwd_xrows, bck_xrows, fwdsc ? fwdsc + o0 : nullptr,
+                       bcksc ? bcksc + o0 : nullptr, status + o0, x0, nullptr, nullptr, 0, nullptr);
+    if (st != BATHGPU_OK) return st;
+    x0 += (int64_t)rows;
+    o0 = o1;
+  }
+  return BATHGPU_OK;
+}
+
+extern "C" int bathgpu_orf_domains(bathgpu_ctx *ctx, const bathgpu_envelope *envs, int n, const float xfE[2],
+                                   bathgpu_domain_result *results, bathgpu_trace_step *traces, int64_t max_steps)
+{
+  if (!ctx || !envs || n < 1 || !xfE || !results || !traces || max_steps < 1)
+    return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_orf_domains");
+  if (!orf_image(ctx))    return fail(ctx, BATHGPU_EINVAL, "no frameshift profile loaded (its amino-acid rows are the protein profile)");
+  if (ctx->S().nres == 0) return fail(ctx, BATHGPU_EINVAL, "no ORF residues uploaded");
+  for (int e = 0; e < n; ++e)
+    if (envs[e].L < 1 || envs[e].start < 0 || envs[e].start + envs[e].L > ctx->S().nres)
+      return fail(ctx, BATHGPU_EINVAL, "envelope %d (offset %lld, L %d) is outside the uploaded residues (n=%lld)",
+                  e, (long long)envs[e].start, envs[e].L, (long long)ctx->S().nres);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ctx->last_ms = 0.f; ctx->last_launches = 0;
+  const size_t row_bytes = (size_t)(kPPCellsP + kOACells) * orf_image(ctx)->mpad * 4 + 100;
+  const size_t max_rows = std::max<size_t>(((size_t)4 << 30) / row_bytes, 4096);
+  int64_t steps_used = 0;
+  int e0 = 0;
+  while (e0 < n) {
+    size_t rows = 0;
+    int e1 = e0;
+    while (e1 < n && (e1 == e0 || rows + envs[e1].L + 1 <= max_rows)) { rows += envs[e1].L + 1; ++e1; }
+    int st = orf_chunk(ctx, reinterpret_cast<const EnvelopeDesc *>(envs) + e0, e1 - e0, xfE, true, nullptr, nullptr, nullptr, nullptr, nullptr, 0,
+                       results + e0, traces, max_steps, &steps_used);
+    if (st != BATHGPU_OK) return st;
+    e0 = e1;
+  }
+  return BATHGPU_OK;
+}
+
+// Test/diagnostic: matrices of envelope e of the last chunk of the last bathgpu_orf_domains call, un-permuted, in the
+// reference's cell order {M,D,I}: pp and oa [(L+1)][(M+1)][3], ppx / oax [(L+1)][6].
+extern "C" int bathgpu_orf_fetch_domain_matrices(bathgpu_ctx *ctx, int e, float *pp, float *oa, float *ppx, float *oax)
+{
+  if (!ctx || e < 0 || e >= (int)ctx->dom_L.size() || !orf_image(ctx)) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_orf_fetch_domain_matrices");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const FsProfileImage &im = *orf_image(ctx);
+  const int M = im.M, mpad = im.mpad, J = im.J, L = ctx->dom_L[e];
+  const size_t r0 = (size_t)ctx->dom_xoff[e], nr = (size_t)L + 1;
+  std::vector<float> hp(nr * kPPCellsP * mpad), ho(nr * kOACells * mpad);
+  CUDA_TRY(ctx, cudaMemcpy(hp.data(), ctx->dpp.as<float>() + r0 * kPPCellsP * mpad, hp.size() * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(ctx, cudaMemcpy(ho.data(), ctx->doa.as<float>() + r0 * kOACells * mpad, ho.size() * 4, cudaMemcpyDeviceToHost));
+  if (ppx) CUDA_TRY(ctx, cudaMemcpy(ppx, ctx->dppx.as<float>() + r0 * 6, nr * 24, cudaMemcpyDeviceToHost));
+  if (oax) CUDA_TRY(ctx, cudaMemcpy(oax, ctx->doax.as<float>() + r0 * 6, nr * 24, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < nr; ++i)
+    for (int k = 0; k <= M; ++k) {
+      float *pc = pp ? pp + (i * (M + 1) + k) * 3 : nullptr;
+      float *oc = oa ? oa + (i * (M + 1) + k) * 3 : nullptr;
+      if (k == 0) {
+        if (pc) for (int c = 0; c < 3; ++c) pc[c] = 0.f;
+        if (oc) for (int c = 0; c < 3; ++c) oc[c] = -INFINITY;
+        continue;
+      }
+      const int p = perm_index(k - 1, J);
+      if (pc) { pc[0] = hp[(i * kPPCellsP + PPP_M) * mpad + p]; pc[1] = 0.f; pc[2] = hp[(i * kPPCellsP + PPP_I) * mpad + p]; }
+      if (oc) { oc[0] = ho[(i * kOACells + OA_M) * mpad + p]; oc[1] = ho[(i * kOACells + OA_D) * mpad + p]; oc[2] = ho[(i * kOACells + OA_I) * mpad + p]; }
+    }
+  return BATHGPU_OK;
 }

@@ -178,6 +178,7 @@ struct Options {
   double F1 = 0.02, F2 = 1e-3, F3 = 1e-5, F4 = 5e-4, E = 10.0;
   int    min_orf = 20, block_length = 262144, lanes_u8 = 16, lanes_i16 = 8;
   bool   do_bias = true, do_null2 = true, top = true, bottom = true;
+  bool   fs = true;                   // --fs; false: bathsearch's default standard-translation pipeline (src/p7_pipeline.c:106-107)
 };
 
 }  // namespace bathhost
@@ -443,6 +444,9 @@ struct Strand {
   std::vector<bathgpu_envelope> ge;
   std::vector<bathgpu_domain_result> res;
   std::vector<bathgpu_trace_step> traces;
+  struct StdItem { int gi, w; };            // ORF sent down the standard-translation branch, and the DNA window it lost to (-1: none)
+  std::vector<StdItem> stdq;
+  std::vector<uint8_t> aligned;             // oxf_holder[i] == NULL: this ORF has been aligned already
   long long goff(const BlockInfo &b, long long n_total) const { return complement ? n_total - b.b1 : b.b0 - 1; }   // device coordinate = goff + block-local
   long long start_of(const BlockInfo &b) const { return complement ? b.b1 : b.b0; }                               // dnasq->start
 };
@@ -796,6 +800,10 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
     }
     int st = filter_strand(s, S, blocks, n, sidx);
     if (st != 0) return st;
+    S.aligned.assign(S.orfs.size(), 0);
+    if (!opt.fs)                                            // default pipeline: every ORF past F3 is aligned by itself (:1720-1771)
+      for (size_t gi = 0; gi < S.orfs.size(); ++gi)
+        if (S.P_orf[gi] <= opt.F3) { s->st.pos_past_fwd += (int64_t) S.orfs[gi].n * 3; S.stdq.push_back(Strand::StdItem{ (int) gi, -1 }); }
   }
 
   // ---- DNA windows, block by block in the reference's order, against the ever-growing hit_windows list
@@ -806,7 +814,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
     for (int sidx : active) {
       Strand &S = strands[sidx];
       S.dwin_begin[b] = (int) S.dwin.size();
-      if (blocks[b].n >= 15) {
+      if (blocks[b].n >= 15 && opt.fs) {
         for (int gi = S.orf_begin[b]; gi < S.orf_begin[b + 1]; ++gi)
           for (const OrfWin &w : S.wins_of_orf[gi]) hit_windows.push_back(w);
         S.hw_count[b] = hit_windows.size();
@@ -856,6 +864,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
         const bool inside = S.complement ? (o.start >= dw.n && o.end <= dw.n + dw.length + 1)
                                          : (o.start >= dw.n && o.end <= dw.n + dw.length - 1);
         if (!inside) continue;
+        S.orfs[gi].window_idx = w;
         P_min = std::min(P_min, S.P_orf[gi]);
         tot_orfsc = flogsum(tot_orfsc, S.fwdsc_orf[gi]);
         orf_cnt++;
@@ -887,15 +896,22 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
           bg.set_length(dw.length / 3);
         }
       }
-      if (S.fs_st[w] != 0) continue;                        // eslERANGE from the Forward parser: treated as no score
-      const float fwdsc = S.fs_fwd[w];
+      const float fwdsc = S.fs_fwd[w];                      // on eslERANGE the score is -inf or NaN and the tests below fail, as in the reference
       const float seqscore = (fwdsc - filtersc) / kLog2;
       const double P_fs   = exp_surv(seqscore, ev[EV_FTAUFS3], ev[EV_FLAMBDA]);
       const double P_null = exp_surv((fwdsc - nullsc) / kLog2, ev[EV_FTAUFS3], ev[EV_FLAMBDA]);
-      if (P_fs <= opt.F3 && (P_null < P_tot || (P_null == P_tot && orf_cnt > 1) || P_min > opt.F3)) {
+      if (S.fs_st[w] == 0 && P_fs <= opt.F3 && (P_null < P_tot || (P_null == P_tot && orf_cnt > 1) || P_min > opt.F3)) {
         s->st.pos_past_fwd += dw.length;
         S.fsw.push_back(w);
-      } else s->st.n_std_windows++;                         // standard-translation branch (:1480-1511): not restated yet
+      } else {                                              // standard-translation branch (:1480-1511)
+        s->st.n_std_windows++;
+        for (int gi = S.orf_begin[b]; gi < S.orf_begin[b + 1]; ++gi) {
+          if (S.orfs[gi].window_idx != w || S.P_orf[gi] > opt.F3 || S.aligned[gi]) continue;
+          s->st.pos_past_fwd += (int64_t) S.orfs[gi].n * 3;
+          S.aligned[gi] = 1;
+          S.stdq.push_back(Strand::StdItem{ gi, w });
+        }
+      }
     }
   }
   tm.lap(s->st.us_bias);
@@ -1173,7 +1189,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
         h.pub.ali_from = orig(dom.iali); h.pub.ali_to = orig(dom.jali);
         h.pub.hmm_from = dom.ihmm; h.pub.hmm_to = dom.jhmm;
         h.pub.sq_len = blk.sq_len;
-        h.pub.score = dom_score; h.pub.bias = dom_bias; h.pub.lnP = dom_lnP;
+        h.pub.score = dom_score; h.pub.bias = dom_bias / kLog2; h.pub.lnP = dom_lnP;
         h.pub.pre_score = bitscore / kLog2;
         h.pub.envsc = dom.envsc; h.pub.oasc = dom.oasc;
         h.pub.trace_len = (int32_t) dom.tr.size();
@@ -1184,6 +1200,200 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
       }
   }
   tm.lap(s->st.us_fs_domains);
+
+  // ---- the standard-translation branch: ORFs whose DNA window lost the arbitration, or every ORF past F3 without --fs
+  // (src/p7_pipeline.c:1480-1511, :1720-1771): BackwardParser + DomainDecoding + regions per ORF, then each envelope rescored
+  for (int sidx : active) {
+    Strand &S = strands[sidx];
+    if (S.stdq.empty()) continue;
+    const size_t nq = S.stdq.size();
+    const float xfEm[2] = { expf(q.xsc_E_move), expf(q.xsc_E_loop) };
+    std::vector<bathgpu_orf> od(nq);
+    std::vector<size_t> xo(nq + 1, 0);
+    for (size_t z = 0; z < nq; ++z) {
+      const Orf &o = S.orfs[S.stdq[z].gi];
+      memset(&od[z], 0, sizeof od[z]);
+      od[z].offset = o.offset; od[z].L = o.n;
+      xo[z + 1] = xo[z] + (size_t) o.n + 1;
+    }
+    std::vector<float> fx(xo[nq] * 6), bx(xo[nq] * 6), fsc(nq), bsc(nq);
+    std::vector<int32_t> pst(nq);
+    BE_TRY(s, s->be.select_slot(s->be.ctx, sidx), "bathgpu_select_slot");
+    BE_TRY(s, s->be.orf_fwd_bck_xrows(s->be.ctx, od.data(), (int) nq, q.nj, xfEm, fx.data(), bx.data(), fsc.data(), bsc.data(), pst.data()),
+           "bathgpu_orf_fwd_bck_xrows");
+
+    // p7_DomainDecoding (src/impl_sse/decoding.c:160-196) and the region logic of p7_domaindef_ByPosteriorHeuristics_BATH
+    // (src/p7_domaindef.c:500-618); ORFs are independent here (the length model is saved and restored around each)
+    struct SEnv { int z, i, j; };
+    std::vector<std::vector<SEnv>> env_of(nq);
+    std::vector<int> nreg(nq, 0), nmulti(nq, 0);
+    parallel_chunks(nq, 1, [&](size_t za, size_t zb) {
+      for (size_t z = za; z < zb; ++z) {
+        if (pst[z] != 0) continue;
+        const int L = od[z].L;
+        const float *xf = &fx[xo[z] * 6], *xb = &bx[xo[z] * 6];
+        auto F = [&](int i, int c) { return xf[(size_t) i * 6 + c]; };
+        auto B = [&](int i, int c) { return xb[(size_t) i * 6 + c]; };
+        const float loop = 1.0f - (2.0f + q.nj) / ((float) L + 2.0f + q.nj);
+        bool own = false;
+        for (int i = 1; i < L; ++i) if (B(i, 5) != F(i, 5)) { own = true; break; }
+        std::vector<float> btot((size_t) L + 1), etot((size_t) L + 1), mocc((size_t) L + 1);
+        float scaleproduct = 1.0 / B(0, 1);
+        btot[0] = etot[0] = mocc[0] = 0.0f;
+        for (int i = 1; i <= L; ++i) {
+          btot[i] = btot[i - 1] + (F(i - 1, 3) * B(i - 1, 3) * F(i - 1, 5) * scaleproduct);
+          if (own) scaleproduct *= F(i - 1, 5) / B(i - 1, 5);
+          etot[i] = etot[i - 1] + (F(i, 0) * B(i, 0) * F(i, 5) * scaleproduct);
+          float njcp;
+          njcp  = F(i - 1, 1) * B(i, 1) * loop * scaleproduct;
+          njcp += F(i - 1, 2) * B(i, 2) * loop * scaleproduct;
+          njcp += F(i - 1, 4) * B(i, 4) * loop * scaleproduct;
+          mocc[i] = 1. - njcp;
+        }
+        if (std::isinf(scaleproduct)) continue;             // eslERANGE
+        const float rt1 = 0.25f, rt2 = 0.10f, rt3 = 0.20f;
+        int i = -1; bool triggered = false;
+        for (int j = 1; j <= L; ++j) {
+          if (!triggered) {
+            if (mocc[j] - (btot[j] - btot[j - 1]) < rt2) i = j;
+            else if (i == -1) i = j;
+            if (mocc[j] >= rt1) triggered = true;
+          } else if (mocc[j] - (etot[j] - etot[j - 1]) < rt2) {
+            nreg[z]++;
+            float mx = -1.0f;                               // is_multidomain_region (:652-664)
+            for (int zz = i; zz <= j; ++zz) mx = std::max(mx, std::min(etot[zz] - etot[i - 1], btot[j] - btot[zz - 1]));
+            if (mx >= rt3) nmulti[z]++;                     // stochastic clustering not restated: rescored as ONE envelope
+            env_of[z].push_back(SEnv{ (int) z, i, j });
+            i = -1; triggered = false;
+          }
+        }
+      }
+    });
+    std::vector<SEnv> envs;
+    std::vector<bathgpu_envelope> ge;
+    int64_t max_steps = 0;
+    for (size_t z = 0; z < nq; ++z) {
+      s->st.n_regions += nreg[z]; s->st.n_multidomain_regions += nmulti[z];
+      for (const SEnv &e : env_of[z]) {
+        const int Ld = e.j - e.i + 1;
+        bathgpu_envelope g;
+        g.start = od[z].offset + e.i - 1; g.L = Ld;
+        bathhost_length_model(Ld, 0.0f, &g.pmove, &g.ploop);     // p7_oprofile_ReconfigLength(om, Ld) in unihit mode (:1244)
+        ge.push_back(g); envs.push_back(e);
+        max_steps += Ld + M + 8;
+      }
+    }
+    if (ge.empty()) continue;
+    std::vector<bathgpu_domain_result> res(ge.size());
+    std::vector<bathgpu_trace_step> traces((size_t) max_steps);
+    const float xfEu[2] = { 1.0f, 0.0f };
+    BE_TRY(s, s->be.orf_domains(s->be.ctx, ge.data(), (int) ge.size(), xfEu, res.data(), traces.data(), max_steps), "bathgpu_orf_domains");
+    s->st.n_envelopes += (int64_t) ge.size();
+
+    for (size_t e = 0; e < envs.size(); ++e) {
+      const bathgpu_domain_result &r = res[e];
+      if (r.status != 0 || r.trace_len == 0) continue;       // eslFAIL (:1252)
+      const Strand::StdItem &it = S.stdq[envs[e].z];
+      const Orf &o = S.orfs[it.gi];
+      const int b = S.orf_blk[it.gi];
+      const BlockInfo &binfo = blocks[b];
+      // windowsq: the DNA window (--fs) or the ORF's own nucleotides (default pipeline); block-local start
+      const long long win_n = (it.w >= 0) ? S.dwin[it.w].n : o.start;
+      const uint8_t *wdsq = S.dsq.data() + S.goff(binfo, n) + win_n - 1;
+      const uint8_t *res_o = S.residues.data() + o.offset - 1;           // ORF residue p is res_o[p]
+      const int i = envs[e].i, j = envs[e].j;
+      Domain dom;
+      dom.tr.assign(traces.begin() + r.trace_offset, traces.begin() + r.trace_offset + r.trace_len);
+      int orf_pos = 0;                                       // tr->sqfrom[0]: ORF position of the first match state (p7_trace_Index)
+      for (auto &ts : dom.tr) {
+        if (ts.i > 0) ts.i += i - 1;                         // (:1260-1261)
+        if (orf_pos == 0 && ts.st == TS_M) orf_pos = ts.i;
+      }
+      {                                                      // p7_trace_fs_Convert (src/p7_trace.c:405-438)
+        const int start = (int) (o.start - win_n);
+        for (size_t z = 0; z < dom.tr.size(); ++z) {
+          bathgpu_trace_step &ts = dom.tr[z];
+          switch (ts.st) {
+          case TS_N: case TS_C: case TS_J:
+            if (z > 0 && dom.tr[z - 1].st == ts.st) ts.i = start + ts.i * 3;
+            ts.c = 0; break;
+          case TS_M: ts.i = start + ts.i * 3; ts.c = 3; break;
+          case TS_I: ts.i = start + ts.i * 3; ts.c = 0; break;
+          default: ts.c = 0; break;
+          }
+        }
+      }
+      const float aliscore = ali_score(m, dom.tr, wdsq);
+      if (aliscore < 0.0f) continue;
+      float domcorrection = 0.0f;                            // (:1296-1305)
+      for (int pos = i; pos <= j; ++pos) domcorrection += logf(r.null2[res_o[pos]]);
+      dom.domcorrection = std::max(0.f, domcorrection);
+      int z1 = 0, z2 = (int) dom.tr.size() - 1;
+      while (z1 < (int) dom.tr.size() && dom.tr[z1].st != TS_M) ++z1;
+      while (z2 >= 0 && dom.tr[z2].st != TS_M) --z2;
+      if (z1 > z2) continue;
+      dom.ihmm = dom.tr[z1].k; dom.jhmm = dom.tr[z2].k;
+      dom.iali = dom.tr[z1].i - (dom.tr[z1].c - 1); dom.jali = dom.tr[z2].i;
+      dom.ienv = i; dom.jenv = j; dom.envsc = r.envsc; dom.oasc = r.oasc;
+
+      // ---- p7_pli_postDomainDef_BATH (src/p7_pipeline.c:1172-1290)
+      const int env_len = dom.jenv - dom.ienv + 1;
+      const int ali_len = (dom.jali - dom.iali + 1) / 3;
+      if (ali_len < 4) continue;
+      const int ml = q.max_length;
+      float bitscore = dom.envsc;
+      bitscore -= 2 * log(2. / (env_len + 2));
+      bitscore += 2 * log(2. / (ml + 2));
+      bitscore -= (env_len - ali_len) * log((float) env_len / (float) (env_len + 2));
+      bitscore += (ml - ali_len) * log((float) ml / (float) (ml + 2));
+      const float dom_bias = opt.do_null2 ? flogsum(0.0, log(bg.omega) + dom.domcorrection) : 0.0f;
+      bg.set_length(ml);
+      const float nullsc = bg.null_one(ml);
+      const float dom_score = (bitscore - (nullsc + dom_bias)) / kLog2;
+      const double dom_lnP = exp_logsurv(dom_score, ev[EV_FTAU], ev[EV_FLAMBDA]);
+      const double Z = (float) binfo.nres_at[sidx] / (float) ml;
+      if (!(exp(dom_lnP) * Z <= opt.E)) continue;
+
+      Hit h;
+      memset(&h.pub, 0, sizeof h.pub);
+      const long long bstart = S.start_of(binfo);            // dnasq->start
+      auto orig = [&](int wpos) -> long long { return S.complement ? bstart - (win_n + wpos) + 2 : bstart + win_n + wpos - 2; };
+      h.pub.seqidx = s->nseqs;
+      snprintf(h.pub.name, sizeof h.pub.name, "%s", name ? name : "");
+      h.pub.strand = S.complement ? -1 : 1;
+      if (!S.complement) { h.pub.env_from = bstart + o.start + dom.ienv * 3 - 4; h.pub.env_to = bstart + o.start + dom.jenv * 3 - 2; }
+      else {                                                 // dnasq->end + orfsq->start, orfsq->start = dnasq->n - o.start + 1 on this strand
+        const long long base = binfo.b0 + (binfo.n - o.start + 1);
+        h.pub.env_from = base - dom.ienv * 3 + 2; h.pub.env_to = base - dom.jenv * 3;
+      }
+      h.pub.ali_from = orig(dom.iali); h.pub.ali_to = orig(dom.jali);
+      h.pub.hmm_from = dom.ihmm; h.pub.hmm_to = dom.jhmm;
+      h.pub.sq_len = (long long) n;
+      h.pub.score = dom_score; h.pub.bias = dom_bias / kLog2; h.pub.lnP = dom_lnP;
+      h.pub.pre_score = bitscore / kLog2;
+      h.pub.envsc = dom.envsc; h.pub.oasc = dom.oasc;
+      h.pub.trace_len = (int32_t) dom.tr.size();
+      {                                                      // p7_alidisplay_nonfs_Create (src/p7_alidisplay.c:937-1230): PID and CIGAR
+        std::string cigar;
+        char buf[32];
+        int exact = 0, ncore = 0, n_count = 0, pos = orf_pos;
+        for (int z = z1; z <= z2; ++z) {
+          const bathgpu_trace_step &ts = dom.tr[z];
+          const int nxt = dom.tr[z + 1].st;                 // z2 + 1 exists: the E state
+          ncore++;
+          if (ts.st == TS_M) { if (res_o[pos] == amino_code(m->hmm.consensus[ts.k])) exact++; pos++; }
+          else if (ts.st == TS_I) pos++;
+          n_count += 3;
+          if (nxt != ts.st) { snprintf(buf, sizeof buf, "%d%c", n_count, ts.st == TS_M ? 'M' : ts.st == TS_I ? 'I' : 'D'); cigar += buf; n_count = 0; }
+        }
+        h.pub.pid = ncore ? ((float) exact / ncore) * 100 : 0.0f;
+        snprintf(h.pub.cigar, sizeof h.pub.cigar, "%s", cigar.c_str());
+      }
+      h.sortkey = -dom_lnP;
+      s->hits.push_back(h);
+    }
+  }
+  tm.lap(s->st.us_std);
   s->nseqs++;
   s->st.nseqs = s->nseqs;
   return 0;
@@ -1212,6 +1422,7 @@ extern "C" int bathhost_search_create(const bathhost_model *m, const bathhost_ba
     if (o->cpu_lanes_i16 > 0) s->opt.lanes_i16 = o->cpu_lanes_i16;
     s->opt.do_bias = !o->no_bias; s->opt.do_null2 = !o->no_null2;
     s->opt.top = !o->bottom_only; s->opt.bottom = !o->top_only;
+    s->opt.fs = !o->std_only;
   }
   if (!genetic_code(m->ct, s->gcode)) { delete s; return BATHHOST_EINVAL; }
   s->compo.assign(m->hmm.compo, m->hmm.compo + kK);

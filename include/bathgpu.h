@@ -209,6 +209,27 @@ int bathgpu_fs_domains(bathgpu_ctx *ctx, const bathgpu_envelope *envs, int n, co
  * decoding), oa [(L+1)][(M+1)][3] {M,D,I}, ppx / oax [(L+1)][6] {E,N,J,B,C,SCALE}.  Any pointer may be NULL. */
 int bathgpu_fs_fetch_domain_matrices(bathgpu_ctx *ctx, int e, float *pp, float *oa, float *ppx, float *oax);
 
+/* ---- f2: the standard-translation branch over ORFs ------------------------ */
+/* p7_ForwardParser + p7_BackwardParser over ORFs of the uploaded residue buffer, X rows kept (what oxf_holder[i] and
+ * pli->oxb hold at src/p7_pipeline.c:1492-1495 / :1762-1764): fwd_xrows / bck_xrows = {E,N,J,B,C,SCALE} x (L+1) per ORF,
+ * ORFs concatenated in call order, for a caller that runs p7_DomainDecoding (an O(L) scalar pass) itself.  The length
+ * model is p7_oprofile_ReconfigLength(om, L) with nj; xfE = {E->MOVE, E->LOOP} odds (multihit: {0.5, 0.5}).
+ * Uses the amino-acid rows and transitions of the loaded frameshift profile, which are the protein profile's own. */
+int bathgpu_orf_fwd_bck_xrows(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n, float nj, const float xfE[2],
+                              float *fwd_xrows, float *bck_xrows, float *fwdsc, float *bcksc, int32_t *status);
+
+/* rescore_isolated_domain_bath (src/p7_domaindef.c:1229-1370) over envelopes of ORFs: p7_Forward, p7_Backward, p7_Decoding,
+ * p7_OptimalAccuracy, p7_OATrace and p7_Null2_ByExpectation (src/impl_sse/impl_sse.h:479-520).  envs[e].start is the 0-based
+ * offset of the envelope's first residue in the uploaded residue buffer (like bathgpu_orf.offset), L its length in residues,
+ * pmove/ploop from p7_oprofile_ReconfigLength(om, L) in unihit mode; xfE = {1, 0} there.  Trace steps carry i in envelope
+ * coordinates (1..L) and c = 0; the caller maps them to nucleotides as p7_trace_fs_Convert does (src/p7_trace.c:405). */
+int bathgpu_orf_domains(bathgpu_ctx *ctx, const bathgpu_envelope *envs, int n, const float xfE[2],
+                        bathgpu_domain_result *results, bathgpu_trace_step *traces, int64_t max_steps);
+
+/* Test/diagnostic: matrices of envelope e of the last chunk of the last bathgpu_orf_domains call, cell order {M,D,I}:
+ * pp and oa [(L+1)][(M+1)][3], ppx / oax [(L+1)][6].  Any pointer may be NULL. */
+int bathgpu_orf_fetch_domain_matrices(bathgpu_ctx *ctx, int e, float *pp, float *oa, float *ppx, float *oax);
+
 /* ---- measurement helpers ------------------------------------------------ */
 /* Device time (ms) of the kernels launched by the most recent stage call, measured with
  * CUDA events on the context's stream, and how many kernels that call launched. */

@@ -113,6 +113,9 @@ typedef struct {
   int (*fs_bck_decode)(void *ctx, const void *wins, int n, const float xfE[2], const float xf5_loop[3], const int64_t *out_offset,
                        float *mocc, float *btot, float *etot, float *fwdsc, float *bcksc, int32_t *status);
   int (*fs_domains)(void *ctx, const void *envs, int n, const float xfE5[2], void *results, void *traces, int64_t max_steps);
+  int (*orf_fwd_bck_xrows)(void *ctx, const void *orfs, int n, float nj, const float xfE[2], float *fwd_xrows, float *bck_xrows,
+                           float *fwdsc, float *bcksc, int32_t *status);
+  int (*orf_domains)(void *ctx, const void *envs, int n, const float xfE[2], void *results, void *traces, int64_t max_steps);
 } bathhost_backend;
 
 /* 0 / unset fields take bathsearch's defaults (src/p7_pipeline.c:145-214; src/bathsearch.c:94) */
@@ -122,6 +125,7 @@ typedef struct {
   int32_t block_length;       /* 262144 */
   int32_t cpu_lanes_u8, cpu_lanes_i16;   /* stripe geometry of the CPU build to match: 16/8 (SSE) */
   int32_t no_bias, no_null2, top_only, bottom_only;
+  int32_t std_only;           /* 0: bathsearch --fs; 1: bathsearch's default pipeline (standard translation only) */
 } bathhost_options;
 
 typedef struct {
@@ -131,7 +135,7 @@ typedef struct {
   int64_t ali_from, ali_to, env_from, env_to, sq_len;
   int32_t hmm_from, hmm_to;
   double  evalue, lnP;
-  float   score, bias, pre_score, envsc, oasc, pid;
+  float   score, bias, pre_score, envsc, oasc, pid;     /* score, bias, pre_score in bits, as the tables print them (src/p7_tophits.c:1325) */
   int32_t shifts, stops, trace_len;
   char    cigar[1024];
 } bathhost_hit;
@@ -141,7 +145,7 @@ typedef struct {
   int64_t pos_past_msv, pos_past_bias, pos_past_vit, pos_past_fwd;   /* the footer's filter counters          */
   int64_t n_orfs, n_windows, n_std_windows, n_regions, n_multidomain_regions, n_envelopes, n_hits_reported;
   /* wall time per stage of the host pipeline, microseconds (host work + the device calls made from it) */
-  int64_t us_orfs, us_upload, us_msv, us_bias, us_vit, us_fwd, us_windows, us_fs_fwd, us_fs_domains;
+  int64_t us_orfs, us_upload, us_msv, us_bias, us_vit, us_fwd, us_windows, us_fs_fwd, us_fs_domains, us_std;
 } bathhost_stats;
 
 typedef struct bathhost_search bathhost_search;

@@ -305,6 +305,17 @@ double bo_exp_logsurv(double x, double mu, double lambda);
 /* ===== orf_fwd.c (impl_sse/fwdback.c) ===== */
 int    bo_ForwardParser(const uint8_t *dsq, int L, const BO_OPROFILE *om, float *opt_sc);
 
+/* ===== orf_domain.c: the standard-translation branch's DP over an ORF (src/impl_sse/fwdback.c, decoding.c, optacc.c, null2.c) ===== */
+void   bo_oprofile_ReconfigMultihit(BO_OPROFILE *om, int L);
+void   bo_oprofile_ReconfigUnihit(BO_OPROFILE *om, int L);
+int    bo_Forward (const uint8_t *dsq, int L, const BO_OPROFILE *om, BO_MX *ox, float *opt_sc);     /* ox->nscells 3: full; 0: parser */
+int    bo_Backward(const uint8_t *dsq, int L, const BO_OPROFILE *om, const BO_MX *fwd, BO_MX *bck, float *opt_sc);
+int    bo_Decoding(const BO_OPROFILE *om, const BO_MX *oxf, BO_MX *oxb, BO_MX *pp);
+int    bo_DomainDecoding(const float xf_loop_NJC[3], const BO_MX *oxf, const BO_MX *oxb, int own_scales, float *btot, float *etot, float *mocc);
+int    bo_OptimalAccuracy(const BO_OPROFILE *om, const BO_MX *pp, BO_MX *ox, float *ret_e);
+int    bo_OATrace(const BO_OPROFILE *om, const BO_MX *pp, const BO_MX *ox, int lanes, BO_TRACE *tr);
+int    bo_Null2_ByExpectation(const BO_OPROFILE *om, const BO_MX *pp, float *null2);
+
 /* ===== batch.c (worker-thread pool over windows; src/bathsearch.c:814-844,1224) ===== */
 int bo_batch_ForwardParser_3Codons(const uint8_t *dsq, const int64_t *start, const int32_t *L, int n,
                                    const BO_FS_OPROFILE *om, int nthreads, float *sc, int32_t *status);

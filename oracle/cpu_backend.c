@@ -348,3 +348,104 @@ int bo_backend_fs_domains(void *ctx, const void *envs, int n, const float xfE5[2
   free(tr);
   return rc;
 }
+
+/* ---- standard-translation branch (orf_domain.c) ---- */
+typedef struct { const bathgpu_orf *orfs; float nj; const float *xfE; float *fsc, *bsc; int32_t *st; float *fx, *bx; const int64_t *xoff; } orfx_args;
+
+static void set_length_model(BO_OPROFILE *om, float pmove, float ploop, const float *xfE)
+{
+  om->xf[BO_X_N][BO_O_LOOP] = om->xf[BO_X_C][BO_O_LOOP] = om->xf[BO_X_J][BO_O_LOOP] = ploop;
+  om->xf[BO_X_N][BO_O_MOVE] = om->xf[BO_X_C][BO_O_MOVE] = om->xf[BO_X_J][BO_O_MOVE] = pmove;
+  om->xf[BO_X_E][BO_O_MOVE] = xfE[0]; om->xf[BO_X_E][BO_O_LOOP] = xfE[1];
+}
+
+static void orfx_item(bo_backend *b, void *arg, int i)
+{
+  orfx_args *a = arg;
+  const bathgpu_orf *o = &a->orfs[i];
+  BO_OPROFILE om = *b->om;
+  uint8_t *d = orf_dsq(b, o);
+  int L = o->L, st;
+  float pmove = (2.0f + a->nj) / ((float) L + 2.0f + a->nj), fsc = 0.0f, bsc = 0.0f;
+  BO_MX *oxf = bo_mx_create(om.M, L, 0), *oxb = bo_mx_create(om.M, L, 0);
+  set_length_model(&om, pmove, 1.0f - pmove, a->xfE);
+  st = bo_Forward(d, L, &om, oxf, &fsc);
+  if (st == BO_OK) st = bo_Backward(d, L, &om, oxf, oxb, &bsc);
+  memcpy(a->fx + a->xoff[i] * 6, oxf->xmx, sizeof(float) * 6 * (size_t)(L + 1));
+  memcpy(a->bx + a->xoff[i] * 6, oxb->xmx, sizeof(float) * 6 * (size_t)(L + 1));
+  if (a->fsc) a->fsc[i] = fsc;
+  if (a->bsc) a->bsc[i] = bsc;
+  a->st[i] = st;
+  bo_mx_destroy(oxf); bo_mx_destroy(oxb); free(d);
+}
+
+int bo_backend_orf_fwd_bck_xrows(void *ctx, const void *orfs, int n, float nj, const float xfE[2], float *fwd_xrows, float *bck_xrows,
+                                 float *fwdsc, float *bcksc, int32_t *status)
+{
+  const bathgpu_orf *o = orfs;
+  int64_t *xoff = malloc(sizeof(int64_t) * (size_t)(n + 1));
+  orfx_args a = { orfs, nj, xfE, fwdsc, bcksc, status, fwd_xrows, bck_xrows, xoff };
+  int i;
+  xoff[0] = 0;
+  for (i = 0; i < n; i++) xoff[i + 1] = xoff[i] + o[i].L + 1;
+  parallel_for(ctx, n, orfx_item, &a);
+  free(xoff);
+  return BO_OK;
+}
+
+static void orfenv_item(bo_backend *b, void *arg, int i)
+{
+  env_args *a = arg;
+  const bathgpu_envelope *e = &a->e[i];
+  bathgpu_domain_result *r = &a->res[i];
+  BO_OPROFILE om = *b->om;
+  int L = e->L, st, M = om.M;
+  uint8_t *sub = malloc((size_t) L + 2);
+  BO_MX *fwd = bo_mx_create(M, L, 3), *bck = bo_mx_create(M, L, 3);
+  sub[0] = sub[L + 1] = BO_DSQ_SENTINEL;
+  memcpy(sub + 1, b->res[b->cur] + e->start, (size_t) L);
+  om.nj = 0.0f;
+  set_length_model(&om, e->pmove, e->ploop, a->xfE5);
+  memset(r, 0, sizeof *r);
+  a->tr[i] = NULL;
+  st = bo_Forward(sub, L, &om, fwd, &r->envsc);
+  if (st == BO_OK) st = bo_Backward(sub, L, &om, fwd, bck, &r->bcksc);
+  if (st == BO_OK) st = bo_Decoding(&om, fwd, bck, bck);          /* bck now holds the posteriors (p7_domaindef.c:1251) */
+  if (st == BO_OK) {
+    BO_TRACE *tr = bo_trace_create();
+    bo_OptimalAccuracy(&om, bck, fwd, &r->oasc);                  /* fwd now holds the OA matrix (:1255) */
+    if (bo_OATrace(&om, bck, fwd, b->lanes_u8 / 4 > 0 ? b->lanes_u8 / 4 : 4, tr) == BO_OK) a->tr[i] = tr;
+    else { bo_trace_destroy(tr); st = BO_EINVAL; }
+    bo_Null2_ByExpectation(&om, bck, r->null2);
+  }
+  r->status = st;
+  bo_mx_destroy(fwd); bo_mx_destroy(bck); free(sub);
+}
+
+int bo_backend_orf_domains(void *ctx, const void *envs, int n, const float xfE[2], void *results, void *traces, int64_t max_steps)
+{
+  bo_backend *b = ctx;
+  BO_TRACE **tr = calloc((size_t) n, sizeof(BO_TRACE *));
+  bathgpu_domain_result *res = results;
+  bathgpu_trace_step *out = traces;
+  env_args a = { envs, xfE, res, tr };
+  int64_t used = 0;
+  int i, z, rc = BO_OK;
+  parallel_for(b, n, orfenv_item, &a);
+  for (i = 0; i < n; i++) {
+    res[i].trace_offset = (int32_t) used; res[i].trace_len = 0;
+    if (!tr[i]) continue;
+    if (used + tr[i]->N > max_steps) { snprintf(b->err, sizeof b->err, "trace buffer too small"); rc = BO_EINVAL; }
+    else {
+      for (z = 0; z < tr[i]->N; z++) {
+        out[used + z].i = tr[i]->i[z]; out[used + z].k = (int16_t) tr[i]->k[z]; out[used + z].st = (uint8_t) tr[i]->st[z];
+        out[used + z].c = (uint8_t) tr[i]->c[z]; out[used + z].pp = tr[i]->pp[z];
+      }
+      res[i].trace_len = tr[i]->N;
+      used += tr[i]->N;
+    }
+    bo_trace_destroy(tr[i]);
+  }
+  free(tr);
+  return rc;
+}

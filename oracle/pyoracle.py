@@ -154,6 +154,15 @@ def lib(native=False):
         "bo_ViterbiFilter_BATH": (C.c_int, [u8p, C.c_int, P(OPROFILE), u8p, C.c_float, C.c_double, C.c_int,
                                             P(WINDOWLIST), fp]),
         "bo_ForwardParser": (C.c_int, [u8p, C.c_int, P(OPROFILE), fp]),
+        "bo_oprofile_ReconfigMultihit": (None, [P(OPROFILE), C.c_int]),
+        "bo_oprofile_ReconfigUnihit": (None, [P(OPROFILE), C.c_int]),
+        "bo_Forward": (C.c_int, [u8p, C.c_int, P(OPROFILE), P(MX), fp]),
+        "bo_Backward": (C.c_int, [u8p, C.c_int, P(OPROFILE), P(MX), P(MX), fp]),
+        "bo_Decoding": (C.c_int, [P(OPROFILE), P(MX), P(MX), P(MX)]),
+        "bo_DomainDecoding": (C.c_int, [fp, P(MX), P(MX), C.c_int, fp, fp, fp]),
+        "bo_OptimalAccuracy": (C.c_int, [P(OPROFILE), P(MX), P(MX), fp]),
+        "bo_OATrace": (C.c_int, [P(OPROFILE), P(MX), P(MX), C.c_int, P(TRACE)]),
+        "bo_Null2_ByExpectation": (C.c_int, [P(OPROFILE), P(MX), fp]),
         "bo_windowlist_reset": (None, [P(WINDOWLIST)]),
         "bo_windowlist_free": (None, [P(WINDOWLIST)]),
         "bo_gumbel_invsurv": (C.c_double, [C.c_double, C.c_double, C.c_double]),

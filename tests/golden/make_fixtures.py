@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 FILES = [
     "tutorial/AMP_N.bhmm", "tutorial/target-AMP_N.fa", "tutorial/AMP_N-fs.out", "tutorial/AMP_N-fs.tbl",
     "tutorial/PTH2.bhmm", "tutorial/target-PTH2.fa", "tutorial/PTH2.out", "tutorial/PTH2.tbl", "tutorial/PTH2-cigar.tbl",
-    "tutorial/tRNA-synthetases.bhmm", "tutorial/PTHR37536.bhmm",
+    "tutorial/tRNA-synthetases.bhmm", "tutorial/PTHR37536.bhmm", "tutorial/AMP_N.out",
+    "tutorial/MET-ct4.bhmm", "tutorial/target-MET.fa", "tutorial/MET-ct4.out",
     "testsuite/2OG-FeII_Oxy_3.bhmm", "testsuite/2OG-FeII_Oxy_3-nt-fs.fa", "testsuite/2OG-FeII_Oxy_3-nt.fa",
 ]
 for f in FILES:
