@@ -196,7 +196,7 @@ def search_leg(ctx, model, dsq, mbp, plants):
     search.close()
     return {"metric": "bathsearch --fs Mbp/s", "value": n / dt / 1e6, "unit": "Mbp/s", "seconds": dt, "target_mbp": n / 1e6,
             "hits": len(hits), "planted": len(planted), "planted_recovered": found, "stats": st,
-            "note": "standard-translation branch and multi-domain clustering not restated yet (windows routed there are counted in stats.n_std_windows)"}
+            "note": "windows that lose the arbitration go down the standard-translation branch (stats.n_std_windows); multi-domain regions are rescored as one envelope (stats.n_multidomain_regions), stochastic clustering is not restated"}
 
 
 def search_leg_cpu(model, dsq, mbp, nthreads):
