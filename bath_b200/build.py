@@ -43,14 +43,49 @@ def build_host_library(force=False):
     return _HOST_SO
 
 
-def build_library(force=False, verbose=False):
+_OBJ = os.path.join(_HERE, "_obj")
+
+# kernels_tu.cu is compiled once per (family, node-count set): see csrc/launch.h
+_FAMILIES = {"fwd": 1, "bck": 2, "fs5": 3, "orf": 4}
+_SETS = {"a": 0, "b": 1, "c": 2, "d": 3, "e": 4, "f": 5}
+_FILTERS = {"msv": 5, "vit_lo": 6, "vit_hi": 7}
+
+
+def _units():
+    """(object name, source, extra -D flags) of every translation unit of libbathgpu.so"""
+    units = [("bathgpu", os.path.join(_CSRC, "bathgpu.cu"), [])]
+    tu = os.path.join(_CSRC, "kernels_tu.cu")
+    for fam, fid in _FAMILIES.items():
+        for sname, sid in _SETS.items():
+            units.append((f"k_{fam}_{sname}", tu, [f"-DBATHGPU_FAMILY={fid}", f"-DBATHGPU_SET={sid}"]))
+    for fam, fid in _FILTERS.items():
+        units.append((f"k_{fam}", tu, [f"-DBATHGPU_FAMILY={fid}", "-DBATHGPU_SET=0"]))
+    return units
+
+
+def build_library(force=False, verbose=False, jobs=None):
     srcs = _sources()
-    if not force and os.path.exists(_SO) and all(os.path.getmtime(s) <= os.path.getmtime(_SO) for s in srcs):
+    newest = max(os.path.getmtime(s) for s in srcs + [os.path.abspath(__file__)])
+    if not force and os.path.exists(_SO) and newest <= os.path.getmtime(_SO):
         return _SO
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    units = sorted(s for s in srcs if s.endswith((".cu", ".cpp")))
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", _SO] + units
-    subprocess.check_call(cmd)
+    os.makedirs(_OBJ, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(unit):
+        name, src, defs = unit
+        obj = os.path.join(_OBJ, name + ".o")
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < newest:
+            subprocess.check_call([nvcc] + flags + defs + ["-c", src, "-o", obj])
+        return obj
+
+    units = _units()
+    # longest first: the node-count sets with the most (or the largest) instantiations
+    units.sort(key=lambda u: (u[0].endswith(("_f", "_e", "_c", "_b")), u[0]), reverse=True)
+    with ThreadPoolExecutor(max_workers=jobs or os.cpu_count() or 4) as pool:
+        objs = list(pool.map(compile_one, units))
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", _SO] + objs)
     return _SO
 
 

@@ -19,6 +19,7 @@
 #include "orf_domain.cuh"
 #include "orf_filters.cuh"
 #include "microbench.cuh"
+#include "launch.h"
 
 using namespace bathgpu;
 
@@ -201,7 +202,7 @@ extern "C" int bathgpu_measure_fp32_peak(bathgpu_ctx *ctx, double *tflops, doubl
 
 // ---------------------------------------------------------------------------------------------
 // profile images
-static const int kSupportedJ[] = { 1, 2, 3, 4, 5, 6, 7, 8, 10, 12 };
+static const int kSupportedJ[] = { 1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 24, 32 };   // 16, 24, 32: part of the state spills (launch.h)
 
 static int choose_J(int M)
 {
@@ -223,7 +224,7 @@ extern "C" int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int n
   const int want_rows = (which == 3 ? 338 : 1367) + BATHGPU_KP;
   if (nrows != want_rows)           return fail(ctx, BATHGPU_EINVAL, "nrows %d != %d for %d codon lengths", nrows, want_rows, which);
   const int J = choose_J(M);
-  if (J == 0) return fail(ctx, BATHGPU_EINVAL, "model length %d exceeds the single-warp kernels' limit (%d)", M, 32 * 12);
+  if (J == 0) return fail(ctx, BATHGPU_EINVAL, "model length %d exceeds the single-warp kernels' limit (%d)", M, 32 * 32);
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 
   FsProfileImage &im = (which == 3) ? ctx->fs3 : ctx->fs5;
@@ -457,73 +458,21 @@ extern "C" int bathgpu_upload_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_
 
 // ---------------------------------------------------------------------------------------------
 // Forward parser stage
-template <int J, bool XMX>
-static cudaError_t launch_fwd(const FsParserArgs &a, int grid, cudaStream_t s)
-{
-  fs3_forward_parser_kernel<J, XMX><<<grid, FwdTune<J>::kThreads, 0, s>>>(a);
-  return cudaGetLastError();
-}
-
 static int fwd_version()      // BATHGPU_FWD=1|3 picks a kernel generation for A/B runs (1: one row per block of code; default 3: the row-pair schedule)
 {
   static const int v = [] { const char *e = getenv("BATHGPU_FWD"); int x = e ? atoi(e) : 3; return (x == 1) ? 1 : 3; }();
   return v;
 }
 
-template <int J, bool XMX>
-static cudaError_t launch_fwd3(const FsParserArgs &a, int grid, cudaStream_t s)
+// one launch entry per kernel family and node-count set (launch.h; kernels_tu.cu)
+static cudaError_t dispatch_fwd(bool xmx, int J, const FsParserArgs &a, int sms, cudaStream_t s)
 {
-  fs3_forward_parser_kernel_v3<J, XMX><<<grid, 32, 0, s>>>(a);
-  return cudaGetLastError();
-}
-
-template <bool XMX>
-static cudaError_t dispatch_fwd(int J, const FsParserArgs &a, int grid, cudaStream_t s)
-{
-  if (fwd_version() >= 3) {
-    switch (J) {
-    case 1:  return launch_fwd3<1, XMX>(a, grid, s);
-    case 2:  return launch_fwd3<2, XMX>(a, grid, s);
-    case 3:  return launch_fwd3<3, XMX>(a, grid, s);
-    case 4:  return launch_fwd3<4, XMX>(a, grid, s);
-    case 5:  return launch_fwd3<5, XMX>(a, grid, s);
-    case 6:  return launch_fwd3<6, XMX>(a, grid, s);
-    case 7:  return launch_fwd3<7, XMX>(a, grid, s);
-    case 8:  return launch_fwd3<8, XMX>(a, grid, s);
-    case 10: return launch_fwd3<10, XMX>(a, grid, s);
-    case 12: return launch_fwd3<12, XMX>(a, grid, s);
-    default: return cudaErrorInvalidValue;
-    }
-  }
-  switch (J) {
-  case 1:  return launch_fwd<1, XMX>(a, grid, s);
-  case 2:  return launch_fwd<2, XMX>(a, grid, s);
-  case 3:  return launch_fwd<3, XMX>(a, grid, s);
-  case 4:  return launch_fwd<4, XMX>(a, grid, s);
-  case 5:  return launch_fwd<5, XMX>(a, grid, s);
-  case 6:  return launch_fwd<6, XMX>(a, grid, s);
-  case 7:  return launch_fwd<7, XMX>(a, grid, s);
-  case 8:  return launch_fwd<8, XMX>(a, grid, s);
-  case 10: return launch_fwd<10, XMX>(a, grid, s);
-  case 12: return launch_fwd<12, XMX>(a, grid, s);
-  default: return cudaErrorInvalidValue;
-  }
-}
-
-template <int J, bool XMX>
-static int fwd_occupancy()
-{
-  int nb = 0;
-  if (fwd_version() >= 3) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fs3_forward_parser_kernel_v3<J, XMX>, 32, 0); return nb; }
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fs3_forward_parser_kernel<J, XMX>, FwdTune<J>::kThreads, 0);
-  return nb;
-}
-
-static int fwd_blocks_per_sm(int J, bool xmx)
-{
-#define OCC(J_) case J_: return xmx ? fwd_occupancy<J_, true>() : fwd_occupancy<J_, false>();
-  switch (J) { OCC(1) OCC(2) OCC(3) OCC(4) OCC(5) OCC(6) OCC(7) OCC(8) OCC(10) OCC(12) default: return 1; }
-#undef OCC
+  cudaError_t e = cudaErrorInvalidValue;
+  const int v = fwd_version();
+#define X(S) if (launch_fs3_forward_##S(J, xmx, v, a, sms, s, &e)) return e;
+  BATHGPU_FOR_EACH_SET(X)
+#undef X
+  return cudaErrorInvalidValue;
 }
 
 static int check_windows(bathgpu_ctx *ctx, const bathgpu_window *wins, int n)
@@ -567,12 +516,9 @@ extern "C" int bathgpu_fs_fwd_staged(bathgpu_ctx *ctx, const float xfE[2])
   a.fwdsc = ctx->fwdsc.as<float>(); a.status = ctx->status.as<int>();
   a.xmx = nullptr; a.xoff = nullptr; a.counter = ctx->counter.as<int>();
 
-  const int per_sm = std::max(1, fwd_blocks_per_sm(im.J, false));
-  const int wpb    = 1;   // FwdTune<J>::kThreads / 32
-  const int grid   = std::min((ctx->nstaged + wpb - 1) / wpb, ctx->prop.multiProcessorCount * per_sm);
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  CUDA_TRY(ctx, dispatch_fwd<false>(im.J, a, grid, ctx->stream));
+  CUDA_TRY(ctx, dispatch_fwd(false, im.J, a, ctx->prop.multiProcessorCount, ctx->stream));
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
@@ -601,20 +547,13 @@ extern "C" int bathgpu_fs_fwd_windows(bathgpu_ctx *ctx, const bathgpu_window *wi
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int J>
-static cudaError_t launch_bck(const FsBackwardArgs &a, int grid, cudaStream_t s)
-{
-  fs3_backward_parser_kernel<J><<<grid, BckTune<J>::kThreads, 0, s>>>(a);
-  return cudaGetLastError();
-}
-
 static cudaError_t dispatch_bck(int J, const FsBackwardArgs &a, int sms, cudaStream_t s)
 {
-#define BCK(J_) case J_: { int nb = 0;                                                                          \
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fs3_backward_parser_kernel<J_>, BckTune<J_>::kThreads, 0); \
-    return launch_bck<J_>(a, std::min(a.nwin, sms * std::max(nb, 1)), s); }
-  switch (J) { BCK(1) BCK(2) BCK(3) BCK(4) BCK(5) BCK(6) BCK(7) BCK(8) BCK(10) BCK(12) default: return cudaErrorInvalidValue; }
-#undef BCK
+  cudaError_t e = cudaErrorInvalidValue;
+#define X(S) if (launch_fs3_backward_##S(J, a, sms, s, &e)) return e;
+  BATHGPU_FOR_EACH_SET(X)
+#undef X
+  return cudaErrorInvalidValue;
 }
 
 // a10 + a11 for one chunk of windows whose descriptors are already in ctx->wins
@@ -652,7 +591,7 @@ static int bck_decode_chunk(bathgpu_ctx *ctx, const bathgpu_window *wins, int n,
   fa.fwdsc = ctx->fwdsc.as<float>(); fa.status = ctx->status.as<int>();
   fa.xmx = ctx->fxmx.as<float>(); fa.xoff = ctx->xoff.as<long long>(); fa.counter = ctx->counter.as<int>();
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
-  CUDA_TRY(ctx, dispatch_fwd<true>(im.J, fa, std::min(n, sms * std::max(1, fwd_blocks_per_sm(im.J, true))), ctx->stream));
+  CUDA_TRY(ctx, dispatch_fwd(true, im.J, fa, sms, ctx->stream));
 
   FsBackwardArgs ba{};
   ba.emis = fa.emis; ba.cellb = im.cellb.as<float>(); ba.dna4 = fa.dna4; ba.wins = fa.wins; ba.nwin = n; ba.mpad = im.mpad;
@@ -772,30 +711,13 @@ extern "C" int bathgpu_fs_fetch_xrows(bathgpu_ctx *ctx, int which, float *out, i
   return BATHGPU_OK;
 }
 
-template <int J> struct DomLaunch {
-  static cudaError_t run(const DomainArgs &a, const TraceArgs &t, int sms, cudaStream_t s)
-  {
-    int nb = 0;
-    cudaError_t e;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fs5_forward_kernel<J>, 32, 0);
-    if ((e = cudaMemsetAsync(a.counter, 0, 4, s)) != cudaSuccess) return e;
-    fs5_forward_kernel<J><<<std::min(a.nenv, sms * std::max(nb, 1)), 32, 0, s>>>(a);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fs5_backward_decode_kernel<J>, 32, 0);
-    if ((e = cudaMemsetAsync(a.counter, 0, 4, s)) != cudaSuccess) return e;
-    fs5_backward_decode_kernel<J><<<std::min(a.nenv, sms * std::max(nb, 1)), 32, 0, s>>>(a);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fs5_optacc_kernel<J>, 32, 0);
-    if ((e = cudaMemsetAsync(a.counter, 0, 4, s)) != cudaSuccess) return e;
-    fs5_optacc_kernel<J><<<std::min(a.nenv, sms * std::max(nb, 1)), 32, 0, s>>>(a);
-    fs5_oatrace_kernel<<<(a.nenv + 3) / 4, 128, 0, s>>>(a, t);
-    return cudaGetLastError();
-  }
-};
-
 static cudaError_t dispatch_domains(int J, const DomainArgs &a, const TraceArgs &t, int sms, cudaStream_t s)
 {
-#define DOM(J_) case J_: return DomLaunch<J_>::run(a, t, sms, s);
-  switch (J) { DOM(1) DOM(2) DOM(3) DOM(4) DOM(5) DOM(6) DOM(7) DOM(8) DOM(10) DOM(12) default: return cudaErrorInvalidValue; }
-#undef DOM
+  cudaError_t e = cudaErrorInvalidValue;
+#define X(S) if (launch_fs5_domains_##S(J, a, t, sms, s, &e)) return e;
+  BATHGPU_FOR_EACH_SET(X)
+#undef X
+  return cudaErrorInvalidValue;
 }
 
 // p7_trace_fs_Reverse (src/p7_trace.c:2527-2568): pull N/C/J residues back by one, then reverse.
@@ -964,12 +886,14 @@ extern "C" int bathgpu_load_filter_profile(bathgpu_ctx *ctx, const bathgpu_filte
 {
   if (!ctx || !prm || !rbv || !rwv || !twv || prm->M < 1) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_load_filter_profile");
   const int M = prm->M, ld = M + 1;
-  if (M > 384) return fail(ctx, BATHGPU_EINVAL, "model length %d exceeds the single-warp kernels' limit (384)", M);
+  if (M > 1024) return fail(ctx, BATHGPU_EINVAL, "model length %d exceeds the single-warp kernels' limit (1024)", M);
   if (prm->cpu_lanes_u8 < 1 || prm->cpu_lanes_i16 < 1) return fail(ctx, BATHGPU_EINVAL, "cpu lane counts must be positive");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   ctx->flt_loaded = false;
   ctx->flt = *prm;
-  const int W = (M + 127) / 128, P = (M + 63) / 64;
+  int W = (M + 127) / 128, P = (M + 63) / 64;
+  if (W == 5) W = 6; else if (W == 7) W = 8;             // instantiated widths (launch.h)
+  if (P > 6) P = (P <= 8) ? 8 : (P <= 12) ? 12 : 16;
   ctx->flt_W = W; ctx->flt_P = P;
   const int nb = 128 * W, nw = 64 * P;                 // nodes per padded row
   std::vector<uint8_t> hb((size_t)29 * nb, 255);
@@ -1067,50 +991,16 @@ static FilterArgs filter_args(bathgpu_ctx *ctx, int n, int max_wins)
   return a;
 }
 
-template <int W, int MODE>
-static cudaError_t launch_msv(const FilterArgs &a, int sms, cudaStream_t s)
+static cudaError_t dispatch_msv(int mode, int W, const FilterArgs &a, int sms, cudaStream_t s)
 {
-  const size_t smem = (size_t)29 * 32 * W * 4;
-  int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msv_filter_kernel<W, MODE>, 128, smem);
-  const int grid = std::min((a.norf + 3) / 4, sms * std::max(nb, 1));
-  msv_filter_kernel<W, MODE><<<grid, 128, smem, s>>>(a);
-  return cudaGetLastError();
-}
-
-template <int MODE>
-static cudaError_t dispatch_msv(int W, const FilterArgs &a, int sms, cudaStream_t s)
-{
-  switch (W) {
-  case 1: return launch_msv<1, MODE>(a, sms, s);
-  case 2: return launch_msv<2, MODE>(a, sms, s);
-  case 3: return launch_msv<3, MODE>(a, sms, s);
-  default: return cudaErrorInvalidValue;
-  }
-}
-
-template <int P>
-static cudaError_t launch_vit(const FilterArgs &a, int sms, cudaStream_t s)
-{
-  const size_t smem = (size_t)(29 + 8) * 32 * P * 4;
-  int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, vit_filter_kernel<P>, 128, smem);
-  const int grid = std::min((a.norf + 3) / 4, sms * std::max(nb, 1));
-  vit_filter_kernel<P><<<grid, 128, smem, s>>>(a);
-  return cudaGetLastError();
+  cudaError_t e = cudaErrorInvalidValue;
+  return launch_msv_filter(W, mode, a, sms, s, &e) ? e : cudaErrorInvalidValue;
 }
 
 static cudaError_t dispatch_vit(int P, const FilterArgs &a, int sms, cudaStream_t s)
 {
-  switch (P) {
-  case 1: return launch_vit<1>(a, sms, s);
-  case 2: return launch_vit<2>(a, sms, s);
-  case 3: return launch_vit<3>(a, sms, s);
-  case 4: return launch_vit<4>(a, sms, s);
-  case 5: return launch_vit<5>(a, sms, s);
-  case 6: return launch_vit<6>(a, sms, s);
-  default: return cudaErrorInvalidValue;
-  }
+  cudaError_t e = cudaErrorInvalidValue;
+  return (launch_vit_filter_lo(P, a, sms, s, &e) || launch_vit_filter_hi(P, a, sms, s, &e)) ? e : cudaErrorInvalidValue;
 }
 
 static int fetch_windows(bathgpu_ctx *ctx, bathgpu_orf_window *wins, int max_wins, int *nwins)
@@ -1149,7 +1039,7 @@ extern "C" int bathgpu_msv_orfs(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n
   if (st != BATHGPU_OK) return st;
   FilterArgs a = filter_args(ctx, n, 0);
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  CUDA_TRY(ctx, dispatch_msv<0>(ctx->flt_W, a, ctx->prop.multiProcessorCount, ctx->stream));
+  CUDA_TRY(ctx, dispatch_msv(0, ctx->flt_W, a, ctx->prop.multiProcessorCount, ctx->stream));
   return finish_filter(ctx, n, sc, status, 1);
 }
 
@@ -1161,7 +1051,7 @@ extern "C" int bathgpu_ssv_windows(bathgpu_ctx *ctx, const bathgpu_orf *orfs, in
   if (st != BATHGPU_OK) return st;
   FilterArgs a = filter_args(ctx, n, max_wins);
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  CUDA_TRY(ctx, dispatch_msv<1>(ctx->flt_W, a, ctx->prop.multiProcessorCount, ctx->stream));
+  CUDA_TRY(ctx, dispatch_msv(1, ctx->flt_W, a, ctx->prop.multiProcessorCount, ctx->stream));
   if ((st = finish_filter(ctx, n, nullptr, nullptr, 1)) != BATHGPU_OK) return st;
   return fetch_windows(ctx, wins, max_wins, nwins);
 }
@@ -1185,15 +1075,6 @@ extern "C" int bathgpu_vit_orfs(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n
   return BATHGPU_OK;
 }
 
-template <int J>
-static cudaError_t launch_orf_fwd(const OrfFwdArgs &a, int sms, cudaStream_t s)
-{
-  int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, orf_forward_parser_kernel<J>, 32, 0);
-  orf_forward_parser_kernel<J><<<std::min(a.norf, sms * std::max(nb, 1)), 32, 0, s>>>(a);
-  return cudaGetLastError();
-}
-
 extern "C" int bathgpu_fwd_orfs(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n, float nj, const float xfE[2], float *fwdsc, int32_t *status)
 {
   if (!ctx || !orfs || n < 1 || !xfE || !fwdsc || !status) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fwd_orfs");
@@ -1215,54 +1096,25 @@ extern "C" int bathgpu_fwd_orfs(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n
   a.tEM = xfE[0]; a.tEL = xfE[1]; a.fwdsc = ctx->fsc.as<float>(); a.status = ctx->fst.as<int>(); a.counter = ctx->counter.as<int>();
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   const int sms = ctx->prop.multiProcessorCount;
-  cudaError_t e;
-  switch (im.J) {
-#define OF(J_) case J_: e = launch_orf_fwd<J_>(a, sms, ctx->stream); break;
-  OF(1) OF(2) OF(3) OF(4) OF(5) OF(6) OF(7) OF(8) OF(10) OF(12)
-#undef OF
-  default: e = cudaErrorInvalidValue;
-  }
+  cudaError_t e = cudaErrorInvalidValue;
+  bool found = false;
+#define X(S) if (!found) found = launch_orf_forward_parser_##S(im.J, a, sms, ctx->stream, &e);
+  BATHGPU_FOR_EACH_SET(X)
+#undef X
+  if (!found) e = cudaErrorInvalidValue;
   CUDA_TRY(ctx, e);
   return finish_filter(ctx, n, fwdsc, status, 1);
 }
 
 // ---------------------------------------------------------------------------------------------
 // Standard-translation branch: protein Forward/Backward over ORFs and the per-envelope domain stage (orf_domain.cuh)
-template <int J> struct OrfDomLaunch {
-  template <class K> static int grid_for(K kernel, int n, int sms)
-  {
-    int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 32, 0);
-    return std::min(n, sms * std::max(nb, 1));
-  }
-  static cudaError_t parsers(const OrfDomainArgs &a, int sms, cudaStream_t s)
-  {
-    cudaError_t e;
-    if ((e = cudaMemsetAsync(a.counter, 0, 4, s)) != cudaSuccess) return e;
-    orf_forward_kernel<J, false><<<grid_for(orf_forward_kernel<J, false>, a.nenv, sms), 32, 0, s>>>(a);
-    if ((e = cudaMemsetAsync(a.counter, 0, 4, s)) != cudaSuccess) return e;
-    orf_backward_kernel<J, false><<<grid_for(orf_backward_kernel<J, false>, a.nenv, sms), 32, 0, s>>>(a);
-    return cudaGetLastError();
-  }
-  static cudaError_t domains(const OrfDomainArgs &a, const TraceArgs &t, int sms, cudaStream_t s)
-  {
-    cudaError_t e;
-    if ((e = cudaMemsetAsync(a.counter, 0, 4, s)) != cudaSuccess) return e;
-    orf_forward_kernel<J, true><<<grid_for(orf_forward_kernel<J, true>, a.nenv, sms), 32, 0, s>>>(a);
-    if ((e = cudaMemsetAsync(a.counter, 0, 4, s)) != cudaSuccess) return e;
-    orf_backward_kernel<J, true><<<grid_for(orf_backward_kernel<J, true>, a.nenv, sms), 32, 0, s>>>(a);
-    if ((e = cudaMemsetAsync(a.counter, 0, 4, s)) != cudaSuccess) return e;
-    orf_optacc_kernel<J><<<grid_for(orf_optacc_kernel<J>, a.nenv, sms), 32, 0, s>>>(a);
-    orf_oatrace_kernel<<<(a.nenv + 3) / 4, 128, 0, s>>>(a, t);
-    return cudaGetLastError();
-  }
-};
-
 static cudaError_t dispatch_orf_domains(int J, bool full, const OrfDomainArgs &a, const TraceArgs &t, int sms, cudaStream_t s)
 {
-#define DOM(J_) case J_: return full ? OrfDomLaunch<J_>::domains(a, t, sms, s) : OrfDomLaunch<J_>::parsers(a, sms, s);
-  switch (J) { DOM(1) DOM(2) DOM(3) DOM(4) DOM(5) DOM(6) DOM(7) DOM(8) DOM(10) DOM(12) default: return cudaErrorInvalidValue; }
-#undef DOM
+  cudaError_t e = cudaErrorInvalidValue;
+#define X(S) if (launch_orf_domains_##S(J, full, a, t, sms, s, &e)) return e;
+  BATHGPU_FOR_EACH_SET(X)
+#undef X
+  return cudaErrorInvalidValue;
 }
 
 static const FsProfileImage *orf_image(bathgpu_ctx *ctx) { return ctx->fs3.loaded ? &ctx->fs3 : (ctx->fs5.loaded ? &ctx->fs5 : nullptr); }

@@ -336,7 +336,7 @@ struct DomainDecodeArgs {
 
 // One warp per window.  The cumulative sums run serially in one lane in the reference's order (the
 // terms are exact zeros except at the few rescaled rows); everything with an expf in it runs lane-parallel.
-__global__ void __launch_bounds__(128) fs_domain_decoding_kernel(DomainDecodeArgs a)
+static __global__ void __launch_bounds__(128) fs_domain_decoding_kernel(DomainDecodeArgs a)
 {
   const int lane = threadIdx.x & 31;
   const int w    = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);

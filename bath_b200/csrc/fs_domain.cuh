@@ -879,7 +879,7 @@ __device__ __forceinline__ int perm_of(int k, int J)      // position of node k 
   return (j / VEC) * (32 * VEC) + ln * VEC + (j % VEC);
 }
 
-__global__ void __launch_bounds__(128) fs5_oatrace_kernel(DomainArgs a, TraceArgs t)
+static __global__ void __launch_bounds__(128) fs5_oatrace_kernel(DomainArgs a, TraceArgs t)
 {
   const int lane = threadIdx.x & 31;
   const int e    = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);

@@ -1,0 +1,198 @@
+// kernels_tu.cu -- template instantiations of one kernel family for one set of node counts (see launch.h).
+// Compiled once per -DBATHGPU_FAMILY=<n> -DBATHGPU_SET=<n> combination by bath_b200/build.py.
+#include <algorithm>
+#include "launch.h"
+#include "fs_parser.cuh"
+#include "fs_parser_v3.cuh"
+#include "fs_backward.cuh"
+#include "fs_domain.cuh"
+#include "orf_domain.cuh"
+#include "orf_filters.cuh"
+
+#define FAM_FWD 1
+#define FAM_BCK 2
+#define FAM_FS5 3
+#define FAM_ORF 4
+#define FAM_FILT_MSV 5
+#define FAM_FILT_VIT_LO 6
+#define FAM_FILT_VIT_HI 7
+
+#if   BATHGPU_SET == 0
+#define SETNAME a
+#define JLIST(X) X(1) X(2) X(3) X(4) X(5)
+#elif BATHGPU_SET == 1
+#define SETNAME b
+#define JLIST(X) X(6) X(7) X(8)
+#elif BATHGPU_SET == 2
+#define SETNAME c
+#define JLIST(X) X(10) X(12)
+#elif BATHGPU_SET == 3
+#define SETNAME d
+#define JLIST(X) X(16)
+#elif BATHGPU_SET == 4
+#define SETNAME e
+#define JLIST(X) X(24)
+#elif BATHGPU_SET == 5
+#define SETNAME f
+#define JLIST(X) X(32)
+#endif
+#define CAT2(a, b) a##b
+#define CAT(a, b) CAT2(a, b)
+
+namespace bathgpu {
+
+template <class K> static int grid_for(K kernel, int threads, size_t smem, int n, int sms)
+{
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem);
+  return std::max(1, std::min(n, sms * std::max(nb, 1)));
+}
+
+#if BATHGPU_FAMILY == FAM_FWD
+template <int J, bool XMX> static cudaError_t run_fwd(int version, const FsParserArgs &a, int sms, cudaStream_t s)
+{
+  if (version >= 3) fs3_forward_parser_kernel_v3<J, XMX><<<grid_for(fs3_forward_parser_kernel_v3<J, XMX>, 32, 0, a.nwin, sms), 32, 0, s>>>(a);
+  else fs3_forward_parser_kernel<J, XMX><<<grid_for(fs3_forward_parser_kernel<J, XMX>, FwdTune<J>::kThreads, 0, a.nwin, sms), FwdTune<J>::kThreads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+bool CAT(launch_fs3_forward_, SETNAME)(int J, bool xmx, int version, const FsParserArgs &a, int sms, cudaStream_t s, cudaError_t *err)
+{
+  switch (J) {
+#define X(J_) case J_: *err = xmx ? run_fwd<J_, true>(version, a, sms, s) : run_fwd<J_, false>(version, a, sms, s); return true;
+  JLIST(X)
+#undef X
+  default: return false;
+  }
+}
+#endif
+
+#if BATHGPU_FAMILY == FAM_BCK
+bool CAT(launch_fs3_backward_, SETNAME)(int J, const FsBackwardArgs &a, int sms, cudaStream_t s, cudaError_t *err)
+{
+  switch (J) {
+#define X(J_) case J_: fs3_backward_parser_kernel<J_><<<grid_for(fs3_backward_parser_kernel<J_>, BckTune<J_>::kThreads, 0, a.nwin, sms), BckTune<J_>::kThreads, 0, s>>>(a); \
+                       *err = cudaGetLastError(); return true;
+  JLIST(X)
+#undef X
+  default: return false;
+  }
+}
+#endif
+
+#if BATHGPU_FAMILY == FAM_FS5
+template <int J> static cudaError_t run_fs5(const DomainArgs &a, const TraceArgs &t, int sms, cudaStream_t s)
+{
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(a.counter, 0, 4, s)) != cudaSuccess) return e;
+  fs5_forward_kernel<J><<<grid_for(fs5_forward_kernel<J>, 32, 0, a.nenv, sms), 32, 0, s>>>(a);
+  if ((e = cudaMemsetAsync(a.counter, 0, 4, s)) != cudaSuccess) return e;
+  fs5_backward_decode_kernel<J><<<grid_for(fs5_backward_decode_kernel<J>, 32, 0, a.nenv, sms), 32, 0, s>>>(a);
+  if ((e = cudaMemsetAsync(a.counter, 0, 4, s)) != cudaSuccess) return e;
+  fs5_optacc_kernel<J><<<grid_for(fs5_optacc_kernel<J>, 32, 0, a.nenv, sms), 32, 0, s>>>(a);
+  fs5_oatrace_kernel<<<(a.nenv + 3) / 4, 128, 0, s>>>(a, t);
+  return cudaGetLastError();
+}
+bool CAT(launch_fs5_domains_, SETNAME)(int J, const DomainArgs &a, const TraceArgs &t, int sms, cudaStream_t s, cudaError_t *err)
+{
+  switch (J) {
+#define X(J_) case J_: *err = run_fs5<J_>(a, t, sms, s); return true;
+  JLIST(X)
+#undef X
+  default: return false;
+  }
+}
+#endif
+
+#if BATHGPU_FAMILY == FAM_ORF
+template <int J> static cudaError_t run_orf(bool full, const OrfDomainArgs &a, const TraceArgs &t, int sms, cudaStream_t s)
+{
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(a.counter, 0, 4, s)) != cudaSuccess) return e;
+  if (!full) {
+    orf_forward_kernel<J, false><<<grid_for(orf_forward_kernel<J, false>, 32, 0, a.nenv, sms), 32, 0, s>>>(a);
+    if ((e = cudaMemsetAsync(a.counter, 0, 4, s)) != cudaSuccess) return e;
+    orf_backward_kernel<J, false><<<grid_for(orf_backward_kernel<J, false>, 32, 0, a.nenv, sms), 32, 0, s>>>(a);
+    return cudaGetLastError();
+  }
+  orf_forward_kernel<J, true><<<grid_for(orf_forward_kernel<J, true>, 32, 0, a.nenv, sms), 32, 0, s>>>(a);
+  if ((e = cudaMemsetAsync(a.counter, 0, 4, s)) != cudaSuccess) return e;
+  orf_backward_kernel<J, true><<<grid_for(orf_backward_kernel<J, true>, 32, 0, a.nenv, sms), 32, 0, s>>>(a);
+  if ((e = cudaMemsetAsync(a.counter, 0, 4, s)) != cudaSuccess) return e;
+  orf_optacc_kernel<J><<<grid_for(orf_optacc_kernel<J>, 32, 0, a.nenv, sms), 32, 0, s>>>(a);
+  orf_oatrace_kernel<<<(a.nenv + 3) / 4, 128, 0, s>>>(a, t);
+  return cudaGetLastError();
+}
+bool CAT(launch_orf_domains_, SETNAME)(int J, bool full, const OrfDomainArgs &a, const TraceArgs &t, int sms, cudaStream_t s, cudaError_t *err)
+{
+  switch (J) {
+#define X(J_) case J_: *err = run_orf<J_>(full, a, t, sms, s); return true;
+  JLIST(X)
+#undef X
+  default: return false;
+  }
+}
+bool CAT(launch_orf_forward_parser_, SETNAME)(int J, const OrfFwdArgs &a, int sms, cudaStream_t s, cudaError_t *err)
+{
+  switch (J) {
+#define X(J_) case J_: orf_forward_parser_kernel<J_><<<grid_for(orf_forward_parser_kernel<J_>, 32, 0, a.norf, sms), 32, 0, s>>>(a); \
+                       *err = cudaGetLastError(); return true;
+  JLIST(X)
+#undef X
+  default: return false;
+  }
+}
+#endif
+
+#if BATHGPU_FAMILY == FAM_FILT_MSV
+template <int W, int MODE> static cudaError_t run_msv(const FilterArgs &a, int sms, cudaStream_t s)
+{
+  const size_t smem = (size_t)29 * 32 * W * 4;
+  msv_filter_kernel<W, MODE><<<grid_for(msv_filter_kernel<W, MODE>, 128, smem, (a.norf + 3) / 4, sms), 128, smem, s>>>(a);
+  return cudaGetLastError();
+}
+bool launch_msv_filter(int W, int mode, const FilterArgs &a, int sms, cudaStream_t s, cudaError_t *err)
+{
+  switch (W) {
+#define X(W_) case W_: *err = mode ? run_msv<W_, 1>(a, sms, s) : run_msv<W_, 0>(a, sms, s); return true;
+  X(1) X(2) X(3) X(4) X(6) X(8)
+#undef X
+  default: return false;
+  }
+}
+#endif
+
+#if BATHGPU_FAMILY == FAM_FILT_VIT_LO || BATHGPU_FAMILY == FAM_FILT_VIT_HI
+template <int P> static cudaError_t run_vit(const FilterArgs &a, int sms, cudaStream_t s)
+{
+  const size_t smem = (size_t)(29 + 8) * 32 * P * 4;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(vit_filter_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  vit_filter_kernel<P><<<grid_for(vit_filter_kernel<P>, 128, smem, (a.norf + 3) / 4, sms), 128, smem, s>>>(a);
+  return cudaGetLastError();
+}
+#if BATHGPU_FAMILY == FAM_FILT_VIT_LO
+bool launch_vit_filter_lo(int P, const FilterArgs &a, int sms, cudaStream_t s, cudaError_t *err)
+{
+  switch (P) {
+#define X(P_) case P_: *err = run_vit<P_>(a, sms, s); return true;
+  X(1) X(2) X(3) X(4) X(5) X(6)
+#undef X
+  default: return false;
+  }
+}
+#else
+bool launch_vit_filter_hi(int P, const FilterArgs &a, int sms, cudaStream_t s, cudaError_t *err)
+{
+  switch (P) {
+#define X(P_) case P_: *err = run_vit<P_>(a, sms, s); return true;
+  X(8) X(12) X(16)
+#undef X
+  default: return false;
+  }
+}
+#endif
+#endif
+
+}  // namespace bathgpu

@@ -7,7 +7,7 @@
 namespace bathgpu {
 
 // 16 independent FFMA chains per thread (enough ILP to hide the 4-cycle pipe latency with 8+ warps per scheduler)
-__global__ void __launch_bounds__(256) fp32_fma_probe_kernel(float *out, int iters, float a, float b)
+static __global__ void __launch_bounds__(256) fp32_fma_probe_kernel(float *out, int iters, float a, float b)
 {
   float x[16];
 #pragma unroll

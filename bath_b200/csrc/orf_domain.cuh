@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(32) orf_forward_kernel(OrfDomainArgs a)
     else if (L > 0 && xC == 0.0f)  { st = 16; sc = -INFINITY; }
     else if (isinf(xC))            { st = 16; sc = xC; }
     else sc = totscale + logf(xC * pmove);
-    if (lane == 0) { a.fwdsc[e] = sc; a.status[e] = st; }
+    if (lane == 0) { a.fwdsc[e] = sc; a.status[e] = st; if (FULL) a.oasc[e] = xC * pmove; }   // oasc[] carries the unscaled path sum to the Backward sweep
   }
 }
 
@@ -191,6 +191,8 @@ __global__ void __launch_bounds__(32) orf_backward_kernel(OrfDomainArgs a)
     float *pprow_lane = FULL ? a.pp + (size_t)xo * kPPCellsP * a.mpad + lane * VEC : nullptr;
     float *ppxrow = FULL ? a.ppx + (size_t)xo * 6 : nullptr;
     const float liz = -a.fwdsc[e];
+    // 1 / (Forward's path sum in Forward's own scaling): what 1 / bck N(0) is while Backward runs on Forward's scale factors
+    const float invz = FULL ? 1.0f / a.oasc[e] : 0.f;
 
     float Mt[J], I[J], accM[J], accI[J];
     float accN = 0.f, accJ = 0.f, accC = 0.f;
@@ -275,7 +277,9 @@ __global__ void __launch_bounds__(32) orf_backward_kernel(OrfDomainArgs a)
         float fI[J], fM[J];
         load_row<J, VEC>(row + PPP_I * a.mpad, fI);
         load_row<J, VEC>(row + PPP_M * a.mpad, fM);
-        const float fac = expf(lsfrow[i] + lsb + liz);
+        // posterior = fwd * bck * scale(i) / Z (decoding.c:107-121); with Backward's own scale factors in play the
+        // cumulative log scales of both sweeps are needed instead
+        const float fac = own ? expf(lsfrow[i] + lsb + liz) : fxrow[(size_t)i * 6 + 5] * invz;
         if (isinf(fac)) st = 16;
 #pragma unroll
         for (int j = 0; j < J; ++j) {
@@ -284,7 +288,7 @@ __global__ void __launch_bounds__(32) orf_backward_kernel(OrfDomainArgs a)
         }
         store_row<J, VEC>(row + PPP_I * a.mpad, fI);
         store_row<J, VEC>(row + PPP_M * a.mpad, fM);
-        const float facx = expf(lsfrow[i - 1] + lsb + liz) * ploop;
+        const float facx = (own ? expf(lsfrow[i - 1] + lsb + liz) : invz) * ploop;
         const float *f1 = fxrow + (size_t)(i - 1) * 6;
         const float pN = f1[1] * xN * facx, pJ = f1[2] * xJ * facx, pC = f1[4] * xC * facx;
         accN += pN; accJ += pJ; accC += pC;
@@ -486,7 +490,7 @@ __global__ void __launch_bounds__(32) orf_optacc_kernel(OrfDomainArgs a)
 }
 
 // Traceback (optacc.c:225-425).  One warp per envelope, the lanes split the E-state argmax.
-__global__ void __launch_bounds__(128) orf_oatrace_kernel(OrfDomainArgs a, TraceArgs t)
+static __global__ void __launch_bounds__(128) orf_oatrace_kernel(OrfDomainArgs a, TraceArgs t)
 {
   const int lane = threadIdx.x & 31;
   const int e    = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);

@@ -7,7 +7,9 @@ sys.path.insert(0, 'tests')
 import common
 ctx = capi.Context(0)
 print(ctx.device_info())
-for hmmfile, idx in [("AMP_N.bhmm",0), ("tRNA-synthetases.bhmm",0), ("tRNA-synthetases.bhmm",2), ("PTHR37536.bhmm",0)]:
+models = [("AMP_N.bhmm",0), ("tRNA-synthetases.bhmm",0), ("tRNA-synthetases.bhmm",2), ("PTHR37536.bhmm",0)]
+if "--big" in sys.argv: models = [("MET-ct4.bhmm",0), ("synthetic_M624.bhmm",0), ("synthetic_M903.bhmm",0)]
+for hmmfile, idx in models:
     model = po.Model(common.golden(hmmfile), idx)
     ctx.load_fs_profile(3, model.rfv(3), model.tfv(3))
     rng = np.random.default_rng(1)

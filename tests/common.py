@@ -14,8 +14,64 @@ STD_CODE = "KNKNTTTTRSRSIIMIQHQHPPPPRRRRLLLLEDEDAAAAGGGGVVVV*Y*YSSSS*CWCLFLF"
 AA = "ACDEFGHIKLMNPQRSTVWY"
 
 
+SYNTHETIC = {   # long models for the kernels' large-M instantiations: node blocks of shipped models concatenated
+    "synthetic_M624.bhmm": [("tRNA-synthetases.bhmm", 0), ("tRNA-synthetases.bhmm", 1), ("tRNA-synthetases.bhmm", 2)],
+    "synthetic_M903.bhmm": [("tRNA-synthetases.bhmm", 0), ("tRNA-synthetases.bhmm", 1), ("tRNA-synthetases.bhmm", 2), ("PTHR37536.bhmm", 0)],
+}
+
+
+def _records(path):
+    out, cur = [], []
+    for line in open(path):
+        cur.append(line)
+        if line.startswith("//"):
+            out.append(cur)
+            cur = []
+    return out
+
+
+def concat_models(parts, out_path, name):
+    """One profile whose nodes are those of the given (file, index) models in a row.  The last node of every part but the final
+    one takes the transition line of the node before it (a model's last node has no delete / insert continuation).  Header,
+    statistics and the node-0 lines come from the first part."""
+    recs = [_records(golden(f))[i] for f, i in parts]
+    head_end = next(z for z, l in enumerate(recs[0]) if l.startswith("HMM "))
+    header = [l for l in recs[0][:head_end] if not l.startswith(("LENG", "MAXL", "NAME"))]
+    nodes = []
+    for r, rec in enumerate(recs):
+        h = next(z for z, l in enumerate(rec) if l.startswith("HMM "))
+        body = rec[h + 2:-1]
+        if body[0].split()[0] == "COMPO":
+            first = body[:3]
+            body = body[3:]
+        else:
+            first = body[:2]
+            body = body[2:]
+        if r == 0:
+            node0 = first
+        blocks = [body[z:z + 3] for z in range(0, len(body), 3)]
+        if r + 1 < len(recs):
+            blocks[-1] = [blocks[-1][0], blocks[-1][1], blocks[-2][2]]
+        nodes += blocks
+    with open(out_path, "w") as f:
+        f.write(header[0])
+        f.write(f"NAME  {name}\nLENG  {len(nodes)}\n")
+        f.writelines(header[1:])
+        f.writelines(recs[0][head_end:head_end + 2])
+        f.writelines(node0)
+        for k, blk in enumerate(nodes, 1):
+            fields = blk[0].split()
+            f.write(f"{k:7d}   " + "  ".join(fields[1:21]) + "      - " + fields[22] + " - \n" if len(fields) >= 23 else blk[0])
+            f.write(blk[1])
+            f.write(blk[2])
+        f.write("//\n")
+
+
 def golden(name):
-    return os.path.join(GOLDEN, name)
+    path = os.path.join(GOLDEN, name)
+    if name in SYNTHETIC and not os.path.exists(path):
+        concat_models(SYNTHETIC[name], path, name.split(".")[0])
+    return path
 
 
 def random_dna(rng, n, p_degenerate=0.0):

@@ -32,11 +32,11 @@ def test_argument_errors(oracle, gpu_ctx):
     with pytest.raises(capi.BathGpuError) as e:            # wrong table height for 3 codon lengths
         fresh.load_fs_profile(3, model.rfv(5), model.tfv(5))
     assert e.value.code == capi.EINVAL
-    big_rfv = np.ones((367, 401), np.float32)              # M = 400 exceeds the single-warp kernels
-    big_tfv = np.full((8, 401), 0.1, np.float32)
+    big_rfv = np.ones((367, 1101), np.float32)             # M = 1100 exceeds the single-warp kernels (32 lanes x 32 nodes)
+    big_tfv = np.full((8, 1101), 0.1, np.float32)
     with pytest.raises(capi.BathGpuError) as e:
         fresh.load_fs_profile(3, big_rfv, big_tfv)
-    assert e.value.code == capi.EINVAL and "384" in str(e.value)
+    assert e.value.code == capi.EINVAL and "1024" in str(e.value)
     fresh.load_fs_profile(5, model.rfv(5), model.tfv(5))
     env = capi.Context.make_windows([1], [300], nj=0.0)
     with pytest.raises(capi.BathGpuError) as e:            # trace buffer too small is an error, not a truncation

@@ -36,7 +36,7 @@ def oracle_bck_decode(po, model, dsq, start, L, xf5_loop):
 
 
 @pytest.mark.parametrize("hmmfile,index", [("AMP_N.bhmm", 0), ("2OG-FeII_Oxy_3.bhmm", 0), ("tRNA-synthetases.bhmm", 1),
-                                           ("tRNA-synthetases.bhmm", 2), ("PTHR37536.bhmm", 0)])
+                                           ("tRNA-synthetases.bhmm", 2), ("PTHR37536.bhmm", 0), ("MET-ct4.bhmm", 0), ("synthetic_M624.bhmm", 0), ("synthetic_M903.bhmm", 0)])
 def test_backward_and_domain_decoding_match_oracle(oracle, gpu_ctx, hmmfile, index):
     po = oracle
     from bath_b200 import capi

@@ -105,7 +105,7 @@ def check_envelope(po, model, ctx, dsq, envs, res, tr, t, stats):
 
 
 @pytest.mark.parametrize("hmmfile,index", [("AMP_N.bhmm", 0), ("2OG-FeII_Oxy_3.bhmm", 0), ("tRNA-synthetases.bhmm", 1),
-                                           ("tRNA-synthetases.bhmm", 2), ("PTHR37536.bhmm", 0)])
+                                           ("tRNA-synthetases.bhmm", 2), ("PTHR37536.bhmm", 0), ("MET-ct4.bhmm", 0), ("synthetic_M624.bhmm", 0), ("synthetic_M903.bhmm", 0)])
 def test_domain_stage_matches_oracle(oracle, gpu_ctx, hmmfile, index):
     po = oracle
     from bath_b200 import capi

@@ -57,7 +57,7 @@ def make_block(rng, model, n_random, n_homolog, lengths):
 
 @pytest.mark.parametrize("hmmfile,index", [("AMP_N.bhmm", 0), ("2OG-FeII_Oxy_3.bhmm", 0),
                                            ("tRNA-synthetases.bhmm", 0), ("tRNA-synthetases.bhmm", 2),
-                                           ("PTHR37536.bhmm", 0)])
+                                           ("PTHR37536.bhmm", 0), ("MET-ct4.bhmm", 0), ("synthetic_M624.bhmm", 0), ("synthetic_M903.bhmm", 0)])
 def test_forward_parser_matches_oracle(oracle, gpu_ctx, hmmfile, index):
     po = oracle
     from bath_b200 import capi

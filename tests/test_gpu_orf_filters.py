@@ -73,7 +73,7 @@ def describe(po, model, seqs, P, filtersc_of):
 
 
 @pytest.mark.parametrize("hmmfile,index", [("AMP_N.bhmm", 0), ("2OG-FeII_Oxy_3.bhmm", 0), ("tRNA-synthetases.bhmm", 1),
-                                           ("tRNA-synthetases.bhmm", 2), ("PTHR37536.bhmm", 0)])
+                                           ("tRNA-synthetases.bhmm", 2), ("PTHR37536.bhmm", 0), ("MET-ct4.bhmm", 0), ("synthetic_M624.bhmm", 0), ("synthetic_M903.bhmm", 0)])
 @pytest.mark.parametrize("lanes", [(16, 8), (32, 16)])
 def test_filters_bit_exact(oracle, gpu_ctx, hmmfile, index, lanes):
     po = oracle
@@ -123,11 +123,13 @@ def test_filters_bit_exact(oracle, gpu_ctx, hmmfile, index, lanes):
         assert got == [(n, k, ln, np.float32(sc)) for (n, k, ln, sc) in want], (t, L, got, want)
         n_swin += len(want)
     lib.bo_windowlist_free(C.byref(wl))
-    assert n_vwin > 0 and n_swin > 0 and n_overflow > 0
+    print(f"{hmmfile}[{index}] lanes={lanes}: {n_vwin} Viterbi windows, {n_swin} SSV windows, {n_overflow} MSV overflows")
+    # (whole homologs of the long models all overflow the byte filter, which leaves no Viterbi-window cases for them)
+    assert n_swin > 0 and n_overflow > 0 and (n_vwin > 0 or model.M > 400)
     print(f"{hmmfile}[{index}] lanes={lanes}: {len(seqs)} ORFs, {n_overflow} MSV overflows, {n_vwin} Viterbi windows, {n_swin} SSV windows")
 
 
-@pytest.mark.parametrize("hmmfile,index", [("AMP_N.bhmm", 0), ("tRNA-synthetases.bhmm", 1), ("PTHR37536.bhmm", 0)])
+@pytest.mark.parametrize("hmmfile,index", [("AMP_N.bhmm", 0), ("tRNA-synthetases.bhmm", 1), ("PTHR37536.bhmm", 0), ("MET-ct4.bhmm", 0), ("synthetic_M624.bhmm", 0), ("synthetic_M903.bhmm", 0)])
 def test_protein_forward_parser(oracle, gpu_ctx, hmmfile, index):
     """a6: p7_ForwardParser over ORFs, within 1e-3 nat of the oracle; statuses equal"""
     po = oracle

@@ -106,17 +106,16 @@ def test_default_pipeline_pth2_and_amp_n(oracle):
     check_amp_n_default(*run_search_cpu(oracle, "AMP_N.bhmm", "target-AMP_N.fa", std_only=1))
 
 
-def test_default_pipeline_met_codon_table_4(oracle):
+def check_met_ct4(make_search):
     """tutorial/MET-ct4.out: two queries (M = 409, 458) built for codon table 4 against a 35.6 kb target, both strands:
     every hit line (score, bias, E-value, model / alignment / envelope coordinates) and the four filter counters"""
     from bath_b200 import hostapi
     out = open(common.golden("MET-ct4.out")).read()
     parts = out.split("Query:       ")[1:]
-    be, keep = oracle.cpu_backend(4)
     for idx, part in enumerate(parts):
         rows = re.findall(r"^ !\s+(\S+)\s+(\S+)\s+(\S+)\s+(\d+)\s+(\d+) \S\S\s+(\d+)\s+(\d+) \S\S\s+(\d+)\s+(\d+)", part, re.M)
         model = hostapi.QueryModel(common.golden("MET-ct4.bhmm"), index=idx)
-        search = hostapi.Search(model, backend=be, std_only=1)
+        search = make_search(model)
         for name, seq in hostapi.read_fasta(common.golden("target-MET.fa")):
             search.add_sequence(name, hostapi.digitize_dna(seq))
         hits, st = search.finish(), search.stats()
@@ -129,6 +128,12 @@ def test_default_pipeline_met_codon_table_4(oracle):
                 ("Residues passing SSV filter", "Residues passing bias filter", "Residues passing Vit filter", "Residues passing Fwd filter")]
         assert [st["pos_past_msv"], st["pos_past_bias"], st["pos_past_vit"], st["pos_past_fwd"]] == want
         assert st["nres"] == 71226
+
+
+def test_default_pipeline_met_codon_table_4(oracle):
+    from bath_b200 import hostapi
+    be, keep = oracle.cpu_backend(4)
+    check_met_ct4(lambda model: hostapi.Search(model, backend=be, std_only=1))
     del keep
 
 
