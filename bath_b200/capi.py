@@ -19,6 +19,7 @@ EXPORTS = [
     "bathgpu_load_filter_profile", "bathgpu_upload_orfs", "bathgpu_msv_orfs", "bathgpu_ssv_windows", "bathgpu_vit_orfs",
     "bathgpu_fwd_orfs", "bathgpu_fs_fwd_bck_xrows", "bathgpu_select_slot",
     "bathgpu_orf_fwd_bck_xrows", "bathgpu_orf_domains", "bathgpu_orf_fetch_domain_matrices",
+    "bathgpu_orfs_msv_screen", "bathgpu_orfs_fetch",
 ]
 
 
@@ -43,6 +44,9 @@ class FilterParams(C.Structure):
 orf_dtype = np.dtype([("offset", "<i8"), ("L", "<i4"), ("tjb_b", "u1"), ("ssv_thresh", "u1"), ("xw_move", "<i2"),
                       ("vit_thresh", "<i2"), ("flags", "<i2"), ("ext_thresh", "<i4")], align=True)
 orf_window_dtype = np.dtype([("orf", "<i4"), ("n", "<i4"), ("k", "<i4"), ("length", "<i4"), ("score", "<f4")], align=True)
+block_dtype = np.dtype([("goff", "<i8"), ("n", "<i4"), ("C", "<i4")], align=True)
+orf_hit_dtype = np.dtype([("block", "<i4"), ("index", "<i4"), ("start", "<i4"), ("end", "<i4"), ("n", "<i4"), ("frame", "<i4"),
+                          ("offset", "<i8"), ("usc", "<f4"), ("status", "<i4")], align=True)
 
 
 class BathGpuError(RuntimeError):
@@ -117,6 +121,11 @@ def load():
     L.bathgpu_orf_domains.argtypes = [vp, vp, C.c_int, fp, vp, vp, C.c_int64]
     L.bathgpu_orf_fetch_domain_matrices.restype = C.c_int
     L.bathgpu_orf_fetch_domain_matrices.argtypes = [vp, C.c_int, fp, fp, fp, fp]
+    L.bathgpu_orfs_msv_screen.restype = C.c_int
+    L.bathgpu_orfs_msv_screen.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_uint8), fp, C.c_int, C.c_double,
+                                          C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.bathgpu_orfs_fetch.restype = C.c_int
+    L.bathgpu_orfs_fetch.argtypes = [vp, vp, C.POINTER(C.c_uint8)]
     L.bathgpu_select_slot.restype = C.c_int
     L.bathgpu_select_slot.argtypes = [vp, C.c_int]
     L.bathgpu_host_alloc.restype = vp
@@ -341,6 +350,23 @@ class Context:
         self._check(self.lib.bathgpu_fs_fwd_bck_xrows(self.h, wins.ctypes.data, n, _f(xf), _f(fx), _f(bx), _f(fsc), _f(bsc), _i(st)))
         off = np.concatenate([[0], np.cumsum(Ls + 1)])
         return [fx[off[w]: off[w + 1]] for w in range(n)], [bx[off[w]: off[w + 1]] for w in range(n)], fsc, bsc, st
+
+    def orfs_msv_screen(self, blocks, complement, gcode, min_len, tjb_of, null_of, min_bits):
+        """bathgpu_orfs_msv_screen + bathgpu_orfs_fetch: (ORFs found per block, survivors, their residues)"""
+        nb = len(blocks)
+        gcode = np.ascontiguousarray(gcode, np.uint8)
+        tjb_of = np.ascontiguousarray(tjb_of, np.uint8)
+        null_of = np.ascontiguousarray(null_of, np.float32)
+        per = np.zeros(nb, np.int64)
+        nh, nr = C.c_int64(), C.c_int64()
+        u8 = C.POINTER(C.c_uint8)
+        self._check(self.lib.bathgpu_orfs_msv_screen(self.h, blocks.ctypes.data, nb, int(complement), gcode.ctypes.data_as(u8), int(min_len),
+                                                     tjb_of.ctypes.data_as(u8), _f(null_of), len(tjb_of) - 1, float(min_bits),
+                                                     per.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(nh), C.byref(nr)))
+        hits = np.zeros(max(nh.value, 1), orf_hit_dtype)
+        res = np.zeros(max(nr.value, 1), np.uint8)
+        self._check(self.lib.bathgpu_orfs_fetch(self.h, hits.ctypes.data, res.ctypes.data_as(u8)))
+        return per, hits[: nh.value], res[: nr.value]
 
     def orf_fwd_bck_xrows(self, orfs, nj=1.0, xfE=(0.5, 0.5)):
         n = len(orfs)

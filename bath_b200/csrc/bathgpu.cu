@@ -18,6 +18,7 @@
 #include "fs_domain.cuh"
 #include "orf_domain.cuh"
 #include "orf_filters.cuh"
+#include "orf_finder.cuh"
 #include "microbench.cuh"
 #include "launch.h"
 
@@ -57,7 +58,7 @@ struct FsProfileImage {
 }  // namespace
 
 struct TargetSlot {          // one resident target: packed DNA block + ORF residues (two slots: one per strand)
-  DevBuf  dna_bytes, dna4, residues;
+  DevBuf  dna_bytes, dna4, residues, cls;
   int64_t block_n = 0, nres = 0;
 };
 
@@ -81,6 +82,8 @@ struct bathgpu_ctx {
   bathgpu_filter_params flt{};
   int           flt_W = 0, flt_P = 0;
   DevBuf        f_rbv, f_rwv, f_twv, f_ddsum, orfs, fsc, fst, fwins, fnw;
+  DevBuf        o_tiles, o_cnt, o_base, o_blocks, o_first, o_tjb, o_null, o_meta, o_hits, o_counters;
+  long long     o_nhits = 0, o_nres = 0;
   // domain stage workspace (last chunk stays resident for bathgpu_fs_fetch_domain_matrices)
   DevBuf        envs, dpp, doa, dfx, dppx, doax, dlsf, dfw, dbk, doasc, dnull2, dstat, dtoff, dtlen, dsteps;
   std::vector<long long> dom_xoff;
@@ -412,6 +415,10 @@ extern "C" int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int n
   CUDA_TRY(ctx, cudaMemcpyAsync(im.emis.p, emis.data(), emis.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   im.loaded = true;
+  // CUDA loads kernels lazily: touch the ones this profile will use now, not inside the first stage call
+#define X(S) preload_fwd_##S(J); preload_bck_##S(J); preload_fs5_##S(J); preload_orf_##S(J);
+  BATHGPU_FOR_EACH_SET(X)
+#undef X
   return BATHGPU_OK;
 }
 
@@ -942,6 +949,7 @@ extern "C" int bathgpu_load_filter_profile(bathgpu_ctx *ctx, const bathgpu_filte
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->f_ddsum.p, dds.data(), dds.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->flt_loaded = true;
+  preload_msv_filter(W); preload_vit_filter_lo(P); preload_vit_filter_hi(P);
   return BATHGPU_OK;
 }
 
@@ -980,7 +988,7 @@ static FilterArgs filter_args(bathgpu_ctx *ctx, int n, int max_wins)
 {
   FilterArgs a{};
   const bathgpu_filter_params &p = ctx->flt;
-  a.residues = ctx->S().residues.as<uint8_t>(); a.orfs = ctx->orfs.as<OrfDesc>(); a.norf = n; a.M = p.M;
+  a.residues = ctx->S().residues.as<uint8_t>(); a.res_stride = 1; a.orfs = ctx->orfs.as<OrfDesc>(); a.norf = n; a.M = p.M;
   a.rbv = ctx->f_rbv.as<uint32_t>(); a.rbv_bytes = ctx->f_rbv.as<uint8_t>(); a.rowwords_b = 32 * ctx->flt_W;
   a.tbm_b = p.tbm_b; a.tec_b = p.tec_b; a.base_b = p.base_b; a.bias_b = p.bias_b; a.scale_b = p.scale_b;
   a.rwv = ctx->f_rwv.as<uint32_t>(); a.twv = ctx->f_twv.as<uint32_t>(); a.ddsum = ctx->f_ddsum.as<int>(); a.rowwords_w = 32 * ctx->flt_P;
@@ -1298,5 +1306,117 @@ extern "C" int bathgpu_orf_fetch_domain_matrices(bathgpu_ctx *ctx, int e, float 
       if (pc) { pc[0] = hp[(i * kPPCellsP + PPP_M) * mpad + p]; pc[1] = 0.f; pc[2] = hp[(i * kPPCellsP + PPP_I) * mpad + p]; }
       if (oc) { oc[0] = ho[(i * kOACells + OA_M) * mpad + p]; oc[1] = ho[(i * kOACells + OA_D) * mpad + p]; oc[2] = ho[(i * kOACells + OA_I) * mpad + p]; }
     }
+  return BATHGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// f1: ORFs of every block of the resident strand found on the device, MSV over all of them, F1 screen (orf_finder.cuh)
+extern "C" int bathgpu_orfs_msv_screen(bathgpu_ctx *ctx, const bathgpu_block *blocks, int nblocks, int complement, const uint8_t gcode[64],
+                                       int min_len, const uint8_t *tjb_of, const float *null_of, int max_len, double min_bits,
+                                       int64_t *norfs_per_block, int64_t *nhits, int64_t *nres)
+{
+  if (!ctx || !blocks || nblocks < 1 || !gcode || min_len < 1 || !tjb_of || !null_of || max_len < 1 || !nhits || !nres)
+    return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_orfs_msv_screen");
+  if (!ctx->flt_loaded)      return fail(ctx, BATHGPU_EINVAL, "filter profile not loaded");
+  TargetSlot &S = ctx->S();
+  if (S.block_n == 0)        return fail(ctx, BATHGPU_EINVAL, "no block uploaded");
+  static_assert(sizeof(BlockDesc) == sizeof(bathgpu_block), "block layouts must agree");
+  static_assert(sizeof(OrfHit) == sizeof(bathgpu_orf_hit), "hit layouts must agree");
+  std::vector<int> tile_block, tile_p0;
+  std::vector<long long> first_tile((size_t)nblocks + 1, 0);
+  for (int b = 0; b < nblocks; ++b) {
+    if (blocks[b].n < 0 || blocks[b].goff < 0 || blocks[b].goff + blocks[b].n > S.block_n)
+      return fail(ctx, BATHGPU_EINVAL, "block %d (offset %lld, n %d) is outside the uploaded sequence (n=%lld)", b, (long long)blocks[b].goff, blocks[b].n, (long long)S.block_n);
+    first_tile[b] = (long long)tile_block.size();
+    if (blocks[b].n >= 3)
+      for (int p0 = 1; p0 <= blocks[b].n + 1; p0 += kOrfTile) { tile_block.push_back(b); tile_p0.push_back(p0); }
+  }
+  first_tile[nblocks] = (long long)tile_block.size();
+  const int ntiles = (int)tile_block.size();
+  *nhits = 0; *nres = 0;
+  ctx->o_nhits = 0; ctx->o_nres = 0; S.nres = 0;
+  if (norfs_per_block) for (int b = 0; b < nblocks; ++b) norfs_per_block[b] = 0;
+  if (ntiles == 0) return BATHGPU_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const long long n = S.block_n;
+  if (S.cls.reserve((size_t)n + 64) != BATHGPU_OK || ctx->o_tiles.reserve((size_t)ntiles * 8) != BATHGPU_OK || ctx->o_cnt.reserve((size_t)ntiles * 4) != BATHGPU_OK ||
+      ctx->o_base.reserve((size_t)ntiles * 8) != BATHGPU_OK || ctx->o_blocks.reserve((size_t)nblocks * sizeof(BlockDesc)) != BATHGPU_OK ||
+      ctx->o_first.reserve((size_t)nblocks * 8) != BATHGPU_OK || ctx->o_tjb.reserve((size_t)max_len + 1) != BATHGPU_OK ||
+      ctx->o_null.reserve(((size_t)max_len + 1) * 4) != BATHGPU_OK || ctx->o_counters.reserve(64) != BATHGPU_OK || ctx->counter.reserve(64) != BATHGPU_OK)
+    return fail(ctx, BATHGPU_EMEM, "device allocation failed");
+  int *d_tile_block = ctx->o_tiles.as<int>(), *d_tile_p0 = ctx->o_tiles.as<int>() + ntiles;
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_tile_block, tile_block.data(), (size_t)ntiles * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_tile_p0, tile_p0.data(), (size_t)ntiles * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->o_blocks.p, blocks, (size_t)nblocks * sizeof(BlockDesc), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->o_tjb.p, tjb_of, (size_t)max_len + 1, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->o_null.p, null_of, ((size_t)max_len + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  GeneticCode gc;
+  memcpy(gc.aa, gcode, 64);
+  {
+    const long long nthreads = (n + 7) / 8;
+    codon_class_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, ctx->stream>>>(S.dna4.as<uint32_t>(), n, gc, S.cls.as<uint8_t>());
+  }
+  OrfScanArgs sa{};
+  sa.cls = S.cls.as<uint8_t>(); sa.blocks = ctx->o_blocks.as<BlockDesc>(); sa.tile_block = d_tile_block; sa.tile_p0 = d_tile_p0;
+  sa.ntiles = ntiles; sa.min_len = min_len; sa.complement = complement; sa.tile_cnt = ctx->o_cnt.as<int>();
+  orf_scan_kernel<false><<<ntiles, kOrfTileThreads, 0, ctx->stream>>>(sa);
+  CUDA_TRY(ctx, cudaGetLastError());
+  std::vector<int> cnt((size_t)ntiles);
+  CUDA_TRY(ctx, cudaMemcpyAsync(cnt.data(), ctx->o_cnt.p, (size_t)ntiles * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  std::vector<long long> base((size_t)ntiles + 1, 0), bfirst((size_t)nblocks, 0);
+  for (int t = 0; t < ntiles; ++t) base[t + 1] = base[t] + cnt[t];
+  for (int b = 0; b < nblocks; ++b) {
+    bfirst[b] = base[first_tile[b]];
+    if (norfs_per_block) norfs_per_block[b] = base[first_tile[b + 1]] - base[first_tile[b]];
+  }
+  const long long N = base[ntiles];
+  if (N == 0) return BATHGPU_OK;
+  if (N > 0x7fffffffLL) return fail(ctx, BATHGPU_EINVAL, "%lld ORFs in one call: split the sequence", N);
+  if (ctx->orfs.reserve((size_t)N * sizeof(OrfDesc)) != BATHGPU_OK || ctx->o_meta.reserve((size_t)N * sizeof(OrfMeta)) != BATHGPU_OK ||
+      ctx->fsc.reserve((size_t)N * 4) != BATHGPU_OK || ctx->fst.reserve((size_t)N * 4) != BATHGPU_OK ||
+      ctx->o_hits.reserve((size_t)N * sizeof(OrfHit)) != BATHGPU_OK || S.residues.reserve((size_t)n + 64) != BATHGPU_OK)
+    return fail(ctx, BATHGPU_EMEM, "device allocation failed for %lld ORFs", N);
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->o_base.p, base.data(), (size_t)ntiles * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->o_first.p, bfirst.data(), (size_t)nblocks * 8, cudaMemcpyHostToDevice, ctx->stream));
+  sa.tile_base = ctx->o_base.as<long long>(); sa.block_first = ctx->o_first.as<long long>(); sa.tjb_of = ctx->o_tjb.as<uint8_t>();
+  sa.max_len = max_len; sa.descs = ctx->orfs.as<OrfDesc>(); sa.meta = ctx->o_meta.as<OrfMeta>();
+  orf_scan_kernel<true><<<ntiles, kOrfTileThreads, 0, ctx->stream>>>(sa);
+  CUDA_TRY(ctx, cudaGetLastError());
+  // MSV over every ORF, residues read from the codon classes with stride 3
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
+  FilterArgs fa = filter_args(ctx, (int)N, 0);
+  fa.residues = S.cls.as<uint8_t>(); fa.res_stride = 3;
+  CUDA_TRY(ctx, dispatch_msv(0, ctx->flt_W, fa, ctx->prop.multiProcessorCount, ctx->stream));
+  OrfScreenArgs ra{};
+  ra.cls = S.cls.as<uint8_t>(); ra.descs = ctx->orfs.as<OrfDesc>(); ra.meta = ctx->o_meta.as<OrfMeta>(); ra.usc = ctx->fsc.as<float>();
+  ra.status = ctx->fst.as<int>(); ra.norf = N; ra.null_of = ctx->o_null.as<float>(); ra.max_len = max_len; ra.min_bits = min_bits;
+  ra.hits = ctx->o_hits.as<OrfHit>(); ra.residues = S.residues.as<uint8_t>(); ra.counters = ctx->o_counters.as<unsigned long long>();
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->o_counters.p, 0, 16, ctx->stream));
+  orf_screen_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(ra);
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  unsigned long long hc[2] = { 0, 0 };
+  CUDA_TRY(ctx, cudaMemcpyAsync(hc, ctx->o_counters.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+  ctx->last_launches = 5;
+  ctx->o_nhits = (long long)hc[0]; ctx->o_nres = (long long)hc[1];
+  S.nres = (int64_t)hc[1];
+  *nhits = (int64_t)hc[0]; *nres = (int64_t)hc[1];
+  return BATHGPU_OK;
+}
+
+extern "C" int bathgpu_orfs_fetch(bathgpu_ctx *ctx, bathgpu_orf_hit *hits, uint8_t *residues)
+{
+  if (!ctx || (ctx->o_nhits > 0 && (!hits || !residues))) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_orfs_fetch");
+  if (ctx->o_nhits == 0) return BATHGPU_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaMemcpyAsync(hits, ctx->o_hits.p, (size_t)ctx->o_nhits * sizeof(OrfHit), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(residues, ctx->S().residues.p, (size_t)ctx->o_nres, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  std::sort(hits, hits + ctx->o_nhits, [](const bathgpu_orf_hit &x, const bathgpu_orf_hit &y) {
+    return x.block != y.block ? x.block < y.block : x.index < y.index; });
   return BATHGPU_OK;
 }

@@ -41,6 +41,8 @@
 
 namespace bathgpu {
 
+template <class K> static void touch(K kernel) { cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kernel); }
+
 template <class K> static int grid_for(K kernel, int threads, size_t smem, int n, int sms)
 {
   int nb = 0;
@@ -64,6 +66,15 @@ bool CAT(launch_fs3_forward_, SETNAME)(int J, bool xmx, int version, const FsPar
   default: return false;
   }
 }
+void CAT(preload_fwd_, SETNAME)(int J)
+{
+  switch (J) {
+#define X(J_) case J_: touch(fs3_forward_parser_kernel_v3<J_, false>); touch(fs3_forward_parser_kernel_v3<J_, true>); break;
+  JLIST(X)
+#undef X
+  default: break;
+  }
+}
 #endif
 
 #if BATHGPU_FAMILY == FAM_BCK
@@ -75,6 +86,15 @@ bool CAT(launch_fs3_backward_, SETNAME)(int J, const FsBackwardArgs &a, int sms,
   JLIST(X)
 #undef X
   default: return false;
+  }
+}
+void CAT(preload_bck_, SETNAME)(int J)
+{
+  switch (J) {
+#define X(J_) case J_: touch(fs3_backward_parser_kernel<J_>); break;
+  JLIST(X)
+#undef X
+  default: break;
   }
 }
 #endif
@@ -99,6 +119,15 @@ bool CAT(launch_fs5_domains_, SETNAME)(int J, const DomainArgs &a, const TraceAr
   JLIST(X)
 #undef X
   default: return false;
+  }
+}
+void CAT(preload_fs5_, SETNAME)(int J)
+{
+  switch (J) {
+#define X(J_) case J_: touch(fs5_forward_kernel<J_>); touch(fs5_backward_decode_kernel<J_>); touch(fs5_optacc_kernel<J_>); touch(fs5_oatrace_kernel); break;
+  JLIST(X)
+#undef X
+  default: break;
   }
 }
 #endif
@@ -141,6 +170,16 @@ bool CAT(launch_orf_forward_parser_, SETNAME)(int J, const OrfFwdArgs &a, int sm
   default: return false;
   }
 }
+void CAT(preload_orf_, SETNAME)(int J)
+{
+  switch (J) {
+#define X(J_) case J_: touch(orf_forward_kernel<J_, false>); touch(orf_forward_kernel<J_, true>); touch(orf_backward_kernel<J_, false>); \
+                       touch(orf_backward_kernel<J_, true>); touch(orf_optacc_kernel<J_>); touch(orf_oatrace_kernel); touch(orf_forward_parser_kernel<J_>); break;
+  JLIST(X)
+#undef X
+  default: break;
+  }
+}
 #endif
 
 #if BATHGPU_FAMILY == FAM_FILT_MSV
@@ -157,6 +196,15 @@ bool launch_msv_filter(int W, int mode, const FilterArgs &a, int sms, cudaStream
   X(1) X(2) X(3) X(4) X(6) X(8)
 #undef X
   default: return false;
+  }
+}
+void preload_msv_filter(int W)
+{
+  switch (W) {
+#define X(W_) case W_: touch(msv_filter_kernel<W_, 0>); touch(msv_filter_kernel<W_, 1>); break;
+  X(1) X(2) X(3) X(4) X(6) X(8)
+#undef X
+  default: break;
   }
 }
 #endif
@@ -182,6 +230,15 @@ bool launch_vit_filter_lo(int P, const FilterArgs &a, int sms, cudaStream_t s, c
   default: return false;
   }
 }
+void preload_vit_filter_lo(int P)
+{
+  switch (P) {
+#define X(P_) case P_: touch(vit_filter_kernel<P_>); break;
+  X(1) X(2) X(3) X(4) X(5) X(6)
+#undef X
+  default: break;
+  }
+}
 #else
 bool launch_vit_filter_hi(int P, const FilterArgs &a, int sms, cudaStream_t s, cudaError_t *err)
 {
@@ -190,6 +247,15 @@ bool launch_vit_filter_hi(int P, const FilterArgs &a, int sms, cudaStream_t s, c
   X(8) X(12) X(16)
 #undef X
   default: return false;
+  }
+}
+void preload_vit_filter_hi(int P)
+{
+  switch (P) {
+#define X(P_) case P_: touch(vit_filter_kernel<P_>); break;
+  X(8) X(12) X(16)
+#undef X
+  default: break;
   }
 }
 #endif

@@ -24,7 +24,8 @@ struct FilterArgs;
   bool launch_fs3_backward_##S(int J, const FsBackwardArgs &a, int sms, cudaStream_t s, cudaError_t *err);                           \
   bool launch_fs5_domains_##S(int J, const DomainArgs &a, const TraceArgs &t, int sms, cudaStream_t s, cudaError_t *err);            \
   bool launch_orf_domains_##S(int J, bool full, const OrfDomainArgs &a, const TraceArgs &t, int sms, cudaStream_t s, cudaError_t *err); \
-  bool launch_orf_forward_parser_##S(int J, const OrfFwdArgs &a, int sms, cudaStream_t s, cudaError_t *err);
+  bool launch_orf_forward_parser_##S(int J, const OrfFwdArgs &a, int sms, cudaStream_t s, cudaError_t *err);                        \
+  void preload_fwd_##S(int J); void preload_bck_##S(int J); void preload_fs5_##S(int J); void preload_orf_##S(int J);
 BATHGPU_FOR_EACH_SET(BATHGPU_DECLARE_SET)
 #undef BATHGPU_DECLARE_SET
 
@@ -32,5 +33,8 @@ BATHGPU_FOR_EACH_SET(BATHGPU_DECLARE_SET)
 bool launch_msv_filter(int W, int mode, const FilterArgs &a, int sms, cudaStream_t s, cudaError_t *err);
 bool launch_vit_filter_lo(int P, const FilterArgs &a, int sms, cudaStream_t s, cudaError_t *err);      // P = 1..6
 bool launch_vit_filter_hi(int P, const FilterArgs &a, int sms, cudaStream_t s, cudaError_t *err);      // P = 8, 12, 16
+// Touch the kernels a profile of this size will use, so that the driver loads their code when the profile is loaded and not
+// inside the first stage call (CUDA loads kernels lazily).
+void preload_msv_filter(int W); void preload_vit_filter_lo(int P); void preload_vit_filter_hi(int P);
 
 }  // namespace bathgpu

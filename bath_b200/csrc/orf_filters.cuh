@@ -40,6 +40,7 @@ struct WindowRec { int orf, n, k, length; float score; };
 
 struct FilterArgs {
   const uint8_t  *residues;
+  int             res_stride;   // 1: residue buffer; 3: codon classes of the resident strand, one per nucleotide (orf_finder.cuh; MSV scores only)
   const OrfDesc  *orfs;
   int             norf;
   int             M;
@@ -107,6 +108,10 @@ __global__ void __launch_bounds__(128) msv_filter_kernel(FilterArgs a)
     if (o >= a.norf) break;
     const OrfDesc od = a.orfs[o];
     const int L = od.L;
+    if (od.flags & 2) {                                    // wholly inside the block's overlap context: not scored (p7_pipeline.c:1634-1637)
+      if (MODE == 0 && lane == 0) { a.sc[o] = -INFINITY; a.status[o] = 0; }
+      continue;
+    }
     const int tjbm = (int)(uint8_t)((int8_t)od.tjb_b + (int8_t)a.tbm_b);      // set1_epi8 of the 8-bit sum (:120)
     uint32_t m[W];
 #pragma unroll
@@ -123,7 +128,7 @@ __global__ void __launch_bounds__(128) msv_filter_kernel(FilterArgs a)
       {
         if (i >= chunk + 32 || i < chunk) {
           chunk = i;
-          myres = (i + lane <= L) ? a.residues[od.offset + i + lane - 1] : 0u;
+          myres = (i + lane <= L) ? a.residues[od.offset + (long long)(i + lane - 1) * a.res_stride] : 0u;
         }
         const unsigned x = __shfl_sync(full, myres, i - chunk);
         uint32_t rb[W];

@@ -21,6 +21,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <memory>
 
 #include "../../include/bathhost.h"
 #include "../../include/bathgpu.h"
@@ -157,6 +158,7 @@ struct Orf {
   long long offset;          // first residue in the block's residue buffer
   int n;                     // residues
   int window_idx = -1;       // orfsq->idx
+  int local_idx = 0;         // rank among ALL ORFs of its block: the reference's index i (hit_windows ids)
 };
 
 struct OrfWin { int id, n, k, length; float score; };      // P7_HMM_WINDOW fields the pipeline reads
@@ -235,39 +237,6 @@ struct StageTimer {              // adds the time since construction / last lap 
 #define BE_TRY(s, call, what)                                                                   \
   do { int st_ = (call); if (st_ != 0) return fail(s, st_, std::string(what) + " failed: " +    \
        (s->be.last_error ? s->be.last_error(s->be.ctx) : "?")); } while (0)
-
-// Six-frame translation is done three frames at a time on the oriented block (bathsearch reverse-complements the
-// block itself, src/bathsearch.c:1087-1096).  ORFs are maximal stop-free runs of whole codons of at least min_len
-// residues, any codon may start one (Easel esl_gencode_ProcessStart/Piece/End with default options); a codon holding
-// a degenerate nucleotide translates to X.  Emitted in order of their last nucleotide, as a left-to-right scan ends them.
-void find_orfs(const uint8_t *dsq, int n, const uint8_t gcode[64], int min_len, std::vector<Orf> &orfs, std::vector<uint8_t> &res)
-{
-  orfs.clear(); res.clear();
-  res.reserve((size_t) n);
-  for (int f = 0; f < 3; ++f) {
-    int run_start = -1;
-    size_t run_res = res.size();
-    auto close = [&](int end) {
-      const int len = (int) (res.size() - run_res);
-      if (run_start > 0 && len >= min_len) {
-        Orf r; r.start = run_start; r.end = end; r.frame = f; r.offset = (long long) run_res; r.n = len;
-        orfs.push_back(r);
-      } else res.resize(run_res);              // too short: its residues are dropped
-      run_start = -1; run_res = res.size();
-    };
-    int i = f + 1;
-    for (; i + 2 <= n; i += 3) {
-      const uint8_t a = dsq[i], b = dsq[i + 1], c = dsq[i + 2];
-      uint8_t aa = 26;                                   // X
-      if (a < 4 && b < 4 && c < 4) aa = gcode[16 * a + 4 * b + c];
-      if (aa == kKp - 2) close(i - 1);                   // a stop codon ends the run before it
-      else { if (run_start < 0) { run_start = i; run_res = res.size(); } res.push_back(aa); }
-    }
-    if (run_start > 0) close(run_start + 3 * (int) (res.size() - run_res) - 1);     // open at the end: ends at its last whole codon
-  }
-  // a left-to-right scan over the three interleaved frames finishes ORFs in order of their last nucleotide
-  std::sort(orfs.begin(), orfs.end(), [](const Orf &x, const Orf &y) { return x.end < y.end; });
-}
 
 // p7_pli_ComputeLocalCompo (src/p7_pipeline.c:427-458)
 void local_compo(const bathhost_model *m, const Background &bg, int k_start, int k_end, float *compo)
@@ -420,7 +389,10 @@ struct BlockInfo {
 
 struct Strand {
   bool complement = false;
-  std::vector<uint8_t> dsq;                 // the whole sequence in this orientation, 1..n with sentinels
+  struct Seq {                              // the whole sequence in this orientation, 1..n with sentinels: the caller's buffer (top) or an owned copy
+    const uint8_t *p = nullptr; std::unique_ptr<uint8_t[]> own;
+    const uint8_t *data() const { return p; }
+  } dsq;
   std::vector<Orf> orfs;                    // of all blocks, block-local coordinates
   std::vector<int> orf_blk;                 // block of each ORF
   std::vector<int> orf_begin;               // [nblocks+1] range of each block's ORFs
@@ -462,46 +434,60 @@ int filter_strand(bathhost_search *s, Strand &S, const std::vector<BlockInfo> &b
   Background &bg = s->bg;
   StageTimer tm;
 
-  S.orf_begin.assign(blocks.size() + 1, 0);
-  {
-    // blocks are independent: translate them on all host cores, then concatenate in block order
-    const size_t nblk = blocks.size();
-    std::vector<std::vector<Orf>> bo(nblk);
-    std::vector<std::vector<uint8_t>> br(nblk);
-    const unsigned nthr = (unsigned) std::max<size_t>(1, std::min<size_t>({ nblk, (size_t) std::thread::hardware_concurrency(), (size_t) 32 }));
-    std::vector<std::thread> pool;
-    for (unsigned t = 0; t < nthr; ++t)
-      pool.emplace_back([&, t]() {
-        for (size_t b = t; b < nblk; b += nthr)
-          if (blocks[b].n >= 15) find_orfs(S.dsq.data() + S.goff(blocks[b], n_total), blocks[b].n, s->gcode, opt.min_orf, bo[b], br[b]);
-      });
-    for (auto &th : pool) th.join();
-    std::vector<size_t> o0(nblk + 1, 0), r0(nblk + 1, 0);
-    for (size_t b = 0; b < nblk; ++b) { o0[b + 1] = o0[b] + bo[b].size(); r0[b + 1] = r0[b] + br[b].size(); }
-    S.orfs.resize(o0[nblk]); S.orf_blk.resize(o0[nblk]); S.residues.resize(r0[nblk]);
-    for (size_t b = 0; b <= nblk; ++b) S.orf_begin[b] = (int) o0[b];
-    parallel_chunks(nblk, 1, [&](size_t ba, size_t bb) {
-      for (size_t b = ba; b < bb; ++b) {
-        for (size_t z = 0; z < bo[b].size(); ++z) {
-          Orf o = bo[b][z]; o.offset += (long long) r0[b];
-          S.orfs[o0[b] + z] = o; S.orf_blk[o0[b] + z] = (int) b;
-        }
-        if (!br[b].empty()) memcpy(S.residues.data() + r0[b], br[b].data(), br[b].size());
-      }
-    });
+  // ---- stage 1: translation of every block, MSV over every ORF and the cheap side of the F1 test in ONE device call
+  // (src/bathsearch.c:385-392, src/p7_pipeline.c:1632-1652).  What comes back are the ORFs that can still pass F1,
+  // with their block-local rank in the reference's ORF order (the window bookkeeping keys on it) and their residues.
+  BE_TRY(s, s->be.select_slot(s->be.ctx, slot), "bathgpu_select_slot");
+  BE_TRY(s, s->be.upload_block(s->be.ctx, S.dsq.data(), n_total), "bathgpu_upload_block");
+  tm.lap(s->st.us_upload);
+  const size_t nblk = blocks.size();
+  S.orf_begin.assign(nblk + 1, 0);
+  std::vector<bathgpu_block> bdesc(nblk);
+  int maxlen = 1;
+  for (size_t b = 0; b < nblk; ++b) {
+    bdesc[b].goff = S.goff(blocks[b], n_total); bdesc[b].n = (blocks[b].n >= 15) ? blocks[b].n : 0; bdesc[b].C = blocks[b].C;
+    maxlen = std::max(maxlen, blocks[b].n / 3 + 1);
   }
-  const int norf = (int) S.orfs.size();
-  s->st.n_orfs += norf;
+  // per-length integers and null1 scores depend on the ORF length only: tabulated once per strand
+  std::vector<uint8_t> tjb_of((size_t) maxlen + 1);
+  std::vector<float>   null_of((size_t) maxlen + 1);
+  tjb_of[0] = q.tjb_for_length(1); null_of[0] = 0.0f;
+  parallel_chunks((size_t) maxlen, 4096, [&](size_t a0, size_t a1) {
+    Background lbg = bg;
+    for (size_t L = a0 + 1; L <= a1; ++L) { tjb_of[L] = q.tjb_for_length((int) L); lbg.set_length((int) L); null_of[L] = lbg.null_one((int) L); }
+  });
+  // the Gumbel tail is monotone: P > F1 exactly when the bit score is below x1 = invsurv(F1); the device keeps what is within a
+  // margin of x1 or above it, the exact tail is evaluated here for those
+  const double x1 = gumbel_invsurv(opt.F1, ev[EV_MMU], ev[EV_MLAMBDA]);
+  std::vector<int64_t> norfs_blk(nblk, 0);
+  int64_t nsurv = 0, nsres = 0;
+  BE_TRY(s, s->be.orfs_msv_screen(s->be.ctx, bdesc.data(), (int) nblk, S.complement ? 1 : 0, s->gcode, opt.min_orf, tjb_of.data(), null_of.data(),
+                                   maxlen, x1 - 0.02, norfs_blk.data(), &nsurv, &nsres), "bathgpu_orfs_msv_screen");
+  for (size_t b = 0; b < nblk; ++b) s->st.n_orfs += norfs_blk[b];
+  std::vector<bathgpu_orf_hit> surv((size_t) nsurv);
+  S.residues.resize((size_t) nsres);
+  BE_TRY(s, s->be.orfs_fetch(s->be.ctx, surv.data(), S.residues.data()), "bathgpu_orfs_fetch");
+  const int norf = (int) nsurv;
+  S.orfs.resize((size_t) norf); S.orf_blk.resize((size_t) norf);
+  {
+    size_t z = 0;
+    for (size_t b = 0; b < nblk; ++b) {
+      S.orf_begin[b] = (int) z;
+      while (z < surv.size() && surv[z].block == (int) b) {
+        Orf &o = S.orfs[z];
+        o.start = surv[z].start; o.end = surv[z].end; o.frame = surv[z].frame; o.offset = surv[z].offset; o.n = surv[z].n;
+        o.local_idx = surv[z].index; o.window_idx = -1;
+        S.orf_blk[z] = (int) b;
+        ++z;
+      }
+    }
+    S.orf_begin[nblk] = (int) z;
+  }
   S.P_orf.assign((size_t) norf, 1.0);
   S.fwdsc_orf.assign((size_t) norf, kNegInfF);
   S.wins_of_orf.assign((size_t) norf, {});
-  tm.lap(s->st.us_orfs);
-
-  BE_TRY(s, s->be.select_slot(s->be.ctx, slot), "bathgpu_select_slot");
-  BE_TRY(s, s->be.upload_block(s->be.ctx, S.dsq.data(), n_total), "bathgpu_upload_block");
+  tm.lap(s->st.us_msv);
   if (norf == 0) return 0;
-  BE_TRY(s, s->be.upload_orfs(s->be.ctx, S.residues.data(), (int64_t) S.residues.size()), "bathgpu_upload_orfs");
-  tm.lap(s->st.us_upload);
 
   std::vector<Orf> &orfs = S.orfs;
   const std::vector<uint8_t> &residues = S.residues;
@@ -509,64 +495,51 @@ int filter_strand(bathhost_search *s, Strand &S, const std::vector<BlockInfo> &b
     buf.assign((size_t) o.n + 2, 255);
     memcpy(buf.data() + 1, residues.data() + o.offset, (size_t) o.n);
   };
-
-  // ---- stage 1: MSV over every ORF not wholly inside the overlap context (:1632-1652)
-  std::vector<int> live;
-  for (int i = 0; i < norf; ++i) {
-    const Orf &o = orfs[i];
-    const BlockInfo &blk = blocks[S.orf_blk[i]];
-    const bool in_context = S.complement ? ((blk.n - o.start + 1) < blk.C) : (o.end < blk.C);
-    if (!in_context && o.n > 0) live.push_back(i);
-  }
-  if (live.empty()) return 0;
-  // per-length integers and null1 scores depend on the ORF length only: tabulate them once per strand
-  int maxlen = 0;
-  for (int i : live) maxlen = std::max(maxlen, orfs[i].n);
-  std::vector<uint8_t> tjb_of((size_t) maxlen + 1);
-  std::vector<int16_t> xw_of((size_t) maxlen + 1);
-  std::vector<float>   null_of((size_t) maxlen + 1);
-  for (int L = 1; L <= maxlen; ++L) {
-    tjb_of[L] = q.tjb_for_length(L); xw_of[L] = q.xw_move_for_length(L);
-    bg.set_length(L); null_of[L] = bg.null_one(L);
-  }
-  std::vector<bathgpu_orf> desc(live.size());
-  for (size_t t = 0; t < live.size(); ++t) {
-    const Orf &o = orfs[live[t]];
-    bathgpu_orf &d = desc[t];
-    memset(&d, 0, sizeof d);
-    d.offset = o.offset; d.L = o.n;
-    d.tjb_b = tjb_of[o.n]; d.xw_move = xw_of[o.n];
-  }
-  std::vector<float> usc(live.size());
-  std::vector<int32_t> ust(live.size());
-  BE_TRY(s, s->be.msv_orfs(s->be.ctx, desc.data(), (int) desc.size(), usc.data(), ust.data()), "bathgpu_msv_orfs");
-  tm.lap(s->st.us_msv);
+  std::vector<int> live((size_t) norf);
+  std::vector<float> usc((size_t) norf);
+  for (int i = 0; i < norf; ++i) { live[i] = i; usc[i] = surv[i].usc; }
   struct Cand { int orf; float nullsc, usc, filtersc, vfsc; double P; bool need_vit; };
   std::vector<Cand> cand;
   std::vector<uint8_t> buf;
-  // the Gumbel tail is monotone: P > F1 exactly when the bit score is below x1 = invsurv(F1); the tail is only evaluated
-  // for scores within a margin of x1 (where rounding could matter) or above it
-  const double x1 = gumbel_invsurv(opt.F1, ev[EV_MMU], ev[EV_MLAMBDA]);
-  for (size_t t = 0; t < live.size(); ++t) {
-    const Orf &o = orfs[live[t]];
-    const float nullsc = null_of[o.n];
-    float seqsc = (usc[t] - nullsc) / kLog2;
-    if (seqsc < x1 - 0.01) continue;
-    double P = gumbel_surv(seqsc, ev[EV_MMU], ev[EV_MLAMBDA]);
-    if (P > opt.F1) continue;
-    bg.set_length(o.n);
-    s->st.pos_past_msv += (int64_t) o.n * 3;
-    float filtersc = nullsc;
-    if (opt.do_bias) {                                  // (:1657-1663)
-      orf_dsq(o, buf);
-      filtersc = bg.filter_score(buf.data(), o.n);
-      seqsc = (usc[t] - filtersc) / kLog2;
-      P = gumbel_surv(seqsc, ev[EV_MMU], ev[EV_MLAMBDA]);
-      if (P > opt.F1) continue;
+  {
+    // the exact F1 test and the bias filter of each survivor are independent of one another: all host cores, then the
+    // counters and the candidate list in ORF order
+    struct Pre { uint8_t stage; float filtersc; double P; };       // stage 0: fails F1 on the MSV score, 1: fails after the bias filter, 2: passes
+    std::vector<Pre> pre(live.size());
+    parallel_chunks(live.size(), 256, [&](size_t ta, size_t tb) {
+      Background lbg = bg;
+      std::vector<uint8_t> lbuf;
+      for (size_t t = ta; t < tb; ++t) {
+        const Orf &o = orfs[live[t]];
+        const float nullsc = null_of[o.n];
+        float seqsc = (usc[t] - nullsc) / kLog2;
+        Pre &r = pre[t];
+        r.stage = 0; r.filtersc = nullsc; r.P = 1.0;
+        if (seqsc < x1 - 0.01) continue;
+        double P = gumbel_surv(seqsc, ev[EV_MMU], ev[EV_MLAMBDA]);
+        if (P > opt.F1) continue;
+        r.stage = 1;
+        if (opt.do_bias) {                                  // (:1657-1663)
+          lbg.set_length(o.n);
+          orf_dsq(o, lbuf);
+          r.filtersc = lbg.filter_score(lbuf.data(), o.n);
+          seqsc = (usc[t] - r.filtersc) / kLog2;
+          P = gumbel_surv(seqsc, ev[EV_MMU], ev[EV_MLAMBDA]);
+          if (P > opt.F1) continue;
+        }
+        r.stage = 2; r.P = P;
+      }
+    });
+    for (size_t t = 0; t < live.size(); ++t) {
+      if (pre[t].stage == 0) continue;
+      const Orf &o = orfs[live[t]];
+      s->st.pos_past_msv += (int64_t) o.n * 3;
+      if (pre[t].stage == 1) continue;
+      s->st.pos_past_bias += (int64_t) o.n * 3;
+      Cand c; c.orf = live[t]; c.nullsc = null_of[o.n]; c.usc = usc[t]; c.filtersc = pre[t].filtersc; c.vfsc = kNegInfF; c.P = pre[t].P;
+      c.need_vit = (c.P > opt.F2);
+      cand.push_back(c);
     }
-    s->st.pos_past_bias += (int64_t) o.n * 3;
-    Cand c; c.orf = live[t]; c.nullsc = nullsc; c.usc = usc[t]; c.filtersc = filtersc; c.vfsc = kNegInfF; c.P = P; c.need_vit = (P > opt.F2);
-    cand.push_back(c);
   }
   tm.lap(s->st.us_bias);
   if (cand.empty()) return 0;
@@ -689,7 +662,7 @@ int filter_strand(bathhost_search *s, Strand &S, const std::vector<BlockInfo> &b
       const float seqsc = (fsc[z] - c.filtersc) / kLog2;
       S.P_orf[c.orf] = exp_surv(seqsc, ev[EV_FTAU], ev[EV_FLAMBDA]);
       S.fwdsc_orf[c.orf] = fsc[z] - c.nullsc;
-      for (const OrfWin &w : wins_of[keep[z]]) { OrfWin x = w; x.id = c.orf - S.orf_begin[S.orf_blk[c.orf]]; S.wins_of_orf[c.orf].push_back(x); }
+      for (const OrfWin &w : wins_of[keep[z]]) { OrfWin x = w; x.id = S.orfs[c.orf].local_idx; S.wins_of_orf[c.orf].push_back(x); }
     }
   }
 
@@ -705,7 +678,7 @@ void build_dna_windows(bathhost_search *s, Strand &S, const BlockInfo &blk, int 
   const int M = q.M;
   std::vector<DnaWin> dwin;
   for (int gi = S.orf_begin[b]; gi < S.orf_begin[b + 1]; ++gi) {
-    const int f = gi - S.orf_begin[b];
+    const int f = S.orfs[gi].local_idx;
     if (S.P_orf[gi] > opt.F4) continue;
     Orf &o = S.orfs[gi];
     int best = -1; float best_score = kNegInfF;
@@ -781,23 +754,25 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
   const size_t nb = blocks.size();
 
   Strand strands[2];
+  StageTimer tm0;
   std::vector<int> active;
   if (opt.top)    active.push_back(0);
   if (opt.bottom) active.push_back(1);
   for (int sidx : active) {
     Strand &S = strands[sidx];
     S.complement = (sidx == 1);
-    S.dsq.resize((size_t) n + 2);
-    S.dsq[0] = S.dsq[(size_t) n + 1] = 255;
-    {
+    if (!S.complement) S.dsq.p = dsq;                       // searched in place
+    else {
       static const uint8_t comp[18] = { 3, 2, 1, 0, 4, 6, 5, 8, 7, 9, 10, 14, 13, 12, 11, 15, 16, 17 };
-      const bool rc = S.complement;
-      uint8_t *out = S.dsq.data();
+      S.dsq.own.reset(new uint8_t[(size_t) n + 2]);
+      uint8_t *out = S.dsq.own.get();
+      out[0] = out[(size_t) n + 1] = 255;
       parallel_chunks((size_t) n, 1 << 20, [&](size_t a, size_t b) {
-        if (!rc) memcpy(out + 1 + a, dsq + 1 + a, b - a);
-        else for (size_t p = a; p < b; ++p) { const uint8_t c = dsq[(size_t) n - p]; out[1 + p] = (c < 18) ? comp[c] : c; }   // oriented p+1 <- original n-p
+        for (size_t p = a; p < b; ++p) { const uint8_t c = dsq[(size_t) n - p]; out[1 + p] = (c < 18) ? comp[c] : c; }   // oriented p+1 <- original n-p
       });
+      S.dsq.p = out;
     }
+    tm0.lap(s->st.us_orfs);
     int st = filter_strand(s, S, blocks, n, sidx);
     if (st != 0) return st;
     S.aligned.assign(S.orfs.size(), 0);
@@ -843,64 +818,78 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
   }
   tm.lap(s->st.us_fs_fwd);
 
-  // ---- arbitration per window (:1392-1465)
-  float lcompo[kK];
+  // ---- arbitration per window (:1392-1465): the scores each window needs (ORF sums, null and bias filter scores) are
+  // independent of one another and computed on all host cores; the decisions are then taken in the reference's order
   for (int sidx : active) {
     Strand &S = strands[sidx];
-    for (int w = 0; w < (int) S.dwin.size(); ++w) {
-      const int b = S.dwin_blk[w];
-      const BlockInfo &blk = blocks[b];
-      const DnaWin &dw = S.dwin[w];
-      const uint8_t *wdsq = S.dsq.data() + S.goff(blk, n) + dw.n - 1;        // window position p is wdsq[p]
-      int orf_cnt = 0, k_min = M, k_max = 0;
-      float tot_orfsc = kNegInfF;
-      double P_tot, P_min = std::numeric_limits<double>::infinity();
-      size_t last_h = 0;
-      const size_t hw_n = S.hw_count[b];
-      for (int gi = S.orf_begin[b]; gi < S.orf_begin[b + 1]; ++gi) {
-        if (S.P_orf[gi] > opt.F4) continue;
-        const int i = gi - S.orf_begin[b];
-        const Orf &o = S.orfs[gi];
-        const bool inside = S.complement ? (o.start >= dw.n && o.end <= dw.n + dw.length + 1)
-                                         : (o.start >= dw.n && o.end <= dw.n + dw.length - 1);
-        if (!inside) continue;
-        S.orfs[gi].window_idx = w;
-        P_min = std::min(P_min, S.P_orf[gi]);
-        tot_orfsc = flogsum(tot_orfsc, S.fwdsc_orf[gi]);
-        orf_cnt++;
-        size_t h = last_h;
-        while (h < hw_n && hit_windows[h].id != i) h++;
-        if (h < hw_n) {
-          while (h < hw_n && hit_windows[h].id == i) {
-            k_min = std::min(k_min, hit_windows[h].k - hit_windows[h].length + 1);
-            k_max = std::max(k_max, hit_windows[h].k);
-            h++;
+    const int nw = (int) S.dwin.size();
+    struct WinPre { int orf_cnt; double P_tot, P_min; float nullsc, filtersc; };
+    std::vector<WinPre> pre((size_t) nw);
+    auto inside_of = [&](const Orf &o, const DnaWin &dw) {
+      return S.complement ? (o.start >= dw.n && o.end <= dw.n + dw.length + 1) : (o.start >= dw.n && o.end <= dw.n + dw.length - 1);
+    };
+    parallel_chunks((size_t) nw, 1, [&](size_t wa, size_t wb) {
+      Background lbg = bg;
+      float lcompo[kK];
+      for (size_t w = wa; w < wb; ++w) {
+        const int b = S.dwin_blk[w];
+        const BlockInfo &blk = blocks[b];
+        const DnaWin &dw = S.dwin[w];
+        const uint8_t *wdsq = S.dsq.data() + S.goff(blk, n) + dw.n - 1;        // window position p is wdsq[p]
+        int orf_cnt = 0, k_min = M, k_max = 0;
+        float tot_orfsc = kNegInfF;
+        double P_min = std::numeric_limits<double>::infinity();
+        size_t last_h = 0;
+        const size_t hw_n = S.hw_count[b];
+        for (int gi = S.orf_begin[b]; gi < S.orf_begin[b + 1]; ++gi) {
+          if (S.P_orf[gi] > opt.F4) continue;
+          const Orf &o = S.orfs[gi];
+          const int i = o.local_idx;
+          if (!inside_of(o, dw)) continue;
+          P_min = std::min(P_min, S.P_orf[gi]);
+          tot_orfsc = flogsum(tot_orfsc, S.fwdsc_orf[gi]);
+          orf_cnt++;
+          size_t h = last_h;
+          while (h < hw_n && hit_windows[h].id != i) h++;
+          if (h < hw_n) {
+            while (h < hw_n && hit_windows[h].id == i) {
+              k_min = std::min(k_min, hit_windows[h].k - hit_windows[h].length + 1);
+              k_max = std::max(k_max, hit_windows[h].k);
+              h++;
+            }
+            last_h = h;
           }
-          last_h = h;
+        }
+        WinPre &r = pre[w];
+        r.orf_cnt = orf_cnt; r.P_min = P_min;
+        r.P_tot = exp_surv(tot_orfsc / kLog2, ev[EV_FTAU], ev[EV_FLAMBDA]);
+        lbg.set_filter(M, s->compo.data());
+        lbg.set_length(dw.length / 3);
+        r.nullsc = lbg.fs_null_one(dw.length / 3);
+        r.filtersc = r.nullsc;
+        if (opt.do_bias) {
+          r.filtersc = lbg.fs_filter_score(wdsq, dw.length, s->gcode);
+          if (k_min <= k_max) {
+            local_compo(m, lbg, k_min, k_max, lcompo);
+            lbg.set_filter(M, lcompo);
+            lbg.set_length(dw.length / 3);
+            const float lf = lbg.fs_filter_score(wdsq, dw.length, s->gcode);
+            if (lf > r.filtersc) r.filtersc = lf;
+          }
         }
       }
-      P_tot = exp_surv(tot_orfsc / kLog2, ev[EV_FTAU], ev[EV_FLAMBDA]);
-
-      bg.set_length(dw.length / 3);
-      const float nullsc = bg.fs_null_one(dw.length / 3);
-      float filtersc = nullsc;
-      if (opt.do_bias) {
-        filtersc = bg.fs_filter_score(wdsq, dw.length, s->gcode);
-        if (k_min <= k_max) {
-          local_compo(m, bg, k_min, k_max, lcompo);
-          bg.set_filter(M, lcompo);
-          bg.set_length(dw.length / 3);
-          const float lf = bg.fs_filter_score(wdsq, dw.length, s->gcode);
-          if (lf > filtersc) filtersc = lf;
-          bg.set_filter(M, s->compo.data());
-          bg.set_length(dw.length / 3);
-        }
-      }
+    });
+    for (int w = 0; w < nw; ++w) {
+      const int b = S.dwin_blk[w];
+      const DnaWin &dw = S.dwin[w];
+      const WinPre &r = pre[w];
+      for (int gi = S.orf_begin[b]; gi < S.orf_begin[b + 1]; ++gi)
+        if (S.P_orf[gi] <= opt.F4 && inside_of(S.orfs[gi], dw)) S.orfs[gi].window_idx = w;
       const float fwdsc = S.fs_fwd[w];                      // on eslERANGE the score is -inf or NaN and the tests below fail, as in the reference
-      const float seqscore = (fwdsc - filtersc) / kLog2;
+      const float seqscore = (fwdsc - r.filtersc) / kLog2;
       const double P_fs   = exp_surv(seqscore, ev[EV_FTAUFS3], ev[EV_FLAMBDA]);
-      const double P_null = exp_surv((fwdsc - nullsc) / kLog2, ev[EV_FTAUFS3], ev[EV_FLAMBDA]);
-      if (S.fs_st[w] == 0 && P_fs <= opt.F3 && (P_null < P_tot || (P_null == P_tot && orf_cnt > 1) || P_min > opt.F3)) {
+      const double P_null = exp_surv((fwdsc - r.nullsc) / kLog2, ev[EV_FTAUFS3], ev[EV_FLAMBDA]);
+      if (S.fs_st[w] == 0 && P_fs <= opt.F3 && (P_null < r.P_tot || (P_null == r.P_tot && r.orf_cnt > 1) || r.P_min > opt.F3)) {
         s->st.pos_past_fwd += dw.length;
         S.fsw.push_back(w);
       } else {                                              // standard-translation branch (:1480-1511)

@@ -209,6 +209,28 @@ int bathgpu_fs_domains(bathgpu_ctx *ctx, const bathgpu_envelope *envs, int n, co
  * decoding), oa [(L+1)][(M+1)][3] {M,D,I}, ppx / oax [(L+1)][6] {E,N,J,B,C,SCALE}.  Any pointer may be NULL. */
 int bathgpu_fs_fetch_domain_matrices(bathgpu_ctx *ctx, int e, float *pp, float *oa, float *ppx, float *oax);
 
+/* ---- f1: six-frame translation, MSV and the F1 screen on the device -------------------------------------------- */
+/* One block of the resident strand: block position p (1..n) is position goff + p of the uploaded sequence; C = nucleotides of
+ * overlap context (dnasq->C): ORFs wholly inside it are not scored (src/p7_pipeline.c:1634-1637). */
+typedef struct { int64_t goff; int32_t n; int32_t C; } bathgpu_block;
+/* An ORF that survived the screen: block and rank inside the block (the reference's ORF order: by last nucleotide), block-local
+ * nucleotide coordinates of its first and last nucleotide, residues, frame (0..2), offset of its residues in the device residue
+ * buffer (what bathgpu_orf.offset of the later stage calls refers to), MSV score (nats) and status. */
+typedef struct { int32_t block, index, start, end, n, frame; int64_t offset; float usc; int32_t status; } bathgpu_orf_hit;
+
+/* Replaces, for a GPU build, the translation of each block (esl_gencode_Process*, src/bathsearch.c:385-392), the upload of ORF
+ * residues and the head of the per-ORF loop (p7_MSVFilter and the cheap side of the F1 test, src/p7_pipeline.c:1632-1652) for ALL
+ * blocks of the selected slot's sequence in one call.  complement: the uploaded sequence is the reverse complement (decides which
+ * end the overlap context is at).  gcode[64]: amino-acid code (27 = stop) of codon 16 a + 4 b + c.  tjb_of[L], null_of[L] for
+ * L = 0..max_len (longer ORFs use max_len): unbiased_byteify(logf(3/(L+3))) and p7_bg_NullOne for that length.  An ORF survives
+ * when its MSV score overflowed or (usc - null_of[L]) / ln 2 >= min_bits; the caller then applies its exact P-value test.
+ * Outputs: ORFs found per block, survivors and their residues (left in the device residue buffer; copy them out with
+ * bathgpu_orfs_fetch, which returns them sorted by block and rank). */
+int bathgpu_orfs_msv_screen(bathgpu_ctx *ctx, const bathgpu_block *blocks, int nblocks, int complement, const uint8_t gcode[64],
+                            int min_len, const uint8_t *tjb_of, const float *null_of, int max_len, double min_bits,
+                            int64_t *norfs_per_block, int64_t *nhits, int64_t *nres);
+int bathgpu_orfs_fetch(bathgpu_ctx *ctx, bathgpu_orf_hit *hits, uint8_t *residues);
+
 /* ---- f2: the standard-translation branch over ORFs ------------------------ */
 /* p7_ForwardParser + p7_BackwardParser over ORFs of the uploaded residue buffer, X rows kept (what oxf_holder[i] and
  * pli->oxb hold at src/p7_pipeline.c:1492-1495 / :1762-1764): fwd_xrows / bck_xrows = {E,N,J,B,C,SCALE} x (L+1) per ORF,

@@ -116,6 +116,10 @@ typedef struct {
   int (*orf_fwd_bck_xrows)(void *ctx, const void *orfs, int n, float nj, const float xfE[2], float *fwd_xrows, float *bck_xrows,
                            float *fwdsc, float *bcksc, int32_t *status);
   int (*orf_domains)(void *ctx, const void *envs, int n, const float xfE[2], void *results, void *traces, int64_t max_steps);
+  int (*orfs_msv_screen)(void *ctx, const void *blocks, int nblocks, int complement, const uint8_t gcode[64], int min_len,
+                         const uint8_t *tjb_of, const float *null_of, int max_len, double min_bits,
+                         int64_t *norfs_per_block, int64_t *nhits, int64_t *nres);
+  int (*orfs_fetch)(void *ctx, void *hits, uint8_t *residues);
 } bathhost_backend;
 
 /* 0 / unset fields take bathsearch's defaults (src/p7_pipeline.c:145-214; src/bathsearch.c:94) */

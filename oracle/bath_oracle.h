@@ -305,6 +305,10 @@ double bo_exp_logsurv(double x, double mu, double lambda);
 /* ===== orf_fwd.c (impl_sse/fwdback.c) ===== */
 int    bo_ForwardParser(const uint8_t *dsq, int L, const BO_OPROFILE *om, float *opt_sc);
 
+/* ===== orfs.c: six-frame translation (Easel esl_gencode semantics) ===== */
+typedef struct { int start, end, frame, n; int64_t offset; } BO_ORF;    /* nucleotide coordinates on the oriented strand, start < end */
+int    bo_find_orfs(const uint8_t *dsq, int n, const uint8_t *gcode, int min_len, BO_ORF **ret_orfs, int *ret_n, uint8_t **ret_res, int64_t *ret_nres);
+
 /* ===== orf_domain.c: the standard-translation branch's DP over an ORF (src/impl_sse/fwdback.c, decoding.c, optacc.c, null2.c) ===== */
 void   bo_oprofile_ReconfigMultihit(BO_OPROFILE *om, int L);
 void   bo_oprofile_ReconfigUnihit(BO_OPROFILE *om, int L);

@@ -449,3 +449,89 @@ int bo_backend_orf_domains(void *ctx, const void *envs, int n, const float xfE[2
   free(tr);
   return rc;
 }
+
+/* ---- translation + MSV + F1 screen over all blocks of the resident strand (bathgpu_orfs_msv_screen on the CPU) ---- */
+typedef struct { const bathgpu_block *blk; int complement; const uint8_t *gcode; int min_len; BO_ORF **orfs; int *norf; uint8_t **res; int64_t *nres; } xl_args;
+static void xl_item(bo_backend *b, void *arg, int i)
+{
+  xl_args *a = arg;
+  a->orfs[i] = NULL; a->norf[i] = 0; a->res[i] = NULL; a->nres[i] = 0;
+  if (a->blk[i].n >= 3) bo_find_orfs(b->dsq[b->cur] + a->blk[i].goff, a->blk[i].n, a->gcode, a->min_len, &a->orfs[i], &a->norf[i], &a->res[i], &a->nres[i]);
+}
+typedef struct { bo_backend *b; const BO_ORF *orfs; const uint8_t *res; const uint8_t *tjb_of; int max_len; float *usc; int32_t *st; const uint8_t *dead; } msvx_args;
+static void msvx_item(bo_backend *b, void *arg, int i)
+{
+  msvx_args *a = arg;
+  BO_OPROFILE om = *b->om;
+  int L = a->orfs[i].n;
+  uint8_t *d;
+  if (a->dead[i]) { a->usc[i] = -INFINITY; a->st[i] = 0; return; }
+  d = malloc((size_t) L + 2);
+  d[0] = d[L + 1] = BO_DSQ_SENTINEL;
+  memcpy(d + 1, a->res + a->orfs[i].offset, (size_t) L);
+  om.tjb_b = a->tjb_of[L < a->max_len ? L : a->max_len];
+  a->st[i] = bo_MSVFilter(d, L, &om, &a->usc[i]);
+  free(d);
+}
+
+static bathgpu_orf_hit *g_hits[2];       /* per slot: survivors of the last screen (the backend is single-context in tests and bench) */
+static int64_t          g_nhits[2];
+
+int bo_backend_orfs_msv_screen(void *ctx, const void *blocks, int nblocks, int complement, const uint8_t gcode[64], int min_len,
+                               const uint8_t *tjb_of, const float *null_of, int max_len, double min_bits,
+                               int64_t *norfs_per_block, int64_t *nhits, int64_t *nres)
+{
+  bo_backend *b = ctx;
+  const bathgpu_block *blk = blocks;
+  BO_ORF **orfs = calloc((size_t) nblocks, sizeof(BO_ORF *));
+  int *norf = calloc((size_t) nblocks, sizeof(int));
+  uint8_t **res = calloc((size_t) nblocks, sizeof(uint8_t *));
+  int64_t *nr = calloc((size_t) nblocks, sizeof(int64_t));
+  xl_args xa = { blk, complement, gcode, min_len, orfs, norf, res, nr };
+  int64_t tot_hits = 0, tot_res = 0, cap_res = 0;
+  int bi, i, s = b->cur;
+  parallel_for(b, nblocks, xl_item, &xa);
+  free(g_hits[s]); g_hits[s] = NULL; g_nhits[s] = 0;
+  free(b->res[s]); b->res[s] = NULL; b->nres[s] = 0;
+  for (bi = 0; bi < nblocks; bi++) cap_res += nr[bi];
+  b->res[s] = malloc((size_t) (cap_res > 0 ? cap_res : 1));
+  for (bi = 0; bi < nblocks; bi++) {
+    int n = norf[bi];
+    float *usc = malloc(sizeof(float) * (size_t) (n > 0 ? n : 1));
+    int32_t *st = malloc(sizeof(int32_t) * (size_t) (n > 0 ? n : 1));
+    uint8_t *dead = calloc((size_t) (n > 0 ? n : 1), 1);
+    msvx_args ma = { b, orfs[bi], res[bi], tjb_of, max_len, usc, st, dead };
+    if (norfs_per_block) norfs_per_block[bi] = n;
+    for (i = 0; i < n; i++)
+      dead[i] = complement ? ((blk[bi].n - orfs[bi][i].start + 1) < blk[bi].C) : (orfs[bi][i].end < blk[bi].C);
+    parallel_for(b, n, msvx_item, &ma);
+    for (i = 0; i < n; i++) {
+      int L = orfs[bi][i].n, keep;
+      if (dead[i]) continue;
+      keep = (st[i] != 0) || (((double) usc[i] - (double) null_of[L < max_len ? L : max_len]) / 0.69314718055994529 >= min_bits);
+      if (!keep) continue;
+      g_hits[s] = realloc(g_hits[s], sizeof(bathgpu_orf_hit) * (size_t) (tot_hits + 1));
+      g_hits[s][tot_hits].block = bi; g_hits[s][tot_hits].index = i; g_hits[s][tot_hits].start = orfs[bi][i].start;
+      g_hits[s][tot_hits].end = orfs[bi][i].end; g_hits[s][tot_hits].n = L; g_hits[s][tot_hits].frame = orfs[bi][i].frame;
+      g_hits[s][tot_hits].offset = tot_res; g_hits[s][tot_hits].usc = usc[i]; g_hits[s][tot_hits].status = st[i];
+      memcpy(b->res[s] + tot_res, res[bi] + orfs[bi][i].offset, (size_t) L);
+      tot_res += L; tot_hits++;
+    }
+    free(usc); free(st); free(dead); free(orfs[bi]); free(res[bi]);
+  }
+  free(orfs); free(norf); free(res); free(nr);
+  g_nhits[s] = tot_hits; b->nres[s] = tot_res;
+  *nhits = tot_hits; *nres = tot_res;
+  return BO_OK;
+}
+
+int bo_backend_orfs_fetch(void *ctx, void *hits, uint8_t *residues)
+{
+  bo_backend *b = ctx;
+  int s = b->cur;
+  if (g_nhits[s] > 0) {
+    memcpy(hits, g_hits[s], sizeof(bathgpu_orf_hit) * (size_t) g_nhits[s]);
+    memcpy(residues, b->res[s], (size_t) b->nres[s]);
+  }
+  return BO_OK;
+}

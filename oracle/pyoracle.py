@@ -73,6 +73,10 @@ class WINDOWLIST(C.Structure):
     _fields_ = [("w", C.POINTER(WINDOW)), ("count", C.c_int), ("nalloc", C.c_int)]
 
 
+class ORF(C.Structure):
+    _fields_ = [("start", C.c_int), ("end", C.c_int), ("frame", C.c_int), ("n", C.c_int), ("offset", C.c_int64)]
+
+
 class MX(C.Structure):
     _fields_ = [("M", C.c_int), ("L", C.c_int), ("allocL", C.c_int), ("nscells", C.c_int),
                 ("dp", C.POINTER(C.c_float)), ("xmx", C.POINTER(C.c_float)), ("totscale", C.c_float),
@@ -154,6 +158,7 @@ def lib(native=False):
         "bo_ViterbiFilter_BATH": (C.c_int, [u8p, C.c_int, P(OPROFILE), u8p, C.c_float, C.c_double, C.c_int,
                                             P(WINDOWLIST), fp]),
         "bo_ForwardParser": (C.c_int, [u8p, C.c_int, P(OPROFILE), fp]),
+        "bo_find_orfs": (C.c_int, [u8p, C.c_int, u8p, C.c_int, P(P(ORF)), P(C.c_int), P(u8p), P(C.c_int64)]),
         "bo_oprofile_ReconfigMultihit": (None, [P(OPROFILE), C.c_int]),
         "bo_oprofile_ReconfigUnihit": (None, [P(OPROFILE), C.c_int]),
         "bo_Forward": (C.c_int, [u8p, C.c_int, P(OPROFILE), P(MX), fp]),
@@ -305,6 +310,20 @@ def digitize_amino(seq):
     a = np.full(len(seq) + 2, 255, dtype=np.uint8)
     a[1:-1] = [_AA[c] for c in seq.upper()]
     return a
+
+
+def find_orfs(dsq, n, gcode, min_len):
+    """bo_find_orfs: list of (start, end, frame, residues array) in the reference's order"""
+    L = lib()
+    orfs, norf, res, nres = C.POINTER(ORF)(), C.c_int(), C.POINTER(C.c_uint8)(), C.c_int64()
+    g = np.ascontiguousarray(gcode, np.uint8)
+    d = np.ascontiguousarray(dsq, np.uint8)
+    assert L.bo_find_orfs(u8ptr(d), int(n), u8ptr(g), int(min_len), C.byref(orfs), C.byref(norf), C.byref(res), C.byref(nres)) == 0
+    r = np.ctypeslib.as_array(res, shape=(max(nres.value, 1),))[: nres.value].copy()
+    out = [(orfs[i].start, orfs[i].end, orfs[i].frame, r[orfs[i].offset: orfs[i].offset + orfs[i].n]) for i in range(norf.value)]
+    libc = C.CDLL(None)
+    libc.free(orfs); libc.free(res)
+    return out
 
 
 def windows(wl):
