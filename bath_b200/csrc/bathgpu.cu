@@ -43,7 +43,7 @@ struct DevBuf {
 };
 
 struct FsProfileImage {
-  int   which = 0, M = 0, nrows = 0, J = 0, mpad = 0;
+  int   which = 0, M = 0, nrows = 0, J = 0, mpad = 0, scan_steps = 5;
   DevBuf emis;     // [nrows][mpad]
   DevBuf cellc;    // forward lane constants
   DevBuf cellb;    // backward lane constants
@@ -281,15 +281,21 @@ extern "C" int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int n
       bfull[lane] = pp;
     }
     std::vector<double> b(bfull);
+    im.scan_steps = 5;
     for (int s = 0; s < 5; ++s) {
       int d = 1 << s;
       std::vector<double> nb(b);
+      double biggest = 0.0;
       for (int lane = 0; lane < 32; ++lane) {
         cc[(size_t)(FC_COUNT * J + FL_B0 + s) * 32 + lane] = (lane >= d) ? (float)b[lane] : 0.0f;
-        if (lane >= d) nb[lane] = b[lane] * b[lane - d];
+        if (lane >= d) { biggest = std::max(biggest, b[lane]); nb[lane] = b[lane] * b[lane - d]; }
       }
+      // step s carries D in from 2^s lanes away with these multipliers: below 1e-9 everywhere it (and every later step) changes
+      // nothing at float resolution -- the cut-off the reference's own D->D passes apply (fwdback_fs.c:415-453)
+      if (biggest < 1.0e-9 && im.scan_steps == 5) im.scan_steps = std::max(s, 2);
       b.swap(nb);
     }
+    if (getenv("BATHGPU_FULL_SCAN")) im.scan_steps = 5;
     if (im.cellc.reserve(cc.size() * sizeof(float)) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
     CUDA_TRY(ctx, cudaMemcpyAsync(im.cellc.p, cc.data(), cc.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -521,7 +527,7 @@ extern "C" int bathgpu_fs_fwd_staged(bathgpu_ctx *ctx, const float xfE[2])
   a.wins = ctx->wins.as<WindowDesc>(); a.nwin = ctx->nstaged; a.mpad = im.mpad;
   a.tEM = xfE[0]; a.tEL = xfE[1];
   a.fwdsc = ctx->fwdsc.as<float>(); a.status = ctx->status.as<int>();
-  a.xmx = nullptr; a.xoff = nullptr; a.counter = ctx->counter.as<int>();
+  a.xmx = nullptr; a.xoff = nullptr; a.counter = ctx->counter.as<int>(); a.scan_steps = im.scan_steps;
 
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
@@ -596,7 +602,7 @@ static int bck_decode_chunk(bathgpu_ctx *ctx, const bathgpu_window *wins, int n,
   fa.emis = im.emis.as<float>(); fa.cellc = im.cellc.as<float>(); fa.dna4 = ctx->S().dna4.as<uint32_t>();
   fa.wins = ctx->wins.as<WindowDesc>(); fa.nwin = n; fa.mpad = im.mpad; fa.tEM = xfE[0]; fa.tEL = xfE[1];
   fa.fwdsc = ctx->fwdsc.as<float>(); fa.status = ctx->status.as<int>();
-  fa.xmx = ctx->fxmx.as<float>(); fa.xoff = ctx->xoff.as<long long>(); fa.counter = ctx->counter.as<int>();
+  fa.xmx = ctx->fxmx.as<float>(); fa.xoff = ctx->xoff.as<long long>(); fa.counter = ctx->counter.as<int>(); fa.scan_steps = im.scan_steps;
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
   CUDA_TRY(ctx, dispatch_fwd(true, im.J, fa, sms, ctx->stream));
 

@@ -55,6 +55,7 @@ struct FsParserArgs {
   float          *xmx;         // optional: X rows, window w at xmx + xoff[w]*6
   const long long *xoff;
   int            *counter;     // work-queue counter
+  int             scan_steps;  // steps of the D->D warp scan this profile needs (5 = all; fewer when the D->D odds products die out)
 };
 
 template <int J> struct VecOf { static constexpr int V = (J % 4 == 0) ? 4 : ((J % 2 == 0) ? 2 : 1); };

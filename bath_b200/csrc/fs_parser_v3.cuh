@@ -17,7 +17,7 @@ namespace bathgpu {
 struct RowOut { float xE, xN, xJ, xC, xB, scale; };
 
 // Row i without the rescale test and without the X-row store.
-template <int J, int VEC, int PH>
+template <int J, int VEC, int PH, int NS>
 __device__ __forceinline__ void fwd_row_compute(int i, int lane, FwdState<J> &S, const FwdConsts<J> &K,
                                                 const char *__restrict__ emis_lane, unsigned rowbytes, uint32_t cw,
                                                 float ploop, float pmove, float tEL, float tEM, RowOut &R)
@@ -44,7 +44,7 @@ __device__ __forceinline__ void fwd_row_compute(int i, int lane, FwdState<J> &S,
 #pragma unroll
   for (int j = 0; j < J; ++j) { a[j] = m[j] * K.md[j]; A = (j == 0) ? a[0] : fmaf(A, K.dd[j], a[j]); }
 #pragma unroll
-  for (int s = 0; s < 5; ++s) {
+  for (int s = 0; s < NS; ++s) {                 // NS < 5: the products of D->D odds over 2^NS lanes are below 1e-9 for this profile
     float up = __shfl_up_sync(0xffffffffu, A, 1 << s);
     A = fmaf(K.bs[s], up, A);
   }
@@ -98,15 +98,15 @@ __device__ __forceinline__ void store_xrow(int i, int lane, const RowOut &R, flo
 }
 
 // Rows i (phase PH) and i+1 (phase PH+1) in one block, then the rescale logic for both in order.
-template <int J, int VEC, int PH, bool XMX>
+template <int J, int VEC, int PH, bool XMX, int NS>
 __device__ __forceinline__ void fwd_row_pair(int i, int lane, FwdState<J> &S, const FwdConsts<J> &K,
                                              const char *__restrict__ emis_lane, unsigned rowbytes, uint32_t cwA, uint32_t cwB,
                                              float ploop, float pmove, float tEL, float tEM,
                                              float &totscale, float *__restrict__ xrow)
 {
   RowOut A, B;
-  fwd_row_compute<J, VEC, PH>(i, lane, S, K, emis_lane, rowbytes, cwA, ploop, pmove, tEL, tEM, A);
-  fwd_row_compute<J, VEC, PH + 1>(i + 1, lane, S, K, emis_lane, rowbytes, cwB, ploop, pmove, tEL, tEM, B);
+  fwd_row_compute<J, VEC, PH, NS>(i, lane, S, K, emis_lane, rowbytes, cwA, ploop, pmove, tEL, tEM, A);
+  fwd_row_compute<J, VEC, PH + 1, NS>(i + 1, lane, S, K, emis_lane, rowbytes, cwB, ploop, pmove, tEL, tEM, B);
   if (A.xE > 1.0e4f || B.xE > 1.0e4f) {          // rare, warp-uniform
     if (A.xE > 1.0e4f) {
       const float sf = 1.0f / A.xE;
@@ -133,7 +133,7 @@ __device__ __forceinline__ void fwd_row_pair(int i, int lane, FwdState<J> &S, co
 #define BATHGPU_V3_WARPS(J) ((J) <= 2 ? 20 : (J) == 3 ? 18 : (J) == 4 ? 16 : (J) == 5 ? 14 : (J) == 6 ? 11 : (J) == 7 ? 10 : (J) == 8 ? 9 : 8)
 #endif
 
-template <int J, bool XMX>
+template <int J, bool XMX, int NS = 5>
 __global__ void __launch_bounds__(32, BATHGPU_V3_WARPS(J)) fs3_forward_parser_kernel_v3(FsParserArgs a)
 {
   constexpr int VEC = VecOf<J>::V;
@@ -181,8 +181,8 @@ __global__ void __launch_bounds__(32, BATHGPU_V3_WARPS(J)) fs3_forward_parser_ke
         const uint32_t c1 = __shfl_sync(0xffffffffu, cwl, qq * 4 + 1);
         const uint32_t c2 = __shfl_sync(0xffffffffu, cwl, qq * 4 + 2);
         const uint32_t c3 = __shfl_sync(0xffffffffu, cwl, qq * 4 + 3);
-        fwd_row_pair<J, VEC, 0, XMX>(i, lane, S, K, emis_lane, rowbytes, c0, c1, ploop, pmove, a.tEL, a.tEM, totscale, xrow); i += 2;
-        fwd_row_pair<J, VEC, 2, XMX>(i, lane, S, K, emis_lane, rowbytes, c2, c3, ploop, pmove, a.tEL, a.tEM, totscale, xrow); i += 2;
+        fwd_row_pair<J, VEC, 0, XMX, NS>(i, lane, S, K, emis_lane, rowbytes, c0, c1, ploop, pmove, a.tEL, a.tEM, totscale, xrow); i += 2;
+        fwd_row_pair<J, VEC, 2, XMX, NS>(i, lane, S, K, emis_lane, rowbytes, c2, c3, ploop, pmove, a.tEL, a.tEM, totscale, xrow); i += 2;
       }
     }
 

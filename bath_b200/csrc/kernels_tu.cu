@@ -53,7 +53,11 @@ template <class K> static int grid_for(K kernel, int threads, size_t smem, int n
 #if BATHGPU_FAMILY == FAM_FWD
 template <int J, bool XMX> static cudaError_t run_fwd(int version, const FsParserArgs &a, int sms, cudaStream_t s)
 {
-  if (version >= 3) fs3_forward_parser_kernel_v3<J, XMX><<<grid_for(fs3_forward_parser_kernel_v3<J, XMX>, 32, 0, a.nwin, sms), 32, 0, s>>>(a);
+  if (version >= 3) {
+    if (a.scan_steps <= 2)      fs3_forward_parser_kernel_v3<J, XMX, 2><<<grid_for(fs3_forward_parser_kernel_v3<J, XMX, 2>, 32, 0, a.nwin, sms), 32, 0, s>>>(a);
+    else if (a.scan_steps == 3) fs3_forward_parser_kernel_v3<J, XMX, 3><<<grid_for(fs3_forward_parser_kernel_v3<J, XMX, 3>, 32, 0, a.nwin, sms), 32, 0, s>>>(a);
+    else                        fs3_forward_parser_kernel_v3<J, XMX, 5><<<grid_for(fs3_forward_parser_kernel_v3<J, XMX, 5>, 32, 0, a.nwin, sms), 32, 0, s>>>(a);
+  }
   else fs3_forward_parser_kernel<J, XMX><<<grid_for(fs3_forward_parser_kernel<J, XMX>, FwdTune<J>::kThreads, 0, a.nwin, sms), FwdTune<J>::kThreads, 0, s>>>(a);
   return cudaGetLastError();
 }
@@ -69,7 +73,8 @@ bool CAT(launch_fs3_forward_, SETNAME)(int J, bool xmx, int version, const FsPar
 void CAT(preload_fwd_, SETNAME)(int J)
 {
   switch (J) {
-#define X(J_) case J_: touch(fs3_forward_parser_kernel_v3<J_, false>); touch(fs3_forward_parser_kernel_v3<J_, true>); break;
+#define X(J_) case J_: touch(fs3_forward_parser_kernel_v3<J_, false, 2>); touch(fs3_forward_parser_kernel_v3<J_, true, 2>); touch(fs3_forward_parser_kernel_v3<J_, false, 3>); \
+                       touch(fs3_forward_parser_kernel_v3<J_, true, 3>); touch(fs3_forward_parser_kernel_v3<J_, false, 5>); touch(fs3_forward_parser_kernel_v3<J_, true, 5>); break;
   JLIST(X)
 #undef X
   default: break;

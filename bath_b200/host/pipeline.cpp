@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <limits>
 #include <string>
 #include <thread>
@@ -213,7 +214,11 @@ int fail(bathhost_search *s, int code, const std::string &msg) { s->err = msg; r
 // static partition of [0,n) over the host cores
 template <class F> void parallel_chunks(size_t n, size_t min_chunk, F &&fn)
 {
-  const size_t hw = std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), 32));
+  static const size_t hw = [] {        // BATHHOST_THREADS: host threads of THIS process (one process per GPU shares the host's cores)
+    const char *e = getenv("BATHHOST_THREADS");
+    const long v = e ? atol(e) : 0;
+    return (size_t) std::max<long>(1, v > 0 ? std::min<long>(v, 64) : std::min<long>((long) std::thread::hardware_concurrency(), 32));
+  }();
   const size_t nthr = std::max<size_t>(1, std::min(hw, n / std::max<size_t>(1, min_chunk)));
   if (nthr <= 1) { fn((size_t) 0, n); return; }
   std::vector<std::thread> pool;
