@@ -19,7 +19,7 @@ EXPORTS = [
     "bathgpu_load_filter_profile", "bathgpu_upload_orfs", "bathgpu_msv_orfs", "bathgpu_ssv_windows", "bathgpu_vit_orfs",
     "bathgpu_fwd_orfs", "bathgpu_fs_fwd_bck_xrows", "bathgpu_select_slot",
     "bathgpu_orf_fwd_bck_xrows", "bathgpu_orf_domains", "bathgpu_orf_fetch_domain_matrices",
-    "bathgpu_orfs_msv_screen", "bathgpu_orfs_fetch",
+    "bathgpu_orfs_msv_screen", "bathgpu_orfs_fetch", "bathgpu_revcomp_slot",
 ]
 
 
@@ -126,6 +126,8 @@ def load():
                                           C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.bathgpu_orfs_fetch.restype = C.c_int
     L.bathgpu_orfs_fetch.argtypes = [vp, vp, C.POINTER(C.c_uint8)]
+    L.bathgpu_revcomp_slot.restype = C.c_int
+    L.bathgpu_revcomp_slot.argtypes = [vp, C.c_int, C.c_int]
     L.bathgpu_select_slot.restype = C.c_int
     L.bathgpu_select_slot.argtypes = [vp, C.c_int]
     L.bathgpu_host_alloc.restype = vp
@@ -350,6 +352,9 @@ class Context:
         self._check(self.lib.bathgpu_fs_fwd_bck_xrows(self.h, wins.ctypes.data, n, _f(xf), _f(fx), _f(bx), _f(fsc), _f(bsc), _i(st)))
         off = np.concatenate([[0], np.cumsum(Ls + 1)])
         return [fx[off[w]: off[w + 1]] for w in range(n)], [bx[off[w]: off[w + 1]] for w in range(n)], fsc, bsc, st
+
+    def revcomp_slot(self, src, dst):
+        self._check(self.lib.bathgpu_revcomp_slot(self.h, int(src), int(dst)))
 
     def orfs_msv_screen(self, blocks, complement, gcode, min_len, tjb_of, null_of, min_bits):
         """bathgpu_orfs_msv_screen + bathgpu_orfs_fetch: (ORFs found per block, survivors, their residues)"""

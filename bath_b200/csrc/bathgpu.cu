@@ -469,6 +469,37 @@ extern "C" int bathgpu_upload_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_
   return BATHGPU_OK;
 }
 
+// dst[1 + p] = complement of src[n - p] (Easel's DNA alphabet: A C G T - R Y M K S W H B V D N * ~)
+__global__ void revcomp_kernel(const uint8_t *__restrict__ src, long long n, uint8_t *__restrict__ dst)
+{
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const uint8_t comp[18] = { 3, 2, 1, 0, 4, 6, 5, 8, 7, 9, 10, 14, 13, 12, 11, 15, 16, 17 };
+  const uint8_t c = src[n - p];
+  dst[1 + p] = (c < 18) ? comp[c] : c;
+  if (p == 0) { dst[0] = 255; dst[n + 1] = 255; }
+}
+
+// The reverse complement of the sequence resident in slot src becomes the resident sequence of slot dst, without a second
+// trip over the host link (bathsearch reverse-complements each block on the host, src/bathsearch.c:1087-1096).
+extern "C" int bathgpu_revcomp_slot(bathgpu_ctx *ctx, int src, int dst)
+{
+  if (!ctx || src < 0 || src > 1 || dst < 0 || dst > 1 || src == dst) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_revcomp_slot");
+  TargetSlot &A = ctx->slot[src], &B = ctx->slot[dst];
+  if (A.block_n == 0) return fail(ctx, BATHGPU_EINVAL, "no block uploaded in slot %d", src);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const long long n = A.block_n;
+  const long long nwords = (n + 8 + 7) / 8 + 24;
+  if (B.dna_bytes.reserve((size_t)n + 2) != BATHGPU_OK || B.dna4.reserve((size_t)nwords * 4) != BATHGPU_OK)
+    return fail(ctx, BATHGPU_EMEM, "device allocation failed for a %lld-nt block", n);
+  revcomp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(A.dna_bytes.as<uint8_t>(), n, B.dna_bytes.as<uint8_t>());
+  pack_dna4_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(B.dna_bytes.as<uint8_t>(), n, B.dna4.as<uint32_t>(), nwords);
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  B.block_n = n; B.nres = 0;
+  return BATHGPU_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Forward parser stage
 static int fwd_version()      // BATHGPU_FWD=1|3 picks a kernel generation for A/B runs (1: one row per block of code; default 3: the row-pair schedule)

@@ -394,10 +394,25 @@ struct BlockInfo {
 
 struct Strand {
   bool complement = false;
-  struct Seq {                              // the whole sequence in this orientation, 1..n with sentinels: the caller's buffer (top) or an owned copy
-    const uint8_t *p = nullptr; std::unique_ptr<uint8_t[]> own;
-    const uint8_t *data() const { return p; }
-  } dsq;
+  const uint8_t *top = nullptr;             // the caller's sequence (top-strand orientation), 1..n with sentinels
+  long long n_total = 0;
+  // q with q[1..len] = nucleotides g+1 .. g+len of THIS strand's orientation (8 more on either side for look-backs): the caller's
+  // buffer itself on the top strand; on the bottom strand a reverse-complemented copy of the stretch -- the bottom strand as a
+  // whole only ever exists on the device (bathgpu_revcomp_slot)
+  const uint8_t *oriented(long long g, int len, std::vector<uint8_t> &buf) const
+  {
+    if (!complement) return top + g;
+    static const uint8_t comp[18] = { 3, 2, 1, 0, 4, 6, 5, 8, 7, 9, 10, 14, 13, 12, 11, 15, 16, 17 };
+    const int pad = 8;
+    buf.resize((size_t) len + 2 * pad + 2);
+    for (int p = -pad + 1; p <= len + pad; ++p) {
+      const long long P = g + p;
+      uint8_t c = 255;
+      if (P >= 1 && P <= n_total) { const uint8_t o = top[n_total - P + 1]; c = (o < 18) ? comp[o] : o; }
+      buf[(size_t) (p + pad)] = c;
+    }
+    return buf.data() + pad;
+  }
   std::vector<Orf> orfs;                    // of all blocks, block-local coordinates
   std::vector<int> orf_blk;                 // block of each ORF
   std::vector<int> orf_begin;               // [nblocks+1] range of each block's ORFs
@@ -443,7 +458,8 @@ int filter_strand(bathhost_search *s, Strand &S, const std::vector<BlockInfo> &b
   // (src/bathsearch.c:385-392, src/p7_pipeline.c:1632-1652).  What comes back are the ORFs that can still pass F1,
   // with their block-local rank in the reference's ORF order (the window bookkeeping keys on it) and their residues.
   BE_TRY(s, s->be.select_slot(s->be.ctx, slot), "bathgpu_select_slot");
-  BE_TRY(s, s->be.upload_block(s->be.ctx, S.dsq.data(), n_total), "bathgpu_upload_block");
+  if (!S.complement) BE_TRY(s, s->be.upload_block(s->be.ctx, S.top, n_total), "bathgpu_upload_block");
+  else               BE_TRY(s, s->be.revcomp_slot(s->be.ctx, 0, 1), "bathgpu_revcomp_slot");      // slot 0 holds the top strand
   tm.lap(s->st.us_upload);
   const size_t nblk = blocks.size();
   S.orf_begin.assign(nblk + 1, 0);
@@ -759,23 +775,17 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
   const size_t nb = blocks.size();
 
   Strand strands[2];
-  StageTimer tm0;
   std::vector<int> active;
   if (opt.top)    active.push_back(0);
   if (opt.bottom) active.push_back(1);
   for (int sidx : active) {
     Strand &S = strands[sidx];
     S.complement = (sidx == 1);
-    if (!S.complement) S.dsq.p = dsq;                       // searched in place
-    else {
-      static const uint8_t comp[18] = { 3, 2, 1, 0, 4, 6, 5, 8, 7, 9, 10, 14, 13, 12, 11, 15, 16, 17 };
-      S.dsq.own.reset(new uint8_t[(size_t) n + 2]);
-      uint8_t *out = S.dsq.own.get();
-      out[0] = out[(size_t) n + 1] = 255;
-      parallel_chunks((size_t) n, 1 << 20, [&](size_t a, size_t b) {
-        for (size_t p = a; p < b; ++p) { const uint8_t c = dsq[(size_t) n - p]; out[1 + p] = (c < 18) ? comp[c] : c; }   // oriented p+1 <- original n-p
-      });
-      S.dsq.p = out;
+    StageTimer tm0;
+    S.top = dsq; S.n_total = n;
+    if (S.complement && !opt.top) {                         // bottom strand only: the device still needs the top strand to complement
+      BE_TRY(s, s->be.select_slot(s->be.ctx, 0), "bathgpu_select_slot");
+      BE_TRY(s, s->be.upload_block(s->be.ctx, dsq, n), "bathgpu_upload_block");
     }
     tm0.lap(s->st.us_orfs);
     int st = filter_strand(s, S, blocks, n, sidx);
@@ -836,11 +846,12 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
     parallel_chunks((size_t) nw, 1, [&](size_t wa, size_t wb) {
       Background lbg = bg;
       float lcompo[kK];
+      std::vector<uint8_t> wbuf;
       for (size_t w = wa; w < wb; ++w) {
         const int b = S.dwin_blk[w];
         const BlockInfo &blk = blocks[b];
         const DnaWin &dw = S.dwin[w];
-        const uint8_t *wdsq = S.dsq.data() + S.goff(blk, n) + dw.n - 1;        // window position p is wdsq[p]
+        const uint8_t *wdsq = S.oriented(S.goff(blk, n) + dw.n - 1, dw.length, wbuf);        // window position p is wdsq[p]
         int orf_cnt = 0, k_min = M, k_max = 0;
         float tot_orfsc = kNegInfF;
         double P_min = std::numeric_limits<double>::infinity();
@@ -1062,6 +1073,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
 
   // ---- scoring and hit records, in the reference's order
   {
+    std::vector<uint8_t> wbuf;
     size_t epos[2] = { 0, 0 };
     for (size_t b = 0; b < nb; ++b)
       for (int sidx : active) {
@@ -1072,7 +1084,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
           const size_t e = epos[sidx];
           const BlockInfo &binfo = blocks[b];
           const DnaWin &dw = S.dwin[S.envs[e].win];
-          const uint8_t *wdsq = S.dsq.data() + S.goff(binfo, n) + dw.n - 1;
+          const uint8_t *wdsq = S.oriented(S.goff(binfo, n) + dw.n - 1, dw.length, wbuf);
           const int Lw = dw.length;
           const long long nres_now = binfo.nres_at[sidx];
           struct { bool complement; long long start; const char *name; long long sq_len; } blk = { S.complement, S.start_of(binfo), name, (long long) n };
@@ -1284,6 +1296,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
     BE_TRY(s, s->be.orf_domains(s->be.ctx, ge.data(), (int) ge.size(), xfEu, res.data(), traces.data(), max_steps), "bathgpu_orf_domains");
     s->st.n_envelopes += (int64_t) ge.size();
 
+    std::vector<uint8_t> wbuf;
     for (size_t e = 0; e < envs.size(); ++e) {
       const bathgpu_domain_result &r = res[e];
       if (r.status != 0 || r.trace_len == 0) continue;       // eslFAIL (:1252)
@@ -1293,7 +1306,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
       const BlockInfo &binfo = blocks[b];
       // windowsq: the DNA window (--fs) or the ORF's own nucleotides (default pipeline); block-local start
       const long long win_n = (it.w >= 0) ? S.dwin[it.w].n : o.start;
-      const uint8_t *wdsq = S.dsq.data() + S.goff(binfo, n) + win_n - 1;
+      const uint8_t *wdsq = S.oriented(S.goff(binfo, n) + win_n - 1, (it.w >= 0) ? S.dwin[it.w].length : (o.end - o.start + 1), wbuf);
       const uint8_t *res_o = S.residues.data() + o.offset - 1;           // ORF residue p is res_o[p]
       const int i = envs[e].i, j = envs[e].j;
       Domain dom;

@@ -166,6 +166,10 @@ int bathgpu_select_slot(bathgpu_ctx *ctx, int slot);
 /* dsq: ESL_DSQ codes, dsq[1..n] valid (dsq[0], dsq[n+1] sentinels).  Packed to 4 bits/nt on device. */
 int bathgpu_upload_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_t n);
 
+/* The reverse complement of slot src's resident sequence becomes slot dst's resident sequence (the bottom strand of a target whose
+ * top strand was uploaded: bathsearch reverse-complements on the host, src/bathsearch.c:1087-1096, and would upload it again). */
+int bathgpu_revcomp_slot(bathgpu_ctx *ctx, int src, int dst);
+
 /* ---- a9: frameshift Forward parser (3 codon lengths) over windows ------- */
 /* xfE = {E->MOVE, E->LOOP} odds (om_fs3->xf[p7O_E]).  Outputs: fwdsc[n] nats, status[n]. */
 int bathgpu_fs_fwd_windows(bathgpu_ctx *ctx, const bathgpu_window *wins, int n, const float xfE[2],

@@ -120,6 +120,7 @@ typedef struct {
                          const uint8_t *tjb_of, const float *null_of, int max_len, double min_bits,
                          int64_t *norfs_per_block, int64_t *nhits, int64_t *nres);
   int (*orfs_fetch)(void *ctx, void *hits, uint8_t *residues);
+  int (*revcomp_slot)(void *ctx, int src, int dst);
 } bathhost_backend;
 
 /* 0 / unset fields take bathsearch's defaults (src/p7_pipeline.c:145-214; src/bathsearch.c:94) */

@@ -130,6 +130,19 @@ int bo_backend_upload_block(void *ctx, const uint8_t *dsq, int64_t n)
   return BO_OK;
 }
 
+int bo_backend_revcomp_slot(void *ctx, int src, int dst)
+{
+  bo_backend *b = ctx;
+  int64_t n = b->n[src];
+  if (src == dst || src < 0 || src > 1 || dst < 0 || dst > 1 || !b->dsq[src]) return BO_EINVAL;
+  free(b->dsq[dst]);
+  b->dsq[dst] = malloc((size_t) n + 2);
+  memcpy(b->dsq[dst], b->dsq[src], (size_t) n + 2);
+  bo_dna_revcomp(b->dsq[dst], n);
+  b->n[dst] = n;
+  return BO_OK;
+}
+
 int bo_backend_upload_orfs(void *ctx, const uint8_t *residues, int64_t n)
 {
   bo_backend *b = ctx;

@@ -143,3 +143,27 @@ def test_slots_hold_two_targets(oracle, gpu_ctx):
             _, osc, _ = oracle_fwd(po, model, dsq, int(w["start"][t]), int(w["L"][t]))
             assert abs(sc[t] - osc) <= 1e-3
     assert not np.allclose(sa, sb)
+
+
+def test_revcomp_slot_is_the_bottom_strand(oracle, gpu_ctx):
+    """bathgpu_revcomp_slot: windows scored on the device-made reverse complement equal the oracle's on the host-made one
+    (degenerate codes included: R<->Y, M<->K, ... as esl_sq_ReverseComplement maps them)"""
+    po = oracle
+    from bath_b200 import capi
+    model = po.Model(common.golden("AMP_N.bhmm"))
+    rng = np.random.default_rng(9)
+    top = common.random_dna(rng, 5000)
+    top[100:110] = [5, 6, 7, 8, 9, 10, 11, 12, 13, 14]
+    bottom = po.revcomp_dsq(top)
+    gpu_ctx.load_fs_profile(3, model.rfv(3), model.tfv(3))
+    gpu_ctx.select_slot(0); gpu_ctx.upload_block(top)
+    gpu_ctx.revcomp_slot(0, 1)
+    gpu_ctx.select_slot(1)
+    w = capi.Context.make_windows([1, 1200, 4401, 4880], [900, 900, 600, 121])
+    sc, st = gpu_ctx.fs_fwd_windows(w)
+    gpu_ctx.select_slot(0)
+    for t in range(len(w)):
+        ost, osc, _ = oracle_fwd(po, model, bottom, int(w["start"][t]), int(w["L"][t]))
+        assert st[t] == ost and abs(sc[t] - osc) <= 1e-3
+    with pytest.raises(capi.BathGpuError):
+        gpu_ctx.revcomp_slot(1, 1)
