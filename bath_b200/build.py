@@ -63,15 +63,18 @@ def _units():
     return units
 
 
-def build_library(force=False, verbose=False, jobs=None):
+def build_library(force=False, verbose=False, jobs=None, variant=None, extra_flags=()):
+    """variant / extra_flags: an A/B build while tuning (libbathgpu_<variant>.so, its own object directory); load it with BATHGPU_LIB."""
     srcs = _sources()
     newest = max(os.path.getmtime(s) for s in srcs + [os.path.abspath(__file__)])
+    _SO = os.path.join(_HERE, f"libbathgpu_{variant}.so") if variant else globals()["_SO"]
+    _OBJ = globals()["_OBJ"] + (f"_{variant}" if variant else "")
     if not force and os.path.exists(_SO) and newest <= os.path.getmtime(_SO):
         return _SO
     from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(_OBJ, exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else []) + list(extra_flags)
 
     def compile_one(unit):
         name, src, defs = unit
@@ -81,10 +84,17 @@ def build_library(force=False, verbose=False, jobs=None):
         return obj
 
     units = _units()
+    if variant and os.environ.get("BATHGPU_VARIANT_UNITS"):      # rebuild only these units, take the rest from the main build
+        only = set(os.environ["BATHGPU_VARIANT_UNITS"].split(","))
+        main_obj = globals()["_OBJ"]
+        keep = [os.path.join(main_obj, u[0] + ".o") for u in units if u[0] not in only]
+        units = [u for u in units if u[0] in only]
+    else:
+        keep = []
     # longest first: the node-count sets with the most (or the largest) instantiations
     units.sort(key=lambda u: (u[0].endswith(("_f", "_e", "_c", "_b")), u[0]), reverse=True)
     with ThreadPoolExecutor(max_workers=jobs or os.cpu_count() or 4) as pool:
-        objs = list(pool.map(compile_one, units))
+        objs = list(pool.map(compile_one, units)) + keep
     subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", _SO] + objs)
     return _SO
 
@@ -92,4 +102,6 @@ def build_library(force=False, verbose=False, jobs=None):
 if __name__ == "__main__":
     import sys
     print(build_host_library(force="--force" in sys.argv))
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    var = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")), None)
+    extra = [a for a in sys.argv[1:] if a.startswith("-D")]
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=var, extra_flags=extra))

@@ -8,6 +8,8 @@ python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/benc
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>&1; cat gpurun_out/bench_ref.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --search-mbp 2 > gpurun_out/ncu_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:fs3_forward -s 3 -c 1 -f -o gpurun_out/prof_fwd \
+ncu --set full --clock-control none --import-source on -k regex:fs3_forward -s 3 -c 1 -f -o /tmp/prof_fwd \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --mbp 20 --search-mbp 0 > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
+python scripts/ncu_summary.py /tmp/prof_fwd.ncu-rep > gpurun_out/fwd_ncu_full.txt
+bash scripts/ncu_all.sh
