@@ -81,7 +81,7 @@ struct bathgpu_ctx {
   bool          flt_loaded = false;
   bathgpu_filter_params flt{};
   int           flt_W = 0, flt_P = 0;
-  DevBuf        f_rbv, f_rwv, f_twv, f_ddsum, orfs, fsc, fst, fwins, fnw;
+  DevBuf        f_rbv, f_rwv, f_twv, f_ddsum, f_nrb, orfs, fsc, fst, fwins, fnw;
   DevBuf        o_tiles, o_cnt, o_base, o_blocks, o_first, o_tjb, o_null, o_meta, o_hits, o_counters;
   long long     o_nhits = 0, o_nres = 0;
   // domain stage workspace (last chunk stays resident for bathgpu_fs_fetch_domain_matrices)
@@ -941,11 +941,12 @@ extern "C" int bathgpu_load_filter_profile(bathgpu_ctx *ctx, const bathgpu_filte
   ctx->flt_W = W; ctx->flt_P = P;
   const int nb = 128 * W, nw = 64 * P;                 // nodes per padded row
   std::vector<uint8_t> hb((size_t)29 * nb, 255);
-  std::vector<int16_t> hw((size_t)29 * nw, -32768), ht((size_t)8 * nw, -32768);
+  std::vector<int16_t> hw((size_t)29 * nw, -32768), ht((size_t)8 * nw, -32768), hn((size_t)29 * nw, -255);
   for (int x = 0; x < 29; ++x)
     for (int k = 1; k <= M; ++k) {
       hb[(size_t)x * nb + (k - 1)] = rbv[(size_t)x * ld + k];
       hw[(size_t)x * nw + (k - 1)] = rwv[(size_t)x * ld + k];
+      hn[(size_t)x * nw + (k - 1)] = (int16_t)(-(int)rbv[(size_t)x * ld + k]);
     }
   for (int t = 0; t < 8; ++t)
     for (int k = 1; k <= M; ++k) {
@@ -978,15 +979,16 @@ extern "C" int bathgpu_load_filter_profile(bathgpu_ctx *ctx, const bathgpu_filte
     }
   }
   if (ctx->f_rbv.reserve(hb.size()) != BATHGPU_OK || ctx->f_rwv.reserve(hw.size() * 2) != BATHGPU_OK ||
-      ctx->f_twv.reserve(ht.size() * 2) != BATHGPU_OK || ctx->f_ddsum.reserve(dds.size() * 4) != BATHGPU_OK)
+      ctx->f_twv.reserve(ht.size() * 2) != BATHGPU_OK || ctx->f_ddsum.reserve(dds.size() * 4) != BATHGPU_OK || ctx->f_nrb.reserve(hn.size() * 2) != BATHGPU_OK)
     return fail(ctx, BATHGPU_EMEM, "device allocation failed");
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->f_rbv.p, hb.data(), hb.size(), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->f_rwv.p, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->f_nrb.p, hn.data(), hn.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->f_twv.p, ht.data(), ht.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->f_ddsum.p, dds.data(), dds.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->flt_loaded = true;
-  preload_msv_filter(W); preload_vit_filter_lo(P); preload_vit_filter_hi(P);
+  preload_msv_filter(W, P); preload_vit_filter_lo(P); preload_vit_filter_hi(P);
   return BATHGPU_OK;
 }
 
@@ -1026,7 +1028,7 @@ static FilterArgs filter_args(bathgpu_ctx *ctx, int n, int max_wins)
   FilterArgs a{};
   const bathgpu_filter_params &p = ctx->flt;
   a.residues = ctx->S().residues.as<uint8_t>(); a.res_stride = 1; a.orfs = ctx->orfs.as<OrfDesc>(); a.norf = n; a.M = p.M;
-  a.rbv = ctx->f_rbv.as<uint32_t>(); a.rbv_bytes = ctx->f_rbv.as<uint8_t>(); a.rowwords_b = 32 * ctx->flt_W;
+  a.rbv = ctx->f_rbv.as<uint32_t>(); a.nrb = ctx->f_nrb.as<uint32_t>(); a.rbv_bytes = ctx->f_rbv.as<uint8_t>(); a.rowwords_b = 32 * ctx->flt_W;
   a.tbm_b = p.tbm_b; a.tec_b = p.tec_b; a.base_b = p.base_b; a.bias_b = p.bias_b; a.scale_b = p.scale_b;
   a.rwv = ctx->f_rwv.as<uint32_t>(); a.twv = ctx->f_twv.as<uint32_t>(); a.ddsum = ctx->f_ddsum.as<int>(); a.rowwords_w = 32 * ctx->flt_P;
   a.base_w = p.base_w; a.ddbound_w = p.ddbound_w; a.xw_E_move = p.xw_E_move; a.xw_E_loop = p.xw_E_loop; a.scale_w = p.scale_w;
@@ -1039,7 +1041,7 @@ static FilterArgs filter_args(bathgpu_ctx *ctx, int n, int max_wins)
 static cudaError_t dispatch_msv(int mode, int W, const FilterArgs &a, int sms, cudaStream_t s)
 {
   cudaError_t e = cudaErrorInvalidValue;
-  return launch_msv_filter(W, mode, a, sms, s, &e) ? e : cudaErrorInvalidValue;
+  return launch_msv_filter(W, a.rowwords_w / 32, mode, a, sms, s, &e) ? e : cudaErrorInvalidValue;
 }
 
 static cudaError_t dispatch_vit(int P, const FilterArgs &a, int sms, cudaStream_t s)

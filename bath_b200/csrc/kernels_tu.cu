@@ -194,20 +194,45 @@ template <int W, int MODE> static cudaError_t run_msv(const FilterArgs &a, int s
   msv_filter_kernel<W, MODE><<<grid_for(msv_filter_kernel<W, MODE>, 128, smem, (a.norf + 3) / 4, sms), 128, smem, s>>>(a);
   return cudaGetLastError();
 }
-bool launch_msv_filter(int W, int mode, const FilterArgs &a, int sms, cudaStream_t s, cudaError_t *err)
+template <int P> static cudaError_t run_msv16(const FilterArgs &a, int sms, cudaStream_t s)
 {
+  const size_t smem = (size_t)29 * 32 * P * 4;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(msv16_filter_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  msv16_filter_kernel<P><<<grid_for(msv16_filter_kernel<P>, 128, smem, (a.norf + 3) / 4, sms), 128, smem, s>>>(a);
+  return cudaGetLastError();
+}
+// mode 0: MSV scores (16-bit lanes, P words per lane); mode 1: SSV windows (byte lanes, W words per lane)
+bool launch_msv_filter(int W, int P, int mode, const FilterArgs &a, int sms, cudaStream_t s, cudaError_t *err)
+{
+  if (mode == 0) {
+    switch (P) {
+#define X(P_) case P_: *err = run_msv16<P_>(a, sms, s); return true;
+    X(1) X(2) X(3) X(4) X(5) X(6) X(8) X(12) X(16)
+#undef X
+    default: return false;
+    }
+  }
   switch (W) {
-#define X(W_) case W_: *err = mode ? run_msv<W_, 1>(a, sms, s) : run_msv<W_, 0>(a, sms, s); return true;
+#define X(W_) case W_: *err = run_msv<W_, 1>(a, sms, s); return true;
   X(1) X(2) X(3) X(4) X(6) X(8)
 #undef X
   default: return false;
   }
 }
-void preload_msv_filter(int W)
+void preload_msv_filter(int W, int P)
 {
   switch (W) {
-#define X(W_) case W_: touch(msv_filter_kernel<W_, 0>); touch(msv_filter_kernel<W_, 1>); break;
+#define X(W_) case W_: touch(msv_filter_kernel<W_, 1>); break;
   X(1) X(2) X(3) X(4) X(6) X(8)
+#undef X
+  default: break;
+  }
+  switch (P) {
+#define X(P_) case P_: touch(msv16_filter_kernel<P_>); break;
+  X(1) X(2) X(3) X(4) X(5) X(6) X(8) X(12) X(16)
 #undef X
   default: break;
   }

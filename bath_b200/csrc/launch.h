@@ -30,11 +30,11 @@ BATHGPU_FOR_EACH_SET(BATHGPU_DECLARE_SET)
 #undef BATHGPU_DECLARE_SET
 
 // integer filters: W words (4 nodes each) per lane for MSV/SSV, P words (2 nodes each) per lane for Viterbi
-bool launch_msv_filter(int W, int mode, const FilterArgs &a, int sms, cudaStream_t s, cudaError_t *err);
+bool launch_msv_filter(int W, int P, int mode, const FilterArgs &a, int sms, cudaStream_t s, cudaError_t *err);
 bool launch_vit_filter_lo(int P, const FilterArgs &a, int sms, cudaStream_t s, cudaError_t *err);      // P = 1..6
 bool launch_vit_filter_hi(int P, const FilterArgs &a, int sms, cudaStream_t s, cudaError_t *err);      // P = 8, 12, 16
 // Touch the kernels a profile of this size will use, so that the driver loads their code when the profile is loaded and not
 // inside the first stage call (CUDA loads kernels lazily).
-void preload_msv_filter(int W); void preload_vit_filter_lo(int P); void preload_vit_filter_hi(int P);
+void preload_msv_filter(int W, int P); void preload_vit_filter_lo(int P); void preload_vit_filter_hi(int P);
 
 }  // namespace bathgpu

@@ -46,6 +46,7 @@ struct FilterArgs {
   int             M;
   // bytes
   const uint32_t *rbv;       // [29][32*W] words, node k at byte k-1 of a row; pad bytes 255
+  const uint32_t *nrb;       // [29][32*P] words, -cost of node k at half k-1 (msv16_filter_kernel); pad -255
   const uint8_t  *rbv_bytes; // same table, byte addressed (diagonal walks)
   int             rowwords_b;
   int             tbm_b, tec_b, base_b, bias_b;
@@ -216,6 +217,114 @@ __global__ void __launch_bounds__(128) msv_filter_kernel(FilterArgs a)
         }
         a.sc[o] = sc; a.status[o] = st;
       }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MSV scores on 16-bit lanes.  The byte-SIMD intrinsics above are emulated on this architecture (about seven integer
+// instructions each), while the 16-bit min/max/add-then-clamp family (VIMNMX.S16x2, VIADDMNMX.S16x2, VIMNMX3) is native:
+// carrying each uint8 cell in a 16-bit lane and clamping explicitly -- min(v + bias, 255), max(v - cost, 0) -- gives the
+// same values as the saturating byte operations (msvfilter.c:145-148) in one instruction per step and two nodes per
+// register.  P = words per lane (2 P nodes), the Viterbi filter's layout; costs are stored negated.
+// One row of the recurrence on 16-bit lanes: returns the row's cells in m[] and folds them into rowmax.
+template <int P>
+__device__ __forceinline__ void msv16_row(const uint32_t *__restrict__ s_nrb_lane, unsigned x, int rowwords, int lane, uint32_t (&m)[P],
+                                          unsigned xBv, unsigned biasv, unsigned &rowmax)
+{
+  uint32_t rb[P];
+  lds_words<P>(s_nrb_lane + x * rowwords, rb);
+  unsigned carry = __shfl_up_sync(0xffffffffu, m[P - 1], 1);
+  if (lane == 0) carry = 0;                               // zeros shift in (:139-143)
+#pragma unroll
+  for (int w = P - 1; w >= 0; --w) {
+    const unsigned lo = (w == 0) ? carry : m[w - 1];
+    unsigned sv = __funnelshift_l(lo, m[w], 16);          // previous row, node k-1
+    sv = __vmaxs2(sv, xBv);
+    sv = __viaddmin_s16x2(sv, biasv, 0x00ff00ffu);        // adds_epu8(sv, bias)
+    sv = __viaddmax_s16x2(sv, rb[w], 0u);                 // subs_epu8(sv, cost)
+    m[w] = sv;
+    rowmax = __vmaxs2(rowmax, sv);
+  }
+}
+
+// Rows are taken 32 at a time (one residue per lane).  While the J state is out of reach -- E never exceeds base + tEC, so B keeps
+// its initial value -- the per-row maximum is not needed row by row: a chunk runs without any reduction and its overall maximum is
+// reduced once (this is the reference's SSV shortcut, ssvfilter.c:14-210, taken per chunk).  A chunk whose maximum shows that J
+// became reachable or that a cell overflowed is re-run from its saved first row with the exact per-row recurrence (msvfilter.c:145-201).
+template <int P>
+__global__ void __launch_bounds__(128) msv16_filter_kernel(FilterArgs a)
+{
+  extern __shared__ uint32_t smem[];
+  uint32_t *s_nrb = smem;                                  // [29][32*P] words: -cost of node k at half k-1
+  const int rowwords = 32 * P;
+  for (int t = threadIdx.x; t < 29 * rowwords; t += blockDim.x) s_nrb[t] = a.nrb[t];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
+  const unsigned biasv = (unsigned)a.bias_b * 0x00010001u;
+  const uint32_t *s_nrb_lane = s_nrb + lane * P;
+
+  for (;;) {
+    int o = 0;
+    if (lane == 0) o = atomicAdd(a.counter, 1);
+    o = __shfl_sync(full, o, 0);
+    if (o >= a.norf) break;
+    const OrfDesc od = a.orfs[o];
+    const int L = od.L;
+    if (od.flags & 2) {                                    // wholly inside the block's overlap context: not scored (p7_pipeline.c:1634-1637)
+      if (lane == 0) { a.sc[o] = -INFINITY; a.status[o] = 0; }
+      continue;
+    }
+    const int tjbm = (int)(uint8_t)((int8_t)od.tjb_b + (int8_t)a.tbm_b);      // set1_epi8 of the 8-bit sum (:120)
+    uint32_t m[P];
+#pragma unroll
+    for (int w = 0; w < P; ++w) m[w] = 0;
+    int xJ = 0;
+    int xB = max(a.base_b - tjbm, 0);
+    unsigned xBv = (unsigned)xB * 0x00010001u;
+    int st = 0;
+    bool exact = false;                                    // J reachable: B moves with it, every row needs its own maximum
+
+    for (int i0 = 1; i0 <= L && !st; i0 += 32) {
+      const int nrow = min(32, L - i0 + 1);
+      const unsigned myres = (lane < nrow) ? a.residues[od.offset + (long long)(i0 + lane - 1) * a.res_stride] : 0u;
+      if (!exact) {
+        uint32_t m0[P];
+#pragma unroll
+        for (int w = 0; w < P; ++w) m0[w] = m[w];
+        unsigned cmax = 0;
+        for (int r = 0; r < nrow; ++r)
+          msv16_row<P>(s_nrb_lane, __shfl_sync(full, myres, r), rowwords, lane, m, xBv, biasv, cmax);
+        const int xEc = (int)__reduce_max_sync(full, (int)max(cmax & 0xffffu, cmax >> 16));
+        if (xEc + a.bias_b < 255 && xEc - a.tec_b <= a.base_b) { xJ = max(xJ, max(xEc - a.tec_b, 0)); continue; }
+        exact = true;                                      // redo this chunk row by row
+#pragma unroll
+        for (int w = 0; w < P; ++w) m[w] = m0[w];
+      }
+      for (int r = 0; r < nrow; ++r) {
+        unsigned rowmax = 0;
+        msv16_row<P>(s_nrb_lane, __shfl_sync(full, myres, r), rowwords, lane, m, xBv, biasv, rowmax);
+        const int xE = (int)__reduce_max_sync(full, (int)max(rowmax & 0xffffu, rowmax >> 16));
+        if (xE + a.bias_b >= 255) { st = 16; break; }       // overflow (:155-180)
+        const int xEt = max(xE - a.tec_b, 0);
+        xJ = max(xJ, xEt);
+        xB = max(max(a.base_b, xJ) - tjbm, 0);
+        xBv = (unsigned)xB * 0x00010001u;
+      }
+    }
+    if (lane == 0) {
+      float sc;
+      if (st) sc = INFINITY;
+      else {                                                 // (:203-205), with the SSV shortcut's floor (see msv_filter_kernel)
+        const int floorJ = a.base_b - (int)od.tjb_b - a.tbm_b - a.tec_b;
+        if ((int)od.tjb_b + a.tbm_b + a.tec_b + a.bias_b < 127 && xJ <= a.base_b && floorJ >= 0) xJ = max(xJ, floorJ);
+        sc = ((float)(xJ - (int)od.tjb_b) - (float)a.base_b);
+        sc /= a.scale_b;
+        sc -= 3.0f;
+      }
+      a.sc[o] = sc; a.status[o] = st;
     }
   }
 }
