@@ -10,6 +10,7 @@
 #include <vector>
 #include <string>
 #include <algorithm>
+#include <mutex>
 
 #include "../../include/bathgpu.h"
 #include "fs_parser.cuh"
@@ -170,14 +171,52 @@ extern "C" int bathgpu_last_stage_timing(const bathgpu_ctx *ctx, float *ms, int 
   return BATHGPU_OK;
 }
 
+// Page-locking memory costs about a millisecond per megabyte, so freed buffers are kept (up to 2 GiB in all) and handed out again.
+namespace {
+struct PinnedCache {
+  std::mutex mu;
+  std::vector<std::pair<void *, size_t>> idle;      // free buffers
+  std::vector<std::pair<void *, size_t>> live;      // handed out: their sizes
+  size_t idle_bytes = 0;
+  ~PinnedCache() { for (auto &b : idle) cudaFreeHost(b.first); }
+};
+PinnedCache g_pinned;
+}
+
 extern "C" void *bathgpu_host_alloc(size_t bytes)
 {
+  if (bytes == 0) bytes = 1;
+  std::lock_guard<std::mutex> lock(g_pinned.mu);
+  int best = -1;
+  for (int i = 0; i < (int)g_pinned.idle.size(); ++i)
+    if (g_pinned.idle[i].second >= bytes && (best < 0 || g_pinned.idle[i].second < g_pinned.idle[best].second)) best = i;
+  if (best >= 0 && g_pinned.idle[best].second <= 2 * bytes + (1u << 20)) {
+    auto b = g_pinned.idle[best];
+    g_pinned.idle.erase(g_pinned.idle.begin() + best);
+    g_pinned.idle_bytes -= b.second;
+    g_pinned.live.push_back(b);
+    return b.first;
+  }
   void *p = nullptr;
   if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  g_pinned.live.push_back({ p, bytes });
   return p;
 }
 
-extern "C" void bathgpu_host_free(void *p) { if (p) cudaFreeHost(p); }
+extern "C" void bathgpu_host_free(void *p)
+{
+  if (!p) return;
+  std::lock_guard<std::mutex> lock(g_pinned.mu);
+  for (size_t i = 0; i < g_pinned.live.size(); ++i)
+    if (g_pinned.live[i].first == p) {
+      auto b = g_pinned.live[i];
+      g_pinned.live.erase(g_pinned.live.begin() + i);
+      if (g_pinned.idle_bytes + b.second <= ((size_t)2 << 30)) { g_pinned.idle.push_back(b); g_pinned.idle_bytes += b.second; }
+      else cudaFreeHost(p);
+      return;
+    }
+  cudaFreeHost(p);
+}
 
 extern "C" int bathgpu_measure_fp32_peak(bathgpu_ctx *ctx, double *tflops, double *sm_mhz_effective)
 {

@@ -188,9 +188,26 @@ struct Options {
 
 using namespace bathhost;
 
+// grow-only host buffer for results the device writes: page-locked when the backend offers it (the copies then run at link rate)
+struct HostBuf {
+  float *p = nullptr; size_t cap = 0; void (*release)(void *) = nullptr;
+  float *get(const bathhost_backend &be, size_t nfloats)
+  {
+    if (nfloats <= cap) return p;
+    if (p) { if (release) release(p); else free(p); }
+    const size_t want = nfloats + nfloats / 4 + 1024;
+    release = be.host_alloc ? be.host_free : nullptr;
+    p = (float *) (be.host_alloc ? be.host_alloc(want * sizeof(float)) : malloc(want * sizeof(float)));
+    cap = p ? want : 0;
+    return p;
+  }
+  ~HostBuf() { if (p) { if (release) release(p); else free(p); } }
+};
+
 struct bathhost_search {
   const bathhost_model *model;
   bathhost_backend      be;
+  HostBuf               xbuf[2][2];
   Options               opt;
   Background            bg;
   std::vector<float>    compo;
@@ -429,7 +446,7 @@ struct Strand {
   std::vector<int32_t> fs_st;
   std::vector<int>     fsw;                 // windows that go down the frameshift branch
   std::vector<size_t>  xoff;
-  std::vector<float>   fxr, bxr;
+  float *fxr = nullptr, *bxr = nullptr;     // X rows of the Forward / Backward parsers (page-locked buffers owned by the search)
   std::vector<int32_t> st2;
   struct Env { int win, i, j; };
   std::vector<Env> envs;
@@ -611,45 +628,56 @@ int filter_strand(bathhost_search *s, Strand &S, const std::vector<BlockInfo> &b
   // ---- Viterbi decision, local-composition bias re-check (:1669-1718); ORFs that need a plain Viterbi re-run are batched
   std::vector<int> keep;                                  // candidate indices that go on to Forward
   std::vector<int> rerun;                                 // candidates needing p7_ViterbiFilter after the local bias raised filtersc
-  float lcompo[kK];
-  for (size_t t = 0; t < cand.size(); ++t) {
-    Cand &c = cand[t];
-    const Orf &o = orfs[c.orf];
-    if (c.need_vit) {
-      const float seqsc = (c.vfsc - c.filtersc) / kLog2;
-      c.P = gumbel_surv(seqsc, ev[EV_VMU], ev[EV_VLAMBDA]);
-      if (c.P > opt.F2) { wins_of[t].clear(); continue; }
-    }
-    s->st.pos_past_vit += (int64_t) o.n * 3;
-    bool dropped = false, need_rerun = false;
-    if (opt.do_bias && !wins_of[t].empty()) {
-      int k_max = wins_of[t][0].k, k_min = k_max - wins_of[t][0].length + 1;
-      for (size_t w = 1; w < wins_of[t].size(); ++w) {
-        k_max = std::max(k_max, wins_of[t][w].k);
-        k_min = std::min(k_min, wins_of[t][w].k - wins_of[t][w].length + 1);
-      }
-      local_compo(m, bg, k_min, k_max, lcompo);
-      bg.set_filter(M, lcompo);
-      bg.set_length(o.n);
-      orf_dsq(o, buf);
-      const float local_filtersc = bg.filter_score(buf.data(), o.n);
-      if (local_filtersc > c.filtersc) {
-        c.filtersc = local_filtersc;
-        if (c.vfsc == kNegInfF) {
-          const float seqsc = (c.usc - c.filtersc) / kLog2;
-          c.P = gumbel_surv(seqsc, ev[EV_MMU], ev[EV_MLAMBDA]);
-          if (c.P > opt.F2) need_rerun = true;
-        } else {
+  {
+    // per candidate: 0 = fails the Viterbi test, 1 = dropped by the local-composition re-check, 2 = needs a plain Viterbi re-run, 3 = kept.
+    // Candidates are independent here (the null model is restored after each in the reference): all host cores, then the counters in order.
+    std::vector<uint8_t> verdict(cand.size(), 0);
+    parallel_chunks(cand.size(), 64, [&](size_t ta, size_t tb) {
+      Background lbg = bg;
+      float lcompo[kK];
+      std::vector<uint8_t> lbuf;
+      for (size_t t = ta; t < tb; ++t) {
+        Cand &c = cand[t];
+        const Orf &o = orfs[c.orf];
+        if (c.need_vit) {
           const float seqsc = (c.vfsc - c.filtersc) / kLog2;
           c.P = gumbel_surv(seqsc, ev[EV_VMU], ev[EV_VLAMBDA]);
-          if (c.P > opt.F2) dropped = true;
+          if (c.P > opt.F2) { verdict[t] = 0; continue; }
         }
+        bool dropped = false, need_rerun = false;
+        if (opt.do_bias && !wins_of[t].empty()) {
+          int k_max = wins_of[t][0].k, k_min = k_max - wins_of[t][0].length + 1;
+          for (size_t w = 1; w < wins_of[t].size(); ++w) {
+            k_max = std::max(k_max, wins_of[t][w].k);
+            k_min = std::min(k_min, wins_of[t][w].k - wins_of[t][w].length + 1);
+          }
+          local_compo(m, lbg, k_min, k_max, lcompo);
+          lbg.set_filter(M, lcompo);
+          lbg.set_length(o.n);
+          orf_dsq(o, lbuf);
+          const float local_filtersc = lbg.filter_score(lbuf.data(), o.n);
+          if (local_filtersc > c.filtersc) {
+            c.filtersc = local_filtersc;
+            if (c.vfsc == kNegInfF) {
+              const float seqsc = (c.usc - c.filtersc) / kLog2;
+              c.P = gumbel_surv(seqsc, ev[EV_MMU], ev[EV_MLAMBDA]);
+              if (c.P > opt.F2) need_rerun = true;
+            } else {
+              const float seqsc = (c.vfsc - c.filtersc) / kLog2;
+              c.P = gumbel_surv(seqsc, ev[EV_VMU], ev[EV_VLAMBDA]);
+              if (c.P > opt.F2) dropped = true;
+            }
+          }
+        }
+        verdict[t] = dropped ? 1 : need_rerun ? 2 : 3;
       }
-      bg.set_filter(M, s->compo.data());
-      bg.set_length(o.n);
+    });
+    for (size_t t = 0; t < cand.size(); ++t) {
+      if (verdict[t] == 0) { wins_of[t].clear(); continue; }
+      s->st.pos_past_vit += (int64_t) orfs[cand[t].orf].n * 3;
+      if (verdict[t] == 1) { wins_of[t].clear(); continue; }
+      if (verdict[t] == 2) rerun.push_back((int) t); else keep.push_back((int) t);
     }
-    if (dropped) { wins_of[t].clear(); continue; }
-    if (need_rerun) rerun.push_back((int) t); else keep.push_back((int) t);
   }
   if (!rerun.empty()) {
     std::vector<bathgpu_orf> d(rerun.size());
@@ -691,8 +719,12 @@ int filter_strand(bathhost_search *s, Strand &S, const std::vector<BlockInfo> &b
   return 0;
 }
 
+// positions in the accumulated hit_windows list of the entries stamped with each ORF index, in list order: the reference
+// scans the whole list for an index (and the list is never reset, so earlier blocks' entries with the same index count too)
+typedef std::vector<std::vector<int>> HitIndex;
+
 // p7_pli_BuildDNAWindows (src/p7_pipeline.c:462-572) for one block-strand, against the accumulated hit_windows list
-void build_dna_windows(bathhost_search *s, Strand &S, const BlockInfo &blk, int b, const std::vector<OrfWin> &hit_windows)
+void build_dna_windows(bathhost_search *s, Strand &S, const BlockInfo &blk, int b, const std::vector<OrfWin> &hit_windows, const HitIndex &by_id)
 {
   const ProteinProfile &q = s->model->prot;
   const Options &opt = s->opt;
@@ -703,8 +735,8 @@ void build_dna_windows(bathhost_search *s, Strand &S, const BlockInfo &blk, int 
     if (S.P_orf[gi] > opt.F4) continue;
     Orf &o = S.orfs[gi];
     int best = -1; float best_score = kNegInfF;
-    for (size_t w = 0; w < hit_windows.size(); ++w) {
-      if (hit_windows[w].id != f) continue;
+    static const std::vector<int> kNone;
+    for (int w : (f < (int) by_id.size() ? by_id[f] : kNone)) {
       if (hit_windows[w].score > best_score ||
           (hit_windows[w].score == best_score && hit_windows[w].length > (best >= 0 ? hit_windows[best].length : 0))) {
         best_score = hit_windows[w].score; best = (int) w;
@@ -799,6 +831,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
   // ---- DNA windows, block by block in the reference's order, against the ever-growing hit_windows list
   StageTimer tm;
   std::vector<OrfWin> hit_windows;
+  HitIndex by_id;
   for (int sidx : active) { strands[sidx].dwin_begin.assign(nb + 1, 0); strands[sidx].hw_count.assign(nb, 0); }
   for (size_t b = 0; b < nb; ++b)
     for (int sidx : active) {
@@ -806,9 +839,13 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
       S.dwin_begin[b] = (int) S.dwin.size();
       if (blocks[b].n >= 15 && opt.fs) {
         for (int gi = S.orf_begin[b]; gi < S.orf_begin[b + 1]; ++gi)
-          for (const OrfWin &w : S.wins_of_orf[gi]) hit_windows.push_back(w);
+          for (const OrfWin &w : S.wins_of_orf[gi]) {
+            if ((size_t) w.id >= by_id.size()) by_id.resize((size_t) w.id + 1);
+            by_id[w.id].push_back((int) hit_windows.size());
+            hit_windows.push_back(w);
+          }
         S.hw_count[b] = hit_windows.size();
-        build_dna_windows(s, S, blocks[b], (int) b, hit_windows);
+        build_dna_windows(s, S, blocks[b], (int) b, hit_windows, by_id);
       } else S.hw_count[b] = hit_windows.size();
       S.dwin_begin[b + 1] = (int) S.dwin.size();
     }
@@ -866,7 +903,11 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
           tot_orfsc = flogsum(tot_orfsc, S.fwdsc_orf[gi]);
           orf_cnt++;
           size_t h = last_h;
-          while (h < hw_n && hit_windows[h].id != i) h++;
+          if ((size_t) i < by_id.size()) {                 // first entry stamped i at or after last_h (the reference scans forward for it)
+            const std::vector<int> &ix = by_id[i];
+            auto it = std::lower_bound(ix.begin(), ix.end(), (int) h);
+            h = (it == ix.end()) ? hw_n : std::min<size_t>(hw_n, (size_t) *it);
+          } else h = hw_n;
           if (h < hw_n) {
             while (h < hw_n && hit_windows[h].id == i) {
               k_min = std::min(k_min, hit_windows[h].k - hit_windows[h].length + 1);
@@ -928,13 +969,14 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
     std::vector<bathgpu_window> gf(S.fsw.size());
     S.xoff.assign(S.fsw.size() + 1, 0);
     for (size_t z = 0; z < S.fsw.size(); ++z) { gf[z] = S.gw[S.fsw[z]]; S.xoff[z + 1] = S.xoff[z] + (size_t) gf[z].L + 1; }
-    S.fxr.resize(S.xoff.back() * 6); S.bxr.resize(S.xoff.back() * 6); S.st2.resize(S.fsw.size());
+    S.fxr = s->xbuf[sidx][0].get(s->be, S.xoff.back() * 6); S.bxr = s->xbuf[sidx][1].get(s->be, S.xoff.back() * 6); S.st2.resize(S.fsw.size());
+    if (!S.fxr || !S.bxr) return fail(s, BATHHOST_EMEM, "host allocation failed");
     std::vector<float> f2(S.fsw.size()), b2(S.fsw.size());
     BE_TRY(s, s->be.select_slot(s->be.ctx, sidx), "bathgpu_select_slot");
-    BE_TRY(s, s->be.fs_fwd_bck_xrows(s->be.ctx, gf.data(), (int) gf.size(), xfE3, S.fxr.data(), S.bxr.data(), f2.data(), b2.data(), S.st2.data()),
+    BE_TRY(s, s->be.fs_fwd_bck_xrows(s->be.ctx, gf.data(), (int) gf.size(), xfE3, S.fxr, S.bxr, f2.data(), b2.data(), S.st2.data()),
            "bathgpu_fs_fwd_bck_xrows");
   }
-  tm.lap(s->st.us_fs_fwd);
+  tm.lap(s->st.us_xrows);
 
   // ---- domain decoding and region finding on the host, in the reference's order (block, then strand, then window):
   // the length model of om_fs5 that p7_DomainDecoding_Frameshift reads is whatever the previous window's rescoring left
@@ -951,7 +993,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
       for (size_t z = za; z < zb; ++z) {
         if (S.st2[z] != 0) continue;
         const int Lw = S.dwin[S.fsw[z]].length;
-        const float *xf = &S.fxr[S.xoff[z] * 6], *xb = &S.bxr[S.xoff[z] * 6];
+        const float *xf = S.fxr + S.xoff[z] * 6, *xb = S.bxr + S.xoff[z] * 6;
         Decoded &D = dec[sidx][z];
         D.btot.assign((size_t) Lw + 1, 0.f); D.etot.assign((size_t) Lw + 1, 0.f);
         D.fb.assign(((size_t) Lw + 1) * 9, 0.f); D.ex.assign(((size_t) Lw + 1) * 9, 0.f);
@@ -980,6 +1022,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
       }
     });
   }
+  tm.lap(s->st.us_decode);
   const float rt1 = 0.25f, rt2 = 0.10f, rt3 = 0.20f;
   const int saveL = 100;                                    // gm_fs5->L: the dummy length bathsearch configures and never changes (src/bathsearch.c:797)
   {
@@ -1071,6 +1114,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
     s->st.n_envelopes += (int64_t) S.ge.size();
   }
 
+  tm.lap(s->st.us_fs_domains);
   // ---- scoring and hit records, in the reference's order
   {
     std::vector<uint8_t> wbuf;
@@ -1205,7 +1249,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
         }
       }
   }
-  tm.lap(s->st.us_fs_domains);
+  tm.lap(s->st.us_score);
 
   // ---- the standard-translation branch: ORFs whose DNA window lost the arbitration, or every ORF past F3 without --fs
   // (src/p7_pipeline.c:1480-1511, :1720-1771): BackwardParser + DomainDecoding + regions per ORF, then each envelope rescored

@@ -33,7 +33,7 @@ class FilterParams(C.Structure):
 class Backend(C.Structure):
     """bathhost_backend: the device library as a table of function pointers (include/bathhost.h)"""
     _names = ["last_error", "load_fs_profile", "load_filter_profile", "select_slot", "upload_block", "upload_orfs", "msv_orfs", "ssv_windows",
-              "vit_orfs", "fwd_orfs", "fs_fwd_windows", "fs_fwd_bck_xrows", "fs_bck_decode", "fs_domains", "orf_fwd_bck_xrows", "orf_domains", "orfs_msv_screen", "orfs_fetch", "revcomp_slot"]
+              "vit_orfs", "fwd_orfs", "fs_fwd_windows", "fs_fwd_bck_xrows", "fs_bck_decode", "fs_domains", "orf_fwd_bck_xrows", "orf_domains", "orfs_msv_screen", "orfs_fetch", "revcomp_slot", "host_alloc", "host_free"]
     _fields_ = [("ctx", C.c_void_p)] + [(n, C.c_void_p) for n in _names]
 
 
@@ -55,7 +55,7 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("nseqs", "nres", "pos_past_msv", "pos_past_bias", "pos_past_vit", "pos_past_fwd", "n_orfs",
                                          "n_windows", "n_std_windows", "n_regions", "n_multidomain_regions", "n_envelopes",
                                          "n_hits_reported", "us_orfs", "us_upload", "us_msv", "us_bias", "us_vit", "us_fwd",
-                                         "us_windows", "us_fs_fwd", "us_fs_domains", "us_std")]
+                                         "us_windows", "us_fs_fwd", "us_fs_domains", "us_std", "us_xrows", "us_decode", "us_score")]
 
 
 _lib = None

@@ -121,6 +121,8 @@ typedef struct {
                          int64_t *norfs_per_block, int64_t *nhits, int64_t *nres);
   int (*orfs_fetch)(void *ctx, void *hits, uint8_t *residues);
   int (*revcomp_slot)(void *ctx, int src, int dst);
+  void *(*host_alloc)(size_t bytes);          /* optional (may be NULL): page-locked host memory for result buffers */
+  void (*host_free)(void *p);
 } bathhost_backend;
 
 /* 0 / unset fields take bathsearch's defaults (src/p7_pipeline.c:145-214; src/bathsearch.c:94) */
@@ -150,7 +152,7 @@ typedef struct {
   int64_t pos_past_msv, pos_past_bias, pos_past_vit, pos_past_fwd;   /* the footer's filter counters          */
   int64_t n_orfs, n_windows, n_std_windows, n_regions, n_multidomain_regions, n_envelopes, n_hits_reported;
   /* wall time per stage of the host pipeline, microseconds (host work + the device calls made from it) */
-  int64_t us_orfs, us_upload, us_msv, us_bias, us_vit, us_fwd, us_windows, us_fs_fwd, us_fs_domains, us_std;
+  int64_t us_orfs, us_upload, us_msv, us_bias, us_vit, us_fwd, us_windows, us_fs_fwd, us_fs_domains, us_std, us_xrows, us_decode, us_score;
 } bathhost_stats;
 
 typedef struct bathhost_search bathhost_search;

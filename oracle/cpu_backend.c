@@ -548,3 +548,7 @@ int bo_backend_orfs_fetch(void *ctx, void *hits, uint8_t *residues)
   }
   return BO_OK;
 }
+
+/* plain heap memory: the CPU backend has no device link to feed */
+void *bo_backend_host_alloc(size_t bytes) { return malloc(bytes); }
+void  bo_backend_host_free(void *p) { free(p); }
