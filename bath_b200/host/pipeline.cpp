@@ -1115,17 +1115,24 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
   }
 
   tm.lap(s->st.us_fs_domains);
-  // ---- scoring and hit records, in the reference's order
+  // ---- scoring and hit records: envelopes are independent of one another (the early E-value cut uses the residue count fixed
+  // for their block), so they are scored on all host cores and the hits appended in the reference's order
   {
-    std::vector<uint8_t> wbuf;
-    size_t epos[2] = { 0, 0 };
-    for (size_t b = 0; b < nb; ++b)
-      for (int sidx : active) {
-        Strand &S = strands[sidx];
-        const std::vector<bathgpu_domain_result> &res = S.res;
-        const std::vector<bathgpu_trace_step> &traces = S.traces;
-        for (; epos[sidx] < S.envs.size() && S.dwin_blk[S.envs[epos[sidx]].win] == (int) b; ++epos[sidx]) {
-          const size_t e = epos[sidx];
+    struct Item { int sidx; size_t e; size_t b; };
+    std::vector<Item> order;
+    {
+      size_t epos[2] = { 0, 0 };
+      for (size_t b = 0; b < nb; ++b)
+        for (int sidx : active) {
+          Strand &S = strands[sidx];
+          for (; epos[sidx] < S.envs.size() && S.dwin_blk[S.envs[epos[sidx]].win] == (int) b; ++epos[sidx]) order.push_back(Item{ sidx, epos[sidx], b });
+        }
+    }
+    auto score_env = [&](const Item &it, Background &lbg, std::vector<uint8_t> &wbuf, Hit &h) -> bool {
+      const int sidx = it.sidx; const size_t e = it.e, b = it.b;
+      Strand &S = strands[sidx];
+      const std::vector<bathgpu_domain_result> &res = S.res;
+      const std::vector<bathgpu_trace_step> &traces = S.traces;
           const BlockInfo &binfo = blocks[b];
           const DnaWin &dw = S.dwin[S.envs[e].win];
           const uint8_t *wdsq = S.oriented(S.goff(binfo, n) + dw.n - 1, dw.length, wbuf);
@@ -1134,20 +1141,20 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
           struct { bool complement; long long start; const char *name; long long sq_len; } blk = { S.complement, S.start_of(binfo), name, (long long) n };
           const int i = S.envs[e].i, j = S.envs[e].j, Ld = S.ge[e].L;
         const bathgpu_domain_result &r = res[e];
-        if (r.status != 0 && r.trace_len == 0) continue;   // Forward/Backward range error: envelope dropped (:1022,1041)
-        bg.set_length(Ld / 3);
-        const float env_null = bg.fs_null_one(Ld / 3);
+        if (r.status != 0 && r.trace_len == 0) return false;   // Forward/Backward range error: envelope dropped (:1022,1041)
+        lbg.set_length(Ld / 3);
+        const float env_null = lbg.fs_null_one(Ld / 3);
         const float seqsc = (r.envsc - env_null) / kLog2;
         const double P = exp_surv(seqsc, ev[EV_FTAUFS5], ev[EV_FLAMBDA]);
         const double Z = (float) nres_now / (float) q.max_length;
-        if (P * Z > opt.E) continue;                         // early cut on the residues seen so far (:1033-1037)
-        if (r.status != 0) continue;
+        if (P * Z > opt.E) return false;                         // early cut on the residues seen so far (:1033-1037)
+        if (r.status != 0) return false;
 
         Domain dom;
         dom.tr.assign(traces.begin() + r.trace_offset, traces.begin() + r.trace_offset + r.trace_len);
         for (auto &ts : dom.tr) ts.i += i - 1;               // window coordinates (:1050-1051; every i >= 0 is shifted)
         const float aliscore = ali_score(m, dom.tr, wdsq);
-        if (aliscore < 0.0f) continue;
+        if (aliscore < 0.0f) return false;
 
         // null2 correction along the trace (:1084-1142)
         float domcorrection = 0.0f;
@@ -1201,7 +1208,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
         int z1 = 0, z2 = (int) dom.tr.size() - 1;
         while (z1 < (int) dom.tr.size() && dom.tr[z1].st != TS_M) ++z1;
         while (z2 >= 0 && dom.tr[z2].st != TS_M) --z2;
-        if (z1 > z2) continue;
+        if (z1 > z2) return false;
         dom.iali = dom.tr[z1].i - (dom.tr[z1].c - 1);
         dom.jali = dom.tr[z2].i;
         dom.ienv = i; dom.jenv = j;
@@ -1210,7 +1217,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
 
         // ---- p7_pli_postDomainDef_Frameshift_BATH (src/p7_pipeline.c:1005-1144)
         const int ali_len = dom.jali - dom.iali + 1;
-        if (ali_len < 12) continue;
+        if (ali_len < 12) return false;
         const int env_len = dom.jenv - dom.ienv + 1;
         const int ml = q.max_length;
         float bitscore = dom.envsc;
@@ -1218,16 +1225,16 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
         bitscore += 2 * log(2. / (ml + 2));
         bitscore -= ((env_len - ali_len) / 3.) * log((float) (env_len / 3.) / (float) ((env_len / 3.) + 2));
         bitscore += ((std::max(env_len, ml * 3) - ali_len) / 3.) * log((float) ml / (float) (ml + 2));
-        const float dom_bias = opt.do_null2 ? flogsum(0.0, log(bg.omega) + dom.domcorrection) : 0.0f;
+        const float dom_bias = opt.do_null2 ? flogsum(0.0, log(lbg.omega) + dom.domcorrection) : 0.0f;
         const int nl = std::max(env_len / 3, ml);
-        bg.set_length(nl);
-        const float hit_null = bg.fs_null_one(nl);
+        lbg.set_length(nl);
+        const float hit_null = lbg.fs_null_one(nl);
         const float dom_score = (bitscore - (hit_null + dom_bias)) / kLog2;
         const double dom_lnP = exp_logsurv(dom_score, ev[EV_FTAUFS5], ev[EV_FLAMBDA]);
         const double Z2 = (float) nres_now / (float) ml;
-        if (!(exp(dom_lnP) * Z2 <= opt.E)) continue;
+        if (!(exp(dom_lnP) * Z2 <= opt.E)) return false;
 
-        Hit h;
+        h = Hit();
         memset(&h.pub, 0, sizeof h.pub);
         auto orig = [&](int wpos) -> long long {            // window position -> coordinate on the source sequence
           return blk.complement ? blk.start - (dw.n + wpos) + 2 : blk.start + dw.n + wpos - 2;
@@ -1245,9 +1252,16 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
         h.pub.trace_len = (int32_t) dom.tr.size();
         summarize_alignment(m, dom.tr, wdsq, h.pub);
         h.sortkey = -dom_lnP;
-        s->hits.push_back(h);
-        }
-      }
+        return true;
+    };
+    std::vector<Hit> out(order.size());
+    std::vector<uint8_t> ok(order.size(), 0);
+    parallel_chunks(order.size(), 8, [&](size_t za, size_t zb) {
+      Background lbg = bg;
+      std::vector<uint8_t> wbuf;
+      for (size_t z = za; z < zb; ++z) ok[z] = score_env(order[z], lbg, wbuf, out[z]) ? 1 : 0;
+    });
+    for (size_t z = 0; z < order.size(); ++z) if (ok[z]) s->hits.push_back(out[z]);
   }
   tm.lap(s->st.us_score);
 
