@@ -19,7 +19,7 @@ EXPORTS = [
     "bathgpu_load_filter_profile", "bathgpu_upload_orfs", "bathgpu_msv_orfs", "bathgpu_ssv_windows", "bathgpu_vit_orfs",
     "bathgpu_fwd_orfs", "bathgpu_fs_fwd_bck_xrows", "bathgpu_select_slot",
     "bathgpu_orf_fwd_bck_xrows", "bathgpu_orf_domains", "bathgpu_orf_fetch_domain_matrices",
-    "bathgpu_orfs_msv_screen", "bathgpu_orfs_fetch", "bathgpu_revcomp_slot",
+    "bathgpu_orfs_msv_screen", "bathgpu_orfs_fetch", "bathgpu_revcomp_slot", "bathgpu_fs_fwd_block",
 ]
 
 
@@ -128,6 +128,8 @@ def load():
     L.bathgpu_orfs_fetch.argtypes = [vp, vp, C.POINTER(C.c_uint8)]
     L.bathgpu_revcomp_slot.restype = C.c_int
     L.bathgpu_revcomp_slot.argtypes = [vp, C.c_int, C.c_int]
+    L.bathgpu_fs_fwd_block.restype = C.c_int
+    L.bathgpu_fs_fwd_block.argtypes = [vp, C.POINTER(C.c_uint8), C.c_int64, vp, C.c_int, fp, fp, ip]
     L.bathgpu_select_slot.restype = C.c_int
     L.bathgpu_select_slot.argtypes = [vp, C.c_int]
     L.bathgpu_host_alloc.restype = vp
@@ -242,6 +244,13 @@ class Context:
         """Same call writing into caller-owned (e.g. pinned) score/status arrays."""
         xf = np.asarray(xfE, np.float32)
         self._check(self.lib.bathgpu_fs_fwd_windows(self.h, wins.ctypes.data, len(wins), _f(xf), _f(sc), _i(st)))
+
+    def fs_fwd_block_into(self, dsq, wins, xfE, sc, st):
+        """bathgpu_fs_fwd_block: upload and score in one call (upload overlapped with the kernel), into caller-owned arrays"""
+        xf = np.asarray(xfE, np.float32)
+        d = np.ascontiguousarray(dsq, np.uint8)
+        self._check(self.lib.bathgpu_fs_fwd_block(self.h, d.ctypes.data_as(C.POINTER(C.c_uint8)), len(d) - 2, wins.ctypes.data, len(wins),
+                                                  _f(xf), _f(sc), _i(st)))
 
     def stage_windows(self, wins):
         self._check(self.lib.bathgpu_stage_windows(self.h, wins.ctypes.data, len(wins)))

@@ -66,7 +66,8 @@ struct TargetSlot {          // one resident target: packed DNA block + ORF resi
 struct bathgpu_ctx {
   int           device = 0;
   cudaDeviceProp prop{};
-  cudaStream_t  stream = nullptr;
+  cudaStream_t  stream = nullptr, copy_stream = nullptr, stream2 = nullptr;
+  cudaEvent_t   chunk_ev[16] = {};
   cudaEvent_t   ev0 = nullptr, ev1 = nullptr;
   std::string   err;
   FsProfileImage fs3, fs5;
@@ -149,6 +150,7 @@ extern "C" void bathgpu_destroy(bathgpu_ctx *ctx)
   for (DevBuf *b : { &ctx->fxmx, &ctx->bxmx, &ctx->lsf, &ctx->lsb, &ctx->xoff, &ctx->dmocc, &ctx->dbtot, &ctx->detot, &ctx->bcksc }) b->release();
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); cudaStreamDestroy(ctx->stream2); for (auto &e : ctx->chunk_ev) if (e) cudaEventDestroy(e); }
   delete ctx;
 }
 
@@ -484,6 +486,21 @@ __global__ void pack_dna4_kernel(const uint8_t *__restrict__ dsq, long long n, u
   out[w] = word;
 }
 
+__global__ void pack_dna4_range_kernel(const uint8_t *__restrict__ dsq, long long n, uint32_t *__restrict__ out, long long wlo, long long whi)
+{
+  const long long w = wlo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= whi) return;
+  uint32_t word = 0;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const long long p = w * 8 + b - 8;
+    uint32_t code = 15u;
+    if (p >= 0 && p < n) { code = dsq[p + 1]; if (code > 15u) code = 15u; }
+    word |= code << (4 * b);
+  }
+  out[w] = word;
+}
+
 extern "C" int bathgpu_select_slot(bathgpu_ctx *ctx, int slot)
 {
   if (!ctx || slot < 0 || slot > 1) return fail(ctx, BATHGPU_EINVAL, "slot must be 0 or 1");
@@ -536,6 +553,109 @@ extern "C" int bathgpu_revcomp_slot(bathgpu_ctx *ctx, int src, int dst)
   CUDA_TRY(ctx, cudaGetLastError());
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   B.block_n = n; B.nres = 0;
+  return BATHGPU_OK;
+}
+
+
+static cudaError_t dispatch_fwd(bool xmx, int J, const FsParserArgs &a, int sms, cudaStream_t s);
+
+// Upload a block and score its windows in one call, with the upload hidden behind the kernel: the block crosses the link in
+// chunks on a second stream, and the windows that end inside the part already resident are scored while the rest is in flight
+// (per block the reference uploads nothing and calls p7_ForwardParser_Frameshift_3Codons window by window, src/p7_pipeline.c:1450).
+extern "C" int bathgpu_fs_fwd_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_t n, const bathgpu_window *wins, int nwin,
+                                    const float xfE[2], float *fwdsc, int32_t *status)
+{
+  if (!ctx || !dsq || n < 1 || !wins || nwin < 1 || !xfE || !fwdsc || !status) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fs_fwd_block");
+  if (!ctx->fs3.loaded) return fail(ctx, BATHGPU_EINVAL, "3-codon profile not loaded");
+  for (int w = 0; w < nwin; ++w)
+    if (wins[w].L < 3 || wins[w].start < 1 || wins[w].start + wins[w].L - 1 > n)
+      return fail(ctx, BATHGPU_EINVAL, "window %d (start %lld, L %d) is outside the block (n=%lld) or shorter than 3", w, (long long)wins[w].start, wins[w].L, (long long)n);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->copy_stream) {
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    for (auto &e : ctx->chunk_ev) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  TargetSlot &S = ctx->S();
+  const long long nwords = (n + 8 + 7) / 8 + 24;
+  if (S.dna_bytes.reserve((size_t)n + 2) != BATHGPU_OK || S.dna4.reserve((size_t)nwords * 4) != BATHGPU_OK ||
+      ctx->wins.reserve((size_t)nwin * sizeof(WindowDesc)) != BATHGPU_OK || ctx->fwdsc.reserve((size_t)nwin * 4) != BATHGPU_OK ||
+      ctx->status.reserve((size_t)nwin * 4) != BATHGPU_OK || ctx->counter.reserve(64) != BATHGPU_OK)
+    return fail(ctx, BATHGPU_EMEM, "device allocation failed");
+  S.block_n = n; S.nres = 0;
+  // Chunks grow fourfold: scoring a chunk takes several times longer than moving it, so every later chunk arrives while the
+  // one before it is being scored, and the first one is small enough that the device starts almost at once.
+  long long cuts[8]; int K = 0;
+  {
+    long long first = n / 85, p = 0;
+    if (n < (4 << 20)) first = n;
+    for (long long sz = std::max<long long>(first, 1 << 20); p < n && K < 7; sz *= 4) { p = std::min<long long>(n, (p + sz + 7) & ~7LL); cuts[K++] = p; }
+    cuts[K - 1] = n;
+  }
+  cudaEvent_t *pack_ev = ctx->chunk_ev, *join_ev = ctx->chunk_ev + 8;
+  for (int c = 0; c < K; ++c) {
+    const long long p0 = c ? cuts[c - 1] : 0, p1 = cuts[c];                       // 0-based nucleotides [p0, p1); dsq[1 + p] is nucleotide p
+    CUDA_TRY(ctx, cudaMemcpyAsync(S.dna_bytes.as<uint8_t>() + 1 + p0, dsq + 1 + p0, (size_t)(p1 - p0), cudaMemcpyHostToDevice, ctx->copy_stream));
+    // packed word w holds nucleotides 8w-8 .. 8w-1: this chunk completes words p0/8+1 .. p1/8 (and the tail guard at the end)
+    const long long wlo = (c == 0) ? 0 : p0 / 8 + 1, whi = (p1 >= n) ? nwords : p1 / 8 + 1;
+    if (whi > wlo)
+      pack_dna4_range_kernel<<<(unsigned)((whi - wlo + 255) / 256), 256, 0, ctx->copy_stream>>>(S.dna_bytes.as<uint8_t>(), n, S.dna4.as<uint32_t>(), wlo, whi);
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaEventRecord(pack_ev[c], ctx->copy_stream));
+  }
+  // windows in order of their last nucleotide (while the first chunks are in flight); callers that tile a block are already in order
+  static_assert(sizeof(WindowDesc) == sizeof(bathgpu_window), "descriptor layouts must agree");
+  bool in_order = true;
+  for (int w = 1; w < nwin && in_order; ++w) in_order = wins[w - 1].start + wins[w - 1].L <= wins[w].start + wins[w].L;
+  std::vector<int> order;
+  std::vector<WindowDesc> sorted;
+  std::vector<float> sc;
+  std::vector<int> st;
+  if (!in_order) {
+    order.resize((size_t)nwin); sorted.resize((size_t)nwin); sc.resize((size_t)nwin); st.resize((size_t)nwin);
+    for (int w = 0; w < nwin; ++w) order[w] = w;
+    std::sort(order.begin(), order.end(), [&](int x, int y) { return wins[x].start + wins[x].L < wins[y].start + wins[y].L; });
+    for (int w = 0; w < nwin; ++w) memcpy(&sorted[w], &wins[order[w]], sizeof(WindowDesc));
+  }
+  const WindowDesc *hw = in_order ? reinterpret_cast<const WindowDesc *>(wins) : sorted.data();
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->wins.p, hw, (size_t)nwin * sizeof(WindowDesc), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, 64, ctx->stream));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  // launches alternate between two streams, so the tail of one launch (its last windows finishing on a thinning set of SMs)
+  // is filled by the head of the next
+  const FsProfileImage &im = ctx->fs3;
+  int w0 = 0, launches = 0;
+  for (int c = 0; c < K; ++c) {
+    const long long ready_nt = (c == K - 1) ? n : 8 * (cuts[c] / 8);               // nucleotides whose packed words are complete
+    int w1 = w0;
+    while (w1 < nwin && hw[w1].start + hw[w1].L - 1 <= ready_nt) ++w1;
+    if (c == K - 1) w1 = nwin;
+    if (w1 == w0) continue;
+    cudaStream_t s = (launches & 1) ? ctx->stream2 : ctx->stream;
+    if (launches == 1) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev0, 0));    // descriptors and counters are set on the first stream
+    CUDA_TRY(ctx, cudaStreamWaitEvent(s, pack_ev[c], 0));
+    FsParserArgs a{};
+    a.emis = im.emis.as<float>(); a.cellc = im.cellc.as<float>(); a.dna4 = S.dna4.as<uint32_t>();
+    a.wins = ctx->wins.as<WindowDesc>() + w0; a.nwin = w1 - w0; a.mpad = im.mpad; a.tEM = xfE[0]; a.tEL = xfE[1];
+    a.fwdsc = ctx->fwdsc.as<float>() + w0; a.status = ctx->status.as<int>() + w0; a.xmx = nullptr; a.xoff = nullptr;
+    a.counter = ctx->counter.as<int>() + launches; a.scan_steps = im.scan_steps;
+    CUDA_TRY(ctx, dispatch_fwd(false, im.J, a, ctx->prop.multiProcessorCount, s));
+    ++launches;
+    w0 = w1;
+  }
+  if (launches > 1) {
+    CUDA_TRY(ctx, cudaEventRecord(join_ev[0], ctx->stream2));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, join_ev[0], 0));
+  }
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(in_order ? fwdsc : sc.data(), ctx->fwdsc.p, (size_t)nwin * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(in_order ? status : st.data(), ctx->status.p, (size_t)nwin * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  if (!in_order) for (int w = 0; w < nwin; ++w) { fwdsc[order[w]] = sc[w]; status[order[w]] = st[w]; }
+  CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+  ctx->last_launches = launches;
+  ctx->nstaged = 0;
   return BATHGPU_OK;
 }
 

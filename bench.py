@@ -318,13 +318,11 @@ def main():
     sc = capi.pinned_array((nwin,), np.float32)
     st = capi.pinned_array((nwin,), np.int32)
     for _ in range(2):
-        ctx.upload_block(dsq)
-        ctx.fs_fwd_windows_into(wins, xfE, sc, st)
+        ctx.fs_fwd_block_into(dsq, wins, xfE, sc, st)          # upload + score in one C-ABI call (the upload rides behind the kernel)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ctx.upload_block(dsq)
-        ctx.fs_fwd_windows_into(wins, xfE, sc, st)
+        ctx.fs_fwd_block_into(dsq, wins, xfE, sc, st)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop() if rank == 0 else None

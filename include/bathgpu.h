@@ -175,6 +175,11 @@ int bathgpu_revcomp_slot(bathgpu_ctx *ctx, int src, int dst);
 int bathgpu_fs_fwd_windows(bathgpu_ctx *ctx, const bathgpu_window *wins, int n, const float xfE[2],
                            float *fwdsc, int32_t *status);
 
+/* bathgpu_upload_block + bathgpu_fs_fwd_windows in one call with the upload hidden behind the kernel: the block crosses the host
+ * link in chunks while the windows that end inside the part already resident are being scored.  Any window order. */
+int bathgpu_fs_fwd_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_t n, const bathgpu_window *wins, int nwin,
+                         const float xfE[2], float *fwdsc, int32_t *status);
+
 /* Same stage on descriptors already resident in device memory (set by
  * bathgpu_stage_windows); results stay on the device until bathgpu_fetch_scores.
  * Used to time the kernel with inputs resident in HBM. */

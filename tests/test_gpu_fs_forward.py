@@ -94,3 +94,23 @@ def test_forward_parser_golden_window(oracle, gpu_ctx):
     assert st[0] == 0 and ost == 0
     assert abs(sc[0] - osc) <= TOL_NATS
     assert abs(sc[0] - 50.70534) <= 2e-3
+
+
+def test_fused_upload_and_forward_matches_two_calls(oracle, gpu_ctx):
+    """bathgpu_fs_fwd_block (chunked upload overlapped with scoring, windows in any order) == upload_block + fs_fwd_windows, bit for bit"""
+    from bath_b200 import capi
+    model = oracle.Model(common.golden("AMP_N.bhmm"))
+    rng = np.random.default_rng(17)
+    n = 9_000_000                                    # three chunks: cuts at 1 Mi and 5 Mi nucleotides
+    dsq = common.random_dna(rng, n, p_degenerate=0.001)
+    gpu_ctx.load_fs_profile(3, model.rfv(3), model.tfv(3))
+    starts = np.sort(rng.integers(1, n - 1500, 4000))
+    starts[:8] = [1, 2, 1_048_000, 1_048_570, 1_048_576, 5_242_880 - 700, n - 1299, n - 1200]      # around the chunk boundaries and both ends
+    lens = rng.integers(60, 1300, len(starts)); lens[7] = 1200; lens[6] = 1300
+    perm = rng.permutation(len(starts))
+    w = capi.Context.make_windows(starts[perm], lens[perm])
+    gpu_ctx.upload_block(dsq)
+    sc0, st0 = gpu_ctx.fs_fwd_windows(w)
+    sc1, st1 = np.empty(len(w), np.float32), np.empty(len(w), np.int32)
+    gpu_ctx.fs_fwd_block_into(dsq, w, (0.5, 0.5), sc1, st1)
+    assert np.array_equal(st0, st1) and np.array_equal(sc0, sc1)
