@@ -19,7 +19,7 @@ EXPORTS = [
     "bathgpu_load_filter_profile", "bathgpu_upload_orfs", "bathgpu_msv_orfs", "bathgpu_ssv_windows", "bathgpu_vit_orfs",
     "bathgpu_fwd_orfs", "bathgpu_fs_fwd_bck_xrows", "bathgpu_select_slot",
     "bathgpu_orf_fwd_bck_xrows", "bathgpu_orf_domains", "bathgpu_orf_fetch_domain_matrices",
-    "bathgpu_orfs_msv_screen", "bathgpu_orfs_fetch", "bathgpu_revcomp_slot", "bathgpu_fs_fwd_block",
+    "bathgpu_orfs_msv_screen", "bathgpu_orfs_fetch", "bathgpu_revcomp_slot", "bathgpu_fs_fwd_block", "bathgpu_fs_forward_matrices",
 ]
 
 
@@ -130,6 +130,8 @@ def load():
     L.bathgpu_revcomp_slot.argtypes = [vp, C.c_int, C.c_int]
     L.bathgpu_fs_fwd_block.restype = C.c_int
     L.bathgpu_fs_fwd_block.argtypes = [vp, C.POINTER(C.c_uint8), C.c_int64, vp, C.c_int, fp, fp, ip]
+    L.bathgpu_fs_forward_matrices.restype = C.c_int
+    L.bathgpu_fs_forward_matrices.argtypes = [vp, vp, C.c_int, fp, fp, fp, C.c_int64, fp, ip]
     L.bathgpu_select_slot.restype = C.c_int
     L.bathgpu_select_slot.argtypes = [vp, C.c_int]
     L.bathgpu_host_alloc.restype = vp
@@ -410,6 +412,19 @@ class Context:
         oax = np.empty((L + 1, 6), np.float32)
         self._check(self.lib.bathgpu_orf_fetch_domain_matrices(self.h, e, _f(pp), _f(oa), _f(ppx), _f(oax)))
         return pp, oa, ppx, oax
+
+    def fs_forward_matrices(self, regs, M, xfE5=(0.5, 0.5)):
+        """bathgpu_fs_forward_matrices: (mx [rows][(M+1)][8], xrows [rows][6], row offsets, fwdsc, status)"""
+        n = len(regs)
+        off = np.concatenate([[0], np.cumsum(regs["L"].astype(np.int64) + 1)])
+        rows = int(off[-1])
+        mx = np.empty((rows, M + 1, 8), np.float32)
+        xr = np.empty((rows, 6), np.float32)
+        sc = np.empty(n, np.float32)
+        st = np.empty(n, np.int32)
+        xf = np.asarray(xfE5, np.float32)
+        self._check(self.lib.bathgpu_fs_forward_matrices(self.h, regs.ctypes.data, n, _f(xf), _f(mx), _f(xr), rows, _f(sc), _i(st)))
+        return mx, xr, off, sc, st
 
     def fs_domains(self, envs, xfE5=(1.0, 0.0), max_steps=None):
         n = len(envs)

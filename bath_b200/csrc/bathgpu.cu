@@ -53,6 +53,7 @@ struct FsProfileImage {
   DevBuf oaflags;  // [mpad] transition-allowed bits per node (optimal accuracy masks)
   DevBuf oapass;   // [5][32] D pass-through flags of the optimal-accuracy scan
   DevBuf tfvraw;   // [8][M+1] transition odds as given (traceback)
+  DevBuf zinv;     // [mpad] 1/Z(k) by node, k-1 (un-folds the stored match cells when a Forward matrix is handed out)
   bool  loaded = false;
 };
 
@@ -87,7 +88,7 @@ struct bathgpu_ctx {
   DevBuf        o_tiles, o_cnt, o_base, o_blocks, o_first, o_tjb, o_null, o_meta, o_hits, o_counters;
   long long     o_nhits = 0, o_nres = 0;
   // domain stage workspace (last chunk stays resident for bathgpu_fs_fetch_domain_matrices)
-  DevBuf        envs, dpp, doa, dfx, dppx, doax, dlsf, dfw, dbk, doasc, dnull2, dstat, dtoff, dtlen, dsteps;
+  DevBuf        envs, dpp, doa, dfx, dppx, doax, dlsf, dfw, dbk, doasc, dnull2, dstat, dtoff, dtlen, dsteps, ddcell, dmxout;
   std::vector<long long> dom_xoff;
   std::vector<int>       dom_L;
   float         last_ms = 0.f;
@@ -139,12 +140,13 @@ extern "C" void bathgpu_destroy(bathgpu_ctx *ctx)
   cudaStreamSynchronize(ctx->stream);
   for (FsProfileImage *im : { &ctx->fs3, &ctx->fs5 }) {
     im->emis.release(); im->cellc.release(); im->cellb.release(); im->cellf5.release(); im->amino.release();
-    im->oaflags.release(); im->oapass.release(); im->tfvraw.release();
+    im->oaflags.release(); im->oapass.release(); im->tfvraw.release(); im->zinv.release();
   }
   for (TargetSlot &t : ctx->slot) { t.dna_bytes.release(); t.dna4.release(); t.residues.release(); }
   ctx->wins.release(); ctx->fwdsc.release();
   ctx->status.release(); ctx->counter.release(); ctx->scratch.release();
   for (DevBuf *b : { &ctx->f_rbv, &ctx->f_rwv, &ctx->f_twv, &ctx->f_ddsum, &ctx->orfs, &ctx->fsc, &ctx->fst, &ctx->fwins, &ctx->fnw }) b->release();
+  ctx->ddcell.release(); ctx->dmxout.release();
   for (DevBuf *b : { &ctx->envs, &ctx->dpp, &ctx->doa, &ctx->dfx, &ctx->dppx, &ctx->doax, &ctx->dlsf, &ctx->dfw, &ctx->dbk, &ctx->doasc,
                      &ctx->dnull2, &ctx->dstat, &ctx->dtoff, &ctx->dtlen, &ctx->dsteps }) b->release();
   for (DevBuf *b : { &ctx->fxmx, &ctx->bxmx, &ctx->lsf, &ctx->lsb, &ctx->xoff, &ctx->dmocc, &ctx->dbtot, &ctx->detot, &ctx->bcksc }) b->release();
@@ -448,8 +450,11 @@ extern "C" int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int n
     }
     if (im.cellf5.reserve(cc.size() * 4) != BATHGPU_OK || im.amino.reserve(am.size() * 4) != BATHGPU_OK ||
         im.oaflags.reserve(fl.size() * 4) != BATHGPU_OK || im.oapass.reserve(pass.size() * 4) != BATHGPU_OK ||
-        im.tfvraw.reserve((size_t)8 * ld * 4) != BATHGPU_OK)
+        im.tfvraw.reserve((size_t)8 * ld * 4) != BATHGPU_OK || im.zinv.reserve((size_t)mpad * 4) != BATHGPU_OK)
       return fail(ctx, BATHGPU_EMEM, "device allocation failed");
+    std::vector<float> zi(mpad, 0.0f);
+    for (int k = 1; k <= M; ++k) zi[k - 1] = (float)(1.0 / zK[k]);
+    CUDA_TRY(ctx, cudaMemcpyAsync(im.zinv.p, zi.data(), zi.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(im.cellf5.p, cc.data(), cc.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(im.amino.p, am.data(), am.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(im.oaflags.p, fl.data(), fl.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -1040,6 +1045,111 @@ extern "C" int bathgpu_fs_domains(bathgpu_ctx *ctx, const bathgpu_envelope *envs
     if (st != BATHGPU_OK) return st;
     e0 = e1;
   }
+  return BATHGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward matrices for the stochastic traceback (a16)
+static cudaError_t dispatch_forward_matrix(int J, const DomainArgs &a, int sms, cudaStream_t s)
+{
+  cudaError_t e = cudaErrorInvalidValue;
+#define X(S) if (launch_fs5_forward_matrix_##S(J, a, sms, s, &e)) return e;
+  BATHGPU_FOR_EACH_SET(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
+// Stored Forward cells -> the reference's cell order and values: out[(row * (M+1) + k) * 8 + {D, I, M_C0..M_C5}]
+// (src/impl_sse/impl_sse.h:296-314, un-striped); match cells are stored times Z(k) (fs_domain.cuh) and divided back here.
+__global__ void fs5_export_forward_kernel(const float *__restrict__ pp, const float *__restrict__ dcell, const float *__restrict__ zinv,
+                                          int J, int M, int mpad, long long rows, float *__restrict__ out)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * (M + 1)) return;
+  const long long row = t / (M + 1);
+  const int k = (int)(t - row * (M + 1));
+  float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+  if (k > 0) {
+    const int VEC = (J % 4 == 0) ? 4 : ((J % 2 == 0) ? 2 : 1);
+    const int kk = k - 1, lane = kk / J, j = kk % J;
+    const int p = (j / VEC) * (32 * VEC) + lane * VEC + (j % VEC);
+    const float *r = pp + (size_t)row * kPPCells * mpad + p;
+    const float zi = zinv[kk];
+    lo.x = dcell[(size_t)row * mpad + p];
+    lo.y = r[(size_t)PP_I * mpad];
+    lo.z = r[(size_t)PP_C0 * mpad] * zi;
+    lo.w = r[(size_t)(PP_C0 + 1) * mpad] * zi;
+    hi.x = r[(size_t)(PP_C0 + 2) * mpad] * zi;
+    hi.y = r[(size_t)(PP_C0 + 3) * mpad] * zi;
+    hi.z = r[(size_t)(PP_C0 + 4) * mpad] * zi;
+    hi.w = r[(size_t)(PP_C0 + 5) * mpad] * zi;
+  }
+  float4 *o = reinterpret_cast<float4 *>(out + (size_t)t * 8);
+  o[0] = lo; o[1] = hi;
+}
+
+extern "C" int bathgpu_fs_forward_matrices(bathgpu_ctx *ctx, const bathgpu_envelope *regs, int n, const float xfE5[2],
+                                           float *mx, float *xrows, int64_t max_rows, float *fwdsc, int32_t *status)
+{
+  if (!ctx || !regs || n < 1 || !xfE5 || !mx || !xrows || !fwdsc || !status) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fs_forward_matrices");
+  if (!ctx->fs5.loaded)      return fail(ctx, BATHGPU_EINVAL, "5-codon profile not loaded");
+  if (ctx->S().block_n == 0) return fail(ctx, BATHGPU_EINVAL, "no block uploaded");
+  int64_t total = 0;
+  for (int e = 0; e < n; ++e) {
+    if (regs[e].L < 6 || regs[e].start < 1 || regs[e].start + regs[e].L - 1 > ctx->S().block_n)
+      return fail(ctx, BATHGPU_EINVAL, "region %d (start %lld, L %d) is outside the uploaded block (n=%lld) or shorter than 6",
+                  e, (long long)regs[e].start, regs[e].L, (long long)ctx->S().block_n);
+    total += regs[e].L + 1;
+  }
+  if (total > max_rows) return fail(ctx, BATHGPU_EINVAL, "matrix buffer too small: %lld rows needed, %lld given", (long long)total, (long long)max_rows);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const FsProfileImage &im = ctx->fs5;
+  const int M = im.M, mpad = im.mpad;
+  ctx->last_ms = 0.f; ctx->last_launches = 0;
+  // chunks bounded by device memory: 8 stored cells + 8 exported per node and row
+  const size_t row_bytes = (size_t)(kPPCells + 1) * mpad * 4 + (size_t)(M + 1) * 32 + 32;
+  const size_t cap_rows = std::max<size_t>(((size_t)4 << 30) / row_bytes, 8192);
+  int e0 = 0;
+  int64_t row0 = 0;
+  while (e0 < n) {
+    int e1 = e0;
+    size_t rows = 0;
+    while (e1 < n && (e1 == e0 || rows + regs[e1].L + 1 <= cap_rows)) { rows += regs[e1].L + 1; ++e1; }
+    const int m = e1 - e0;
+    std::vector<long long> xoff(m + 1, 0);
+    for (int e = 0; e < m; ++e) xoff[e + 1] = xoff[e] + regs[e0 + e].L + 1;
+    if (ctx->envs.reserve((size_t)m * sizeof(EnvelopeDesc)) != BATHGPU_OK || ctx->xoff.reserve((size_t)(m + 1) * 8) != BATHGPU_OK ||
+        ctx->dpp.reserve(rows * kPPCells * mpad * 4) != BATHGPU_OK || ctx->ddcell.reserve(rows * mpad * 4) != BATHGPU_OK ||
+        ctx->dmxout.reserve(rows * (size_t)(M + 1) * 32) != BATHGPU_OK || ctx->dfx.reserve(rows * 24) != BATHGPU_OK ||
+        ctx->dlsf.reserve(rows * 4) != BATHGPU_OK || ctx->dfw.reserve((size_t)m * 4) != BATHGPU_OK ||
+        ctx->dstat.reserve((size_t)m * 4) != BATHGPU_OK || ctx->counter.reserve(64) != BATHGPU_OK)
+      return fail(ctx, BATHGPU_EMEM, "device allocation failed for %d regions (%zu rows, M=%d)", m, rows, M);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->envs.p, regs + e0, (size_t)m * sizeof(EnvelopeDesc), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->xoff.p, xoff.data(), (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    DomainArgs a{};
+    a.emis = im.emis.as<float>(); a.cellf = im.cellf5.as<float>(); a.dna4 = ctx->S().dna4.as<uint32_t>();
+    a.envs = ctx->envs.as<EnvelopeDesc>(); a.nenv = m; a.M = M; a.mpad = mpad; a.tEM = xfE5[0]; a.tEL = xfE5[1];
+    a.xoff = ctx->xoff.as<long long>(); a.pp = ctx->dpp.as<float>(); a.dcell = ctx->ddcell.as<float>(); a.fx = ctx->dfx.as<float>();
+    a.lsf = ctx->dlsf.as<float>(); a.fwdsc = ctx->dfw.as<float>(); a.status = ctx->dstat.as<int>(); a.counter = ctx->counter.as<int>();
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    CUDA_TRY(ctx, dispatch_forward_matrix(im.J, a, ctx->prop.multiProcessorCount, ctx->stream));
+    const long long cells = (long long)rows * (M + 1);
+    fs5_export_forward_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(ctx->dpp.as<float>(), ctx->ddcell.as<float>(), im.zinv.as<float>(),
+                                                                                        im.J, M, mpad, (long long)rows, ctx->dmxout.as<float>());
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(mx + (size_t)row0 * (M + 1) * 8, ctx->dmxout.p, (size_t)cells * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(xrows + (size_t)row0 * 6, ctx->dfx.p, rows * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(fwdsc + e0, ctx->dfw.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(status + e0, ctx->dstat.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_ms += ms; ctx->last_launches += 2;
+    row0 += (int64_t)rows;
+    e0 = e1;
+  }
+  ctx->dom_L.clear(); ctx->dom_xoff.clear();           // the posterior matrices of the last bathgpu_fs_domains call are gone
   return BATHGPU_OK;
 }
 

@@ -7,7 +7,8 @@
 // One warp per envelope, lane l owns J contiguous nodes, rows sequential -- the parsers' decomposition.
 // Three sweeps over the envelope instead of the reference's six passes over stored matrices:
 //   1. fs5_forward_kernel:  Forward, row state in registers; stores per cell {M_C0..M_C5 (times Z(k)), I}
-//      (the D cell is only ever read by the stochastic trace, which is not on this path) and the X rows;
+//      and the X rows; the D cell is only ever read by the stochastic trace (stotrace_fs.c:72), so only the
+//      fs5_forward_kernel<J, true> instantiation behind bathgpu_fs_forward_matrices keeps it;
 //   2. fs5_backward_decode_kernel: Backward row state in registers; each Backward row is multiplied into the
 //      stored Forward row at once and normalised, so the Backward matrix is never stored; the posterior
 //      matrix overwrites the Forward one in place (as the reference does), and the null2 column sums
@@ -60,6 +61,7 @@ struct DomainArgs {
   float           tEM, tEL;    // E->MOVE, E->LOOP odds of the 5-codon profile as configured by the caller
   const long long *xoff;       // X-row offset of envelope e (rows), xoff[e+1]-xoff[e] = L+1
   float          *pp;          // [rows][7][mpad]   Forward cells, then posteriors
+  float          *dcell;       // [rows][mpad]      Forward D cells (fs5_forward_kernel<J, true> only: the stochastic trace reads them)
   float          *oa;          // [rows][3][mpad]
   float          *fx;          // [rows][6] Forward X rows
   float          *ppx;         // [rows][6] posterior X rows (N,J,C used)
@@ -138,11 +140,11 @@ struct Fwd5State { float W[5][J]; float I[5][J]; float xN[5], xJ[5], xC[5]; };
 struct Fwd5Ctx { int L; float ploop, pmove, tEL, tEM, totscale, lsf; };
 
 // One Forward row.  PH = padded row mod 5 (compile time): ring slot of row i; row i-c sits in slot (PH+5-c)%5.
-template <int J, int VEC, int PH>
+template <int J, int VEC, int PH, bool STORE_D>
 __device__ __forceinline__ void fwd5_row(int i, int lane, Fwd5State<J> &S, const Fwd5Consts<J> &K,
                                          const char *__restrict__ emis_lane, unsigned rowbytes, uint32_t codes,
                                          Fwd5Ctx &R, float *__restrict__ pprow_lane, int mpad,
-                                         float *__restrict__ fxrow, float *__restrict__ lsfrow)
+                                         float *__restrict__ fxrow, float *__restrict__ lsfrow, float *__restrict__ drow_lane)
 {
   constexpr int P0 = PH, P1 = (PH + 4) % 5, P2 = (PH + 3) % 5, P3 = (PH + 2) % 5, P4 = (PH + 1) % 5;   // rows i, i-1, .., i-4
   int c[5];
@@ -195,11 +197,13 @@ __device__ __forceinline__ void fwd5_row(int i, int lane, Fwd5State<J> &S, const
   float xB = fmaf(xJ, R.pmove, xN * R.pmove);
 
   float o[J], icur[J];
+  float dv[STORE_D ? J : 1];
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     icur[j] = S.I[P0][j];
     float t = fmaf(icur[j], K.im[j], m0[j] * K.mm[j]);
     o[j] = fmaf(d, K.dm[j], t);
+    if constexpr (STORE_D) dv[j] = d;
     if (j + 1 < J) d = fmaf(d, K.dd[j], a[j]);
     S.I[P2][j] = fmaf(icur[j], K.ii[j], m0[j] * K.mi[j]);      // I(i+3): slot (i+3)%5 == (i-2)%5
   }
@@ -224,6 +228,7 @@ __device__ __forceinline__ void fwd5_row(int i, int lane, Fwd5State<J> &S, const
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       m0[j] *= sf; icur[j] *= sf;
+      if constexpr (STORE_D) dv[j] *= sf;
 #pragma unroll
       for (int cc = 0; cc < 5; ++cc) mc[cc][j] *= sf;
     }
@@ -239,6 +244,7 @@ __device__ __forceinline__ void fwd5_row(int i, int lane, Fwd5State<J> &S, const
     store_row<J, VEC>(row + PP_C0 * mpad, m0);
 #pragma unroll
     for (int cc = 0; cc < 5; ++cc) store_row<J, VEC>(row + (PP_C0 + 1 + cc) * mpad, mc[cc]);
+    if constexpr (STORE_D) store_row<J, VEC>(drow_lane + (size_t)i * mpad, dv);
     if (lane == 0) {
       float2 *x2 = reinterpret_cast<float2 *>(fxrow + (size_t)i * 6);
       x2[0] = make_float2(xE, xN);
@@ -266,7 +272,7 @@ __device__ __forceinline__ void load_fwd5_consts(const float *__restrict__ cc, i
   for (int s = 0; s < 5; ++s) K.bs[s] = __ldg(cc + F5_COUNT * J * kWarp + s * kWarp + lane);
 }
 
-template <int J>
+template <int J, bool STORE_D = false>
 __global__ void __launch_bounds__(32) fs5_forward_kernel(DomainArgs a)
 {
   constexpr int VEC = VecOf<J>::V;
@@ -289,6 +295,7 @@ __global__ void __launch_bounds__(32) fs5_forward_kernel(DomainArgs a)
     float *pprow_lane = a.pp + (size_t)xo * kPPCells * a.mpad + lane * VEC;
     float *fxrow = a.fx + (size_t)xo * 6;
     float *lsfrow = a.lsf + xo;
+    float *drow_lane = STORE_D ? a.dcell + (size_t)xo * a.mpad + lane * VEC : nullptr;
 
     Fwd5State<J> S;
 #pragma unroll
@@ -308,7 +315,7 @@ __global__ void __launch_bounds__(32) fs5_forward_kernel(DomainArgs a)
 #define BATHGPU_F5ROW(PH_)                                                                           \
         {                                                                                            \
           uint32_t codes = __shfl_sync(0xffffffffu, codes_l, g * 5 + PH_);                           \
-          fwd5_row<J, VEC, PH_>(i, lane, S, K, emis_lane, rowbytes, codes, R, pprow_lane, a.mpad, fxrow, lsfrow); \
+          fwd5_row<J, VEC, PH_, STORE_D>(i, lane, S, K, emis_lane, rowbytes, codes, R, pprow_lane, a.mpad, fxrow, lsfrow, drow_lane); \
           ++i;                                                                                       \
         }
         BATHGPU_F5ROW(0) BATHGPU_F5ROW(1) BATHGPU_F5ROW(2) BATHGPU_F5ROW(3) BATHGPU_F5ROW(4)

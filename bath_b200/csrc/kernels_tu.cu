@@ -126,6 +126,19 @@ bool CAT(launch_fs5_domains_, SETNAME)(int J, const DomainArgs &a, const TraceAr
   default: return false;
   }
 }
+// Forward alone, D cells kept: the matrix the stochastic traceback samples from (p7_Forward_Frameshift before
+// region_trace_ensemble_frameshift, src/p7_domaindef.c:411-414)
+bool CAT(launch_fs5_forward_matrix_, SETNAME)(int J, const DomainArgs &a, int sms, cudaStream_t s, cudaError_t *err)
+{
+  switch (J) {
+#define X(J_) case J_: if ((*err = cudaMemsetAsync(a.counter, 0, 4, s)) != cudaSuccess) return true;                               \
+                       fs5_forward_kernel<J_, true><<<grid_for(fs5_forward_kernel<J_, true>, 32, 0, a.nenv, sms), 32, 0, s>>>(a);   \
+                       *err = cudaGetLastError(); return true;
+  JLIST(X)
+#undef X
+  default: return false;
+  }
+}
 void CAT(preload_fs5_, SETNAME)(int J)
 {
   switch (J) {

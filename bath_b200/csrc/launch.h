@@ -23,6 +23,7 @@ struct FilterArgs;
   bool launch_fs3_forward_##S(int J, bool xmx, int version, const FsParserArgs &a, int sms, cudaStream_t s, cudaError_t *err);       \
   bool launch_fs3_backward_##S(int J, const FsBackwardArgs &a, int sms, cudaStream_t s, cudaError_t *err);                           \
   bool launch_fs5_domains_##S(int J, const DomainArgs &a, const TraceArgs &t, int sms, cudaStream_t s, cudaError_t *err);            \
+  bool launch_fs5_forward_matrix_##S(int J, const DomainArgs &a, int sms, cudaStream_t s, cudaError_t *err);                         \
   bool launch_orf_domains_##S(int J, bool full, const OrfDomainArgs &a, const TraceArgs &t, int sms, cudaStream_t s, cudaError_t *err); \
   bool launch_orf_forward_parser_##S(int J, const OrfFwdArgs &a, int sms, cudaStream_t s, cudaError_t *err);                        \
   void preload_fwd_##S(int J); void preload_bck_##S(int J); void preload_fs5_##S(int J); void preload_orf_##S(int J);

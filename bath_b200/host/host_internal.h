@@ -78,6 +78,18 @@ struct ProteinProfile {
   int16_t xw_move_for_length(int L) const;  // p7_oprofile_ReconfigRestLength
 };
 
+// ---- stotrace.cpp: the multi-domain branch of frameshift domain definition
+struct Segment { int idx, i, j, k, m; float prob; };             // struct p7_spcoord_s (src/p7_spensemble.c)
+struct ForwardMatrix {                                            // one region of bathgpu_fs_forward_matrices' output
+  const float *mx;                                                // [(L+1)][(M+1)][8] {D, I, M_C0..M_C5}
+  const float *xr;                                                // [(L+1)][6]        {E, N, J, B, C, SCALE}
+  int M, L;
+};
+struct SpecialOdds { float move, loop, e_move, e_loop; };         // N/J/C -> MOVE and LOOP, E -> MOVE and LOOP of the multihit profile
+bool sample_region_segments(const ForwardMatrix &F, const float *tfv, const SpecialOdds &X, uint32_t seed, int nsamples, int ireg,
+                            std::vector<Segment> &out);
+std::vector<Segment> cluster_region_segments(const std::vector<Segment> &sp, int nsamples);
+
 int   builder_max_length(const CoreModel &h, double emit_thresh);
 int   amino_code(char c);
 int   dna_code(char c);

@@ -9,9 +9,10 @@
 // are computed here exactly as the reference computes them; nothing in this file does dynamic programming
 // over model nodes except the 2-state bias filter (p7_bg_FilterScore), which the reference also runs on the host.
 //
-// Not restated yet ("next" rows): the standard-translation branch for windows the frameshift
-// arbitration rejects (src/p7_pipeline.c:1480-1511), and the stochastic-trace clustering of multi-domain regions
-// (src/p7_domaindef.c:411-451) -- such regions are rescored as one envelope and counted in the statistics.
+// Multi-domain regions of the frameshift branch are split as the reference splits them (src/p7_domaindef.c:395-453): Forward
+// matrix from the device, 200 sampled tracebacks and their clustering in stotrace.cpp.  Not restated: the same step of the
+// standard-translation branch (region_trace_ensemble, src/p7_domaindef.c:539-587) -- there such regions are rescored as one
+// envelope and counted in the statistics.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -19,6 +20,8 @@
 #include <cstring>
 #include <cstdlib>
 #include <limits>
+#include <map>
+#include <tuple>
 #include <string>
 #include <thread>
 #include <vector>
@@ -208,6 +211,7 @@ struct bathhost_search {
   const bathhost_model *model;
   bathhost_backend      be;
   HostBuf               xbuf[2][2];
+  HostBuf               mxbuf[2];                 // Forward matrices and X rows of multi-domain regions
   Options               opt;
   Background            bg;
   std::vector<float>    compo;
@@ -1024,8 +1028,26 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
   }
   tm.lap(s->st.us_decode);
   const float rt1 = 0.25f, rt2 = 0.10f, rt3 = 0.20f;
+  const uint32_t kStotraceSeed = 42; const int kStotraceSamples = 200;   // --seed default (src/bathsearch.c:131), ddef->nsamples (src/p7_domaindef.c:83)
   const int saveL = 100;                                    // gm_fs5->L: the dummy length bathsearch configures and never changes (src/bathsearch.c:797)
-  {
+  // Multi-domain regions (is_multidomain_region_frameshift) are split by stochastic-trace clustering (src/p7_domaindef.c:395-453).
+  // Their envelopes feed the length-model chain like any other, so the walk cannot simply skip them: it runs once with every
+  // unresolved multi-domain region taken as one envelope, the Forward matrices of those regions are then filled on the device in
+  // one batch and sampled and clustered here on all cores, and the walk is repeated with the clusters in place -- until it meets
+  // no unresolved region (two passes unless a changed length model moves a later region's borders).
+  struct RegionKey { int sidx, w, i, j; bool operator<(const RegionKey &o) const { return std::tie(sidx, w, i, j) < std::tie(o.sidx, o.w, o.i, o.j); } };
+  std::map<RegionKey, std::vector<std::pair<int, int>>> resolved;
+  const float walk_nj0 = s->om5_nj; const int walk_L0 = s->om5_L;
+  const int64_t walk_regions0 = s->st.n_regions, walk_multi0 = s->st.n_multidomain_regions;
+  // what a window's walk produced for the length model it started from: a repeated pass replays it unless the state differs
+  struct WalkMemo { bool valid = false, had_pending = false; float nj_in = 0, nj_out = 0; int L_in = 0, L_out = 0, nreg = 0, nmulti = 0;
+                    std::vector<bathgpu_envelope> ge; std::vector<Strand::Env> envs; };
+  std::vector<WalkMemo> memo[2];
+  for (int sidx : active) memo[sidx].resize(strands[sidx].fsw.size());
+  for (int walk_pass = 0; ; ++walk_pass) {
+    std::vector<RegionKey> pending;
+    s->om5_nj = walk_nj0; s->om5_L = walk_L0; s->st.n_regions = walk_regions0; s->st.n_multidomain_regions = walk_multi0;
+    for (int sidx : active) { strands[sidx].ge.clear(); strands[sidx].envs.clear(); }
     size_t zpos[2] = { 0, 0 };
     for (size_t b = 0; b < nb; ++b)
       for (int sidx : active) {
@@ -1033,6 +1055,16 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
         for (; zpos[sidx] < S.fsw.size() && S.dwin_blk[S.fsw[zpos[sidx]]] == (int) b; ++zpos[sidx]) {
           const size_t z = zpos[sidx];
           if (S.st2[z] != 0) continue;                      // backward underflow: skip domain definition for this window (:1471)
+          WalkMemo &wm = memo[sidx][z];
+          if (wm.valid && !wm.had_pending && wm.nj_in == s->om5_nj && wm.L_in == s->om5_L) {
+            S.ge.insert(S.ge.end(), wm.ge.begin(), wm.ge.end()); S.envs.insert(S.envs.end(), wm.envs.begin(), wm.envs.end());
+            s->st.n_regions += wm.nreg; s->st.n_multidomain_regions += wm.nmulti;
+            s->om5_nj = wm.nj_out; s->om5_L = wm.L_out;
+            continue;
+          }
+          wm.valid = true; wm.nj_in = s->om5_nj; wm.L_in = s->om5_L;
+          const size_t ge_before = S.ge.size(), pending_before = pending.size();
+          const int64_t nreg_before = s->st.n_regions, nmulti_before = s->st.n_multidomain_regions;
           const int w = S.fsw[z];
           const int Lw = S.dwin[w].length;
           const float tL = 1.0f - (2.0f + s->om5_nj) / ((float) s->om5_L + 2.0f + s->om5_nj);
@@ -1083,21 +1115,73 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
                 scan(i + 2, -1, (j - i + 1) % 3);
                 scan(i + 3, 0, (j - i) % 3);
                 scan(i + 4, 1, (j - i - 1) % 3);
-                if (mx >= rt3) s->st.n_multidomain_regions++;   // rescored as ONE envelope (see the file header)
-                const int Ld = j - i + 1;
-                if (Ld >= 15) {                              // rescore_isolated_domain_frameshift returns at once below 15 (:1012)
+                auto envelope = [&](int i2, int j2) {
+                  const int Ld = j2 - i2 + 1;
+                  if (Ld < 15) return;                       // rescore_isolated_domain_frameshift returns at once below 15 (:1012)
                   bathgpu_envelope g;
-                  g.start = S.gw[w].start + i - 1; g.L = Ld;
+                  g.start = S.gw[w].start + i2 - 1; g.L = Ld;
                   bathhost_length_model(Ld / 3, 0.0f, &g.pmove, &g.ploop);
-                  S.ge.push_back(g); S.envs.push_back(Strand::Env{ w, i, j });
+                  S.ge.push_back(g); S.envs.push_back(Strand::Env{ w, i2, j2 });
                   s->om5_nj = 0.0f; s->om5_L = Ld / 3;       // p7_fs_oprofile_ReconfigLength(om_fs5, Ld/3) (:1018)
+                };
+                const std::vector<std::pair<int, int>> *clusters = nullptr;
+                if (mx >= rt3) {
+                  s->st.n_multidomain_regions++;
+                  const RegionKey key{ sidx, w, i, j };
+                  auto it = resolved.find(key);
+                  if (it != resolved.end()) clusters = &it->second; else pending.push_back(key);
                 }
+                if (clusters) {
+                  s->om5_nj = 0.0f; s->om5_L = saveL;        // ReconfigMultihit(saveL) .. ReconfigUnihit(om_fs5, saveL) (:409,:417)
+                  for (const auto &c2 : *clusters) envelope(std::max(1, c2.first), c2.second);      // (:421-445)
+                } else envelope(i, j);
               }
               i = -1; triggered = false; start = false; end = false;
             }
           }
+          wm.nj_out = s->om5_nj; wm.L_out = s->om5_L; wm.had_pending = pending.size() > pending_before;
+          wm.nreg = (int)(s->st.n_regions - nreg_before); wm.nmulti = (int)(s->st.n_multidomain_regions - nmulti_before);
+          wm.ge.assign(S.ge.begin() + ge_before, S.ge.end()); wm.envs.assign(S.envs.begin() + ge_before, S.envs.end());
         }
       }
+    if (pending.empty()) break;
+    if (walk_pass > 64) return fail(s, BATHHOST_EINVAL, "multi-domain region resolution does not settle");
+    // ---- Forward matrices of the unresolved regions (multihit, target length saveL: :409-412), one device call per strand
+    const float xfE5m[2] = { 0.5f, 0.5f };
+    float mh_pmove, mh_ploop;
+    bathhost_length_model(saveL, 1.0f, &mh_pmove, &mh_ploop);
+    for (int sidx : active) {
+      Strand &S = strands[sidx];
+      std::vector<bathgpu_envelope> regs;
+      std::vector<RegionKey> keys;
+      std::vector<int64_t> off(1, 0);
+      for (const RegionKey &k : pending) if (k.sidx == sidx) {
+        bathgpu_envelope g;
+        g.start = S.gw[k.w].start + k.i - 1; g.L = k.j - k.i + 1; g.pmove = mh_pmove; g.ploop = mh_ploop;
+        regs.push_back(g); keys.push_back(k); off.push_back(off.back() + g.L + 1);
+      }
+      if (regs.empty()) continue;
+      float *mxbuf = s->mxbuf[0].get(s->be, (size_t) off.back() * (M + 1) * 8), *xrbuf = s->mxbuf[1].get(s->be, (size_t) off.back() * 6);
+      if (!mxbuf || !xrbuf) return fail(s, BATHHOST_EMEM, "host allocation failed");
+      std::vector<float> fsc(regs.size());
+      std::vector<int32_t> fst(regs.size());
+      BE_TRY(s, s->be.select_slot(s->be.ctx, sidx), "bathgpu_select_slot");
+      if (!s->be.fs_forward_matrices) return fail(s, BATHHOST_EINVAL, "the device library has no bathgpu_fs_forward_matrices");
+      BE_TRY(s, s->be.fs_forward_matrices(s->be.ctx, regs.data(), (int) regs.size(), xfE5m, mxbuf, xrbuf, off.back(), fsc.data(), fst.data()),
+             "bathgpu_fs_forward_matrices");
+      std::vector<std::vector<std::pair<int, int>>> found(regs.size());
+      const SpecialOdds X{ mh_pmove, mh_ploop, xfE5m[0], xfE5m[1] };
+      parallel_chunks(regs.size(), 1, [&](size_t ra, size_t rb) {
+        for (size_t r = ra; r < rb; ++r) {
+          if (fst[r] != 0) continue;                         // Forward out of range: no clusters (:412-413)
+          const ForwardMatrix F{ mxbuf + (size_t) off[r] * (M + 1) * 8, xrbuf + (size_t) off[r] * 6, M, regs[r].L };
+          std::vector<Segment> sp;
+          if (!sample_region_segments(F, m->om5.tfv.data(), X, kStotraceSeed, kStotraceSamples, keys[r].i, sp)) continue;
+          for (const Segment &g : cluster_region_segments(sp, kStotraceSamples)) found[r].push_back({ g.i, g.j });
+        }
+      });
+      for (size_t r = 0; r < regs.size(); ++r) resolved[keys[r]] = std::move(found[r]);
+    }
   }
   tm.lap(s->st.us_windows);
 

@@ -15,6 +15,7 @@ EXPORTS = [
     "bathhost_orf_length_params", "bathhost_model_computed_max_length",
     "bathhost_search_create", "bathhost_search_destroy", "bathhost_search_last_error", "bathhost_search_sequence",
     "bathhost_search_finish", "bathhost_search_nhits", "bathhost_search_get_hit", "bathhost_search_get_stats",
+    "bathhost_sample_region_segments", "bathhost_cluster_region_segments",
 ]
 
 
@@ -33,7 +34,7 @@ class FilterParams(C.Structure):
 class Backend(C.Structure):
     """bathhost_backend: the device library as a table of function pointers (include/bathhost.h)"""
     _names = ["last_error", "load_fs_profile", "load_filter_profile", "select_slot", "upload_block", "upload_orfs", "msv_orfs", "ssv_windows",
-              "vit_orfs", "fwd_orfs", "fs_fwd_windows", "fs_fwd_bck_xrows", "fs_bck_decode", "fs_domains", "orf_fwd_bck_xrows", "orf_domains", "orfs_msv_screen", "orfs_fetch", "revcomp_slot", "host_alloc", "host_free"]
+              "vit_orfs", "fwd_orfs", "fs_fwd_windows", "fs_fwd_bck_xrows", "fs_bck_decode", "fs_domains", "fs_forward_matrices", "orf_fwd_bck_xrows", "orf_domains", "orfs_msv_screen", "orfs_fetch", "revcomp_slot", "host_alloc", "host_free"]
     _fields_ = [("ctx", C.c_void_p)] + [(n, C.c_void_p) for n in _names]
 
 
@@ -58,6 +59,10 @@ class Stats(C.Structure):
                                          "us_windows", "us_fs_fwd", "us_fs_domains", "us_std", "us_xrows", "us_decode", "us_score")]
 
 
+class Segment(C.Structure):
+    _fields_ = [("idx", C.c_int32), ("i", C.c_int32), ("j", C.c_int32), ("k", C.c_int32), ("m", C.c_int32), ("prob", C.c_float)]
+
+
 _lib = None
 
 
@@ -72,6 +77,11 @@ def load():
     vp, fp, u8p = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint8)
     L.bathhost_model_read.restype = C.c_int
     L.bathhost_model_read.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]
+    L.bathhost_sample_region_segments.restype = C.c_int
+    L.bathhost_sample_region_segments.argtypes = [fp, fp, C.c_int, C.c_int, fp, fp, C.c_uint32, C.c_int, C.c_int, C.POINTER(Segment), C.c_int,
+                                                  C.POINTER(C.c_int)]
+    L.bathhost_cluster_region_segments.restype = C.c_int
+    L.bathhost_cluster_region_segments.argtypes = [C.POINTER(Segment), C.c_int, C.c_int, C.POINTER(Segment), C.c_int, C.POINTER(C.c_int)]
     L.bathhost_model_count.restype = C.c_int
     L.bathhost_model_count.argtypes = [C.c_char_p]
     L.bathhost_model_destroy.restype = None
@@ -290,3 +300,32 @@ class Search:
         s = Stats()
         self.lib.bathhost_search_get_stats(self.h, C.byref(s))
         return {n: getattr(s, n) for n, _ in Stats._fields_}
+
+
+def sample_region_segments(mx, xrows, tfv, odds, ireg, seed=42, nsamples=200):
+    """bathhost_sample_region_segments on one region's Forward matrix mx [(L+1)][(M+1)][8], xrows [(L+1)][6]:
+    list of (idx, i, j, k, m, prob), one per sampled domain"""
+    import numpy as np
+    L = load()
+    mx = np.ascontiguousarray(mx, np.float32); xr = np.ascontiguousarray(xrows, np.float32)
+    tf = np.ascontiguousarray(tfv, np.float32); od = np.ascontiguousarray(odds, np.float32)
+    fp = C.POINTER(C.c_float)
+    cap = nsamples * 64
+    out = (Segment * cap)()
+    n = C.c_int(0)
+    st = L.bathhost_sample_region_segments(mx.ctypes.data_as(fp), xr.ctypes.data_as(fp), mx.shape[1] - 1, mx.shape[0] - 1, tf.ctypes.data_as(fp),
+                                           od.ctypes.data_as(fp), seed, nsamples, ireg, out, cap, C.byref(n))
+    if st != 0:
+        raise RuntimeError(f"bathhost_sample_region_segments: status {st}")
+    return [(g.idx, g.i, g.j, g.k, g.m, g.prob) for g in out[:n.value]]
+
+
+def cluster_region_segments(segments, nsamples=200):
+    L = load()
+    sp = (Segment * max(1, len(segments)))(*[Segment(*g) for g in segments])
+    out = (Segment * 64)()
+    n = C.c_int(0)
+    st = L.bathhost_cluster_region_segments(sp, len(segments), nsamples, out, 64, C.byref(n))
+    if st != 0:
+        raise RuntimeError(f"bathhost_cluster_region_segments: status {st}")
+    return [(g.idx, g.i, g.j, g.k, g.m, g.prob) for g in out[:n.value]]

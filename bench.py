@@ -203,7 +203,7 @@ def search_leg(ctx, model, dsq, mbp, plants):
     search.close()
     return {"metric": "bathsearch --fs Mbp/s", "value": n / dt / 1e6, "unit": "Mbp/s", "seconds": dt, "first_pass_seconds": cold, "target_mbp": n / 1e6,
             "hits": len(hits), "planted": len(planted), "planted_recovered": found, "stats": st,
-            "note": "windows that lose the arbitration go down the standard-translation branch (stats.n_std_windows); multi-domain regions are rescored as one envelope (stats.n_multidomain_regions), stochastic clustering is not restated"}
+            "note": "windows that lose the arbitration go down the standard-translation branch (stats.n_std_windows); multi-domain regions of the frameshift branch (stats.n_multidomain_regions) are split by stochastic-trace clustering: Forward matrix on the device, sampling and clustering on the host"}
 
 
 def search_leg_cpu(model, dsq, mbp, nthreads):

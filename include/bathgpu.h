@@ -17,6 +17,8 @@
  *   bathgpu_fs_domains        <- p7_Forward_Frameshift, p7_Backward_Frameshift, p7_Decoding_Frameshift,
  *                                p7_OptimalAccuracy_Frameshift, p7_OATrace_Frameshift, p7_Null2_fs_ByExpectation
  *                                src/impl_sse/impl_sse.h:497-498,483,523-524,516 (call sites src/p7_domaindef.c:1022-1082)
+ *   bathgpu_fs_forward_matrices <- p7_Forward_Frameshift with the matrix kept for p7_StochasticTrace_Frameshift
+ *                                (call site src/p7_domaindef.c:411-414; the sampling and clustering stay host code)
  *
  * Plain pointers and sizes only.  All functions return an Easel-style status
  * (0 = eslOK); per-item status[] carries eslERANGE (16) exactly where the reference
@@ -212,6 +214,16 @@ int bathgpu_fs_fetch_xrows(bathgpu_ctx *ctx, int which, float *out, int64_t nrow
  * of max_steps steps; results[e].trace_offset/len index into it. */
 int bathgpu_fs_domains(bathgpu_ctx *ctx, const bathgpu_envelope *envs, int n, const float xfE5[2],
                        bathgpu_domain_result *results, bathgpu_trace_step *traces, int64_t max_steps);
+
+/* ---- a16 (device part): the Forward matrix p7_StochasticTrace_Frameshift samples from ------ */
+/* p7_Forward_Frameshift (src/impl_sse/impl_sse.h:497) over regions of the resident block, full matrix handed back as the
+ * call at src/p7_domaindef.c:411-414 leaves it in pli->fwd_fs, un-striped: region r occupies rows off .. off + L of
+ *   mx    [rows][(M+1)][8]  {D, I, M_C0, M_C1 .. M_C5} (impl_sse.h:296-314), node 0 all zero
+ *   xrows [rows][6]         {E, N, J, B, C, SCALE}
+ * with off = sum over earlier regions of (L+1); max_rows = rows the caller allocated.  xfE5 = {E->MOVE, E->LOOP} odds
+ * (multihit: {0.5, 0.5}); the length model of each region is in its descriptor.  status[r] = eslERANGE as the reference. */
+int bathgpu_fs_forward_matrices(bathgpu_ctx *ctx, const bathgpu_envelope *regs, int n, const float xfE5[2],
+                                float *mx, float *xrows, int64_t max_rows, float *fwdsc, int32_t *status);
 
 /* Test/diagnostic: matrices of envelope e of the last chunk of the last bathgpu_fs_domains call, in the
  * reference's cell order: pp [(L+1)][(M+1)][8] {D,I,M_C0..M_C5} (impl_sse.h:296-314; D cells are 0 after

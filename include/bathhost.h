@@ -113,6 +113,8 @@ typedef struct {
   int (*fs_bck_decode)(void *ctx, const void *wins, int n, const float xfE[2], const float xf5_loop[3], const int64_t *out_offset,
                        float *mocc, float *btot, float *etot, float *fwdsc, float *bcksc, int32_t *status);
   int (*fs_domains)(void *ctx, const void *envs, int n, const float xfE5[2], void *results, void *traces, int64_t max_steps);
+  int (*fs_forward_matrices)(void *ctx, const void *regs, int n, const float xfE5[2], float *mx, float *xrows, int64_t max_rows,
+                             float *fwdsc, int32_t *status);
   int (*orf_fwd_bck_xrows)(void *ctx, const void *orfs, int n, float nj, const float xfE[2], float *fwd_xrows, float *bck_xrows,
                            float *fwdsc, float *bcksc, int32_t *status);
   int (*orf_domains)(void *ctx, const void *envs, int n, const float xfE[2], void *results, void *traces, int64_t max_steps);
@@ -154,6 +156,16 @@ typedef struct {
   /* wall time per stage of the host pipeline, microseconds (host work + the device calls made from it) */
   int64_t us_orfs, us_upload, us_msv, us_bias, us_vit, us_fwd, us_windows, us_fs_fwd, us_fs_domains, us_std, us_xrows, us_decode, us_score;
 } bathhost_stats;
+
+/* ---- multi-domain regions (stotrace.cpp): p7_StochasticTrace_Frameshift x nsamples reduced to domain end points
+ * (src/impl_sse/stotrace_fs.c:72; region_trace_ensemble_frameshift, src/p7_domaindef.c:892-954), then p7_spensemble_fs_Cluster
+ * and the removal of dominated clusters (src/p7_spensemble.c:498; src/p7_domaindef.c:923-952).
+ * mx / xrows: one region of bathgpu_fs_forward_matrices' output; tfv [8][M+1] odds {BM,MM,IM,DM,MD,MI,II,DD};
+ * odds = {N/J/C->MOVE, N/J/C->LOOP, E->MOVE, E->LOOP}; segments come back in window coordinates (ireg = region start). */
+typedef struct { int32_t idx, i, j, k, m; float prob; } bathhost_segment;
+int bathhost_sample_region_segments(const float *mx, const float *xrows, int M, int L, const float *tfv, const float odds[4],
+                                    uint32_t seed, int nsamples, int ireg, bathhost_segment *out, int max_out, int *nout);
+int bathhost_cluster_region_segments(const bathhost_segment *sp, int n, int nsamples, bathhost_segment *out, int max_out, int *nout);
 
 typedef struct bathhost_search bathhost_search;
 int  bathhost_search_create(const bathhost_model *m, const bathhost_backend *be, const bathhost_options *opt, bathhost_search **ret);

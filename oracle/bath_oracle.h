@@ -275,6 +275,18 @@ int bo_DomainDecoding_Frameshift(const float xf_loop_NJC[3], const BO_MX *oxf, c
 int bo_OptimalAccuracy_Frameshift(const BO_FS_OPROFILE *om, const BO_MX *pp, BO_MX *ox, float *ret_e);
 int bo_OATrace_Frameshift(const BO_FS_OPROFILE *om, const BO_MX *pp, const BO_MX *ox, BO_TRACE *tr);
 
+/* ===== fs_stotrace.c (impl_sse/stotrace_fs.c, p7_spensemble.c, p7_domaindef.c:892-954) ===== */
+typedef struct { uint32_t seed, x; } BO_RNG;                         /* Easel's fast generator (esl_randomness_CreateFast) */
+typedef struct { int idx, i, j, k, m; float prob; } BO_SEGMENT;      /* struct p7_spcoord_s */
+void   bo_rng_init(BO_RNG *r, uint32_t seed);
+double bo_random(BO_RNG *r);
+int bo_StochasticTrace_Frameshift(BO_RNG *rng, int L, const BO_FS_OPROFILE *om, const BO_MX *ox, BO_TRACE *tr);
+int bo_trace_fs_Index(const BO_TRACE *tr, BO_SEGMENT *seg, int max_seg);
+int bo_spensemble_fs_Cluster(const BO_SEGMENT *sp, int n, int nsamples, float min_overlap, int of_smaller, int max_diagdiff,
+                             float min_posterior, float min_endpointp, BO_SEGMENT *out, int max_out);
+int bo_region_trace_ensemble_frameshift(const BO_FS_OPROFILE *om, const BO_MX *fwd, int ireg, int jreg, uint32_t seed, int nsamples,
+                                        BO_SEGMENT *samples, int max_samples, int *ret_nsamples, BO_SEGMENT *out, int max_out);
+
 /* ===== fs_null2.c (impl_sse/null2_fs.c) ===== */
 int bo_Null2_fs_ByExpectation(const BO_FS_OPROFILE *om, BO_MX *pp, float *null2 /* [Kp] */);
 

@@ -362,6 +362,45 @@ int bo_backend_fs_domains(void *ctx, const void *envs, int n, const float xfE5[2
   return rc;
 }
 
+/* ---- Forward matrices of multi-domain regions, for the host's stochastic traceback ---- */
+typedef struct { const bathgpu_envelope *e; const float *xfE5; float *mx, *xr, *sc; int32_t *st; const int64_t *off; } fmx_args;
+
+static void fmx_item(bo_backend *b, void *arg, int i)
+{
+  fmx_args *a = arg;
+  const bathgpu_envelope *e = &a->e[i];
+  BO_FS_OPROFILE om = *b->om5;
+  int L = e->L, M = om.M;
+  uint8_t *sub = malloc((size_t) L + 2);
+  BO_MX *fwd = bo_mx_create(M, L, 8);
+  sub[0] = sub[L + 1] = BO_DSQ_SENTINEL;
+  memcpy(sub + 1, b->dsq[b->cur] + e->start, (size_t) L);
+  om.xf[BO_X_N][BO_O_LOOP] = om.xf[BO_X_C][BO_O_LOOP] = om.xf[BO_X_J][BO_O_LOOP] = e->ploop;
+  om.xf[BO_X_N][BO_O_MOVE] = om.xf[BO_X_C][BO_O_MOVE] = om.xf[BO_X_J][BO_O_MOVE] = e->pmove;
+  om.xf[BO_X_E][BO_O_MOVE] = a->xfE5[0]; om.xf[BO_X_E][BO_O_LOOP] = a->xfE5[1];
+  a->sc[i] = 0.0f;
+  a->st[i] = bo_Forward_Frameshift(sub, L, &om, fwd, &a->sc[i]);
+  memcpy(a->mx + (size_t) a->off[i] * (M + 1) * 8, fwd->dp, sizeof(float) * (size_t)(L + 1) * (M + 1) * 8);
+  memcpy(a->xr + (size_t) a->off[i] * 6, fwd->xmx, sizeof(float) * 6 * (size_t)(L + 1));
+  bo_mx_destroy(fwd); free(sub);
+}
+
+int bo_backend_fs_forward_matrices(void *ctx, const void *regs, int n, const float xfE5[2], float *mx, float *xrows, int64_t max_rows,
+                                   float *fwdsc, int32_t *status)
+{
+  bo_backend *b = ctx;
+  const bathgpu_envelope *e = regs;
+  int64_t *off = malloc(sizeof(int64_t) * (size_t)(n + 1));
+  fmx_args a = { e, xfE5, mx, xrows, fwdsc, status, off };
+  int i;
+  off[0] = 0;
+  for (i = 0; i < n; i++) off[i + 1] = off[i] + e[i].L + 1;
+  if (off[n] > max_rows) { free(off); snprintf(b->err, sizeof b->err, "matrix buffer too small"); return BO_EINVAL; }
+  parallel_for(b, n, fmx_item, &a);
+  free(off);
+  return BO_OK;
+}
+
 /* ---- standard-translation branch (orf_domain.c) ---- */
 typedef struct { const bathgpu_orf *orfs; float nj; const float *xfE; float *fsc, *bsc; int32_t *st; float *fx, *bx; const int64_t *xoff; } orfx_args;
 

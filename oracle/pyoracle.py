@@ -83,6 +83,10 @@ class MX(C.Structure):
                 ("has_own_scales", C.c_int)]
 
 
+class SEGMENT(C.Structure):
+    _fields_ = [("idx", C.c_int), ("i", C.c_int), ("j", C.c_int), ("k", C.c_int), ("m", C.c_int), ("prob", C.c_float)]
+
+
 class TRACE(C.Structure):
     _fields_ = [("N", C.c_int), ("nalloc", C.c_int), ("M", C.c_int), ("L", C.c_int),
                 ("st", C.POINTER(C.c_char)), ("k", C.POINTER(C.c_int)), ("i", C.POINTER(C.c_int)),
@@ -184,6 +188,8 @@ def lib(native=False):
         "bo_aa_digitize": (C.c_int, [C.c_char]),
         "bo_dna_revcomp": (None, [u8p, C.c_int64]),
         "bo_gencode_basic": (u8p, [C.c_int]),
+        "bo_region_trace_ensemble_frameshift": (C.c_int, [P(FS_OPROFILE), P(MX), C.c_int, C.c_int, C.c_uint32, C.c_int,
+                                                          P(SEGMENT), C.c_int, P(C.c_int), P(SEGMENT), C.c_int]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -355,6 +361,19 @@ def cpu_backend(nthreads=1):
                 pass
 
     return be, _Handle(h)
+
+
+def region_trace_ensemble(om_fs5, fwd, ireg, jreg, seed=42, nsamples=200):
+    """region_trace_ensemble_frameshift on a filled multihit Forward matrix: (sampled segments, consensus envelopes), each a list
+    of (idx, i, j, k, m, prob)"""
+    cap = nsamples * 64
+    sp, out = (SEGMENT * cap)(), (SEGMENT * 64)()
+    nsp = C.c_int(0)
+    nc = lib().bo_region_trace_ensemble_frameshift(om_fs5, fwd, ireg, jreg, seed, nsamples, sp, cap, C.byref(nsp), out, 64)
+    if nc < 0:
+        raise RuntimeError("stochastic traceback failed")
+    as_t = lambda g: (g.idx, g.i, g.j, g.k, g.m, g.prob)
+    return [as_t(sp[z]) for z in range(nsp.value)], [as_t(out[z]) for z in range(nc)]
 
 
 def mx_xmx(mx):
