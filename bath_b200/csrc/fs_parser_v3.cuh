@@ -31,9 +31,9 @@ __device__ __forceinline__ void fwd_row_compute(int i, int lane, FwdState<J> &S,
   float es0 = 0.f, es1 = 0.f;
 #pragma unroll
   for (int j = 0; j < J; ++j) {
-    float t = S.W[P0][j] * e2[j];
+    float t = S.W[P2][j] * e4[j];              // W[P0] was finished last (by row i-2): its term closes the chain (+1-3 %)
     t = fmaf(S.W[P1][j], e3[j], t);
-    t = fmaf(S.W[P2][j], e4[j], t);
+    t = fmaf(S.W[P0][j], e2[j], t);
     m[j] = t;
     if (j == 0) es0 = t; else if (j == 1) es1 = t; else if (j & 1) es1 += t; else es0 += t;
   }

@@ -366,6 +366,15 @@ def main():
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     per_gpu_cells_s = cells_local * args.steps / (dev_ms * 1e-3)
     achieved_tf = FLOP_PER_CELL * per_gpu_cells_s / 1e12
+    # DRAM traffic of one launch of the dominant kernel from the committed ncu --set full capture of this same workload
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "forward_traffic.json")))
+        if tr.get("profile_M") == M and tr.get("windows") == nwin:
+            traffic = {"bytes_per_launch": tr["dram_bytes_read"] + tr["dram_bytes_write"], "dram_bytes_read": tr["dram_bytes_read"],
+                       "dram_bytes_write": tr["dram_bytes_write"], "source": tr["source"]}
+    except (OSError, ValueError, KeyError):
+        pass
     alg_bytes = float(lengths.astype(np.int64).sum()) / 2 + nwin * (24 + 8)      # packed DNA in, descriptors in, score+status out
     out = {
         "metric": "frameshift Forward GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
@@ -377,7 +386,7 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
-                     "frac": achieved_tf / fp32_peak, "traffic": None,
+                     "frac": achieved_tf / fp32_peak, "traffic": traffic,
                      "kernel": "fs3_forward_parser_kernel", "flop_per_cell": FLOP_PER_CELL,
                      "peak_source": f"FFMA probe in this process ({eff_mhz:.0f} MHz effective x 148 SM x 128 lanes x 2)",
                      "hbm": {"achieved": alg_bytes * args.steps / (dev_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
