@@ -305,34 +305,42 @@ extern "C" int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int n
   {
     std::vector<float> cc((size_t)(FC_COUNT * J + FL_COUNT) * 32, 0.0f);
     auto C = [&](int which_c, int j, int lane) -> float & { return cc[(size_t)(which_c * J + j) * 32 + lane]; };
-    std::vector<double> bfull(32, 1.0);
+    // The delete chain is carried divided by g(k), g(k+1) = md(k) = tMD(k) / Z(k), g(1) = 1 (fs_parser.cuh, FwdConsts): the
+    // match term then enters it with coefficient 1.  A node that no delete path leaves (tMD = 0; no shipped model has one
+    // before node M) takes a vanishing md instead, which leaves a 1e-20 relative trace in D and keeps the scaled form finite.
+    auto mdK = [&](int k) -> double { return std::max(T(tMD, k) / zK[k], 1.0e-20); };
+    auto gK  = [&](int k) -> double { return (k >= 2 && k <= M) ? mdK(k - 1) : 1.0; };
+    auto ddS = [&](int k) -> double { return (k >= 1 && k < M) ? gK(k) * T(tDD, k) / mdK(k) : 0.0; };
+    std::vector<double> bfull(32, 1.0), bscaled(32, 1.0);
     for (int lane = 0; lane < 32; ++lane) {
-      double pp = 1.0;
+      double pp = 1.0, ps = 1.0;
       for (int j = 0; j < J; ++j) {
         int k = lane * J + j + 1;
         if (k <= M) {
           double sn = sK[k + 1];      // s(k+1); 1.0 at k = M where every outgoing transition is 0
           C(FC_MM, j, lane) = (float)(T(tMM, k) / (zK[k] * sn));
-          C(FC_DM, j, lane) = (float)(T(tDM, k) / sn);
-          C(FC_MD, j, lane) = (float)(T(tMD, k) / zK[k]);
-          C(FC_DD, j, lane) = (float)T(tDD, k);
+          C(FC_DM, j, lane) = (float)(gK(k) * T(tDM, k) / sn);
+          C(FC_MD, j, lane) = (float)(T(tMD, k) / zK[k]);          // not read by the kernels any more; kept for the layout
+          C(FC_DD, j, lane) = (float)ddS(k);
           C(FC_MI, j, lane) = (float)(T(tMI, k) * T(tIM, k) / (zK[k] * sn));
           C(FC_II, j, lane) = (float)T(tII, k);
         }
         pp *= T(tDD, k);
+        ps *= ddS(k);
       }
-      bfull[lane] = pp;
+      bfull[lane] = pp; bscaled[lane] = ps;
     }
-    std::vector<double> b(bfull);
+    std::vector<double> b(bfull), bs(bscaled);
     im.scan_steps = 5;
     for (int s = 0; s < 5; ++s) {
       int d = 1 << s;
-      std::vector<double> nb(b);
+      std::vector<double> nb(b), nbs(bs);
       double biggest = 0.0;
       for (int lane = 0; lane < 32; ++lane) {
-        cc[(size_t)(FC_COUNT * J + FL_B0 + s) * 32 + lane] = (lane >= d) ? (float)b[lane] : 0.0f;
-        if (lane >= d) { biggest = std::max(biggest, b[lane]); nb[lane] = b[lane] * b[lane - d]; }
+        cc[(size_t)(FC_COUNT * J + FL_B0 + s) * 32 + lane] = (lane >= d) ? (float)bs[lane] : 0.0f;
+        if (lane >= d) { biggest = std::max(biggest, b[lane]); nb[lane] = b[lane] * b[lane - d]; nbs[lane] = bs[lane] * bs[lane - d]; }
       }
+      bs.swap(nbs);
       // step s carries D in from 2^s lanes away with these multipliers: below 1e-9 everywhere it (and every later step) changes
       // nothing at float resolution -- the cut-off the reference's own D->D passes apply (fwdback_fs.c:415-453)
       if (biggest < 1.0e-9 && im.scan_steps == 5) im.scan_steps = std::max(s, 2);

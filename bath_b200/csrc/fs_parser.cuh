@@ -108,11 +108,13 @@ struct FwdState {
 
 // Per-node constants with the entry odds s(k) and the E weights Z(k) folded in (see bathgpu.cu):
 //   table T[c][k] = R[c][k] s(k) Z(k)  =>  sum_c W T = M(i,k) Z(k) =: Mz
-//   mm = tMM(k) / (Z(k) s(k+1)),  dm = tDM(k) / s(k+1),  md = tMD(k) / Z(k),  dd = tDD(k),
-//   mi = tMI(k) tIM(k) / (Z(k) s(k+1)),  ii = tII(k)
+//   mm = tMM(k) / (Z(k) s(k+1)),  mi = tMI(k) tIM(k) / (Z(k) s(k+1)),  ii = tII(k)
+// The delete chain D(k+1) = D(k) tDD(k) + Mz(k) md(k), md(k) = tMD(k) / Z(k), is carried as Dg(k) = D(k) / g(k) with
+// g(k+1) = md(k) (g(1) = 1), so that the match term enters with coefficient 1 and needs no multiply of its own:
+//   Dg(k+1) = Dg(k) dd(k) + Mz(k),   dd(k) = g(k) tDD(k) / md(k),   dm(k) = g(k) tDM(k) / s(k+1)
 template <int J>
 struct FwdConsts {
-  float mm[J], dm[J], md[J], dd[J], mi[J], ii[J];
+  float mm[J], dm[J], dd[J], mi[J], ii[J];
   float bs[5];
 };
 
@@ -144,12 +146,11 @@ __device__ __forceinline__ void fwd_row(int i, int lane, FwdState<J> &S, const F
   }
   float xE = warp_allsum(J > 1 ? es0 + es1 : es0);
 
-  // D chain (:415-453): a(k) = M(k) tMD(k); lane carry-out with zero carry-in, warp scan of carries,
+  // D chain (:415-453), in the scaled form of FwdConsts: lane carry-out with zero carry-in, warp scan of carries,
   // then the lane re-runs the recurrence from its true carry-in.
-  float a[J];
   float A = 0.f;
 #pragma unroll
-  for (int j = 0; j < J; ++j) { a[j] = m[j] * K.md[j]; A = (j == 0) ? a[0] : fmaf(A, K.dd[j], a[j]); }
+  for (int j = 0; j < J; ++j) A = (j == 0) ? m[0] : fmaf(A, K.dd[j], m[j]);
 #pragma unroll
   for (int s = 0; s < 5; ++s) {
     float up = __shfl_up_sync(0xffffffffu, A, 1 << s);
@@ -172,7 +173,7 @@ __device__ __forceinline__ void fwd_row(int i, int lane, FwdState<J> &S, const F
   for (int j = 0; j < J; ++j) {
     float t = fmaf(m[j], K.mm[j], S.I[P0][j]);
     o[j] = fmaf(d, K.dm[j], t);
-    if (j + 1 < J) d = fmaf(d, K.dd[j], a[j]);
+    if (j + 1 < J) d = fmaf(d, K.dd[j], m[j]);
     S.I[P1][j] = fmaf(S.I[P0][j], K.ii[j], m[j] * K.mi[j]);     // slot (i+3)&3 == (i-1)&3
   }
   float oprev = __shfl_up_sync(0xffffffffu, o[J - 1], 1);
@@ -214,7 +215,6 @@ __device__ __forceinline__ void load_fwd_consts(const float *__restrict__ cc, in
   for (int j = 0; j < J; ++j) {
     K.mm[j] = __ldg(cc + (FC_MM * J + j) * kWarp + lane);
     K.dm[j] = __ldg(cc + (FC_DM * J + j) * kWarp + lane);
-    K.md[j] = __ldg(cc + (FC_MD * J + j) * kWarp + lane);
     K.dd[j] = __ldg(cc + (FC_DD * J + j) * kWarp + lane);
     K.mi[j] = __ldg(cc + (FC_MI * J + j) * kWarp + lane);
     K.ii[j] = __ldg(cc + (FC_II * J + j) * kWarp + lane);
@@ -396,10 +396,9 @@ __global__ void __launch_bounds__(32) orf_forward_parser_kernel(OrfFwdArgs a)
       for (int j = 0; j < J; ++j) { m[j] = W[j] * e[j]; es += m[j]; }
       float xE = warp_allsum(es);
 
-      float av[J];
       float A = 0.f;
 #pragma unroll
-      for (int j = 0; j < J; ++j) { av[j] = m[j] * K.md[j]; A = (j == 0) ? av[0] : fmaf(A, K.dd[j], av[j]); }
+      for (int j = 0; j < J; ++j) A = (j == 0) ? m[0] : fmaf(A, K.dd[j], m[j]);
 #pragma unroll
       for (int s = 0; s < 5; ++s) {
         float up = __shfl_up_sync(full, A, 1 << s);
@@ -418,7 +417,7 @@ __global__ void __launch_bounds__(32) orf_forward_parser_kernel(OrfFwdArgs a)
       for (int j = 0; j < J; ++j) {
         float t = fmaf(m[j], K.mm[j], It[j]);
         ov[j] = fmaf(d, K.dm[j], t);
-        if (j + 1 < J) d = fmaf(d, K.dd[j], av[j]);
+        if (j + 1 < J) d = fmaf(d, K.dd[j], m[j]);
         It[j] = fmaf(It[j], K.ii[j], m[j] * K.mi[j]);
       }
       float oprev = __shfl_up_sync(full, ov[J - 1], 1);

@@ -39,10 +39,9 @@ __device__ __forceinline__ void fwd_row_compute(int i, int lane, FwdState<J> &S,
   }
   float xE = warp_allsum(J > 1 ? es0 + es1 : es0);
 
-  float a[J];
   float A = 0.f;
 #pragma unroll
-  for (int j = 0; j < J; ++j) { a[j] = m[j] * K.md[j]; A = (j == 0) ? a[0] : fmaf(A, K.dd[j], a[j]); }
+  for (int j = 0; j < J; ++j) A = (j == 0) ? m[0] : fmaf(A, K.dd[j], m[j]);   // scaled delete chain: the match term needs no multiply
 #pragma unroll
   for (int s = 0; s < NS; ++s) {                 // NS < 5: the products of D->D odds over 2^NS lanes are below 1e-9 for this profile
     float up = __shfl_up_sync(0xffffffffu, A, 1 << s);
@@ -61,7 +60,7 @@ __device__ __forceinline__ void fwd_row_compute(int i, int lane, FwdState<J> &S,
   for (int j = 0; j < J; ++j) {
     float t = fmaf(m[j], K.mm[j], S.I[P0][j]);
     o[j] = fmaf(d, K.dm[j], t);
-    if (j + 1 < J) d = fmaf(d, K.dd[j], a[j]);
+    if (j + 1 < J) d = fmaf(d, K.dd[j], m[j]);
     S.I[P1][j] = fmaf(S.I[P0][j], K.ii[j], m[j] * K.mi[j]);
   }
   float oprev = __shfl_up_sync(0xffffffffu, o[J - 1], 1);
@@ -130,7 +129,14 @@ __device__ __forceinline__ void fwd_row_pair(int i, int lane, FwdState<J> &S, co
 
 #ifndef BATHGPU_V3_WARPS
 // resident warps per SM the kernel is compiled for (register budget 65536/(32 n)); measured on B200 per J
-#define BATHGPU_V3_WARPS(J) ((J) <= 2 ? 20 : (J) == 3 ? 18 : (J) == 4 ? 16 : (J) == 5 ? 14 : (J) == 6 ? 11 : (J) == 7 ? 10 : (J) == 8 ? 9 : 8)
+// (J = 6: a budget of 13 makes ptxas settle on 128 registers without spilling, 16 resident warps: +2.7 % over 152 registers / 12 warps;
+//  J = 5, 8, 10 pushed the same way spill and lose 15-20 %)
+#define BATHGPU_V3_WARPS(J) ((J) <= 2 ? 20 : (J) == 3 ? 18 : (J) == 4 ? 16 : (J) == 5 ? 14 : (J) == 6 ? 13 : (J) == 7 ? 10 : (J) == 8 ? 9 : 8)
+#endif
+
+#ifndef BATHGPU_V3_RESIDENT
+// resident warps per SM the launch aims for (the grid is sized to it; kernels_tu.cu): no cap until measured otherwise
+#define BATHGPU_V3_RESIDENT(J) 64
 #endif
 
 template <int J, bool XMX, int NS = 5>

@@ -1,6 +1,7 @@
 // kernels_tu.cu -- template instantiations of one kernel family for one set of node counts (see launch.h).
 // Compiled once per -DBATHGPU_FAMILY=<n> -DBATHGPU_SET=<n> combination by bath_b200/build.py.
 #include <algorithm>
+#include <cstdlib>
 #include "launch.h"
 #include "fs_parser.cuh"
 #include "fs_parser_v3.cuh"
@@ -51,12 +52,23 @@ template <class K> static int grid_for(K kernel, int threads, size_t smem, int n
 }
 
 #if BATHGPU_FAMILY == FAM_FWD
+// resident one-warp blocks per SM of the row-pair Forward kernel: what fits, capped at the measured optimum for this J
+// (BATHGPU_V3_RESIDENT in fs_parser_v3.cuh; BATHGPU_FWD_WARPS overrides it for tuning runs)
+template <class K> static int fwd_grid(K kernel, int J, int n, int sms)
+{
+  static const int env_cap = [] { const char *e = getenv("BATHGPU_FWD_WARPS"); return e ? atoi(e) : 0; }();
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 32, 0);
+  const int cap = env_cap > 0 ? env_cap : BATHGPU_V3_RESIDENT(J);
+  return std::max(1, std::min(n, sms * std::max(1, std::min(nb, cap))));
+}
+
 template <int J, bool XMX> static cudaError_t run_fwd(int version, const FsParserArgs &a, int sms, cudaStream_t s)
 {
   if (version >= 3) {
-    if (a.scan_steps <= 2)      fs3_forward_parser_kernel_v3<J, XMX, 2><<<grid_for(fs3_forward_parser_kernel_v3<J, XMX, 2>, 32, 0, a.nwin, sms), 32, 0, s>>>(a);
-    else if (a.scan_steps == 3) fs3_forward_parser_kernel_v3<J, XMX, 3><<<grid_for(fs3_forward_parser_kernel_v3<J, XMX, 3>, 32, 0, a.nwin, sms), 32, 0, s>>>(a);
-    else                        fs3_forward_parser_kernel_v3<J, XMX, 5><<<grid_for(fs3_forward_parser_kernel_v3<J, XMX, 5>, 32, 0, a.nwin, sms), 32, 0, s>>>(a);
+    if (a.scan_steps <= 2)      fs3_forward_parser_kernel_v3<J, XMX, 2><<<fwd_grid(fs3_forward_parser_kernel_v3<J, XMX, 2>, J, a.nwin, sms), 32, 0, s>>>(a);
+    else if (a.scan_steps == 3) fs3_forward_parser_kernel_v3<J, XMX, 3><<<fwd_grid(fs3_forward_parser_kernel_v3<J, XMX, 3>, J, a.nwin, sms), 32, 0, s>>>(a);
+    else                        fs3_forward_parser_kernel_v3<J, XMX, 5><<<fwd_grid(fs3_forward_parser_kernel_v3<J, XMX, 5>, J, a.nwin, sms), 32, 0, s>>>(a);
   }
   else fs3_forward_parser_kernel<J, XMX><<<grid_for(fs3_forward_parser_kernel<J, XMX>, FwdTune<J>::kThreads, 0, a.nwin, sms), FwdTune<J>::kThreads, 0, s>>>(a);
   return cudaGetLastError();
