@@ -46,6 +46,7 @@ struct DevBuf {
 struct FsProfileImage {
   int   which = 0, M = 0, nrows = 0, J = 0, mpad = 0, scan_steps = 5;
   DevBuf emis;     // [nrows][mpad]
+  DevBuf emis_fwd; // [nrows][mpad] the Forward parsers' copy: match->match odds folded in as well (fs_parser.cuh, FwdConsts)
   DevBuf cellc;    // forward lane constants
   DevBuf cellb;    // backward lane constants
   DevBuf cellf5;   // 5-codon full-matrix Forward lane constants (fs_domain.cuh)
@@ -140,7 +141,7 @@ extern "C" void bathgpu_destroy(bathgpu_ctx *ctx)
   cudaStreamSynchronize(ctx->stream);
   for (FsProfileImage *im : { &ctx->fs3, &ctx->fs5 }) {
     im->emis.release(); im->cellc.release(); im->cellb.release(); im->cellf5.release(); im->amino.release();
-    im->oaflags.release(); im->oapass.release(); im->tfvraw.release(); im->zinv.release();
+    im->oaflags.release(); im->oapass.release(); im->tfvraw.release(); im->zinv.release(); im->emis_fwd.release();
   }
   for (TargetSlot &t : ctx->slot) { t.dna_bytes.release(); t.dna4.release(); t.residues.release(); }
   ctx->wins.release(); ctx->fwdsc.release();
@@ -305,24 +306,37 @@ extern "C" int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int n
   {
     std::vector<float> cc((size_t)(FC_COUNT * J + FL_COUNT) * 32, 0.0f);
     auto C = [&](int which_c, int j, int lane) -> float & { return cc[(size_t)(which_c * J + j) * 32 + lane]; };
-    // The delete chain is carried divided by g(k), g(k+1) = md(k) = tMD(k) / Z(k), g(1) = 1 (fs_parser.cuh, FwdConsts): the
-    // match term then enters it with coefficient 1.  A node that no delete path leaves (tMD = 0; no shipped model has one
-    // before node M) takes a vanishing md instead, which leaves a 1e-20 relative trace in D and keeps the scaled form finite.
-    auto mdK = [&](int k) -> double { return std::max(T(tMD, k) / zK[k], 1.0e-20); };
+    // Scaled forms of the Forward parsers (fs_parser.cuh, FwdConsts): the table copy they read carries mm(k) too, and the
+    // delete and insert chains are divided by g(k) and hi(k) so that the match value enters every chain with coefficient 1.
+    // Divisors that vanish take tiny stand-ins: node M has no way out (mm := 1, its flow is never read); a node no delete or
+    // insert path leaves (no shipped model has one before node M) leaves a relative trace of 1e-20 or less.
+    auto mmK = [&](int k) -> double {
+      if (k >= M) return 1.0;
+      const double v = T(tMM, k) / (zK[k] * sK[k + 1]);
+      return v > 0.0 ? v : 1.0e-12;
+    };
+    auto mdK = [&](int k) -> double { return std::max(T(tMD, k) / (zK[k] * mmK(k)), 1.0e-20); };
     auto gK  = [&](int k) -> double { return (k >= 2 && k <= M) ? mdK(k - 1) : 1.0; };
     auto ddS = [&](int k) -> double { return (k >= 1 && k < M) ? gK(k) * T(tDD, k) / mdK(k) : 0.0; };
     std::vector<double> bfull(32, 1.0), bscaled(32, 1.0);
+    std::vector<float> ef((size_t)nrows * mpad, 0.0f);
+    for (int c = 0; c < nrows; ++c)
+      for (int k = 1; k <= M; ++k)
+        ef[(size_t)c * mpad + perm_index(k - 1, J)] = (float)((double)rfv[(size_t)c * ld + k] * sK[k] * zK[k] * mmK(k));
+    if (im.emis_fwd.reserve(ef.size() * sizeof(float)) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
+    CUDA_TRY(ctx, cudaMemcpyAsync(im.emis_fwd.p, ef.data(), ef.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     for (int lane = 0; lane < 32; ++lane) {
       double pp = 1.0, ps = 1.0;
       for (int j = 0; j < J; ++j) {
         int k = lane * J + j + 1;
         if (k <= M) {
           double sn = sK[k + 1];      // s(k+1); 1.0 at k = M where every outgoing transition is 0
-          C(FC_MM, j, lane) = (float)(T(tMM, k) / (zK[k] * sn));
+          C(FC_MM, j, lane) = (float)(1.0 / mmK(k));                                                         // qm
           C(FC_DM, j, lane) = (float)(gK(k) * T(tDM, k) / sn);
           C(FC_MD, j, lane) = (float)(T(tMD, k) / zK[k]);          // not read by the kernels any more; kept for the layout
           C(FC_DD, j, lane) = (float)ddS(k);
-          C(FC_MI, j, lane) = (float)(T(tMI, k) * T(tIM, k) / (zK[k] * sn));
+          C(FC_MI, j, lane) = (float)std::max(T(tMI, k) * T(tIM, k) / (zK[k] * sn * mmK(k)), 1.0e-20);      // hi
           C(FC_II, j, lane) = (float)T(tII, k);
         }
         pp *= T(tDD, k);
@@ -648,7 +662,7 @@ extern "C" int bathgpu_fs_fwd_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_
     if (launches == 1) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev0, 0));    // descriptors and counters are set on the first stream
     CUDA_TRY(ctx, cudaStreamWaitEvent(s, pack_ev[c], 0));
     FsParserArgs a{};
-    a.emis = im.emis.as<float>(); a.cellc = im.cellc.as<float>(); a.dna4 = S.dna4.as<uint32_t>();
+    a.emis = im.emis_fwd.as<float>(); a.cellc = im.cellc.as<float>(); a.dna4 = S.dna4.as<uint32_t>();
     a.wins = ctx->wins.as<WindowDesc>() + w0; a.nwin = w1 - w0; a.mpad = im.mpad; a.tEM = xfE[0]; a.tEL = xfE[1];
     a.fwdsc = ctx->fwdsc.as<float>() + w0; a.status = ctx->status.as<int>() + w0; a.xmx = nullptr; a.xoff = nullptr;
     a.counter = ctx->counter.as<int>() + launches; a.scan_steps = im.scan_steps;
@@ -726,7 +740,7 @@ extern "C" int bathgpu_fs_fwd_staged(bathgpu_ctx *ctx, const float xfE[2])
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   const FsProfileImage &im = ctx->fs3;
   FsParserArgs a{};
-  a.emis = im.emis.as<float>(); a.cellc = im.cellc.as<float>(); a.dna4 = ctx->S().dna4.as<uint32_t>();
+  a.emis = im.emis_fwd.as<float>(); a.cellc = im.cellc.as<float>(); a.dna4 = ctx->S().dna4.as<uint32_t>();
   a.wins = ctx->wins.as<WindowDesc>(); a.nwin = ctx->nstaged; a.mpad = im.mpad;
   a.tEM = xfE[0]; a.tEL = xfE[1];
   a.fwdsc = ctx->fwdsc.as<float>(); a.status = ctx->status.as<int>();
@@ -802,7 +816,7 @@ static int bck_decode_chunk(bathgpu_ctx *ctx, const bathgpu_window *wins, int n,
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
 
   FsParserArgs fa{};
-  fa.emis = im.emis.as<float>(); fa.cellc = im.cellc.as<float>(); fa.dna4 = ctx->S().dna4.as<uint32_t>();
+  fa.emis = im.emis_fwd.as<float>(); fa.cellc = im.cellc.as<float>(); fa.dna4 = ctx->S().dna4.as<uint32_t>();
   fa.wins = ctx->wins.as<WindowDesc>(); fa.nwin = n; fa.mpad = im.mpad; fa.tEM = xfE[0]; fa.tEL = xfE[1];
   fa.fwdsc = ctx->fwdsc.as<float>(); fa.status = ctx->status.as<int>();
   fa.xmx = ctx->fxmx.as<float>(); fa.xoff = ctx->xoff.as<long long>(); fa.counter = ctx->counter.as<int>(); fa.scan_steps = im.scan_steps;
@@ -810,7 +824,7 @@ static int bck_decode_chunk(bathgpu_ctx *ctx, const bathgpu_window *wins, int n,
   CUDA_TRY(ctx, dispatch_fwd(true, im.J, fa, sms, ctx->stream));
 
   FsBackwardArgs ba{};
-  ba.emis = fa.emis; ba.cellb = im.cellb.as<float>(); ba.dna4 = fa.dna4; ba.wins = fa.wins; ba.nwin = n; ba.mpad = im.mpad;
+  ba.emis = im.emis.as<float>(); ba.cellb = im.cellb.as<float>(); ba.dna4 = fa.dna4; ba.wins = fa.wins; ba.nwin = n; ba.mpad = im.mpad;
   ba.tEM = xfE[0]; ba.tEL = xfE[1]; ba.fxmx = ctx->fxmx.as<float>(); ba.bxmx = ctx->bxmx.as<float>(); ba.xoff = fa.xoff;
   ba.bcksc = ctx->bcksc.as<float>(); ba.status = fa.status; ba.counter = fa.counter;
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
@@ -1415,7 +1429,7 @@ extern "C" int bathgpu_fwd_orfs(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
   const FsProfileImage &im = ctx->fs3;
   OrfFwdArgs a{};
-  a.emis = im.emis.as<float>(); a.cellc = im.cellc.as<float>(); a.residues = ctx->S().residues.as<uint8_t>();
+  a.emis = im.emis_fwd.as<float>(); a.cellc = im.cellc.as<float>(); a.residues = ctx->S().residues.as<uint8_t>();
   a.orfs = ctx->orfs.p; a.orf_stride = (int)sizeof(OrfDesc); a.norf = n; a.mpad = im.mpad; a.nj = nj;
   a.tEM = xfE[0]; a.tEL = xfE[1]; a.fwdsc = ctx->fsc.as<float>(); a.status = ctx->fst.as<int>(); a.counter = ctx->counter.as<int>();
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));

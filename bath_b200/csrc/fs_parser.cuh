@@ -102,19 +102,26 @@ __device__ __forceinline__ uint32_t fetch_quad(const uint32_t *__restrict__ dna4
 template <int J>
 struct FwdState {
   float W[4][J];       // W(r)[k] = V(r)[k] / s(k), s(k) = tBM(k-1), in slot r&3   (V = the reference's IVX)
-  float I[4][J];       // I~(r)[k] = I(r,k) tIM(k) / s(k+1) in slot r&3
+  float I[4][J];       // Ih(r)[k] = I(r,k) tIM(k) / (s(k+1) hi(k)) in slot r&3 (FwdConsts)
   float xN[4], xJ[4], xC[4];
 };
 
-// Per-node constants with the entry odds s(k) and the E weights Z(k) folded in (see bathgpu.cu):
-//   table T[c][k] = R[c][k] s(k) Z(k)  =>  sum_c W T = M(i,k) Z(k) =: Mz
-//   mm = tMM(k) / (Z(k) s(k+1)),  mi = tMI(k) tIM(k) / (Z(k) s(k+1)),  ii = tII(k)
-// The delete chain D(k+1) = D(k) tDD(k) + Mz(k) md(k), md(k) = tMD(k) / Z(k), is carried as Dg(k) = D(k) / g(k) with
-// g(k+1) = md(k) (g(1) = 1), so that the match term enters with coefficient 1 and needs no multiply of its own:
-//   Dg(k+1) = Dg(k) dd(k) + Mz(k),   dd(k) = g(k) tDD(k) / md(k),   dm(k) = g(k) tDM(k) / s(k+1)
+// Per-node constants.  The Forward parsers read their own copy of the emission table (FsProfileImage::emis_fwd) with the entry
+// odds s(k) = tBM(k-1), the E weight Z(k) and the match->match odds folded in:
+//   T[c][k] = R[c][k] s(k) Z(k) mm(k),  mm(k) = tMM(k) / (Z(k) s(k+1))   =>   sum_c W T = Mq := M(i,k) Z(k) mm(k)
+// so that the flow into node k+1 takes Mq with coefficient 1, and the other two chains are carried divided by whatever makes
+// Mq enter them with coefficient 1 as well -- no chain multiplies the match value:
+//   E(i)          = sum_k Mq qm,                 qm = 1 / mm(k)                       (an FMA where a plain sum would need an add)
+//   Dg(k) = D(k) / g(k),  g(k+1) = tMD(k) / (Z(k) mm(k)),  g(1) = 1:
+//   Dg(k+1)       = Dg(k) dd + Mq,               dd = g(k) tDD(k) / g(k+1)
+//   Ih(k) = I(k) tIM(k) / (s(k+1) hi),           hi = tMI(k) tIM(k) / tMM(k):
+//   Ih(i+3,k)     = Ih(i,k) ii + Mq,             ii = tII(k)
+//   flow(k)       = Mq + Ih hi + Dg dm,          dm = g(k) tDM(k) / s(k+1)
+// 10 floating-point instructions per cell against 12 with every transition applied where the reference applies it.
+// Node M (no way out) and nodes with a vanishing tMM / tMD / tMI take tiny stand-ins for the divisors (bathgpu.cu).
 template <int J>
 struct FwdConsts {
-  float mm[J], dm[J], dd[J], mi[J], ii[J];
+  float qm[J], dm[J], dd[J], hi[J], ii[J];
   float bs[5];
 };
 
@@ -142,7 +149,7 @@ __device__ __forceinline__ void fwd_row(int i, int lane, FwdState<J> &S, const F
     t = fmaf(S.W[P1][j], e3[j], t);
     t = fmaf(S.W[P2][j], e4[j], t);
     m[j] = t;
-    if (j == 0) es0 = t; else if (j == 1) es1 = t; else if (j & 1) es1 += t; else es0 += t;
+    if (j == 0) es0 = t * K.qm[0]; else if (j == 1) es1 = t * K.qm[1]; else if (j & 1) es1 = fmaf(t, K.qm[j], es1); else es0 = fmaf(t, K.qm[j], es0);
   }
   float xE = warp_allsum(J > 1 ? es0 + es1 : es0);
 
@@ -171,10 +178,10 @@ __device__ __forceinline__ void fwd_row(int i, int lane, FwdState<J> &S, const F
   float o[J];
 #pragma unroll
   for (int j = 0; j < J; ++j) {
-    float t = fmaf(m[j], K.mm[j], S.I[P0][j]);
+    float t = fmaf(S.I[P0][j], K.hi[j], m[j]);
     o[j] = fmaf(d, K.dm[j], t);
     if (j + 1 < J) d = fmaf(d, K.dd[j], m[j]);
-    S.I[P1][j] = fmaf(S.I[P0][j], K.ii[j], m[j] * K.mi[j]);     // slot (i+3)&3 == (i-1)&3
+    S.I[P1][j] = fmaf(S.I[P0][j], K.ii[j], m[j]);               // slot (i+3)&3 == (i-1)&3
   }
   float oprev = __shfl_up_sync(0xffffffffu, o[J - 1], 1);
   if (lane == 0) oprev = 0.f;
@@ -213,10 +220,10 @@ __device__ __forceinline__ void load_fwd_consts(const float *__restrict__ cc, in
 {
 #pragma unroll
   for (int j = 0; j < J; ++j) {
-    K.mm[j] = __ldg(cc + (FC_MM * J + j) * kWarp + lane);
+    K.qm[j] = __ldg(cc + (FC_MM * J + j) * kWarp + lane);
     K.dm[j] = __ldg(cc + (FC_DM * J + j) * kWarp + lane);
     K.dd[j] = __ldg(cc + (FC_DD * J + j) * kWarp + lane);
-    K.mi[j] = __ldg(cc + (FC_MI * J + j) * kWarp + lane);
+    K.hi[j] = __ldg(cc + (FC_MI * J + j) * kWarp + lane);
     K.ii[j] = __ldg(cc + (FC_II * J + j) * kWarp + lane);
   }
 #pragma unroll
@@ -393,7 +400,7 @@ __global__ void __launch_bounds__(32) orf_forward_parser_kernel(OrfFwdArgs a)
       load_emission_row<J, VEC>(emis_lane + (size_t)x * a.mpad, e);
       float es = 0.f;
 #pragma unroll
-      for (int j = 0; j < J; ++j) { m[j] = W[j] * e[j]; es += m[j]; }
+      for (int j = 0; j < J; ++j) { m[j] = W[j] * e[j]; es = fmaf(m[j], K.qm[j], es); }
       float xE = warp_allsum(es);
 
       float A = 0.f;
@@ -415,10 +422,10 @@ __global__ void __launch_bounds__(32) orf_forward_parser_kernel(OrfFwdArgs a)
       float ov[J];
 #pragma unroll
       for (int j = 0; j < J; ++j) {
-        float t = fmaf(m[j], K.mm[j], It[j]);
+        float t = fmaf(It[j], K.hi[j], m[j]);
         ov[j] = fmaf(d, K.dm[j], t);
         if (j + 1 < J) d = fmaf(d, K.dd[j], m[j]);
-        It[j] = fmaf(It[j], K.ii[j], m[j] * K.mi[j]);
+        It[j] = fmaf(It[j], K.ii[j], m[j]);
       }
       float oprev = __shfl_up_sync(full, ov[J - 1], 1);
       if (lane == 0) oprev = 0.f;

@@ -35,7 +35,7 @@ __device__ __forceinline__ void fwd_row_compute(int i, int lane, FwdState<J> &S,
     t = fmaf(S.W[P1][j], e3[j], t);
     t = fmaf(S.W[P0][j], e2[j], t);
     m[j] = t;
-    if (j == 0) es0 = t; else if (j == 1) es1 = t; else if (j & 1) es1 += t; else es0 += t;
+    if (j == 0) es0 = t * K.qm[0]; else if (j == 1) es1 = t * K.qm[1]; else if (j & 1) es1 = fmaf(t, K.qm[j], es1); else es0 = fmaf(t, K.qm[j], es0);
   }
   float xE = warp_allsum(J > 1 ? es0 + es1 : es0);
 
@@ -58,10 +58,10 @@ __device__ __forceinline__ void fwd_row_compute(int i, int lane, FwdState<J> &S,
   float o[J];
 #pragma unroll
   for (int j = 0; j < J; ++j) {
-    float t = fmaf(m[j], K.mm[j], S.I[P0][j]);
+    float t = fmaf(S.I[P0][j], K.hi[j], m[j]);
     o[j] = fmaf(d, K.dm[j], t);
     if (j + 1 < J) d = fmaf(d, K.dd[j], m[j]);
-    S.I[P1][j] = fmaf(S.I[P0][j], K.ii[j], m[j] * K.mi[j]);
+    S.I[P1][j] = fmaf(S.I[P0][j], K.ii[j], m[j]);
   }
   float oprev = __shfl_up_sync(0xffffffffu, o[J - 1], 1);
   if (lane == 0) oprev = 0.f;
