@@ -317,7 +317,8 @@ extern "C" int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int n
     };
     auto mdK = [&](int k) -> double { return std::max(T(tMD, k) / (zK[k] * mmK(k)), 1.0e-20); };
     auto gK  = [&](int k) -> double { return (k >= 2 && k <= M) ? mdK(k - 1) : 1.0; };
-    auto ddS = [&](int k) -> double { return (k >= 1 && k < M) ? gK(k) * T(tDD, k) / mdK(k) : 0.0; };
+    // node 1 has no delete state (D(i,1) = 0): its dd and dm are 0, which also cancels whatever lane 0 is handed as inflow
+    auto ddS = [&](int k) -> double { return (k >= 2 && k < M) ? gK(k) * T(tDD, k) / mdK(k) : 0.0; };
     std::vector<double> bfull(32, 1.0), bscaled(32, 1.0);
     std::vector<float> ef((size_t)nrows * mpad, 0.0f);
     for (int c = 0; c < nrows; ++c)
@@ -333,7 +334,7 @@ extern "C" int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int n
         if (k <= M) {
           double sn = sK[k + 1];      // s(k+1); 1.0 at k = M where every outgoing transition is 0
           C(FC_MM, j, lane) = (float)(1.0 / mmK(k));                                                         // qm
-          C(FC_DM, j, lane) = (float)(gK(k) * T(tDM, k) / sn);
+          C(FC_DM, j, lane) = (k >= 2) ? (float)(gK(k) * T(tDM, k) / sn) : 0.0f;
           C(FC_MD, j, lane) = (float)(T(tMD, k) / zK[k]);          // not read by the kernels any more; kept for the layout
           C(FC_DD, j, lane) = (float)ddS(k);
           C(FC_MI, j, lane) = (float)std::max(T(tMI, k) * T(tIM, k) / (zK[k] * sn * mmK(k)), 1.0e-20);      // hi

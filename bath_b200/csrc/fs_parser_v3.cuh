@@ -17,7 +17,9 @@ namespace bathgpu {
 struct RowOut { float xE, xN, xJ, xC, xB, scale; };
 
 // Row i without the rescale test and without the X-row store.
-template <int J, int VEC, int PH, int NS>
+// HEAD: the row may be one of the first rows of the window (pad rows i < 0, rows 0..2 where N is held at 1); only the first
+// 32 rows of a window run the instantiation that tests for it.
+template <int J, int VEC, int PH, int NS, bool HEAD>
 __device__ __forceinline__ void fwd_row_compute(int i, int lane, FwdState<J> &S, const FwdConsts<J> &K,
                                                 const char *__restrict__ emis_lane, unsigned rowbytes, uint32_t cw,
                                                 float ploop, float pmove, float tEL, float tEM, RowOut &R)
@@ -47,10 +49,10 @@ __device__ __forceinline__ void fwd_row_compute(int i, int lane, FwdState<J> &S,
     float up = __shfl_up_sync(0xffffffffu, A, 1 << s);
     A = fmaf(K.bs[s], up, A);
   }
-  float d = __shfl_up_sync(0xffffffffu, A, 1);
-  if (lane == 0) d = 0.f;
+  float d = __shfl_up_sync(0xffffffffu, A, 1);      // lane 0 reads its own A: node 1 has no delete state, its dd and dm are 0 (bathgpu.cu)
 
-  float xN = (i < 3) ? ((i >= 0) ? 1.0f : 0.0f) : S.xN[P3] * ploop;
+  float xN = S.xN[P3] * ploop;
+  if constexpr (HEAD) xN = (i < 3) ? ((i >= 0) ? 1.0f : 0.0f) : xN;
   float xJ = fmaf(S.xJ[P3], ploop, xE * tEL);
   float xC = fmaf(S.xC[P3], ploop, xE * tEM);
   float xB = fmaf(xJ, pmove, xN * pmove);
@@ -64,7 +66,7 @@ __device__ __forceinline__ void fwd_row_compute(int i, int lane, FwdState<J> &S,
     S.I[P1][j] = fmaf(S.I[P0][j], K.ii[j], m[j]);
   }
   float oprev = __shfl_up_sync(0xffffffffu, o[J - 1], 1);
-  if (lane == 0) oprev = 0.f;
+  if (lane == 0) oprev = 0.f;                       // a select: a 0/1 lane constant in an FMA costs a register the J = 6 kernel lacks
   S.W[P2][0] = xB + oprev;
 #pragma unroll
   for (int j = 1; j < J; ++j) S.W[P2][j] = xB + o[j - 1];
@@ -97,16 +99,16 @@ __device__ __forceinline__ void store_xrow(int i, int lane, const RowOut &R, flo
 }
 
 // Rows i (phase PH) and i+1 (phase PH+1) in one block, then the rescale logic for both in order.
-template <int J, int VEC, int PH, bool XMX, int NS>
+template <int J, int VEC, int PH, bool XMX, int NS, bool HEAD>
 __device__ __forceinline__ void fwd_row_pair(int i, int lane, FwdState<J> &S, const FwdConsts<J> &K,
                                              const char *__restrict__ emis_lane, unsigned rowbytes, uint32_t cwA, uint32_t cwB,
                                              float ploop, float pmove, float tEL, float tEM,
                                              float &totscale, float *__restrict__ xrow)
 {
   RowOut A, B;
-  fwd_row_compute<J, VEC, PH, NS>(i, lane, S, K, emis_lane, rowbytes, cwA, ploop, pmove, tEL, tEM, A);
-  fwd_row_compute<J, VEC, PH + 1, NS>(i + 1, lane, S, K, emis_lane, rowbytes, cwB, ploop, pmove, tEL, tEM, B);
-  if (A.xE > 1.0e4f || B.xE > 1.0e4f) {          // rare, warp-uniform
+  fwd_row_compute<J, VEC, PH, NS, HEAD>(i, lane, S, K, emis_lane, rowbytes, cwA, ploop, pmove, tEL, tEM, A);
+  fwd_row_compute<J, VEC, PH + 1, NS, HEAD>(i + 1, lane, S, K, emis_lane, rowbytes, cwB, ploop, pmove, tEL, tEM, B);
+  if (__builtin_expect(A.xE > 1.0e4f || B.xE > 1.0e4f, 0)) {          // rare, warp-uniform
     if (A.xE > 1.0e4f) {
       const float sf = 1.0f / A.xE;
       scale_state<J>(S, sf);                     // includes what row i+1 has just written
@@ -177,20 +179,26 @@ __global__ void __launch_bounds__(32, BATHGPU_V3_WARPS(J)) fs3_forward_parser_ke
     uint32_t lo = __ldg(a.dna4 + (nib >> 3)), hi = __ldg(a.dna4 + (nib >> 3) + 1);
     int i = -pad;
 
-    for (int q0 = 0; q0 < nq; q0 += 8) {
-      const uint32_t cwl = codon_word(lo, hi, (int)(nib & 7) * 4, i + lane, L);
-      nib += 32;
-      if (q0 + 8 < nq) { lo = __ldg(a.dna4 + (nib >> 3)); hi = __ldg(a.dna4 + (nib >> 3) + 1); }
-      const int qn = min(8, nq - q0);
-      for (int qq = 0; qq < qn; ++qq) {
-        const uint32_t c0 = __shfl_sync(0xffffffffu, cwl, qq * 4 + 0);
-        const uint32_t c1 = __shfl_sync(0xffffffffu, cwl, qq * 4 + 1);
-        const uint32_t c2 = __shfl_sync(0xffffffffu, cwl, qq * 4 + 2);
-        const uint32_t c3 = __shfl_sync(0xffffffffu, cwl, qq * 4 + 3);
-        fwd_row_pair<J, VEC, 0, XMX, NS>(i, lane, S, K, emis_lane, rowbytes, c0, c1, ploop, pmove, a.tEL, a.tEM, totscale, xrow); i += 2;
-        fwd_row_pair<J, VEC, 2, XMX, NS>(i, lane, S, K, emis_lane, rowbytes, c2, c3, ploop, pmove, a.tEL, a.tEM, totscale, xrow); i += 2;
-      }
+    // 32 rows per chunk: lane l prepares the codon word of row i + l; the first chunk runs the HEAD instantiation
+#define BATHGPU_V3_CHUNK(HEAD_)                                                                                                   \
+    {                                                                                                                             \
+      const uint32_t cwl = codon_word(lo, hi, (int)(nib & 7) * 4, i + lane, L);                                                   \
+      nib += 32;                                                                                                                  \
+      if (q0 + 8 < nq) { lo = __ldg(a.dna4 + (nib >> 3)); hi = __ldg(a.dna4 + (nib >> 3) + 1); }                                  \
+      const int qn = min(8, nq - q0);                                                                                             \
+      for (int qq = 0; qq < qn; ++qq) {                                                                                           \
+        const uint32_t c0 = __shfl_sync(0xffffffffu, cwl, qq * 4 + 0);                                                            \
+        const uint32_t c1 = __shfl_sync(0xffffffffu, cwl, qq * 4 + 1);                                                            \
+        const uint32_t c2 = __shfl_sync(0xffffffffu, cwl, qq * 4 + 2);                                                            \
+        const uint32_t c3 = __shfl_sync(0xffffffffu, cwl, qq * 4 + 3);                                                            \
+        fwd_row_pair<J, VEC, 0, XMX, NS, HEAD_>(i, lane, S, K, emis_lane, rowbytes, c0, c1, ploop, pmove, a.tEL, a.tEM, totscale, xrow); i += 2; \
+        fwd_row_pair<J, VEC, 2, XMX, NS, HEAD_>(i, lane, S, K, emis_lane, rowbytes, c2, c3, ploop, pmove, a.tEL, a.tEM, totscale, xrow); i += 2; \
+      }                                                                                                                           \
     }
+    int q0 = 0;
+    BATHGPU_V3_CHUNK(true)
+    for (q0 = 8; q0 < nq; q0 += 8) BATHGPU_V3_CHUNK(false)
+#undef BATHGPU_V3_CHUNK
 
     {
       float tot = S.xC[3] + S.xC[2] * ploop + S.xC[1] * ploop;
