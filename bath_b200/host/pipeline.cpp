@@ -1039,35 +1039,35 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
   std::map<RegionKey, std::vector<std::pair<int, int>>> resolved;
   const float walk_nj0 = s->om5_nj; const int walk_L0 = s->om5_L;
   const int64_t walk_regions0 = s->st.n_regions, walk_multi0 = s->st.n_multidomain_regions;
-  // what a window's walk produced for the length model it started from: a repeated pass replays it unless the state differs
-  struct WalkMemo { bool valid = false, had_pending = false; float nj_in = 0, nj_out = 0; int L_in = 0, L_out = 0, nreg = 0, nmulti = 0;
-                    std::vector<bathgpu_envelope> ge; std::vector<Strand::Env> envs; };
+  // What a window's walk produces is a function of the length model it starts from (it enters only through the loop odds of the
+  // decoding) and of the clusters known so far: envelopes, the length model it leaves behind, counters, unresolved regions.
+  // That makes the chain speculative-parallel: every window is walked on all cores from a guessed input, the outputs are
+  // chained, and whatever started from a wrong input is walked again -- until every window has been walked from the state its
+  // predecessor really leaves, which is the sequential result.  Region borders hardly ever move with the loop odds, so this
+  // settles in two or three rounds.
+  struct WalkMemo { bool valid = false; float nj_in = 0, nj_out = 0; int L_in = 0, L_out = 0, nreg = 0, nmulti = 0;
+                    std::vector<bathgpu_envelope> ge; std::vector<Strand::Env> envs; std::vector<RegionKey> pend; };
   std::vector<WalkMemo> memo[2];
   for (int sidx : active) memo[sidx].resize(strands[sidx].fsw.size());
-  for (int walk_pass = 0; ; ++walk_pass) {
-    std::vector<RegionKey> pending;
-    s->om5_nj = walk_nj0; s->om5_L = walk_L0; s->st.n_regions = walk_regions0; s->st.n_multidomain_regions = walk_multi0;
-    for (int sidx : active) { strands[sidx].ge.clear(); strands[sidx].envs.clear(); }
+  struct WalkItem { int sidx; size_t z; };
+  std::vector<WalkItem> worder;                               // the reference's order: block, then strand, then window
+  {
     size_t zpos[2] = { 0, 0 };
     for (size_t b = 0; b < nb; ++b)
       for (int sidx : active) {
         Strand &S = strands[sidx];
-        for (; zpos[sidx] < S.fsw.size() && S.dwin_blk[S.fsw[zpos[sidx]]] == (int) b; ++zpos[sidx]) {
-          const size_t z = zpos[sidx];
-          if (S.st2[z] != 0) continue;                      // backward underflow: skip domain definition for this window (:1471)
-          WalkMemo &wm = memo[sidx][z];
-          if (wm.valid && !wm.had_pending && wm.nj_in == s->om5_nj && wm.L_in == s->om5_L) {
-            S.ge.insert(S.ge.end(), wm.ge.begin(), wm.ge.end()); S.envs.insert(S.envs.end(), wm.envs.begin(), wm.envs.end());
-            s->st.n_regions += wm.nreg; s->st.n_multidomain_regions += wm.nmulti;
-            s->om5_nj = wm.nj_out; s->om5_L = wm.L_out;
-            continue;
-          }
-          wm.valid = true; wm.nj_in = s->om5_nj; wm.L_in = s->om5_L;
-          const size_t ge_before = S.ge.size(), pending_before = pending.size();
-          const int64_t nreg_before = s->st.n_regions, nmulti_before = s->st.n_multidomain_regions;
+        for (; zpos[sidx] < S.fsw.size() && S.dwin_blk[S.fsw[zpos[sidx]]] == (int) b; ++zpos[sidx])
+          if (S.st2[zpos[sidx]] == 0) worder.push_back(WalkItem{ sidx, zpos[sidx] });   // backward underflow: no domain definition (:1471)
+      }
+  }
+  auto walk_window = [&](int sidx, size_t z, float nj_in, int L_in, WalkMemo &wm) {
+    Strand &S = strands[sidx];
+    wm.valid = true; wm.nj_in = nj_in; wm.L_in = L_in; wm.nreg = 0; wm.nmulti = 0;
+    wm.ge.clear(); wm.envs.clear(); wm.pend.clear();
+    float om5_nj = nj_in; int om5_L = L_in;
           const int w = S.fsw[z];
           const int Lw = S.dwin[w].length;
-          const float tL = 1.0f - (2.0f + s->om5_nj) / ((float) s->om5_L + 2.0f + s->om5_nj);
+          const float tL = 1.0f - (2.0f + om5_nj) / ((float) om5_L + 2.0f + om5_nj);
           // mocc[i] = 1 - sum over N,J,C and the three codon offsets of fwd * bck * loop odds * scale (decoding_fs.c:309-352)
           const Decoded &D = dec[sidx][z];
           const std::vector<float> &btot = D.btot, &etot = D.etot;
@@ -1082,7 +1082,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
             }
             mocc[i] = 1. - njcp;
           }
-          s->om5_nj = 0.0f; s->om5_L = saveL / 3;           // p7_fs_oprofile_ReconfigUnihit(om_fs5, saveL/3) (:325)
+          om5_nj = 0.0f; om5_L = saveL / 3;                 // p7_fs_oprofile_ReconfigUnihit(om_fs5, saveL/3) (:325)
           // region finding (src/p7_domaindef.c:332-383)
           int i = -1, d = 0; bool triggered = false, start = false, end = false;
           for (int j = 1; j < Lw; ++j) {
@@ -1104,7 +1104,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
               }
               j = std::min(Lw, d + 3);
               if (j - i + 1 >= 12) {
-                s->st.n_regions++;
+                wm.nreg++;
                 float mx = -1.0f;                           // is_multidomain_region_frameshift (:684-714)
                 auto scan = [&](int z0, int eoff, int f) {
                   for (int zz = z0; zz <= j - f; zz += 3) {
@@ -1121,29 +1121,50 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
                   bathgpu_envelope g;
                   g.start = S.gw[w].start + i2 - 1; g.L = Ld;
                   bathhost_length_model(Ld / 3, 0.0f, &g.pmove, &g.ploop);
-                  S.ge.push_back(g); S.envs.push_back(Strand::Env{ w, i2, j2 });
-                  s->om5_nj = 0.0f; s->om5_L = Ld / 3;       // p7_fs_oprofile_ReconfigLength(om_fs5, Ld/3) (:1018)
+                  wm.ge.push_back(g); wm.envs.push_back(Strand::Env{ w, i2, j2 });
+                  om5_nj = 0.0f; om5_L = Ld / 3;             // p7_fs_oprofile_ReconfigLength(om_fs5, Ld/3) (:1018)
                 };
                 const std::vector<std::pair<int, int>> *clusters = nullptr;
                 if (mx >= rt3) {
-                  s->st.n_multidomain_regions++;
+                  wm.nmulti++;
                   const RegionKey key{ sidx, w, i, j };
                   auto it = resolved.find(key);
-                  if (it != resolved.end()) clusters = &it->second; else pending.push_back(key);
+                  if (it != resolved.end()) clusters = &it->second; else wm.pend.push_back(key);
                 }
                 if (clusters) {
-                  s->om5_nj = 0.0f; s->om5_L = saveL;        // ReconfigMultihit(saveL) .. ReconfigUnihit(om_fs5, saveL) (:409,:417)
+                  om5_nj = 0.0f; om5_L = saveL;              // ReconfigMultihit(saveL) .. ReconfigUnihit(om_fs5, saveL) (:409,:417)
                   for (const auto &c2 : *clusters) envelope(std::max(1, c2.first), c2.second);      // (:421-445)
                 } else envelope(i, j);
               }
               i = -1; triggered = false; start = false; end = false;
             }
           }
-          wm.nj_out = s->om5_nj; wm.L_out = s->om5_L; wm.had_pending = pending.size() > pending_before;
-          wm.nreg = (int)(s->st.n_regions - nreg_before); wm.nmulti = (int)(s->st.n_multidomain_regions - nmulti_before);
-          wm.ge.assign(S.ge.begin() + ge_before, S.ge.end()); wm.envs.assign(S.envs.begin() + ge_before, S.envs.end());
-        }
+    wm.nj_out = om5_nj; wm.L_out = om5_L;
+  };
+  static const bool walk_sequential = getenv("BATHHOST_SEQUENTIAL_WALK") != nullptr;
+  for (int walk_pass = 0; ; ++walk_pass) {
+    for (int round = 0; ; ++round) {
+      std::vector<size_t> todo;
+      float nj = walk_nj0; int L = walk_L0;
+      for (size_t t = 0; t < worder.size(); ++t) {
+        WalkMemo &wm = memo[worder[t].sidx][worder[t].z];
+        if (!wm.valid || wm.nj_in != nj || wm.L_in != L) { todo.push_back(t); wm.nj_in = nj; wm.L_in = L; }
+        if (wm.valid) { nj = wm.nj_out; L = wm.L_out; } else { nj = 0.0f; L = saveL / 3; }   // first round: a guess for the successor
       }
+      if (todo.empty()) break;
+      if (walk_sequential) todo.resize(1);                    // test hook: one window per round from its true input = the plain sequential walk
+      if (round > (int) worder.size() + 2) return fail(s, BATHHOST_EINVAL, "the region walk does not settle");
+      parallel_chunks(todo.size(), 4, [&](size_t ta, size_t tb) {
+        for (size_t q = ta; q < tb; ++q) {
+          const WalkItem &it = worder[todo[q]];
+          WalkMemo &wm = memo[it.sidx][it.z];
+          walk_window(it.sidx, it.z, wm.nj_in, wm.L_in, wm);
+        }
+      });
+    }
+    std::vector<RegionKey> pending;
+    for (const WalkItem &it : worder) { const WalkMemo &wm = memo[it.sidx][it.z]; pending.insert(pending.end(), wm.pend.begin(), wm.pend.end()); }
+    for (const WalkItem &it : worder) { WalkMemo &wm = memo[it.sidx][it.z]; if (!wm.pend.empty()) wm.valid = false; }   // walked again once resolved
     if (pending.empty()) break;
     if (walk_pass > 64) return fail(s, BATHHOST_EINVAL, "multi-domain region resolution does not settle");
     // ---- Forward matrices of the unresolved regions (multihit, target length saveL: :409-412), one device call per strand
@@ -1182,6 +1203,15 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
       });
       for (size_t r = 0; r < regs.size(); ++r) resolved[keys[r]] = std::move(found[r]);
     }
+  }
+  s->st.n_regions = walk_regions0; s->st.n_multidomain_regions = walk_multi0;
+  for (int sidx : active) { strands[sidx].ge.clear(); strands[sidx].envs.clear(); }
+  for (const WalkItem &it : worder) {
+    const WalkMemo &wm = memo[it.sidx][it.z];
+    Strand &S = strands[it.sidx];
+    S.ge.insert(S.ge.end(), wm.ge.begin(), wm.ge.end()); S.envs.insert(S.envs.end(), wm.envs.begin(), wm.envs.end());
+    s->st.n_regions += wm.nreg; s->st.n_multidomain_regions += wm.nmulti;
+    s->om5_nj = wm.nj_out; s->om5_L = wm.L_out;
   }
   tm.lap(s->st.us_windows);
 

@@ -144,3 +144,49 @@ def test_fs_pipeline_keeps_unshifted_hits(oracle):
     f = [l.split() for l in open(common.golden("PTH2.tbl")) if not l.startswith("#")][0]
     assert st["n_std_windows"] == 1 and len(hits) == 4
     assert _row(hits[0]) == (int(f[6]), int(f[7]), int(f[9]), int(f[10]), f"{float(f[11]):.2g}", f[12], f[13]) and hits[0]["cigar"] == f[15]
+
+
+def test_speculative_region_walk_equals_the_sequential_walk(oracle):
+    """The region walk chains the length model from window to window (src/p7_domaindef.c:320-325, :1018).  The host pipeline walks
+    all windows in parallel from guessed inputs and repeats what started from a wrong one; BATHHOST_SEQUENTIAL_WALK forces one
+    window per round from its true input.  Both must give the same hits, envelope for envelope, on a target with many windows
+    (planted homologs, some back to back so that the multi-domain branch is in the chain as well)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, json, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import common
+from oracle import pyoracle as oracle
+from bath_b200 import hostapi
+om = oracle.Model(common.golden("AMP_N.bhmm"))
+mat = common.hmm_mat(om)
+rng = np.random.default_rng(3)
+parts = []
+for t in range(14):
+    parts.append(rng.integers(0, 4, int(rng.integers(300, 2500))).astype(np.uint8))
+    parts.append(common.sample_homolog(rng, mat, fs_rate=0.02, stop_rate=0.002))
+    if t %% 4 == 1:
+        parts.append(common.sample_homolog(rng, mat, fs_rate=0.01, stop_rate=0.0))
+body = np.concatenate(parts)
+dsq = np.full(len(body) + 2, 255, np.uint8); dsq[1:-1] = body
+be, keep = oracle.cpu_backend(4)
+search = hostapi.Search(hostapi.QueryModel(common.golden("AMP_N.bhmm")), backend=be, block_length=4000)
+search.add_sequence("many", dsq)
+hits = search.finish(); st = search.stats(); search.close()
+print(json.dumps({"hits": [[h["ali_from"], h["ali_to"], h["env_from"], h["env_to"], h["hmm_from"], h["hmm_to"], h["cigar"], "%%.6g" %% h["evalue"]] for h in hits],
+                  "stats": {k: st[k] for k in ("n_windows", "n_regions", "n_multidomain_regions", "n_envelopes")}}))
+''' % (root, os.path.join(root, "tests"))
+    runs = []
+    for seq in (False, True):
+        env = dict(os.environ)
+        env.pop("BATHHOST_SEQUENTIAL_WALK", None)
+        if seq:
+            env["BATHHOST_SEQUENTIAL_WALK"] = "1"
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        runs.append(__import__("json").loads(out.stdout.strip().splitlines()[-1]))
+    assert runs[0] == runs[1]
+    assert runs[0]["stats"]["n_windows"] >= 10 and runs[0]["stats"]["n_multidomain_regions"] >= 1 and len(runs[0]["hits"]) >= 14
