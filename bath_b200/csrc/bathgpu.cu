@@ -978,7 +978,8 @@ static int domains_chunk(bathgpu_ctx *ctx, const bathgpu_envelope *envs, int n, 
 
   if (ctx->envs.reserve((size_t)n * sizeof(EnvelopeDesc)) != BATHGPU_OK || ctx->xoff.reserve((size_t)(n + 1) * 8) != BATHGPU_OK ||
       ctx->dtoff.reserve((size_t)(n + 1) * 8) != BATHGPU_OK || ctx->dtlen.reserve((size_t)n * 4) != BATHGPU_OK ||
-      ctx->dpp.reserve(rows * kPPCells * mpad * 4) != BATHGPU_OK || ctx->doa.reserve(rows * kOACells * mpad * 4) != BATHGPU_OK ||
+      ctx->dpp.reserve((rows + 1) * kPPCells * mpad * 4) != BATHGPU_OK ||        /* + 1: the optimal-accuracy sweep prefetches one row ahead */
+      ctx->doa.reserve(rows * kOACells * mpad * 4) != BATHGPU_OK ||
       ctx->dfx.reserve(rows * 24) != BATHGPU_OK || ctx->dppx.reserve(rows * 24) != BATHGPU_OK || ctx->doax.reserve(rows * 24) != BATHGPU_OK ||
       ctx->dlsf.reserve(rows * 4) != BATHGPU_OK || ctx->dfw.reserve((size_t)n * 4) != BATHGPU_OK || ctx->dbk.reserve((size_t)n * 4) != BATHGPU_OK ||
       ctx->doasc.reserve((size_t)n * 4) != BATHGPU_OK || ctx->dnull2.reserve((size_t)n * 29 * 4) != BATHGPU_OK ||

@@ -131,6 +131,18 @@ __device__ __forceinline__ uint32_t nuc_codes5(const uint32_t *__restrict__ dna4
   return out;
 }
 
+// Pull the lines of one stored matrix row (ncell cells of mpad floats) towards L1 ahead of the sweep that will read it: these
+// sweeps are one warp per envelope walking rows one after the other, so a row's loads are otherwise a full DRAM round trip on the
+// critical path (the matrices of a batch of envelopes are far larger than L2).
+__device__ __forceinline__ void prefetch_matrix_row(const float *row_base, int ncell, int mpad, int lane)
+{
+#ifndef BATHGPU_NO_ROW_PREFETCH
+  const char *p = reinterpret_cast<const char *>(row_base);
+  const int nbytes = ncell * mpad * 4;
+  for (int off = lane * 128; off < nbytes; off += 32 * 128) asm volatile("prefetch.global.L1 [%0];" :: "l"(p + off));
+#endif
+}
+
 template <int J>
 struct Fwd5Consts { float mm[J], im[J], dm[J], md[J], dd[J], mi[J], ii[J]; float bs[5]; };
 
@@ -361,6 +373,7 @@ __device__ __forceinline__ void bck5_row(int i, int lane, Bck5State<J> &S, const
   constexpr int S0 = PH, S1 = (PH + 1) % 5, S2 = (PH + 2) % 5, S3 = (PH + 3) % 5, S4 = (PH + 4) % 5;   // rows i(=i+5), i+1, .., i+4
   const int L = R.L;
   if (i > L) return;
+  if (i >= 1) prefetch_matrix_row(pprow_lane - lane * VEC + (size_t)(i - 1) * kPPCells * mpad, kPPCells, mpad, lane);   // the row this sweep reads next
 
   float xN, xJ, xC, xB, xE;
   const float fscale = fxrow[(size_t)i * 6 + 5];
@@ -657,6 +670,7 @@ __device__ __forceinline__ void oa_row(int i, int lane, OAState<J> &S, const uin
   constexpr int P0 = PH, P1 = (PH + 4) % 5, P2 = (PH + 3) % 5, P3 = (PH + 2) % 5, P4 = (PH + 1) % 5;
   if (i < 1) return;
   const float *row = pprow_lane + (size_t)i * kPPCells * mpad;
+  prefetch_matrix_row(row - lane * VEC + (size_t)kPPCells * mpad, kPPCells, mpad, lane);       // row i+1 (one row past the end is still inside the buffer or its guard)
   float pc[J], mnew[J], inew[J];
   // M(i,k) = max_c ( P(i-c)[k] + pp_Cc(i,k) ); rows before 0 count as row 0 (:101-108) -- the ring holds row 0 there
   load_row<J, VEC>(row + (PP_C0 + 1) * mpad, pc);

@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(32) orf_backward_kernel(OrfDomainArgs a)
     int chunk = 1 << 30;
     unsigned myres = 0;
     for (int i = L; i >= 0; --i) {
+      if constexpr (FULL) { if (i >= 1) prefetch_matrix_row(pprow_lane - lane * VEC + (size_t)(i - 1) * kPPCellsP * a.mpad, kPPCellsP, a.mpad, lane); }
       float scale = 1.0f;
       if (i < L) {
         // residue x_{i+1}
@@ -398,6 +399,7 @@ __global__ void __launch_bounds__(32) orf_optacc_kernel(OrfDomainArgs a)
     }
     for (int i = 1; i <= L; ++i) {
       const float *row = pprow_lane + (size_t)i * kPPCellsP * a.mpad;
+      if (i < L) prefetch_matrix_row(row - lane * VEC + (size_t)kPPCellsP * a.mpad, kPPCellsP, a.mpad, lane);
       float pc[J], mnew[J], inew[J], dnew[J];
       load_row<J, VEC>(row + PPP_M * a.mpad, pc);
 #pragma unroll
