@@ -1698,6 +1698,56 @@ extern "C" int bathhost_search_get_hit(const bathhost_search *s, int idx, bathho
   return BATHHOST_EINVAL;
 }
 
+// p7_tophits_TabularTargets (src/p7_tophits.c:1603-1712) as bathsearch calls it with --tblout --cigar: the header and one line per
+// reported hit, byte for byte (column widths grow with the longest name / coordinate exactly as there).  The trailer the
+// reference appends (p7_tophits_TabularTail: program, files, command line, date) is the caller's.
+extern "C" int bathhost_search_format_tblout(const bathhost_search *s, int show_header, char *buf, size_t cap, size_t *needed)
+{
+  if (!s || !needed || (!buf && cap > 0)) return BATHHOST_EINVAL;
+  const bathhost_model *m = s->model;
+  const std::string qname = m->hmm.name, qacc = m->hmm.acc;
+  const bool fs_pipe = s->opt.fs;
+  int tnamew = 20, posw = 9;
+  for (const Hit &h : s->hits) {
+    tnamew = std::max(tnamew, (int) strlen(h.pub.name));
+    if (h.pub.ali_from > 0) {
+      posw = std::max(posw, (int) std::to_string((long long) h.pub.ali_from).size());
+      posw = std::max(posw, (int) std::to_string((long long) h.pub.ali_to).size());
+    }
+  }
+  const int qnamew = std::max(20, (int) qname.size()), qaccw = std::max(10, (int) qacc.size()), taccw = 10;
+  std::string out;
+  char line[4096];
+  auto put = [&](const char *fmt, auto... args) { snprintf(line, sizeof line, fmt, args...); out += line; };
+  if (show_header) {
+    put("#%7s %-*s %-*s %-*s %-*s %9s %9s %9s %9s %9s %9s", " hit ID", tnamew - 1, " target name", taccw, " accession", qnamew, " query name",
+        qaccw, " accession", "  hmm len", " hmm from", "   hmm to", "  seq len", " ali from", "   ali to");
+    put("  %9s %6s %5s %5s", "  E-value", " score", " bias", "  PID");
+    if (fs_pipe) put(" %7s %6s", " shifts", " stops");
+    put(" %s\n", "CIGAR");
+    put("#%7s %-*s %-*s %-*s %-*s %9s %9s %9s %9s %9s %9s", "-------", tnamew - 1, "-------------------", taccw, "----------", qnamew,
+        "--------------------", qaccw, "----------", "---------", "---------", "---------", "---------", "---------", "---------");
+    put("  %9s %6s %5s %5s", "---------", "------", "-----", "-----");
+    if (fs_pipe) put(" %7s %6s", "-------", "------");
+    put(" %s\n", "---------------------");
+  }
+  int id = 0;
+  for (const Hit &h : s->hits) {
+    if (!h.reported) continue;
+    ++id;
+    put("%8d %-*s %-*s %-*s %-*s %8d  %8d  %8d  %*lld %*lld %*lld", id, tnamew, h.pub.name, taccw, "-", qnamew, qname.c_str(), qaccw,
+        qacc.empty() ? "-" : qacc.c_str(), m->hmm.M, h.pub.hmm_from, h.pub.hmm_to, posw, (long long) h.pub.sq_len, posw, (long long) h.pub.ali_from,
+        posw, (long long) h.pub.ali_to);
+    put(" %9.2g %6.1f %5.1f %5.2f", h.pub.evalue, h.pub.score, h.pub.bias, h.pub.pid);
+    if (fs_pipe) put(" %7d %6d", h.pub.shifts, h.pub.stops);
+    put(" %s\n", h.pub.cigar);
+  }
+  *needed = out.size() + 1;
+  if (out.size() + 1 > cap) return buf ? BATHHOST_EINVAL : BATHHOST_OK;
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return BATHHOST_OK;
+}
+
 extern "C" int bathhost_search_get_stats(const bathhost_search *s, bathhost_stats *st)
 {
   if (!s || !st) return BATHHOST_EINVAL;

@@ -15,7 +15,7 @@ EXPORTS = [
     "bathhost_orf_length_params", "bathhost_model_computed_max_length",
     "bathhost_search_create", "bathhost_search_destroy", "bathhost_search_last_error", "bathhost_search_sequence",
     "bathhost_search_finish", "bathhost_search_nhits", "bathhost_search_get_hit", "bathhost_search_get_stats",
-    "bathhost_sample_region_segments", "bathhost_cluster_region_segments",
+    "bathhost_sample_region_segments", "bathhost_cluster_region_segments", "bathhost_search_format_tblout",
 ]
 
 
@@ -295,6 +295,17 @@ class Search:
             self.lib.bathhost_search_get_hit(self.h, i, C.byref(h))
             hits.append({n: (getattr(h, n).decode() if isinstance(getattr(h, n), bytes) else getattr(h, n)) for n, _ in Hit._fields_})
         return hits
+
+    def tblout(self, header=True):
+        """the --tblout --cigar table of the reported hits (header + hit lines, no trailer), as bathsearch writes it"""
+        need = C.c_size_t(0)
+        self.lib.bathhost_search_format_tblout.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        self.lib.bathhost_search_format_tblout(self.h, int(header), None, 0, C.byref(need))
+        buf = C.create_string_buffer(need.value)
+        st = self.lib.bathhost_search_format_tblout(self.h, int(header), buf, need.value, C.byref(need))
+        if st != OK:
+            raise RuntimeError(f"bathhost_search_format_tblout: status {st}")
+        return buf.value.decode()
 
     def stats(self):
         s = Stats()

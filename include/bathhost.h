@@ -177,6 +177,9 @@ int  bathhost_search_finish(bathhost_search *s);
 int  bathhost_search_nhits(const bathhost_search *s);
 int  bathhost_search_get_hit(const bathhost_search *s, int idx, bathhost_hit *hit);
 int  bathhost_search_get_stats(const bathhost_search *s, bathhost_stats *st);
+/* The --tblout --cigar table of the reported hits as p7_tophits_TabularTargets writes it (src/p7_tophits.c:1603-1712): header
+ * (if show_header) + one line per hit, NUL-terminated, without the trailer.  *needed = bytes required; call with buf = NULL to size. */
+int  bathhost_search_format_tblout(const bathhost_search *s, int show_header, char *buf, size_t cap, size_t *needed);
 
 #ifdef __cplusplus
 }

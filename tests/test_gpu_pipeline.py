@@ -57,3 +57,18 @@ def test_pth2_filter_cascade_counters_match_golden(gpu_ctx):
     assert st["nres"] == 6000
     assert [st["pos_past_msv"], st["pos_past_bias"], st["pos_past_vit"]] == want
     print(hits, st)
+
+
+def test_tblout_from_the_gpu_search_is_byte_identical_to_the_shipped_tables(gpu_ctx):
+    """header + hit lines of tutorial/AMP_N-fs.tbl (--fs) and tutorial/PTH2.tbl (default pipeline) from the device stages + host pipeline"""
+    from bath_b200 import hostapi
+    from test_host_pipeline_cpu import golden_table
+    for hmm, fasta, tbl, opt in (("AMP_N.bhmm", "target-AMP_N.fa", "AMP_N-fs.tbl", {}),
+                                 ("PTH2.bhmm", "target-PTH2.fa", "PTH2.tbl", {"std_only": 1})):
+        search = hostapi.Search(hostapi.QueryModel(common.golden(hmm)), gpu_ctx, **opt)
+        for name, seq in hostapi.read_fasta(common.golden(fasta)):
+            search.add_sequence(name, hostapi.digitize_dna(seq))
+        search.finish()
+        got = search.tblout()
+        search.close()
+        assert got == golden_table(tbl), (tbl, got)

@@ -190,3 +190,26 @@ print(json.dumps({"hits": [[h["ali_from"], h["ali_to"], h["env_from"], h["env_to
         runs.append(__import__("json").loads(out.stdout.strip().splitlines()[-1]))
     assert runs[0] == runs[1]
     assert runs[0]["stats"]["n_windows"] >= 10 and runs[0]["stats"]["n_multidomain_regions"] >= 1 and len(runs[0]["hits"]) >= 14
+
+
+def golden_table(name):
+    """header and hit lines of a shipped --tblout file (everything before the trailer that starts with a bare '#')"""
+    lines = open(common.golden(name)).read().split("\n")
+    return "\n".join(lines[:lines.index("#")]) + "\n"
+
+
+def test_tblout_is_byte_identical_to_the_shipped_tables(oracle):
+    """bathhost_search_format_tblout (p7_tophits_TabularTargets, src/p7_tophits.c:1603-1712) against tutorial/AMP_N-fs.tbl
+    (bathsearch --fs --cigar) and tutorial/PTH2.tbl (default pipeline, --cigar): header and every hit line, byte for byte."""
+    from bath_b200 import hostapi
+    for hmm, fasta, tbl, opt in (("AMP_N.bhmm", "target-AMP_N.fa", "AMP_N-fs.tbl", {}),
+                                 ("PTH2.bhmm", "target-PTH2.fa", "PTH2.tbl", {"std_only": 1})):
+        be, keep = oracle.cpu_backend(4)
+        search = hostapi.Search(hostapi.QueryModel(common.golden(hmm)), backend=be, **opt)
+        for name, seq in hostapi.read_fasta(common.golden(fasta)):
+            search.add_sequence(name, hostapi.digitize_dna(seq))
+        search.finish()
+        got = search.tblout()
+        search.close()
+        del keep
+        assert got == golden_table(tbl), (tbl, got)
