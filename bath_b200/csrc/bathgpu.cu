@@ -46,6 +46,7 @@ struct DevBuf {
 struct FsProfileImage {
   int   which = 0, M = 0, nrows = 0, J = 0, mpad = 0, scan_steps = 5;
   DevBuf emis;     // [nrows][mpad]
+  DevBuf emis_bck, cellb3;   // the 3-codon Backward parser's table copy and constants (fs_backward.cuh, Bck3Consts)
   DevBuf emis_fwd; // [nrows][mpad] the Forward parsers' copy: match->match odds folded in as well (fs_parser.cuh, FwdConsts)
   DevBuf cellc;    // forward lane constants
   DevBuf cellb;    // backward lane constants
@@ -141,7 +142,7 @@ extern "C" void bathgpu_destroy(bathgpu_ctx *ctx)
   cudaStreamSynchronize(ctx->stream);
   for (FsProfileImage *im : { &ctx->fs3, &ctx->fs5 }) {
     im->emis.release(); im->cellc.release(); im->cellb.release(); im->cellf5.release(); im->amino.release();
-    im->oaflags.release(); im->oapass.release(); im->tfvraw.release(); im->zinv.release(); im->emis_fwd.release();
+    im->oaflags.release(); im->oapass.release(); im->tfvraw.release(); im->zinv.release(); im->emis_fwd.release(); im->emis_bck.release(); im->cellb3.release();
   }
   for (TargetSlot &t : ctx->slot) { t.dna_bytes.release(); t.dna4.release(); t.residues.release(); }
   ctx->wins.release(); ctx->fwdsc.release();
@@ -402,6 +403,54 @@ extern "C" int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int n
     }
     if (im.cellb.reserve(cc.size() * sizeof(float)) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
     CUDA_TRY(ctx, cudaMemcpyAsync(im.cellb.p, cc.data(), cc.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+
+  // ---- the 3-codon Backward parser's scaled constants and table copy (fs_backward.cuh, Bck3Consts)
+  {
+    auto vmmE = [&](int k) -> double {               // match->match odds as the flow into node k+1 sees them; stand-ins where they vanish
+      if (k < 1 || k >= M) return 1.0;
+      const double v = T(tMM, k) / (sK[k + 1] * zK[k]);
+      return v > 0.0 ? v : 1.0e-12;
+    };
+    auto rE = [&](int k) -> double { return (k >= 1 && k < M) ? std::max(T(tDM, k) / sK[k + 1] / vmmE(k), 1.0e-20) : 1.0; };
+    auto uE = [&](int k) -> double { return (k >= 1 && k < M) ? std::max(T(tIM, k) / sK[k + 1] / vmmE(k), 1.0e-20) : 1.0; };
+    auto dd3 = [&](int k) -> double { return (k >= 1 && k < M) ? rE(k + 1) * T(tDD, k) / rE(k) : 0.0; };
+    std::vector<float> eb((size_t)nrows * mpad, 0.0f);
+    for (int c = 0; c < nrows; ++c)
+      for (int k = 1; k <= M; ++k)
+        eb[(size_t)c * mpad + perm_index(k - 1, J)] = (float)((double)rfv[(size_t)c * ld + k] * sK[k] * zK[k] * vmmE(k - 1));
+    std::vector<float> cc((size_t)(B3_COUNT * J + 5) * 32, 0.0f);
+    auto C = [&](int which_c, int j, int lane) -> float & { return cc[(size_t)(which_c * J + j) * 32 + lane]; };
+    std::vector<double> b(32, 1.0);
+    for (int lane = 0; lane < 32; ++lane) {
+      double pp = 1.0;
+      for (int j = 0; j < J; ++j) {
+        int k = lane * J + j + 1;
+        if (k <= M) {
+          C(B3_QB, j, lane) = (float)(1.0 / vmmE(k - 1));
+          C(B3_DD, j, lane) = (float)dd3(k);
+          C(B3_MD, j, lane) = (k < M) ? (float)(rE(k + 1) * T(tMD, k) / zK[k]) : 0.0f;
+          C(B3_MI, j, lane) = (float)(uE(k) * T(tMI, k) / zK[k]);
+          C(B3_II, j, lane) = (float)T(tII, k);
+        }
+        pp *= dd3(k);
+      }
+      b[lane] = pp;
+    }
+    for (int s = 0; s < 5; ++s) {
+      int d = 1 << s;
+      std::vector<double> nb(b);
+      for (int lane = 0; lane < 32; ++lane) {
+        cc[(size_t)(B3_COUNT * J + s) * 32 + lane] = (lane + d <= 31) ? (float)b[lane] : 0.0f;
+        if (lane + d <= 31) nb[lane] = b[lane] * b[lane + d];
+      }
+      b.swap(nb);
+    }
+    if (im.cellb3.reserve(cc.size() * sizeof(float)) != BATHGPU_OK || im.emis_bck.reserve(eb.size() * sizeof(float)) != BATHGPU_OK)
+      return fail(ctx, BATHGPU_EMEM, "device allocation failed");
+    CUDA_TRY(ctx, cudaMemcpyAsync(im.cellb3.p, cc.data(), cc.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(im.emis_bck.p, eb.data(), eb.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   }
 
@@ -825,7 +874,7 @@ static int bck_decode_chunk(bathgpu_ctx *ctx, const bathgpu_window *wins, int n,
   CUDA_TRY(ctx, dispatch_fwd(true, im.J, fa, sms, ctx->stream));
 
   FsBackwardArgs ba{};
-  ba.emis = im.emis.as<float>(); ba.cellb = im.cellb.as<float>(); ba.dna4 = fa.dna4; ba.wins = fa.wins; ba.nwin = n; ba.mpad = im.mpad;
+  ba.emis = im.emis_bck.as<float>(); ba.cellb = im.cellb3.as<float>(); ba.dna4 = fa.dna4; ba.wins = fa.wins; ba.nwin = n; ba.mpad = im.mpad;
   ba.tEM = xfE[0]; ba.tEL = xfE[1]; ba.fxmx = ctx->fxmx.as<float>(); ba.bxmx = ctx->bxmx.as<float>(); ba.xoff = fa.xoff;
   ba.bcksc = ctx->bcksc.as<float>(); ba.status = fa.status; ba.counter = fa.counter;
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));

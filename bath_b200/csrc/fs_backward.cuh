@@ -17,6 +17,16 @@
 //     emission table (already multiplied by tBM(k-1) Z(k)) is shared with Forward, B(i) is a plain sum, and
 //     nothing that depends on E(i) sits inside the D chain:  Mt(i,k) = E(i) + G(i,k), where G needs only
 //     v, I and the E-free chain D0(i,k) = v(k+1) tDM(k) + D0(i,k+1) tDD(k)  (a downward warp scan);
+//   * every chain takes the emission product with coefficient 1, as in the Forward parser (fs_parser.cuh, FwdConsts): this kernel
+//     reads its own table copy with vmm(k-1) = tMM(k-1) / (Z(k-1) s(k)) folded into column k, so that the shifted product
+//     vn(k) = v(k+1) already is the match->match term of G(k); the D0 chain and the insert row are carried divided by
+//     r(k) = vdm(k) / vmm(k) and u(k) = vim(k) / vmm(k):
+//         B(i) = sum_k v(k) qb(k)                         qb(k) = 1 / vmm(k-1)        (an FMA where the plain sum needs an add)
+//         Ds(k) = vn(k) + Ds(k+1) dd3(k)                  dd3 = r(k+1) tDD(k) / r(k)
+//         Is(i,k) = Is(i+3,k) tII(k) + vn(k)
+//         G(k) = vn(k) + Is(i+3,k) mi3(k) + Ds(k+1) md3(k)   mi3 = u(k) tMI(k) / Z(k),  md3 = r(k+1) tMD(k) / Z(k)
+//     10 floating-point instructions per cell instead of 13 and 5 constants per node instead of 7 (Bck3Consts; the 5-codon
+//     Backward of fs_domain.cuh keeps BckConsts);
 //   * 4-slot rings for Mt and I (rows i+1..i+4 live), 4-slot rings for the N/J/C specials.
 // Scaling follows the reference: row i is divided by the Forward row's SCALE(i) unless Backward has
 // switched to its own scales (xB > 1e16; :912-915), the two initialisation rows do not rescale the special
@@ -32,8 +42,8 @@ enum BckCellConst { BC_VMM = 0, BC_VIM, BC_VDM, BC_DD, BC_MD, BC_MI, BC_II, BC_C
 enum BckLaneConst { BL_B0 = 0, BL_B1, BL_B2, BL_B3, BL_B4, BL_COUNT };
 
 struct FsBackwardArgs {
-  const float    *emis;        // same table as Forward: R[c][k] tBM(k-1) Z(k), permuted
-  const float    *cellb;       // backward lane constants [BC_COUNT][J][32] + [BL_COUNT][32]
+  const float    *emis;        // the Backward parser's table copy: R[c][k] tBM(k-1) Z(k) vmm(k-1), permuted (FsProfileImage::emis_bck)
+  const float    *cellb;       // Bck3Consts: [B3_COUNT][J][32] + [5][32]
   const uint32_t *dna4;
   const WindowDesc *wins;
   int             nwin;
@@ -52,6 +62,29 @@ struct BckConsts {
   float vmm[J], vim[J], vdm[J], dd[J], md[J], mi[J], ii[J];
   float bs[5];
 };
+
+enum Bck3CellConst { B3_QB = 0, B3_DD, B3_MD, B3_MI, B3_II, B3_COUNT };
+
+template <int J>
+struct Bck3Consts {
+  float qb[J], dd[J], md[J], mi[J], ii[J];
+  float bs[5];
+};
+
+template <int J>
+__device__ __forceinline__ void load_bck3_consts(const float *__restrict__ cc, int lane, Bck3Consts<J> &K)
+{
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    K.qb[j] = __ldg(cc + (B3_QB * J + j) * kWarp + lane);
+    K.dd[j] = __ldg(cc + (B3_DD * J + j) * kWarp + lane);
+    K.md[j] = __ldg(cc + (B3_MD * J + j) * kWarp + lane);
+    K.mi[j] = __ldg(cc + (B3_MI * J + j) * kWarp + lane);
+    K.ii[j] = __ldg(cc + (B3_II * J + j) * kWarp + lane);
+  }
+#pragma unroll
+  for (int s = 0; s < 5; ++s) K.bs[s] = __ldg(cc + B3_COUNT * J * kWarp + s * kWarp + lane);
+}
 
 template <int J>
 struct BckState {
@@ -98,7 +131,7 @@ struct BckRowCtx {
 
 // One Backward row.  PH = i & 3 (compile time).
 template <int J, int VEC, int PH>
-__device__ __forceinline__ void bck_row(int i, int lane, BckState<J> &S, const BckConsts<J> &K,
+__device__ __forceinline__ void bck_row(int i, int lane, BckState<J> &S, const Bck3Consts<J> &K,
                                         const char *__restrict__ emis_lane, unsigned rowbytes, uint32_t cw,
                                         float fscale, BckRowCtx &R, float *__restrict__ xrow)
 {
@@ -139,7 +172,7 @@ __device__ __forceinline__ void bck_row(int i, int lane, BckState<J> &S, const B
   load_emission_row<J, VEC>(reinterpret_cast<const float *>(emis_lane + (size_t)((cw >> 9) & 511u) * rowbytes), e3);
   load_emission_row<J, VEC>(reinterpret_cast<const float *>(emis_lane + (size_t)(cw >> 18) * rowbytes), e4);
 
-  // v'(k) = tBM(k-1) sum_c R[c][k] M(i+c,k);  B(i) = sum_k v'(k)            (:820-835)
+  // v(k) = tBM(k-1) vmm(k-1) sum_c R[c][k] M(i+c,k);  B(i) = sum_k v(k) qb(k)            (:820-835)
   float bs0 = 0.f, bs1 = 0.f;
 #pragma unroll
   for (int j = 0; j < J; ++j) {
@@ -147,11 +180,11 @@ __device__ __forceinline__ void bck_row(int i, int lane, BckState<J> &S, const B
     t = fmaf(S.Mt[S3][j], e3[j], t);
     t = fmaf(S.Mt[S0][j], e4[j], t);
     v[j] = t;
-    if (j == 0) bs0 = t; else if (j == 1) bs1 = t; else if (j & 1) bs1 += t; else bs0 += t;
+    if (j == 0) bs0 = t * K.qb[0]; else if (j == 1) bs1 = t * K.qb[1]; else if (j & 1) bs1 = fmaf(t, K.qb[j], bs1); else bs0 = fmaf(t, K.qb[j], bs0);
   }
   float xB = warp_allsum(J > 1 ? bs0 + bs1 : bs0);
 
-  // vn(k) = v'(k+1): shift down by one node
+  // vn(k) = v(k+1): shift down by one node
   float vn[J];
   {
     float up = __shfl_down_sync(0xffffffffu, v[0], 1);
@@ -161,28 +194,26 @@ __device__ __forceinline__ void bck_row(int i, int lane, BckState<J> &S, const B
     vn[J - 1] = up;
   }
 
-  // E-free D chain, downward: D0(k) = vn(k) vdm(k) + D0(k+1) dd(k)          (:885-909)
-  float a[J];
+  // E-free D chain, downward, scaled: Ds(k) = vn(k) + Ds(k+1) dd3(k)          (:885-909)
   float A = 0.f;
 #pragma unroll
-  for (int j = J - 1; j >= 0; --j) { a[j] = vn[j] * K.vdm[j]; A = (j == J - 1) ? a[j] : fmaf(A, K.dd[j], a[j]); }
+  for (int j = J - 1; j >= 0; --j) A = (j == J - 1) ? vn[j] : fmaf(A, K.dd[j], vn[j]);
 #pragma unroll
   for (int s = 0; s < 5; ++s) {
     float dn = __shfl_down_sync(0xffffffffu, A, 1 << s);
     A = fmaf(K.bs[s], dn, A);
   }
-  float d = __shfl_down_sync(0xffffffffu, A, 1);     // D0 at the first node of the next lane
+  float d = __shfl_down_sync(0xffffffffu, A, 1);     // Ds at the first node of the next lane
   if (lane == 31) d = 0.f;
 
-  // G(k) = (I(i+3,k) tMI(k) + vn(k) tMM(k) + D0(k+1) tMD(k)) / Z(k);  I(i,k) = I(i+3,k) tII(k) + vn(k) tIM(k)
+  // G(k) = vn(k) + Is(i+3,k) mi3(k) + Ds(k+1) md3(k);  Is(i,k) = Is(i+3,k) tII(k) + vn(k)
   float g[J];
 #pragma unroll
   for (int j = J - 1; j >= 0; --j) {
-    float t = S.I[S3][j] * K.mi[j];
-    t = fmaf(vn[j], K.vmm[j], t);
+    float t = fmaf(S.I[S3][j], K.mi[j], vn[j]);
     g[j] = fmaf(d, K.md[j], t);
-    d = fmaf(d, K.dd[j], a[j]);
-    S.I[S0][j] = fmaf(S.I[S3][j], K.ii[j], vn[j] * K.vim[j]);
+    d = fmaf(d, K.dd[j], vn[j]);
+    S.I[S0][j] = fmaf(S.I[S3][j], K.ii[j], vn[j]);
   }
 
   // specials (:837-857)
@@ -241,8 +272,8 @@ __global__ void __launch_bounds__(BckTune<J>::kThreads, BckTune<J>::kMinBlocks) 
   constexpr int VEC = VecOf<J>::V;
   const int lane = threadIdx.x & 31;
 
-  BckConsts<J> K;
-  load_bck_consts<J>(a.cellb, lane, K);
+  Bck3Consts<J> K;
+  load_bck3_consts<J>(a.cellb, lane, K);
   const char    *emis_lane = reinterpret_cast<const char *>(a.emis + lane * VEC);
   const unsigned rowbytes  = (unsigned)a.mpad * 4u;
 

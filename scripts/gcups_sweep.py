@@ -25,7 +25,7 @@ for hmm, idx in models:
         for _ in range(2): ctx.fs_fwd_staged()
         t = min((ctx.fs_fwd_staged(), ctx.last_stage_timing()[0])[1] for _ in range(3))
         cells = nwin * Lw * model.M
-        nb = min(nwin, 2048)
+        nb = min(nwin, 8192 if Lw <= 1200 else 4096)      # several waves of windows per resident warp, and X rows that still fit in host memory
         ctx.fs_fwd_bck_xrows(w[:nb])
         tb = min((ctx.fs_fwd_bck_xrows(w[:nb]), ctx.last_stage_timing()[0])[1] for _ in range(2))
         print(f"| {model.M} | {Lw} | {nwin} | {cells / t / 1e6:.0f} | {2 * nb * Lw * model.M / tb / 1e6:.0f} |", flush=True)
