@@ -129,44 +129,15 @@ struct BckRowCtx {
   bool  own_scales;
 };
 
-// One Backward row.  PH = i & 3 (compile time).
+// The row itself: emission products, B(i), the scaled D0 chain, G, the insert row, the specials -- everything up to, but not
+// including, the rescaling.  Writes Is(i,.) and Mt(i,.) = E(i) + G into slot S0; returns the row's specials, unscaled.
+struct BckOut { float xB, xN, xJ, xC, xE; };
+
 template <int J, int VEC, int PH>
-__device__ __forceinline__ void bck_row(int i, int lane, BckState<J> &S, const Bck3Consts<J> &K,
-                                        const char *__restrict__ emis_lane, unsigned rowbytes, uint32_t cw,
-                                        float fscale, BckRowCtx &R, float *__restrict__ xrow)
+__device__ __forceinline__ BckOut bck_row_core(int lane, BckState<J> &S, const Bck3Consts<J> &K,
+                                               const char *__restrict__ emis_lane, unsigned rowbytes, uint32_t cw, const BckRowCtx &R)
 {
-  constexpr int S0 = PH, S1 = (PH + 1) & 3, S2 = (PH + 2) & 3, S3 = (PH + 3) & 3;   // slots of rows i(=i+4), i+1, i+2, i+3
-  const int L = R.L;
-
-  if (i >= L - 1) {                 // warp-uniform: pad rows above L do nothing, rows L and L-1 initialise (:628-690)
-    if (i <= L) {
-      float xC = (i == L) ? R.pmove : R.ploop * R.pmove;
-      float xE = xC * R.tEM;
-      float sc = fscale;
-      if (sc > 1.0f) {
-        float sf = 1.0f / sc;
-        xC *= sf; xE *= sf;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-#pragma unroll
-          for (int j = 0; j < J; ++j) { S.Mt[r][j] *= sf; S.I[r][j] *= sf; }
-        }
-        R.totscale += logf(sc);
-      }
-#pragma unroll
-      for (int j = 0; j < J; ++j) { S.Mt[S0][j] = xE; S.I[S0][j] = 0.f; }
-      S.xN[S0] = 0.f; S.xJ[S0] = 0.f; S.xC[S0] = xC;
-      if (i == L) S.xC[S1] = R.pmove;     // so that row L-2 reads C = tCL tCM (:815), whatever rows L, L-1 were scaled by
-      if (lane == 0) {
-        float2 *x2 = reinterpret_cast<float2 *>(xrow + (size_t)i * 6);
-        x2[0] = make_float2(xE, 0.f);
-        x2[1] = make_float2(0.f, 0.f);
-        x2[2] = make_float2(xC, sc);
-      }
-    }
-    return;
-  }
-
+  constexpr int S0 = PH, S2 = (PH + 2) & 3, S3 = (PH + 3) & 3;
   float e2[J], e3[J], e4[J], v[J];
   load_emission_row<J, VEC>(reinterpret_cast<const float *>(emis_lane + (size_t)(cw & 511u) * rowbytes), e2);
   load_emission_row<J, VEC>(reinterpret_cast<const float *>(emis_lane + (size_t)((cw >> 9) & 511u) * rowbytes), e3);
@@ -222,6 +193,52 @@ __device__ __forceinline__ void bck_row(int i, int lane, BckState<J> &S, const B
   float xN = fmaf(S.xN[S3], R.ploop, xB * R.pmove);
   float xE = fmaf(xJ, R.tEL, xC * R.tEM);
 
+#pragma unroll
+  for (int j = 0; j < J; ++j) S.Mt[S0][j] = xE + g[j];
+  return BckOut{ xB, xN, xJ, xC, xE };
+}
+
+// One Backward row.  PH = i & 3 (compile time).
+template <int J, int VEC, int PH>
+__device__ __forceinline__ void bck_row(int i, int lane, BckState<J> &S, const Bck3Consts<J> &K,
+                                        const char *__restrict__ emis_lane, unsigned rowbytes, uint32_t cw,
+                                        float fscale, BckRowCtx &R, float *__restrict__ xrow)
+{
+  constexpr int S0 = PH, S1 = (PH + 1) & 3, S2 = (PH + 2) & 3, S3 = (PH + 3) & 3;   // slots of rows i(=i+4), i+1, i+2, i+3
+  const int L = R.L;
+
+  if (i >= L - 1) {                 // warp-uniform: pad rows above L do nothing, rows L and L-1 initialise (:628-690)
+    if (i <= L) {
+      float xC = (i == L) ? R.pmove : R.ploop * R.pmove;
+      float xE = xC * R.tEM;
+      float sc = fscale;
+      if (sc > 1.0f) {
+        float sf = 1.0f / sc;
+        xC *= sf; xE *= sf;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+          for (int j = 0; j < J; ++j) { S.Mt[r][j] *= sf; S.I[r][j] *= sf; }
+        }
+        R.totscale += logf(sc);
+      }
+#pragma unroll
+      for (int j = 0; j < J; ++j) { S.Mt[S0][j] = xE; S.I[S0][j] = 0.f; }
+      S.xN[S0] = 0.f; S.xJ[S0] = 0.f; S.xC[S0] = xC;
+      if (i == L) S.xC[S1] = R.pmove;     // so that row L-2 reads C = tCL tCM (:815), whatever rows L, L-1 were scaled by
+      if (lane == 0) {
+        float2 *x2 = reinterpret_cast<float2 *>(xrow + (size_t)i * 6);
+        x2[0] = make_float2(xE, 0.f);
+        x2[1] = make_float2(0.f, 0.f);
+        x2[2] = make_float2(xC, sc);
+      }
+    }
+    return;
+  }
+
+  const BckOut O = bck_row_core<J, VEC, PH>(lane, S, K, emis_lane, rowbytes, cw, R);
+  float xB = O.xB, xN = O.xN, xJ = O.xJ, xC = O.xC, xE = O.xE;
+
   if (i == 0) {                    // termination (:951-987): only B and N are defined on row 0, no rescaling
     S.xN[S0] = xN;
     if (lane == 0) {
@@ -232,9 +249,6 @@ __device__ __forceinline__ void bck_row(int i, int lane, BckState<J> &S, const B
     }
     return;
   }
-
-#pragma unroll
-  for (int j = 0; j < J; ++j) S.Mt[S0][j] = xE + g[j];
 
   float scale = fscale;
   if (i < L - 2) {                 // (:910-916)
@@ -261,9 +275,71 @@ __device__ __forceinline__ void bck_row(int i, int lane, BckState<J> &S, const B
   }
 }
 
+// Rows i (phase PH) and i-1 (phase PH-1) in one basic block: row i-1 reads rows i+1 .. i+3 only, so the two rows are independent
+// and the compiler interleaves their shuffle chains (the Forward parser's row-pair schedule, fs_parser_v3.cuh).  Everything is
+// linear in the state, so row i's rescaling is applied afterwards to what row i-1 has just computed, then row i-1's own.
+// Both rows must be regular rows: i <= L-2 and i-1 >= 1.
+template <int J, int VEC, int PH>
+__device__ __forceinline__ void bck_row_pair(int i, int lane, BckState<J> &S, const Bck3Consts<J> &K,
+                                             const char *__restrict__ emis_lane, unsigned rowbytes, uint32_t cwA, uint32_t cwB,
+                                             float fsA, float fsB, BckRowCtx &R, float *__restrict__ xrow)
+{
+  static_assert(PH == 3 || PH == 1, "pairs start on odd phases");
+  BckOut A = bck_row_core<J, VEC, PH>(lane, S, K, emis_lane, rowbytes, cwA, R);
+  BckOut B = bck_row_core<J, VEC, PH - 1>(lane, S, K, emis_lane, rowbytes, cwB, R);
+  const int L = R.L;
+  auto rescale_all = [&](float sf) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int j = 0; j < J; ++j) { S.Mt[r][j] *= sf; S.I[r][j] *= sf; }
+      S.xN[r] *= sf; S.xJ[r] *= sf; S.xC[r] *= sf;
+    }
+  };
+  float scaleA = fsA;
+  if (i < L - 2) {                 // (:910-916)
+    if (A.xB > 1.0e16f) R.own_scales = true;
+    if (R.own_scales) scaleA = (A.xB > 1.0e4f) ? A.xB : 1.0f;
+  }
+  if (scaleA > 1.0f) {             // warp-uniform
+    const float sf = 1.0f / scaleA;
+    A.xN *= sf; A.xJ *= sf; A.xC *= sf; A.xB *= sf; A.xE *= sf;
+    B.xN *= sf; B.xJ *= sf; B.xC *= sf; B.xB *= sf; B.xE *= sf;
+    rescale_all(sf);
+    R.totscale += logf(scaleA);
+  }
+  S.xN[PH] = A.xN; S.xJ[PH] = A.xJ; S.xC[PH] = A.xC;
+  float scaleB = fsB;
+  if (i - 1 < L - 2) {
+    if (B.xB > 1.0e16f) R.own_scales = true;
+    if (R.own_scales) scaleB = (B.xB > 1.0e4f) ? B.xB : 1.0f;
+  }
+  if (scaleB > 1.0f) {
+    const float sf = 1.0f / scaleB;
+    B.xN *= sf; B.xJ *= sf; B.xC *= sf; B.xB *= sf; B.xE *= sf;
+    rescale_all(sf);
+    R.totscale += logf(scaleB);
+  }
+  S.xN[PH - 1] = B.xN; S.xJ[PH - 1] = B.xJ; S.xC[PH - 1] = B.xC;
+  if (lane == 0) {
+    float2 *x2 = reinterpret_cast<float2 *>(xrow + (size_t)i * 6);
+    x2[0] = make_float2(A.xE, A.xN);
+    x2[1] = make_float2(A.xJ, A.xB);
+    x2[2] = make_float2(A.xC, scaleA);
+    x2 = reinterpret_cast<float2 *>(xrow + (size_t)(i - 1) * 6);
+    x2[0] = make_float2(B.xE, B.xN);
+    x2[1] = make_float2(B.xJ, B.xB);
+    x2[2] = make_float2(B.xC, scaleB);
+  }
+}
+
 template <int J> struct BckTune {
   static constexpr int kThreads   = 32;
-  static constexpr int kMinBlocks = (J <= 3) ? 20 : (J == 4) ? 16 : (J == 5) ? 14 : (J == 6) ? 13 : (J == 7) ? 11 : (J == 8) ? 10 : 8;
+#ifdef BATHGPU_BCK_WARPS
+  static constexpr int kMinBlocks = BATHGPU_BCK_WARPS(J);
+#else
+  static constexpr int kMinBlocks = (J <= 3) ? 20 : (J == 4) ? 16 : (J == 5) ? 14 : (J == 6) ? 12 : (J == 7) ? 11 : (J == 8) ? 10 : 8;   // J = 6: 160 registers, no spill (+5 % over 128 with a 96-byte stack)
+#endif
 };
 
 template <int J>
@@ -315,16 +391,20 @@ __global__ void __launch_bounds__(BckTune<J>::kThreads, BckTune<J>::kMinBlocks) 
       }
       const int qn = min(8, nq - q0);
       for (int qq = 0; qq < qn; ++qq) {
-#define BATHGPU_BROW(PH_)                                                                             \
+#define BATHGPU_BPAIR(PH_)                                                                            \
         {                                                                                             \
-          const int src = qq * 4 + (3 - PH_);                                                         \
-          uint32_t cw = __shfl_sync(0xffffffffu, cwl, src);                                           \
-          float    fs = __shfl_sync(0xffffffffu, fsl, src);                                           \
-          bck_row<J, VEC, PH_>(i, lane, S, K, emis_lane, rowbytes, cw, fs, R, xrow);                  \
-          --i;                                                                                        \
+          const int srcA = qq * 4 + (3 - PH_), srcB = srcA + 1;                                       \
+          const uint32_t cwA = __shfl_sync(0xffffffffu, cwl, srcA), cwB = __shfl_sync(0xffffffffu, cwl, srcB); \
+          const float    fsA = __shfl_sync(0xffffffffu, fsl, srcA), fsB = __shfl_sync(0xffffffffu, fsl, srcB); \
+          if (i <= L - 2 && i >= 2) bck_row_pair<J, VEC, PH_>(i, lane, S, K, emis_lane, rowbytes, cwA, cwB, fsA, fsB, R, xrow); \
+          else {                                                                                      \
+            bck_row<J, VEC, PH_>(i, lane, S, K, emis_lane, rowbytes, cwA, fsA, R, xrow);              \
+            bck_row<J, VEC, PH_ - 1>(i - 1, lane, S, K, emis_lane, rowbytes, cwB, fsB, R, xrow);      \
+          }                                                                                           \
+          i -= 2;                                                                                     \
         }
-        BATHGPU_BROW(3) BATHGPU_BROW(2) BATHGPU_BROW(1) BATHGPU_BROW(0)
-#undef BATHGPU_BROW
+        BATHGPU_BPAIR(3) BATHGPU_BPAIR(1)
+#undef BATHGPU_BPAIR
       }
     }
 
