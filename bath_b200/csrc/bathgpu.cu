@@ -1164,7 +1164,8 @@ __global__ void fs5_export_forward_kernel(const float *__restrict__ pp, const fl
 extern "C" int bathgpu_fs_forward_matrices(bathgpu_ctx *ctx, const bathgpu_envelope *regs, int n, const float xfE5[2],
                                            float *mx, float *xrows, int64_t max_rows, float *fwdsc, int32_t *status)
 {
-  if (!ctx || !regs || n < 1 || !xfE5 || !mx || !xrows || !fwdsc || !status) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fs_forward_matrices");
+  if (!ctx || !regs || n < 1 || !xfE5 || (!mx) != (!xrows) || !fwdsc || !status) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fs_forward_matrices");
+  const bool scores_only = !mx;          // p7_ForwardParser_Frameshift_5Codons: the score, nothing handed back
   if (!ctx->fs5.loaded)      return fail(ctx, BATHGPU_EINVAL, "5-codon profile not loaded");
   if (ctx->S().block_n == 0) return fail(ctx, BATHGPU_EINVAL, "no block uploaded");
   int64_t total = 0;
@@ -1174,7 +1175,7 @@ extern "C" int bathgpu_fs_forward_matrices(bathgpu_ctx *ctx, const bathgpu_envel
                   e, (long long)regs[e].start, regs[e].L, (long long)ctx->S().block_n);
     total += regs[e].L + 1;
   }
-  if (total > max_rows) return fail(ctx, BATHGPU_EINVAL, "matrix buffer too small: %lld rows needed, %lld given", (long long)total, (long long)max_rows);
+  if (!scores_only && total > max_rows) return fail(ctx, BATHGPU_EINVAL, "matrix buffer too small: %lld rows needed, %lld given", (long long)total, (long long)max_rows);
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   const FsProfileImage &im = ctx->fs5;
   const int M = im.M, mpad = im.mpad;
@@ -1193,7 +1194,7 @@ extern "C" int bathgpu_fs_forward_matrices(bathgpu_ctx *ctx, const bathgpu_envel
     for (int e = 0; e < m; ++e) xoff[e + 1] = xoff[e] + regs[e0 + e].L + 1;
     if (ctx->envs.reserve((size_t)m * sizeof(EnvelopeDesc)) != BATHGPU_OK || ctx->xoff.reserve((size_t)(m + 1) * 8) != BATHGPU_OK ||
         ctx->dpp.reserve(rows * kPPCells * mpad * 4) != BATHGPU_OK || ctx->ddcell.reserve(rows * mpad * 4) != BATHGPU_OK ||
-        ctx->dmxout.reserve(rows * (size_t)(M + 1) * 32) != BATHGPU_OK || ctx->dfx.reserve(rows * 24) != BATHGPU_OK ||
+        ctx->dmxout.reserve(scores_only ? 32 : rows * (size_t)(M + 1) * 32) != BATHGPU_OK || ctx->dfx.reserve(rows * 24) != BATHGPU_OK ||
         ctx->dlsf.reserve(rows * 4) != BATHGPU_OK || ctx->dfw.reserve((size_t)m * 4) != BATHGPU_OK ||
         ctx->dstat.reserve((size_t)m * 4) != BATHGPU_OK || ctx->counter.reserve(64) != BATHGPU_OK)
       return fail(ctx, BATHGPU_EMEM, "device allocation failed for %d regions (%zu rows, M=%d)", m, rows, M);
@@ -1207,18 +1208,22 @@ extern "C" int bathgpu_fs_forward_matrices(bathgpu_ctx *ctx, const bathgpu_envel
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     CUDA_TRY(ctx, dispatch_forward_matrix(im.J, a, ctx->prop.multiProcessorCount, ctx->stream));
     const long long cells = (long long)rows * (M + 1);
-    fs5_export_forward_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(ctx->dpp.as<float>(), ctx->ddcell.as<float>(), im.zinv.as<float>(),
-                                                                                        im.J, M, mpad, (long long)rows, ctx->dmxout.as<float>());
-    CUDA_TRY(ctx, cudaGetLastError());
+    if (!scores_only) {
+      fs5_export_forward_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(ctx->dpp.as<float>(), ctx->ddcell.as<float>(), im.zinv.as<float>(),
+                                                                                          im.J, M, mpad, (long long)rows, ctx->dmxout.as<float>());
+      CUDA_TRY(ctx, cudaGetLastError());
+    }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(mx + (size_t)row0 * (M + 1) * 8, ctx->dmxout.p, (size_t)cells * 32, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(xrows + (size_t)row0 * 6, ctx->dfx.p, rows * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!scores_only) {
+      CUDA_TRY(ctx, cudaMemcpyAsync(mx + (size_t)row0 * (M + 1) * 8, ctx->dmxout.p, (size_t)cells * 32, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpyAsync(xrows + (size_t)row0 * 6, ctx->dfx.p, rows * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CUDA_TRY(ctx, cudaMemcpyAsync(fwdsc + e0, ctx->dfw.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(status + e0, ctx->dstat.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    ctx->last_ms += ms; ctx->last_launches += 2;
+    ctx->last_ms += ms; ctx->last_launches += scores_only ? 1 : 2;
     row0 += (int64_t)rows;
     e0 = e1;
   }

@@ -16,6 +16,7 @@ EXPORTS = [
     "bathhost_search_create", "bathhost_search_destroy", "bathhost_search_last_error", "bathhost_search_sequence",
     "bathhost_search_finish", "bathhost_search_nhits", "bathhost_search_get_hit", "bathhost_search_get_stats",
     "bathhost_sample_region_segments", "bathhost_cluster_region_segments", "bathhost_search_format_tblout",
+    "bathhost_calibrate", "bathhost_model_lambda",
 ]
 
 
@@ -64,6 +65,12 @@ class Segment(C.Structure):
 
 
 _lib = None
+
+
+class Calibration(C.Structure):
+    """bathhost_calibration (include/bathhost.h)"""
+    _fields_ = [("seed", C.c_uint32), ("rng_state", C.c_uint32), ("convert_flow", C.c_int32), ("which_mask", C.c_int32),
+                ("lambda_", C.c_double)]
 
 
 def load():
@@ -126,6 +133,10 @@ def load():
     L.bathhost_search_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.bathhost_model_computed_max_length.restype = C.c_int
     L.bathhost_model_computed_max_length.argtypes = [vp]
+    L.bathhost_calibrate.restype = C.c_int
+    L.bathhost_calibrate.argtypes = [vp, C.POINTER(Backend), C.POINTER(Calibration), C.POINTER(C.c_double)]
+    L.bathhost_model_lambda.restype = C.c_double
+    L.bathhost_model_lambda.argtypes = [vp]
     L.bathhost_length_model.restype = None
     L.bathhost_length_model.argtypes = [C.c_int, C.c_float, fp, fp]
     _lib = L
@@ -245,6 +256,22 @@ def backend_from(gpu_lib, ctx_handle):
     for n in Backend._names:
         setattr(be, n, C.cast(getattr(gpu_lib, "bathgpu_" + n), C.c_void_p))
     return be
+
+
+def calibrate(model, gpu_ctx=None, backend=None, seed=42, lam=0.0, which=31, convert_flow=False, rng_state=0):
+    """E-value parameters of a model by simulation on the device (p7_Calibrate with the frameshift branch, or bathconvert's
+    frameshift-only flow): returns (evparam[8], generator state).  See bathhost_calibrate in include/bathhost.h."""
+    lib = load()
+    if backend is None:
+        if gpu_ctx is None:
+            raise ValueError("a device context is required: the product has no CPU path")
+        backend = backend_from(gpu_ctx.lib, gpu_ctx.h)
+    cal = Calibration(seed, rng_state, int(convert_flow), which, float(lam))
+    out = (C.c_double * 8)()
+    st = lib.bathhost_calibrate(model.h, C.byref(backend), C.byref(cal), out)
+    if st != OK:
+        raise RuntimeError(f"bathhost_calibrate: status {st}")
+    return [float(v) for v in out], int(cal.rng_state)
 
 
 class Search:

@@ -221,7 +221,9 @@ int bathgpu_fs_domains(bathgpu_ctx *ctx, const bathgpu_envelope *envs, int n, co
  *   mx    [rows][(M+1)][8]  {D, I, M_C0, M_C1 .. M_C5} (impl_sse.h:296-314), node 0 all zero
  *   xrows [rows][6]         {E, N, J, B, C, SCALE}
  * with off = sum over earlier regions of (L+1); max_rows = rows the caller allocated.  xfE5 = {E->MOVE, E->LOOP} odds
- * (multihit: {0.5, 0.5}); the length model of each region is in its descriptor.  status[r] = eslERANGE as the reference. */
+ * (multihit: {0.5, 0.5}); the length model of each region is in its descriptor.  status[r] = eslERANGE as the reference.
+ * mx = xrows = NULL: scores only -- what p7_ForwardParser_Frameshift_5Codons returns (src/impl_sse/impl_sse.h:495; its one
+ * caller is the calibration p7_fs_Tau_5codons, src/evalues.c:759); max_rows is then ignored. */
 int bathgpu_fs_forward_matrices(bathgpu_ctx *ctx, const bathgpu_envelope *regs, int n, const float xfE5[2],
                                 float *mx, float *xrows, int64_t max_rows, float *fwdsc, int32_t *status);
 

@@ -12,6 +12,7 @@
  *                                + p7_fs_oprofile_Convert                      src/impl_sse/p7_fs_oprofile.c:222-296
  *                                as bathsearch sets a query up                 src/bathsearch.c:794-801
  *   bathhost_length_model     <- p7_fs_oprofile_ReconfigLength                 src/impl_sse/p7_fs_oprofile.c:636-651
+ *   bathhost_calibrate        <- p7_Calibrate / bathconvert's frameshift taus  src/evalues.c:64-183; src/bathconvert.c:128-161
  */
 #ifndef BATHHOST_H
 #define BATHHOST_H
@@ -180,6 +181,26 @@ int  bathhost_search_get_stats(const bathhost_search *s, bathhost_stats *st);
 /* The --tblout --cigar table of the reported hits as p7_tophits_TabularTargets writes it (src/p7_tophits.c:1603-1712): header
  * (if show_header) + one line per hit, NUL-terminated, without the trailer.  *needed = bytes required; call with buf = NULL to size. */
 int  bathhost_search_format_tblout(const bathhost_search *s, int show_header, char *buf, size_t cap, size_t *needed);
+
+/* ---- f4: E-value calibration by brief simulation (calibrate.cpp) ------------------------------------------------
+ * p7_Calibrate with the frameshift branch (src/evalues.c:64-183: p7_Lambda, p7_MSVMu, p7_ViterbiMu, p7_Tau, p7_fs_Tau_3codons,
+ * p7_fs_Tau_5codons), each simulation one batched stage call into the device library instead of 200 single-sequence kernel calls.
+ *   convert_flow = 0  bathbuild: all five simulations from one generator seeded per model (src/p7_builder.c:130, evalues.c:94-98)
+ *   convert_flow = 1  bathconvert / bathfetch (src/bathconvert.c:128-161; src/bathfetch.c:295-325): the two frameshift simulations
+ *                     only, on a generator created once per run that keeps running from model to model: rng_state carries it
+ *                     (0 = fresh generator from seed) and receives the state left behind.
+ * seed 0 = 42 (the programs' default); which_mask bit 0 MSV, 1 Viterbi, 2 Forward, 3 FS3, 4 FS5 (0 = all; the generator is
+ * advanced past skipped simulations); lambda <= 0: p7_Lambda of the model (flow 0) or the model file's lambda (flow 1).
+ * evparam[8] in the order of bathhost_model_info.evparam; simulations not run stay -99999. */
+typedef struct {
+  uint32_t seed;
+  uint32_t rng_state;
+  int32_t  convert_flow;
+  int32_t  which_mask;
+  double   lambda;
+} bathhost_calibration;
+int    bathhost_calibrate(const bathhost_model *m, const bathhost_backend *be, bathhost_calibration *cal, double evparam[8]);
+double bathhost_model_lambda(const bathhost_model *m);          /* p7_Lambda, src/evalues.c:243-250 */
 
 #ifdef __cplusplus
 }

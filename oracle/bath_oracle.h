@@ -287,6 +287,11 @@ int bo_spensemble_fs_Cluster(const BO_SEGMENT *sp, int n, int nsamples, float mi
 int bo_region_trace_ensemble_frameshift(const BO_FS_OPROFILE *om, const BO_MX *fwd, int ireg, int jreg, uint32_t seed, int nsamples,
                                         BO_SEGMENT *samples, int max_samples, int *ret_nsamples, BO_SEGMENT *out, int max_out);
 
+/* ===== calibrate.c (src/evalues.c: p7_Calibrate, p7_Lambda, p7_MSVMu, p7_ViterbiMu, p7_Tau, p7_fs_Tau_3codons/_5codons) ===== */
+double bo_Lambda(const BO_HMM *hmm, const BO_BG *bg);
+double bo_gumbel_FitCompleteLoc(const double *x, int n, double lambda);
+void   bo_gumbel_FitComplete(const double *x, int n, double *ret_mu, double *ret_lambda);
+
 /* ===== fs_null2.c (impl_sse/null2_fs.c) ===== */
 int bo_Null2_fs_ByExpectation(const BO_FS_OPROFILE *om, BO_MX *pp, float *null2 /* [Kp] */);
 
@@ -339,4 +344,7 @@ int bo_batch_ForwardParser_3Codons(const uint8_t *dsq, const int64_t *start, con
 #ifdef __cplusplus
 }
 #endif
+int bo_Calibrate(const BO_HMM *hmm, BO_BG *bg, BO_OPROFILE *om, BO_FS_OPROFILE *om_fs3, BO_FS_OPROFILE *om_fs5, int ct,
+                 uint32_t seed, double lambda, int which_mask, int convert_flow, uint32_t *rng_x, double out[8]);
+
 #endif

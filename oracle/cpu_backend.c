@@ -380,8 +380,8 @@ static void fmx_item(bo_backend *b, void *arg, int i)
   om.xf[BO_X_E][BO_O_MOVE] = a->xfE5[0]; om.xf[BO_X_E][BO_O_LOOP] = a->xfE5[1];
   a->sc[i] = 0.0f;
   a->st[i] = bo_Forward_Frameshift(sub, L, &om, fwd, &a->sc[i]);
-  memcpy(a->mx + (size_t) a->off[i] * (M + 1) * 8, fwd->dp, sizeof(float) * (size_t)(L + 1) * (M + 1) * 8);
-  memcpy(a->xr + (size_t) a->off[i] * 6, fwd->xmx, sizeof(float) * 6 * (size_t)(L + 1));
+  if (a->mx) memcpy(a->mx + (size_t) a->off[i] * (M + 1) * 8, fwd->dp, sizeof(float) * (size_t)(L + 1) * (M + 1) * 8);
+  if (a->xr) memcpy(a->xr + (size_t) a->off[i] * 6, fwd->xmx, sizeof(float) * 6 * (size_t)(L + 1));
   bo_mx_destroy(fwd); free(sub);
 }
 
@@ -395,7 +395,7 @@ int bo_backend_fs_forward_matrices(void *ctx, const void *regs, int n, const flo
   int i;
   off[0] = 0;
   for (i = 0; i < n; i++) off[i + 1] = off[i] + e[i].L + 1;
-  if (off[n] > max_rows) { free(off); snprintf(b->err, sizeof b->err, "matrix buffer too small"); return BO_EINVAL; }
+  if ((mx || xrows) && off[n] > max_rows) { free(off); snprintf(b->err, sizeof b->err, "matrix buffer too small"); return BO_EINVAL; }
   parallel_for(b, n, fmx_item, &a);
   free(off);
   return BO_OK;

@@ -188,6 +188,9 @@ def lib(native=False):
         "bo_aa_digitize": (C.c_int, [C.c_char]),
         "bo_dna_revcomp": (None, [u8p, C.c_int64]),
         "bo_gencode_basic": (u8p, [C.c_int]),
+        "bo_Lambda": (C.c_double, [P(HMM), P(BG)]),
+        "bo_Calibrate": (C.c_int, [P(HMM), P(BG), P(OPROFILE), P(FS_OPROFILE), P(FS_OPROFILE), C.c_int, C.c_uint32, C.c_double,
+                                   C.c_int, C.c_int, P(C.c_uint32), P(C.c_double)]),
         "bo_region_trace_ensemble_frameshift": (C.c_int, [P(FS_OPROFILE), P(MX), C.c_int, C.c_int, C.c_uint32, C.c_int,
                                                           P(SEGMENT), C.c_int, P(C.c_int), P(SEGMENT), C.c_int]),
     }
@@ -250,6 +253,7 @@ class Model:
 
     def __init__(self, path, index=0, ct=None):
         L = lib()
+        self.path, self.index = path, index
         hp = C.POINTER(HMM)()
         st = L.bo_hmmfile_read(path.encode(), index, C.byref(hp))
         if st != OK:
@@ -292,6 +296,24 @@ class Model:
     def xf(self, which=3):
         om = (self.om_fs3 if which == 3 else self.om_fs5).contents
         return np.array([[om.xf[s][t] for t in range(2)] for s in range(4)], dtype=np.float32)
+
+
+def calibrate(model, seed=42, lam=None, which=31, convert_flow=False, rng_x=0):
+    """p7_Calibrate with the frameshift branch (src/evalues.c:64-183) on a FRESH copy of the model's profiles (the simulations
+    reconfigure the length models): evparam[8].  lam=None: the model file's lambda, as bathconvert passes it
+    (src/bathconvert.c:157); lam <= 0: p7_Lambda.  convert_flow: bathconvert's frameshift-only
+    calibration on a generator that runs on from model to model (rng_x = state left by the previous model, 0 = fresh).
+    Returns (evparam, generator state)."""
+    m = Model.__new__(Model)
+    Model.__init__(m, model.path, model.index, model.ct)
+    out = (C.c_double * 8)()
+    if lam is None:
+        lam = float(model.evparam[5])
+    x = C.c_uint32(rng_x)
+    st = lib().bo_Calibrate(m.hmm, m.bg, m.om, m.om_fs3, m.om_fs5, m.ct, seed, float(lam), which, int(convert_flow), C.byref(x), out)
+    if st != OK:
+        raise RuntimeError(f"bo_Calibrate: status {st}")
+    return [float(v) for v in out], x.value
 
 
 def batch_forward_parser(model, dsq, starts, lengths, nthreads=1):
