@@ -22,7 +22,8 @@ struct CoreModel {                 // P7_HMM as read from a BATH3/f file (probab
   float evparam[8] = { -99999.f, -99999.f, -99999.f, -99999.f, -99999.f, -99999.f, -99999.f, -99999.f };
   bool  has_fs3 = false, has_fs5 = false, has_compo = false;
   float compo[kK] = { 0 };
-  std::string name, acc;
+  std::string name, acc, desc;
+  std::string rf, cs;              // [M+2] reference / consensus-structure annotation, 1..M; empty if the file has none
   std::vector<float> t, mat, ins;  // [(M+1)][7], [(M+1)][20], [(M+1)][20]
   std::vector<char>  consensus;    // [M+2], 1..M
 };

@@ -170,13 +170,16 @@ static int read_record(std::istream &in, CoreModel &h)
   if (!magic) return BATHHOST_EOF;
 
   h = CoreModel();
-  bool body = false;
+  bool body = false, has_rf = false, has_cs = false;
   while (std::getline(in, line)) {
     f = split(line);
     if (f.empty()) continue;
     const std::string &tag = f[0];
     if      (tag == "NAME" && f.size() > 1) h.name = f[1];
     else if (tag == "ACC"  && f.size() > 1) h.acc = f[1];
+    else if (tag == "DESC") { const size_t at = line.find_first_not_of(" \t", line.find("DESC") + 4); h.desc = (at == std::string::npos) ? "" : line.substr(at); }
+    else if (tag == "RF" && f.size() > 1) has_rf = (f[1] == "yes");
+    else if (tag == "CS" && f.size() > 1) has_cs = (f[1] == "yes");
     else if (tag == "LENG" && f.size() > 1) h.M = atoi(f[1].c_str());
     else if (tag == "MAXL" && f.size() > 1) h.max_length = atoi(f[1].c_str());
     else if (tag == "ALPH") { if (f.size() < 2 || f[1] != "amino") return BATHHOST_EFORMAT; }
@@ -203,6 +206,8 @@ static int read_record(std::istream &in, CoreModel &h)
   h.ins.assign((size_t) (M + 1) * kK, 0.0f);
   h.consensus.assign((size_t) M + 2, ' ');
   h.consensus[M + 1] = '\0';
+  if (has_rf) h.rf.assign((size_t) M + 2, ' ');
+  if (has_cs) h.cs.assign((size_t) M + 2, ' ');
 
   auto next_fields = [&](size_t need) -> bool {
     if (!std::getline(in, line)) return false;
@@ -226,6 +231,8 @@ static int read_record(std::istream &in, CoreModel &h)
     if (!next_fields(1 + kK) || atoi(f[0].c_str()) != k) return BATHHOST_EFORMAT;
     for (int x = 0; x < kK; ++x) h.mat[(size_t) k * kK + x] = neglog_to_prob(f[1 + x]);
     h.consensus[k] = (f.size() > (size_t) (2 + kK)) ? f[2 + kK][0] : '-';
+    if (has_rf) h.rf[k] = (f.size() > (size_t) (3 + kK)) ? f[3 + kK][0] : '-';       // match line: k, 20 emissions, MAP, CONS, RF, MM, CS
+    if (has_cs) h.cs[k] = (f.size() > (size_t) (5 + kK)) ? f[5 + kK][0] : '-';
     if (!next_fields(kK)) return BATHHOST_EFORMAT;
     for (int x = 0; x < kK; ++x) h.ins[(size_t) k * kK + x] = neglog_to_prob(f[x]);
     if (!next_fields(7)) return BATHHOST_EFORMAT;

@@ -174,8 +174,17 @@ struct Domain {
   std::vector<bathgpu_trace_step> tr;          // positions relative to the window
 };
 
+// P7_ALIDISPLAY as p7_alidisplay_fs_Create / p7_alidisplay_nonfs_Create fill it (src/p7_alidisplay.c:538-931, :937-1232):
+// one character per core trace position (five for the nucleotide line); codon[] = codon length, 0 delete, 6 stop codon
+struct AliDisplay {
+  std::string model, mline, aseq, ntseq, ppline, csline, rfline;
+  std::vector<uint8_t> codon;
+  int N = 0;
+};
+
 struct Hit {
   bathhost_hit pub;
+  AliDisplay ad;
   double sortkey;
   bool duplicate = false, reported = false;
 };
@@ -351,9 +360,37 @@ float ali_score(const bathhost_model *m, const std::vector<bathgpu_trace_step> &
 
 // the alignment summary p7_alidisplay_fs_Create derives from a trace (src/p7_alidisplay.c:696-895): frameshifts,
 // stop codons, percent identity and the CIGAR string
-void summarize_alignment(const bathhost_model *m, const std::vector<bathgpu_trace_step> &tr, const uint8_t *dsq, bathhost_hit &h)
+static const char kDnaSym[]   = "ACGT-RYMKSWHBVDN*~";
+static const char kAminoSym[] = "ACDEFGHIKLMNPQRSTVWY-BJZOUX*~";
+enum { Pxxx = 9 };                                          // p7P_xxx: the fifth 3-nucleotide pattern (src/hmmer.h, enum p7p_indel_e)
+
+static char encode_post_prob(float p) { return (p + 0.05 >= 1.0) ? '*' : (char) ((p + 0.05) * 10.0) + '0'; }     // p7_alidisplay_EncodePostProb
+
+// nuc_one .. nuc_five (src/p7_alidisplay.c:107-213): the five display characters of a quasi-codon; bases the alignment
+// treats as inserted are lower case, missing ones '-'
+static void codon_chars(int c, int indel, const int n[5], char out[5])
+{
+  auto up = [&](int z) { return kDnaSym[n[z]]; };
+  auto lo = [&](int z) { return (char) tolower(kDnaSym[n[z]]); };
+  out[0] = (c < 4) ? ' ' : (indel == PxXXX || indel == PxxXXX || indel == Pxxx) ? lo(0) : up(0);
+  if (c < 4) out[1] = (indel == P__X || indel == P_XX) ? '-' : (indel == PxXX || indel == Pxxx) ? lo(0) : up(0);
+  else       out[1] = (indel == PXXxX || indel == PxXXX || indel == PXXxxX) ? up(1) : lo(1);
+  if (c == 1 || indel == PX_X) out[2] = '-';
+  else if (indel == P_XX)      out[2] = up(0);
+  else if (c < 4)              out[2] = (indel == PXxX || indel == Pxxx) ? lo(1) : up(1);
+  else                         out[2] = (indel == PXxXX || indel == PxXXX || indel == PxxXXX) ? up(2) : lo(2);
+  if (indel == P__X)                        out[3] = up(0);
+  else if (indel == PX_X || indel == P_XX)  out[3] = up(1);
+  else if (c < 3)                           out[3] = '-';
+  else if (c == 3)                          out[3] = (indel == PXXx || indel == Pxxx) ? lo(2) : up(2);
+  else                                      out[3] = (indel == PXXxxX || indel == Pxxx) ? lo(3) : up(3);
+  out[4] = (c < 5) ? ' ' : (indel == Pxxx) ? lo(4) : up(4);
+}
+
+void summarize_alignment(const bathhost_model *m, const std::vector<bathgpu_trace_step> &tr, const uint8_t *dsq, bathhost_hit &h, AliDisplay *ad = nullptr)
 {
   const FsProfile &gm = m->gm5;
+  const size_t ld = (size_t) gm.M + 1;
   std::vector<const bathgpu_trace_step *> core;
   for (const auto &s : tr) if (s.st == TS_M || s.st == TS_D || s.st == TS_I) core.push_back(&s);
   std::string cigar;
@@ -367,6 +404,18 @@ void summarize_alignment(const bathhost_model *m, const std::vector<bathgpu_trac
       const int aa = gm.codons[(size_t) s.k * gm.maxcodons + ci];
       const int indel = gm.indel_pos[(size_t) s.k * gm.maxcodons + ci];
       if (aa == amino_code(m->hmm.consensus[s.k])) exact++;
+      if (ad) {
+        int n[5] = { 0, 0, 0, 0, 0 };
+        for (int z5 = 0; z5 < s.c; ++z5) n[z5] = dsq[s.i - (s.c - 1) + z5];
+        char cc[5];
+        codon_chars(s.c, indel, n, cc);
+        ad->ntseq.append(cc, 5);
+        ad->model += m->hmm.consensus[s.k];
+        ad->mline += (aa == amino_code(m->hmm.consensus[s.k])) ? m->hmm.consensus[s.k]
+                     : (expf(gm.rsc[(size_t) (gm.maxcodons + aa) * ld + s.k]) > 1.0) ? '+' : ' ';
+        ad->aseq += (char) toupper(kAminoSym[aa]);
+        ad->codon.push_back((uint8_t) ((s.c == 3 && (indel == PXXx || indel == PXxX || indel == PxXX)) ? 6 : s.c));
+      }
       if (s.c != 3) shifts++;
       else if (indel == PXXx || indel == PXxX || indel == PxXX) stops++;
       if (nxt != TS_M || s.c != 3) {
@@ -384,14 +433,30 @@ void summarize_alignment(const bathhost_model *m, const std::vector<bathgpu_trac
     } else if (s.st == TS_I) {
       const int ci = codon_index5(dsq, s.i, 3);
       const int indel = gm.indel_pos[(size_t) s.k * gm.maxcodons + ci];
-      if (indel == PXXx || indel == PXxX || indel == PxXX) stops++;
+      const bool stop = (indel == PXXx || indel == PXxX || indel == PxXX);
+      if (stop) stops++;
+      if (ad) {
+        const int aa = stop ? 27 : gm.codons[(size_t) s.k * gm.maxcodons + ci];
+        ad->model += '.'; ad->mline += ' ';
+        ad->aseq += (char) tolower(kAminoSym[aa]);
+        const char cc[5] = { ' ', kDnaSym[dsq[s.i - 2]], kDnaSym[dsq[s.i - 1]], kDnaSym[dsq[s.i]], ' ' };
+        ad->ntseq.append(cc, 5);
+        ad->codon.push_back(stop ? 6 : 3);
+      }
       n_count += 3;
       if (nxt != TS_I) { snprintf(buf, sizeof buf, "%dI", n_count); cigar += buf; n_count = 0; }
     } else {
+      if (ad) { ad->model += m->hmm.consensus[s.k]; ad->mline += ' '; ad->aseq += '-'; ad->ntseq += " --- "; ad->codon.push_back(0); }
       n_count += 3;
       if (nxt != TS_D) { snprintf(buf, sizeof buf, "%dD", n_count); cigar += buf; n_count = 0; }
     }
+    if (ad) {
+      ad->ppline += (s.st == TS_D) ? '.' : encode_post_prob(s.pp);
+      if (!m->hmm.cs.empty()) ad->csline += (s.st == TS_I) ? '.' : m->hmm.cs[s.k];
+      if (!m->hmm.rf.empty()) ad->rfline += (s.st == TS_I) ? '.' : m->hmm.rf[s.k];
+    }
   }
+  if (ad) ad->N = (int) core.size();
   h.shifts = shifts; h.stops = stops;
   h.pid = core.empty() ? 0.0f : ((float) exact / (float) core.size()) * 100;
   snprintf(h.cigar, sizeof h.cigar, "%s", cigar.c_str());
@@ -1364,7 +1429,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
         h.pub.pre_score = bitscore / kLog2;
         h.pub.envsc = dom.envsc; h.pub.oasc = dom.oasc;
         h.pub.trace_len = (int32_t) dom.tr.size();
-        summarize_alignment(m, dom.tr, wdsq, h.pub);
+        summarize_alignment(m, dom.tr, wdsq, h.pub, &h.ad);
         h.sortkey = -dom_lnP;
         return true;
     };
@@ -1560,6 +1625,26 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
           const bathgpu_trace_step &ts = dom.tr[z];
           const int nxt = dom.tr[z + 1].st;                 // z2 + 1 exists: the E state
           ncore++;
+          {                                                  // display lines (:1128-1215)
+            AliDisplay &ad = h.ad;
+            const char cons = m->hmm.consensus[ts.k];
+            if (ts.st == TS_D) { ad.model += cons; ad.mline += ' '; ad.aseq += '-'; ad.ntseq += " --- "; ad.codon.push_back(0); }
+            else {
+              const int x = res_o[pos];
+              const char cc[5] = { ' ', (char) toupper(kDnaSym[wdsq[ts.i - 2]]), (char) toupper(kDnaSym[wdsq[ts.i - 1]]), (char) toupper(kDnaSym[wdsq[ts.i]]), ' ' };
+              ad.ntseq.append(cc, 5);
+              ad.aseq += (char) toupper(kAminoSym[x]);
+              if (ts.st == TS_M) {
+                ad.model += cons;
+                ad.mline += (x == amino_code(cons)) ? cons : (expf(q.msc[(size_t) x * (q.M + 1) + ts.k]) > 1.0) ? '+' : ' ';
+                ad.codon.push_back(ts.c);
+              } else { ad.model += '.'; ad.mline += ' '; ad.codon.push_back(3); }
+            }
+            ad.ppline += (ts.st == TS_D) ? '.' : encode_post_prob(ts.pp);
+            if (!m->hmm.cs.empty()) ad.csline += (ts.st == TS_I) ? '.' : m->hmm.cs[ts.k];
+            if (!m->hmm.rf.empty()) ad.rfline += (ts.st == TS_I) ? '.' : m->hmm.rf[ts.k];
+            ad.N++;
+          }
           if (ts.st == TS_M) { if (res_o[pos] == amino_code(m->hmm.consensus[ts.k])) exact++; pos++; }
           else if (ts.st == TS_I) pos++;
           n_count += 3;
@@ -1742,6 +1827,138 @@ extern "C" int bathhost_search_format_tblout(const bathhost_search *s, int show_
     if (fs_pipe) put(" %7d %6d", h.pub.shifts, h.pub.stops);
     put(" %s\n", h.pub.cigar);
   }
+  *needed = out.size() + 1;
+  if (out.size() + 1 > cap) return buf ? BATHHOST_EINVAL : BATHHOST_OK;
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return BATHHOST_OK;
+}
+
+// p7_alidisplay_Print_BATH (src/p7_alidisplay.c:3758-4095) without the spliced-alignment and --frameline branches: blocks of
+// (CS) (RF) model / match / translation / codons / PP lines, each alignment column five characters wide
+static void print_alidisplay(std::string &out, const AliDisplay &ad, const std::string &hmmname, const char *sqname, int hmmfrom, int hmmto,
+                             long long sqfrom, long long sqto, int linewidth)
+{
+  char line[512];
+  auto put = [&](const char *fmt, auto... args) { snprintf(line, sizeof line, fmt, args...); out += line; };
+  auto textwidth = [](long long n) { int w = (n < 0) ? 1 : 0; while (n != 0) { n /= 10; w++; } return w; };
+  const int max_namewidth = 30, min_aliwidth = 40;
+  std::string show_hmm = hmmname, show_sq = sqname;
+  int namewidth = (int) std::max(show_hmm.size(), show_sq.size());
+  while (namewidth > max_namewidth + 3) {
+    std::string &longer = (show_hmm.size() > show_sq.size()) ? show_hmm : show_sq;
+    longer = longer.substr(0, max_namewidth) + "...";
+    namewidth = (int) std::max(show_hmm.size(), show_sq.size());
+  }
+  namewidth = std::max(namewidth, 8);
+  const int coordwidth = std::max(std::max(textwidth(hmmfrom), textwidth(hmmto)), std::max(textwidth(sqfrom), textwidth(sqto)));
+  int max_aliwidth = (linewidth > 0) ? linewidth - namewidth - 2 * coordwidth - 5 : ad.N;
+  if (max_aliwidth < ad.N && max_aliwidth < min_aliwidth) max_aliwidth = min_aliwidth;
+  max_aliwidth -= 4;
+  max_aliwidth /= 5;
+  const bool fwd = sqfrom < sqto;
+  long long i1 = sqfrom, i2 = fwd ? i1 - 1 : i1 + 1;
+  int k1 = hmmfrom, pos = 0;
+  auto row = [&](const std::string &chars, int w) { for (int i = 0; i < w && pos + i < (int) chars.size(); ++i) put("  %c  ", chars[pos + i]); };
+  while (pos < ad.N) {
+    if (pos > 0) out += "\n";
+    const int w = max_aliwidth;
+    int ni = 0, nk = 0;
+    for (int z = pos; z < pos + w && z < ad.N; ++z) {
+      if (ad.model[z] != '.' && ad.model[z] != ' ') nk++;
+      if (ad.aseq[z] != '-') ni++;
+    }
+    const int k2 = k1 + nk - 1;
+    if (!ad.csline.empty()) { put("  %*s ", namewidth + coordwidth + 1, " "); out += "  "; row(ad.csline, w); out += "  \n"; }
+    if (!ad.rfline.empty()) { put("  %*s ", namewidth + coordwidth + 1, " "); out += "  "; row(ad.rfline, w); out += "   RF\n"; }
+    put("  %*s %*d ", namewidth, show_hmm.c_str(), coordwidth, k1); out += "  "; row(ad.model, w); out += "  "; put(" %-*d\n", coordwidth, k2);
+    put("  %*s ", namewidth + coordwidth + 1, " "); out += "  "; row(ad.mline, w); out += "  \n";
+    put("  %*s ", namewidth + coordwidth + 1, " "); out += "  "; row(ad.aseq, w); out += "  \n";
+    put("  %*s", namewidth, show_sq.c_str());
+    if (ni > 0) put(" %*lld ", coordwidth, i1); else put(" %*s ", coordwidth, "-");
+    out += "  ";
+    for (int j = 0; j < w && pos + j < ad.N; ++j) {
+      out.append(ad.ntseq, (size_t) (pos + j) * 5, 5);
+      const int c = ad.codon[pos + j] == 6 ? 3 : ad.codon[pos + j];
+      i2 += fwd ? c : -c;
+    }
+    out += "  ";
+    if (ni > 0) put(" %-*lld\n", coordwidth, i2); else put(" %*s\n", coordwidth, "-");
+    put("  %*s ", namewidth + coordwidth + 1, ""); out += "  "; row(ad.ppline, w); out += "  "; out += " PP\n";
+    k1 += nk;
+    i1 = fwd ? i2 + 1 : i2 - 1;
+    pos += w;
+  }
+}
+
+// The hit-dependent part of bathsearch's report: p7_tophits_Targets, two blank lines, p7_tophits_Domains (with alignments), two blank
+// lines (src/p7_tophits.c:1073-1227, :1232-1410 as called from src/bathsearch.c:960-961) -- everything between the "Query:" block and
+// "Internal pipeline statistics summary:".  textw = --textw (150 by default; 0 = --notextw).
+extern "C" int bathhost_search_format_report(const bathhost_search *s, int textw, char *buf, size_t cap, size_t *needed)
+{
+  if (!s || !needed || (!buf && cap > 0)) return BATHHOST_EINVAL;
+  const bathhost_model *m = s->model;
+  const bool fs_pipe = s->opt.fs;
+  const double incE = 0.01;                                // --incE (src/p7_pipeline.c:166)
+  int namew = 8, posw = 6, nreported = 0;
+  for (const Hit &h : s->hits) {                           // p7_tophits_GetMaxNameLength / GetMaxPositionLength run over all hits
+    namew = std::max(namew, (int) strlen(h.pub.name));
+    if (h.pub.ali_from > 0) {
+      posw = std::max(posw, (int) std::to_string((long long) h.pub.ali_from).size());
+      posw = std::max(posw, (int) std::to_string((long long) h.pub.ali_to).size());
+    }
+    if (h.reported) nreported++;
+  }
+  std::string out;
+  char line[4096];
+  auto put = [&](const char *fmt, auto... args) { snprintf(line, sizeof line, fmt, args...); out += line; };
+
+  out += "Scores for complete hits:\n";
+  if (fs_pipe) {
+    put("  %9s %6s %5s  %-*s %*s %*s  %6s  %5s  %s\n", "E-value", " score", " bias", namew, "Sequence", posw, "start", posw, "end", "shifts", "stops", "Description");
+    put("  %9s %6s %5s  %-*s %*s %*s  %6s  %5s  %s\n", "-------", "------", "-----", namew, "--------", posw, "-----", posw, "-----", "------", "-----", "-----------");
+  } else {
+    put("  %9s %6s %5s  %-*s %*s %*s  %s\n", "E-value", " score", " bias", namew, "Sequence", posw, "start", posw, "end", "Description");
+    put("  %9s %6s %5s  %-*s %*s %*s  %s\n", "-------", "------", "-----", namew, "--------", posw, "-----", posw, "-----", "-----------");
+  }
+  bool printed_incthresh = false;
+  for (const Hit &h : s->hits) {
+    if (!h.reported) continue;
+    if (!(h.pub.evalue <= incE) && !printed_incthresh) { out += "  ------ inclusion threshold ------\n"; printed_incthresh = true; }
+    put("%c %9.2g %6.1f %5.1f  %-*s %*lld %*lld  ", ' ', h.pub.evalue, h.pub.score, h.pub.bias, namew, h.pub.name, posw, (long long) h.pub.ali_from,
+        posw, (long long) h.pub.ali_to);
+    if (fs_pipe) put("%6d  %5d", h.pub.shifts, h.pub.stops);
+    put("  %s\n", "");
+  }
+  if (nreported == 0) out += "\n   [No hits detected that satisfy reporting thresholds]\n";
+  out += "\n\n";
+
+  out += "Annotation for each hit (and alignments):\n";
+  for (const Hit &h : s->hits) {
+    if (!h.reported) continue;
+    put(">> %s  %s\n", h.pub.name, "");
+    if (fs_pipe) {
+      put("   %6s %5s %9s %10s %9s    %9s %9s    %6s  %5s %9s   %4s\n", "score", "bias", "   Evalue", "hmm-from", " hmm-to", " ali-from", "   ali-to",
+          "shifts", "stops", "   sq-len", "acc");
+      put("   %6s %5s %9s %10s %9s    %9s %9s    %6s  %5s %9s   %4s\n", "------", "-----", "---------", "--------", "-------", "---------", "---------",
+          "------", "-----", "---------", "----");
+    } else {
+      put("   %6s %5s %9s %10s %9s    %9s %9s    %9s   %4s\n", "score", "bias", "   Evalue", "hmm-from", " hmm-to", " ali-from", "   ali-to", "   sq-len", "acc");
+      put("   %6s %5s %9s %10s %9s    %9s %9s    %9s   %4s\n", "------", "-----", "---------", "--------", "-------", "---------", "---------", "---------", "----");
+    }
+    put(" %c %6.1f %5.1f %9.2g %10d %9d %c%c %9lld %9lld %c%c", (h.pub.evalue <= incE) ? '!' : '?', h.pub.score, h.pub.bias, h.pub.evalue,
+        h.pub.hmm_from, h.pub.hmm_to, (h.pub.hmm_from == 1) ? '[' : '.', (h.pub.hmm_to == m->hmm.M) ? ']' : '.',
+        (long long) h.pub.ali_from, (long long) h.pub.ali_to, (h.pub.ali_from == 1) ? '[' : '.', (h.pub.ali_to == h.pub.sq_len) ? ']' : '.');
+    if (fs_pipe) put(" %6d  %5d", h.pub.shifts, h.pub.stops);
+    put(" %9lld   %4.2f\n", (long long) h.pub.sq_len, (h.pub.oasc / (1.0 + fabs((float) (h.pub.env_to - h.pub.env_from) / 3))));
+    out += "\n  Alignment:\n";
+    put("  score: %.1f bits", h.pub.score);
+    out += "\n";
+    print_alidisplay(out, h.ad, m->hmm.name, h.pub.name, h.pub.hmm_from, h.pub.hmm_to, h.pub.ali_from, h.pub.ali_to, textw);
+    out += "\n";
+  }
+  if (nreported == 0) out += "\n   [No hits detected that satisfy reporting thresholds]\n";
+  out += "\n\n";
+
   *needed = out.size() + 1;
   if (out.size() + 1 > cap) return buf ? BATHHOST_EINVAL : BATHHOST_OK;
   memcpy(buf, out.c_str(), out.size() + 1);

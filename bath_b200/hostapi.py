@@ -16,7 +16,7 @@ EXPORTS = [
     "bathhost_search_create", "bathhost_search_destroy", "bathhost_search_last_error", "bathhost_search_sequence",
     "bathhost_search_finish", "bathhost_search_nhits", "bathhost_search_get_hit", "bathhost_search_get_stats",
     "bathhost_sample_region_segments", "bathhost_cluster_region_segments", "bathhost_search_format_tblout",
-    "bathhost_calibrate", "bathhost_model_lambda",
+    "bathhost_calibrate", "bathhost_model_lambda", "bathhost_search_format_report",
 ]
 
 
@@ -332,6 +332,19 @@ class Search:
         st = self.lib.bathhost_search_format_tblout(self.h, int(header), buf, need.value, C.byref(need))
         if st != OK:
             raise RuntimeError(f"bathhost_search_format_tblout: status {st}")
+        return buf.value.decode()
+
+    def report(self, textw=150):
+        """the hit-dependent part of bathsearch's main output: "Scores for complete hits" table and the per-hit annotation with
+        alignments (everything between the "Query:" block and the pipeline statistics), as bathsearch writes it"""
+        need = C.c_size_t(0)
+        f = self.lib.bathhost_search_format_report
+        f.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        f(self.h, int(textw), None, 0, C.byref(need))
+        buf = C.create_string_buffer(need.value)
+        st = f(self.h, int(textw), buf, need.value, C.byref(need))
+        if st != OK:
+            raise RuntimeError(f"bathhost_search_format_report: status {st}")
         return buf.value.decode()
 
     def stats(self):

@@ -181,6 +181,13 @@ int  bathhost_search_get_stats(const bathhost_search *s, bathhost_stats *st);
 /* The --tblout --cigar table of the reported hits as p7_tophits_TabularTargets writes it (src/p7_tophits.c:1603-1712): header
  * (if show_header) + one line per hit, NUL-terminated, without the trailer.  *needed = bytes required; call with buf = NULL to size. */
 int  bathhost_search_format_tblout(const bathhost_search *s, int show_header, char *buf, size_t cap, size_t *needed);
+/* The hit-dependent part of the main report, alignments included: "Scores for complete hits:" table (p7_tophits_Targets,
+ * src/p7_tophits.c:1073-1227), two blank lines, "Annotation for each hit (and alignments):" with one block per reported hit
+ * (p7_tophits_Domains, :1232-1410; alignment display built as p7_alidisplay_fs_Create / p7_alidisplay_nonfs_Create do,
+ * src/p7_alidisplay.c:538-931 / :937-1232, and printed as p7_alidisplay_Print_BATH, :3758-4095), two blank lines -- what bathsearch
+ * writes between the "Query:" block and "Internal pipeline statistics summary:" (src/bathsearch.c:960-961).  textw = --textw
+ * (150 by default, 0 = unlimited).  Same sizing protocol as bathhost_search_format_tblout. */
+int  bathhost_search_format_report(const bathhost_search *s, int textw, char *buf, size_t cap, size_t *needed);
 
 /* ---- f4: E-value calibration by brief simulation (calibrate.cpp) ------------------------------------------------
  * p7_Calibrate with the frameshift branch (src/evalues.c:64-183: p7_Lambda, p7_MSVMu, p7_ViterbiMu, p7_Tau, p7_fs_Tau_3codons,

@@ -1,0 +1,71 @@
+"""bathsearch's main report, alignments included: Search.report() / bathhost_search_format_report against the
+outputs the reference ships in tutorial/.
+
+  * AMP_N-fs.out (bathsearch --fs: one hit with 6 frameshifts and a stop codon) and PTH2.out (default pipeline: 4 hits on both strands,
+    model with a CS line): everything between the "Query:" block and the pipeline statistics -- the "Scores for complete hits" table,
+    the per-hit table line and every alignment block -- byte for byte;
+  * AMP_N.out and MET-ct4.out (2 queries, codon table 4, 6 hits) were written by an earlier program version whose per-hit table has two
+    more columns: their alignment blocks (model / match / translation / codon / PP lines with coordinates) byte for byte.
+The CPU tests put the oracle's stage calls behind the host pipeline; the gpu tests run the product path."""
+import re
+
+import pytest
+
+import common
+
+
+def run(hostapi, hmm, fasta, index=0, backend=None, gpu_ctx=None, **opt):
+    model = hostapi.QueryModel(common.golden(hmm), index)
+    search = hostapi.Search(model, gpu_ctx=gpu_ctx, backend=backend, **opt)
+    for name, seq in hostapi.read_fasta(common.golden(fasta)):
+        search.add_sequence(name, hostapi.digitize_dna(seq))
+    search.finish()
+    text = search.report()
+    search.close()
+    return text
+
+
+def hit_section(path):
+    txt = open(path).read()
+    return txt[txt.index("Scores for complete hits:"):txt.index("Internal pipeline statistics summary:")]
+
+
+def alignment_blocks(txt):
+    return [m.group(1) for m in re.finditer(r"  Alignment:\n(.*?)\n\n(?=>>|\n|Internal)", txt, re.S)]
+
+
+def check_all(hostapi, **where):
+    assert run(hostapi, "AMP_N.bhmm", "target-AMP_N.fa", **where) == hit_section(common.golden("AMP_N-fs.out"))
+    assert run(hostapi, "PTH2.bhmm", "target-PTH2.fa", std_only=1, **where) == hit_section(common.golden("PTH2.out"))
+    got = alignment_blocks(run(hostapi, "AMP_N.bhmm", "target-AMP_N.fa", std_only=1, **where))
+    assert len(got) == 1 and got == alignment_blocks(open(common.golden("AMP_N.out")).read())
+    sections = open(common.golden("MET-ct4.out")).read().split("Query:")[1:]
+    for q in range(2):
+        got = alignment_blocks(run(hostapi, "MET-ct4.bhmm", "target-MET.fa", index=q, std_only=1, **where))
+        assert len(got) == 3 and got == alignment_blocks(sections[q])
+
+
+def test_report_matches_shipped_outputs_cpu_backend(oracle):
+    from bath_b200 import hostapi
+    be, keep = oracle.cpu_backend(4)
+    check_all(hostapi, backend=be)
+    del keep
+
+
+def test_report_without_hits(oracle):
+    from bath_b200 import hostapi
+    be, keep = oracle.cpu_backend(2)
+    model = hostapi.QueryModel(common.golden("PTH2.bhmm"))
+    search = hostapi.Search(model, backend=be)
+    rng = __import__("numpy").random.default_rng(5)
+    search.add_sequence("noise", hostapi.digitize_dna("".join("ACGT"[z] for z in rng.integers(0, 4, 3000))))
+    assert search.finish() == []
+    text = search.report()
+    assert text.count("[No hits detected that satisfy reporting thresholds]") == 2 and text.endswith("\n\n\n")
+    del keep
+
+
+@pytest.mark.gpu
+def test_report_matches_shipped_outputs_gpu(gpu_ctx):
+    from bath_b200 import hostapi
+    check_all(hostapi, gpu_ctx=gpu_ctx)
