@@ -1965,6 +1965,47 @@ extern "C" int bathhost_search_format_report(const bathhost_search *s, int textw
   return BATHHOST_OK;
 }
 
+// One query's section of bathsearch's output without the lines that depend on the run (banner, option echo, timings): the "Query:"
+// block (src/bathsearch.c:783-785), bathhost_search_format_report, and p7_pli_Statistics up to "Total number of hits"
+// (src/p7_pipeline.c:1836-1874; n_output / pos_output as src/bathsearch.c:950-957).
+extern "C" int bathhost_search_format_output(const bathhost_search *s, int textw, char *buf, size_t cap, size_t *needed)
+{
+  if (!s || !needed || (!buf && cap > 0)) return BATHHOST_EINVAL;
+  const bathhost_model *m = s->model;
+  std::string out;
+  char line[1024];
+  auto put = [&](const char *fmt, auto... args) { snprintf(line, sizeof line, fmt, args...); out += line; };
+  put("Query:       %s  [M=%d]\n", m->hmm.name.c_str(), m->hmm.M);
+  if (!m->hmm.acc.empty())  put("Accession:   %s\n", m->hmm.acc.c_str());
+  if (!m->hmm.desc.empty()) put("Description: %s\n", m->hmm.desc.c_str());
+  size_t need = 0;
+  int st = bathhost_search_format_report(s, textw, nullptr, 0, &need);
+  if (st != BATHHOST_OK) return st;
+  std::vector<char> rep(need);
+  if ((st = bathhost_search_format_report(s, textw, rep.data(), need, &need)) != BATHHOST_OK) return st;
+  out += rep.data();
+  long long n_output = 0, pos_output = 0;
+  for (const Hit &h : s->hits) {
+    if (!h.reported) continue;
+    n_output++;
+    pos_output += 1 + std::llabs((long long) h.pub.ali_to - (long long) h.pub.ali_from);
+  }
+  const bathhost_stats &t = s->st;
+  const double denom = (double) t.nres;                     // nres * nmodels, one model per search object
+  out += "Internal pipeline statistics summary:\n-------------------------------------\n";
+  put("Query model(s):              %15lld  (%lld nodes)\n", 1LL, (long long) m->hmm.M);
+  put("Target %-12s          %15lld  (%lld residues searched)\n", "sequence(s):", (long long) t.nseqs, (long long) t.nres);
+  put("Residues passing SSV filter: %15lld  (%.3g); expected (%.3g)\n", (long long) t.pos_past_msv, (double) t.pos_past_msv / denom, s->opt.F1);
+  put("Residues passing bias filter:%15lld  (%.3g); expected (%.3g)\n", (long long) t.pos_past_bias, (double) t.pos_past_bias / denom, s->opt.F1);
+  put("Residues passing Vit filter: %15lld  (%.3g); expected (%.3g)\n", (long long) t.pos_past_vit, (double) t.pos_past_vit / denom, s->opt.F2);
+  put("Residues passing Fwd filter: %15lld  (%.3g); expected (%.3g)\n", (long long) t.pos_past_fwd, (double) t.pos_past_fwd / denom, s->opt.F3);
+  put("Total number of hits:        %15d  (%.3g)\n", (int) n_output, (double) pos_output / denom);
+  *needed = out.size() + 1;
+  if (out.size() + 1 > cap) return buf ? BATHHOST_EINVAL : BATHHOST_OK;
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return BATHHOST_OK;
+}
+
 extern "C" int bathhost_search_get_stats(const bathhost_search *s, bathhost_stats *st)
 {
   if (!s || !st) return BATHHOST_EINVAL;

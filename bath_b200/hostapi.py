@@ -16,7 +16,7 @@ EXPORTS = [
     "bathhost_search_create", "bathhost_search_destroy", "bathhost_search_last_error", "bathhost_search_sequence",
     "bathhost_search_finish", "bathhost_search_nhits", "bathhost_search_get_hit", "bathhost_search_get_stats",
     "bathhost_sample_region_segments", "bathhost_cluster_region_segments", "bathhost_search_format_tblout",
-    "bathhost_calibrate", "bathhost_model_lambda", "bathhost_search_format_report",
+    "bathhost_calibrate", "bathhost_model_lambda", "bathhost_search_format_report", "bathhost_search_format_output",
 ]
 
 
@@ -334,17 +334,23 @@ class Search:
             raise RuntimeError(f"bathhost_search_format_tblout: status {st}")
         return buf.value.decode()
 
+    def output(self, textw=150):
+        """one query's section of bathsearch's output from "Query:" to "Total number of hits:" (no banner, no timings)"""
+        return self._format(self.lib.bathhost_search_format_output, textw)
+
     def report(self, textw=150):
         """the hit-dependent part of bathsearch's main output: "Scores for complete hits" table and the per-hit annotation with
         alignments (everything between the "Query:" block and the pipeline statistics), as bathsearch writes it"""
+        return self._format(self.lib.bathhost_search_format_report, textw)
+
+    def _format(self, f, textw):
         need = C.c_size_t(0)
-        f = self.lib.bathhost_search_format_report
         f.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
         f(self.h, int(textw), None, 0, C.byref(need))
         buf = C.create_string_buffer(need.value)
         st = f(self.h, int(textw), buf, need.value, C.byref(need))
         if st != OK:
-            raise RuntimeError(f"bathhost_search_format_report: status {st}")
+            raise RuntimeError(f"{f.__name__}: status {st}")
         return buf.value.decode()
 
     def stats(self):

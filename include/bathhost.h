@@ -188,6 +188,10 @@ int  bathhost_search_format_tblout(const bathhost_search *s, int show_header, ch
  * writes between the "Query:" block and "Internal pipeline statistics summary:" (src/bathsearch.c:960-961).  textw = --textw
  * (150 by default, 0 = unlimited).  Same sizing protocol as bathhost_search_format_tblout. */
 int  bathhost_search_format_report(const bathhost_search *s, int textw, char *buf, size_t cap, size_t *needed);
+/* One query's section of bathsearch's output minus the run-dependent lines (banner, option echo, "# CPU time", "# Mc/sec", "//"):
+ * "Query:" / "Accession:" / "Description:" (src/bathsearch.c:783-785), the report above, and p7_pli_Statistics from "Internal pipeline
+ * statistics summary:" to "Total number of hits:" (src/p7_pipeline.c:1836-1874).  Call after bathhost_search_finish. */
+int  bathhost_search_format_output(const bathhost_search *s, int textw, char *buf, size_t cap, size_t *needed);
 
 /* ---- f4: E-value calibration by brief simulation (calibrate.cpp) ------------------------------------------------
  * p7_Calibrate with the frameshift branch (src/evalues.c:64-183: p7_Lambda, p7_MSVMu, p7_ViterbiMu, p7_Tau, p7_fs_Tau_3codons,

@@ -14,13 +14,13 @@ import pytest
 import common
 
 
-def run(hostapi, hmm, fasta, index=0, backend=None, gpu_ctx=None, **opt):
+def run(hostapi, hmm, fasta, index=0, backend=None, gpu_ctx=None, whole=False, **opt):
     model = hostapi.QueryModel(common.golden(hmm), index)
     search = hostapi.Search(model, gpu_ctx=gpu_ctx, backend=backend, **opt)
     for name, seq in hostapi.read_fasta(common.golden(fasta)):
         search.add_sequence(name, hostapi.digitize_dna(seq))
     search.finish()
-    text = search.report()
+    text = search.output() if whole else search.report()
     search.close()
     return text
 
@@ -30,6 +30,13 @@ def hit_section(path):
     return txt[txt.index("Scores for complete hits:"):txt.index("Internal pipeline statistics summary:")]
 
 
+def query_section(path):
+    """from "Query:" to the "Total number of hits:" line: everything but the banner, the option echo and the timings"""
+    txt = open(path).read()
+    end = txt.index("\n", txt.index("Total number of hits:")) + 1
+    return txt[txt.index("Query:"):end]
+
+
 def alignment_blocks(txt):
     return [m.group(1) for m in re.finditer(r"  Alignment:\n(.*?)\n\n(?=>>|\n|Internal)", txt, re.S)]
 
@@ -37,6 +44,8 @@ def alignment_blocks(txt):
 def check_all(hostapi, **where):
     assert run(hostapi, "AMP_N.bhmm", "target-AMP_N.fa", **where) == hit_section(common.golden("AMP_N-fs.out"))
     assert run(hostapi, "PTH2.bhmm", "target-PTH2.fa", std_only=1, **where) == hit_section(common.golden("PTH2.out"))
+    assert run(hostapi, "AMP_N.bhmm", "target-AMP_N.fa", whole=True, **where) == query_section(common.golden("AMP_N-fs.out"))
+    assert run(hostapi, "PTH2.bhmm", "target-PTH2.fa", whole=True, std_only=1, **where) == query_section(common.golden("PTH2.out"))
     got = alignment_blocks(run(hostapi, "AMP_N.bhmm", "target-AMP_N.fa", std_only=1, **where))
     assert len(got) == 1 and got == alignment_blocks(open(common.golden("AMP_N.out")).read())
     sections = open(common.golden("MET-ct4.out")).read().split("Query:")[1:]
