@@ -193,6 +193,7 @@ struct Options {
   double F1 = 0.02, F2 = 1e-3, F3 = 1e-5, F4 = 5e-4, E = 10.0;
   int    min_orf = 20, block_length = 262144, lanes_u8 = 16, lanes_i16 = 8;
   bool   do_bias = true, do_null2 = true, top = true, bottom = true;
+  bool   frameline = false;           // --frameline: a FRAME line in every alignment block
   bool   fs = true;                   // --fs; false: bathsearch's default standard-translation pipeline (src/p7_pipeline.c:106-107)
 };
 
@@ -1687,6 +1688,7 @@ extern "C" int bathhost_search_create(const bathhost_model *m, const bathhost_ba
     s->opt.do_bias = !o->no_bias; s->opt.do_null2 = !o->no_null2;
     s->opt.top = !o->bottom_only; s->opt.bottom = !o->top_only;
     s->opt.fs = !o->std_only;
+    s->opt.frameline = o->show_frameline != 0;
   }
   if (!genetic_code(m->ct, s->gcode)) { delete s; return BATHHOST_EINVAL; }
   s->compo.assign(m->hmm.compo, m->hmm.compo + kK);
@@ -1836,7 +1838,7 @@ extern "C" int bathhost_search_format_tblout(const bathhost_search *s, int show_
 // p7_alidisplay_Print_BATH (src/p7_alidisplay.c:3758-4095) without the spliced-alignment and --frameline branches: blocks of
 // (CS) (RF) model / match / translation / codons / PP lines, each alignment column five characters wide
 static void print_alidisplay(std::string &out, const AliDisplay &ad, const std::string &hmmname, const char *sqname, int hmmfrom, int hmmto,
-                             long long sqfrom, long long sqto, int linewidth)
+                             long long sqfrom, long long sqto, int linewidth, bool show_frameline)
 {
   char line[512];
   auto put = [&](const char *fmt, auto... args) { snprintf(line, sizeof line, fmt, args...); out += line; };
@@ -1876,13 +1878,31 @@ static void print_alidisplay(std::string &out, const AliDisplay &ad, const std::
     put("  %*s", namewidth, show_sq.c_str());
     if (ni > 0) put(" %*lld ", coordwidth, i1); else put(" %*s ", coordwidth, "-");
     out += "  ";
+    std::vector<int> frameline;
     for (int j = 0; j < w && pos + j < ad.N; ++j) {
       out.append(ad.ntseq, (size_t) (pos + j) * 5, 5);
       const int c = ad.codon[pos + j] == 6 ? 3 : ad.codon[pos + j];
+      const long long c1 = fwd ? i2 : i2 - 1;
       i2 += fwd ? c : -c;
+      int frame = 0;                                         // p7_alidiplay_frame (:3719-3735)
+      if (ad.codon[pos + j] != 0 && ad.codon[pos + j] != 6) {
+        if (c1 < i2) { frame = (int) ((i2 + 1) % 3); if (frame == 0) frame = 3; }
+        else         { frame = -(int) (i2 % 3);      if (frame == 0) frame = -3; }
+      }
+      frameline.push_back(frame);
     }
     out += "  ";
     if (ni > 0) put(" %-*lld\n", coordwidth, i2); else put(" %*s\n", coordwidth, "-");
+    if (show_frameline) {                                    // --frameline (:3998-4013)
+      put("  %*s ", namewidth + coordwidth + 1, ""); out += "  ";
+      for (size_t j = 0; j < frameline.size(); ++j) {
+        if (frameline[j] > 0)                put("  %d  ", frameline[j]);
+        else if (frameline[j] < 0)           put(" %d  ", frameline[j]);
+        else if (ad.codon[pos + j] == 6)     put("  %d  ", frameline[j]);
+        else                                 out += "  .  ";
+      }
+      out += "  "; out += " FRAME\n";
+    }
     put("  %*s ", namewidth + coordwidth + 1, ""); out += "  "; row(ad.ppline, w); out += "  "; out += " PP\n";
     k1 += nk;
     i1 = fwd ? i2 + 1 : i2 - 1;
@@ -1953,7 +1973,7 @@ extern "C" int bathhost_search_format_report(const bathhost_search *s, int textw
     out += "\n  Alignment:\n";
     put("  score: %.1f bits", h.pub.score);
     out += "\n";
-    print_alidisplay(out, h.ad, m->hmm.name, h.pub.name, h.pub.hmm_from, h.pub.hmm_to, h.pub.ali_from, h.pub.ali_to, textw);
+    print_alidisplay(out, h.ad, m->hmm.name, h.pub.name, h.pub.hmm_from, h.pub.hmm_to, h.pub.ali_from, h.pub.ali_to, textw, s->opt.frameline);
     out += "\n";
   }
   if (nreported == 0) out += "\n   [No hits detected that satisfy reporting thresholds]\n";

@@ -42,7 +42,8 @@ class Backend(C.Structure):
 class Options(C.Structure):
     _fields_ = [("F1", C.c_double), ("F2", C.c_double), ("F3", C.c_double), ("F4", C.c_double), ("E", C.c_double),
                 ("min_orf_len", C.c_int32), ("block_length", C.c_int32), ("cpu_lanes_u8", C.c_int32), ("cpu_lanes_i16", C.c_int32),
-                ("no_bias", C.c_int32), ("no_null2", C.c_int32), ("top_only", C.c_int32), ("bottom_only", C.c_int32), ("std_only", C.c_int32)]
+                ("no_bias", C.c_int32), ("no_null2", C.c_int32), ("top_only", C.c_int32), ("bottom_only", C.c_int32), ("std_only", C.c_int32),
+                ("show_frameline", C.c_int32)]
 
 
 class Hit(C.Structure):

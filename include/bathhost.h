@@ -136,6 +136,7 @@ typedef struct {
   int32_t cpu_lanes_u8, cpu_lanes_i16;   /* stripe geometry of the CPU build to match: 16/8 (SSE) */
   int32_t no_bias, no_null2, top_only, bottom_only;
   int32_t std_only;           /* 0: bathsearch --fs; 1: bathsearch's default pipeline (standard translation only) */
+  int32_t show_frameline;     /* --frameline: the report's alignment blocks carry a FRAME line (src/p7_alidisplay.c:3998-4013) */
 } bathhost_options;
 
 typedef struct {

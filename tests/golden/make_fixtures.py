@@ -15,6 +15,7 @@ FILES = [
     "tutorial/PTH2.bhmm", "tutorial/target-PTH2.fa", "tutorial/PTH2.out", "tutorial/PTH2.tbl", "tutorial/PTH2-cigar.tbl",
     "tutorial/tRNA-synthetases.bhmm", "tutorial/PTHR37536.bhmm", "tutorial/AMP_N.out",
     "tutorial/MET-ct4.bhmm", "tutorial/target-MET.fa", "tutorial/MET-ct4.out",
+    "tutorial/AMP_N-frameline.out",
     "tutorial/tRNA-proteins.bhmm",      # 12 models whose FS3/FS5 STATS lines one bathconvert run produced: calibration golden values
     "testsuite/2OG-FeII_Oxy_3.bhmm", "testsuite/2OG-FeII_Oxy_3-nt-fs.fa", "testsuite/2OG-FeII_Oxy_3-nt.fa",
 ]

@@ -4,7 +4,7 @@ outputs the reference ships in tutorial/.
   * AMP_N-fs.out (bathsearch --fs: one hit with 6 frameshifts and a stop codon) and PTH2.out (default pipeline: 4 hits on both strands,
     model with a CS line): everything between the "Query:" block and the pipeline statistics -- the "Scores for complete hits" table,
     the per-hit table line and every alignment block -- byte for byte;
-  * AMP_N.out and MET-ct4.out (2 queries, codon table 4, 6 hits) were written by an earlier program version whose per-hit table has two
+  * AMP_N-frameline.out (--fs --frameline), AMP_N.out and MET-ct4.out (2 queries, codon table 4, 6 hits) were written by an earlier program version whose per-hit table has two
     more columns: their alignment blocks (model / match / translation / codon / PP lines with coordinates) byte for byte.
 The CPU tests put the oracle's stage calls behind the host pipeline; the gpu tests run the product path."""
 import re
@@ -48,6 +48,8 @@ def check_all(hostapi, **where):
     assert run(hostapi, "PTH2.bhmm", "target-PTH2.fa", whole=True, std_only=1, **where) == query_section(common.golden("PTH2.out"))
     got = alignment_blocks(run(hostapi, "AMP_N.bhmm", "target-AMP_N.fa", std_only=1, **where))
     assert len(got) == 1 and got == alignment_blocks(open(common.golden("AMP_N.out")).read())
+    got = alignment_blocks(run(hostapi, "AMP_N.bhmm", "target-AMP_N.fa", show_frameline=1, **where))       # bathsearch --fs --frameline
+    assert len(got) == 1 and " FRAME\n" in got[0] and got == alignment_blocks(open(common.golden("AMP_N-frameline.out")).read())
     sections = open(common.golden("MET-ct4.out")).read().split("Query:")[1:]
     for q in range(2):
         got = alignment_blocks(run(hostapi, "MET-ct4.bhmm", "target-MET.fa", index=q, std_only=1, **where))
