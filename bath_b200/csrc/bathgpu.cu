@@ -49,6 +49,8 @@ struct FsProfileImage {
   DevBuf emis_bck, cellb3;   // the 3-codon Backward parser's table copy and constants (fs_backward.cuh, Bck3Consts)
   DevBuf emis_fwd; // [nrows][mpad] the Forward parsers' copy: match->match odds folded in as well (fs_parser.cuh, FwdConsts)
   DevBuf cellc;    // forward lane constants
+  DevBuf cellmw;   // the same for the multi-warp Forward kernel (J >= 16: 8 nodes per lane, J/8 warps per window)
+  int    mw_scan_steps = 5;
   DevBuf cellb;    // backward lane constants
   DevBuf cellf5;   // 5-codon full-matrix Forward lane constants (fs_domain.cuh)
   DevBuf amino;    // [20][mpad] amino-acid odds, unfolded, permuted (null2)
@@ -141,7 +143,7 @@ extern "C" void bathgpu_destroy(bathgpu_ctx *ctx)
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (FsProfileImage *im : { &ctx->fs3, &ctx->fs5 }) {
-    im->emis.release(); im->cellc.release(); im->cellb.release(); im->cellf5.release(); im->amino.release();
+    im->emis.release(); im->cellc.release(); im->cellmw.release(); im->cellb.release(); im->cellf5.release(); im->amino.release();
     im->oaflags.release(); im->oapass.release(); im->tfvraw.release(); im->zinv.release(); im->emis_fwd.release(); im->emis_bck.release(); im->cellb3.release();
   }
   for (TargetSlot &t : ctx->slot) { t.dna_bytes.release(); t.dna4.release(); t.residues.release(); }
@@ -362,6 +364,50 @@ extern "C" int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int n
       if (biggest < 1.0e-9 && im.scan_steps == 5) im.scan_steps = std::max(s, 2);
       b.swap(nb);
     }
+    if (which == 3 && J >= 16) {
+      // multi-warp Forward kernel (fs_parser_mw.cuh): JW nodes per lane, NW = J/JW warps, virtual lane v = 32 w + lane owns nodes
+      // JW v + 1 .. JW v + JW
+      const int JW = kMwNodesPerLane, NW = J / JW, VL = 32 * NW;
+      std::vector<float> mw((size_t)(5 * JW + 6) * VL + NW, 0.0f);
+      std::vector<double> lp(VL, 1.0), lpfull(VL, 1.0);
+      for (int v = 0; v < VL; ++v)
+        for (int j = 0; j < JW; ++j) {
+          const int k = v * JW + j + 1;
+          if (k <= M) {
+            const double sn = sK[k + 1];
+            mw[(size_t)(0 * JW + j) * VL + v] = (float)(1.0 / mmK(k));
+            mw[(size_t)(1 * JW + j) * VL + v] = (k >= 2) ? (float)(gK(k) * T(tDM, k) / sn) : 0.0f;
+            mw[(size_t)(2 * JW + j) * VL + v] = (float)ddS(k);
+            mw[(size_t)(3 * JW + j) * VL + v] = (float)std::max(T(tMI, k) * T(tIM, k) / (zK[k] * sn * mmK(k)), 1.0e-20);
+            mw[(size_t)(4 * JW + j) * VL + v] = (float)T(tII, k);
+          }
+          lp[v] *= ddS(k); lpfull[v] *= T(tDD, k);
+        }
+      im.mw_scan_steps = 3;
+      for (int w = 0; w < NW; ++w) {
+        std::vector<double> bsw(lp.begin() + 32 * w, lp.begin() + 32 * w + 32), bw(lpfull.begin() + 32 * w, lpfull.begin() + 32 * w + 32);
+        double q = 1.0;
+        for (int lane = 0; lane < 32; ++lane) { mw[(size_t)(5 * JW + 5) * VL + 32 * w + lane] = (float)q; q *= lp[32 * w + lane]; }
+        mw[(size_t)(5 * JW + 6) * VL + w] = (float)q;                     // PW(w): the whole warp's product
+        int need = 5;
+        for (int s2 = 0; s2 < 5; ++s2) {
+          const int d = 1 << s2;
+          std::vector<double> nbs(bsw), nb(bw);
+          double biggest = 0.0;
+          for (int lane = 0; lane < 32; ++lane) {
+            mw[(size_t)(5 * JW + s2) * VL + 32 * w + lane] = (lane >= d) ? (float)bsw[lane] : 0.0f;
+            if (lane >= d) { biggest = std::max(biggest, bw[lane]); nbs[lane] = bsw[lane] * bsw[lane - d]; nb[lane] = bw[lane] * bw[lane - d]; }
+          }
+          bsw.swap(nbs); bw.swap(nb);
+          if (biggest < 1.0e-9 && need == 5) need = std::max(s2, 3);
+        }
+        im.mw_scan_steps = std::max(im.mw_scan_steps, need);
+      }
+      if (getenv("BATHGPU_FULL_SCAN")) im.mw_scan_steps = 5;
+      if (im.cellmw.reserve(mw.size() * sizeof(float)) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
+      CUDA_TRY(ctx, cudaMemcpyAsync(im.cellmw.p, mw.data(), mw.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    } else im.cellmw.release();
     if (getenv("BATHGPU_FULL_SCAN")) im.scan_steps = 5;
     if (im.cellc.reserve(cc.size() * sizeof(float)) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
     CUDA_TRY(ctx, cudaMemcpyAsync(im.cellc.p, cc.data(), cc.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
@@ -715,7 +761,7 @@ extern "C" int bathgpu_fs_fwd_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_
     a.emis = im.emis_fwd.as<float>(); a.cellc = im.cellc.as<float>(); a.dna4 = S.dna4.as<uint32_t>();
     a.wins = ctx->wins.as<WindowDesc>() + w0; a.nwin = w1 - w0; a.mpad = im.mpad; a.tEM = xfE[0]; a.tEL = xfE[1];
     a.fwdsc = ctx->fwdsc.as<float>() + w0; a.status = ctx->status.as<int>() + w0; a.xmx = nullptr; a.xoff = nullptr;
-    a.counter = ctx->counter.as<int>() + launches; a.scan_steps = im.scan_steps;
+    a.counter = ctx->counter.as<int>() + launches; a.scan_steps = im.scan_steps; a.cellmw = im.cellmw.as<float>(); a.mw_scan_steps = im.mw_scan_steps;
     CUDA_TRY(ctx, dispatch_fwd(false, im.J, a, ctx->prop.multiProcessorCount, s));
     ++launches;
     w0 = w1;
@@ -794,7 +840,7 @@ extern "C" int bathgpu_fs_fwd_staged(bathgpu_ctx *ctx, const float xfE[2])
   a.wins = ctx->wins.as<WindowDesc>(); a.nwin = ctx->nstaged; a.mpad = im.mpad;
   a.tEM = xfE[0]; a.tEL = xfE[1];
   a.fwdsc = ctx->fwdsc.as<float>(); a.status = ctx->status.as<int>();
-  a.xmx = nullptr; a.xoff = nullptr; a.counter = ctx->counter.as<int>(); a.scan_steps = im.scan_steps;
+  a.xmx = nullptr; a.xoff = nullptr; a.counter = ctx->counter.as<int>(); a.scan_steps = im.scan_steps; a.cellmw = im.cellmw.as<float>(); a.mw_scan_steps = im.mw_scan_steps;
 
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
@@ -869,7 +915,7 @@ static int bck_decode_chunk(bathgpu_ctx *ctx, const bathgpu_window *wins, int n,
   fa.emis = im.emis_fwd.as<float>(); fa.cellc = im.cellc.as<float>(); fa.dna4 = ctx->S().dna4.as<uint32_t>();
   fa.wins = ctx->wins.as<WindowDesc>(); fa.nwin = n; fa.mpad = im.mpad; fa.tEM = xfE[0]; fa.tEL = xfE[1];
   fa.fwdsc = ctx->fwdsc.as<float>(); fa.status = ctx->status.as<int>();
-  fa.xmx = ctx->fxmx.as<float>(); fa.xoff = ctx->xoff.as<long long>(); fa.counter = ctx->counter.as<int>(); fa.scan_steps = im.scan_steps;
+  fa.xmx = ctx->fxmx.as<float>(); fa.xoff = ctx->xoff.as<long long>(); fa.counter = ctx->counter.as<int>(); fa.scan_steps = im.scan_steps; fa.cellmw = im.cellmw.as<float>(); fa.mw_scan_steps = im.mw_scan_steps;
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
   CUDA_TRY(ctx, dispatch_fwd(true, im.J, fa, sms, ctx->stream));
 

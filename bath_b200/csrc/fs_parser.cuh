@@ -56,6 +56,8 @@ struct FsParserArgs {
   const long long *xoff;
   int            *counter;     // work-queue counter
   int             scan_steps;  // steps of the D->D warp scan this profile needs (5 = all; fewer when the D->D odds products die out)
+  const float    *cellmw;      // lane-constant image of the multi-warp kernel (fs_parser_mw.cuh); null for models the one-warp kernels keep in registers
+  int             mw_scan_steps;
 };
 
 template <int J> struct VecOf { static constexpr int V = (J % 4 == 0) ? 4 : ((J % 2 == 0) ? 2 : 1); };

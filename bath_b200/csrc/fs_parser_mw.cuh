@@ -18,8 +18,7 @@
 
 namespace bathgpu {
 
-// lane-constant image of the multi-warp kernel: [MW_ROWS][32 NW] floats, then PW[NW]
-enum { MW_QM = 0, MW_DM = 8, MW_DD = 16, MW_HI = 24, MW_II = 32, MW_BS = 40, MW_Q = 45, MW_ROWS = 46 };
+// lane-constant image of the multi-warp kernel: [5 JW + 6][32 NW] floats (qm, dm, dd, hi, ii per node; 5 scan multipliers; Q), then PW[NW]
 
 template <int NW> struct MwShared {
   float A[2][NW], E[2][NW], W[2][NW];
@@ -27,18 +26,27 @@ template <int NW> struct MwShared {
 };
 
 // first half of a row: emissions, match values, the warp's E partial and its delete-chain scan with zero carry-in
-template <int PH, int NS>
-__device__ __forceinline__ void mw_row_front(const FwdState<8> &S, const FwdConsts<8> &K, const char *__restrict__ emis_lane, unsigned rowbytes,
-                                             uint32_t cw, float (&m)[8], float &epart, float &A, float &dloc)
+// the three table rows of one DP row, this lane's 8 nodes.  The table of a long model (1.1-1.5 MB) lives in L2 and 42 % of the
+// stall samples of the first version waited for these loads, so they are issued one row pair ahead: the next pair's rows travel
+// while this pair sits at its barriers.
+template <int JW> struct MwRows { float e2[JW], e3[JW], e4[JW]; };
+template <int JW>
+__device__ __forceinline__ void mw_load_rows(const char *__restrict__ emis_lane, unsigned rowbytes, uint32_t cw, MwRows<JW> &R)
+{
+  load_emission_row<JW, 4>(reinterpret_cast<const float *>(emis_lane + (size_t)(cw & 511u) * rowbytes), R.e2);
+  load_emission_row<JW, 4>(reinterpret_cast<const float *>(emis_lane + (size_t)((cw >> 9) & 511u) * rowbytes), R.e3);
+  load_emission_row<JW, 4>(reinterpret_cast<const float *>(emis_lane + (size_t)(cw >> 18) * rowbytes), R.e4);
+}
+
+template <int JW, int PH, int NS>
+__device__ __forceinline__ void mw_row_front(const FwdState<JW> &S, const FwdConsts<JW> &K, const MwRows<JW> &T,
+                                             float (&m)[JW], float &epart, float &A, float &dloc)
 {
   constexpr int P0 = PH, P1 = (PH + 3) & 3, P2 = (PH + 2) & 3;
-  float e2[8], e3[8], e4[8];
-  load_emission_row<8, 4>(reinterpret_cast<const float *>(emis_lane + (size_t)(cw & 511u) * rowbytes), e2);
-  load_emission_row<8, 4>(reinterpret_cast<const float *>(emis_lane + (size_t)((cw >> 9) & 511u) * rowbytes), e3);
-  load_emission_row<8, 4>(reinterpret_cast<const float *>(emis_lane + (size_t)(cw >> 18) * rowbytes), e4);
+  const float (&e2)[JW] = T.e2, (&e3)[JW] = T.e3, (&e4)[JW] = T.e4;
   float es0 = 0.f, es1 = 0.f;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < JW; ++j) {
     float t = S.W[P2][j] * e4[j];
     t = fmaf(S.W[P1][j], e3[j], t);
     t = fmaf(S.W[P0][j], e2[j], t);
@@ -48,7 +56,7 @@ __device__ __forceinline__ void mw_row_front(const FwdState<8> &S, const FwdCons
   epart = warp_allsum(es0 + es1);
   A = m[0];
 #pragma unroll
-  for (int j = 1; j < 8; ++j) A = fmaf(A, K.dd[j], m[j]);
+  for (int j = 1; j < JW; ++j) A = fmaf(A, K.dd[j], m[j]);
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
     float up = __shfl_up_sync(0xffffffffu, A, 1 << s);
@@ -57,9 +65,23 @@ __device__ __forceinline__ void mw_row_front(const FwdState<8> &S, const FwdCons
   dloc = __shfl_up_sync(0xffffffffu, A, 1);
 }
 
+// Requesting the next pair's six table rows towards L1 with prefetch instructions instead of loading them early was measured first and
+// LOSES 6-11 % (404 vs 429 GCUPS at M = 903): off.
+#ifndef BATHGPU_MW_PREFETCH
+#define BATHGPU_MW_PREFETCH 0
+#endif
+__device__ __forceinline__ void mw_prefetch_rows(const char *__restrict__ emis_lane, unsigned rowbytes, uint32_t cw)
+{
+  const char *p2 = emis_lane + (size_t)(cw & 511u) * rowbytes, *p3 = emis_lane + (size_t)((cw >> 9) & 511u) * rowbytes,
+             *p4 = emis_lane + (size_t)(cw >> 18) * rowbytes;
+  asm volatile("prefetch.global.L1 [%0];" :: "l"(p2));  asm volatile("prefetch.global.L1 [%0];" :: "l"(p2 + 512));
+  asm volatile("prefetch.global.L1 [%0];" :: "l"(p3));  asm volatile("prefetch.global.L1 [%0];" :: "l"(p3 + 512));
+  asm volatile("prefetch.global.L1 [%0];" :: "l"(p4));  asm volatile("prefetch.global.L1 [%0];" :: "l"(p4 + 512));
+}
+
 // second half: specials from the block-wide E, the chains replayed from the true inflow, the outflow into row i+2
-template <int PH, bool HEAD>
-__device__ __forceinline__ void mw_row_back(int i, int lane, FwdState<8> &S, const FwdConsts<8> &K, const float (&m)[8], float xE, float d,
+template <int JW, int PH, bool HEAD>
+__device__ __forceinline__ void mw_row_back(int i, int lane, FwdState<JW> &S, const FwdConsts<JW> &K, const float (&m)[JW], float xE, float d,
                                             float ploop, float pmove, float tEL, float tEM, RowOut &R, float &wnext)
 {
   constexpr int P0 = PH, P1 = (PH + 3) & 3, P2 = (PH + 2) & 3, P3 = (PH + 1) & 3;
@@ -68,35 +90,37 @@ __device__ __forceinline__ void mw_row_back(int i, int lane, FwdState<8> &S, con
   float xJ = fmaf(S.xJ[P3], ploop, xE * tEL);
   float xC = fmaf(S.xC[P3], ploop, xE * tEM);
   float xB = fmaf(xJ, pmove, xN * pmove);
-  float o[8];
+  float o[JW];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < JW; ++j) {
     float t = fmaf(S.I[P0][j], K.hi[j], m[j]);
     o[j] = fmaf(d, K.dm[j], t);
-    if (j + 1 < 8) d = fmaf(d, K.dd[j], m[j]);
+    if (j + 1 < JW) d = fmaf(d, K.dd[j], m[j]);
     S.I[P1][j] = fmaf(S.I[P0][j], K.ii[j], m[j]);
   }
-  float oprev = __shfl_up_sync(0xffffffffu, o[7], 1);
+  float oprev = __shfl_up_sync(0xffffffffu, o[JW - 1], 1);
   if (lane == 0) oprev = 0.f;                       // warps behind the first one take their lane 0 entry from shared memory after the pair
   S.W[P2][0] = xB + oprev;
 #pragma unroll
-  for (int j = 1; j < 8; ++j) S.W[P2][j] = xB + o[j - 1];
-  wnext = xB + o[7];                                // lane 31: entry value of the next warp's first node
+  for (int j = 1; j < JW; ++j) S.W[P2][j] = xB + o[j - 1];
+  wnext = xB + o[JW - 1];                                // lane 31: entry value of the next warp's first node
   S.xN[P0] = xN; S.xJ[P0] = xJ; S.xC[P0] = xC;
   R.xE = xE; R.xN = xN; R.xJ = xJ; R.xC = xC; R.xB = xB; R.scale = 1.0f;
 }
 
-template <int NW, int PH, bool XMX, int NS, bool HEAD>
-__device__ __forceinline__ void mw_row_pair(int i, int lane, int warp, FwdState<8> &S, const FwdConsts<8> &K, float Q, const float (&PW)[NW],
-                                            MwShared<NW> &sh, const char *__restrict__ emis_lane, unsigned rowbytes, uint32_t cwA, uint32_t cwB,
-                                            float ploop, float pmove, float tEL, float tEM, float &totscale, float *__restrict__ xrow)
+template <int NW, int JW, int PH, bool XMX, int NS, bool HEAD>
+__device__ __forceinline__ void mw_row_pair(int i, int lane, int warp, FwdState<JW> &S, const FwdConsts<JW> &K, float Q, const float (&PW)[NW],
+                                            MwShared<NW> &sh, const char *__restrict__ emis_lane, unsigned rowbytes, MwRows<JW> &TA, MwRows<JW> &TB,
+                                            uint32_t cwNA, uint32_t cwNB, bool have_next, float ploop, float pmove, float tEL, float tEM, float &totscale, float *__restrict__ xrow)
 {
   constexpr int P2A = (PH + 2) & 3, P2B = (PH + 3) & 3;
-  float mA[8], mB[8], eA, eB, aA, aB, dA, dB;
-  mw_row_front<PH, NS>(S, K, emis_lane, rowbytes, cwA, mA, eA, aA, dA);
-  mw_row_front<PH + 1, NS>(S, K, emis_lane, rowbytes, cwB, mB, eB, aB, dB);
+  float mA[JW], mB[JW], eA, eB, aA, aB, dA, dB;
+  mw_row_front<JW, PH, NS>(S, K, TA, mA, eA, aA, dA);
+  mw_row_front<JW, PH + 1, NS>(S, K, TB, mB, eB, aB, dB);
+  if (have_next) { mw_load_rows<JW>(emis_lane, rowbytes, cwNA, TA); mw_load_rows<JW>(emis_lane, rowbytes, cwNB, TB); }   // consumed by the next pair
   if (lane == 31) { sh.A[0][warp] = aA; sh.A[1][warp] = aB; }
   if (lane == 0)  { sh.E[0][warp] = eA; sh.E[1][warp] = eB; dA = 0.f; dB = 0.f; }
+  if (BATHGPU_MW_PREFETCH && have_next) { mw_prefetch_rows(emis_lane, rowbytes, cwNA); mw_prefetch_rows(emis_lane, rowbytes, cwNB); }
   __syncthreads();
   float xEA = 0.f, xEB = 0.f, XA = 0.f, XB = 0.f;
 #pragma unroll
@@ -107,12 +131,12 @@ __device__ __forceinline__ void mw_row_pair(int i, int lane, int warp, FwdState<
   dA = fmaf(XA, Q, dA); dB = fmaf(XB, Q, dB);
   RowOut A, B;
   float wnA, wnB;
-  mw_row_back<PH, HEAD>(i, lane, S, K, mA, xEA, dA, ploop, pmove, tEL, tEM, A, wnA);
-  mw_row_back<PH + 1, HEAD>(i + 1, lane, S, K, mB, xEB, dB, ploop, pmove, tEL, tEM, B, wnB);
+  mw_row_back<JW, PH, HEAD>(i, lane, S, K, mA, xEA, dA, ploop, pmove, tEL, tEM, A, wnA);
+  mw_row_back<JW, PH + 1, HEAD>(i + 1, lane, S, K, mB, xEB, dB, ploop, pmove, tEL, tEM, B, wnB);
   if (__builtin_expect(A.xE > 1.0e4f || B.xE > 1.0e4f, 0)) {          // rare, block-uniform
     if (A.xE > 1.0e4f) {
       const float sf = 1.0f / A.xE;
-      scale_state<8>(S, sf); wnA *= sf; wnB *= sf;
+      scale_state<JW>(S, sf); wnA *= sf; wnB *= sf;
       A.scale = A.xE; A.xN *= sf; A.xJ *= sf; A.xC *= sf; A.xB *= sf;
       B.xE *= sf; B.xN *= sf; B.xJ *= sf; B.xC *= sf; B.xB *= sf;
       totscale += logf(A.xE);
@@ -120,7 +144,7 @@ __device__ __forceinline__ void mw_row_pair(int i, int lane, int warp, FwdState<
     }
     if (B.xE > 1.0e4f) {
       const float sf = 1.0f / B.xE;
-      scale_state<8>(S, sf); wnA *= sf; wnB *= sf;
+      scale_state<JW>(S, sf); wnA *= sf; wnB *= sf;
       B.scale = B.xE; B.xN *= sf; B.xJ *= sf; B.xC *= sf; B.xB *= sf;
       totscale += logf(B.xE);
       B.xE = 1.0f;
@@ -132,34 +156,38 @@ __device__ __forceinline__ void mw_row_pair(int i, int lane, int warp, FwdState<
   if (lane == 0 && warp > 0) { S.W[P2A][0] = sh.W[0][warp - 1]; S.W[P2B][0] = sh.W[1][warp - 1]; }
 }
 
-template <int NW> struct MwTune { static constexpr int kBlocks = (NW == 4) ? 2 : (NW == 3) ? 3 : 4; };
+// JW nodes per lane, NW warps per window (32 NW JW >= M).  Resident blocks per SM the kernel is compiled for.
+template <int NW, int JW> struct MwTune { static constexpr int kBlocks = (JW == 8) ? ((NW == 4) ? 2 : (NW == 3) ? 2 : 4) : ((NW >= 5) ? 2 : 4); };
 
-template <int NW, bool XMX, int NS>
-__global__ void __launch_bounds__(32 * NW, MwTune<NW>::kBlocks) fs3_forward_parser_kernel_mw(FsParserArgs a)
+template <int NW, int JW, bool XMX, int NS>
+__global__ void __launch_bounds__(32 * NW, MwTune<NW, JW>::kBlocks) fs3_forward_parser_kernel_mw(FsParserArgs a)
 {
   __shared__ MwShared<NW> sh;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, vl = threadIdx.x;
   constexpr int VL = 32 * NW;
+  constexpr int CPL = NW * JW / 4;               // float4 chunks per real lane of the one-warp table layout (J = NW JW nodes per lane)
 
-  FwdConsts<8> K;
+  FwdConsts<JW> K;
   const float *cc = a.cellmw;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    K.qm[j] = __ldg(cc + (MW_QM + j) * VL + vl);
-    K.dm[j] = __ldg(cc + (MW_DM + j) * VL + vl);
-    K.dd[j] = __ldg(cc + (MW_DD + j) * VL + vl);
-    K.hi[j] = __ldg(cc + (MW_HI + j) * VL + vl);
-    K.ii[j] = __ldg(cc + (MW_II + j) * VL + vl);
+  for (int j = 0; j < JW; ++j) {
+    K.qm[j] = __ldg(cc + (0 * JW + j) * VL + vl);
+    K.dm[j] = __ldg(cc + (1 * JW + j) * VL + vl);
+    K.dd[j] = __ldg(cc + (2 * JW + j) * VL + vl);
+    K.hi[j] = __ldg(cc + (3 * JW + j) * VL + vl);
+    K.ii[j] = __ldg(cc + (4 * JW + j) * VL + vl);
   }
 #pragma unroll
-  for (int s = 0; s < 5; ++s) K.bs[s] = __ldg(cc + (MW_BS + s) * VL + vl);
-  const float Q = __ldg(cc + MW_Q * VL + vl);
+  for (int s = 0; s < 5; ++s) K.bs[s] = __ldg(cc + (5 * JW + s) * VL + vl);
+  const float Q = __ldg(cc + (5 * JW + 5) * VL + vl);
   float PW[NW];
 #pragma unroll
-  for (int v = 0; v < NW; ++v) PW[v] = __ldg(cc + MW_ROWS * VL + v);
-  // the one-warp table layout holds NW * 8 nodes per real lane: this thread's 8 nodes are two of that lane's float4 chunks
-  const char    *emis_lane = reinterpret_cast<const char *>(a.emis + ((size_t)(2 * (vl % NW)) * 32 + vl / NW) * 4);
+  for (int v = 0; v < NW; ++v) PW[v] = __ldg(cc + (5 * JW + 6) * VL + v);
+  // this thread's JW nodes are JW/4 consecutive float4 chunks of real lane (JW vl) / (NW JW) of the one-warp table layout
+  const int node0 = JW * vl, rl = node0 / (NW * JW), c0 = (node0 % (NW * JW)) / 4;
+  const char    *emis_lane = reinterpret_cast<const char *>(a.emis + ((size_t)c0 * 32 + rl) * 4);
   const unsigned rowbytes  = (unsigned)a.mpad * 4u;
+  (void)CPL;
 
   for (;;) {
     if (threadIdx.x == 0) sh.win = atomicAdd(a.counter, 1);
@@ -174,11 +202,11 @@ __global__ void __launch_bounds__(32 * NW, MwTune<NW>::kBlocks) fs3_forward_pars
     float *xrow = nullptr;
     if constexpr (XMX) xrow = a.xmx + (size_t)a.xoff[w] * 6;
 
-    FwdState<8> S;
+    FwdState<JW> S;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { S.W[r][j] = 0.f; S.I[r][j] = 0.f; }
+      for (int j = 0; j < JW; ++j) { S.W[r][j] = 0.f; S.I[r][j] = 0.f; }
       S.xN[r] = 0.f; S.xJ[r] = 0.f; S.xC[r] = 0.f;
     }
     float totscale = 0.f;
@@ -189,20 +217,34 @@ __global__ void __launch_bounds__(32 * NW, MwTune<NW>::kBlocks) fs3_forward_pars
     uint32_t lo = __ldg(a.dna4 + (nib >> 3)), hi = __ldg(a.dna4 + (nib >> 3) + 1);
     int i = -pad;
 
+    // 32 rows per chunk: lane l prepares the codon word of row i + l; the next chunk's words are made one chunk ahead so that the
+    // last pair of a chunk can request the first rows of the next one
+    uint32_t cwl = codon_word(lo, hi, (int)(nib & 7) * 4, i + lane, L);
+    nib += 32;
+    if (8 < nq) { lo = __ldg(a.dna4 + (nib >> 3)); hi = __ldg(a.dna4 + (nib >> 3) + 1); }
+    MwRows<JW> TA, TB;
+    mw_load_rows<JW>(emis_lane, rowbytes, __shfl_sync(0xffffffffu, cwl, 0), TA);
+    mw_load_rows<JW>(emis_lane, rowbytes, __shfl_sync(0xffffffffu, cwl, 1), TB);
 #define BATHGPU_MW_CHUNK(HEAD_)                                                                                                   \
     {                                                                                                                             \
-      const uint32_t cwl = codon_word(lo, hi, (int)(nib & 7) * 4, i + lane, L);                                                   \
-      nib += 32;                                                                                                                  \
-      if (q0 + 8 < nq) { lo = __ldg(a.dna4 + (nib >> 3)); hi = __ldg(a.dna4 + (nib >> 3) + 1); }                                  \
+      const bool more = q0 + 8 < nq;                                                                                              \
+      uint32_t cwn = 0;                                                                                                           \
+      if (more) {                                                                                                                 \
+        cwn = codon_word(lo, hi, (int)(nib & 7) * 4, i + 32 + lane, L);                                                           \
+        nib += 32;                                                                                                                \
+        if (q0 + 16 < nq) { lo = __ldg(a.dna4 + (nib >> 3)); hi = __ldg(a.dna4 + (nib >> 3) + 1); }                               \
+      }                                                                                                                           \
       const int qn = min(8, nq - q0);                                                                                             \
       for (int qq = 0; qq < qn; ++qq) {                                                                                           \
-        const uint32_t c0 = __shfl_sync(0xffffffffu, cwl, qq * 4 + 0);                                                            \
-        const uint32_t c1 = __shfl_sync(0xffffffffu, cwl, qq * 4 + 1);                                                            \
         const uint32_t c2 = __shfl_sync(0xffffffffu, cwl, qq * 4 + 2);                                                            \
         const uint32_t c3 = __shfl_sync(0xffffffffu, cwl, qq * 4 + 3);                                                            \
-        mw_row_pair<NW, 0, XMX, NS, HEAD_>(i, lane, warp, S, K, Q, PW, sh, emis_lane, rowbytes, c0, c1, ploop, pmove, a.tEL, a.tEM, totscale, xrow); i += 2; \
-        mw_row_pair<NW, 2, XMX, NS, HEAD_>(i, lane, warp, S, K, Q, PW, sh, emis_lane, rowbytes, c2, c3, ploop, pmove, a.tEL, a.tEM, totscale, xrow); i += 2; \
+        const uint32_t src = (qq < 7) ? cwl : cwn;                                                                                \
+        const uint32_t n0 = __shfl_sync(0xffffffffu, src, (qq * 4 + 4) & 31);                                                     \
+        const uint32_t n1 = __shfl_sync(0xffffffffu, src, (qq * 4 + 5) & 31);                                                     \
+        mw_row_pair<NW, JW, 0, XMX, NS, HEAD_>(i, lane, warp, S, K, Q, PW, sh, emis_lane, rowbytes, TA, TB, c2, c3, true, ploop, pmove, a.tEL, a.tEM, totscale, xrow); i += 2; \
+        mw_row_pair<NW, JW, 2, XMX, NS, HEAD_>(i, lane, warp, S, K, Q, PW, sh, emis_lane, rowbytes, TA, TB, n0, n1, (qq + 1 < qn) || more, ploop, pmove, a.tEL, a.tEM, totscale, xrow); i += 2; \
       }                                                                                                                           \
+      cwl = cwn;                                                                                                                  \
     }
     int q0 = 0;
     BATHGPU_MW_CHUNK(true)

@@ -5,6 +5,7 @@
 #include "launch.h"
 #include "fs_parser.cuh"
 #include "fs_parser_v3.cuh"
+#include "fs_parser_mw.cuh"
 #include "fs_backward.cuh"
 #include "fs_domain.cuh"
 #include "orf_domain.cuh"
@@ -63,8 +64,23 @@ template <class K> static int fwd_grid(K kernel, int J, int n, int sms)
   return std::max(1, std::min(n, sms * std::max(1, std::min(nb, cap))));
 }
 
+// models past the one-warp kernels' register budget (J >= 16): J/8 warps per window (fs_parser_mw.cuh); BATHGPU_FWD_MW=0 keeps the
+// one-warp kernel for comparison
+template <int NW, int JW, bool XMX> static cudaError_t run_fwd_mw(const FsParserArgs &a, int sms, cudaStream_t s)
+{
+  if (a.mw_scan_steps <= 3) fs3_forward_parser_kernel_mw<NW, JW, XMX, 3><<<grid_for(fs3_forward_parser_kernel_mw<NW, JW, XMX, 3>, 32 * NW, 0, a.nwin, sms), 32 * NW, 0, s>>>(a);
+  else                      fs3_forward_parser_kernel_mw<NW, JW, XMX, 5><<<grid_for(fs3_forward_parser_kernel_mw<NW, JW, XMX, 5>, 32 * NW, 0, a.nwin, sms), 32 * NW, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
 template <int J, bool XMX> static cudaError_t run_fwd(int version, const FsParserArgs &a, int sms, cudaStream_t s)
 {
+  if constexpr (J >= 16) {
+    // BATHGPU_FWD_MW: 0 never, 1 (default) from 24 nodes per lane up -- at 16 the one-warp kernel is still ahead (800 vs 620 GCUPS
+    // at M = 409) --, 2 from 16 up
+    static const int mw_mode = [] { const char *e = getenv("BATHGPU_FWD_MW"); return e ? atoi(e) : 1; }();
+    if (version >= 3 && a.cellmw && (mw_mode >= 2 || (mw_mode == 1 && J >= 24))) return run_fwd_mw<J / kMwNodesPerLane, kMwNodesPerLane, XMX>(a, sms, s);
+  }
   if (version >= 3) {
     if (a.scan_steps <= 2)      fs3_forward_parser_kernel_v3<J, XMX, 2><<<fwd_grid(fs3_forward_parser_kernel_v3<J, XMX, 2>, J, a.nwin, sms), 32, 0, s>>>(a);
     else if (a.scan_steps == 3) fs3_forward_parser_kernel_v3<J, XMX, 3><<<fwd_grid(fs3_forward_parser_kernel_v3<J, XMX, 3>, J, a.nwin, sms), 32, 0, s>>>(a);

@@ -30,6 +30,11 @@ struct FilterArgs;
 BATHGPU_FOR_EACH_SET(BATHGPU_DECLARE_SET)
 #undef BATHGPU_DECLARE_SET
 
+// nodes per lane of the multi-warp Forward kernel for long models (fs_parser_mw.cuh); the constant image built by bathgpu.cu and the
+// kernel instantiations must agree.  4 nodes per lane (twice the warps per window) was measured at half the speed: 235 vs 458 GCUPS
+// at M = 903.
+constexpr int kMwNodesPerLane = 8;
+
 // integer filters: W words (4 nodes each) per lane for MSV/SSV, P words (2 nodes each) per lane for Viterbi
 bool launch_msv_filter(int W, int P, int mode, const FilterArgs &a, int sms, cudaStream_t s, cudaError_t *err);
 bool launch_vit_filter_lo(int P, const FilterArgs &a, int sms, cudaStream_t s, cudaError_t *err);      // P = 1..6
