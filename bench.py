@@ -157,7 +157,7 @@ def run_reference(args, rank, world):
     value = cells * args.steps / dt / 1e9
     sample = f"{n} of {len(starts)} windows of {args.window} nt per step ({cells / 1e9:.3f} Gcells), {ncpu} threads"
     search = search_leg_cpu(model, dsq, args.search_cpu_mbp, ncpu) if args.search_mbp > 0 else None
-    print(json.dumps({
+    emit_json_line({
         "impl": "reference", "metric": "frameshift Forward GCUPS", "value": value, "unit": "GCUPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -167,7 +167,7 @@ def run_reference(args, rank, world):
         "search": ({"metric": "bathsearch --fs Mbp/s", **search} if search else None),
         "note": "restated CPU oracle (scalar C, -O3 -march=native, pthreads over windows); the reference binary needs Easel, "
                 "which is not vendored, so it cannot be compiled here",
-    }))
+    })
 
 
 def search_leg(ctx, model, dsq, mbp, plants):
@@ -237,11 +237,34 @@ def workload_config(args, M, nwin):
 
 
 # ------------------------------------------------------------------------------------------------
+# Rank 0 prints exactly ONE line on stdout.  Libraries write there too (NCCL's version banner appears on some boxes whatever
+# NCCL_DEBUG says), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor.
+_JSON_FD = None
+
+
+def capture_stdout():
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json_line(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    capture_stdout()
 
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -406,7 +429,7 @@ def main():
         out["cpu_baseline"] = {"value": v, "unit": "GCUPS", "cores": ncpu, "kind": "port",
                                "sample": f"first {n} of {nwin} windows ({dt:.1f} s, {ncpu} threads, scalar C oracle -O3 -march=native)"}
         out["checks"]["max_abs_diff_vs_oracle_nats"] = float(np.max(np.abs(osc - sc[:n])))
-    print(json.dumps(out))
+    emit_json_line(out)
     if world > 1:
         dist.destroy_process_group()
 
