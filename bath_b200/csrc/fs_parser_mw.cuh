@@ -1,8 +1,8 @@
 // fs_parser_mw.cuh -- frameshift Forward parser for LONG models (384 < M <= 1024): several warps per window.
 //
 // The one-warp kernels keep a window's whole row state in one warp's registers; beyond 12 nodes per lane ptxas moves part of it to
-// local memory and the kernel falls from 1.0-1.3 TCUPS to 0.27 at M = 903.  Here a window belongs to a block of NW = 2..4 warps and
-// every lane owns 8 nodes (the best-running register footprint of fs_parser_v3.cuh), node k = 8 (32 w + lane) + j + 1.  The
+// local memory and the kernel falls from 1.0-1.3 TCUPS to 0.23 at M = 903.  Here a window belongs to a block of NW = 2..4 warps and
+// every lane owns JW = 8 nodes (the best-running register footprint of fs_parser_v3.cuh), node k = 8 (32 w + lane) + j + 1.  The
 // recurrence, the folded table, the scaled chains and the row-pair schedule are those of fs_parser_v3.cuh; what is new is the two
 // places where a DP row couples the warps:
 //   * E(i) is the sum of the warps' partial sums, and the delete chain's carry into warp w is the chain value at the end of warp
@@ -10,6 +10,7 @@
 //     over the warp's 256 nodes -- a profile constant; lane l then takes X(w-1) Q(l) on top of its local inflow, Q(l) = the same
 //     product over the lanes in front of it.  One barrier per row pair (both rows' values go through shared memory together);
 //   * the flow out of a warp's last node is the entry value of the next warp's first node: a second barrier per pair.
+// Each exchange slot is written before a barrier, read after it and rewritten only after the next barrier (racecheck: 0 hazards).
 // The specials (N, J, C, B) are computed redundantly by every warp from the same E, so the rescale decision is block-uniform.
 // The emission table is the one-warp kernels' (J = 8 NW nodes per lane, [J/4][32][4] floats per row): virtual lane v = 32 w + lane
 // reads the two float4 of chunks 2 (v % (J/8)) .. +1 of real lane v / (J/8), 128 contiguous bytes per 8 lanes.
@@ -165,7 +166,6 @@ __global__ void __launch_bounds__(32 * NW, MwTune<NW, JW>::kBlocks) fs3_forward_
   __shared__ MwShared<NW> sh;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, vl = threadIdx.x;
   constexpr int VL = 32 * NW;
-  constexpr int CPL = NW * JW / 4;               // float4 chunks per real lane of the one-warp table layout (J = NW JW nodes per lane)
 
   FwdConsts<JW> K;
   const float *cc = a.cellmw;
@@ -187,7 +187,6 @@ __global__ void __launch_bounds__(32 * NW, MwTune<NW, JW>::kBlocks) fs3_forward_
   const int node0 = JW * vl, rl = node0 / (NW * JW), c0 = (node0 % (NW * JW)) / 4;
   const char    *emis_lane = reinterpret_cast<const char *>(a.emis + ((size_t)c0 * 32 + rl) * 4);
   const unsigned rowbytes  = (unsigned)a.mpad * 4u;
-  (void)CPL;
 
   for (;;) {
     if (threadIdx.x == 0) sh.win = atomicAdd(a.counter, 1);

@@ -185,6 +185,7 @@ struct AliDisplay {
 struct Hit {
   bathhost_hit pub;
   AliDisplay ad;
+  bool from_fs_branch = false;      // P7_HIT::frameshift: made by p7_pli_postDomainDef_Frameshift_BATH (src/p7_pipeline.c:1114)
   double sortkey;
   bool duplicate = false, reported = false;
 };
@@ -1431,6 +1432,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
         h.pub.envsc = dom.envsc; h.pub.oasc = dom.oasc;
         h.pub.trace_len = (int32_t) dom.tr.size();
         summarize_alignment(m, dom.tr, wdsq, h.pub, &h.ad);
+        h.from_fs_branch = true;
         h.sortkey = -dom_lnP;
         return true;
     };
@@ -1979,6 +1981,62 @@ extern "C" int bathhost_search_format_report(const bathhost_search *s, int textw
   if (nreported == 0) out += "\n   [No hits detected that satisfy reporting thresholds]\n";
   out += "\n\n";
 
+  *needed = out.size() + 1;
+  if (out.size() + 1 > cap) return buf ? BATHHOST_EINVAL : BATHHOST_OK;
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return BATHHOST_OK;
+}
+
+// p7_tophits_TabularFrameshifts (src/p7_tophits.c:1442-1600), the --fstblout table: one line per frameshift ('I' / 'D' with its length)
+// and per in-frame stop codon ('S') of every reported hit of the frameshift branch, with its position in the alignment and on the
+// target.  Walks the alignment display's codon lengths, which are the trace's c values (6 = stop codon in a match state).
+extern "C" int bathhost_search_format_fstblout(const bathhost_search *s, int show_header, char *buf, size_t cap, size_t *needed)
+{
+  if (!s || !needed || (!buf && cap > 0)) return BATHHOST_EINVAL;
+  const bathhost_model *m = s->model;
+  const std::string qname = m->hmm.name, qacc = m->hmm.acc;
+  int tnamew = 20, posw = 9, nhits = 0;
+  for (const Hit &h : s->hits) {
+    tnamew = std::max(tnamew, (int) strlen(h.pub.name));
+    if (h.pub.ali_from > 0) {
+      posw = std::max(posw, (int) std::to_string((long long) h.pub.ali_from).size());
+      posw = std::max(posw, (int) std::to_string((long long) h.pub.ali_to).size());
+    }
+    nhits++;
+  }
+  const int qnamew = std::max(20, (int) qname.size()), qaccw = std::max(10, (int) qacc.size()), taccw = 10;
+  std::string out;
+  char line[4096];
+  auto put = [&](const char *fmt, auto... args) { snprintf(line, sizeof line, fmt, args...); out += line; };
+  if (show_header && nhits > 0) {
+    put("#%-*s %-*s %-*s %-*s %-9s %-*s %-*s  %5s %6s %-*s %9s\n", tnamew - 1, " target name", taccw, " accession", qnamew, " query name", qaccw,
+        " accession", " E-value", posw, " ali from", posw, " ali to", " I D S", " length", posw, " seq start", " ali start");
+    put("#%*s %*s %*s %*s %9s %-*s %-*s  %5s  %6s  %-*s  %9s\n", tnamew - 1, "-------------------", taccw, "-----------", qnamew, "--------------------",
+        qaccw, "----------", "---------", posw, "---------", posw, "---------", "-----", "------", posw, "---------", "---------");
+  }
+  for (const Hit &h : s->hits) {
+    if (!h.reported || !h.from_fs_branch) continue;
+    const long long seq_from = h.pub.ali_from, seq_to = h.pub.ali_to;
+    int ali_pos = 1;
+    for (int z = 0; z < h.ad.N; ++z) {
+      const bool is_match = h.ad.model[z] != '.' && h.ad.aseq[z] != '-';
+      const bool is_insert = h.ad.model[z] == '.';
+      if (!is_match) { if (is_insert) ali_pos += 3; continue; }
+      const int c = h.ad.codon[z];
+      char type = 0; int len = 0, adv = 3;
+      if      (c == 1) { type = 'D'; len = 2; adv = 1; }
+      else if (c == 2) { type = 'D'; len = 1; adv = 2; }
+      else if (c == 6) { type = 'S'; len = 0; adv = 3; }
+      else if (c == 4) { type = 'I'; len = 1; adv = 4; }
+      else if (c == 5) { type = 'I'; len = 2; adv = 5; }
+      if (type) {
+        const long long seq_start = (seq_from < seq_to) ? seq_from + ali_pos - 1 : seq_from - ali_pos + 1;
+        put(" %-*s %-*s %-*s %-*s %9.2g %-*lld %-*lld  %5c  %6d  %-*lld  %9d\n", tnamew, h.pub.name, taccw, "-", qnamew, qname.c_str(), qaccw,
+            qacc.empty() ? "-" : qacc.c_str(), h.pub.evalue, posw, seq_from, posw, seq_to, type, len, posw, seq_start, ali_pos);
+      }
+      ali_pos += adv;
+    }
+  }
   *needed = out.size() + 1;
   if (out.size() + 1 > cap) return buf ? BATHHOST_EINVAL : BATHHOST_OK;
   memcpy(buf, out.c_str(), out.size() + 1);

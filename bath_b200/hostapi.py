@@ -16,7 +16,7 @@ EXPORTS = [
     "bathhost_search_create", "bathhost_search_destroy", "bathhost_search_last_error", "bathhost_search_sequence",
     "bathhost_search_finish", "bathhost_search_nhits", "bathhost_search_get_hit", "bathhost_search_get_stats",
     "bathhost_sample_region_segments", "bathhost_cluster_region_segments", "bathhost_search_format_tblout",
-    "bathhost_calibrate", "bathhost_model_lambda", "bathhost_search_format_report", "bathhost_search_format_output",
+    "bathhost_calibrate", "bathhost_model_lambda", "bathhost_search_format_report", "bathhost_search_format_output", "bathhost_search_format_fstblout",
 ]
 
 
@@ -334,6 +334,10 @@ class Search:
         if st != OK:
             raise RuntimeError(f"bathhost_search_format_tblout: status {st}")
         return buf.value.decode()
+
+    def fstblout(self, header=True):
+        """the --fstblout table: one line per frameshift / stop codon of the reported frameshift-branch hits"""
+        return self._format(self.lib.bathhost_search_format_fstblout, int(header))
 
     def output(self, textw=150):
         """one query's section of bathsearch's output from "Query:" to "Total number of hits:" (no banner, no timings)"""

@@ -189,6 +189,10 @@ int  bathhost_search_format_tblout(const bathhost_search *s, int show_header, ch
  * writes between the "Query:" block and "Internal pipeline statistics summary:" (src/bathsearch.c:960-961).  textw = --textw
  * (150 by default, 0 = unlimited).  Same sizing protocol as bathhost_search_format_tblout. */
 int  bathhost_search_format_report(const bathhost_search *s, int textw, char *buf, size_t cap, size_t *needed);
+/* The --fstblout table (p7_tophits_TabularFrameshifts, src/p7_tophits.c:1442-1600): one line per frameshift ('I' / 'D' and its length)
+ * and per in-frame stop codon ('S') of the reported hits of the frameshift branch.  The reference ships no example of this table:
+ * restated from the source, checked against the hit's CIGAR string. */
+int  bathhost_search_format_fstblout(const bathhost_search *s, int show_header, char *buf, size_t cap, size_t *needed);
 /* One query's section of bathsearch's output minus the run-dependent lines (banner, option echo, "# CPU time", "# Mc/sec", "//"):
  * "Query:" / "Accession:" / "Description:" (src/bathsearch.c:783-785), the report above, and p7_pli_Statistics from "Internal pipeline
  * statistics summary:" to "Total number of hits:" (src/p7_pipeline.c:1836-1874).  Call after bathhost_search_finish. */

@@ -63,6 +63,36 @@ def test_report_matches_shipped_outputs_cpu_backend(oracle):
     del keep
 
 
+def test_fstblout_lists_the_frameshifts_of_the_cigar(oracle):
+    """--fstblout (no shipped example): the AMP_N hit's table must list, in order, exactly the frameshifts of its CIGAR string
+    44M1F39M1B114M9I25M2B19M1B44M1B4M6I30M2B67M (F = 1-nt insertion, nB = n-nt deletion) plus its one stop codon, at the target
+    positions the CIGAR's operation lengths add up to."""
+    from bath_b200 import hostapi
+    be, keep = oracle.cpu_backend(2)
+    model = hostapi.QueryModel(common.golden("AMP_N.bhmm"))
+    search = hostapi.Search(model, backend=be)
+    for name, seq in hostapi.read_fasta(common.golden("target-AMP_N.fa")):
+        search.add_sequence(name, hostapi.digitize_dna(seq))
+    hit = search.finish()[0]
+    lines = search.fstblout().splitlines()
+    assert lines[0].startswith("# target name") and lines[1].startswith("#---")
+    rows = [l.split() for l in lines[2:]]
+    assert all(r[0] == "seq1" and r[2] == "AMP_N" and (int(r[5]), int(r[6])) == (1, 402) for r in rows)
+    events = [(r[7], int(r[8])) for r in rows if r[7] != "S"]
+    want, pos, starts = [], 1, []
+    for n, op in re.findall(r"(\d+)([MIDFB])", hit["cigar"]):
+        n = int(n)
+        if op == "F":
+            want.append(("I", n))
+        elif op == "B":
+            want.append(("D", n))
+    assert events == want and sum(1 for r in rows if r[7] == "S") == hit["stops"] == 1
+    seq_starts = [int(r[9]) for r in rows]
+    assert seq_starts == sorted(seq_starts) and 1 <= seq_starts[0] and seq_starts[-1] <= 402
+    assert all(int(r[9]) == int(r[10]) for r in rows)          # the hit starts at target position 1: alignment and target positions agree
+    del keep
+
+
 def test_report_without_hits(oracle):
     from bath_b200 import hostapi
     be, keep = oracle.cpu_backend(2)
