@@ -180,6 +180,14 @@ struct AliDisplay {
   std::string model, mline, aseq, ntseq, ppline, csline, rfline;
   std::vector<uint8_t> codon;
   int N = 0;
+  void size_for(int n, bool cs, bool rf)          // all lines are written by column index: one allocation each
+  {
+    N = n;
+    model.assign(n, ' '); mline.assign(n, ' '); aseq.assign(n, ' '); ppline.assign(n, ' '); ntseq.assign((size_t) 5 * n, ' ');
+    if (cs) csline.assign(n, ' ');
+    if (rf) rfline.assign(n, ' ');
+    codon.assign(n, 0);
+  }
 };
 
 struct Hit {
@@ -398,6 +406,7 @@ void summarize_alignment(const bathhost_model *m, const std::vector<bathgpu_trac
   std::string cigar;
   int shifts = 0, stops = 0, exact = 0, n_count = 0;
   char buf[32];
+  if (ad) ad->size_for((int) core.size(), !m->hmm.cs.empty(), !m->hmm.rf.empty());
   for (size_t z = 0; z < core.size(); ++z) {
     const bathgpu_trace_step &s = *core[z];
     const int nxt = (z + 1 < core.size()) ? core[z + 1]->st : TS_E;
@@ -411,12 +420,12 @@ void summarize_alignment(const bathhost_model *m, const std::vector<bathgpu_trac
         for (int z5 = 0; z5 < s.c; ++z5) n[z5] = dsq[s.i - (s.c - 1) + z5];
         char cc[5];
         codon_chars(s.c, indel, n, cc);
-        ad->ntseq.append(cc, 5);
-        ad->model += m->hmm.consensus[s.k];
-        ad->mline += (aa == amino_code(m->hmm.consensus[s.k])) ? m->hmm.consensus[s.k]
-                     : (expf(gm.rsc[(size_t) (gm.maxcodons + aa) * ld + s.k]) > 1.0) ? '+' : ' ';
-        ad->aseq += (char) toupper(kAminoSym[aa]);
-        ad->codon.push_back((uint8_t) ((s.c == 3 && (indel == PXXx || indel == PXxX || indel == PxXX)) ? 6 : s.c));
+        memcpy(&ad->ntseq[5 * z], cc, 5);
+        ad->model[z] = m->hmm.consensus[s.k];
+        ad->mline[z] = (aa == amino_code(m->hmm.consensus[s.k])) ? m->hmm.consensus[s.k]
+                       : (expf(gm.rsc[(size_t) (gm.maxcodons + aa) * ld + s.k]) > 1.0) ? '+' : ' ';
+        ad->aseq[z] = (char) toupper(kAminoSym[aa]);
+        ad->codon[z] = (uint8_t) ((s.c == 3 && (indel == PXXx || indel == PXxX || indel == PxXX)) ? 6 : s.c);
       }
       if (s.c != 3) shifts++;
       else if (indel == PXXx || indel == PXxX || indel == PxXX) stops++;
@@ -439,26 +448,25 @@ void summarize_alignment(const bathhost_model *m, const std::vector<bathgpu_trac
       if (stop) stops++;
       if (ad) {
         const int aa = stop ? 27 : gm.codons[(size_t) s.k * gm.maxcodons + ci];
-        ad->model += '.'; ad->mline += ' ';
-        ad->aseq += (char) tolower(kAminoSym[aa]);
+        ad->model[z] = '.';
+        ad->aseq[z] = (char) tolower(kAminoSym[aa]);
         const char cc[5] = { ' ', kDnaSym[dsq[s.i - 2]], kDnaSym[dsq[s.i - 1]], kDnaSym[dsq[s.i]], ' ' };
-        ad->ntseq.append(cc, 5);
-        ad->codon.push_back(stop ? 6 : 3);
+        memcpy(&ad->ntseq[5 * z], cc, 5);
+        ad->codon[z] = stop ? 6 : 3;
       }
       n_count += 3;
       if (nxt != TS_I) { snprintf(buf, sizeof buf, "%dI", n_count); cigar += buf; n_count = 0; }
     } else {
-      if (ad) { ad->model += m->hmm.consensus[s.k]; ad->mline += ' '; ad->aseq += '-'; ad->ntseq += " --- "; ad->codon.push_back(0); }
+      if (ad) { ad->model[z] = m->hmm.consensus[s.k]; ad->aseq[z] = '-'; memcpy(&ad->ntseq[5 * z], " --- ", 5); }
       n_count += 3;
       if (nxt != TS_D) { snprintf(buf, sizeof buf, "%dD", n_count); cigar += buf; n_count = 0; }
     }
     if (ad) {
-      ad->ppline += (s.st == TS_D) ? '.' : encode_post_prob(s.pp);
-      if (!m->hmm.cs.empty()) ad->csline += (s.st == TS_I) ? '.' : m->hmm.cs[s.k];
-      if (!m->hmm.rf.empty()) ad->rfline += (s.st == TS_I) ? '.' : m->hmm.rf[s.k];
+      ad->ppline[z] = (s.st == TS_D) ? '.' : encode_post_prob(s.pp);
+      if (!m->hmm.cs.empty()) ad->csline[z] = (s.st == TS_I) ? '.' : m->hmm.cs[s.k];
+      if (!m->hmm.rf.empty()) ad->rfline[z] = (s.st == TS_I) ? '.' : m->hmm.rf[s.k];
     }
   }
-  if (ad) ad->N = (int) core.size();
   h.shifts = shifts; h.stops = stops;
   h.pid = core.empty() ? 0.0f : ((float) exact / (float) core.size()) * 100;
   snprintf(h.cigar, sizeof h.cigar, "%s", cigar.c_str());
@@ -1443,7 +1451,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
       std::vector<uint8_t> wbuf;
       for (size_t z = za; z < zb; ++z) ok[z] = score_env(order[z], lbg, wbuf, out[z]) ? 1 : 0;
     });
-    for (size_t z = 0; z < order.size(); ++z) if (ok[z]) s->hits.push_back(out[z]);
+    for (size_t z = 0; z < order.size(); ++z) if (ok[z]) s->hits.push_back(std::move(out[z]));
   }
   tm.lap(s->st.us_score);
 
@@ -1624,29 +1632,30 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
         std::string cigar;
         char buf[32];
         int exact = 0, ncore = 0, n_count = 0, pos = orf_pos;
+        h.ad.size_for(z2 - z1 + 1, !m->hmm.cs.empty(), !m->hmm.rf.empty());
         for (int z = z1; z <= z2; ++z) {
           const bathgpu_trace_step &ts = dom.tr[z];
           const int nxt = dom.tr[z + 1].st;                 // z2 + 1 exists: the E state
           ncore++;
           {                                                  // display lines (:1128-1215)
             AliDisplay &ad = h.ad;
+            const int y = z - z1;
             const char cons = m->hmm.consensus[ts.k];
-            if (ts.st == TS_D) { ad.model += cons; ad.mline += ' '; ad.aseq += '-'; ad.ntseq += " --- "; ad.codon.push_back(0); }
+            if (ts.st == TS_D) { ad.model[y] = cons; ad.aseq[y] = '-'; memcpy(&ad.ntseq[5 * y], " --- ", 5); }
             else {
               const int x = res_o[pos];
               const char cc[5] = { ' ', (char) toupper(kDnaSym[wdsq[ts.i - 2]]), (char) toupper(kDnaSym[wdsq[ts.i - 1]]), (char) toupper(kDnaSym[wdsq[ts.i]]), ' ' };
-              ad.ntseq.append(cc, 5);
-              ad.aseq += (char) toupper(kAminoSym[x]);
+              memcpy(&ad.ntseq[5 * y], cc, 5);
+              ad.aseq[y] = (char) toupper(kAminoSym[x]);
               if (ts.st == TS_M) {
-                ad.model += cons;
-                ad.mline += (x == amino_code(cons)) ? cons : (expf(q.msc[(size_t) x * (q.M + 1) + ts.k]) > 1.0) ? '+' : ' ';
-                ad.codon.push_back(ts.c);
-              } else { ad.model += '.'; ad.mline += ' '; ad.codon.push_back(3); }
+                ad.model[y] = cons;
+                ad.mline[y] = (x == amino_code(cons)) ? cons : (expf(q.msc[(size_t) x * (q.M + 1) + ts.k]) > 1.0) ? '+' : ' ';
+                ad.codon[y] = ts.c;
+              } else { ad.model[y] = '.'; ad.codon[y] = 3; }
             }
-            ad.ppline += (ts.st == TS_D) ? '.' : encode_post_prob(ts.pp);
-            if (!m->hmm.cs.empty()) ad.csline += (ts.st == TS_I) ? '.' : m->hmm.cs[ts.k];
-            if (!m->hmm.rf.empty()) ad.rfline += (ts.st == TS_I) ? '.' : m->hmm.rf[ts.k];
-            ad.N++;
+            ad.ppline[y] = (ts.st == TS_D) ? '.' : encode_post_prob(ts.pp);
+            if (!m->hmm.cs.empty()) ad.csline[y] = (ts.st == TS_I) ? '.' : m->hmm.cs[ts.k];
+            if (!m->hmm.rf.empty()) ad.rfline[y] = (ts.st == TS_I) ? '.' : m->hmm.rf[ts.k];
           }
           if (ts.st == TS_M) { if (res_o[pos] == amino_code(m->hmm.consensus[ts.k])) exact++; pos++; }
           else if (ts.st == TS_I) pos++;
@@ -1657,7 +1666,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
         snprintf(h.pub.cigar, sizeof h.pub.cigar, "%s", cigar.c_str());
       }
       h.sortkey = -dom_lnP;
-      s->hits.push_back(h);
+      s->hits.push_back(std::move(h));
     }
   }
   tm.lap(s->st.us_std);
