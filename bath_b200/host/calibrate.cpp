@@ -217,8 +217,9 @@ extern "C" int bathhost_calibrate(const bathhost_model *m, const bathhost_backen
     float pmove, ploop;
     bathhost_length_model(EfL, 1.0f, &pmove, &ploop);                 // p7_fs_oprofile_ReconfigLength(om_fs, EfL), multihit
     const float nullsc = fs_null_one(EfL);
-    int need = EfN;
+    int need = EfN, rounds = 0;
     while (need > 0) {
+      if (++rounds > 64) return BATHHOST_EFAIL;             // every score overflows: the reference would draw for ever (:649)
       dna.assign((size_t) need * Ln + 2, 255);
       for (int i = 0; i < need; ++i) {
         for (int a = 0; a < EfL; ++a) amino[a] = (uint8_t) rng.choose(m->bg.f, kK);
