@@ -66,6 +66,8 @@ __device__ __forceinline__ void mw_row_front(const FwdState<JW> &S, const FwdCon
   dloc = __shfl_up_sync(0xffffffffu, A, 1);
 }
 
+// Also measured and dropped: both rows' E shares reduced in one butterfly (upper half-warp row i+1, lower row i: 5 shuffles for 10)
+// together with a 2-step scan: 452 vs 458 GCUPS at M = 903, 468 vs 519 at M = 624.
 // Requesting the next pair's six table rows towards L1 with prefetch instructions instead of loading them early was measured first and
 // LOSES 6-11 % (404 vs 429 GCUPS at M = 903): off.
 #ifndef BATHGPU_MW_PREFETCH

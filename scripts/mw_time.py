@@ -6,7 +6,7 @@ from oracle import pyoracle as po          # reads the profile files; checks a s
 from bath_b200 import capi
 ctx = capi.Context(0)
 rng = np.random.default_rng(42)
-for hmm, idx in [m for m in [("MET-ct4.bhmm", 1), ("synthetic_M624.bhmm", 0), ("synthetic_M903.bhmm", 0)] if os.environ.get("MW_ONLY", "") in m[0]]:
+for hmm, idx in [m for m in [("synthetic_M624.bhmm", 0), ("synthetic_M903.bhmm", 0)] if os.environ.get("MW_ONLY", "") in m[0]]:
     model = po.Model(common.golden(hmm), idx)
     ctx.load_fs_profile(3, model.rfv(3), model.tfv(3))
     for Lw in (1200,):
