@@ -11,6 +11,7 @@
 #include <string>
 #include <algorithm>
 #include <mutex>
+#include <memory>
 
 #include "../../include/bathgpu.h"
 #include "fs_parser.cuh"
@@ -30,6 +31,10 @@ namespace {
 struct DevBuf {
   void  *p = nullptr;
   size_t cap = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { release(); }          // bathgpu_destroy selects the context's device before the context goes away
   int reserve(size_t bytes) {
     if (bytes <= cap) return BATHGPU_OK;
     if (p) cudaFree(p);
@@ -63,10 +68,11 @@ struct FsProfileImage {
 
 }  // namespace
 
-struct TargetSlot {          // one resident target: packed DNA block + ORF residues (two slots: one per strand)
+struct TargetSlot {          // one resident target: packed DNA + codon classes + survivor residues (e.g. one strand of one chunk of the target)
   DevBuf  dna_bytes, dna4, residues, cls;
   int64_t block_n = 0, nres = 0;
 };
+constexpr int kMaxSlots = 1 << 16;
 
 struct bathgpu_ctx {
   int           device = 0;
@@ -76,9 +82,10 @@ struct bathgpu_ctx {
   cudaEvent_t   ev0 = nullptr, ev1 = nullptr;
   std::string   err;
   FsProfileImage fs3, fs5;
-  TargetSlot    slot[2];
+  std::vector<std::unique_ptr<TargetSlot>> slot;      // grows on demand (bathgpu_select_slot)
   int           cur = 0;
-  TargetSlot   &S() { return slot[cur]; }
+  TargetSlot   &S() { return *slot[cur]; }
+  TargetSlot   &slot_at(int i) { while ((int)slot.size() <= i) slot.emplace_back(new TargetSlot()); return *slot[i]; }
   DevBuf        wins, fwdsc, status, counter;
   int           nstaged = 0;
   DevBuf        scratch;
@@ -133,6 +140,7 @@ extern "C" int bathgpu_create(int device, bathgpu_ctx **ret_ctx)
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
     cudaGetLastError(); delete ctx; return BATHGPU_ECUDA;
   }
+  ctx->slot_at(1);                 // slots 0 and 1 exist from the start
   *ret_ctx = ctx;
   return BATHGPU_OK;
 }
@@ -142,18 +150,7 @@ extern "C" void bathgpu_destroy(bathgpu_ctx *ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (FsProfileImage *im : { &ctx->fs3, &ctx->fs5 }) {
-    im->emis.release(); im->cellc.release(); im->cellmw.release(); im->cellb.release(); im->cellf5.release(); im->amino.release();
-    im->oaflags.release(); im->oapass.release(); im->tfvraw.release(); im->zinv.release(); im->emis_fwd.release(); im->emis_bck.release(); im->cellb3.release();
-  }
-  for (TargetSlot &t : ctx->slot) { t.dna_bytes.release(); t.dna4.release(); t.residues.release(); }
-  ctx->wins.release(); ctx->fwdsc.release();
-  ctx->status.release(); ctx->counter.release(); ctx->scratch.release();
-  for (DevBuf *b : { &ctx->f_rbv, &ctx->f_rwv, &ctx->f_twv, &ctx->f_ddsum, &ctx->orfs, &ctx->fsc, &ctx->fst, &ctx->fwins, &ctx->fnw }) b->release();
-  ctx->ddcell.release(); ctx->dmxout.release();
-  for (DevBuf *b : { &ctx->envs, &ctx->dpp, &ctx->doa, &ctx->dfx, &ctx->dppx, &ctx->doax, &ctx->dlsf, &ctx->dfw, &ctx->dbk, &ctx->doasc,
-                     &ctx->dnull2, &ctx->dstat, &ctx->dtoff, &ctx->dtlen, &ctx->dsteps }) b->release();
-  for (DevBuf *b : { &ctx->fxmx, &ctx->bxmx, &ctx->lsf, &ctx->lsb, &ctx->xoff, &ctx->dmocc, &ctx->dbtot, &ctx->detot, &ctx->bcksc }) b->release();
+  // every device buffer of the context (profile images, target slots, stage workspaces) is a DevBuf and frees itself with the context
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); cudaStreamDestroy(ctx->stream2); for (auto &e : ctx->chunk_ev) if (e) cudaEventDestroy(e); }
@@ -626,7 +623,8 @@ __global__ void pack_dna4_range_kernel(const uint8_t *__restrict__ dsq, long lon
 
 extern "C" int bathgpu_select_slot(bathgpu_ctx *ctx, int slot)
 {
-  if (!ctx || slot < 0 || slot > 1) return fail(ctx, BATHGPU_EINVAL, "slot must be 0 or 1");
+  if (!ctx || slot < 0 || slot >= kMaxSlots) return fail(ctx, BATHGPU_EINVAL, "slot must be in 0..%d", kMaxSlots - 1);
+  ctx->slot_at(slot);
   ctx->cur = slot;
   return BATHGPU_OK;
 }
@@ -663,8 +661,9 @@ __global__ void revcomp_kernel(const uint8_t *__restrict__ src, long long n, uin
 // trip over the host link (bathsearch reverse-complements each block on the host, src/bathsearch.c:1087-1096).
 extern "C" int bathgpu_revcomp_slot(bathgpu_ctx *ctx, int src, int dst)
 {
-  if (!ctx || src < 0 || src > 1 || dst < 0 || dst > 1 || src == dst) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_revcomp_slot");
-  TargetSlot &A = ctx->slot[src], &B = ctx->slot[dst];
+  if (!ctx || src < 0 || src >= kMaxSlots || dst < 0 || dst >= kMaxSlots || src == dst) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_revcomp_slot");
+  ctx->slot_at(std::max(src, dst));
+  TargetSlot &A = *ctx->slot[src], &B = *ctx->slot[dst];
   if (A.block_n == 0) return fail(ctx, BATHGPU_EINVAL, "no block uploaded in slot %d", src);
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   const long long n = A.block_n;
@@ -784,17 +783,21 @@ extern "C" int bathgpu_fs_fwd_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_
 
 // ---------------------------------------------------------------------------------------------
 // Forward parser stage
-static int fwd_version()      // BATHGPU_FWD=1|3 picks a kernel generation for A/B runs (1: one row per block of code; default 3: the row-pair schedule)
+// BATHGPU_FWD=1|3|4 forces a kernel generation for A/B runs (1: one row per block of code; 3: the row-pair schedule; 4: row pairs on
+// packed FP32, fs_parser_v4.cuh).  Unset: per node count, what measured faster on B200 (profiles/r02_forward_v3_v4.md): the packed
+// kernel from 10 nodes per lane up (M > 256: +21 % at M = 279), the scalar row-pair kernel below (equal at 6, spills at 7-8).
+static int fwd_version(int J)
 {
-  static const int v = [] { const char *e = getenv("BATHGPU_FWD"); int x = e ? atoi(e) : 3; return (x == 1) ? 1 : 3; }();
-  return v;
+  static const int forced = [] { const char *e = getenv("BATHGPU_FWD"); int x = e ? atoi(e) : 0; return (x == 1 || x == 3 || x == 4) ? x : 0; }();
+  if (forced) return forced;
+  return (J >= 10) ? 4 : 3;
 }
 
 // one launch entry per kernel family and node-count set (launch.h; kernels_tu.cu)
 static cudaError_t dispatch_fwd(bool xmx, int J, const FsParserArgs &a, int sms, cudaStream_t s)
 {
   cudaError_t e = cudaErrorInvalidValue;
-  const int v = fwd_version();
+  const int v = fwd_version(J);
 #define X(S) if (launch_fs3_forward_##S(J, xmx, v, a, sms, s, &e)) return e;
   BATHGPU_FOR_EACH_SET(X)
 #undef X
@@ -1764,6 +1767,10 @@ extern "C" int bathgpu_orfs_msv_screen(bathgpu_ctx *ctx, const bathgpu_block *bl
       for (int p0 = 1; p0 <= blocks[b].n + 1; p0 += kOrfTile) { tile_block.push_back(b); tile_p0.push_back(p0); }
   }
   first_tile[nblocks] = (long long)tile_block.size();
+  // the residues of every ORF of every block fit in sum of the block lengths (three frames of n/3 codons each); blocks overlap by
+  // their context, so this can exceed the sequence length
+  long long sum_block_n = 0;
+  for (int b = 0; b < nblocks; ++b) sum_block_n += blocks[b].n;
   const int ntiles = (int)tile_block.size();
   *nhits = 0; *nres = 0;
   ctx->o_nhits = 0; ctx->o_nres = 0; S.nres = 0;
@@ -1808,7 +1815,7 @@ extern "C" int bathgpu_orfs_msv_screen(bathgpu_ctx *ctx, const bathgpu_block *bl
   if (N > 0x7fffffffLL) return fail(ctx, BATHGPU_EINVAL, "%lld ORFs in one call: split the sequence", N);
   if (ctx->orfs.reserve((size_t)N * sizeof(OrfDesc)) != BATHGPU_OK || ctx->o_meta.reserve((size_t)N * sizeof(OrfMeta)) != BATHGPU_OK ||
       ctx->fsc.reserve((size_t)N * 4) != BATHGPU_OK || ctx->fst.reserve((size_t)N * 4) != BATHGPU_OK ||
-      ctx->o_hits.reserve((size_t)N * sizeof(OrfHit)) != BATHGPU_OK || S.residues.reserve((size_t)n + 64) != BATHGPU_OK)
+      ctx->o_hits.reserve((size_t)N * sizeof(OrfHit)) != BATHGPU_OK || S.residues.reserve((size_t)sum_block_n / 3 * 3 + 64) != BATHGPU_OK)
     return fail(ctx, BATHGPU_EMEM, "device allocation failed for %lld ORFs", N);
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->o_base.p, base.data(), (size_t)ntiles * 8, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->o_first.p, bfirst.data(), (size_t)nblocks * 8, cudaMemcpyHostToDevice, ctx->stream));

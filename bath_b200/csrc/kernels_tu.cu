@@ -5,6 +5,7 @@
 #include "launch.h"
 #include "fs_parser.cuh"
 #include "fs_parser_v3.cuh"
+#include "fs_parser_v4.cuh"
 #include "fs_parser_mw.cuh"
 #include "fs_backward.cuh"
 #include "fs_domain.cuh"
@@ -81,7 +82,12 @@ template <int J, bool XMX> static cudaError_t run_fwd(int version, const FsParse
     static const int mw_mode = [] { const char *e = getenv("BATHGPU_FWD_MW"); return e ? atoi(e) : 1; }();
     if (version >= 3 && a.cellmw && (mw_mode >= 2 || (mw_mode == 1 && J >= 24))) return run_fwd_mw<J / kMwNodesPerLane, kMwNodesPerLane, XMX>(a, sms, s);
   }
-  if (version >= 3) {
+  if (version >= 4) {                 // packed-FP32 row pairs (fs_parser_v4.cuh)
+    if (a.scan_steps <= 2)      fs3_forward_parser_kernel_v4<J, XMX, 2><<<fwd_grid(fs3_forward_parser_kernel_v4<J, XMX, 2>, J, a.nwin, sms), 32, 0, s>>>(a);
+    else if (a.scan_steps == 3) fs3_forward_parser_kernel_v4<J, XMX, 3><<<fwd_grid(fs3_forward_parser_kernel_v4<J, XMX, 3>, J, a.nwin, sms), 32, 0, s>>>(a);
+    else                        fs3_forward_parser_kernel_v4<J, XMX, 5><<<fwd_grid(fs3_forward_parser_kernel_v4<J, XMX, 5>, J, a.nwin, sms), 32, 0, s>>>(a);
+  }
+  else if (version >= 3) {
     if (a.scan_steps <= 2)      fs3_forward_parser_kernel_v3<J, XMX, 2><<<fwd_grid(fs3_forward_parser_kernel_v3<J, XMX, 2>, J, a.nwin, sms), 32, 0, s>>>(a);
     else if (a.scan_steps == 3) fs3_forward_parser_kernel_v3<J, XMX, 3><<<fwd_grid(fs3_forward_parser_kernel_v3<J, XMX, 3>, J, a.nwin, sms), 32, 0, s>>>(a);
     else                        fs3_forward_parser_kernel_v3<J, XMX, 5><<<fwd_grid(fs3_forward_parser_kernel_v3<J, XMX, 5>, J, a.nwin, sms), 32, 0, s>>>(a);

@@ -22,15 +22,29 @@ typedef struct {
   BO_OPROFILE    *om;             /* integer tables from load_filter_profile; float tables from the 3-codon image */
   uint8_t        *ssv_scores;
   int             lanes_u8, lanes_i16;
-  int             cur;
-  uint8_t        *dsq[2];   int64_t n[2];
-  uint8_t        *res[2];   int64_t nres[2];
+  int             cur, nslots;    /* target slots grow on demand (bathgpu_select_slot) */
+  uint8_t       **dsq;      int64_t *n;
+  uint8_t       **res;      int64_t *nres;
+  bathgpu_orf_hit **hits;   int64_t *nhits;     /* per slot: survivors of the last screen */
 } bo_backend;
+
+static int grow_slots(bo_backend *b, int want)
+{
+  int s;
+  if (want <= b->nslots) return BO_OK;
+  b->dsq   = realloc(b->dsq,   sizeof(uint8_t *) * (size_t) want);          b->n     = realloc(b->n,     sizeof(int64_t) * (size_t) want);
+  b->res   = realloc(b->res,   sizeof(uint8_t *) * (size_t) want);          b->nres  = realloc(b->nres,  sizeof(int64_t) * (size_t) want);
+  b->hits  = realloc(b->hits,  sizeof(bathgpu_orf_hit *) * (size_t) want);  b->nhits = realloc(b->nhits, sizeof(int64_t) * (size_t) want);
+  if (!b->dsq || !b->n || !b->res || !b->nres || !b->hits || !b->nhits) return BO_EMEM;
+  for (s = b->nslots; s < want; s++) { b->dsq[s] = NULL; b->n[s] = 0; b->res[s] = NULL; b->nres[s] = 0; b->hits[s] = NULL; b->nhits[s] = 0; }
+  b->nslots = want;
+  return BO_OK;
+}
 
 bo_backend *bo_backend_create(int nthreads)
 {
   bo_backend *b = calloc(1, sizeof(bo_backend));
-  if (b) b->nthreads = nthreads > 0 ? nthreads : 1;
+  if (b) { b->nthreads = nthreads > 0 ? nthreads : 1; grow_slots(b, 2); }
   bo_FLogsumInit();
   return b;
 }
@@ -41,7 +55,8 @@ void bo_backend_destroy(bo_backend *b)
   if (!b) return;
   bo_fs_oprofile_destroy(b->om3); bo_fs_oprofile_destroy(b->om5); bo_oprofile_destroy(b->om);
   free(b->ssv_scores);
-  for (s = 0; s < 2; s++) { free(b->dsq[s]); free(b->res[s]); }
+  for (s = 0; s < b->nslots; s++) { free(b->dsq[s]); free(b->res[s]); free(b->hits[s]); }
+  free(b->dsq); free(b->n); free(b->res); free(b->nres); free(b->hits); free(b->nhits);
   free(b);
 }
 
@@ -118,7 +133,13 @@ int bo_backend_load_filter_profile(void *ctx, const void *prm_, const uint8_t *r
 }
 
 /* ---- targets ---- */
-int bo_backend_select_slot(void *ctx, int slot) { bo_backend *b = ctx; if (slot < 0 || slot > 1) return BO_EINVAL; b->cur = slot; return BO_OK; }
+int bo_backend_select_slot(void *ctx, int slot)
+{
+  bo_backend *b = ctx;
+  if (slot < 0 || slot >= 65536 || grow_slots(b, slot + 1) != BO_OK) return BO_EINVAL;
+  b->cur = slot;
+  return BO_OK;
+}
 
 int bo_backend_upload_block(void *ctx, const uint8_t *dsq, int64_t n)
 {
@@ -133,8 +154,9 @@ int bo_backend_upload_block(void *ctx, const uint8_t *dsq, int64_t n)
 int bo_backend_revcomp_slot(void *ctx, int src, int dst)
 {
   bo_backend *b = ctx;
-  int64_t n = b->n[src];
-  if (src == dst || src < 0 || src > 1 || dst < 0 || dst > 1 || !b->dsq[src]) return BO_EINVAL;
+  int64_t n;
+  if (src == dst || src < 0 || dst < 0 || src >= 65536 || dst >= 65536 || grow_slots(b, (src > dst ? src : dst) + 1) != BO_OK || !b->dsq[src]) return BO_EINVAL;
+  n = b->n[src];
   free(b->dsq[dst]);
   b->dsq[dst] = malloc((size_t) n + 2);
   memcpy(b->dsq[dst], b->dsq[src], (size_t) n + 2);
@@ -526,8 +548,6 @@ static void msvx_item(bo_backend *b, void *arg, int i)
   free(d);
 }
 
-static bathgpu_orf_hit *g_hits[2];       /* per slot: survivors of the last screen (the backend is single-context in tests and bench) */
-static int64_t          g_nhits[2];
 
 int bo_backend_orfs_msv_screen(void *ctx, const void *blocks, int nblocks, int complement, const uint8_t gcode[64], int min_len,
                                const uint8_t *tjb_of, const float *null_of, int max_len, double min_bits,
@@ -543,7 +563,7 @@ int bo_backend_orfs_msv_screen(void *ctx, const void *blocks, int nblocks, int c
   int64_t tot_hits = 0, tot_res = 0, cap_res = 0;
   int bi, i, s = b->cur;
   parallel_for(b, nblocks, xl_item, &xa);
-  free(g_hits[s]); g_hits[s] = NULL; g_nhits[s] = 0;
+  free(b->hits[s]); b->hits[s] = NULL; b->nhits[s] = 0;
   free(b->res[s]); b->res[s] = NULL; b->nres[s] = 0;
   for (bi = 0; bi < nblocks; bi++) cap_res += nr[bi];
   b->res[s] = malloc((size_t) (cap_res > 0 ? cap_res : 1));
@@ -562,17 +582,17 @@ int bo_backend_orfs_msv_screen(void *ctx, const void *blocks, int nblocks, int c
       if (dead[i]) continue;
       keep = (st[i] != 0) || (((double) usc[i] - (double) null_of[L < max_len ? L : max_len]) / 0.69314718055994529 >= min_bits);
       if (!keep) continue;
-      g_hits[s] = realloc(g_hits[s], sizeof(bathgpu_orf_hit) * (size_t) (tot_hits + 1));
-      g_hits[s][tot_hits].block = bi; g_hits[s][tot_hits].index = i; g_hits[s][tot_hits].start = orfs[bi][i].start;
-      g_hits[s][tot_hits].end = orfs[bi][i].end; g_hits[s][tot_hits].n = L; g_hits[s][tot_hits].frame = orfs[bi][i].frame;
-      g_hits[s][tot_hits].offset = tot_res; g_hits[s][tot_hits].usc = usc[i]; g_hits[s][tot_hits].status = st[i];
+      b->hits[s] = realloc(b->hits[s], sizeof(bathgpu_orf_hit) * (size_t) (tot_hits + 1));
+      b->hits[s][tot_hits].block = bi; b->hits[s][tot_hits].index = i; b->hits[s][tot_hits].start = orfs[bi][i].start;
+      b->hits[s][tot_hits].end = orfs[bi][i].end; b->hits[s][tot_hits].n = L; b->hits[s][tot_hits].frame = orfs[bi][i].frame;
+      b->hits[s][tot_hits].offset = tot_res; b->hits[s][tot_hits].usc = usc[i]; b->hits[s][tot_hits].status = st[i];
       memcpy(b->res[s] + tot_res, res[bi] + orfs[bi][i].offset, (size_t) L);
       tot_res += L; tot_hits++;
     }
     free(usc); free(st); free(dead); free(orfs[bi]); free(res[bi]);
   }
   free(orfs); free(norf); free(res); free(nr);
-  g_nhits[s] = tot_hits; b->nres[s] = tot_res;
+  b->nhits[s] = tot_hits; b->nres[s] = tot_res;
   *nhits = tot_hits; *nres = tot_res;
   return BO_OK;
 }
@@ -581,8 +601,8 @@ int bo_backend_orfs_fetch(void *ctx, void *hits, uint8_t *residues)
 {
   bo_backend *b = ctx;
   int s = b->cur;
-  if (g_nhits[s] > 0) {
-    memcpy(hits, g_hits[s], sizeof(bathgpu_orf_hit) * (size_t) g_nhits[s]);
+  if (b->nhits[s] > 0) {
+    memcpy(hits, b->hits[s], sizeof(bathgpu_orf_hit) * (size_t) b->nhits[s]);
     memcpy(residues, b->res[s], (size_t) b->nres[s]);
   }
   return BO_OK;
