@@ -14,7 +14,11 @@
 // standard-translation branch (region_trace_ensemble, src/p7_domaindef.c:539-587) -- there such regions are rescored as one
 // envelope and counted in the statistics.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -196,6 +200,8 @@ struct Hit {
   bool from_fs_branch = false;      // P7_HIT::frameshift: made by p7_pli_postDomainDef_Frameshift_BATH (src/p7_pipeline.c:1114)
   double sortkey;
   bool duplicate = false, reported = false;
+  bool evalue_done = false;         // lnP_raw holds the hit's own ln P; pub.lnP the search-space corrected one
+  double lnP_raw = 0.0;
 };
 
 struct Options {
@@ -226,10 +232,16 @@ struct HostBuf {
   ~HostBuf() { if (p) { if (release) release(p); else free(p); } }
 };
 
+struct SeqRef {                                  // one queued target sequence (the caller keeps dsq alive until the batch has run)
+  std::string name;
+  const uint8_t *dsq = nullptr;                  // 1..n with sentinels
+  int64_t n = 0, seqidx = 0;
+  std::vector<uint8_t> own;                      // bathhost_search_sequence copies nothing; _queue_copy keeps the bytes here
+};
+
 struct bathhost_search {
   const bathhost_model *model;
-  bathhost_backend      be;
-  HostBuf               xbuf[2][2];
+  std::vector<bathhost_backend> bes;              // device contexts the stages are dealt to (one or more per GPU)
   HostBuf               mxbuf[2];                 // Forward matrices and X rows of multi-domain regions
   Options               opt;
   Background            bg;
@@ -238,36 +250,104 @@ struct bathhost_search {
   bathhost_stats        st{};
   std::vector<Hit>      hits;
   std::string           err;
+  std::mutex            err_mu;
+  std::vector<SeqRef>   queue;                    // sequences waiting for bathhost_search_run
+  bool                  finished = false;
+  // ---- state the reference carries from one block-strand to the next, across sequences (src/bathsearch.c:817,1060-1105):
+  // the hit_windows list is created once per query and never reset; by_id indexes it by ORF rank
+  std::vector<OrfWin>   hit_windows;
+  std::vector<std::vector<int>> by_id;
   // the length model left in om_fs5 by the last thing that reconfigured it (src/p7_domaindef.c:324, :1018):
   // p7_DomainDecoding_Frameshift reads its N/J/C loop odds (decoding_fs.c:309-349)
   float                 om5_nj = 1.0f;
   int                   om5_L = 100;
   int64_t               nseqs = 0;
+  int64_t               chunk_nt = 0;             // 0: chosen per batch
 
-  bathhost_search(const bathhost_model *m, const bathhost_backend &b) : model(m), be(b), bg(m->bg) {}
+  bathhost_search(const bathhost_model *m, const bathhost_backend *b, int nb) : model(m), bes(b, b + nb), bg(m->bg) {}
 };
 
 namespace {
 
-int fail(bathhost_search *s, int code, const std::string &msg) { s->err = msg; return code; }
+int fail(bathhost_search *s, int code, const std::string &msg) { std::lock_guard<std::mutex> lk(s->err_mu); s->err = msg; return code; }
 
-// static partition of [0,n) over the host cores
-template <class F> void parallel_chunks(size_t n, size_t min_chunk, F &&fn)
-{
-  static const size_t hw = [] {        // BATHHOST_THREADS: host threads of THIS process (one process per GPU shares the host's cores)
+// The host threads of this process: ONE persistent pool shared by every search and every device driver thread (a pool per
+// GPU-rank, re-spawned per stage, starved the 8-GPU search of cores).  BATHHOST_THREADS caps it (default: all cores, at most 64).
+// parallel_chunks(n, min_chunk, fn) runs fn(a, b) over a partition of [0, n); the caller works too, and calls from several
+// threads at once share the workers.
+class HostPool {
+ public:
+  static HostPool &get() { static HostPool p; return p; }
+  size_t size() const { return workers_.size() + 1; }
+  struct Job { std::function<void(size_t, size_t)> fn; size_t n = 0, step = 1; std::atomic<size_t> next{ 0 }, done{ 0 }; size_t nchunks = 0; };
+  void run(size_t n, size_t nthr, const std::function<void(size_t, size_t)> &fn)
+  {
+    auto job = std::make_shared<Job>();
+    job->fn = fn; job->n = n;
+    const size_t pieces = nthr * 4;                         // finer than the thread count: uneven items even out
+    job->step = std::max<size_t>(1, (n + pieces - 1) / pieces);
+    job->nchunks = (n + job->step - 1) / job->step;
+    { std::lock_guard<std::mutex> lk(mu_); jobs_.push_back(job); }
+    cv_.notify_all();
+    work(*job);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [&] { return job->done.load() >= job->nchunks; });
+    jobs_.erase(std::remove(jobs_.begin(), jobs_.end(), job), jobs_.end());
+  }
+ private:
+  HostPool()
+  {
     const char *e = getenv("BATHHOST_THREADS");
     const long v = e ? atol(e) : 0;
-    return (size_t) std::max<long>(1, v > 0 ? std::min<long>(v, 64) : std::min<long>((long) std::thread::hardware_concurrency(), 32));
-  }();
-  const size_t nthr = std::max<size_t>(1, std::min(hw, n / std::max<size_t>(1, min_chunk)));
-  if (nthr <= 1) { fn((size_t) 0, n); return; }
-  std::vector<std::thread> pool;
-  const size_t step = (n + nthr - 1) / nthr;
-  for (size_t t = 0; t < nthr; ++t) {
-    const size_t a = t * step, b = std::min(n, a + step);
-    if (a < b) pool.emplace_back([&fn, a, b]() { fn(a, b); });
+    const long hw = std::max<long>(1, v > 0 ? std::min<long>(v, 256) : std::min<long>((long) std::thread::hardware_concurrency(), 64));
+    for (long t = 1; t < hw; ++t) workers_.emplace_back([this] { loop(); });
   }
-  for (auto &th : pool) th.join();
+  ~HostPool()
+  {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+    cv_.notify_all();
+    for (auto &t : workers_) t.join();
+  }
+  void work(Job &j)
+  {
+    for (;;) {
+      const size_t c = j.next.fetch_add(1);
+      if (c >= j.nchunks) return;
+      const size_t a = c * j.step, b = std::min(j.n, a + j.step);
+      j.fn(a, b);
+      if (j.done.fetch_add(1) + 1 >= j.nchunks) { std::lock_guard<std::mutex> lk(mu_); done_cv_.notify_all(); }
+    }
+  }
+  void loop()
+  {
+    for (;;) {
+      std::shared_ptr<Job> job;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] {
+          if (stop_) return true;
+          for (auto &j : jobs_) if (j->next.load() < j->nchunks) return true;
+          return false;
+        });
+        if (stop_) return;
+        for (auto &j : jobs_) if (j->next.load() < j->nchunks) { job = j; break; }
+      }
+      if (job) work(*job);
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::vector<std::shared_ptr<Job>> jobs_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_cv_;
+  bool stop_ = false;
+};
+
+template <class F> void parallel_chunks(size_t n, size_t min_chunk, F &&fn)
+{
+  HostPool &pool = HostPool::get();
+  const size_t nthr = std::max<size_t>(1, std::min(pool.size(), n / std::max<size_t>(1, min_chunk)));
+  if (nthr <= 1) { fn((size_t) 0, n); return; }
+  pool.run(n, nthr, std::function<void(size_t, size_t)>(std::ref(fn)));
 }
 
 struct StageTimer {              // adds the time since construction / last lap to a stats counter
@@ -279,9 +359,10 @@ struct StageTimer {              // adds the time since construction / last lap 
   }
 };
 
+// BE: the bathhost_backend the call goes to (a local reference at every call site)
 #define BE_TRY(s, call, what)                                                                   \
   do { int st_ = (call); if (st_ != 0) return fail(s, st_, std::string(what) + " failed: " +    \
-       (s->be.last_error ? s->be.last_error(s->be.ctx) : "?")); } while (0)
+       (BE.last_error ? BE.last_error(BE.ctx) : "?")); } while (0)
 
 // p7_pli_ComputeLocalCompo (src/p7_pipeline.c:427-458)
 void local_compo(const bathhost_model *m, const Background &bg, int k_start, int k_end, float *compo)
@@ -472,46 +553,56 @@ void summarize_alignment(const bathhost_model *m, const std::vector<bathgpu_trac
   snprintf(h.cigar, sizeof h.cigar, "%s", cigar.c_str());
 }
 
-// ---- one target sequence, both strands, stage-batched ------------------------------------------------------
-// The reference walks the sequence in blocks of block_length nucleotides carrying max_length*3 nucleotides of left
-// context, top strand then bottom strand of each block (src/bathsearch.c:1060-1105).  Here every DP stage runs ONCE PER
-// STRAND over the work of all blocks (the two strands sit in the device library's two target slots), and everything
-// whose result depends on the order the reference visits blocks in is done on the host in exactly that order:
-//   * hit_windows is never reset between blocks or strands in the reference (info->hw, src/bathsearch.c:817,1076,1090),
-//     so the window picked for an ORF (p7_pli_BuildDNAWindows) and the k-range scan of p7_pli_Frameshift see every
-//     window stamped with the same ORF index by EARLIER blocks -- reproduced by appending in reference order;
+// ---- a batch of target sequences, both strands, stage-batched and dealt to one or more devices ---------------------------
+// The reference walks each sequence in blocks of block_length nucleotides carrying max_length*3 nucleotides of left
+// context, top strand then bottom strand of each block (src/bathsearch.c:1060-1105).  Here the blocks of ALL queued
+// sequences are cut into CHUNKS (runs of consecutive blocks, a few Mbp); a chunk's two strands are two UNITS, resident in two
+// target slots of one device context.  Every DP stage runs once per unit over the work of all its blocks; units are dealt
+// round-robin to the device contexts, each driven by its own host thread, and everything whose result depends on the
+// order the reference visits blocks in is done on the host in exactly that order, whatever the number of devices:
+//   * hit_windows is never reset between blocks, strands or sequences in the reference (info->hw, src/bathsearch.c:817,
+//     1076,1090), so the window picked for an ORF (p7_pli_BuildDNAWindows) and the k-range scan of p7_pli_Frameshift see
+//     every window stamped with the same ORF index by EARLIER blocks -- reproduced by appending in reference order;
 //   * the length model left in om_fs5 by the previous window's rescoring feeds p7_DomainDecoding_Frameshift;
 //   * the early E-value cuts use the residue count at the time the block is processed.
+// So the merged hit list of N devices is the one-device list by construction: the same items go through the same kernels,
+// only in different batches.
 struct BlockInfo {
-  long long b0, b1;          // original coordinates of the block (context included)
+  long long b0, b1;          // original coordinates of the block on its sequence (context included)
   int       n, C, bw;        // dnasq->n, dnasq->C, dnasq->W
   long long nres_at[2];      // pli->nres when the top / bottom strand of this block is processed
+  int       seq;             // index into the batch's sequence list
+  long long coff;            // chunk coordinate (top strand, 0-based) of b0: the block is chunk positions coff+1 .. coff+n
 };
 
-struct Strand {
-  bool complement = false;
-  const uint8_t *top = nullptr;             // the caller's sequence (top-strand orientation), 1..n with sentinels
-  long long n_total = 0;
-  // q with q[1..len] = nucleotides g+1 .. g+len of THIS strand's orientation (8 more on either side for look-backs): the caller's
-  // buffer itself on the top strand; on the bottom strand a reverse-complemented copy of the stretch -- the bottom strand as a
-  // whole only ever exists on the device (bathgpu_revcomp_slot)
-  const uint8_t *oriented(long long g, int len, std::vector<uint8_t> &buf) const
-  {
-    if (!complement) return top + g;
-    static const uint8_t comp[18] = { 3, 2, 1, 0, 4, 6, 5, 8, 7, 9, 10, 14, 13, 12, 11, 15, 16, 17 };
-    const int pad = 8;
-    buf.resize((size_t) len + 2 * pad + 2);
-    for (int p = -pad + 1; p <= len + pad; ++p) {
-      const long long P = g + p;
-      uint8_t c = 255;
-      if (P >= 1 && P <= n_total) { const uint8_t o = top[n_total - P + 1]; c = (o < 18) ? comp[o] : o; }
-      buf[(size_t) (p + pad)] = c;
-    }
-    return buf.data() + pad;
+// q with q[1..len] = positions local0+1 .. local0+len of the block in the strand's orientation (8 more on either side for
+// look-backs): the caller's buffer itself on the top strand; on the bottom strand a reverse-complemented copy of the stretch --
+// the bottom strand as a whole only ever exists on the device (bathgpu_revcomp_slot)
+const uint8_t *oriented(const SeqRef &sq, const BlockInfo &blk, bool complement, long long local0, int len, std::vector<uint8_t> &buf)
+{
+  if (!complement) return sq.dsq + (blk.b0 - 1) + local0;
+  static const uint8_t comp[18] = { 3, 2, 1, 0, 4, 6, 5, 8, 7, 9, 10, 14, 13, 12, 11, 15, 16, 17 };
+  const int pad = 8;
+  buf.resize((size_t) len + 2 * pad + 2);
+  for (int p = -pad + 1; p <= len + pad; ++p) {
+    const long long P = blk.b1 + 1 - (local0 + p);          // sequence coordinate of oriented block position local0 + p
+    uint8_t c = 255;
+    if (P >= 1 && P <= sq.n) { const uint8_t o = sq.dsq[P]; c = (o < 18) ? comp[o] : o; }
+    buf[(size_t) (p + pad)] = c;
   }
+  return buf.data() + pad;
+}
+
+struct Unit {                               // one strand of one chunk
+  bool complement = false;
+  int  sidx = 0, chunk = 0, be = 0, slot = 0;
+  int  blk0 = 0, blk1 = 0;                  // its blocks: [blk0, blk1) of the batch's block list
+  long long n_total = 0;                    // chunk length (both strands)
+  bathhost_stats st{};                      // this unit's share of the counters and stage times
+  HostBuf xbuf[2];
   std::vector<Orf> orfs;                    // of all blocks, block-local coordinates
   std::vector<int> orf_blk;                 // block of each ORF
-  std::vector<int> orf_begin;               // [nblocks+1] range of each block's ORFs
+  std::vector<int> orf_begin;               // [nblocks+1] range of each block's ORFs (index: block - blk0)
   std::vector<uint8_t> residues;
   std::vector<double> P_orf;
   std::vector<float>  fwdsc_orf;
@@ -525,7 +616,7 @@ struct Strand {
   std::vector<int32_t> fs_st;
   std::vector<int>     fsw;                 // windows that go down the frameshift branch
   std::vector<size_t>  xoff;
-  float *fxr = nullptr, *bxr = nullptr;     // X rows of the Forward / Backward parsers (page-locked buffers owned by the search)
+  float *fxr = nullptr, *bxr = nullptr;     // X rows of the Forward / Backward parsers (page-locked buffers owned by the unit)
   std::vector<int32_t> st2;
   struct Env { int win, i, j; };
   std::vector<Env> envs;
@@ -535,35 +626,38 @@ struct Strand {
   struct StdItem { int gi, w; };            // ORF sent down the standard-translation branch, and the DNA window it lost to (-1: none)
   std::vector<StdItem> stdq;
   std::vector<uint8_t> aligned;             // oxf_holder[i] == NULL: this ORF has been aligned already
-  long long goff(const BlockInfo &b, long long n_total) const { return complement ? n_total - b.b1 : b.b0 - 1; }   // device coordinate = goff + block-local
-  long long start_of(const BlockInfo &b) const { return complement ? b.b1 : b.b0; }                               // dnasq->start
+  std::vector<std::pair<int, Hit>> hits_fs, hits_std;      // (block, hit) in the order the unit produces them
+  int &ob(int b) { return orf_begin[(size_t) (b - blk0)]; }
+  int &db(int b) { return dwin_begin[(size_t) (b - blk0)]; }
+  size_t &hwc(int b) { return hw_count[(size_t) (b - blk0)]; }
+  long long goff(const BlockInfo &b) const { return complement ? n_total - (b.coff + b.n) : b.coff; }   // slot coordinate = goff + block-local
+  long long start_of(const BlockInfo &b) const { return complement ? b.b1 : b.b0; }                       // dnasq->start
 };
 
-// stages 1-3 for one strand: ORFs of every block, MSV, bias, Viterbi/SSV windows, local-composition re-check, protein Forward
-int filter_strand(bathhost_search *s, Strand &S, const std::vector<BlockInfo> &blocks, long long n_total, int slot)
+// stages 1-3 for one unit: ORFs of every block, MSV, bias, Viterbi/SSV windows, local-composition re-check, protein Forward
+int filter_unit(bathhost_search *s, Unit &S, const std::vector<BlockInfo> &blocks)
 {
   const bathhost_model *m = s->model;
   const ProteinProfile &q = m->prot;
   const Options &opt = s->opt;
   const int M = q.M;
   const float *ev = m->hmm.evparam;
-  Background &bg = s->bg;
+  const Background &bg = s->bg;
+  const bathhost_backend &BE = s->bes[(size_t) S.be];
   StageTimer tm;
 
   // ---- stage 1: translation of every block, MSV over every ORF and the cheap side of the F1 test in ONE device call
   // (src/bathsearch.c:385-392, src/p7_pipeline.c:1632-1652).  What comes back are the ORFs that can still pass F1,
   // with their block-local rank in the reference's ORF order (the window bookkeeping keys on it) and their residues.
-  BE_TRY(s, s->be.select_slot(s->be.ctx, slot), "bathgpu_select_slot");
-  if (!S.complement) BE_TRY(s, s->be.upload_block(s->be.ctx, S.top, n_total), "bathgpu_upload_block");
-  else               BE_TRY(s, s->be.revcomp_slot(s->be.ctx, 0, 1), "bathgpu_revcomp_slot");      // slot 0 holds the top strand
-  tm.lap(s->st.us_upload);
-  const size_t nblk = blocks.size();
+  BE_TRY(s, BE.select_slot(BE.ctx, S.slot), "bathgpu_select_slot");      // the unit's nucleotides were made resident by the caller
+  const size_t nblk = (size_t) (S.blk1 - S.blk0);
   S.orf_begin.assign(nblk + 1, 0);
   std::vector<bathgpu_block> bdesc(nblk);
   int maxlen = 1;
   for (size_t b = 0; b < nblk; ++b) {
-    bdesc[b].goff = S.goff(blocks[b], n_total); bdesc[b].n = (blocks[b].n >= 15) ? blocks[b].n : 0; bdesc[b].C = blocks[b].C;
-    maxlen = std::max(maxlen, blocks[b].n / 3 + 1);
+    const BlockInfo &blk = blocks[(size_t) S.blk0 + b];
+    bdesc[b].goff = S.goff(blk); bdesc[b].n = (blk.n >= 15) ? blk.n : 0; bdesc[b].C = blk.C;
+    maxlen = std::max(maxlen, blk.n / 3 + 1);
   }
   // per-length integers and null1 scores depend on the ORF length only: tabulated once per strand
   std::vector<uint8_t> tjb_of((size_t) maxlen + 1);
@@ -578,12 +672,12 @@ int filter_strand(bathhost_search *s, Strand &S, const std::vector<BlockInfo> &b
   const double x1 = gumbel_invsurv(opt.F1, ev[EV_MMU], ev[EV_MLAMBDA]);
   std::vector<int64_t> norfs_blk(nblk, 0);
   int64_t nsurv = 0, nsres = 0;
-  BE_TRY(s, s->be.orfs_msv_screen(s->be.ctx, bdesc.data(), (int) nblk, S.complement ? 1 : 0, s->gcode, opt.min_orf, tjb_of.data(), null_of.data(),
+  BE_TRY(s, BE.orfs_msv_screen(BE.ctx, bdesc.data(), (int) nblk, S.complement ? 1 : 0, s->gcode, opt.min_orf, tjb_of.data(), null_of.data(),
                                    maxlen, x1 - 0.02, norfs_blk.data(), &nsurv, &nsres), "bathgpu_orfs_msv_screen");
-  for (size_t b = 0; b < nblk; ++b) s->st.n_orfs += norfs_blk[b];
+  for (size_t b = 0; b < nblk; ++b) S.st.n_orfs += norfs_blk[b];
   std::vector<bathgpu_orf_hit> surv((size_t) nsurv);
   S.residues.resize((size_t) nsres);
-  BE_TRY(s, s->be.orfs_fetch(s->be.ctx, surv.data(), S.residues.data()), "bathgpu_orfs_fetch");
+  BE_TRY(s, BE.orfs_fetch(BE.ctx, surv.data(), S.residues.data()), "bathgpu_orfs_fetch");
   const int norf = (int) nsurv;
   S.orfs.resize((size_t) norf); S.orf_blk.resize((size_t) norf);
   {
@@ -594,7 +688,7 @@ int filter_strand(bathhost_search *s, Strand &S, const std::vector<BlockInfo> &b
         Orf &o = S.orfs[z];
         o.start = surv[z].start; o.end = surv[z].end; o.frame = surv[z].frame; o.offset = surv[z].offset; o.n = surv[z].n;
         o.local_idx = surv[z].index; o.window_idx = -1;
-        S.orf_blk[z] = (int) b;
+        S.orf_blk[z] = S.blk0 + (int) b;
         ++z;
       }
     }
@@ -603,7 +697,7 @@ int filter_strand(bathhost_search *s, Strand &S, const std::vector<BlockInfo> &b
   S.P_orf.assign((size_t) norf, 1.0);
   S.fwdsc_orf.assign((size_t) norf, kNegInfF);
   S.wins_of_orf.assign((size_t) norf, {});
-  tm.lap(s->st.us_msv);
+  tm.lap(S.st.us_msv);
   if (norf == 0) return 0;
 
   std::vector<Orf> &orfs = S.orfs;
@@ -650,15 +744,15 @@ int filter_strand(bathhost_search *s, Strand &S, const std::vector<BlockInfo> &b
     for (size_t t = 0; t < live.size(); ++t) {
       if (pre[t].stage == 0) continue;
       const Orf &o = orfs[live[t]];
-      s->st.pos_past_msv += (int64_t) o.n * 3;
+      S.st.pos_past_msv += (int64_t) o.n * 3;
       if (pre[t].stage == 1) continue;
-      s->st.pos_past_bias += (int64_t) o.n * 3;
+      S.st.pos_past_bias += (int64_t) o.n * 3;
       Cand c; c.orf = live[t]; c.nullsc = null_of[o.n]; c.usc = usc[t]; c.filtersc = pre[t].filtersc; c.vfsc = kNegInfF; c.P = pre[t].P;
       c.need_vit = (c.P > opt.F2);
       cand.push_back(c);
     }
   }
-  tm.lap(s->st.us_bias);
+  tm.lap(S.st.us_bias);
   if (cand.empty()) return 0;
 
   // ---- stage 2: Viterbi filter with windows, or the SSV window finder for ORFs already below F2 (:1666-1680)
@@ -690,7 +784,7 @@ int filter_strand(bathhost_search *s, Strand &S, const std::vector<BlockInfo> &b
     int max_w = 0; for (auto &x : d) max_w += x.L / 2 + 4;
     std::vector<bathgpu_orf_window> w((size_t) max_w);
     int nw = 0;
-    BE_TRY(s, s->be.vit_orfs(s->be.ctx, d.data(), (int) d.size(), vsc.data(), vst.data(), w.data(), max_w, &nw), "bathgpu_vit_orfs");
+    BE_TRY(s, BE.vit_orfs(BE.ctx, d.data(), (int) d.size(), vsc.data(), vst.data(), w.data(), max_w, &nw), "bathgpu_vit_orfs");
     for (size_t z = 0; z < vit_idx.size(); ++z) cand[vit_idx[z]].vfsc = vsc[z];
     for (int x = 0; x < nw; ++x) wins_of[vit_idx[w[x].orf]].push_back(OrfWin{ 0, w[x].n, w[x].k, w[x].length, w[x].score });
   }
@@ -700,7 +794,7 @@ int filter_strand(bathhost_search *s, Strand &S, const std::vector<BlockInfo> &b
     int max_w = 0; for (auto &x : d) max_w += x.L / 2 + 4;
     std::vector<bathgpu_orf_window> w((size_t) max_w);
     int nw = 0;
-    BE_TRY(s, s->be.ssv_windows(s->be.ctx, d.data(), (int) d.size(), w.data(), max_w, &nw), "bathgpu_ssv_windows");
+    BE_TRY(s, BE.ssv_windows(BE.ctx, d.data(), (int) d.size(), w.data(), max_w, &nw), "bathgpu_ssv_windows");
     for (int x = 0; x < nw; ++x) wins_of[ssv_idx[w[x].orf]].push_back(OrfWin{ 0, w[x].n, w[x].k, w[x].length, w[x].score });
   }
 
@@ -753,7 +847,7 @@ int filter_strand(bathhost_search *s, Strand &S, const std::vector<BlockInfo> &b
     });
     for (size_t t = 0; t < cand.size(); ++t) {
       if (verdict[t] == 0) { wins_of[t].clear(); continue; }
-      s->st.pos_past_vit += (int64_t) orfs[cand[t].orf].n * 3;
+      S.st.pos_past_vit += (int64_t) orfs[cand[t].orf].n * 3;
       if (verdict[t] == 1) { wins_of[t].clear(); continue; }
       if (verdict[t] == 2) rerun.push_back((int) t); else keep.push_back((int) t);
     }
@@ -764,7 +858,7 @@ int filter_strand(bathhost_search *s, Strand &S, const std::vector<BlockInfo> &b
     std::vector<float> vsc(d.size());
     std::vector<int32_t> vst(d.size());
     int nw = 0;
-    BE_TRY(s, s->be.vit_orfs(s->be.ctx, d.data(), (int) d.size(), vsc.data(), vst.data(), nullptr, 0, &nw), "bathgpu_vit_orfs");
+    BE_TRY(s, BE.vit_orfs(BE.ctx, d.data(), (int) d.size(), vsc.data(), vst.data(), nullptr, 0, &nw), "bathgpu_vit_orfs");
     for (size_t z = 0; z < rerun.size(); ++z) {
       Cand &c = cand[rerun[z]];
       c.vfsc = vsc[z];
@@ -774,7 +868,7 @@ int filter_strand(bathhost_search *s, Strand &S, const std::vector<BlockInfo> &b
     }
     std::sort(keep.begin(), keep.end());
   }
-  tm.lap(s->st.us_vit);
+  tm.lap(S.st.us_vit);
   if (keep.empty()) return 0;
 
   // ---- stage 3: protein Forward over the survivors (:1774-1789)
@@ -784,7 +878,7 @@ int filter_strand(bathhost_search *s, Strand &S, const std::vector<BlockInfo> &b
     std::vector<float> fsc(d.size());
     std::vector<int32_t> fst(d.size());
     const float xfE[2] = { expf(q.xsc_E_move), expf(q.xsc_E_loop) };
-    BE_TRY(s, s->be.fwd_orfs(s->be.ctx, d.data(), (int) d.size(), q.nj, xfE, fsc.data(), fst.data()), "bathgpu_fwd_orfs");
+    BE_TRY(s, BE.fwd_orfs(BE.ctx, d.data(), (int) d.size(), q.nj, xfE, fsc.data(), fst.data()), "bathgpu_fwd_orfs");
     for (size_t z = 0; z < keep.size(); ++z) {
       const Cand &c = cand[keep[z]];
       const float seqsc = (fsc[z] - c.filtersc) / kLog2;
@@ -794,7 +888,7 @@ int filter_strand(bathhost_search *s, Strand &S, const std::vector<BlockInfo> &b
     }
   }
 
-  tm.lap(s->st.us_fwd);
+  tm.lap(S.st.us_fwd);
   return 0;
 }
 
@@ -802,14 +896,17 @@ int filter_strand(bathhost_search *s, Strand &S, const std::vector<BlockInfo> &b
 // scans the whole list for an index (and the list is never reset, so earlier blocks' entries with the same index count too)
 typedef std::vector<std::vector<int>> HitIndex;
 
-// p7_pli_BuildDNAWindows (src/p7_pipeline.c:462-572) for one block-strand, against the accumulated hit_windows list
-void build_dna_windows(bathhost_search *s, Strand &S, const BlockInfo &blk, int b, const std::vector<OrfWin> &hit_windows, const HitIndex &by_id)
+// p7_pli_BuildDNAWindows (src/p7_pipeline.c:462-572) for one block-strand, against the accumulated hit_windows list.
+// The ORF's window_idx mirrors orfsq->idx, stale values included: BuildDNAWindows leaves the pre-merge rank there (:545), and its
+// merge loop then stamps "orf_block->list[i].idx = new_hit_cnt" on the ORF whose BLOCK RANK equals the window index i (:569) --
+// p7_pli_Frameshift's standard-translation loop (:1484) reads idx of every ORF, also of those no window of the loop touched yet.
+void build_dna_windows(bathhost_search *s, Unit &S, const BlockInfo &blk, int b, const std::vector<OrfWin> &hit_windows, const HitIndex &by_id)
 {
   const ProteinProfile &q = s->model->prot;
   const Options &opt = s->opt;
   const int M = q.M;
   std::vector<DnaWin> dwin;
-  for (int gi = S.orf_begin[b]; gi < S.orf_begin[b + 1]; ++gi) {
+  for (int gi = S.ob(b); gi < S.ob(b + 1); ++gi) {
     const int f = S.orfs[gi].local_idx;
     if (S.P_orf[gi] > opt.F4) continue;
     Orf &o = S.orfs[gi];
@@ -832,9 +929,15 @@ void build_dna_windows(bathhost_search *s, Strand &S, const BlockInfo &blk, int 
     ws = std::max<long long>(1, o.start + ws * 3);       // (n - start_ref + 1) == o.start on the bottom strand
     we = std::min<long long>(blk.n, o.start + we * 3);
     dwin.push_back(DnaWin{ ws, cw.k, (int) (we - ws + 1) });
+    o.window_idx = (int) dwin.size() - 1;                // curr_orf->idx = windowlist->count - 1 (:545)
   }
   if (!dwin.empty()) {
     std::stable_sort(dwin.begin(), dwin.end(), [](const DnaWin &x, const DnaWin &y) { return x.n < y.n; });
+    auto stamp = [&](int rank, int idx) {                // the survivor of block b whose rank in the block is `rank`, if it survived
+      int lo = S.ob(b), hi = S.ob(b + 1);
+      while (lo < hi) { const int mid = (lo + hi) / 2; if (S.orfs[mid].local_idx < rank) lo = mid + 1; else hi = mid; }
+      if (lo < S.ob(b + 1) && S.orfs[lo].local_idx == rank) S.orfs[lo].window_idx = idx;
+    };
     size_t nh = 0;
     for (size_t i = 1; i < dwin.size(); ++i) {
       DnaWin &pw = dwin[nh];
@@ -845,263 +948,375 @@ void build_dna_windows(bathhost_search *s, Strand &S, const BlockInfo &blk, int 
       const long long w_len = w_e - w_s + 1;
       if (((float) ov_len / std::min(pw.length, cw.length) > 0.0f) && w_len < (2 * (q.max_length * 3))) { pw.n = w_s; pw.length = (int) w_len; }
       else { nh++; dwin[nh] = dwin[i]; }
+      stamp((int) i, (int) nh);                          // orf_block->list[i].idx = new_hit_cnt (:569)
     }
     dwin.resize(nh + 1);
   }
   for (const DnaWin &d : dwin) { S.dwin.push_back(d); S.dwin_blk.push_back(b); }
 }
 
-int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, int64_t n)
+// run fn(backend index) on one host thread per device context; the first failure is returned
+template <class F> int for_each_backend(bathhost_search *s, F &&fn)
+{
+  const size_t nbe = s->bes.size();
+  std::vector<int> rc(nbe, 0);
+  if (nbe == 1) return fn(0);
+  std::vector<std::thread> th;
+  for (size_t k = 1; k < nbe; ++k) th.emplace_back([&, k] { rc[k] = fn((int) k); });
+  rc[0] = fn(0);
+  for (auto &t : th) t.join();
+  for (int r : rc) if (r != 0) return r;
+  return 0;
+}
+
+void add_stats(bathhost_stats &a, const bathhost_stats &b)
+{
+  a.pos_past_msv += b.pos_past_msv; a.pos_past_bias += b.pos_past_bias; a.pos_past_vit += b.pos_past_vit; a.pos_past_fwd += b.pos_past_fwd;
+  a.n_orfs += b.n_orfs; a.n_windows += b.n_windows; a.n_std_windows += b.n_std_windows; a.n_regions += b.n_regions;
+  a.n_multidomain_regions += b.n_multidomain_regions; a.n_envelopes += b.n_envelopes;
+  a.us_orfs += b.us_orfs; a.us_upload += b.us_upload; a.us_msv += b.us_msv; a.us_bias += b.us_bias; a.us_vit += b.us_vit; a.us_fwd += b.us_fwd;
+  a.us_windows += b.us_windows; a.us_fs_fwd += b.us_fs_fwd; a.us_fs_domains += b.us_fs_domains; a.us_std += b.us_std; a.us_xrows += b.us_xrows;
+  a.us_decode += b.us_decode; a.us_score += b.us_score;
+}
+
+// Every queued sequence, both strands.  Stage times in the statistics are summed over units (device contexts work side by side,
+// so with several of them the sum exceeds the wall time).
+int run_batch(bathhost_search *s)
 {
   const bathhost_model *m = s->model;
   const ProteinProfile &q = m->prot;
   const Options &opt = s->opt;
   const int M = q.M;
   const float *ev = m->hmm.evparam;
-  Background &bg = s->bg;
+  const Background &bg = s->bg;
+  std::vector<SeqRef> seqs;
+  seqs.swap(s->queue);
+  if (seqs.empty()) return 0;
 
   // ---- the reference's blocks (src/bathsearch.c:1060-1105) and the residue count as each block-strand is reached
   std::vector<BlockInfo> blocks;
   {
     const int C = q.max_length * 3, W = opt.block_length;
-    int64_t pos = 1;
-    bool first = true;
     long long nres = s->st.nres;
-    while (pos <= n) {
-      const int64_t ctx = first ? 0 : std::min<int64_t>(C, pos - 1);
-      BlockInfo b;
-      b.b0 = pos - ctx; b.b1 = std::min<int64_t>(n, pos + W - 1);
-      b.n = (int) (b.b1 - b.b0 + 1); b.C = (int) ctx; b.bw = (int) (b.b1 - pos + 1);
-      b.nres_at[0] = b.nres_at[1] = nres;
-      if (b.n >= 15) {
-        if (opt.top)    { nres += b.bw; b.nres_at[0] = nres; }
-        if (opt.bottom) { nres += b.bw; b.nres_at[1] = nres; }
+    for (size_t sq = 0; sq < seqs.size(); ++sq) {
+      const int64_t n = seqs[sq].n;
+      int64_t pos = 1;
+      bool first = true;
+      while (pos <= n) {
+        const int64_t ctx = first ? 0 : std::min<int64_t>(C, pos - 1);
+        BlockInfo b;
+        b.b0 = pos - ctx; b.b1 = std::min<int64_t>(n, pos + W - 1);
+        b.n = (int) (b.b1 - b.b0 + 1); b.C = (int) ctx; b.bw = (int) (b.b1 - pos + 1);
+        b.seq = (int) sq; b.coff = 0;
+        b.nres_at[0] = b.nres_at[1] = nres;
+        if (b.n >= 15) {
+          if (opt.top)    { nres += b.bw; b.nres_at[0] = nres; }
+          if (opt.bottom) { nres += b.bw; b.nres_at[1] = nres; }
+        }
+        blocks.push_back(b);
+        pos = b.b1 + 1;
+        first = false;
       }
-      blocks.push_back(b);
-      pos = b.b1 + 1;
-      first = false;
     }
     s->st.nres = nres;
   }
   const size_t nb = blocks.size();
 
-  Strand strands[2];
+  // ---- chunks: runs of consecutive blocks; a chunk's nucleotides are the concatenation of its SEGMENTS (one per sequence it
+  // touches: first block's b0 .. last block's b1), so blocks of one sequence keep their overlap and nothing is stored twice
+  struct ChunkSeg { int seq; long long from, to, off; };     // sequence coordinates from..to at chunk offset off (0-based)
+  struct Chunk { int blk0, blk1; long long n; std::vector<ChunkSeg> segs; };
+  std::vector<Chunk> chunks;
+  {
+    long long total = 0;
+    for (const BlockInfo &b : blocks) total += b.n;
+    long long target = s->chunk_nt;
+    if (target <= 0) {
+      static const long long env_mbp = [] { const char *e = getenv("BATHHOST_CHUNK_MBP"); return e ? atoll(e) : 0LL; }();
+      target = env_mbp > 0 ? env_mbp * 1000000LL
+                           : std::max<long long>(4000000LL, std::min<long long>(32000000LL, total / (long long) (3 * s->bes.size()) + 1));
+    }
+    for (size_t b = 0; b < nb; ++b) {
+      const BlockInfo &blk = blocks[b];
+      const bool same_seq = !chunks.empty() && chunks.back().blk1 == (int) b && !chunks.back().segs.empty() && chunks.back().segs.back().seq == blk.seq;
+      const long long grow = same_seq ? blk.b1 - chunks.back().segs.back().to : blk.n;
+      if (chunks.empty() || chunks.back().n + grow > target) { chunks.push_back(Chunk{ (int) b, (int) b, 0, {} }); }
+      Chunk &c = chunks.back();
+      if (!c.segs.empty() && c.segs.back().seq == blk.seq && c.blk1 == (int) b) {      // the sequence's next block: extend its segment
+        blocks[b].coff = c.segs.back().off + (blk.b0 - c.segs.back().from);
+        c.n += blk.b1 - c.segs.back().to;
+        c.segs.back().to = blk.b1;
+      } else {
+        c.segs.push_back(ChunkSeg{ blk.seq, blk.b0, blk.b1, c.n });
+        blocks[b].coff = c.n;
+        c.n += blk.n;
+      }
+      c.blk1 = (int) b + 1;
+    }
+  }
+
+  // ---- units: the two strands of a chunk live in two slots of the same device context (the bottom strand is made from the top
+  // one on the device); chunks are dealt round-robin to the contexts
   std::vector<int> active;
   if (opt.top)    active.push_back(0);
   if (opt.bottom) active.push_back(1);
-  for (int sidx : active) {
-    Strand &S = strands[sidx];
-    S.complement = (sidx == 1);
-    StageTimer tm0;
-    S.top = dsq; S.n_total = n;
-    if (S.complement && !opt.top) {                         // bottom strand only: the device still needs the top strand to complement
-      BE_TRY(s, s->be.select_slot(s->be.ctx, 0), "bathgpu_select_slot");
-      BE_TRY(s, s->be.upload_block(s->be.ctx, dsq, n), "bathgpu_upload_block");
+  std::vector<std::unique_ptr<Unit>> units(chunks.size() * 2);
+  std::vector<std::vector<int>> chunks_of_be(s->bes.size());
+  for (size_t c = 0; c < chunks.size(); ++c) {
+    const int be = (int) (c % s->bes.size());
+    const int nth = (int) chunks_of_be[(size_t) be].size();
+    chunks_of_be[(size_t) be].push_back((int) c);
+    for (int sidx = 0; sidx < 2; ++sidx) {
+      units[2 * c + sidx].reset(new Unit());
+      Unit &U = *units[2 * c + sidx];
+      U.complement = (sidx == 1); U.sidx = sidx; U.chunk = (int) c; U.be = be; U.slot = 2 * nth + sidx;
+      U.blk0 = chunks[c].blk0; U.blk1 = chunks[c].blk1; U.n_total = chunks[c].n;
     }
-    tm0.lap(s->st.us_orfs);
-    int st = filter_strand(s, S, blocks, n, sidx);
-    if (st != 0) return st;
-    S.aligned.assign(S.orfs.size(), 0);
-    if (!opt.fs)                                            // default pipeline: every ORF past F3 is aligned by itself (:1720-1771)
-      for (size_t gi = 0; gi < S.orfs.size(); ++gi)
-        if (S.P_orf[gi] <= opt.F3) { s->st.pos_past_fwd += (int64_t) S.orfs[gi].n * 3; S.stdq.push_back(Strand::StdItem{ (int) gi, -1 }); }
   }
+  auto unit_of = [&](size_t c, int sidx) -> Unit & { return *units[2 * c + sidx]; };
+  std::vector<int> chunk_of_block(nb);
+  for (size_t c = 0; c < chunks.size(); ++c) for (int b = chunks[c].blk0; b < chunks[c].blk1; ++b) chunk_of_block[(size_t) b] = (int) c;
 
-  // ---- DNA windows, block by block in the reference's order, against the ever-growing hit_windows list
+  // ---- stages 1-3 per unit, device contexts side by side: upload (top) / reverse complement on the device (bottom), ORFs, filters
+  int rc = for_each_backend(s, [&](int be) -> int {
+    const bathhost_backend &BE = s->bes[(size_t) be];
+    HostBuf stage;                                             // concatenation buffer for chunks of several sequences
+    for (int c : chunks_of_be[(size_t) be]) {
+      const Chunk &ch = chunks[(size_t) c];
+      Unit &T = unit_of((size_t) c, 0), &B = unit_of((size_t) c, 1);
+      StageTimer tm0;
+      BE_TRY(s, BE.select_slot(BE.ctx, T.slot), "bathgpu_select_slot");
+      if (ch.segs.size() == 1) {                               // the caller's buffer as it is (the byte before and the one after are not read)
+        const ChunkSeg &g = ch.segs[0];
+        BE_TRY(s, BE.upload_block(BE.ctx, seqs[(size_t) g.seq].dsq + (g.from - 1), ch.n), "bathgpu_upload_block");
+      } else {
+        uint8_t *buf = reinterpret_cast<uint8_t *>(stage.get(BE, ((size_t) ch.n + 2 + 3) / 4));
+        if (!buf) return fail(s, BATHHOST_EMEM, "host allocation failed");
+        buf[0] = 255; buf[ch.n + 1] = 255;
+        parallel_chunks(ch.segs.size(), 1, [&](size_t ga, size_t gb) {
+          for (size_t g = ga; g < gb; ++g) memcpy(buf + 1 + ch.segs[g].off, seqs[(size_t) ch.segs[g].seq].dsq + ch.segs[g].from, (size_t) (ch.segs[g].to - ch.segs[g].from + 1));
+        });
+        BE_TRY(s, BE.upload_block(BE.ctx, buf, ch.n), "bathgpu_upload_block");
+      }
+      if (opt.bottom) BE_TRY(s, BE.revcomp_slot(BE.ctx, T.slot, B.slot), "bathgpu_revcomp_slot");
+      tm0.lap(T.st.us_upload);
+      for (int sidx : active) {
+        Unit &S = unit_of((size_t) c, sidx);
+        const int st = filter_unit(s, S, blocks);
+        if (st != 0) return st;
+        S.aligned.assign(S.orfs.size(), 0);
+        if (!opt.fs)                                            // default pipeline: every ORF past F3 is aligned by itself (:1720-1771)
+          for (size_t gi = 0; gi < S.orfs.size(); ++gi)
+            if (S.P_orf[gi] <= opt.F3) { S.st.pos_past_fwd += (int64_t) S.orfs[gi].n * 3; S.stdq.push_back(Unit::StdItem{ (int) gi, -1 }); }
+      }
+    }
+    return 0;
+  });
+  if (rc != 0) return rc;
+
+  // ---- DNA windows, block by block in the reference's order, against the ever-growing hit_windows list (kept across batches)
   StageTimer tm;
-  std::vector<OrfWin> hit_windows;
-  HitIndex by_id;
-  for (int sidx : active) { strands[sidx].dwin_begin.assign(nb + 1, 0); strands[sidx].hw_count.assign(nb, 0); }
+  std::vector<OrfWin> &hit_windows = s->hit_windows;
+  HitIndex &by_id = s->by_id;
+  for (size_t c = 0; c < chunks.size(); ++c)
+    for (int sidx : active) { Unit &S = unit_of(c, sidx); S.dwin_begin.assign((size_t) (S.blk1 - S.blk0) + 1, 0); S.hw_count.assign((size_t) (S.blk1 - S.blk0), 0); }
   for (size_t b = 0; b < nb; ++b)
     for (int sidx : active) {
-      Strand &S = strands[sidx];
-      S.dwin_begin[b] = (int) S.dwin.size();
+      Unit &S = unit_of((size_t) chunk_of_block[b], sidx);
+      S.db((int) b) = (int) S.dwin.size();
       if (blocks[b].n >= 15 && opt.fs) {
-        for (int gi = S.orf_begin[b]; gi < S.orf_begin[b + 1]; ++gi)
+        for (int gi = S.ob((int) b); gi < S.ob((int) b + 1); ++gi)
           for (const OrfWin &w : S.wins_of_orf[gi]) {
             if ((size_t) w.id >= by_id.size()) by_id.resize((size_t) w.id + 1);
             by_id[w.id].push_back((int) hit_windows.size());
             hit_windows.push_back(w);
           }
-        S.hw_count[b] = hit_windows.size();
+        S.hwc((int) b) = hit_windows.size();
         build_dna_windows(s, S, blocks[b], (int) b, hit_windows, by_id);
-      } else S.hw_count[b] = hit_windows.size();
-      S.dwin_begin[b + 1] = (int) S.dwin.size();
+      } else S.hwc((int) b) = hit_windows.size();
+      S.db((int) b + 1) = (int) S.dwin.size();
     }
-  for (int sidx : active) for (size_t b = 0; b + 1 <= nb; ++b) strands[sidx].dwin_begin[b + 1] = std::max(strands[sidx].dwin_begin[b + 1], strands[sidx].dwin_begin[b]);
   tm.lap(s->st.us_windows);
 
-  // ---- stage 4: frameshift Forward parser over every DNA window, one call per strand (:1446-1450)
+  // ---- stages 4-5 per unit, device contexts side by side: frameshift Forward parser over every DNA window (:1446-1450), the
+  // arbitration between window and ORFs (:1392-1465), Forward + Backward X rows of the windows that stay (:1469-1470), and the
+  // part of p7_DomainDecoding_Frameshift that does not depend on the length-model chain
   const float xfE3[2] = { m->om3.xfE_move, m->om3.xfE_loop };
-  for (int sidx : active) {
-    Strand &S = strands[sidx];
-    const int nwin = (int) S.dwin.size();
-    if (nwin == 0) continue;
-    S.gw.resize((size_t) nwin);
-    for (int w = 0; w < nwin; ++w) {
-      S.gw[w].start = S.goff(blocks[S.dwin_blk[w]], n) + S.dwin[w].n; S.gw[w].L = S.dwin[w].length;
-      bathhost_length_model(S.dwin[w].length / 3, 1.0f, &S.gw[w].pmove, &S.gw[w].ploop);
-    }
-    S.fs_fwd.resize((size_t) nwin); S.fs_st.resize((size_t) nwin);
-    BE_TRY(s, s->be.select_slot(s->be.ctx, sidx), "bathgpu_select_slot");
-    BE_TRY(s, s->be.fs_fwd_windows(s->be.ctx, S.gw.data(), nwin, xfE3, S.fs_fwd.data(), S.fs_st.data()), "bathgpu_fs_fwd_windows");
-    s->st.n_windows += nwin;
-  }
-  tm.lap(s->st.us_fs_fwd);
+  struct Decoded { std::vector<float> btot, etot, fb, ex; };   // fb, ex: [L+1][9]
+  std::vector<std::vector<Decoded>> dec(units.size());
+  rc = for_each_backend(s, [&](int be) -> int {
+    const bathhost_backend &BE = s->bes[(size_t) be];
+    for (int c : chunks_of_be[(size_t) be])
+      for (int sidx : active) {
+        Unit &S = unit_of((size_t) c, sidx);
+        StageTimer tmu;
+        const int nwin = (int) S.dwin.size();
+        if (nwin == 0) continue;
+        S.gw.resize((size_t) nwin);
+        for (int w = 0; w < nwin; ++w) {
+          S.gw[w].start = S.goff(blocks[(size_t) S.dwin_blk[w]]) + S.dwin[w].n; S.gw[w].L = S.dwin[w].length;
+          bathhost_length_model(S.dwin[w].length / 3, 1.0f, &S.gw[w].pmove, &S.gw[w].ploop);
+        }
+        S.fs_fwd.resize((size_t) nwin); S.fs_st.resize((size_t) nwin);
+        BE_TRY(s, BE.select_slot(BE.ctx, S.slot), "bathgpu_select_slot");
+        BE_TRY(s, BE.fs_fwd_windows(BE.ctx, S.gw.data(), nwin, xfE3, S.fs_fwd.data(), S.fs_st.data()), "bathgpu_fs_fwd_windows");
+        S.st.n_windows += nwin;
+        tmu.lap(S.st.us_fs_fwd);
 
-  // ---- arbitration per window (:1392-1465): the scores each window needs (ORF sums, null and bias filter scores) are
-  // independent of one another and computed on all host cores; the decisions are then taken in the reference's order
-  for (int sidx : active) {
-    Strand &S = strands[sidx];
-    const int nw = (int) S.dwin.size();
-    struct WinPre { int orf_cnt; double P_tot, P_min; float nullsc, filtersc; };
-    std::vector<WinPre> pre((size_t) nw);
-    auto inside_of = [&](const Orf &o, const DnaWin &dw) {
-      return S.complement ? (o.start >= dw.n && o.end <= dw.n + dw.length + 1) : (o.start >= dw.n && o.end <= dw.n + dw.length - 1);
-    };
-    parallel_chunks((size_t) nw, 1, [&](size_t wa, size_t wb) {
-      Background lbg = bg;
-      float lcompo[kK];
-      std::vector<uint8_t> wbuf;
-      for (size_t w = wa; w < wb; ++w) {
-        const int b = S.dwin_blk[w];
-        const BlockInfo &blk = blocks[b];
-        const DnaWin &dw = S.dwin[w];
-        const uint8_t *wdsq = S.oriented(S.goff(blk, n) + dw.n - 1, dw.length, wbuf);        // window position p is wdsq[p]
-        int orf_cnt = 0, k_min = M, k_max = 0;
-        float tot_orfsc = kNegInfF;
-        double P_min = std::numeric_limits<double>::infinity();
-        size_t last_h = 0;
-        const size_t hw_n = S.hw_count[b];
-        for (int gi = S.orf_begin[b]; gi < S.orf_begin[b + 1]; ++gi) {
-          if (S.P_orf[gi] > opt.F4) continue;
-          const Orf &o = S.orfs[gi];
-          const int i = o.local_idx;
-          if (!inside_of(o, dw)) continue;
-          P_min = std::min(P_min, S.P_orf[gi]);
-          tot_orfsc = flogsum(tot_orfsc, S.fwdsc_orf[gi]);
-          orf_cnt++;
-          size_t h = last_h;
-          if ((size_t) i < by_id.size()) {                 // first entry stamped i at or after last_h (the reference scans forward for it)
-            const std::vector<int> &ix = by_id[i];
-            auto it = std::lower_bound(ix.begin(), ix.end(), (int) h);
-            h = (it == ix.end()) ? hw_n : std::min<size_t>(hw_n, (size_t) *it);
-          } else h = hw_n;
-          if (h < hw_n) {
-            while (h < hw_n && hit_windows[h].id == i) {
-              k_min = std::min(k_min, hit_windows[h].k - hit_windows[h].length + 1);
-              k_max = std::max(k_max, hit_windows[h].k);
-              h++;
+        // arbitration per window: the scores each window needs (ORF sums, null and bias filter scores) are independent of one
+        // another and computed on all host cores; the decisions are then taken in the reference's order
+        {
+          const int nw = nwin;
+          struct WinPre { int orf_cnt; double P_tot, P_min; float nullsc, filtersc; };
+          std::vector<WinPre> pre((size_t) nw);
+          auto inside_of = [&](const Orf &o, const DnaWin &dw) {
+            return S.complement ? (o.start >= dw.n && o.end <= dw.n + dw.length + 1) : (o.start >= dw.n && o.end <= dw.n + dw.length - 1);
+          };
+          const std::vector<OrfWin> &hit_windows = s->hit_windows;
+          const HitIndex &by_id = s->by_id;
+          parallel_chunks((size_t) nw, 1, [&](size_t wa, size_t wb) {
+            Background lbg = bg;
+            float lcompo[kK];
+            std::vector<uint8_t> wbuf;
+            for (size_t w = wa; w < wb; ++w) {
+              const int b = S.dwin_blk[w];
+              const BlockInfo &blk = blocks[(size_t) b];
+              const DnaWin &dw = S.dwin[w];
+              const uint8_t *wdsq = oriented(seqs[(size_t) blk.seq], blk, S.complement, dw.n - 1, dw.length, wbuf);        // window position p is wdsq[p]
+              int orf_cnt = 0, k_min = M, k_max = 0;
+              float tot_orfsc = kNegInfF;
+              double P_min = std::numeric_limits<double>::infinity();
+              size_t last_h = 0;
+              const size_t hw_n = S.hwc(b);
+              for (int gi = S.ob(b); gi < S.ob(b + 1); ++gi) {
+                if (S.P_orf[gi] > opt.F4) continue;
+                const Orf &o = S.orfs[gi];
+                const int i = o.local_idx;
+                if (!inside_of(o, dw)) continue;
+                P_min = std::min(P_min, S.P_orf[gi]);
+                tot_orfsc = flogsum(tot_orfsc, S.fwdsc_orf[gi]);
+                orf_cnt++;
+                size_t h = last_h;
+                if ((size_t) i < by_id.size()) {                 // first entry stamped i at or after last_h (the reference scans forward for it)
+                  const std::vector<int> &ix = by_id[i];
+                  auto it = std::lower_bound(ix.begin(), ix.end(), (int) h);
+                  h = (it == ix.end()) ? hw_n : std::min<size_t>(hw_n, (size_t) *it);
+                } else h = hw_n;
+                if (h < hw_n) {
+                  while (h < hw_n && hit_windows[h].id == i) {
+                    k_min = std::min(k_min, hit_windows[h].k - hit_windows[h].length + 1);
+                    k_max = std::max(k_max, hit_windows[h].k);
+                    h++;
+                  }
+                  last_h = h;
+                }
+              }
+              WinPre &r = pre[w];
+              r.orf_cnt = orf_cnt; r.P_min = P_min;
+              r.P_tot = exp_surv(tot_orfsc / kLog2, ev[EV_FTAU], ev[EV_FLAMBDA]);
+              lbg.set_filter(M, s->compo.data());
+              lbg.set_length(dw.length / 3);
+              r.nullsc = lbg.fs_null_one(dw.length / 3);
+              r.filtersc = r.nullsc;
+              if (opt.do_bias) {
+                r.filtersc = lbg.fs_filter_score(wdsq, dw.length, s->gcode);
+                if (k_min <= k_max) {
+                  local_compo(m, lbg, k_min, k_max, lcompo);
+                  lbg.set_filter(M, lcompo);
+                  lbg.set_length(dw.length / 3);
+                  const float lf = lbg.fs_filter_score(wdsq, dw.length, s->gcode);
+                  if (lf > r.filtersc) r.filtersc = lf;
+                }
+              }
             }
-            last_h = h;
+          });
+          for (int w = 0; w < nw; ++w) {
+            const int b = S.dwin_blk[w];
+            const int wl = w - S.db(b);                         // the window's index in its block's list: what orfsq->idx holds
+            const DnaWin &dw = S.dwin[w];
+            const WinPre &r = pre[w];
+            for (int gi = S.ob(b); gi < S.ob(b + 1); ++gi)
+              if (S.P_orf[gi] <= opt.F4 && inside_of(S.orfs[gi], dw)) S.orfs[gi].window_idx = wl;
+            const float fwdsc = S.fs_fwd[w];                      // on eslERANGE the score is -inf or NaN and the tests below fail, as in the reference
+            const float seqscore = (fwdsc - r.filtersc) / kLog2;
+            const double P_fs   = exp_surv(seqscore, ev[EV_FTAUFS3], ev[EV_FLAMBDA]);
+            const double P_null = exp_surv((fwdsc - r.nullsc) / kLog2, ev[EV_FTAUFS3], ev[EV_FLAMBDA]);
+            if (S.fs_st[w] == 0 && P_fs <= opt.F3 && (P_null < r.P_tot || (P_null == r.P_tot && r.orf_cnt > 1) || r.P_min > opt.F3)) {
+              S.st.pos_past_fwd += dw.length;
+              S.fsw.push_back(w);
+            } else {                                              // standard-translation branch (:1480-1511)
+              S.st.n_std_windows++;
+              for (int gi = S.ob(b); gi < S.ob(b + 1); ++gi) {
+                if (S.orfs[gi].window_idx != wl || S.P_orf[gi] > opt.F3 || S.aligned[gi]) continue;
+                S.st.pos_past_fwd += (int64_t) S.orfs[gi].n * 3;
+                S.aligned[gi] = 1;
+                S.stdq.push_back(Unit::StdItem{ gi, w });
+              }
+            }
           }
         }
-        WinPre &r = pre[w];
-        r.orf_cnt = orf_cnt; r.P_min = P_min;
-        r.P_tot = exp_surv(tot_orfsc / kLog2, ev[EV_FTAU], ev[EV_FLAMBDA]);
-        lbg.set_filter(M, s->compo.data());
-        lbg.set_length(dw.length / 3);
-        r.nullsc = lbg.fs_null_one(dw.length / 3);
-        r.filtersc = r.nullsc;
-        if (opt.do_bias) {
-          r.filtersc = lbg.fs_filter_score(wdsq, dw.length, s->gcode);
-          if (k_min <= k_max) {
-            local_compo(m, lbg, k_min, k_max, lcompo);
-            lbg.set_filter(M, lcompo);
-            lbg.set_length(dw.length / 3);
-            const float lf = lbg.fs_filter_score(wdsq, dw.length, s->gcode);
-            if (lf > r.filtersc) r.filtersc = lf;
-          }
-        }
-      }
-    });
-    for (int w = 0; w < nw; ++w) {
-      const int b = S.dwin_blk[w];
-      const DnaWin &dw = S.dwin[w];
-      const WinPre &r = pre[w];
-      for (int gi = S.orf_begin[b]; gi < S.orf_begin[b + 1]; ++gi)
-        if (S.P_orf[gi] <= opt.F4 && inside_of(S.orfs[gi], dw)) S.orfs[gi].window_idx = w;
-      const float fwdsc = S.fs_fwd[w];                      // on eslERANGE the score is -inf or NaN and the tests below fail, as in the reference
-      const float seqscore = (fwdsc - r.filtersc) / kLog2;
-      const double P_fs   = exp_surv(seqscore, ev[EV_FTAUFS3], ev[EV_FLAMBDA]);
-      const double P_null = exp_surv((fwdsc - r.nullsc) / kLog2, ev[EV_FTAUFS3], ev[EV_FLAMBDA]);
-      if (S.fs_st[w] == 0 && P_fs <= opt.F3 && (P_null < r.P_tot || (P_null == r.P_tot && r.orf_cnt > 1) || r.P_min > opt.F3)) {
-        s->st.pos_past_fwd += dw.length;
-        S.fsw.push_back(w);
-      } else {                                              // standard-translation branch (:1480-1511)
-        s->st.n_std_windows++;
-        for (int gi = S.orf_begin[b]; gi < S.orf_begin[b + 1]; ++gi) {
-          if (S.orfs[gi].window_idx != w || S.P_orf[gi] > opt.F3 || S.aligned[gi]) continue;
-          s->st.pos_past_fwd += (int64_t) S.orfs[gi].n * 3;
-          S.aligned[gi] = 1;
-          S.stdq.push_back(Strand::StdItem{ gi, w });
-        }
-      }
-    }
-  }
-  tm.lap(s->st.us_bias);
+        tmu.lap(S.st.us_bias);
 
-  // ---- stage 5: Forward (X rows kept) + Backward parsers over the frameshift-branch windows, one call per strand (:1469-1470)
-  for (int sidx : active) {
-    Strand &S = strands[sidx];
-    if (S.fsw.empty()) continue;
-    std::vector<bathgpu_window> gf(S.fsw.size());
-    S.xoff.assign(S.fsw.size() + 1, 0);
-    for (size_t z = 0; z < S.fsw.size(); ++z) { gf[z] = S.gw[S.fsw[z]]; S.xoff[z + 1] = S.xoff[z] + (size_t) gf[z].L + 1; }
-    S.fxr = s->xbuf[sidx][0].get(s->be, S.xoff.back() * 6); S.bxr = s->xbuf[sidx][1].get(s->be, S.xoff.back() * 6); S.st2.resize(S.fsw.size());
-    if (!S.fxr || !S.bxr) return fail(s, BATHHOST_EMEM, "host allocation failed");
-    std::vector<float> f2(S.fsw.size()), b2(S.fsw.size());
-    BE_TRY(s, s->be.select_slot(s->be.ctx, sidx), "bathgpu_select_slot");
-    BE_TRY(s, s->be.fs_fwd_bck_xrows(s->be.ctx, gf.data(), (int) gf.size(), xfE3, S.fxr, S.bxr, f2.data(), b2.data(), S.st2.data()),
-           "bathgpu_fs_fwd_bck_xrows");
-  }
-  tm.lap(s->st.us_xrows);
+        // Forward (X rows kept) + Backward parsers over the frameshift-branch windows
+        if (S.fsw.empty()) continue;
+        std::vector<bathgpu_window> gf(S.fsw.size());
+        S.xoff.assign(S.fsw.size() + 1, 0);
+        for (size_t z = 0; z < S.fsw.size(); ++z) { gf[z] = S.gw[S.fsw[z]]; S.xoff[z + 1] = S.xoff[z] + (size_t) gf[z].L + 1; }
+        S.fxr = S.xbuf[0].get(BE, S.xoff.back() * 6); S.bxr = S.xbuf[1].get(BE, S.xoff.back() * 6); S.st2.resize(S.fsw.size());
+        if (!S.fxr || !S.bxr) return fail(s, BATHHOST_EMEM, "host allocation failed");
+        std::vector<float> f2(S.fsw.size()), b2(S.fsw.size());
+        BE_TRY(s, BE.fs_fwd_bck_xrows(BE.ctx, gf.data(), (int) gf.size(), xfE3, S.fxr, S.bxr, f2.data(), b2.data(), S.st2.data()),
+               "bathgpu_fs_fwd_bck_xrows");
+        tmu.lap(S.st.us_xrows);
+
+        // The transcendental part of p7_DomainDecoding_Frameshift does not depend on the length model the walk below chains from
+        // window to window: it is precomputed for all windows on all host cores (cumulative log scales, Z, the btot/etot sums,
+        // the nine forward x backward products and their scale factors per row)
+        std::vector<Decoded> &DV = dec[(size_t) (2 * c + sidx)];
+        DV.resize(S.fsw.size());
+        parallel_chunks(S.fsw.size(), 1, [&](size_t za, size_t zb) {
+          for (size_t z = za; z < zb; ++z) {
+            if (S.st2[z] != 0) continue;
+            const int Lw = S.dwin[S.fsw[z]].length;
+            const float *xf = S.fxr + S.xoff[z] * 6, *xb = S.bxr + S.xoff[z] * 6;
+            Decoded &D = DV[z];
+            D.btot.assign((size_t) Lw + 1, 0.f); D.etot.assign((size_t) Lw + 1, 0.f);
+            D.fb.assign(((size_t) Lw + 1) * 9, 0.f); D.ex.assign(((size_t) Lw + 1) * 9, 0.f);
+            std::vector<float> lsf((size_t) Lw + 2), lsb((size_t) Lw + 2);
+            lsf[0] = logf(xf[5]);
+            for (int i = 1; i <= Lw; ++i) lsf[i] = lsf[i - 1] + logf(xf[(size_t) i * 6 + 5]);
+            lsb[Lw + 1] = 0.0f;
+            for (int i = Lw; i >= 0; --i) lsb[i] = lsb[i + 1] + logf(xb[(size_t) i * 6 + 5]);
+            const float liz = -flogsum(logf(xb[0 * 6 + 1]) + lsb[0], flogsum(logf(xb[1 * 6 + 1]) + lsb[1], logf(xb[2 * 6 + 1]) + lsb[2]));
+            auto F = [&](int i, int cc) { return xf[(size_t) i * 6 + cc]; };
+            auto B = [&](int i, int cc) { return xb[(size_t) i * 6 + cc]; };
+            static const int cells[3] = { 1, 2, 4 };          // N, J, C
+            for (int i = 3; i <= Lw; ++i) {
+              D.btot[i] = D.btot[i - 3] + F(i - 3, 3) * B(i - 3, 3) * expf(lsf[i - 3] + lsb[i - 3] + liz);
+              D.etot[i] = D.etot[i - 3] + F(i, 0) * B(i, 0) * expf(lsf[i] + lsb[i] + liz);
+              const float e0 = expf(lsf[i - 3] + lsb[i] + liz);
+              const float e1 = (i < Lw)     ? expf(lsf[i - 2] + lsb[i + 1] + liz) : 0.f;
+              const float e2 = (i < Lw - 1) ? expf(lsf[i - 1] + lsb[i + 2] + liz) : 0.f;
+              for (int cc = 0; cc < 3; ++cc) {
+                float *fb = &D.fb[(size_t) i * 9 + 3 * cc], *ex = &D.ex[(size_t) i * 9 + 3 * cc];
+                fb[0] = F(i - 3, cells[cc]) * B(i, cells[cc]); ex[0] = e0;
+                if (i < Lw)     { fb[1] = F(i - 2, cells[cc]) * B(i + 1, cells[cc]); ex[1] = e1; }
+                if (i < Lw - 1) { fb[2] = F(i - 1, cells[cc]) * B(i + 2, cells[cc]); ex[2] = e2; }
+              }
+            }
+          }
+        });
+        tmu.lap(S.st.us_decode);
+      }
+    return 0;
+  });
+  if (rc != 0) return rc;
+  tm = StageTimer();
 
   // ---- domain decoding and region finding on the host, in the reference's order (block, then strand, then window):
   // the length model of om_fs5 that p7_DomainDecoding_Frameshift reads is whatever the previous window's rescoring left
-  // (src/p7_domaindef.c:320-325, :1018)
-  // The transcendental part of p7_DomainDecoding_Frameshift does not depend on that length model: it is precomputed for
-  // all windows on all host cores (cumulative log scales, Z, the btot/etot sums, the nine forward x backward products and
-  // their scale factors per row); the sequential walk below only applies the loop odds, in the reference's operation order.
-  struct Decoded { std::vector<float> btot, etot, fb, ex; };   // fb, ex: [L+1][9]
-  std::vector<Decoded> dec[2];
-  for (int sidx : active) {
-    Strand &S = strands[sidx];
-    dec[sidx].resize(S.fsw.size());
-    parallel_chunks(S.fsw.size(), 1, [&](size_t za, size_t zb) {
-      for (size_t z = za; z < zb; ++z) {
-        if (S.st2[z] != 0) continue;
-        const int Lw = S.dwin[S.fsw[z]].length;
-        const float *xf = S.fxr + S.xoff[z] * 6, *xb = S.bxr + S.xoff[z] * 6;
-        Decoded &D = dec[sidx][z];
-        D.btot.assign((size_t) Lw + 1, 0.f); D.etot.assign((size_t) Lw + 1, 0.f);
-        D.fb.assign(((size_t) Lw + 1) * 9, 0.f); D.ex.assign(((size_t) Lw + 1) * 9, 0.f);
-        std::vector<float> lsf((size_t) Lw + 2), lsb((size_t) Lw + 2);
-        lsf[0] = logf(xf[5]);
-        for (int i = 1; i <= Lw; ++i) lsf[i] = lsf[i - 1] + logf(xf[(size_t) i * 6 + 5]);
-        lsb[Lw + 1] = 0.0f;
-        for (int i = Lw; i >= 0; --i) lsb[i] = lsb[i + 1] + logf(xb[(size_t) i * 6 + 5]);
-        const float liz = -flogsum(logf(xb[0 * 6 + 1]) + lsb[0], flogsum(logf(xb[1 * 6 + 1]) + lsb[1], logf(xb[2 * 6 + 1]) + lsb[2]));
-        auto F = [&](int i, int c) { return xf[(size_t) i * 6 + c]; };
-        auto B = [&](int i, int c) { return xb[(size_t) i * 6 + c]; };
-        static const int cells[3] = { 1, 2, 4 };          // N, J, C
-        for (int i = 3; i <= Lw; ++i) {
-          D.btot[i] = D.btot[i - 3] + F(i - 3, 3) * B(i - 3, 3) * expf(lsf[i - 3] + lsb[i - 3] + liz);
-          D.etot[i] = D.etot[i - 3] + F(i, 0) * B(i, 0) * expf(lsf[i] + lsb[i] + liz);
-          const float e0 = expf(lsf[i - 3] + lsb[i] + liz);
-          const float e1 = (i < Lw)     ? expf(lsf[i - 2] + lsb[i + 1] + liz) : 0.f;
-          const float e2 = (i < Lw - 1) ? expf(lsf[i - 1] + lsb[i + 2] + liz) : 0.f;
-          for (int c = 0; c < 3; ++c) {
-            float *fb = &D.fb[(size_t) i * 9 + 3 * c], *ex = &D.ex[(size_t) i * 9 + 3 * c];
-            fb[0] = F(i - 3, cells[c]) * B(i, cells[c]); ex[0] = e0;
-            if (i < Lw)     { fb[1] = F(i - 2, cells[c]) * B(i + 1, cells[c]); ex[1] = e1; }
-            if (i < Lw - 1) { fb[2] = F(i - 1, cells[c]) * B(i + 2, cells[c]); ex[2] = e2; }
-          }
-        }
-      }
-    });
-  }
-  tm.lap(s->st.us_decode);
+  // (src/p7_domaindef.c:320-325, :1018); the walk below only applies its loop odds to the precomputed products, in the
+  // reference's operation order.
   const float rt1 = 0.25f, rt2 = 0.10f, rt3 = 0.20f;
   const uint32_t kStotraceSeed = 42; const int kStotraceSamples = 200;   // --seed default (src/bathsearch.c:131), ddef->nsamples (src/p7_domaindef.c:83)
   const int saveL = 100;                                    // gm_fs5->L: the dummy length bathsearch configures and never changes (src/bathsearch.c:797)
@@ -1110,7 +1325,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
   // unresolved multi-domain region taken as one envelope, the Forward matrices of those regions are then filled on the device in
   // one batch and sampled and clustered here on all cores, and the walk is repeated with the clusters in place -- until it meets
   // no unresolved region (two passes unless a changed length model moves a later region's borders).
-  struct RegionKey { int sidx, w, i, j; bool operator<(const RegionKey &o) const { return std::tie(sidx, w, i, j) < std::tie(o.sidx, o.w, o.i, o.j); } };
+  struct RegionKey { int u, w, i, j; bool operator<(const RegionKey &o) const { return std::tie(u, w, i, j) < std::tie(o.u, o.w, o.i, o.j); } };   // u: unit
   std::map<RegionKey, std::vector<std::pair<int, int>>> resolved;
   const float walk_nj0 = s->om5_nj; const int walk_L0 = s->om5_L;
   const int64_t walk_regions0 = s->st.n_regions, walk_multi0 = s->st.n_multidomain_regions;
@@ -1121,22 +1336,23 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
   // predecessor really leaves, which is the sequential result.  Region borders hardly ever move with the loop odds, so this
   // settles in two or three rounds.
   struct WalkMemo { bool valid = false; float nj_in = 0, nj_out = 0; int L_in = 0, L_out = 0, nreg = 0, nmulti = 0;
-                    std::vector<bathgpu_envelope> ge; std::vector<Strand::Env> envs; std::vector<RegionKey> pend; };
-  std::vector<WalkMemo> memo[2];
-  for (int sidx : active) memo[sidx].resize(strands[sidx].fsw.size());
-  struct WalkItem { int sidx; size_t z; };
+                    std::vector<bathgpu_envelope> ge; std::vector<Unit::Env> envs; std::vector<RegionKey> pend; };
+  std::vector<std::vector<WalkMemo>> memo(units.size());
+  for (size_t u = 0; u < units.size(); ++u) memo[u].resize(units[u]->fsw.size());
+  struct WalkItem { int u; size_t z; };
   std::vector<WalkItem> worder;                               // the reference's order: block, then strand, then window
   {
-    size_t zpos[2] = { 0, 0 };
+    std::vector<size_t> zpos(units.size(), 0);
     for (size_t b = 0; b < nb; ++b)
       for (int sidx : active) {
-        Strand &S = strands[sidx];
-        for (; zpos[sidx] < S.fsw.size() && S.dwin_blk[S.fsw[zpos[sidx]]] == (int) b; ++zpos[sidx])
-          if (S.st2[zpos[sidx]] == 0) worder.push_back(WalkItem{ sidx, zpos[sidx] });   // backward underflow: no domain definition (:1471)
+        const int u = 2 * chunk_of_block[b] + sidx;
+        Unit &S = *units[(size_t) u];
+        for (; zpos[u] < S.fsw.size() && S.dwin_blk[S.fsw[zpos[u]]] == (int) b; ++zpos[u])
+          if (S.st2[zpos[u]] == 0) worder.push_back(WalkItem{ u, zpos[u] });   // backward underflow: no domain definition (:1471)
       }
   }
-  auto walk_window = [&](int sidx, size_t z, float nj_in, int L_in, WalkMemo &wm) {
-    Strand &S = strands[sidx];
+  auto walk_window = [&](int sidx, size_t z, float nj_in, int L_in, WalkMemo &wm) {      // sidx: the unit
+    Unit &S = *units[(size_t) sidx];
     wm.valid = true; wm.nj_in = nj_in; wm.L_in = L_in; wm.nreg = 0; wm.nmulti = 0;
     wm.ge.clear(); wm.envs.clear(); wm.pend.clear();
     float om5_nj = nj_in; int om5_L = L_in;
@@ -1144,7 +1360,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
           const int Lw = S.dwin[w].length;
           const float tL = 1.0f - (2.0f + om5_nj) / ((float) om5_L + 2.0f + om5_nj);
           // mocc[i] = 1 - sum over N,J,C and the three codon offsets of fwd * bck * loop odds * scale (decoding_fs.c:309-352)
-          const Decoded &D = dec[sidx][z];
+          const Decoded &D = dec[(size_t) sidx][z];
           const std::vector<float> &btot = D.btot, &etot = D.etot;
           std::vector<float> mocc((size_t) Lw + 1, 0.f);
           for (int i = 3; i <= Lw; ++i) {
@@ -1196,7 +1412,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
                   bathgpu_envelope g;
                   g.start = S.gw[w].start + i2 - 1; g.L = Ld;
                   bathhost_length_model(Ld / 3, 0.0f, &g.pmove, &g.ploop);
-                  wm.ge.push_back(g); wm.envs.push_back(Strand::Env{ w, i2, j2 });
+                  wm.ge.push_back(g); wm.envs.push_back(Unit::Env{ w, i2, j2 });
                   om5_nj = 0.0f; om5_L = Ld / 3;             // p7_fs_oprofile_ReconfigLength(om_fs5, Ld/3) (:1018)
                 };
                 const std::vector<std::pair<int, int>> *clusters = nullptr;
@@ -1222,7 +1438,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
       std::vector<size_t> todo;
       float nj = walk_nj0; int L = walk_L0;
       for (size_t t = 0; t < worder.size(); ++t) {
-        WalkMemo &wm = memo[worder[t].sidx][worder[t].z];
+        WalkMemo &wm = memo[(size_t) worder[t].u][worder[t].z];
         if (!wm.valid || wm.nj_in != nj || wm.L_in != L) { todo.push_back(t); wm.nj_in = nj; wm.L_in = L; }
         if (wm.valid) { nj = wm.nj_out; L = wm.L_out; } else { nj = 0.0f; L = saveL / 3; }   // first round: a guess for the successor
       }
@@ -1232,38 +1448,40 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
       parallel_chunks(todo.size(), 4, [&](size_t ta, size_t tb) {
         for (size_t q = ta; q < tb; ++q) {
           const WalkItem &it = worder[todo[q]];
-          WalkMemo &wm = memo[it.sidx][it.z];
-          walk_window(it.sidx, it.z, wm.nj_in, wm.L_in, wm);
+          WalkMemo &wm = memo[(size_t) it.u][it.z];
+          walk_window(it.u, it.z, wm.nj_in, wm.L_in, wm);
         }
       });
     }
     std::vector<RegionKey> pending;
-    for (const WalkItem &it : worder) { const WalkMemo &wm = memo[it.sidx][it.z]; pending.insert(pending.end(), wm.pend.begin(), wm.pend.end()); }
-    for (const WalkItem &it : worder) { WalkMemo &wm = memo[it.sidx][it.z]; if (!wm.pend.empty()) wm.valid = false; }   // walked again once resolved
+    for (const WalkItem &it : worder) { const WalkMemo &wm = memo[(size_t) it.u][it.z]; pending.insert(pending.end(), wm.pend.begin(), wm.pend.end()); }
+    for (const WalkItem &it : worder) { WalkMemo &wm = memo[(size_t) it.u][it.z]; if (!wm.pend.empty()) wm.valid = false; }   // walked again once resolved
     if (pending.empty()) break;
     if (walk_pass > 64) return fail(s, BATHHOST_EINVAL, "multi-domain region resolution does not settle");
     // ---- Forward matrices of the unresolved regions (multihit, target length saveL: :409-412), one device call per strand
     const float xfE5m[2] = { 0.5f, 0.5f };
     float mh_pmove, mh_ploop;
     bathhost_length_model(saveL, 1.0f, &mh_pmove, &mh_ploop);
-    for (int sidx : active) {
-      Strand &S = strands[sidx];
+    for (size_t sidx = 0; sidx < units.size(); ++sidx) {                 // sidx: the unit (regions of this kind are rare: one device call per unit that has any)
+      if (!units[sidx]) continue;
+      Unit &S = *units[sidx];
+      const bathhost_backend &BE = s->bes[(size_t) S.be];
       std::vector<bathgpu_envelope> regs;
       std::vector<RegionKey> keys;
       std::vector<int64_t> off(1, 0);
-      for (const RegionKey &k : pending) if (k.sidx == sidx) {
+      for (const RegionKey &k : pending) if (k.u == (int) sidx) {
         bathgpu_envelope g;
         g.start = S.gw[k.w].start + k.i - 1; g.L = k.j - k.i + 1; g.pmove = mh_pmove; g.ploop = mh_ploop;
         regs.push_back(g); keys.push_back(k); off.push_back(off.back() + g.L + 1);
       }
       if (regs.empty()) continue;
-      float *mxbuf = s->mxbuf[0].get(s->be, (size_t) off.back() * (M + 1) * 8), *xrbuf = s->mxbuf[1].get(s->be, (size_t) off.back() * 6);
+      float *mxbuf = s->mxbuf[0].get(BE, (size_t) off.back() * (M + 1) * 8), *xrbuf = s->mxbuf[1].get(BE, (size_t) off.back() * 6);
       if (!mxbuf || !xrbuf) return fail(s, BATHHOST_EMEM, "host allocation failed");
       std::vector<float> fsc(regs.size());
       std::vector<int32_t> fst(regs.size());
-      BE_TRY(s, s->be.select_slot(s->be.ctx, sidx), "bathgpu_select_slot");
-      if (!s->be.fs_forward_matrices) return fail(s, BATHHOST_EINVAL, "the device library has no bathgpu_fs_forward_matrices");
-      BE_TRY(s, s->be.fs_forward_matrices(s->be.ctx, regs.data(), (int) regs.size(), xfE5m, mxbuf, xrbuf, off.back(), fsc.data(), fst.data()),
+      BE_TRY(s, BE.select_slot(BE.ctx, S.slot), "bathgpu_select_slot");
+      if (!BE.fs_forward_matrices) return fail(s, BATHHOST_EINVAL, "the device library has no bathgpu_fs_forward_matrices");
+      BE_TRY(s, BE.fs_forward_matrices(BE.ctx, regs.data(), (int) regs.size(), xfE5m, mxbuf, xrbuf, off.back(), fsc.data(), fst.data()),
              "bathgpu_fs_forward_matrices");
       std::vector<std::vector<std::pair<int, int>>> found(regs.size());
       const SpecialOdds X{ mh_pmove, mh_ploop, xfE5m[0], xfE5m[1] };
@@ -1280,54 +1498,49 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
     }
   }
   s->st.n_regions = walk_regions0; s->st.n_multidomain_regions = walk_multi0;
-  for (int sidx : active) { strands[sidx].ge.clear(); strands[sidx].envs.clear(); }
+  for (auto &U : units) { U->ge.clear(); U->envs.clear(); }
   for (const WalkItem &it : worder) {
-    const WalkMemo &wm = memo[it.sidx][it.z];
-    Strand &S = strands[it.sidx];
+    const WalkMemo &wm = memo[(size_t) it.u][it.z];
+    Unit &S = *units[(size_t) it.u];
     S.ge.insert(S.ge.end(), wm.ge.begin(), wm.ge.end()); S.envs.insert(S.envs.end(), wm.envs.begin(), wm.envs.end());
     s->st.n_regions += wm.nreg; s->st.n_multidomain_regions += wm.nmulti;
     s->om5_nj = wm.nj_out; s->om5_L = wm.L_out;
   }
   tm.lap(s->st.us_windows);
 
-  // ---- stage 6: every envelope of a strand rescored in one batched call (rescore_isolated_domain_frameshift, :993-1191)
+  // ---- stage 6 and everything after it, per unit, device contexts side by side: every envelope of the unit rescored in one
+  // batched call (rescore_isolated_domain_frameshift, :993-1191), scoring and hit records, then the standard-translation branch
   const float xfE5[2] = { 1.0f, 0.0f };
-  for (int sidx : active) {
-    Strand &S = strands[sidx];
-    if (S.ge.empty()) continue;
+  auto finish_unit = [&](Unit &S) -> int {
+    const bathhost_backend &BE = s->bes[(size_t) S.be];
+    const int sidx = S.sidx;
+    StageTimer tm;
+  if (!S.ge.empty()) {
     S.res.resize(S.ge.size());
     int64_t max_steps = 0; for (auto &g : S.ge) max_steps += g.L + M + 8;
     S.traces.resize((size_t) max_steps);
-    BE_TRY(s, s->be.select_slot(s->be.ctx, sidx), "bathgpu_select_slot");
-    BE_TRY(s, s->be.fs_domains(s->be.ctx, S.ge.data(), (int) S.ge.size(), xfE5, S.res.data(), S.traces.data(), max_steps), "bathgpu_fs_domains");
-    s->st.n_envelopes += (int64_t) S.ge.size();
+    BE_TRY(s, BE.select_slot(BE.ctx, S.slot), "bathgpu_select_slot");
+    BE_TRY(s, BE.fs_domains(BE.ctx, S.ge.data(), (int) S.ge.size(), xfE5, S.res.data(), S.traces.data(), max_steps), "bathgpu_fs_domains");
+    S.st.n_envelopes += (int64_t) S.ge.size();
   }
-
-  tm.lap(s->st.us_fs_domains);
+  tm.lap(S.st.us_fs_domains);
   // ---- scoring and hit records: envelopes are independent of one another (the early E-value cut uses the residue count fixed
-  // for their block), so they are scored on all host cores and the hits appended in the reference's order
+  // for their block), so they are scored on all host cores and the hits kept in the reference's order
   {
-    struct Item { int sidx; size_t e; size_t b; };
+    struct Item { size_t e; size_t b; };
     std::vector<Item> order;
-    {
-      size_t epos[2] = { 0, 0 };
-      for (size_t b = 0; b < nb; ++b)
-        for (int sidx : active) {
-          Strand &S = strands[sidx];
-          for (; epos[sidx] < S.envs.size() && S.dwin_blk[S.envs[epos[sidx]].win] == (int) b; ++epos[sidx]) order.push_back(Item{ sidx, epos[sidx], b });
-        }
-    }
+    for (size_t e = 0; e < S.envs.size(); ++e) order.push_back(Item{ e, (size_t) S.dwin_blk[S.envs[e].win] });
     auto score_env = [&](const Item &it, Background &lbg, std::vector<uint8_t> &wbuf, Hit &h) -> bool {
-      const int sidx = it.sidx; const size_t e = it.e, b = it.b;
-      Strand &S = strands[sidx];
+      const size_t e = it.e, b = it.b;
       const std::vector<bathgpu_domain_result> &res = S.res;
       const std::vector<bathgpu_trace_step> &traces = S.traces;
           const BlockInfo &binfo = blocks[b];
           const DnaWin &dw = S.dwin[S.envs[e].win];
-          const uint8_t *wdsq = S.oriented(S.goff(binfo, n) + dw.n - 1, dw.length, wbuf);
+          const SeqRef &sq = seqs[(size_t) binfo.seq];
+          const uint8_t *wdsq = oriented(sq, binfo, S.complement, dw.n - 1, dw.length, wbuf);
           const int Lw = dw.length;
           const long long nres_now = binfo.nres_at[sidx];
-          struct { bool complement; long long start; const char *name; long long sq_len; } blk = { S.complement, S.start_of(binfo), name, (long long) n };
+          struct { bool complement; long long start; const char *name; long long sq_len; } blk = { S.complement, S.start_of(binfo), sq.name.c_str(), (long long) sq.n };
           const int i = S.envs[e].i, j = S.envs[e].j, Ld = S.ge[e].L;
         const bathgpu_domain_result &r = res[e];
         if (r.status != 0 && r.trace_len == 0) return false;   // Forward/Backward range error: envelope dropped (:1022,1041)
@@ -1428,7 +1641,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
         auto orig = [&](int wpos) -> long long {            // window position -> coordinate on the source sequence
           return blk.complement ? blk.start - (dw.n + wpos) + 2 : blk.start + dw.n + wpos - 2;
         };
-        h.pub.seqidx = s->nseqs;
+        h.pub.seqidx = sq.seqidx;
         snprintf(h.pub.name, sizeof h.pub.name, "%s", blk.name ? blk.name : "");
         h.pub.strand = blk.complement ? -1 : 1;
         h.pub.env_from = orig(dom.ienv); h.pub.env_to = orig(dom.jenv);
@@ -1451,15 +1664,14 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
       std::vector<uint8_t> wbuf;
       for (size_t z = za; z < zb; ++z) ok[z] = score_env(order[z], lbg, wbuf, out[z]) ? 1 : 0;
     });
-    for (size_t z = 0; z < order.size(); ++z) if (ok[z]) s->hits.push_back(std::move(out[z]));
+    for (size_t z = 0; z < order.size(); ++z) if (ok[z]) S.hits_fs.emplace_back((int) order[z].b, std::move(out[z]));
   }
-  tm.lap(s->st.us_score);
+  tm.lap(S.st.us_score);
 
   // ---- the standard-translation branch: ORFs whose DNA window lost the arbitration, or every ORF past F3 without --fs
   // (src/p7_pipeline.c:1480-1511, :1720-1771): BackwardParser + DomainDecoding + regions per ORF, then each envelope rescored
-  for (int sidx : active) {
-    Strand &S = strands[sidx];
-    if (S.stdq.empty()) continue;
+  if (!S.stdq.empty()) {
+    Background ubg = bg;                                     // the null model's length is set per hit: a private copy per unit
     const size_t nq = S.stdq.size();
     const float xfEm[2] = { expf(q.xsc_E_move), expf(q.xsc_E_loop) };
     std::vector<bathgpu_orf> od(nq);
@@ -1472,8 +1684,8 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
     }
     std::vector<float> fx(xo[nq] * 6), bx(xo[nq] * 6), fsc(nq), bsc(nq);
     std::vector<int32_t> pst(nq);
-    BE_TRY(s, s->be.select_slot(s->be.ctx, sidx), "bathgpu_select_slot");
-    BE_TRY(s, s->be.orf_fwd_bck_xrows(s->be.ctx, od.data(), (int) nq, q.nj, xfEm, fx.data(), bx.data(), fsc.data(), bsc.data(), pst.data()),
+    BE_TRY(s, BE.select_slot(BE.ctx, S.slot), "bathgpu_select_slot");
+    BE_TRY(s, BE.orf_fwd_bck_xrows(BE.ctx, od.data(), (int) nq, q.nj, xfEm, fx.data(), bx.data(), fsc.data(), bsc.data(), pst.data()),
            "bathgpu_orf_fwd_bck_xrows");
 
     // p7_DomainDecoding (src/impl_sse/decoding.c:160-196) and the region logic of p7_domaindef_ByPosteriorHeuristics_BATH
@@ -1527,7 +1739,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
     std::vector<bathgpu_envelope> ge;
     int64_t max_steps = 0;
     for (size_t z = 0; z < nq; ++z) {
-      s->st.n_regions += nreg[z]; s->st.n_multidomain_regions += nmulti[z];
+      S.st.n_regions += nreg[z]; S.st.n_multidomain_regions += nmulti[z];
       for (const SEnv &e : env_of[z]) {
         const int Ld = e.j - e.i + 1;
         bathgpu_envelope g;
@@ -1537,24 +1749,30 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
         max_steps += Ld + M + 8;
       }
     }
-    if (ge.empty()) continue;
+    if (!ge.empty()) {
     std::vector<bathgpu_domain_result> res(ge.size());
     std::vector<bathgpu_trace_step> traces((size_t) max_steps);
     const float xfEu[2] = { 1.0f, 0.0f };
-    BE_TRY(s, s->be.orf_domains(s->be.ctx, ge.data(), (int) ge.size(), xfEu, res.data(), traces.data(), max_steps), "bathgpu_orf_domains");
-    s->st.n_envelopes += (int64_t) ge.size();
+    BE_TRY(s, BE.orf_domains(BE.ctx, ge.data(), (int) ge.size(), xfEu, res.data(), traces.data(), max_steps), "bathgpu_orf_domains");
+    S.st.n_envelopes += (int64_t) ge.size();
 
     std::vector<uint8_t> wbuf;
     for (size_t e = 0; e < envs.size(); ++e) {
       const bathgpu_domain_result &r = res[e];
       if (r.status != 0 || r.trace_len == 0) continue;       // eslFAIL (:1252)
-      const Strand::StdItem &it = S.stdq[envs[e].z];
+      const Unit::StdItem &it = S.stdq[envs[e].z];
       const Orf &o = S.orfs[it.gi];
       const int b = S.orf_blk[it.gi];
       const BlockInfo &binfo = blocks[b];
       // windowsq: the DNA window (--fs) or the ORF's own nucleotides (default pipeline); block-local start
+      // (an ORF sent here on a stale orfsq->idx need not lie inside that window: the stretch covers both)
+      const SeqRef &sq = seqs[(size_t) binfo.seq];
+      const long long n = sq.n;
+      const char *name = sq.name.c_str();
       const long long win_n = (it.w >= 0) ? S.dwin[it.w].n : o.start;
-      const uint8_t *wdsq = S.oriented(S.goff(binfo, n) + win_n - 1, (it.w >= 0) ? S.dwin[it.w].length : (o.end - o.start + 1), wbuf);
+      const long long win_e = (it.w >= 0) ? win_n + S.dwin[it.w].length - 1 : o.end;
+      const long long lo0 = std::min<long long>(win_n, o.start) - 1, hi0 = std::max<long long>(win_e, o.end);
+      const uint8_t *wdsq = oriented(sq, binfo, S.complement, lo0, (int) (hi0 - lo0), wbuf) + (lo0 - (win_n - 1));    // wdsq[p] = block position win_n - 1 + p
       const uint8_t *res_o = S.residues.data() + o.offset - 1;           // ORF residue p is res_o[p]
       const int i = envs[e].i, j = envs[e].j;
       Domain dom;
@@ -1601,9 +1819,9 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
       bitscore += 2 * log(2. / (ml + 2));
       bitscore -= (env_len - ali_len) * log((float) env_len / (float) (env_len + 2));
       bitscore += (ml - ali_len) * log((float) ml / (float) (ml + 2));
-      const float dom_bias = opt.do_null2 ? flogsum(0.0, log(bg.omega) + dom.domcorrection) : 0.0f;
-      bg.set_length(ml);
-      const float nullsc = bg.null_one(ml);
+      const float dom_bias = opt.do_null2 ? flogsum(0.0, log(ubg.omega) + dom.domcorrection) : 0.0f;
+      ubg.set_length(ml);
+      const float nullsc = ubg.null_one(ml);
       const float dom_score = (bitscore - (nullsc + dom_bias)) / kLog2;
       const double dom_lnP = exp_logsurv(dom_score, ev[EV_FTAU], ev[EV_FLAMBDA]);
       const double Z = (float) binfo.nres_at[sidx] / (float) ml;
@@ -1613,7 +1831,7 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
       memset(&h.pub, 0, sizeof h.pub);
       const long long bstart = S.start_of(binfo);            // dnasq->start
       auto orig = [&](int wpos) -> long long { return S.complement ? bstart - (win_n + wpos) + 2 : bstart + win_n + wpos - 2; };
-      h.pub.seqidx = s->nseqs;
+      h.pub.seqidx = sq.seqidx;
       snprintf(h.pub.name, sizeof h.pub.name, "%s", name ? name : "");
       h.pub.strand = S.complement ? -1 : 1;
       if (!S.complement) { h.pub.env_from = bstart + o.start + dom.ienv * 3 - 4; h.pub.env_to = bstart + o.start + dom.jenv * 3 - 2; }
@@ -1666,11 +1884,33 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
         snprintf(h.pub.cigar, sizeof h.pub.cigar, "%s", cigar.c_str());
       }
       h.sortkey = -dom_lnP;
-      s->hits.push_back(std::move(h));
+      S.hits_std.emplace_back(b, std::move(h));
+    }
     }
   }
-  tm.lap(s->st.us_std);
-  s->nseqs++;
+  tm.lap(S.st.us_std);
+  return 0;
+  };   // finish_unit
+  rc = for_each_backend(s, [&](int be) -> int {
+    for (int c : chunks_of_be[(size_t) be])
+      for (int sidx : active) { const int st = finish_unit(unit_of((size_t) c, sidx)); if (st != 0) return st; }
+    return 0;
+  });
+  if (rc != 0) return rc;
+
+  // ---- hits in the reference's order: block by block, top strand then bottom strand; counters summed over units
+  {
+    std::vector<size_t> pf(units.size(), 0), ps(units.size(), 0);
+    for (size_t b = 0; b < nb; ++b)
+      for (int sidx : active) {
+        const size_t u = 2 * (size_t) chunk_of_block[b] + (size_t) sidx;
+        Unit &S = *units[u];
+        for (; pf[u] < S.hits_fs.size() && S.hits_fs[pf[u]].first == (int) b; ++pf[u]) s->hits.push_back(std::move(S.hits_fs[pf[u]].second));
+        for (; ps[u] < S.hits_std.size() && S.hits_std[ps[u]].first == (int) b; ++ps[u]) s->hits.push_back(std::move(S.hits_std[ps[u]].second));
+      }
+  }
+  for (auto &U : units) add_stats(s->st, U->st);
+  s->nseqs += (int64_t) seqs.size();
   s->st.nseqs = s->nseqs;
   return 0;
 }
@@ -1678,13 +1918,13 @@ int search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, in
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
-extern "C" int bathhost_search_create(const bathhost_model *m, const bathhost_backend *be, const bathhost_options *o, bathhost_search **ret)
+extern "C" int bathhost_search_create_multi(const bathhost_model *m, const bathhost_backend *be, int nbackends, const bathhost_options *o, bathhost_search **ret)
 {
-  if (!m || !be || !ret) return BATHHOST_EINVAL;
+  if (!m || !be || nbackends < 1 || nbackends > 256 || !ret) return BATHHOST_EINVAL;
   *ret = nullptr;
   if (!m->hmm.has_fs3 || !m->hmm.has_fs5 || !(m->hmm.fsprob > 0) || m->hmm.max_length < 1) return BATHHOST_EINVAL;   // src/bathsearch.c:747-759
   flogsum_init();
-  bathhost_search *s = new (std::nothrow) bathhost_search(m, *be);
+  bathhost_search *s = new (std::nothrow) bathhost_search(m, be, nbackends);
   if (!s) return BATHHOST_EMEM;
   if (o) {
     if (o->F1 > 0) s->opt.F1 = o->F1;
@@ -1700,34 +1940,67 @@ extern "C" int bathhost_search_create(const bathhost_model *m, const bathhost_ba
     s->opt.top = !o->bottom_only; s->opt.bottom = !o->top_only;
     s->opt.fs = !o->std_only;
     s->opt.frameline = o->show_frameline != 0;
+    if (o->chunk_nt > 0) s->chunk_nt = o->chunk_nt;
   }
   if (!genetic_code(m->ct, s->gcode)) { delete s; return BATHHOST_EINVAL; }
   s->compo.assign(m->hmm.compo, m->hmm.compo + kK);
   s->bg.set_filter(m->hmm.M, s->compo.data());           // p7_pli_NewModel -> p7_bg_SetFilter(bg, om->M, om->compo)
 
-  // device images: the three profiles of a query
+  // device images: the three profiles of a query, replicated on every device context
   const int M = m->hmm.M;
-  int st;
-  if ((st = be->load_fs_profile(be->ctx, 3, M, m->om3.nrows, m->om3.rfv.data(), m->om3.tfv.data())) != 0 ||
-      (st = be->load_fs_profile(be->ctx, 5, M, m->om5.nrows, m->om5.rfv.data(), m->om5.tfv.data())) != 0) { delete s; return st; }
   bathgpu_filter_params fp;
   const ProteinProfile &q = m->prot;
   fp.M = M; fp.tbm_b = q.tbm_b; fp.tec_b = q.tec_b; fp.base_b = q.base_b; fp.bias_b = q.bias_b; fp.scale_b = q.scale_b;
   fp.base_w = q.base_w; fp.ddbound_w = q.ddbound_w; fp.xw_E_move = q.xw_E_move; fp.xw_E_loop = q.xw_E_loop; fp.scale_w = q.scale_w;
   fp.cpu_lanes_u8 = s->opt.lanes_u8; fp.cpu_lanes_i16 = s->opt.lanes_i16;
-  if ((st = be->load_filter_profile(be->ctx, &fp, q.rbv.data(), q.rwv.data(), q.twv.data())) != 0) { delete s; return st; }
+  const int st = for_each_backend(s, [&](int k) -> int {
+    const bathhost_backend &BE = s->bes[(size_t) k];
+    int rc;
+    if ((rc = BE.load_fs_profile(BE.ctx, 3, M, m->om3.nrows, m->om3.rfv.data(), m->om3.tfv.data())) != 0 ||
+        (rc = BE.load_fs_profile(BE.ctx, 5, M, m->om5.nrows, m->om5.rfv.data(), m->om5.tfv.data())) != 0 ||
+        (rc = BE.load_filter_profile(BE.ctx, &fp, q.rbv.data(), q.rwv.data(), q.twv.data())) != 0) return rc;
+    return 0;
+  });
+  if (st != 0) { delete s; return st; }
   *ret = s;
   return BATHHOST_OK;
+}
+
+extern "C" int bathhost_search_create(const bathhost_model *m, const bathhost_backend *be, const bathhost_options *o, bathhost_search **ret)
+{
+  return bathhost_search_create_multi(m, be, 1, o, ret);
 }
 
 extern "C" void bathhost_search_destroy(bathhost_search *s) { delete s; }
 extern "C" const char *bathhost_search_last_error(const bathhost_search *s) { return s ? s->err.c_str() : "no search"; }
 
-// One target sequence: dsq[1..n] (sentinels at 0 and n+1), both strands unless restricted.
-extern "C" int bathhost_search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, int64_t n)
+// One more target sequence for the next bathhost_search_run: dsq[1..n] (sentinels at 0 and n+1), which the caller keeps alive
+// and unchanged until that call returns.  Sequences are numbered in the order they are queued.
+extern "C" int bathhost_search_queue(bathhost_search *s, const char *name, const uint8_t *dsq, int64_t n)
 {
   if (!s || !dsq || n < 1) return BATHHOST_EINVAL;
-  return search_sequence(s, name, dsq, n);
+  SeqRef r;
+  r.name = name ? name : ""; r.dsq = dsq; r.n = n; r.seqidx = s->nseqs + (int64_t) s->queue.size();
+  s->queue.push_back(std::move(r));
+  return BATHHOST_OK;
+}
+
+// Every queued sequence, both strands unless restricted, through the whole pipeline: one stage-batched pass over all of them,
+// dealt to the search's device contexts.  The state the reference carries from block to block (hit-window list, length model,
+// residue count) continues from the previous run, so queueing everything and running once, or running after every sequence, gives
+// the same hits.
+extern "C" int bathhost_search_run(bathhost_search *s)
+{
+  if (!s) return BATHHOST_EINVAL;
+  s->finished = false;
+  return run_batch(s);
+}
+
+// One target sequence searched at once (queue + run).
+extern "C" int bathhost_search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, int64_t n)
+{
+  const int st = bathhost_search_queue(s, name, dsq, n);
+  return st != BATHHOST_OK ? st : bathhost_search_run(s);
 }
 
 // E-values over the whole search space, duplicate removal, final ordering and reporting threshold
@@ -1735,19 +2008,30 @@ extern "C" int bathhost_search_sequence(bathhost_search *s, const char *name, co
 extern "C" int bathhost_search_finish(bathhost_search *s)
 {
   if (!s) return BATHHOST_EINVAL;
+  if (!s->queue.empty()) { const int st = bathhost_search_run(s); if (st != BATHHOST_OK) return st; }
+  if (s->finished) return BATHHOST_OK;
+  s->finished = true;
   const int Wn = s->model->prot.max_length * 3;
   for (Hit &h : s->hits) {
-    h.pub.lnP += log((float) s->st.nres / (float) Wn);
+    if (!h.evalue_done) {                                   // hits of earlier finish calls keep the pre-correction value in lnP_raw
+      h.lnP_raw = h.pub.lnP;
+      h.evalue_done = true;
+    }
+    h.duplicate = false;
+    h.pub.lnP = h.lnP_raw + log((float) s->st.nres / (float) Wn);      // p7_tophits_ComputeEvalues_BATH over the residues searched so far
     h.sortkey = -1.0 * h.pub.lnP;
     h.pub.evalue = exp(h.pub.lnP);
   }
-  // p7_tophits_SortBySeqidxAndAlipos: seqidx, plus strand first, start ascending, end descending
+  // p7_tophits_SortBySeqidxAndAlipos (hit_sorter_by_seqidx_aliposition, src/p7_tophits.c:286-306): seqidx, plus strand first, then
+  // the smaller coordinate ascending and the larger one descending -- start and end are swapped on the minus strand first
   std::stable_sort(s->hits.begin(), s->hits.end(), [](const Hit &a, const Hit &b) {
     if (a.pub.seqidx != b.pub.seqidx) return a.pub.seqidx < b.pub.seqidx;
     const int da = a.pub.ali_from < a.pub.ali_to ? 1 : -1, db = b.pub.ali_from < b.pub.ali_to ? 1 : -1;
     if (da != db) return da > db;
-    if (a.pub.ali_from != b.pub.ali_from) return a.pub.ali_from < b.pub.ali_from;
-    return a.pub.ali_to > b.pub.ali_to;
+    const long long as = std::min(a.pub.ali_from, a.pub.ali_to), ae = std::max(a.pub.ali_from, a.pub.ali_to);
+    const long long bs = std::min(b.pub.ali_from, b.pub.ali_to), be = std::max(b.pub.ali_from, b.pub.ali_to);
+    if (as != bs) return as < bs;
+    return ae > be;
   });
   if (s->hits.size() > 1) {                                 // p7_tophits_RemoveDuplicates
     size_t j = 0;

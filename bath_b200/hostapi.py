@@ -13,7 +13,7 @@ EXPORTS = [
     "bathhost_model_indel_pos", "bathhost_model_mat", "bathhost_model_consensus", "bathhost_length_model",
     "bathhost_model_filter_params", "bathhost_model_rbv", "bathhost_model_rwv", "bathhost_model_twv",
     "bathhost_orf_length_params", "bathhost_model_computed_max_length",
-    "bathhost_search_create", "bathhost_search_destroy", "bathhost_search_last_error", "bathhost_search_sequence",
+    "bathhost_search_create", "bathhost_search_create_multi", "bathhost_search_queue", "bathhost_search_run", "bathhost_search_destroy", "bathhost_search_last_error", "bathhost_search_sequence",
     "bathhost_search_finish", "bathhost_search_nhits", "bathhost_search_get_hit", "bathhost_search_get_stats",
     "bathhost_sample_region_segments", "bathhost_cluster_region_segments", "bathhost_search_format_tblout",
     "bathhost_calibrate", "bathhost_model_lambda", "bathhost_search_format_report", "bathhost_search_format_output", "bathhost_search_format_fstblout",
@@ -43,7 +43,7 @@ class Options(C.Structure):
     _fields_ = [("F1", C.c_double), ("F2", C.c_double), ("F3", C.c_double), ("F4", C.c_double), ("E", C.c_double),
                 ("min_orf_len", C.c_int32), ("block_length", C.c_int32), ("cpu_lanes_u8", C.c_int32), ("cpu_lanes_i16", C.c_int32),
                 ("no_bias", C.c_int32), ("no_null2", C.c_int32), ("top_only", C.c_int32), ("bottom_only", C.c_int32), ("std_only", C.c_int32),
-                ("show_frameline", C.c_int32)]
+                ("show_frameline", C.c_int32), ("reserved0", C.c_int32), ("chunk_nt", C.c_int64)]
 
 
 class Hit(C.Structure):
@@ -118,6 +118,12 @@ def load():
     L.bathhost_orf_length_params.argtypes = [vp, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_int16)]
     L.bathhost_search_create.restype = C.c_int
     L.bathhost_search_create.argtypes = [vp, C.POINTER(Backend), C.POINTER(Options), C.POINTER(vp)]
+    L.bathhost_search_create_multi.restype = C.c_int
+    L.bathhost_search_create_multi.argtypes = [vp, C.POINTER(Backend), C.c_int, C.POINTER(Options), C.POINTER(vp)]
+    L.bathhost_search_queue.restype = C.c_int
+    L.bathhost_search_queue.argtypes = [vp, C.c_char_p, u8p, C.c_int64]
+    L.bathhost_search_run.restype = C.c_int
+    L.bathhost_search_run.argtypes = [vp]
     L.bathhost_search_destroy.restype = None
     L.bathhost_search_destroy.argtypes = [vp]
     L.bathhost_search_last_error.restype = C.c_char_p
@@ -279,21 +285,25 @@ class Search:
     """One query against target sequences: the stage-batched pipeline of bathsearch --fs (pipeline.cpp)."""
 
     def __init__(self, model, gpu_ctx=None, backend=None, **options):
-        """gpu_ctx: a capi.Context (the product path).  backend: a ready bathhost_backend table instead -- used by the tests
-        and the CPU-baseline legs of bench.py to put the CPU oracle behind the same pipeline."""
+        """gpu_ctx: a capi.Context, or a list of them (several GPUs, or several contexts per GPU): the product path.
+        backend: a ready bathhost_backend table (or a list of them) instead -- used by the tests and the CPU-baseline legs
+        of bench.py to put the CPU oracle behind the same pipeline."""
         self.lib = load()
         self.model = model
-        self.gpu_ctx = gpu_ctx                       # keeps the device context alive
+        self.gpu_ctx = gpu_ctx                       # keeps the device context(s) alive
         if backend is None:
             if gpu_ctx is None:
                 raise ValueError("a device context is required: the product has no CPU path")
-            backend = backend_from(gpu_ctx.lib, gpu_ctx.h)
-        self.backend = backend
+            ctxs = gpu_ctx if isinstance(gpu_ctx, (list, tuple)) else [gpu_ctx]
+            backend = [backend_from(c.lib, c.h) for c in ctxs]
+        backends = list(backend) if isinstance(backend, (list, tuple)) else [backend]
+        self.backend = (Backend * len(backends))(*backends)
+        self._keep = []                              # queued target arrays: they must outlive bathhost_search_run
         opt = Options(**options)
         h = C.c_void_p()
-        st = self.lib.bathhost_search_create(model.h, C.byref(self.backend), C.byref(opt), C.byref(h))
+        st = self.lib.bathhost_search_create_multi(model.h, self.backend, len(backends), C.byref(opt), C.byref(h))
         if st != OK:
-            raise RuntimeError(f"bathhost_search_create: status {st}")
+            raise RuntimeError(f"bathhost_search_create_multi: status {st}")
         self.h = h
 
     def close(self):
@@ -313,7 +323,23 @@ class Search:
         if st != OK:
             raise RuntimeError(f"bathhost_search_sequence: status {st}: {self.lib.bathhost_search_last_error(self.h).decode()}")
 
+    def queue_sequence(self, name, dsq):
+        """one more target for the next run(): all queued sequences are searched in one stage-batched pass"""
+        dsq = np.ascontiguousarray(dsq, np.uint8)
+        self._keep.append(dsq)
+        st = self.lib.bathhost_search_queue(self.h, name.encode(), dsq.ctypes.data_as(C.POINTER(C.c_uint8)), len(dsq) - 2)
+        if st != OK:
+            raise RuntimeError(f"bathhost_search_queue: status {st}")
+
+    def run(self):
+        st = self.lib.bathhost_search_run(self.h)
+        self._keep = []
+        if st != OK:
+            raise RuntimeError(f"bathhost_search_run: status {st}: {self.lib.bathhost_search_last_error(self.h).decode()}")
+
     def finish(self):
+        if self._keep:
+            self.run()
         st = self.lib.bathhost_search_finish(self.h)
         if st != OK:
             raise RuntimeError(f"bathhost_search_finish: status {st}")

@@ -137,6 +137,9 @@ typedef struct {
   int32_t no_bias, no_null2, top_only, bottom_only;
   int32_t std_only;           /* 0: bathsearch --fs; 1: bathsearch's default pipeline (standard translation only) */
   int32_t show_frameline;     /* --frameline: the report's alignment blocks carry a FRAME line (src/p7_alidisplay.c:3998-4013) */
+  int32_t reserved0;
+  int64_t chunk_nt;           /* nucleotides per device-resident chunk of the target (0: chosen from the batch size and the number of
+                                 device contexts; env BATHHOST_CHUNK_MBP overrides the choice).  Results do not depend on it. */
 } bathhost_options;
 
 typedef struct {
@@ -171,10 +174,25 @@ int bathhost_cluster_region_segments(const bathhost_segment *sp, int n, int nsam
 
 typedef struct bathhost_search bathhost_search;
 int  bathhost_search_create(const bathhost_model *m, const bathhost_backend *be, const bathhost_options *opt, bathhost_search **ret);
+/* The same search over SEVERAL device contexts (bathgpu_ctx on different GPUs, or more than one per GPU so that one context's host
+ * stages run under another's kernels): the target is cut into chunks of consecutive blocks (src/bathsearch.c:1150,1198-1205 deals
+ * blocks to worker threads the same way), chunks are dealt round-robin to the contexts, each context is driven by its own host thread,
+ * and ONE hit list comes out -- E-values over the summed residue count, duplicates at block borders removed, as the reference merges
+ * its workers' lists (src/bathsearch.c:869-921).  Everything the reference computes in block order (hit-window list, length-model
+ * chain, early E-value cuts) is computed in that order on the host, so the list is identical whatever the number of contexts. */
+int  bathhost_search_create_multi(const bathhost_model *m, const bathhost_backend *be, int nbackends, const bathhost_options *opt,
+                                  bathhost_search **ret);
 void bathhost_search_destroy(bathhost_search *s);
 const char *bathhost_search_last_error(const bathhost_search *s);
-/* dsq[1..n] Easel digital nucleotides with sentinels at [0] and [n+1]; both strands unless restricted */
+/* dsq[1..n] Easel digital nucleotides with sentinels at [0] and [n+1]; both strands unless restricted.
+ * bathhost_search_sequence searches one sequence at once.  bathhost_search_queue + bathhost_search_run search a whole set of
+ * sequences in one stage-batched pass (larger device batches; the way to feed several GPUs): queued buffers must stay valid and
+ * unchanged until bathhost_search_run returns.  Both ways give the same hits. */
 int  bathhost_search_sequence(bathhost_search *s, const char *name, const uint8_t *dsq, int64_t n);
+int  bathhost_search_queue(bathhost_search *s, const char *name, const uint8_t *dsq, int64_t n);
+int  bathhost_search_run(bathhost_search *s);
+/* E-values over the whole search space, duplicate removal, ordering, reporting threshold.  Runs anything still queued first;
+ * calling it again without new sequences changes nothing. */
 int  bathhost_search_finish(bathhost_search *s);
 int  bathhost_search_nhits(const bathhost_search *s);
 int  bathhost_search_get_hit(const bathhost_search *s, int idx, bathhost_hit *hit);
