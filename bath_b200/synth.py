@@ -82,6 +82,38 @@ def planted_genome(rng, n, mat, every=50000, fs_rate=0.01, stop_every=300, revco
     return d, plants
 
 
+def planted_contigs(rng, total, mats, every=50000, fs_rates=0.01, min_len=1_000_000, max_len=10_000_000):
+    """BASELINE config 4's target: iid-ACGT contigs of min_len..max_len nt adding up to `total`, a homolog planted every `every` nt,
+    taken in turn from the models whose match emissions are in `mats` (half on the bottom strand).  Returns
+    [(name, dsq)], [(contig, start, end, strand, model)]."""
+    if not isinstance(fs_rates, (list, tuple)):
+        fs_rates = [fs_rates] * len(mats)
+    comp = np.array([3, 2, 1, 0], np.uint8)
+    contigs, plants, left, turn = [], [], int(total), 0
+    while left > 0:
+        n = int(min(left, rng.integers(min_len, max_len + 1)))
+        if left - n < min_len // 2:
+            n = left
+        d = iid_genome(rng, n)
+        pos = every // 2
+        while True:
+            k = turn % len(mats)
+            h = homolog(rng, mats[k], fs_rates[k])
+            if pos + len(h) + 1 > n:
+                break
+            strand = 1
+            if rng.random() < 0.5:
+                h = comp[h[::-1]]
+                strand = -1
+            d[pos: pos + len(h)] = h
+            plants.append((len(contigs), pos, pos + len(h) - 1, strand, k))
+            pos += every
+            turn += 1
+        contigs.append((f"contig{len(contigs) + 1}", d))
+        left -= n
+    return contigs, plants
+
+
 def tile_windows(n, length, step=None):
     """Window starts/lengths tiling [1..n]: the last window is pulled back so that every window is full length."""
     step = step or length

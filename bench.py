@@ -17,6 +17,13 @@ reference's own Mc/s definition (src/impl_sse/fwdback_fs.c:3115).
 
 N > 1: one process per GPU (torchrun), each rank owns its own 100 Mbp shard (weak scaling, no collective
 on the DP path); the only communication is the barrier and the max-over-ranks of the timings.
+
+Second metric, "search" (BASELINE.json configs[3] as written): bathsearch --fs Mbp/s of the three profiles of
+tRNA-synthetases.bhmm against ONE synthetic genome in contigs of 1-10 Mbp with planted homologs of all three, sharded by
+blocks over the N devices by ONE process (rank 0; bathhost_search_create_multi, two contexts per device) with one merged
+hit list per profile: strong scaling on a fixed target.  At N > 1 the same search is also run on one device and the two
+tables compared byte for byte (search.checks.hits_identical_to_1gpu); at N = 1 the GPU search of the CPU-baseline prefix
+is compared with the CPU-oracle pipeline's table (search.checks.hits_identical_to_cpu_prefix).
 """
 import argparse
 import json
@@ -47,8 +54,9 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--search-cpu-mbp", type=float, default=4.0, help="size of the CPU-baseline sample of the search leg, Mbp")
-    ap.add_argument("--search-mbp", type=float, default=100.0,
-                    help="also run the whole stage-batched bathsearch --fs pipeline over this many Mbp of the genome (0 = skip)")
+    ap.add_argument("--search-mbp", type=float, default=1000.0,
+                    help="also run the whole stage-batched bathsearch --fs pipeline (3 profiles) over a genome of this many Mbp (0 = skip)")
+    ap.add_argument("--contexts-per-gpu", type=int, default=2, help="device contexts per GPU in the search leg")
     return ap.parse_args()
 
 
@@ -156,7 +164,7 @@ def run_reference(args, rank, world):
     cells = float(lengths[:n].astype(np.int64).sum()) * model.M
     value = cells * args.steps / dt / 1e9
     sample = f"{n} of {len(starts)} windows of {args.window} nt per step ({cells / 1e9:.3f} Gcells), {ncpu} threads"
-    search = search_leg_cpu(model, dsq, args.search_cpu_mbp, ncpu) if args.search_mbp > 0 else None
+    search = search_leg_cpu(args.search_cpu_mbp, ncpu) if args.search_mbp > 0 else None
     emit_json_line({
         "impl": "reference", "metric": "frameshift Forward GCUPS", "value": value, "unit": "GCUPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
@@ -170,63 +178,127 @@ def run_reference(args, rank, world):
     })
 
 
-def search_leg(ctx, model, dsq, mbp, plants):
-    """BASELINE.json's second metric on rank 0's shard: bathsearch --fs end to end (ORF translation, MSV/bias/Viterbi/Forward
-    filters, DNA windows, frameshift Forward/Backward, domain definition, rescoring, hit list) through the host pipeline
-    (bath_b200/host/pipeline.cpp) and the C ABI, host buffers in, hit records out.  Mbp/s = target nucleotides (one strand
-    counted, both searched) / wall seconds.  Planted homologs recovered = hits overlapping a planted interval."""
-    from bath_b200 import capi, hostapi
-    n = int(min(mbp * 1e6, len(dsq) - 2))
-    sub = capi.pinned_array((n + 2,), np.uint8)             # the target sequence sits in page-locked host memory, as the e2e leg's inputs do
-    sub[:] = 255
-    sub[1:-1] = dsq[1:n + 1]
-    # one untimed pass first (device buffers get allocated, kernels loaded: the steady state of a multi-sequence search), then the timed one
-    warm = hostapi.Search(model, ctx)
-    t0 = time.perf_counter()
-    warm.add_sequence("synthetic", sub)
-    warm.finish()
-    cold = time.perf_counter() - t0
-    warm.close()
-    search = hostapi.Search(model, ctx)
-    t0 = time.perf_counter()
-    search.add_sequence("synthetic", sub)
-    hits = search.finish()
-    dt = time.perf_counter() - t0
-    st = search.stats()
-    planted = [(a, b) for (a, b, strand) in plants if b <= n]
-    found = 0
-    for a, b in planted:
-        for h in hits:
-            lo, hi = min(h["ali_from"], h["ali_to"]), max(h["ali_from"], h["ali_to"])
-            if lo <= b and hi >= a:
-                found += 1
-                break
-    search.close()
-    return {"metric": "bathsearch --fs Mbp/s", "value": n / dt / 1e6, "unit": "Mbp/s", "seconds": dt, "first_pass_seconds": cold, "target_mbp": n / 1e6,
-            "hits": len(hits), "planted": len(planted), "planted_recovered": found, "stats": st,
-            "note": "windows that lose the arbitration go down the standard-translation branch (stats.n_std_windows); multi-domain regions of the frameshift branch (stats.n_multidomain_regions) are split by stochastic-trace clustering: Forward matrix on the device, sampling and clustering on the host; the target sequence is read from page-locked host memory"}
+SEARCH_MODELS = (0, 1, 2)        # tRNA-synthetases.bhmm: M = 185, 192, 247
 
 
-def search_leg_cpu(model, dsq, mbp, nthreads):
-    """The same pipeline (bath_b200/host/pipeline.cpp) with the CPU oracle behind the stage calls (oracle/cpu_backend.c) on all
-    host threads, on a bounded prefix of the genome: the CPU baseline of the Mbp/s metric.  Oracle code is the thing timed here,
-    never part of the product path."""
+def search_target(mbp):
+    """BASELINE configs[3]'s target: contigs of 1-10 Mbp, a homolog every 50 kbp taken in turn from the three profiles (seed 42)"""
+    from bath_b200 import hostapi, synth
+    models = [hostapi.QueryModel(HMM_FILE, i) for i in SEARCH_MODELS]
+    rng = np.random.default_rng(42)
+    total = int(mbp * 1e6)
+    contigs, plants = synth.planted_contigs(rng, total, [m.mat() for m in models], every=50000, fs_rates=[m.fsprob for m in models],
+                                            min_len=min(1_000_000, total), max_len=min(10_000_000, total))
+    return models, contigs, plants
+
+
+def run_search(models, contigs, gpu_ctxs=None, backends=None):
+    """every profile against the whole target: (seconds per profile, tables, stats, hit lists)"""
     from bath_b200 import hostapi
+    secs, tables, stats, hits = [], [], [], []
+    for model in models:
+        search = hostapi.Search(model, gpu_ctx=gpu_ctxs, backend=backends)
+        t0 = time.perf_counter()
+        for name, dsq in contigs:
+            search.queue_sequence(name, dsq)
+        h = search.finish()
+        secs.append(time.perf_counter() - t0)
+        tables.append(search.tblout(header=False))
+        stats.append(search.stats())
+        hits.append(h)
+        search.close()
+    return secs, tables, stats, hits
+
+
+def recovered(hits_per_model, contigs, plants):
+    """planted homologs overlapped by a hit of their own profile on their own contig"""
+    names = [n for n, _ in contigs]
+    by = {}
+    for k, hits in enumerate(hits_per_model):
+        for h in hits:
+            by.setdefault((k, h["name"]), []).append((min(h["ali_from"], h["ali_to"]), max(h["ali_from"], h["ali_to"])))
+    found = 0
+    for c, a, b, strand, k in plants:
+        if any(lo <= b and hi >= a for lo, hi in by.get((k, names[c]), ())):
+            found += 1
+    return found
+
+
+def search_leg(devices, per_gpu, mbp, cpu_mbp, with_cpu):
+    """BASELINE.json's second metric on rank 0: bathsearch --fs end to end (ORF translation, MSV/bias/Viterbi/Forward filters, DNA
+    windows, frameshift Forward/Backward, domain definition, rescoring, merged hit list) through the host pipeline
+    (bath_b200/host/pipeline.cpp) and the C ABI, host buffers in, hit records out, for each of the three profiles.  Mbp/s = target
+    nucleotides x profiles (one strand counted, both searched) / wall seconds."""
+    from bath_b200 import capi, hostapi
+    models, contigs, plants = search_target(mbp)
+    pinned = []
+    for name, dsq in contigs:                                  # the target sits in page-locked host memory, as the e2e leg's inputs do
+        buf = capi.pinned_array(dsq.shape, np.uint8)
+        buf[:] = dsq
+        pinned.append((name, buf))
+    total_nt = sum(len(d) - 2 for _, d in contigs)
+    ctxs = [capi.Context(d) for d in devices for _ in range(per_gpu)]
+    # one untimed pass of the first profile (device buffers get allocated, kernels loaded: the steady state of a multi-query search)
+    t0 = time.perf_counter()
+    run_search(models[:1], pinned, gpu_ctxs=ctxs)
+    cold = time.perf_counter() - t0
+    secs, tables, stats, hits = run_search(models, pinned, gpu_ctxs=ctxs)
+    dt = sum(secs)
+    out = {"metric": "bathsearch --fs Mbp/s", "value": total_nt * len(models) / dt / 1e6, "unit": "Mbp/s", "seconds": dt, "seconds_per_profile": secs,
+           "first_pass_seconds": cold, "target_mbp": total_nt / 1e6, "contigs": len(contigs), "profiles": [m.M for m in models],
+           "n_gpus": len(devices), "contexts_per_gpu": per_gpu, "scaling": "strong",
+           "hits": [len(h) for h in hits], "planted": len(plants), "planted_recovered": recovered(hits, contigs, plants),
+           "stats": stats[1], "checks": {},
+           "note": "one process drives every device (bathhost_search_create_multi): blocks of the one target are dealt to the device "
+                   "contexts, the hit-window list / length-model chain / residue counts are kept in the reference's serial order on the "
+                   "host, one merged hit list per profile; stage times in stats are summed over contexts"}
+    if len(devices) > 1:                                        # the same search on one device: the tables must agree byte for byte
+        one = [capi.Context(devices[0]) for _ in range(per_gpu)]
+        run_search(models[:1], pinned, gpu_ctxs=one)
+        secs1, tables1, _, _ = run_search(models, pinned, gpu_ctxs=one)
+        out["one_gpu"] = {"value": total_nt * len(models) / sum(secs1) / 1e6, "seconds": sum(secs1)}
+        out["checks"]["hits_identical_to_1gpu"] = bool(tables1 == tables)
+        for c in one:
+            c.close()
+    if with_cpu:
+        # CPU baseline of this metric: the same pipeline over the CPU oracle's stage calls on a bounded prefix of the target; the GPU
+        # search of the same prefix must write the same table
+        from oracle import pyoracle as po
+        po.lib(native=True)
+        ncpu = os.cpu_count() or 1
+        n = int(min(cpu_mbp * 1e6, len(contigs[0][1]) - 2))
+        sub = np.full(n + 2, 255, np.uint8)
+        sub[1:-1] = contigs[0][1][1:n + 1]
+        be, keep = po.cpu_backend(ncpu)
+        t0 = time.perf_counter()
+        csecs, ctables, _, chits = run_search(models, [("contig1", sub)], backends=be)
+        cdt = time.perf_counter() - t0
+        del keep
+        _, gtables, _, _ = run_search(models, [("contig1", sub)], gpu_ctxs=ctxs)
+        out["cpu_baseline"] = {"value": n * len(models) / cdt / 1e6, "unit": "Mbp/s", "cores": ncpu, "kind": "port", "hits": [len(h) for h in chits],
+                               "sample": f"first {n / 1e6:g} Mbp of contig1, 3 profiles ({cdt:.1f} s, {ncpu} threads, scalar C oracle behind the same host pipeline)"}
+        out["checks"]["hits_identical_to_cpu_prefix"] = bool(gtables == ctables)
+    for c in ctxs:
+        c.close()
+    return out
+
+
+def search_leg_cpu(mbp, nthreads):
+    """--impl reference: the same pipeline with the CPU oracle behind the stage calls (oracle/cpu_backend.c) on all host threads, on a
+    bounded prefix of the target.  Oracle code is the thing timed here, never part of the product path."""
     from oracle import pyoracle as po
     po.lib(native=True)
-    be, keep = po.cpu_backend(nthreads)
-    n = int(min(mbp * 1e6, len(dsq) - 2))
+    models, contigs, plants = search_target(max(mbp, 1.0))
+    n = int(min(mbp * 1e6, len(contigs[0][1]) - 2))
     sub = np.full(n + 2, 255, np.uint8)
-    sub[1:-1] = dsq[1:n + 1]
-    search = hostapi.Search(model, backend=be)
+    sub[1:-1] = contigs[0][1][1:n + 1]
+    be, keep = po.cpu_backend(nthreads)
     t0 = time.perf_counter()
-    search.add_sequence("synthetic", sub)
-    hits = search.finish()
+    secs, tables, stats, hits = run_search(models, [("contig1", sub)], backends=be)
     dt = time.perf_counter() - t0
-    search.close()
     del keep
-    return {"value": n / dt / 1e6, "unit": "Mbp/s", "cores": nthreads, "kind": "port", "hits": len(hits),
-            "sample": f"first {n / 1e6:g} Mbp of the genome ({dt:.1f} s, {nthreads} threads, scalar C oracle behind the same host pipeline)"}
+    return {"value": n * len(models) / dt / 1e6, "unit": "Mbp/s", "cores": nthreads, "kind": "port", "hits": [len(h) for h in hits],
+            "sample": f"first {n / 1e6:g} Mbp of contig1, 3 profiles ({dt:.1f} s, {nthreads} threads, scalar C oracle behind the same host pipeline)"}
 
 
 def workload_config(args, M, nwin):
@@ -281,22 +353,26 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner out of stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # the ranks that wait while rank 0 runs the sharded search wait on the CPU (an NCCL barrier would spin on their GPUs, which rank 0 is using)
+    cpu_group = dist.new_group(backend="gloo") if world > 1 else None
+
+    def cpu_barrier():
+        if world > 1:
+            dist.barrier(group=cpu_group)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    from bath_b200 import shard
+    from bath_b200 import ranks
 
     def max_over_ranks(x):
-        return shard.reduce_scalar(x, "max", device="cuda")
+        return ranks.reduce_scalar(x, "max", device="cuda")
 
     def sum_over_ranks(x):
-        return shard.reduce_scalar(x, "sum", device="cuda")
+        return ranks.reduce_scalar(x, "sum", device="cuda")
 
-    # one process per GPU shares the host: each gets its share of the cores for the host side of the search leg
-    os.environ.setdefault("BATHHOST_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))))
     model, dsq_np, starts, lengths, plants = make_workload(rank, args.mbp, args.window)
     nplants = len(plants)
     M, nwin = model.M, len(starts)
@@ -360,21 +436,18 @@ def main():
     h2d = int(dsq.nbytes + wins.nbytes)
     d2h = int(sc.nbytes + st.nbytes)
 
-    # ---- second metric: the whole search on every rank's own genome shard; only timings, residue counts and hit lists cross ranks
+    # ---- second metric: the whole search, config 4 as written: ONE target, three profiles, blocks dealt to the N devices by one process
+    # (rank 0 drives every device; the other ranks wait at the barrier with their devices idle)
     search = None
     if args.search_mbp > 0:
+        ctx.close()
+        del flush
+        torch.cuda.empty_cache()
         barrier()
-        search = search_leg(ctx, model, dsq_np, min(args.search_mbp, args.mbp), plants)
-        barrier()
-        mbp_total = sum_over_ranks(search["target_mbp"])
-        secs = max_over_ranks(search["seconds"])
-        hits_total = sum_over_ranks(search["hits"])
-        rec_total, planted_total = sum_over_ranks(search["planted_recovered"]), sum_over_ranks(search["planted"])
-        if world > 1:
-            search["rank0"] = {"value": search["value"], "seconds": search["seconds"], "hits": search["hits"]}
-            search.update({"value": mbp_total / secs, "seconds": secs, "target_mbp": mbp_total, "hits": int(hits_total),
-                           "planted": int(planted_total), "planted_recovered": int(rec_total), "n_gpus": world,
-                           "aggregation": "each rank searches its own shard (profiles replicated); Mbp summed over ranks / max wall time over ranks"})
+        devices = ranks.search_devices(rank, world, torch.cuda.device_count())
+        if devices:
+            search = search_leg(devices, args.contexts_per_gpu, args.search_mbp, args.search_cpu_mbp, world == 1 and not args.no_cpu_baseline)
+        cpu_barrier()
 
     if rank != 0:
         if world > 1:
@@ -421,8 +494,6 @@ def main():
     }
     if search is not None:
         out["search"] = search
-        if world == 1 and not args.no_cpu_baseline:
-            out["search"]["cpu_baseline"] = search_leg_cpu(model, dsq_np, min(args.search_mbp, args.search_cpu_mbp), os.cpu_count() or 1)
     if world == 1 and not args.no_cpu_baseline:
         ncpu = os.cpu_count() or 1
         v, n, dt, osc = cpu_sample(M, dsq_np, starts, lengths, args.cpu_seconds, ncpu)

@@ -1,4 +1,6 @@
-"""N > 1 path on CPU: two gloo ranks exercise the sharding and the cross-rank bookkeeping (no collective on the DP path)."""
+"""N > 1 on CPU: two gloo ranks run the cross-rank plumbing of bench.py (bath_b200/ranks.py), and rank 0 runs the sharded search
+the way it does under torchrun -- one process, one context per device -- here with two CPU-oracle contexts standing in for two
+GPUs; the merged table must equal the one-context table."""
 import os
 import socket
 
@@ -15,39 +17,54 @@ def _free_port():
 
 
 def _worker(rank, world_size, port, q):
+    import sys
     import torch.distributed as dist
-    from bath_b200 import shard
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.dirname(here)); sys.path.insert(0, here)
+    import common
+    from bath_b200 import hostapi, ranks, synth
+    from oracle import pyoracle
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world_size)
-    blocks = shard.shard_blocks(11, rank, world_size)
-    t_max = shard.reduce_scalar(10.0 + rank, "max")
-    nres = shard.reduce_scalar(1000 * (rank + 1), "sum")
-    hits = [{"name": f"seq{rank}", "strand": 1, "ali_from": 5 + rank, "ali_to": 90, "lnP_raw": -30.0 - rank},
-            {"name": f"seq{rank}", "strand": -1, "ali_from": 500, "ali_to": 400, "lnP_raw": -1.0}]
-    gathered = shard.gather_hits(hits)
-    merged = shard.merge_hits(gathered, nres, 167) if rank == 0 else None
-    q.put((rank, blocks, t_max, nres, merged))
+    t_max = ranks.reduce_scalar(10.0 + rank, "max")
+    cells = ranks.reduce_scalar(1000 * (rank + 1), "sum")
+    devices = ranks.search_devices(rank, world_size, n_visible=world_size)
+    tables = None
+    if devices:                                   # rank 0: the whole target over one context per "device"
+        model = hostapi.QueryModel(common.golden("tRNA-synthetases.bhmm"), 1)
+        contigs, plants = synth.planted_contigs(np.random.default_rng(5), 600_000, [model.mat()], every=20_000, fs_rates=model.fsprob,
+                                                min_len=150_000, max_len=300_000)
+        tables = []
+        for nctx in (1, len(devices)):
+            pairs = [pyoracle.cpu_backend(2) for _ in range(nctx)]
+            search = hostapi.Search(model, backend=[p[0] for p in pairs], chunk_nt=120_000)
+            for name, dsq in contigs:
+                search.queue_sequence(name, dsq)
+            hits = search.finish()
+            tables.append((search.tblout(), search.stats()["nres"], len(hits)))
+            search.close()
+    dist.barrier()
+    q.put((rank, t_max, cells, devices, tables))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_rank_sharding_and_merge():
+def test_two_ranks_reductions_and_rank0_sharded_search():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted([q.get(timeout=120) for _ in range(2)])
+    res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda r: r[0])
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (r0, b0, t0, n0, m0), (r1, b1, t1, n1, m1) = res
-    assert sorted(b0 + b1) == list(range(11)) and not set(b0) & set(b1)      # every block searched exactly once
-    assert t0 == t1 == 11.0                                                   # max over ranks
-    assert n0 == n1 == 3000.0                                                 # residue count = E-value search space
-    assert m1 is None and [h["name"] for h in m0] == ["seq1", "seq0", "seq0", "seq1"][: len(m0)] or len(m0) >= 2
-    # lnP = lnP_raw + log(N / W), W = 3 * max_length (src/p7_tophits.c:795)
-    assert abs(m0[0]["lnP"] - (-31.0 + float(np.log(np.float32(3000) / np.float32(501))))) < 1e-6
-    assert all(m0[i]["lnP"] <= m0[i + 1]["lnP"] for i in range(len(m0) - 1))
+    (r0, t0, c0, d0, tab0), (r1, t1, c1, d1, tab1) = res
+    assert t0 == t1 == 11.0                                  # max over ranks
+    assert c0 == c1 == 3000.0                                # sum over ranks
+    assert d0 == [0, 1] and d1 == [] and tab1 is None       # rank 0 drives both devices, rank 1 none
+    one, two = tab0
+    assert one[2] >= 20 and one[1] == 2 * 600_000            # hits found; residues = both strands of the whole target
+    assert one == two                                         # merged list of two contexts == one context
