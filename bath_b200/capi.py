@@ -20,6 +20,7 @@ EXPORTS = [
     "bathgpu_fwd_orfs", "bathgpu_fs_fwd_bck_xrows", "bathgpu_select_slot",
     "bathgpu_orf_fwd_bck_xrows", "bathgpu_orf_domains", "bathgpu_orf_fetch_domain_matrices",
     "bathgpu_orfs_msv_screen", "bathgpu_orfs_fetch", "bathgpu_revcomp_slot", "bathgpu_fs_fwd_block", "bathgpu_fs_forward_matrices",
+    "bathgpu_bias_forward",
 ]
 
 
@@ -44,6 +45,7 @@ class FilterParams(C.Structure):
 orf_dtype = np.dtype([("offset", "<i8"), ("L", "<i4"), ("tjb_b", "u1"), ("ssv_thresh", "u1"), ("xw_move", "<i2"),
                       ("vit_thresh", "<i2"), ("flags", "<i2"), ("ext_thresh", "<i4")], align=True)
 orf_window_dtype = np.dtype([("orf", "<i4"), ("n", "<i4"), ("k", "<i4"), ("length", "<i4"), ("score", "<f4")], align=True)
+bias_item_dtype = np.dtype([("start", "<i8"), ("L", "<i4"), ("table", "<i4"), ("t00", "<f4"), ("pad_", "<i4")], align=True)
 block_dtype = np.dtype([("goff", "<i8"), ("n", "<i4"), ("C", "<i4")], align=True)
 orf_hit_dtype = np.dtype([("block", "<i4"), ("index", "<i4"), ("start", "<i4"), ("end", "<i4"), ("n", "<i4"), ("frame", "<i4"),
                           ("offset", "<i8"), ("usc", "<f4"), ("status", "<i4")], align=True)
@@ -134,6 +136,8 @@ def load():
     L.bathgpu_fs_forward_matrices.argtypes = [vp, vp, C.c_int, fp, fp, fp, C.c_int64, fp, ip]
     L.bathgpu_select_slot.restype = C.c_int
     L.bathgpu_select_slot.argtypes = [vp, C.c_int]
+    L.bathgpu_bias_forward.restype = C.c_int
+    L.bathgpu_bias_forward.argtypes = [vp, C.c_int, vp, C.c_int, fp, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_uint8), fp]
     L.bathgpu_host_alloc.restype = vp
     L.bathgpu_host_alloc.argtypes = [C.c_size_t]
     L.bathgpu_host_free.restype = None
@@ -366,6 +370,16 @@ class Context:
 
     def revcomp_slot(self, src, dst):
         self._check(self.lib.bathgpu_revcomp_slot(self.h, int(src), int(dst)))
+
+    def bias_forward(self, kind, items, tables, t10, t11, gcode=None):
+        """bathgpu_bias_forward: items = bias_item_dtype array; tables [ntab][29][2]; returns n (kind 0) or n x 3 (kind 1) scores"""
+        items = np.ascontiguousarray(items, bias_item_dtype)
+        tables = np.ascontiguousarray(tables, np.float32).reshape(-1, KP, 2)
+        out = np.zeros(len(items) * (3 if kind == 1 else 1), np.float32)
+        g = np.ascontiguousarray(gcode if gcode is not None else np.zeros(64), np.uint8)
+        self._check(self.lib.bathgpu_bias_forward(self.h, int(kind), items.ctypes.data_as(C.c_void_p), len(items), _f(tables), len(tables),
+                                                  float(t10), float(t11), g.ctypes.data_as(C.POINTER(C.c_uint8)), _f(out)))
+        return out.reshape(-1, 3) if kind == 1 else out
 
     def orfs_msv_screen(self, blocks, complement, gcode, min_len, tjb_of, null_of, min_bits):
         """bathgpu_orfs_msv_screen + bathgpu_orfs_fetch: (ORFs found per block, survivors, their residues)"""

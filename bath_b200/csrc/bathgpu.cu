@@ -21,6 +21,7 @@
 #include "orf_domain.cuh"
 #include "orf_filters.cuh"
 #include "orf_finder.cuh"
+#include "bias_filter.cuh"
 #include "microbench.cuh"
 #include "launch.h"
 
@@ -96,6 +97,7 @@ struct bathgpu_ctx {
   bathgpu_filter_params flt{};
   int           flt_W = 0, flt_P = 0;
   DevBuf        f_rbv, f_rwv, f_twv, f_ddsum, f_nrb, orfs, fsc, fst, fwins, fnw;
+  DevBuf        b_items, b_tables, b_out;      // bias filter
   DevBuf        o_tiles, o_cnt, o_base, o_blocks, o_first, o_tjb, o_null, o_meta, o_hits, o_counters;
   long long     o_nhits = 0, o_nres = 0;
   // domain stage workspace (last chunk stays resident for bathgpu_fs_fetch_domain_matrices)
@@ -1741,6 +1743,43 @@ extern "C" int bathgpu_orf_fetch_domain_matrices(bathgpu_ctx *ctx, int e, float 
       if (pc) { pc[0] = hp[(i * kPPCellsP + PPP_M) * mpad + p]; pc[1] = 0.f; pc[2] = hp[(i * kPPCellsP + PPP_I) * mpad + p]; }
       if (oc) { oc[0] = ho[(i * kOACells + OA_M) * mpad + p]; oc[1] = ho[(i * kOACells + OA_D) * mpad + p]; oc[2] = ho[(i * kOACells + OA_I) * mpad + p]; }
     }
+  return BATHGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a5: the bias-composition filter over ORFs or over the three frames of DNA windows (bias_filter.cuh)
+extern "C" int bathgpu_bias_forward(bathgpu_ctx *ctx, int kind, const bathgpu_bias_item *items, int n, const float *tables, int ntab,
+                                    float t10, float t11, const uint8_t gcode[64], float *out)
+{
+  if (!ctx || (kind != 0 && kind != 1) || !items || n < 1 || !tables || ntab < 1 || !out || (kind == 1 && !gcode))
+    return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_bias_forward");
+  TargetSlot &S = ctx->S();
+  static_assert(sizeof(BiasItem) == sizeof(bathgpu_bias_item), "item layouts must agree");
+  for (int i = 0; i < n; ++i) {
+    const bathgpu_bias_item &d = items[i];
+    if (d.table < 0 || d.table >= ntab || d.L < 0) return fail(ctx, BATHGPU_EINVAL, "bias item %d: table %d of %d, L %d", i, d.table, ntab, d.L);
+    if (kind == 0 ? (d.start < 0 || d.start + d.L > S.nres) : (d.start < 1 || d.start + d.L - 1 > S.block_n))
+      return fail(ctx, BATHGPU_EINVAL, "bias item %d (start %lld, L %d) is outside the resident %s", i, (long long)d.start, d.L, kind == 0 ? "residues" : "sequence");
+  }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int per = (kind == 1) ? 3 : 1;
+  if (ctx->b_items.reserve((size_t)n * sizeof(BiasItem)) != BATHGPU_OK || ctx->b_tables.reserve((size_t)ntab * 58 * 4) != BATHGPU_OK ||
+      ctx->b_out.reserve((size_t)n * per * 4) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->b_items.p, items, (size_t)n * sizeof(BiasItem), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->b_tables.p, tables, (size_t)ntab * 58 * 4, cudaMemcpyHostToDevice, ctx->stream));
+  BiasArgs a{};
+  a.items = ctx->b_items.as<BiasItem>(); a.n = n; a.kind = kind; a.tables = ctx->b_tables.as<float>(); a.t10 = t10; a.t11 = t11;
+  a.residues = S.residues.as<uint8_t>(); a.dna4 = S.dna4.as<uint32_t>(); a.out = ctx->b_out.as<float>();
+  if (gcode) memcpy(a.gcode, gcode, 64);
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  const long long nthreads = (long long)n * per;
+  bias_forward_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, ctx->stream>>>(a);
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->b_out.p, (size_t)n * per * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+  ctx->last_launches = 1;
   return BATHGPU_OK;
 }
 

@@ -79,7 +79,8 @@ struct Background {
   float t[2][3], e[2][kK], eo[kKp][2], pi[2];
 
   explicit Background(const NullModel &n) { for (int x = 0; x < kK; ++x) f[x] = n.f[x]; p1 = n.p1; omega = n.omega; }
-  void set_length(int L) { p1 = (float) L / (float) (L + 1); t[0][0] = p1; t[0][1] = 1.0f - p1; }
+  static float p1_for_length(int L) { return (float) L / (float) (L + 1); }
+  void set_length(int L) { p1 = p1_for_length(L); t[0][0] = p1; t[0][1] = 1.0f - p1; }
   float null_one(int L) const { return (float) L * log(p1) + log(1. - p1); }
   float fs_null_one(int La) const { float per_frame = (float) La * log(p1) + log(1. - p1); return per_frame + log(3.0); }
 
@@ -106,56 +107,64 @@ struct Background {
       }
   }
 
-  // esl_hmm_Forward, 2 states, per-row rescaling by the row maximum
-  float hmm_forward(const uint8_t *dsq, int L) const
+  // esl_hmm_Forward, 2 states, per-row rescaling by the row maximum; eo = [kKp][2] emission odds, t00 = t[0][0] (the rest of row 0 follows),
+  // t10/t11 = row 1.  Returns the summed log scale factors.  bathgpu_bias_forward runs exactly these operations in this order.
+  static float hmm_forward_tab(const float *eo, float t00, float t10, float t11, const uint8_t *dsq, int L)
   {
-    if (L == 0) return 0.0f;           // pi[M] is 0 in this model: log(0); never reached (L >= 1 everywhere it is called)
+    if (L == 0) return 0.0f;           // pi[M] is 0 in this model: log(0); never reached in the reference (L >= 1 everywhere it is called)
+    const float t[2][2] = { { t00, 1.0f - t00 }, { t10, t11 } };
+    const float pi[2] = { 0.999f, 0.001f };
     float prev[2], cur[2], logsc = 0;
     float mx = 0.0;
-    for (int k = 0; k < 2; ++k) { prev[k] = eo[dsq[1]][k] * pi[k]; mx = std::max(prev[k], mx); }
+    for (int k = 0; k < 2; ++k) { prev[k] = eo[2 * dsq[1] + k] * pi[k]; mx = std::max(prev[k], mx); }
     for (int k = 0; k < 2; ++k) prev[k] /= mx;
-    logsc += log(mx);                  // accumulated in float as esl_hmm_Forward sums fwd->sc[]
-    std::vector<float> sc;
-    sc.reserve((size_t) L + 2);
-    sc.push_back((float) log(mx));
+    logsc += (float) log(mx);          // accumulated in float, in row order, as esl_hmm_Forward sums fwd->sc[]
     for (int i = 2; i <= L; ++i) {
       mx = 0.0;
       for (int k = 0; k < 2; ++k) {
         cur[k] = 0.0;
         for (int m = 0; m < 2; ++m) cur[k] += prev[m] * t[m][k];
-        cur[k] *= eo[dsq[i]][k];
+        cur[k] *= eo[2 * dsq[i] + k];
         mx = std::max(cur[k], mx);
       }
       for (int k = 0; k < 2; ++k) prev[k] = cur[k] / mx;
-      sc.push_back((float) log(mx));
+      logsc += (float) log(mx);
     }
     float last = 0.0;
-    for (int m = 0; m < 2; ++m) last += prev[m] * t[m][2];
-    sc.push_back((float) log(last));
-    logsc = 0.0;
-    for (float v : sc) logsc += v;
+    for (int m = 0; m < 2; ++m) last += prev[m] * 1.0f;
+    logsc += (float) log(last);
     return logsc;
   }
-  float filter_score(const uint8_t *dsq, int L) const { return hmm_forward(dsq, L) + (float) L * logf(p1) + logf(1. - p1); }
+  float hmm_forward(const uint8_t *dsq, int L) const { return hmm_forward_tab(&eo[0][0], t[0][0], t[1][0], t[1][1], dsq, L); }
+  // p7_bg_FilterScore: the Forward score with the null model's length distribution imposed (src/p7_bg.c:491-500)
+  float filter_score_from(float fwd, int L) const { return fwd + (float) L * logf(p1) + logf(1. - p1); }
+  float filter_score(const uint8_t *dsq, int L) const { return filter_score_from(hmm_forward(dsq, L), L); }
 
-  // p7_bg_fs_FilterScore: three frames of the DNA window, canonical residues only
+  // p7_bg_fs_FilterScore: three frames of the DNA window, canonical residues only (src/p7_bg.c:522-573)
+  static int frame_residues(const uint8_t *dna, int L, int fr, const uint8_t gcode[64], uint8_t *orf)     // fills orf[1..], returns the count
+  {
+    int j = 1;
+    for (int i = fr; i <= L - 2; i += 3) {
+      const uint8_t a = dna[i], b = dna[i + 1], c = dna[i + 2];
+      if (a < 4 && b < 4 && c < 4) {
+        const uint8_t aa = gcode[16 * a + 4 * b + c];
+        if (aa < kK) orf[j++] = aa;
+      }
+    }
+    return j - 1;
+  }
+  float fs_filter_score_from(const float sc[3], int L) const
+  {
+    float sum = kNegInfF;
+    for (int fr = 0; fr < 3; ++fr) sum = flogsum(sum, sc[fr]);
+    return sum + ((float) (L / 3) * logf(p1) + logf(1. - p1) + log(3.0));
+  }
   float fs_filter_score(const uint8_t *dna, int L, const uint8_t gcode[64]) const
   {
     std::vector<uint8_t> orf((size_t) L + 2);
-    float sum = kNegInfF;
-    for (int fr = 1; fr <= 3; ++fr) {
-      int j = 1;
-      for (int i = fr; i <= L - 2; i += 3) {
-        const uint8_t a = dna[i], b = dna[i + 1], c = dna[i + 2];
-        if (a < 4 && b < 4 && c < 4) {
-          const uint8_t aa = gcode[16 * a + 4 * b + c];
-          if (aa < kK) orf[j++] = aa;
-        }
-      }
-      const float sc = hmm_forward(orf.data(), j - 1);
-      sum = flogsum(sum, sc);
-    }
-    return sum + ((float) (L / 3) * logf(p1) + logf(1. - p1) + log(3.0));
+    float sc[3];
+    for (int fr = 1; fr <= 3; ++fr) sc[fr - 1] = hmm_forward(orf.data(), frame_residues(dna, L, fr, gcode, orf.data()));
+    return fs_filter_score_from(sc, L);
   }
 };
 
@@ -243,6 +252,7 @@ struct bathhost_search {
   const bathhost_model *model;
   std::vector<bathhost_backend> bes;              // device contexts the stages are dealt to (one or more per GPU)
   HostBuf               mxbuf[2];                 // Forward matrices and X rows of multi-domain regions
+  std::vector<std::unique_ptr<HostBuf[]>> be_xbuf;   // per device context: X rows of the Forward / Backward parsers (page-locked, reused from unit to unit)
   Options               opt;
   Background            bg;
   std::vector<float>    compo;
@@ -264,7 +274,10 @@ struct bathhost_search {
   int64_t               nseqs = 0;
   int64_t               chunk_nt = 0;             // 0: chosen per batch
 
-  bathhost_search(const bathhost_model *m, const bathhost_backend *b, int nb) : model(m), bes(b, b + nb), bg(m->bg) {}
+  bathhost_search(const bathhost_model *m, const bathhost_backend *b, int nb) : model(m), bes(b, b + nb), bg(m->bg)
+  {
+    for (int k = 0; k < nb; ++k) be_xbuf.emplace_back(new HostBuf[2]);
+  }
 };
 
 namespace {
@@ -599,7 +612,6 @@ struct Unit {                               // one strand of one chunk
   int  blk0 = 0, blk1 = 0;                  // its blocks: [blk0, blk1) of the batch's block list
   long long n_total = 0;                    // chunk length (both strands)
   bathhost_stats st{};                      // this unit's share of the counters and stage times
-  HostBuf xbuf[2];
   std::vector<Orf> orfs;                    // of all blocks, block-local coordinates
   std::vector<int> orf_blk;                 // block of each ORF
   std::vector<int> orf_begin;               // [nblocks+1] range of each block's ORFs (index: block - blk0)
@@ -616,7 +628,7 @@ struct Unit {                               // one strand of one chunk
   std::vector<int32_t> fs_st;
   std::vector<int>     fsw;                 // windows that go down the frameshift branch
   std::vector<size_t>  xoff;
-  float *fxr = nullptr, *bxr = nullptr;     // X rows of the Forward / Backward parsers (page-locked buffers owned by the unit)
+  float *fxr = nullptr, *bxr = nullptr;     // X rows of the Forward / Backward parsers (the device context's page-locked buffers; valid until its next unit)
   std::vector<int32_t> st2;
   struct Env { int win, i, j; };
   std::vector<Env> envs;
@@ -633,6 +645,30 @@ struct Unit {                               // one strand of one chunk
   long long goff(const BlockInfo &b) const { return complement ? n_total - (b.coff + b.n) : b.coff; }   // slot coordinate = goff + block-local
   long long start_of(const BlockInfo &b) const { return complement ? b.b1 : b.b0; }                       // dnasq->start
 };
+
+// One batch of bias-filter Forward recursions: on the device when the backend offers bathgpu_bias_forward, else on the host
+// cores with the same operations (Background::hmm_forward_tab).  kind 0: items are ORFs of the selected slot's residue buffer, one
+// score each; kind 1: DNA windows of the selected slot, three scores each (frames 1..3).  host_item(i, out) is the host path for item i.
+static bool bias_on_device(const bathhost_backend &BE)
+{
+  static const bool off = [] { const char *e = getenv("BATHHOST_BIAS_HOST"); return e && atoi(e) != 0; }();
+  return BE.bias_forward != nullptr && !off;
+}
+template <class HostItem>
+int bias_batch(bathhost_search *s, const bathhost_backend &BE, int kind, const std::vector<bathgpu_bias_item> &items, const std::vector<float> &tables,
+               const Background &bg, std::vector<float> &out, HostItem &&host_item)
+{
+  const size_t per = (kind == 1) ? 3 : 1;
+  out.assign(items.size() * per, 0.0f);
+  if (items.empty()) return 0;
+  if (bias_on_device(BE)) {
+    BE_TRY(s, BE.bias_forward(BE.ctx, kind, items.data(), (int) items.size(), tables.data(), (int) (tables.size() / (2 * kKp)), bg.t[1][0], bg.t[1][1],
+                              s->gcode, out.data()), "bathgpu_bias_forward");
+    return 0;
+  }
+  parallel_chunks(items.size(), kind == 1 ? 1 : 64, [&](size_t a, size_t b) { for (size_t i = a; i < b; ++i) host_item(i, &out[i * per]); });
+  return 0;
+}
 
 // stages 1-3 for one unit: ORFs of every block, MSV, bias, Viterbi/SSV windows, local-composition re-check, protein Forward
 int filter_unit(bathhost_search *s, Unit &S, const std::vector<BlockInfo> &blocks)
@@ -718,29 +754,47 @@ int filter_unit(bathhost_search *s, Unit &S, const std::vector<BlockInfo> &block
     struct Pre { uint8_t stage; float filtersc; double P; };       // stage 0: fails F1 on the MSV score, 1: fails after the bias filter, 2: passes
     std::vector<Pre> pre(live.size());
     parallel_chunks(live.size(), 256, [&](size_t ta, size_t tb) {
-      Background lbg = bg;
-      std::vector<uint8_t> lbuf;
       for (size_t t = ta; t < tb; ++t) {
         const Orf &o = orfs[live[t]];
         const float nullsc = null_of[o.n];
-        float seqsc = (usc[t] - nullsc) / kLog2;
+        const float seqsc = (usc[t] - nullsc) / kLog2;
         Pre &r = pre[t];
         r.stage = 0; r.filtersc = nullsc; r.P = 1.0;
         if (seqsc < x1 - 0.01) continue;
-        double P = gumbel_surv(seqsc, ev[EV_MMU], ev[EV_MLAMBDA]);
+        const double P = gumbel_surv(seqsc, ev[EV_MMU], ev[EV_MLAMBDA]);
         if (P > opt.F1) continue;
-        r.stage = 1;
-        if (opt.do_bias) {                                  // (:1657-1663)
-          lbg.set_length(o.n);
-          orf_dsq(o, lbuf);
-          r.filtersc = lbg.filter_score(lbuf.data(), o.n);
-          seqsc = (usc[t] - r.filtersc) / kLog2;
-          P = gumbel_surv(seqsc, ev[EV_MMU], ev[EV_MLAMBDA]);
-          if (P > opt.F1) continue;
-        }
         r.stage = 2; r.P = P;
       }
     });
+    if (opt.do_bias) {                                      // (:1657-1663) one batch over everything that passed F1 on the MSV score
+      std::vector<int> bt;
+      for (size_t t = 0; t < live.size(); ++t) if (pre[t].stage == 2) bt.push_back((int) t);
+      std::vector<bathgpu_bias_item> items(bt.size());
+      std::vector<float> tables(&bg.eo[0][0], &bg.eo[0][0] + 2 * kKp), fsc;
+      for (size_t z = 0; z < bt.size(); ++z) {
+        const Orf &o = orfs[live[bt[z]]];
+        items[z] = bathgpu_bias_item{ o.offset, o.n, 0, Background::p1_for_length(o.n), 0 };
+      }
+      const int rc = bias_batch(s, BE, 0, items, tables, bg, fsc, [&](size_t z, float *out) {
+        std::vector<uint8_t> lbuf;
+        orf_dsq(orfs[live[bt[z]]], lbuf);
+        *out = Background::hmm_forward_tab(tables.data(), items[z].t00, bg.t[1][0], bg.t[1][1], lbuf.data(), items[z].L);
+      });
+      if (rc != 0) return rc;
+      parallel_chunks(bt.size(), 1024, [&](size_t za, size_t zb) {
+        Background lbg = bg;
+        for (size_t z = za; z < zb; ++z) {
+          const size_t t = (size_t) bt[z];
+          const Orf &o = orfs[live[t]];
+          Pre &r = pre[t];
+          lbg.set_length(o.n);
+          r.filtersc = lbg.filter_score_from(fsc[z], o.n);
+          const float seqsc = (usc[t] - r.filtersc) / kLog2;
+          r.P = gumbel_surv(seqsc, ev[EV_MMU], ev[EV_MLAMBDA]);
+          if (r.P > opt.F1) r.stage = 1;
+        }
+      });
+    }
     for (size_t t = 0; t < live.size(); ++t) {
       if (pre[t].stage == 0) continue;
       const Orf &o = orfs[live[t]];
@@ -805,20 +859,31 @@ int filter_unit(bathhost_search *s, Unit &S, const std::vector<BlockInfo> &block
     // per candidate: 0 = fails the Viterbi test, 1 = dropped by the local-composition re-check, 2 = needs a plain Viterbi re-run, 3 = kept.
     // Candidates are independent here (the null model is restored after each in the reference): all host cores, then the counters in order.
     std::vector<uint8_t> verdict(cand.size(), 0);
-    parallel_chunks(cand.size(), 64, [&](size_t ta, size_t tb) {
-      Background lbg = bg;
-      float lcompo[kK];
-      std::vector<uint8_t> lbuf;
+    std::vector<int> slot_of(cand.size(), -1);             // candidates whose local-composition filter score is needed -> their batch item
+    parallel_chunks(cand.size(), 256, [&](size_t ta, size_t tb) {
       for (size_t t = ta; t < tb; ++t) {
         Cand &c = cand[t];
-        const Orf &o = orfs[c.orf];
+        verdict[t] = 3;
         if (c.need_vit) {
           const float seqsc = (c.vfsc - c.filtersc) / kLog2;
           c.P = gumbel_surv(seqsc, ev[EV_VMU], ev[EV_VLAMBDA]);
           if (c.P > opt.F2) { verdict[t] = 0; continue; }
         }
-        bool dropped = false, need_rerun = false;
-        if (opt.do_bias && !wins_of[t].empty()) {
+        if (opt.do_bias && !wins_of[t].empty()) slot_of[t] = 0;
+      }
+    });
+    std::vector<int> bt;
+    for (size_t t = 0; t < cand.size(); ++t) if (slot_of[t] == 0) { slot_of[t] = (int) bt.size(); bt.push_back((int) t); }
+    if (!bt.empty()) {
+      // the filter HMM of each candidate's local composition (p7_pli_ComputeLocalCompo over the nodes its windows cover), one table each
+      std::vector<bathgpu_bias_item> items(bt.size());
+      std::vector<float> tables(bt.size() * 2 * kKp), fsc;
+      parallel_chunks(bt.size(), 64, [&](size_t za, size_t zb) {
+        Background lbg = bg;
+        float lcompo[kK];
+        for (size_t z = za; z < zb; ++z) {
+          const size_t t = (size_t) bt[z];
+          const Orf &o = orfs[cand[t].orf];
           int k_max = wins_of[t][0].k, k_min = k_max - wins_of[t][0].length + 1;
           for (size_t w = 1; w < wins_of[t].size(); ++w) {
             k_max = std::max(k_max, wins_of[t][w].k);
@@ -826,9 +891,25 @@ int filter_unit(bathhost_search *s, Unit &S, const std::vector<BlockInfo> &block
           }
           local_compo(m, lbg, k_min, k_max, lcompo);
           lbg.set_filter(M, lcompo);
+          memcpy(&tables[z * 2 * kKp], &lbg.eo[0][0], sizeof(float) * 2 * kKp);
+          items[z] = bathgpu_bias_item{ o.offset, o.n, (int32_t) z, Background::p1_for_length(o.n), 0 };
+        }
+      });
+      const int rc = bias_batch(s, BE, 0, items, tables, bg, fsc, [&](size_t z, float *out) {
+        std::vector<uint8_t> lbuf;
+        orf_dsq(orfs[cand[(size_t) bt[z]].orf], lbuf);
+        *out = Background::hmm_forward_tab(&tables[z * 2 * kKp], items[z].t00, bg.t[1][0], bg.t[1][1], lbuf.data(), items[z].L);
+      });
+      if (rc != 0) return rc;
+      parallel_chunks(bt.size(), 1024, [&](size_t za, size_t zb) {
+        Background lbg = bg;
+        for (size_t z = za; z < zb; ++z) {
+          const size_t t = (size_t) bt[z];
+          Cand &c = cand[t];
+          const Orf &o = orfs[c.orf];
+          bool dropped = false, need_rerun = false;
           lbg.set_length(o.n);
-          orf_dsq(o, lbuf);
-          const float local_filtersc = lbg.filter_score(lbuf.data(), o.n);
+          const float local_filtersc = lbg.filter_score_from(fsc[z], o.n);
           if (local_filtersc > c.filtersc) {
             c.filtersc = local_filtersc;
             if (c.vfsc == kNegInfF) {
@@ -841,10 +922,10 @@ int filter_unit(bathhost_search *s, Unit &S, const std::vector<BlockInfo> &block
               if (c.P > opt.F2) dropped = true;
             }
           }
+          verdict[t] = dropped ? 1 : need_rerun ? 2 : 3;
         }
-        verdict[t] = dropped ? 1 : need_rerun ? 2 : 3;
-      }
-    });
+      });
+    }
     for (size_t t = 0; t < cand.size(); ++t) {
       if (verdict[t] == 0) { wins_of[t].clear(); continue; }
       S.st.pos_past_vit += (int64_t) orfs[cand[t].orf].n * 3;
@@ -1167,7 +1248,7 @@ int run_batch(bathhost_search *s)
         // another and computed on all host cores; the decisions are then taken in the reference's order
         {
           const int nw = nwin;
-          struct WinPre { int orf_cnt; double P_tot, P_min; float nullsc, filtersc; };
+          struct WinPre { int orf_cnt, k_min, k_max; double P_tot, P_min; float nullsc, filtersc; };
           std::vector<WinPre> pre((size_t) nw);
           auto inside_of = [&](const Orf &o, const DnaWin &dw) {
             return S.complement ? (o.start >= dw.n && o.end <= dw.n + dw.length + 1) : (o.start >= dw.n && o.end <= dw.n + dw.length - 1);
@@ -1176,13 +1257,9 @@ int run_batch(bathhost_search *s)
           const HitIndex &by_id = s->by_id;
           parallel_chunks((size_t) nw, 1, [&](size_t wa, size_t wb) {
             Background lbg = bg;
-            float lcompo[kK];
-            std::vector<uint8_t> wbuf;
             for (size_t w = wa; w < wb; ++w) {
               const int b = S.dwin_blk[w];
-              const BlockInfo &blk = blocks[(size_t) b];
               const DnaWin &dw = S.dwin[w];
-              const uint8_t *wdsq = oriented(seqs[(size_t) blk.seq], blk, S.complement, dw.n - 1, dw.length, wbuf);        // window position p is wdsq[p]
               int orf_cnt = 0, k_min = M, k_max = 0;
               float tot_orfsc = kNegInfF;
               double P_min = std::numeric_limits<double>::infinity();
@@ -1212,24 +1289,69 @@ int run_batch(bathhost_search *s)
                 }
               }
               WinPre &r = pre[w];
-              r.orf_cnt = orf_cnt; r.P_min = P_min;
+              r.orf_cnt = orf_cnt; r.P_min = P_min; r.k_min = k_min; r.k_max = k_max;
               r.P_tot = exp_surv(tot_orfsc / kLog2, ev[EV_FTAU], ev[EV_FLAMBDA]);
-              lbg.set_filter(M, s->compo.data());
               lbg.set_length(dw.length / 3);
               r.nullsc = lbg.fs_null_one(dw.length / 3);
               r.filtersc = r.nullsc;
-              if (opt.do_bias) {
-                r.filtersc = lbg.fs_filter_score(wdsq, dw.length, s->gcode);
-                if (k_min <= k_max) {
-                  local_compo(m, lbg, k_min, k_max, lcompo);
-                  lbg.set_filter(M, lcompo);
-                  lbg.set_length(dw.length / 3);
-                  const float lf = lbg.fs_filter_score(wdsq, dw.length, s->gcode);
-                  if (lf > r.filtersc) r.filtersc = lf;
-                }
-              }
             }
           });
+          if (opt.do_bias) {
+            // p7_bg_fs_FilterScore of every window under the model composition, and under the local composition of the nodes its
+            // ORFs' filter windows cover where there are any (:1432-1440): one batch, three frames per item
+            std::vector<int> item_win, first_item((size_t) nw + 1, 0);
+            for (int w = 0; w < nw; ++w) {
+              first_item[(size_t) w] = (int) item_win.size();
+              item_win.push_back(w);
+              if (pre[(size_t) w].k_min <= pre[(size_t) w].k_max) item_win.push_back(w);
+            }
+            first_item[(size_t) nw] = (int) item_win.size();
+            std::vector<bathgpu_bias_item> items(item_win.size());
+            std::vector<float> tables((item_win.size() - (size_t) nw + 1) * 2 * kKp), fsc;
+            {
+              Background lbg = bg;
+              lbg.set_filter(M, s->compo.data());
+              memcpy(tables.data(), &lbg.eo[0][0], sizeof(float) * 2 * kKp);
+              int ntab = 1;
+              for (int w = 0; w < nw; ++w) {
+                const float t00 = Background::p1_for_length(S.dwin[(size_t) w].length / 3);
+                const int z = first_item[(size_t) w];
+                items[(size_t) z] = bathgpu_bias_item{ S.gw[(size_t) w].start, S.dwin[(size_t) w].length, 0, t00, 0 };
+                if (first_item[(size_t) w + 1] - z == 2) items[(size_t) z + 1] = bathgpu_bias_item{ S.gw[(size_t) w].start, S.dwin[(size_t) w].length, ntab++, t00, 0 };
+              }
+            }
+            parallel_chunks((size_t) nw, 8, [&](size_t wa, size_t wb) {
+              Background lbg = bg;
+              float lcompo[kK];
+              for (size_t w = wa; w < wb; ++w) {
+                if (first_item[w + 1] - first_item[w] != 2) continue;
+                local_compo(m, lbg, pre[w].k_min, pre[w].k_max, lcompo);
+                lbg.set_filter(M, lcompo);
+                memcpy(&tables[(size_t) items[(size_t) first_item[w] + 1].table * 2 * kKp], &lbg.eo[0][0], sizeof(float) * 2 * kKp);
+              }
+            });
+            const int rcb = bias_batch(s, BE, 1, items, tables, bg, fsc, [&](size_t z, float *out) {
+              const int w = item_win[z];
+              const BlockInfo &blk = blocks[(size_t) S.dwin_blk[(size_t) w]];
+              const DnaWin &dw = S.dwin[(size_t) w];
+              std::vector<uint8_t> wbuf, orf((size_t) dw.length + 2);
+              const uint8_t *wdsq = oriented(seqs[(size_t) blk.seq], blk, S.complement, dw.n - 1, dw.length, wbuf);        // window position p is wdsq[p]
+              for (int fr = 1; fr <= 3; ++fr)
+                out[fr - 1] = Background::hmm_forward_tab(&tables[(size_t) items[z].table * 2 * kKp], items[z].t00, bg.t[1][0], bg.t[1][1], orf.data(),
+                                                          Background::frame_residues(wdsq, dw.length, fr, s->gcode, orf.data()));
+            });
+            if (rcb != 0) return rcb;
+            Background lbg = bg;
+            for (int w = 0; w < nw; ++w) {
+              WinPre &r = pre[(size_t) w];
+              const int L = S.dwin[(size_t) w].length;
+              lbg.set_length(L / 3);
+              for (int z = first_item[(size_t) w]; z < first_item[(size_t) w + 1]; ++z) {
+                const float f = lbg.fs_filter_score_from(&fsc[(size_t) z * 3], L);
+                if (z == first_item[(size_t) w] || f > r.filtersc) r.filtersc = f;
+              }
+            }
+          }
           for (int w = 0; w < nw; ++w) {
             const int b = S.dwin_blk[w];
             const int wl = w - S.db(b);                         // the window's index in its block's list: what orfsq->idx holds
@@ -1262,7 +1384,8 @@ int run_batch(bathhost_search *s)
         std::vector<bathgpu_window> gf(S.fsw.size());
         S.xoff.assign(S.fsw.size() + 1, 0);
         for (size_t z = 0; z < S.fsw.size(); ++z) { gf[z] = S.gw[S.fsw[z]]; S.xoff[z + 1] = S.xoff[z] + (size_t) gf[z].L + 1; }
-        S.fxr = S.xbuf[0].get(BE, S.xoff.back() * 6); S.bxr = S.xbuf[1].get(BE, S.xoff.back() * 6); S.st2.resize(S.fsw.size());
+        // the X rows are consumed by the precomputation just below: one pair of page-locked buffers per device context serves all its units
+        S.fxr = s->be_xbuf[(size_t) be][0].get(BE, S.xoff.back() * 6); S.bxr = s->be_xbuf[(size_t) be][1].get(BE, S.xoff.back() * 6); S.st2.resize(S.fsw.size());
         if (!S.fxr || !S.bxr) return fail(s, BATHHOST_EMEM, "host allocation failed");
         std::vector<float> f2(S.fsw.size()), b2(S.fsw.size());
         BE_TRY(s, BE.fs_fwd_bck_xrows(BE.ctx, gf.data(), (int) gf.size(), xfE3, S.fxr, S.bxr, f2.data(), b2.data(), S.st2.data()),

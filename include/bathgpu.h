@@ -254,6 +254,21 @@ int bathgpu_orfs_msv_screen(bathgpu_ctx *ctx, const bathgpu_block *blocks, int n
                             int64_t *norfs_per_block, int64_t *nhits, int64_t *nres);
 int bathgpu_orfs_fetch(bathgpu_ctx *ctx, bathgpu_orf_hit *hits, uint8_t *residues);
 
+/* ---- a5: the bias-composition filter ---------------------------------------------------------------------------------- */
+/* esl_hmm_Forward over the 2-state filter HMM of p7_bg_SetFilter (src/p7_bg.c:449-471), batched: what p7_bg_FilterScore computes
+ * for an ORF (:491-500; call sites src/p7_pipeline.c:1659, :1697) and p7_bg_fs_FilterScore for each of the three reading frames of a
+ * DNA window (:522-573, canonical residues only; call sites src/p7_pipeline.c:1432, :1437).
+ *   kind 0: item = ORF of the selected slot's residue buffer (start = offset of its first residue); out[n]
+ *   kind 1: item = DNA window of the selected slot (start = 1-based coordinate of its first nucleotide); out[3 n], frames 1..3
+ * tables: [ntab][29][2] emission odds e[state][x] / f[x] as esl_hmm_Configure leaves them (table 0 = the model composition, others
+ * the local compositions of p7_pli_ComputeLocalCompo); item.table picks one.  t00 = p1 of the null model at the item's length
+ * (p7_bg_SetLength copies it into the filter HMM), t10/t11 = 1/(L1+1), L1/(L1+1) with L1 = M/8; state priors 0.999 / 0.001.
+ * out = the summed log scale factors (esl_hmm_Forward's score); the caller adds the length terms and combines the frames as the
+ * reference does.  Bit-identical to the host code for the same inputs (same operations in the same order, no fused multiply-adds). */
+typedef struct { int64_t start; int32_t L; int32_t table; float t00; int32_t pad_; } bathgpu_bias_item;
+int bathgpu_bias_forward(bathgpu_ctx *ctx, int kind, const bathgpu_bias_item *items, int n, const float *tables, int ntab,
+                         float t10, float t11, const uint8_t gcode[64], float *out);
+
 /* ---- f2: the standard-translation branch over ORFs ------------------------ */
 /* p7_ForwardParser + p7_BackwardParser over ORFs of the uploaded residue buffer, X rows kept (what oxf_holder[i] and
  * pli->oxb hold at src/p7_pipeline.c:1492-1495 / :1762-1764): fwd_xrows / bck_xrows = {E,N,J,B,C,SCALE} x (L+1) per ORF,

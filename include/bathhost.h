@@ -126,6 +126,9 @@ typedef struct {
   int (*revcomp_slot)(void *ctx, int src, int dst);
   void *(*host_alloc)(size_t bytes);          /* optional (may be NULL): page-locked host memory for result buffers */
   void (*host_free)(void *p);
+  /* optional (may be NULL: the host library then runs the same recursion on the host cores): bathgpu_bias_forward */
+  int (*bias_forward)(void *ctx, int kind, const void *items, int n, const float *tables, int ntab, float t10, float t11,
+                      const uint8_t gcode[64], float *out);
 } bathhost_backend;
 
 /* 0 / unset fields take bathsearch's defaults (src/p7_pipeline.c:145-214; src/bathsearch.c:94) */

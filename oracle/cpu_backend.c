@@ -611,3 +611,72 @@ int bo_backend_orfs_fetch(void *ctx, void *hits, uint8_t *residues)
 /* plain heap memory: the CPU backend has no device link to feed */
 void *bo_backend_host_alloc(size_t bytes) { return malloc(bytes); }
 void  bo_backend_host_free(void *p) { free(p); }
+
+/* ---- a5: the bias-composition filter (bathgpu_bias_forward) ---------------------------------------------------------------
+ * esl_hmm_Forward over the 2-state filter HMM that p7_bg_SetFilter configures (src/p7_bg.c:449-471), as p7_bg_FilterScore runs it
+ * on an ORF (:491-500) and p7_bg_fs_FilterScore on the three reading frames of a DNA window (:522-573).  Easel is absent from
+ * /root/reference (INSTALL:6-8), so esl_hmm_Forward is restated from Easel's published esl_hmm.c: row i holds
+ * fwd[i][k] = e_k(x_i) * sum_m fwd[i-1][m] t[m][k] divided by the row maximum, sc[i] = log(max), the termination row adds
+ * log(sum_m fwd[L][m] t[m][E]) with t[m][E] = 1, and the score is the float sum of sc[] in row order. */
+static float bias_hmm_forward(const float *eo, float t00, float t10, float t11, const uint8_t *x, int L)
+{
+  float t[2][2], pi[2] = { 0.999, 0.001 }, prev[2], cur[2], max, logsc = 0.0f, last;
+  int   i, k, m;
+  if (L == 0) return 0.0f;
+  t[0][0] = t00; t[0][1] = 1.0f - t00; t[1][0] = t10; t[1][1] = t11;
+  max = 0.0;
+  for (k = 0; k < 2; k++) { prev[k] = eo[2 * x[0] + k] * pi[k]; if (prev[k] > max) max = prev[k]; }
+  for (k = 0; k < 2; k++) prev[k] /= max;
+  logsc += (float) log(max);
+  for (i = 1; i < L; i++) {
+    max = 0.0;
+    for (k = 0; k < 2; k++) {
+      cur[k] = 0.0;
+      for (m = 0; m < 2; m++) cur[k] += prev[m] * t[m][k];
+      cur[k] *= eo[2 * x[i] + k];
+      if (cur[k] > max) max = cur[k];
+    }
+    for (k = 0; k < 2; k++) prev[k] = cur[k] / max;
+    logsc += (float) log(max);
+  }
+  last = 0.0;
+  for (m = 0; m < 2; m++) last += prev[m] * 1.0f;
+  logsc += (float) log(last);
+  return logsc;
+}
+
+typedef struct { int kind; const bathgpu_bias_item *items; const float *tables; float t10, t11; const uint8_t *gcode; float *out; } bias_job;
+static void bias_item_fn(bo_backend *b, void *arg, int it)
+{
+  bias_job *j = arg;
+  const bathgpu_bias_item *d = &j->items[it];
+  const float *eo = j->tables + (size_t) d->table * 58;
+  if (j->kind == 0) j->out[it] = bias_hmm_forward(eo, d->t00, j->t10, j->t11, b->res[b->cur] + d->start, d->L);
+  else {
+    const uint8_t *dna = b->dsq[b->cur] + d->start - 1;          /* window position p is dna[p] */
+    uint8_t *orf = malloc((size_t) d->L + 2);
+    int f, i, n;
+    for (f = 1; f <= 3; f++) {
+      n = 0;
+      for (i = f; i <= d->L - 2; i += 3) {
+        uint8_t a = dna[i], c = dna[i + 1], g = dna[i + 2], aa;
+        if (a >= 4 || c >= 4 || g >= 4) continue;               /* a codon with a degenerate nucleotide is X here, as in the ORF finder */
+        aa = j->gcode[16 * a + 4 * c + g];
+        if (aa < 20) orf[n++] = aa;
+      }
+      j->out[3 * it + f - 1] = bias_hmm_forward(eo, d->t00, j->t10, j->t11, orf, n);
+    }
+    free(orf);
+  }
+}
+int bo_backend_bias_forward(void *ctx, int kind, const void *items, int n, const float *tables, int ntab, float t10, float t11,
+                            const uint8_t gcode[64], float *out)
+{
+  bo_backend *b = ctx;
+  bias_job j;
+  if (!b || (kind != 0 && kind != 1) || n < 0 || ntab < 1) return BO_EINVAL;
+  if ((kind == 0 && !b->res[b->cur]) || (kind == 1 && !b->dsq[b->cur])) return BO_EINVAL;
+  j.kind = kind; j.items = items; j.tables = tables; j.t10 = t10; j.t11 = t11; j.gcode = gcode; j.out = out;
+  parallel_for(b, n, bias_item_fn, &j);
+  return BO_OK;
+}
