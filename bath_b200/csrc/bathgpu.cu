@@ -24,11 +24,18 @@
 #include "bias_filter.cuh"
 #include "microbench.cuh"
 #include "launch.h"
+#include <chrono>
 
 using namespace bathgpu;
 
 namespace {
 
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync): a buffer that has to grow hands its old block back to
+// the pool and takes a larger one without the device-wide synchronisation of cudaFree / cudaMalloc -- with several contexts per GPU
+// those stalled every context's stage calls whenever one of them outgrew a workspace (3 s of 1.2 s x 8 contexts on the config-4 search
+// leg, profiles/r02d_search_alloc_trace.md).  The pool keeps what is freed (release threshold = no limit, set in bathgpu_create),
+// so the blocks a context lets go are what the next one's growth is served from.
+static thread_local cudaStream_t tl_alloc_stream = nullptr;      // the stream of the context the calling thread is working for
 struct DevBuf {
   void  *p = nullptr;
   size_t cap = 0;
@@ -36,13 +43,24 @@ struct DevBuf {
   DevBuf(const DevBuf &) = delete;
   DevBuf &operator=(const DevBuf &) = delete;
   ~DevBuf() { release(); }          // bathgpu_destroy selects the context's device before the context goes away
-  int reserve(size_t bytes) {
+  int reserve(size_t bytes) { return bytes <= cap ? BATHGPU_OK : reserve_exact(bytes + bytes / 2 + 256); }
+  int reserve_exact(size_t bytes) {
     if (bytes <= cap) return BATHGPU_OK;
-    if (p) cudaFree(p);
+    static const bool trace = getenv("BATHGPU_TRACE") != nullptr;      // tuning aid: slow (re)allocations on stderr
+    const auto t0 = std::chrono::steady_clock::now();
+    const size_t old = cap;
+    cudaStream_t st = tl_alloc_stream;
+    if (p) cudaFreeAsync(p, st);
     p = nullptr; cap = 0;
-    size_t want = bytes + bytes / 4 + 256;
-    if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return BATHGPU_EMEM; }
+    const size_t want = (bytes + 511) & ~(size_t)511;
+    if (cudaMallocAsync(&p, want, st) != cudaSuccess) { cudaGetLastError(); p = nullptr; return BATHGPU_EMEM; }
+    // the block is used from the context's other streams as well (chunked uploads): make the allocation complete before anyone sees it
+    if (cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); return BATHGPU_EMEM; }
     cap = want;
+    if (trace) {
+      const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      if (ms >= 1.0) fprintf(stderr, "[bathgpu] device buffer %zu -> %zu bytes: %.2f ms\n", old, want, ms);
+    }
     return BATHGPU_OK;
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -124,6 +142,31 @@ static int fail(bathgpu_ctx *ctx, int code, const char *fmt, ...)
        if (e_ != cudaSuccess) { cudaGetLastError();                                              \
          return fail(ctx, BATHGPU_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
 
+// every stage call starts here: the context's device becomes current and its stream the one device buffers are (re)allocated on
+static cudaError_t enter(bathgpu_ctx *ctx)
+{
+  tl_alloc_stream = ctx->stream;
+  return cudaSetDevice(ctx->device);
+}
+
+// The per-envelope matrices (posterior / optimal-accuracy cells of fs_domain.cuh and orf_domain.cuh, the Forward matrix of the
+// multi-domain branch) are the context's one large workspace.  It is taken at its full budget the first time it is needed and the
+// stage calls cut their batches to fit it, so it never has to grow in the middle of a search whatever the profile length
+// (growing a 0.4 GB block to 0.8 GB costs ~0.1 s of driver time; 30 of those fell into the third profile of the config-4 search).
+// BATHGPU_MATRIX_MB overrides the budget (default 2048).
+static size_t matrix_budget()
+{
+  static const size_t b = [] { const char *e = getenv("BATHGPU_MATRIX_MB"); const long long v = e ? atoll(e) : 0; return (size_t)(v > 0 ? v : 2048) << 20; }();
+  return b;
+}
+static int reserve_matrices(bathgpu_ctx *ctx, size_t pp_bytes, size_t oa_bytes)
+{
+  const size_t b = matrix_budget();
+  if (ctx->dpp.reserve_exact(std::max(pp_bytes, b / 10 * 7 + (1u << 20))) != BATHGPU_OK) return BATHGPU_EMEM;
+  if (oa_bytes && ctx->doa.reserve_exact(std::max(oa_bytes, b / 10 * 3 + (1u << 20))) != BATHGPU_OK) return BATHGPU_EMEM;
+  return BATHGPU_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 extern "C" int bathgpu_create(int device, bathgpu_ctx **ret_ctx)
 {
@@ -142,6 +185,14 @@ extern "C" int bathgpu_create(int device, bathgpu_ctx **ret_ctx)
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
     cudaGetLastError(); delete ctx; return BATHGPU_ECUDA;
   }
+  {                                // the pool never hands memory back to the driver on its own: what one stage frees the next one reuses
+    cudaMemPool_t pool;
+    unsigned long long keep = ~0ULL;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) != cudaSuccess || cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess) {
+      cudaGetLastError(); bathgpu_destroy(ctx); return BATHGPU_ECUDA;
+    }
+  }
+  tl_alloc_stream = ctx->stream;
   ctx->slot_at(1);                 // slots 0 and 1 exist from the start
   *ret_ctx = ctx;
   return BATHGPU_OK;
@@ -178,7 +229,7 @@ extern "C" int bathgpu_last_stage_timing(const bathgpu_ctx *ctx, float *ms, int 
   return BATHGPU_OK;
 }
 
-// Page-locking memory costs about a millisecond per megabyte, so freed buffers are kept (up to 2 GiB in all) and handed out again.
+// Page-locking memory costs about a millisecond per megabyte, so freed buffers are kept (up to 8 GiB in all) and handed out again.
 namespace {
 struct PinnedCache {
   std::mutex mu;
@@ -192,12 +243,17 @@ PinnedCache g_pinned;
 
 extern "C" void *bathgpu_host_alloc(size_t bytes)
 {
-  if (bytes == 0) bytes = 1;
+  // sizes are rounded up to a power of two (64 KiB at least), so that a buffer given back is the size the next request asks for:
+  // page-locking blocks every other thread's CUDA calls while it runs, and a search whose staging buffers missed the cache by a few
+  // bytes stalled all its device contexts for 30-100 ms at a time
+  size_t want = (size_t)64 << 10;
+  while (want < bytes) want <<= 1;
+  bytes = want;
   std::lock_guard<std::mutex> lock(g_pinned.mu);
   int best = -1;
   for (int i = 0; i < (int)g_pinned.idle.size(); ++i)
     if (g_pinned.idle[i].second >= bytes && (best < 0 || g_pinned.idle[i].second < g_pinned.idle[best].second)) best = i;
-  if (best >= 0 && g_pinned.idle[best].second <= 2 * bytes + (1u << 20)) {
+  if (best >= 0 && g_pinned.idle[best].second <= 4 * bytes) {
     auto b = g_pinned.idle[best];
     g_pinned.idle.erase(g_pinned.idle.begin() + best);
     g_pinned.idle_bytes -= b.second;
@@ -218,7 +274,7 @@ extern "C" void bathgpu_host_free(void *p)
     if (g_pinned.live[i].first == p) {
       auto b = g_pinned.live[i];
       g_pinned.live.erase(g_pinned.live.begin() + i);
-      if (g_pinned.idle_bytes + b.second <= ((size_t)2 << 30)) { g_pinned.idle.push_back(b); g_pinned.idle_bytes += b.second; }
+      if (g_pinned.idle_bytes + b.second <= ((size_t)8 << 30)) { g_pinned.idle.push_back(b); g_pinned.idle_bytes += b.second; }
       else cudaFreeHost(p);
       return;
     }
@@ -228,7 +284,7 @@ extern "C" void bathgpu_host_free(void *p)
 extern "C" int bathgpu_measure_fp32_peak(bathgpu_ctx *ctx, double *tflops, double *sm_mhz_effective)
 {
   if (!ctx || !tflops) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_measure_fp32_peak");
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   if (ctx->scratch.reserve(1 << 20) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
   const int blocks = ctx->prop.multiProcessorCount * 8, threads = 256, iters = 4096;
   const double flop = (double)blocks * threads * (double)iters * 8.0 * 16.0 * 2.0;
@@ -274,7 +330,7 @@ extern "C" int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int n
   if (nrows != want_rows)           return fail(ctx, BATHGPU_EINVAL, "nrows %d != %d for %d codon lengths", nrows, want_rows, which);
   const int J = choose_J(M);
   if (J == 0) return fail(ctx, BATHGPU_EINVAL, "model length %d exceeds the single-warp kernels' limit (%d)", M, 32 * 32);
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
 
   FsProfileImage &im = (which == 3) ? ctx->fs3 : ctx->fs5;
   im.loaded = false;
@@ -634,7 +690,7 @@ extern "C" int bathgpu_select_slot(bathgpu_ctx *ctx, int slot)
 extern "C" int bathgpu_upload_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_t n)
 {
   if (!ctx || !dsq || n < 1) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_upload_block");
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   const long long nwords = (n + 8 + 7) / 8 + 24;     // kernels prefetch up to ~100 nt past a window
   if (ctx->S().dna_bytes.reserve((size_t)n + 2) != BATHGPU_OK || ctx->S().dna4.reserve((size_t)nwords * 4) != BATHGPU_OK)
     return fail(ctx, BATHGPU_EMEM, "device allocation failed for a %lld-nt block", (long long)n);
@@ -667,7 +723,7 @@ extern "C" int bathgpu_revcomp_slot(bathgpu_ctx *ctx, int src, int dst)
   ctx->slot_at(std::max(src, dst));
   TargetSlot &A = *ctx->slot[src], &B = *ctx->slot[dst];
   if (A.block_n == 0) return fail(ctx, BATHGPU_EINVAL, "no block uploaded in slot %d", src);
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   const long long n = A.block_n;
   const long long nwords = (n + 8 + 7) / 8 + 24;
   if (B.dna_bytes.reserve((size_t)n + 2) != BATHGPU_OK || B.dna4.reserve((size_t)nwords * 4) != BATHGPU_OK)
@@ -694,7 +750,7 @@ extern "C" int bathgpu_fs_fwd_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_
   for (int w = 0; w < nwin; ++w)
     if (wins[w].L < 3 || wins[w].start < 1 || wins[w].start + wins[w].L - 1 > n)
       return fail(ctx, BATHGPU_EINVAL, "window %d (start %lld, L %d) is outside the block (n=%lld) or shorter than 3", w, (long long)wins[w].start, wins[w].L, (long long)n);
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   if (!ctx->copy_stream) {
     CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
@@ -822,7 +878,7 @@ extern "C" int bathgpu_stage_windows(bathgpu_ctx *ctx, const bathgpu_window *win
   if (ctx->S().block_n == 0)      return fail(ctx, BATHGPU_EINVAL, "no block uploaded");
   int st = check_windows(ctx, wins, n);
   if (st != BATHGPU_OK) return st;
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   static_assert(sizeof(WindowDesc) == sizeof(bathgpu_window), "descriptor layouts must agree");
   if (ctx->wins.reserve((size_t)n * sizeof(WindowDesc)) != BATHGPU_OK || ctx->fwdsc.reserve((size_t)n * 4) != BATHGPU_OK ||
       ctx->status.reserve((size_t)n * 4) != BATHGPU_OK || ctx->counter.reserve(64) != BATHGPU_OK)
@@ -838,7 +894,7 @@ extern "C" int bathgpu_fs_fwd_staged(bathgpu_ctx *ctx, const float xfE[2])
   if (!ctx || !xfE)          return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fs_fwd_staged");
   if (!ctx->fs3.loaded)      return fail(ctx, BATHGPU_EINVAL, "3-codon profile not loaded");
   if (ctx->nstaged < 1)      return fail(ctx, BATHGPU_EINVAL, "no windows staged");
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   const FsProfileImage &im = ctx->fs3;
   FsParserArgs a{};
   a.emis = im.emis_fwd.as<float>(); a.cellc = im.cellc.as<float>(); a.dna4 = ctx->S().dna4.as<uint32_t>();
@@ -860,7 +916,7 @@ extern "C" int bathgpu_fs_fwd_staged(bathgpu_ctx *ctx, const float xfE[2])
 extern "C" int bathgpu_fetch_scores(bathgpu_ctx *ctx, float *fwdsc, int32_t *status, int n)
 {
   if (!ctx || n < 1 || n > ctx->nstaged) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fetch_scores");
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   if (fwdsc)  CUDA_TRY(ctx, cudaMemcpyAsync(fwdsc,  ctx->fwdsc.p,  (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (status) CUDA_TRY(ctx, cudaMemcpyAsync(status, ctx->status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -982,7 +1038,7 @@ extern "C" int bathgpu_fs_bck_decode(bathgpu_ctx *ctx, const bathgpu_window *win
   if (st != BATHGPU_OK) return st;
   for (int w = 0; w < n; ++w)
     if (wins[w].L < 5) return fail(ctx, BATHGPU_EINVAL, "window %d: the Backward parser needs L >= 5 (fwdback_fs.c:600)", w);
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   ctx->last_ms = 0.f; ctx->last_launches = 0;
   // chunks bounded by X-row memory: 68 B per row of scratch
   const size_t max_rows = (size_t)16 << 20;
@@ -1013,7 +1069,7 @@ extern "C" int bathgpu_fs_fwd_bck_xrows(bathgpu_ctx *ctx, const bathgpu_window *
   if (st != BATHGPU_OK) return st;
   for (int w = 0; w < n; ++w)
     if (wins[w].L < 5) return fail(ctx, BATHGPU_EINVAL, "window %d: the Backward parser needs L >= 5 (fwdback_fs.c:600)", w);
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   ctx->last_ms = 0.f; ctx->last_launches = 0;
   const size_t max_rows = (size_t)16 << 20;
   int w0 = 0;
@@ -1035,7 +1091,7 @@ extern "C" int bathgpu_fs_fetch_xrows(bathgpu_ctx *ctx, int which, float *out, i
 {
   if (!ctx || !out || nrows < 1 || nrows > ctx->xrows || (which != 0 && which != 1))
     return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fs_fetch_xrows");
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   const DevBuf &b = which ? ctx->bxmx : ctx->fxmx;
   CUDA_TRY(ctx, cudaMemcpyAsync(out, b.p, (size_t)nrows * 24, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1078,8 +1134,7 @@ static int domains_chunk(bathgpu_ctx *ctx, const bathgpu_envelope *envs, int n, 
 
   if (ctx->envs.reserve((size_t)n * sizeof(EnvelopeDesc)) != BATHGPU_OK || ctx->xoff.reserve((size_t)(n + 1) * 8) != BATHGPU_OK ||
       ctx->dtoff.reserve((size_t)(n + 1) * 8) != BATHGPU_OK || ctx->dtlen.reserve((size_t)n * 4) != BATHGPU_OK ||
-      ctx->dpp.reserve((rows + 1) * kPPCells * mpad * 4) != BATHGPU_OK ||        /* + 1: the optimal-accuracy sweep prefetches one row ahead */
-      ctx->doa.reserve(rows * kOACells * mpad * 4) != BATHGPU_OK ||
+      reserve_matrices(ctx, (rows + 1) * kPPCells * mpad * 4, rows * kOACells * mpad * 4) != BATHGPU_OK ||        /* + 1: the optimal-accuracy sweep prefetches one row ahead */
       ctx->dfx.reserve(rows * 24) != BATHGPU_OK || ctx->dppx.reserve(rows * 24) != BATHGPU_OK || ctx->doax.reserve(rows * 24) != BATHGPU_OK ||
       ctx->dlsf.reserve(rows * 4) != BATHGPU_OK || ctx->dfw.reserve((size_t)n * 4) != BATHGPU_OK || ctx->dbk.reserve((size_t)n * 4) != BATHGPU_OK ||
       ctx->doasc.reserve((size_t)n * 4) != BATHGPU_OK || ctx->dnull2.reserve((size_t)n * 29 * 4) != BATHGPU_OK ||
@@ -1154,11 +1209,11 @@ extern "C" int bathgpu_fs_domains(bathgpu_ctx *ctx, const bathgpu_envelope *envs
     if (envs[e].L < 6 || envs[e].start < 1 || envs[e].start + envs[e].L - 1 > ctx->S().block_n)
       return fail(ctx, BATHGPU_EINVAL, "envelope %d (start %lld, L %d) is outside the uploaded block (n=%lld) or shorter than 6",
                   e, (long long)envs[e].start, envs[e].L, (long long)ctx->S().block_n);
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   ctx->last_ms = 0.f; ctx->last_launches = 0;
   // chunks bounded by matrix memory: (7 + 3) * mpad * 4 B per row
-  const size_t row_bytes = (size_t)(kPPCells + kOACells) * ctx->fs5.mpad * 4 + 80;
-  const size_t max_rows = std::max<size_t>(((size_t)8 << 30) / row_bytes, 4096);
+  const size_t row_bytes = (size_t)(kPPCells + kOACells) * ctx->fs5.mpad * 4;
+  const size_t max_rows = std::max<size_t>(matrix_budget() / row_bytes - 1, 4096);
   int64_t steps_used = 0;
   int e0 = 0;
   while (e0 < n) {
@@ -1227,13 +1282,13 @@ extern "C" int bathgpu_fs_forward_matrices(bathgpu_ctx *ctx, const bathgpu_envel
     total += regs[e].L + 1;
   }
   if (!scores_only && total > max_rows) return fail(ctx, BATHGPU_EINVAL, "matrix buffer too small: %lld rows needed, %lld given", (long long)total, (long long)max_rows);
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   const FsProfileImage &im = ctx->fs5;
   const int M = im.M, mpad = im.mpad;
   ctx->last_ms = 0.f; ctx->last_launches = 0;
   // chunks bounded by device memory: 8 stored cells + 8 exported per node and row
   const size_t row_bytes = (size_t)(kPPCells + 1) * mpad * 4 + (size_t)(M + 1) * 32 + 32;
-  const size_t cap_rows = std::max<size_t>(((size_t)4 << 30) / row_bytes, 8192);
+  const size_t cap_rows = std::max<size_t>(std::min<size_t>(((size_t)4 << 30) / row_bytes, matrix_budget() / 10 * 7 / ((size_t)kPPCells * mpad * 4)), 8192);
   int e0 = 0;
   int64_t row0 = 0;
   while (e0 < n) {
@@ -1244,7 +1299,7 @@ extern "C" int bathgpu_fs_forward_matrices(bathgpu_ctx *ctx, const bathgpu_envel
     std::vector<long long> xoff(m + 1, 0);
     for (int e = 0; e < m; ++e) xoff[e + 1] = xoff[e] + regs[e0 + e].L + 1;
     if (ctx->envs.reserve((size_t)m * sizeof(EnvelopeDesc)) != BATHGPU_OK || ctx->xoff.reserve((size_t)(m + 1) * 8) != BATHGPU_OK ||
-        ctx->dpp.reserve(rows * kPPCells * mpad * 4) != BATHGPU_OK || ctx->ddcell.reserve(rows * mpad * 4) != BATHGPU_OK ||
+        reserve_matrices(ctx, rows * kPPCells * mpad * 4, 0) != BATHGPU_OK || ctx->ddcell.reserve(rows * mpad * 4) != BATHGPU_OK ||
         ctx->dmxout.reserve(scores_only ? 32 : rows * (size_t)(M + 1) * 32) != BATHGPU_OK || ctx->dfx.reserve(rows * 24) != BATHGPU_OK ||
         ctx->dlsf.reserve(rows * 4) != BATHGPU_OK || ctx->dfw.reserve((size_t)m * 4) != BATHGPU_OK ||
         ctx->dstat.reserve((size_t)m * 4) != BATHGPU_OK || ctx->counter.reserve(64) != BATHGPU_OK)
@@ -1288,7 +1343,7 @@ extern "C" int bathgpu_fs_forward_matrices(bathgpu_ctx *ctx, const bathgpu_envel
 extern "C" int bathgpu_fs_fetch_domain_matrices(bathgpu_ctx *ctx, int e, float *pp, float *oa, float *ppx, float *oax)
 {
   if (!ctx || e < 0 || e >= (int)ctx->dom_L.size()) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fs_fetch_domain_matrices");
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   const FsProfileImage &im = ctx->fs5;
   const int M = im.M, mpad = im.mpad, J = im.J, L = ctx->dom_L[e];
   const size_t r0 = (size_t)ctx->dom_xoff[e], nr = (size_t)L + 1;
@@ -1330,7 +1385,7 @@ extern "C" int bathgpu_load_filter_profile(bathgpu_ctx *ctx, const bathgpu_filte
   const int M = prm->M, ld = M + 1;
   if (M > 1024) return fail(ctx, BATHGPU_EINVAL, "model length %d exceeds the single-warp kernels' limit (1024)", M);
   if (prm->cpu_lanes_u8 < 1 || prm->cpu_lanes_i16 < 1) return fail(ctx, BATHGPU_EINVAL, "cpu lane counts must be positive");
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   ctx->flt_loaded = false;
   ctx->flt = *prm;
   int W = (M + 127) / 128, P = (M + 63) / 64;
@@ -1393,7 +1448,7 @@ extern "C" int bathgpu_load_filter_profile(bathgpu_ctx *ctx, const bathgpu_filte
 extern "C" int bathgpu_upload_orfs(bathgpu_ctx *ctx, const uint8_t *residues, int64_t n)
 {
   if (!ctx || !residues || n < 1) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_upload_orfs");
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   if (ctx->S().residues.reserve((size_t)n + 64) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->S().residues.p, residues, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1479,7 +1534,7 @@ static int finish_filter(bathgpu_ctx *ctx, int n, float *sc, int32_t *status, in
 extern "C" int bathgpu_msv_orfs(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n, float *sc, int32_t *status)
 {
   if (!ctx || !orfs || n < 1 || !sc || !status) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_msv_orfs");
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   int st = stage_orfs(ctx, orfs, n, 0);
   if (st != BATHGPU_OK) return st;
   FilterArgs a = filter_args(ctx, n, 0);
@@ -1491,7 +1546,7 @@ extern "C" int bathgpu_msv_orfs(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n
 extern "C" int bathgpu_ssv_windows(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n, bathgpu_orf_window *wins, int max_wins, int *nwins)
 {
   if (!ctx || !orfs || n < 1 || !wins || max_wins < 1 || !nwins) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_ssv_windows");
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   int st = stage_orfs(ctx, orfs, n, max_wins);
   if (st != BATHGPU_OK) return st;
   FilterArgs a = filter_args(ctx, n, max_wins);
@@ -1508,7 +1563,7 @@ extern "C" int bathgpu_vit_orfs(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n
   bool any = false;
   for (int o = 0; o < n; ++o) any = any || (orfs[o].flags & 1);
   if (any && (!wins || max_wins < 1 || !nwins)) return fail(ctx, BATHGPU_EINVAL, "window output buffers are required when any ORF asks for windows");
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   int st = stage_orfs(ctx, orfs, n, any ? max_wins : 0);
   if (st != BATHGPU_OK) return st;
   FilterArgs a = filter_args(ctx, n, any ? max_wins : 0);
@@ -1528,7 +1583,7 @@ extern "C" int bathgpu_fwd_orfs(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n
   for (int o = 0; o < n; ++o)
     if (orfs[o].L < 1 || orfs[o].offset < 0 || orfs[o].offset + orfs[o].L > ctx->S().nres)
       return fail(ctx, BATHGPU_EINVAL, "ORF %d is outside the uploaded residues", o);
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   if (ctx->orfs.reserve((size_t)n * sizeof(OrfDesc)) != BATHGPU_OK || ctx->fsc.reserve((size_t)n * 4) != BATHGPU_OK ||
       ctx->fst.reserve((size_t)n * 4) != BATHGPU_OK || ctx->counter.reserve(64) != BATHGPU_OK)
     return fail(ctx, BATHGPU_EMEM, "device allocation failed");
@@ -1580,7 +1635,7 @@ static int orf_chunk(bathgpu_ctx *ctx, const EnvelopeDesc *envs, int n, const fl
       ctx->dstat.reserve((size_t)n * 4) != BATHGPU_OK || ctx->counter.reserve(64) != BATHGPU_OK)
     return fail(ctx, BATHGPU_EMEM, "device allocation failed for %d ORFs (%zu rows)", n, rows);
   if (full && (ctx->dtoff.reserve((size_t)(n + 1) * 8) != BATHGPU_OK || ctx->dtlen.reserve((size_t)n * 4) != BATHGPU_OK ||
-               ctx->dpp.reserve(rows * kPPCellsP * mpad * 4) != BATHGPU_OK || ctx->doa.reserve(rows * kOACells * mpad * 4) != BATHGPU_OK ||
+               reserve_matrices(ctx, rows * kPPCellsP * mpad * 4, rows * kOACells * mpad * 4) != BATHGPU_OK ||
                ctx->dppx.reserve(rows * 24) != BATHGPU_OK || ctx->doax.reserve(rows * 24) != BATHGPU_OK ||
                ctx->doasc.reserve((size_t)n * 4) != BATHGPU_OK || ctx->dnull2.reserve((size_t)n * 29 * 4) != BATHGPU_OK ||
                ctx->dsteps.reserve((size_t)toff[n] * sizeof(TraceStep)) != BATHGPU_OK))
@@ -1669,7 +1724,7 @@ extern "C" int bathgpu_orf_fwd_bck_xrows(bathgpu_ctx *ctx, const bathgpu_orf *or
     ed[o].pmove = (2.0f + nj) / ((float)orfs[o].L + 2.0f + nj);      // p7_oprofile_ReconfigRestLength (p7_oprofile.c:1312-1313)
     ed[o].ploop = 1.0f - ed[o].pmove;
   }
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   ctx->last_ms = 0.f; ctx->last_launches = 0;
   const size_t max_rows = (size_t)16 << 20;
   int o0 = 0;
@@ -1698,10 +1753,10 @@ extern "C" int bathgpu_orf_domains(bathgpu_ctx *ctx, const bathgpu_envelope *env
     if (envs[e].L < 1 || envs[e].start < 0 || envs[e].start + envs[e].L > ctx->S().nres)
       return fail(ctx, BATHGPU_EINVAL, "envelope %d (offset %lld, L %d) is outside the uploaded residues (n=%lld)",
                   e, (long long)envs[e].start, envs[e].L, (long long)ctx->S().nres);
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   ctx->last_ms = 0.f; ctx->last_launches = 0;
-  const size_t row_bytes = (size_t)(kPPCellsP + kOACells) * orf_image(ctx)->mpad * 4 + 100;
-  const size_t max_rows = std::max<size_t>(((size_t)4 << 30) / row_bytes, 4096);
+  const size_t row_bytes = (size_t)kOACells * orf_image(ctx)->mpad * 4 / 3 * 10;      // the optimal-accuracy cells have 3/10 of the workspace
+  const size_t max_rows = std::max<size_t>(matrix_budget() / row_bytes - 1, 4096);
   int64_t steps_used = 0;
   int e0 = 0;
   while (e0 < n) {
@@ -1721,7 +1776,7 @@ extern "C" int bathgpu_orf_domains(bathgpu_ctx *ctx, const bathgpu_envelope *env
 extern "C" int bathgpu_orf_fetch_domain_matrices(bathgpu_ctx *ctx, int e, float *pp, float *oa, float *ppx, float *oax)
 {
   if (!ctx || e < 0 || e >= (int)ctx->dom_L.size() || !orf_image(ctx)) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_orf_fetch_domain_matrices");
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   const FsProfileImage &im = *orf_image(ctx);
   const int M = im.M, mpad = im.mpad, J = im.J, L = ctx->dom_L[e];
   const size_t r0 = (size_t)ctx->dom_xoff[e], nr = (size_t)L + 1;
@@ -1761,7 +1816,7 @@ extern "C" int bathgpu_bias_forward(bathgpu_ctx *ctx, int kind, const bathgpu_bi
     if (kind == 0 ? (d.start < 0 || d.start + d.L > S.nres) : (d.start < 1 || d.start + d.L - 1 > S.block_n))
       return fail(ctx, BATHGPU_EINVAL, "bias item %d (start %lld, L %d) is outside the resident %s", i, (long long)d.start, d.L, kind == 0 ? "residues" : "sequence");
   }
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   const int per = (kind == 1) ? 3 : 1;
   if (ctx->b_items.reserve((size_t)n * sizeof(BiasItem)) != BATHGPU_OK || ctx->b_tables.reserve((size_t)ntab * 58 * 4) != BATHGPU_OK ||
       ctx->b_out.reserve((size_t)n * per * 4) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
@@ -1815,7 +1870,7 @@ extern "C" int bathgpu_orfs_msv_screen(bathgpu_ctx *ctx, const bathgpu_block *bl
   ctx->o_nhits = 0; ctx->o_nres = 0; S.nres = 0;
   if (norfs_per_block) for (int b = 0; b < nblocks; ++b) norfs_per_block[b] = 0;
   if (ntiles == 0) return BATHGPU_OK;
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   const long long n = S.block_n;
   if (S.cls.reserve((size_t)n + 64) != BATHGPU_OK || ctx->o_tiles.reserve((size_t)ntiles * 8) != BATHGPU_OK || ctx->o_cnt.reserve((size_t)ntiles * 4) != BATHGPU_OK ||
       ctx->o_base.reserve((size_t)ntiles * 8) != BATHGPU_OK || ctx->o_blocks.reserve((size_t)nblocks * sizeof(BlockDesc)) != BATHGPU_OK ||
@@ -1890,7 +1945,7 @@ extern "C" int bathgpu_orfs_fetch(bathgpu_ctx *ctx, bathgpu_orf_hit *hits, uint8
 {
   if (!ctx || (ctx->o_nhits > 0 && (!hits || !residues))) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_orfs_fetch");
   if (ctx->o_nhits == 0) return BATHGPU_OK;
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, enter(ctx));
   CUDA_TRY(ctx, cudaMemcpyAsync(hits, ctx->o_hits.p, (size_t)ctx->o_nhits * sizeof(OrfHit), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(residues, ctx->S().residues.p, (size_t)ctx->o_nres, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

@@ -232,7 +232,8 @@ struct HostBuf {
   {
     if (nfloats <= cap) return p;
     if (p) { if (release) release(p); else free(p); }
-    const size_t want = nfloats + nfloats / 4 + 1024;
+    size_t want = (size_t) 1 << 18;                       // powers of two: a buffer given back to the backend's cache fits the next request
+    while (want < nfloats) want <<= 1;
     release = be.host_alloc ? be.host_free : nullptr;
     p = (float *) (be.host_alloc ? be.host_alloc(want * sizeof(float)) : malloc(want * sizeof(float)));
     cap = p ? want : 0;
@@ -372,9 +373,28 @@ struct StageTimer {              // adds the time since construction / last lap 
   }
 };
 
+// BATHHOST_TRACE=1: wall time of every phase of run_batch on stderr (tuning aid)
+struct PhaseTrace {
+  bool on = getenv("BATHHOST_TRACE") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), t = t0;
+  void mark(const char *what)
+  {
+    if (!on) return;
+    const auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[bathhost] %-34s %9.2f ms (at %9.2f)\n", what, std::chrono::duration<double, std::milli>(n - t).count(),
+            std::chrono::duration<double, std::milli>(n - t0).count());
+    t = n;
+  }
+};
+
 // BE: the bathhost_backend the call goes to (a local reference at every call site)
+static const bool g_trace_calls = [] { const char *e = getenv("BATHHOST_TRACE"); return e && atoi(e) >= 2; }();   // BATHHOST_TRACE=2: slow stage calls too
 #define BE_TRY(s, call, what)                                                                   \
-  do { int st_ = (call); if (st_ != 0) return fail(s, st_, std::string(what) + " failed: " +    \
+  do { const auto t0_ = std::chrono::steady_clock::now();                                       \
+       int st_ = (call);                                                                        \
+       if (g_trace_calls) { const double ms_ = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0_).count(); \
+         if (ms_ >= 5.0) fprintf(stderr, "[bathhost]   ctx %p %-28s %9.2f ms\n", BE.ctx, what, ms_); } \
+       if (st_ != 0) return fail(s, st_, std::string(what) + " failed: " +                      \
        (BE.last_error ? BE.last_error(BE.ctx) : "?")); } while (0)
 
 // p7_pli_ComputeLocalCompo (src/p7_pipeline.c:427-458)
@@ -1073,6 +1093,7 @@ int run_batch(bathhost_search *s)
   std::vector<SeqRef> seqs;
   seqs.swap(s->queue);
   if (seqs.empty()) return 0;
+  PhaseTrace trace;
 
   // ---- the reference's blocks (src/bathsearch.c:1060-1105) and the residue count as each block-strand is reached
   std::vector<BlockInfo> blocks;
@@ -1194,6 +1215,7 @@ int run_batch(bathhost_search *s)
     return 0;
   });
   if (rc != 0) return rc;
+  trace.mark("upload + ORFs + filters (devices)");
 
   // ---- DNA windows, block by block in the reference's order, against the ever-growing hit_windows list (kept across batches)
   StageTimer tm;
@@ -1218,6 +1240,7 @@ int run_batch(bathhost_search *s)
       S.db((int) b + 1) = (int) S.dwin.size();
     }
   tm.lap(s->st.us_windows);
+  trace.mark("DNA windows (host, serial)");
 
   // ---- stages 4-5 per unit, device contexts side by side: frameshift Forward parser over every DNA window (:1446-1450), the
   // arbitration between window and ORFs (:1392-1465), Forward + Backward X rows of the windows that stay (:1469-1470), and the
@@ -1434,6 +1457,7 @@ int run_batch(bathhost_search *s)
     return 0;
   });
   if (rc != 0) return rc;
+  trace.mark("fs Forward, arbitration, X rows");
   tm = StageTimer();
 
   // ---- domain decoding and region finding on the host, in the reference's order (block, then strand, then window):
@@ -1630,6 +1654,7 @@ int run_batch(bathhost_search *s)
     s->om5_nj = wm.nj_out; s->om5_L = wm.L_out;
   }
   tm.lap(s->st.us_windows);
+  trace.mark("region walk (host)");
 
   // ---- stage 6 and everything after it, per unit, device contexts side by side: every envelope of the unit rescored in one
   // batched call (rescore_isolated_domain_frameshift, :993-1191), scoring and hit records, then the standard-translation branch
@@ -2020,6 +2045,7 @@ int run_batch(bathhost_search *s)
     return 0;
   });
   if (rc != 0) return rc;
+  trace.mark("envelopes, scoring, std branch");
 
   // ---- hits in the reference's order: block by block, top strand then bottom strand; counters summed over units
   {
@@ -2035,6 +2061,7 @@ int run_batch(bathhost_search *s)
   for (auto &U : units) add_stats(s->st, U->st);
   s->nseqs += (int64_t) seqs.size();
   s->st.nseqs = s->nseqs;
+  trace.mark("hit list");
   return 0;
 }
 

@@ -20,7 +20,7 @@ on the DP path); the only communication is the barrier and the max-over-ranks of
 
 Second metric, "search" (BASELINE.json configs[3] as written): bathsearch --fs Mbp/s of the three profiles of
 tRNA-synthetases.bhmm against ONE synthetic genome in contigs of 1-10 Mbp with planted homologs of all three, sharded by
-blocks over the N devices by ONE process (rank 0; bathhost_search_create_multi, two contexts per device) with one merged
+blocks over the N devices by ONE process (rank 0; bathhost_search_create_multi, eight contexts per device) with one merged
 hit list per profile: strong scaling on a fixed target.  At N > 1 the same search is also run on one device and the two
 tables compared byte for byte (search.checks.hits_identical_to_1gpu); at N = 1 the GPU search of the CPU-baseline prefix
 is compared with the CPU-oracle pipeline's table (search.checks.hits_identical_to_cpu_prefix).
@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument("--search-cpu-mbp", type=float, default=4.0, help="size of the CPU-baseline sample of the search leg, Mbp")
     ap.add_argument("--search-mbp", type=float, default=1000.0,
                     help="also run the whole stage-batched bathsearch --fs pipeline (3 profiles) over a genome of this many Mbp (0 = skip)")
-    ap.add_argument("--contexts-per-gpu", type=int, default=2, help="device contexts per GPU in the search leg")
+    ap.add_argument("--contexts-per-gpu", type=int, default=8, help="device contexts per GPU in the search leg")
     return ap.parse_args()
 
 
@@ -248,7 +248,7 @@ def search_leg(devices, per_gpu, mbp, cpu_mbp, with_cpu):
            "first_pass_seconds": cold, "target_mbp": total_nt / 1e6, "contigs": len(contigs), "profiles": [m.M for m in models],
            "n_gpus": len(devices), "contexts_per_gpu": per_gpu, "scaling": "strong",
            "hits": [len(h) for h in hits], "planted": len(plants), "planted_recovered": recovered(hits, contigs, plants),
-           "stats": stats[1], "checks": {},
+           "stats": stats[1], "stats_per_profile": stats, "checks": {},
            "note": "one process drives every device (bathhost_search_create_multi): blocks of the one target are dealt to the device "
                    "contexts, the hit-window list / length-model chain / residue counts are kept in the reference's serial order on the "
                    "host, one merged hit list per profile; stage times in stats are summed over contexts"}
