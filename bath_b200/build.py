@@ -43,6 +43,28 @@ def build_host_library(force=False):
     return _HOST_SO
 
 
+_INTEG = os.path.join(_HERE, "..", "integration")
+_SHIM_SO = os.path.join(_INTEG, "libbathshim.so")
+
+
+def shim_library_path():
+    return _SHIM_SO
+
+
+def build_shim_library(force=False):
+    """integration/libbathshim.so: the reference's impl-layer parser prototypes implemented on libbathgpu.so (impl_cuda_shim.c), compiled
+    against the stand-in for impl_sse.h, plus the test helper that stripes profiles the SSE way.  gcc only; needs libbathgpu.so to link."""
+    srcs = [os.path.join(_INTEG, f) for f in ("impl_cuda_shim.c", "shim_test_helper.c", "bath_impl_standin.h")]
+    srcs.append(os.path.join(_HERE, "..", "include", "bathgpu.h"))
+    if not force and os.path.exists(_SHIM_SO) and all(os.path.getmtime(s) <= os.path.getmtime(_SHIM_SO) for s in srcs + [_SO]):
+        return _SHIM_SO
+    cmd = [os.environ.get("CC", "gcc"), "-O2", "-g", "-std=gnu11", "-msse2", "-fPIC", "-shared", "-Wall", "-Wextra",
+           "-I", _INTEG, "-I", os.path.join(_HERE, "..", "include"), "-o", _SHIM_SO] + [s for s in srcs if s.endswith(".c")] + \
+          ["-L", _HERE, "-lbathgpu", "-Wl,-rpath,$ORIGIN/../bath_b200", "-lm"]
+    subprocess.check_call(cmd)
+    return _SHIM_SO
+
+
 _OBJ = os.path.join(_HERE, "_obj")
 
 # kernels_tu.cu is compiled once per (family, node-count set): see csrc/launch.h
@@ -105,3 +127,5 @@ if __name__ == "__main__":
     var = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")), None)
     extra = [a for a in sys.argv[1:] if a.startswith("-D")]
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=var, extra_flags=extra))
+    if not var:
+        print(build_shim_library(force="--force" in sys.argv))
