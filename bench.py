@@ -120,23 +120,46 @@ def make_workload(rank, mbp, window):
     return model, dsq, starts, lengths, plants
 
 
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_sample(model_M, dsq, starts, lengths, seconds, nthreads):
-    """Times the CPU oracle (native build, all host threads) on a bounded prefix of the windows.
-    The only place besides tests/ and smoke() where oracle/ is executed -- as the thing compared against."""
+    """Times the CPU port (native build, all host threads) on a bounded prefix of the windows: the AVX2 + FMA build of the parser
+    (oracle/fwd3_avx2.c) where the host has it -- the reference's production build is SIMD too -- and the scalar restatement, which is
+    the checker, beside it.  The only place besides tests/ and smoke() where oracle/ is executed -- as the thing compared against.
+    Returns (SIMD or scalar GCUPS, its description, windows checked, scalar scores of those windows, scalar GCUPS)."""
     from oracle import pyoracle as po
     po.lib(native=True)
     omodel = po.Model(HMM_FILE, HMM_INDEX)
     assert omodel.M == model_M
-    probe = min(len(starts), 64 * nthreads)
-    t0 = time.perf_counter()
-    po.batch_forward_parser(omodel, dsq, starts[:probe], lengths[:probe], nthreads)
-    dt = max(time.perf_counter() - t0, 1e-6)
-    n = int(min(len(starts), max(probe, probe * seconds / dt)))
-    t0 = time.perf_counter()
-    sc, st = po.batch_forward_parser(omodel, dsq, starts[:n], lengths[:n], nthreads)
-    dt = time.perf_counter() - t0
-    cells = float(lengths[:n].astype(np.int64).sum()) * model_M
-    return cells / dt / 1e9, n, dt, sc
+
+    def timed(simd, budget):
+        probe = min(len(starts), 64 * nthreads)
+        t0 = time.perf_counter()
+        po.batch_forward_parser(omodel, dsq, starts[:probe], lengths[:probe], nthreads, simd=simd)
+        dt = max(time.perf_counter() - t0, 1e-6)
+        n = int(min(len(starts), max(probe, probe * budget / dt)))
+        t0 = time.perf_counter()
+        sc, st = po.batch_forward_parser(omodel, dsq, starts[:n], lengths[:n], nthreads, simd=simd)
+        dt = time.perf_counter() - t0
+        return float(lengths[:n].astype(np.int64).sum()) * model_M / dt / 1e9, n, dt, sc
+
+    v_sc, n_sc, dt_sc, sc = timed(False, seconds * 0.5)
+    if po.simd_supported():
+        v, n, dt, ssc = timed(True, seconds * 0.5)
+        m = min(n, n_sc)
+        what = (f"first {n} of {len(starts)} windows ({dt:.1f} s, {nthreads} threads, AVX2+FMA port of the parser, -O3 -march=native, "
+                f"{cpu_model_name()}; max |simd - scalar oracle| = {float(np.max(np.abs(ssc[:m] - sc[:m]))):.1e} nat on {m} windows)")
+        return v, what, n_sc, sc, v_sc, "avx2+fma"
+    what = f"first {n_sc} of {len(starts)} windows ({dt_sc:.1f} s, {nthreads} threads, scalar C oracle -O3 -march=native, {cpu_model_name()})"
+    return v_sc, what, n_sc, sc, v_sc, "scalar"
 
 
 def run_reference(args, rank, world):
@@ -150,31 +173,34 @@ def run_reference(args, rank, world):
     from oracle import pyoracle as po
     po.lib(native=True)
     omodel = po.Model(HMM_FILE, HMM_INDEX)
+    simd = po.simd_supported()                      # the reference's production build is SIMD: so is this arm where the host allows
     probe = min(len(starts), 64 * ncpu)
     t0 = time.perf_counter()
-    po.batch_forward_parser(omodel, dsq, starts[:probe], lengths[:probe], ncpu)
+    po.batch_forward_parser(omodel, dsq, starts[:probe], lengths[:probe], ncpu, simd=simd)
     dt = max(time.perf_counter() - t0, 1e-6)
     n = int(min(len(starts), max(probe, probe * per_step / dt)))
     for _ in range(args.warmup):
-        po.batch_forward_parser(omodel, dsq, starts[:n], lengths[:n], ncpu)
+        po.batch_forward_parser(omodel, dsq, starts[:n], lengths[:n], ncpu, simd=simd)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        po.batch_forward_parser(omodel, dsq, starts[:n], lengths[:n], ncpu)
+        po.batch_forward_parser(omodel, dsq, starts[:n], lengths[:n], ncpu, simd=simd)
     dt = time.perf_counter() - t0
     cells = float(lengths[:n].astype(np.int64).sum()) * model.M
     value = cells * args.steps / dt / 1e9
-    sample = f"{n} of {len(starts)} windows of {args.window} nt per step ({cells / 1e9:.3f} Gcells), {ncpu} threads"
+    sample = (f"{n} of {len(starts)} windows of {args.window} nt per step ({cells / 1e9:.3f} Gcells), {ncpu} threads, "
+              f"{'AVX2+FMA port of the parser (oracle/fwd3_avx2.c)' if simd else 'scalar C oracle'}, {cpu_model_name()}")
     search = search_leg_cpu(args.search_cpu_mbp, ncpu) if args.search_mbp > 0 else None
     emit_json_line({
         "impl": "reference", "metric": "frameshift Forward GCUPS", "value": value, "unit": "GCUPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, model.M, len(starts)),
-        "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": ncpu, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": ncpu, "kind": "port", "simd": "avx2+fma" if simd else "scalar", "sample": sample},
         "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "search": ({"metric": "bathsearch --fs Mbp/s", **search} if search else None),
-        "note": "restated CPU oracle (scalar C, -O3 -march=native, pthreads over windows); the reference binary needs Easel, "
-                "which is not vendored, so it cannot be compiled here",
+        "note": "restated CPU port (AVX2+FMA build of the parser where the host has it, else scalar C; -O3 -march=native, pthreads over "
+                "windows, FTZ/DAZ per thread as impl_Init sets them); the reference binary needs Easel, which is not vendored, so it "
+                "cannot be compiled here",
     })
 
 
@@ -496,10 +522,11 @@ def main():
         out["search"] = search
     if world == 1 and not args.no_cpu_baseline:
         ncpu = os.cpu_count() or 1
-        v, n, dt, osc = cpu_sample(M, dsq_np, starts, lengths, args.cpu_seconds, ncpu)
-        out["cpu_baseline"] = {"value": v, "unit": "GCUPS", "cores": ncpu, "kind": "port",
-                               "sample": f"first {n} of {nwin} windows ({dt:.1f} s, {ncpu} threads, scalar C oracle -O3 -march=native)"}
+        v, what, n, osc, v_scalar, simd = cpu_sample(M, dsq_np, starts, lengths, args.cpu_seconds, ncpu)
+        out["cpu_baseline"] = {"value": v, "unit": "GCUPS", "cores": ncpu, "kind": "port", "simd": simd, "sample": what,
+                               "scalar_oracle_value": v_scalar}
         out["checks"]["max_abs_diff_vs_oracle_nats"] = float(np.max(np.abs(osc - sc[:n])))
+        out["checks"]["windows_checked_against_oracle"] = int(n)
     emit_json_line(out)
     if world > 1:
         dist.destroy_process_group()

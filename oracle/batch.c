@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
+#include <xmmintrin.h>
 #include "bath_oracle.h"
 
 typedef struct {
@@ -19,9 +20,8 @@ typedef struct {
   const BO_FS_OPROFILE *om;
   float                *sc;       /* [n] out */
   int32_t              *status;   /* [n] out */
-  int                   next;     /* work counter */
+  int                   next;     /* work counter (atomic) */
   int                   maxL;
-  pthread_mutex_t       mu;
 } fwd_job;
 
 static void *fwd_worker(void *arg)
@@ -30,11 +30,9 @@ static void *fwd_worker(void *arg)
   BO_FS_OPROFILE om = *job->om;                 /* private length model; tables shared read-only */
   BO_MX *ox = bo_mx_create(om.M, job->maxL, 0);
   uint8_t *sub = malloc((size_t) job->maxL + 2);
+  _mm_setcsr(_mm_getcsr() | 0x8040);            /* flush-to-zero + denormals-are-zero in every worker, as impl_Init does (src/impl_sse/impl_sse.h:559-577; src/bathsearch.c:1235) */
   for (;;) {
-    int w;
-    pthread_mutex_lock(&job->mu);
-    w = job->next++;
-    pthread_mutex_unlock(&job->mu);
+    const int w = __atomic_fetch_add(&job->next, 1, __ATOMIC_RELAXED);      /* lock-free work counter */
     if (w >= job->n) break;
     int L = job->L[w];
     /* the reference hands each window to the kernel as its own sub-sequence (src/p7_pipeline.c:1376-1380) */
@@ -60,11 +58,9 @@ int bo_batch_ForwardParser_3Codons(const uint8_t *dsq, const int64_t *start, con
   for (t = 0; t < n; t++) if (L[t] > maxL) maxL = L[t];
   job.dsq = dsq; job.start = start; job.L = L; job.n = n; job.om = om; job.sc = sc; job.status = status;
   job.next = 0; job.maxL = maxL;
-  pthread_mutex_init(&job.mu, NULL);
   th = malloc(sizeof(pthread_t) * (size_t) nthreads);
   for (t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, fwd_worker, &job);
   for (t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
   free(th);
-  pthread_mutex_destroy(&job.mu);
   return BO_OK;
 }

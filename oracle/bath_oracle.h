@@ -340,6 +340,10 @@ int    bo_Null2_ByExpectation(const BO_OPROFILE *om, const BO_MX *pp, float *nul
 /* ===== batch.c (worker-thread pool over windows; src/bathsearch.c:814-844,1224) ===== */
 int bo_batch_ForwardParser_3Codons(const uint8_t *dsq, const int64_t *start, const int32_t *L, int n,
                                    const BO_FS_OPROFILE *om, int nthreads, float *sc, int32_t *status);
+/* ===== fwd3_avx2.c: the same batch on an AVX2 + FMA build of the parser (the CPU arm of bench.py; checked against the scalar one) ===== */
+int bo_fwd3_simd_supported(void);
+int bo_batch_ForwardParser_3Codons_simd(const uint8_t *dsq, const int64_t *start, const int32_t *L, int n,
+                                        const BO_FS_OPROFILE *om, int nthreads, float *sc, int32_t *status);
 
 #ifdef __cplusplus
 }

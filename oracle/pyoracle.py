@@ -316,16 +316,25 @@ def calibrate(model, seed=42, lam=None, which=31, convert_flow=False, rng_x=0):
     return [float(v) for v in out], x.value
 
 
-def batch_forward_parser(model, dsq, starts, lengths, nthreads=1):
-    """Forward parser (3 codon lengths) over windows dsq[start .. start+L-1] with a thread pool."""
+def simd_supported():
+    L = lib()
+    L.bo_fwd3_simd_supported.restype = C.c_int
+    return bool(L.bo_fwd3_simd_supported())
+
+
+def batch_forward_parser(model, dsq, starts, lengths, nthreads=1, simd=False):
+    """Forward parser (3 codon lengths) over windows dsq[start .. start+L-1] with a thread pool.  simd: the AVX2 + FMA build
+    (fwd3_avx2.c) instead of the scalar restatement."""
     n = len(starts)
     st64 = np.ascontiguousarray(starts, np.int64)
     l32 = np.ascontiguousarray(lengths, np.int32)
     sc = np.empty(n, np.float32)
     status = np.empty(n, np.int32)
-    rc = lib().bo_batch_ForwardParser_3Codons(u8ptr(dsq), st64.ctypes.data_as(C.POINTER(C.c_int64)),
-                                              l32.ctypes.data_as(C.POINTER(C.c_int32)), n, model.om_fs3,
-                                              int(nthreads), fptr(sc), status.ctypes.data_as(C.POINTER(C.c_int32)))
+    fn = lib().bo_batch_ForwardParser_3Codons_simd if simd else lib().bo_batch_ForwardParser_3Codons
+    if simd:
+        fn.restype, fn.argtypes = lib().bo_batch_ForwardParser_3Codons.restype, lib().bo_batch_ForwardParser_3Codons.argtypes
+    rc = fn(u8ptr(dsq), st64.ctypes.data_as(C.POINTER(C.c_int64)), l32.ctypes.data_as(C.POINTER(C.c_int32)), n, model.om_fs3,
+            int(nthreads), fptr(sc), status.ctypes.data_as(C.POINTER(C.c_int32)))
     if rc != OK:
         raise RuntimeError(f"bo_batch_ForwardParser_3Codons: status {rc}")
     return sc, status
