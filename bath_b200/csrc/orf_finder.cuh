@@ -7,9 +7,9 @@
 //
 //   codon_class_kernel   cls[s] = amino-acid code of the codon starting at strand position s+1 (27 = stop): 1 B per nucleotide,
 //                        shared by the three frames and by every block that covers the position;
-//   orf_scan_kernel      a stop codon (or the end of the block) at block position p closes the ORF of its frame: the thread
-//                        that owns p walks back over cls in steps of three to the previous stop (21 codons on average in
-//                        random DNA).  Pass 1 counts ORFs per tile of 2048 positions; after a scan of the tile counts, pass 2
+//   orf_scan_kernel      a stop codon (or the end of the block) at block position p closes the ORF of its frame, which starts behind
+//                        the previous stop of that frame: found by a max-scan over the tile (a walk back over cls only for the
+//                        first ORF of each frame in a tile).  Pass 1 counts ORFs per tile of 2048 positions; after a scan of the tile counts, pass 2
 //                        writes the descriptors in order of p -- the order in which a left-to-right scan finishes ORFs,
 //                        which is the reference's ORF order inside a block (the window bookkeeping depends on it);
 //   (the MSV kernel then reads residues from cls with stride 3: nothing is materialised for the 98 % of ORFs that fail)
@@ -65,6 +65,11 @@ struct OrfScanArgs {
 
 __global__ void __launch_bounds__(256) codon_class_kernel(const uint32_t *__restrict__ dna4, long long n, GeneticCode gc, uint8_t *__restrict__ cls)
 {
+  // the 64-entry code table in shared memory: 16 words in 16 banks, so any 32 lookups are conflict-free (indexing the kernel
+  // parameter instead serialises the lanes of a warp in the constant cache)
+  __shared__ uint8_t s_aa[64];
+  if (threadIdx.x < 64) s_aa[threadIdx.x] = gc.aa[threadIdx.x];
+  __syncthreads();
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // nucleotides 8t .. 8t+7 (0-based)
   if (t * 8 >= n) return;
   const uint32_t w0 = __ldg(dna4 + t + 1), w1 = __ldg(dna4 + t + 2);       // one guard word in front
@@ -74,42 +79,78 @@ __global__ void __launch_bounds__(256) codon_class_kernel(const uint32_t *__rest
   for (int b = 0; b < 8; ++b) {
     const unsigned a = (unsigned)(bits >> (4 * b)) & 15u, c = (unsigned)(bits >> (4 * b + 4)) & 15u, g = (unsigned)(bits >> (4 * b + 8)) & 15u;
     unsigned aa = 26;                                   // X
-    if (a < 4 && c < 4 && g < 4) aa = gc.aa[16 * a + 4 * c + g];
+    if (a < 4 && c < 4 && g < 4) aa = s_aa[16 * a + 4 * c + g];
     out |= (unsigned long long)aa << (8 * b);
   }
   *reinterpret_cast<unsigned long long *>(cls + t * 8) = out;
 }
 
-// does an ORF end just before block position p?  Its length in residues (0: none or shorter than min_len).
-__device__ __forceinline__ int orf_ending_before(const uint8_t *__restrict__ cls, long long goff, int n, int p, int min_len)
-{
-  bool ends;
-  if (p + 2 <= n) ends = (cls[goff + p - 1] == kStopCode);
-  else            ends = (p <= n + 1);                  // the three positions without a whole codon: one per frame
-  if (!ends || p < 1) return 0;
-  int len = 0;
-  for (int q = p - 3; q >= 1 && cls[goff + q - 1] != kStopCode; q -= 3) ++len;
-  return (len >= min_len) ? len : 0;
-}
-
+// One tile of 2048 block positions per thread block, 8 consecutive positions per thread.  The ORF that ends before position p starts
+// behind the previous stop codon of p's frame: instead of every closing position walking back over the class bytes (21 dependent
+// loads on average), each thread notes the last stop of each frame among its own positions, a block-wide max-scan hands every thread
+// the last stop of each frame in front of it, and only the first ORF of each frame in a tile (whose stop lies in an earlier tile) walks.
 template <bool EMIT>
 __global__ void __launch_bounds__(kOrfTileThreads) orf_scan_kernel(OrfScanArgs a)
 {
   __shared__ int s_warp[kOrfTileThreads / 32];
+  __shared__ int s_last[3][kOrfTileThreads / 32];
   const int tile = blockIdx.x;
   const int b = a.tile_block[tile];
   const BlockDesc bd = a.blocks[b];
   const int p0 = a.tile_p0[tile] + threadIdx.x * kOrfPosPerThread;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint8_t *__restrict__ cls = a.cls + bd.goff - 1;          // cls[p] = class of the codon starting at block position p
+
+  // is there a stop codon at block position p (whole codons only)?
+  bool stop[kOrfPosPerThread];
+  int  mine[3] = { -1, -1, -1 };                                   // last stop of each frame (p mod 3) among this thread's positions
+#pragma unroll
+  for (int z = 0; z < kOrfPosPerThread; ++z) {
+    const int p = p0 + z;
+    stop[z] = (p >= 1 && p + 2 <= bd.n) && (__ldg(cls + p) == kStopCode);
+    if (stop[z]) mine[p % 3] = p;
+  }
+  // exclusive max-scan over the block, per frame
+  int prev[3];
+#pragma unroll
+  for (int f = 0; f < 3; ++f) {
+    int incl = mine[f];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl = max(incl, v); }
+    if (lane == 31) s_last[f][wid] = incl;
+    int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    prev[f] = (lane == 0) ? -1 : excl;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int f = 0; f < 3; ++f)
+    for (int w = 0; w < wid; ++w) prev[f] = max(prev[f], s_last[f][w]);
+
   int lens[kOrfPosPerThread];
   int cnt = 0;
 #pragma unroll
   for (int z = 0; z < kOrfPosPerThread; ++z) {
     const int p = p0 + z;
-    lens[z] = (p <= bd.n + 1) ? orf_ending_before(a.cls, bd.goff, bd.n, p, a.min_len) : 0;
-    cnt += lens[z] > 0;
+    int len = 0;
+    if (p >= 1 && p <= bd.n + 1) {
+      const bool ends = (p + 2 <= bd.n) ? stop[z] : true;          // the three positions without a whole codon close one frame each
+      if (ends) {
+        const int f = p % 3;
+        if (prev[f] >= 0) len = (p - prev[f]) / 3 - 1;             // the stop is in this tile
+        else {                                                     // it lies in an earlier tile (or the frame has none yet): walk
+          const int t0 = a.tile_p0[tile];
+          int q = p - 3;
+          for (; q >= t0; q -= 3) ++len;                           // no stop of this frame in the tile before p
+          for (; q >= 1 && __ldg(cls + q) != kStopCode; q -= 3) ++len;
+        }
+        if (len < a.min_len) len = 0;
+      }
+      if (stop[z]) prev[p % 3] = p;
+    }
+    lens[z] = len;
+    cnt += len > 0;
   }
   // block-wide exclusive scan of cnt
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int incl = cnt;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }

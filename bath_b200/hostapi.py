@@ -337,12 +337,17 @@ class Search:
         if st != OK:
             raise RuntimeError(f"bathhost_search_run: status {st}: {self.lib.bathhost_search_last_error(self.h).decode()}")
 
-    def finish(self):
+    def finish(self, fetch=True):
+        """bathhost_search_finish: everything still queued is searched, E-values, duplicate removal, ordering, thresholds.
+        fetch=False returns the number of hits and leaves their conversion into Python dicts to hits() (a harness cost, ~10 us per hit)."""
         if self._keep:
             self.run()
         st = self.lib.bathhost_search_finish(self.h)
         if st != OK:
             raise RuntimeError(f"bathhost_search_finish: status {st}")
+        return self.hits() if fetch else int(self.lib.bathhost_search_nhits(self.h))
+
+    def hits(self):
         hits = []
         for i in range(self.lib.bathhost_search_nhits(self.h)):
             h = Hit()
