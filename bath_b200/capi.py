@@ -20,7 +20,7 @@ EXPORTS = [
     "bathgpu_fwd_orfs", "bathgpu_fs_fwd_bck_xrows", "bathgpu_select_slot",
     "bathgpu_orf_fwd_bck_xrows", "bathgpu_orf_domains", "bathgpu_orf_fetch_domain_matrices",
     "bathgpu_orfs_msv_screen", "bathgpu_orfs_fetch", "bathgpu_revcomp_slot", "bathgpu_fs_fwd_block", "bathgpu_fs_forward_matrices",
-    "bathgpu_bias_forward",
+    "bathgpu_bias_forward", "bathgpu_orfs_stage_breakdown", "bathgpu_measure_int16_peak",
 ]
 
 
@@ -136,6 +136,10 @@ def load():
     L.bathgpu_fs_forward_matrices.argtypes = [vp, vp, C.c_int, fp, fp, fp, C.c_int64, fp, ip]
     L.bathgpu_select_slot.restype = C.c_int
     L.bathgpu_select_slot.argtypes = [vp, C.c_int]
+    L.bathgpu_measure_int16_peak.restype = C.c_int
+    L.bathgpu_measure_int16_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    L.bathgpu_orfs_stage_breakdown.restype = C.c_int
+    L.bathgpu_orfs_stage_breakdown.argtypes = [vp, fp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.bathgpu_bias_forward.restype = C.c_int
     L.bathgpu_bias_forward.argtypes = [vp, C.c_int, vp, C.c_int, fp, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_uint8), fp]
     L.bathgpu_host_alloc.restype = vp
@@ -370,6 +374,18 @@ class Context:
 
     def revcomp_slot(self, src, dst):
         self._check(self.lib.bathgpu_revcomp_slot(self.h, int(src), int(dst)))
+
+    def measure_int16_peak(self):
+        t = C.c_double(0)
+        self._check(self.lib.bathgpu_measure_int16_peak(self.h, C.byref(t)))
+        return float(t.value)
+
+    def orfs_stage_breakdown(self):
+        """(ms of [classes, count pass, emit pass, MSV, screen], ORFs found, residues scored) of the last orfs_msv_screen call"""
+        ms = np.zeros(5, np.float32)
+        no, nr = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.bathgpu_orfs_stage_breakdown(self.h, _f(ms), C.byref(no), C.byref(nr)))
+        return ms, int(no.value), int(nr.value)
 
     def bias_forward(self, kind, items, tables, t10, t11, gcode=None):
         """bathgpu_bias_forward: items = bias_item_dtype array; tables [ntab][29][2]; returns n (kind 0) or n x 3 (kind 1) scores"""

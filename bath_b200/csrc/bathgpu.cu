@@ -118,6 +118,9 @@ struct bathgpu_ctx {
   DevBuf        b_items, b_tables, b_out;      // bias filter
   DevBuf        o_tiles, o_cnt, o_base, o_blocks, o_first, o_tjb, o_null, o_meta, o_hits, o_counters;
   long long     o_nhits = 0, o_nres = 0;
+  cudaEvent_t   o_ev[6] = {};                      // boundaries of the kernel groups of the last bathgpu_orfs_msv_screen call
+  float         o_ms[5] = {};                      // classes, count pass, emit pass, MSV, screen
+  long long     o_scored = 0, o_norf = 0;          // residues and ORFs the MSV kernel scored
   // domain stage workspace (last chunk stays resident for bathgpu_fs_fetch_domain_matrices)
   DevBuf        envs, dpp, doa, dfx, dppx, doax, dlsf, dfw, dbk, doasc, dnull2, dstat, dtoff, dtlen, dsteps, ddcell, dmxout;
   std::vector<long long> dom_xoff;
@@ -205,6 +208,7 @@ extern "C" void bathgpu_destroy(bathgpu_ctx *ctx)
   cudaStreamSynchronize(ctx->stream);
   // every device buffer of the context (profile images, target slots, stage workspaces) is a DevBuf and frees itself with the context
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+  for (auto &e : ctx->o_ev) if (e) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); cudaStreamDestroy(ctx->stream2); for (auto &e : ctx->chunk_ev) if (e) cudaEventDestroy(e); }
   delete ctx;
@@ -279,6 +283,30 @@ extern "C" void bathgpu_host_free(void *p)
       return;
     }
   cudaFreeHost(p);
+}
+
+// 16-bit lane operations per second (add and max each counted, two halves per register) the device sustains: bench.py's denominator
+// for the MSV and Viterbi filters
+extern "C" int bathgpu_measure_int16_peak(bathgpu_ctx *ctx, double *tera_ops)
+{
+  if (!ctx || !tera_ops) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_measure_int16_peak");
+  CUDA_TRY(ctx, enter(ctx));
+  if (ctx->scratch.reserve(1 << 20) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
+  const int blocks = ctx->prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  const double ops = (double)blocks * threads * (double)iters * 8.0 * 16.0 * 4.0;
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    int16x2_probe_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->scratch.as<unsigned>(), iters, 0x00030001u, 0x00050002u);
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (rep >= 2 && ms < best) best = ms;
+  }
+  *tera_ops = ops / (best * 1e-3) / 1e12;
+  return BATHGPU_OK;
 }
 
 extern "C" int bathgpu_measure_fp32_peak(bathgpu_ctx *ctx, double *tflops, double *sm_mhz_effective)
@@ -1884,17 +1912,23 @@ extern "C" int bathgpu_orfs_msv_screen(bathgpu_ctx *ctx, const bathgpu_block *bl
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->o_tjb.p, tjb_of, (size_t)max_len + 1, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->o_null.p, null_of, ((size_t)max_len + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  if (!ctx->o_ev[0]) for (auto &e : ctx->o_ev) CUDA_TRY(ctx, cudaEventCreate(&e));
+  for (float &m : ctx->o_ms) m = 0.f;
+  ctx->o_scored = 0; ctx->o_norf = 0;
   GeneticCode gc;
   memcpy(gc.aa, gcode, 64);
+  CUDA_TRY(ctx, cudaEventRecord(ctx->o_ev[0], ctx->stream));
   {
     const long long nthreads = (n + 7) / 8;
     codon_class_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, ctx->stream>>>(S.dna4.as<uint32_t>(), n, gc, S.cls.as<uint8_t>());
   }
+  CUDA_TRY(ctx, cudaEventRecord(ctx->o_ev[1], ctx->stream));
   OrfScanArgs sa{};
   sa.cls = S.cls.as<uint8_t>(); sa.blocks = ctx->o_blocks.as<BlockDesc>(); sa.tile_block = d_tile_block; sa.tile_p0 = d_tile_p0;
   sa.ntiles = ntiles; sa.min_len = min_len; sa.complement = complement; sa.tile_cnt = ctx->o_cnt.as<int>();
   orf_scan_kernel<false><<<ntiles, kOrfTileThreads, 0, ctx->stream>>>(sa);
   CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaEventRecord(ctx->o_ev[2], ctx->stream));
   std::vector<int> cnt((size_t)ntiles);
   CUDA_TRY(ctx, cudaMemcpyAsync(cnt.data(), ctx->o_cnt.p, (size_t)ntiles * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1915,29 +1949,48 @@ extern "C" int bathgpu_orfs_msv_screen(bathgpu_ctx *ctx, const bathgpu_block *bl
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->o_first.p, bfirst.data(), (size_t)nblocks * 8, cudaMemcpyHostToDevice, ctx->stream));
   sa.tile_base = ctx->o_base.as<long long>(); sa.block_first = ctx->o_first.as<long long>(); sa.tjb_of = ctx->o_tjb.as<uint8_t>();
   sa.max_len = max_len; sa.descs = ctx->orfs.as<OrfDesc>(); sa.meta = ctx->o_meta.as<OrfMeta>();
+  sa.scored = ctx->o_counters.as<unsigned long long>() + 2;
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->o_counters.p, 0, 32, ctx->stream));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->o_ev[5], ctx->stream));
   orf_scan_kernel<true><<<ntiles, kOrfTileThreads, 0, ctx->stream>>>(sa);
   CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaEventRecord(ctx->o_ev[3], ctx->stream));
   // MSV over every ORF, residues read from the codon classes with stride 3
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
   FilterArgs fa = filter_args(ctx, (int)N, 0);
   fa.residues = S.cls.as<uint8_t>(); fa.res_stride = 3;
   CUDA_TRY(ctx, dispatch_msv(0, ctx->flt_W, fa, ctx->prop.multiProcessorCount, ctx->stream));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->o_ev[4], ctx->stream));
   OrfScreenArgs ra{};
   ra.cls = S.cls.as<uint8_t>(); ra.descs = ctx->orfs.as<OrfDesc>(); ra.meta = ctx->o_meta.as<OrfMeta>(); ra.usc = ctx->fsc.as<float>();
   ra.status = ctx->fst.as<int>(); ra.norf = N; ra.null_of = ctx->o_null.as<float>(); ra.max_len = max_len; ra.min_bits = min_bits;
   ra.hits = ctx->o_hits.as<OrfHit>(); ra.residues = S.residues.as<uint8_t>(); ra.counters = ctx->o_counters.as<unsigned long long>();
-  CUDA_TRY(ctx, cudaMemsetAsync(ctx->o_counters.p, 0, 16, ctx->stream));
   orf_screen_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(ra);
   CUDA_TRY(ctx, cudaGetLastError());
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-  unsigned long long hc[2] = { 0, 0 };
-  CUDA_TRY(ctx, cudaMemcpyAsync(hc, ctx->o_counters.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  unsigned long long hc[3] = { 0, 0, 0 };
+  CUDA_TRY(ctx, cudaMemcpyAsync(hc, ctx->o_counters.p, 24, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+  CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->o_ms[0], ctx->o_ev[0], ctx->o_ev[1]));
+  CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->o_ms[1], ctx->o_ev[1], ctx->o_ev[2]));
+  CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->o_ms[2], ctx->o_ev[5], ctx->o_ev[3]));
+  CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->o_ms[3], ctx->o_ev[3], ctx->o_ev[4]));
+  CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->o_ms[4], ctx->o_ev[4], ctx->ev1));
+  ctx->o_scored = (long long)hc[2]; ctx->o_norf = N;
   ctx->last_launches = 5;
   ctx->o_nhits = (long long)hc[0]; ctx->o_nres = (long long)hc[1];
   S.nres = (int64_t)hc[1];
   *nhits = (int64_t)hc[0]; *nres = (int64_t)hc[1];
+  return BATHGPU_OK;
+}
+
+extern "C" int bathgpu_orfs_stage_breakdown(bathgpu_ctx *ctx, float ms[5], int64_t *norfs, int64_t *residues_scored)
+{
+  if (!ctx || !ms) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_orfs_stage_breakdown");
+  for (int z = 0; z < 5; ++z) ms[z] = ctx->o_ms[z];
+  if (norfs) *norfs = ctx->o_norf;
+  if (residues_scored) *residues_scored = ctx->o_scored;
   return BATHGPU_OK;
 }
 

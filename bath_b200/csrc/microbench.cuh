@@ -25,4 +25,25 @@ static __global__ void __launch_bounds__(256) fp32_fma_probe_kernel(float *out, 
   if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;   // never true; keeps the chains live
 }
 
+// 16-bit SIMD-in-register issue probe: the denominator of the integer filters' roofline.  Each statement is one add-then-clamp
+// (VIADDMNMX.S16x2) and one max (VIMNMX.S16x2) on both 16-bit halves of a register -- the native instructions the MSV / Viterbi cells
+// are made of (orf_filters.cuh); an instruction counts as one operation per half.  16 independent chains per thread.
+static __global__ void __launch_bounds__(256) int16x2_probe_kernel(unsigned *out, int iters, unsigned a, unsigned b)
+{
+  unsigned x[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) x[j] = (threadIdx.x + j) * 0x00010001u;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) x[j] = __vmaxs2(__viaddmin_s16x2(x[j], a, 0x00ff00ffu), b);
+    }
+  }
+  unsigned s = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s ^= x[j];
+  if (s == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = s;   // never true in practice; keeps the chains live
+}
+
 }  // namespace bathgpu

@@ -61,6 +61,7 @@ struct OrfScanArgs {
   int              max_len;
   OrfDesc         *descs;
   OrfMeta         *meta;
+  unsigned long long *scored;      // += residues of the ORFs that will be scored (the MSV stage's cell count / M)
 };
 
 __global__ void __launch_bounds__(256) codon_class_kernel(const uint32_t *__restrict__ dna4, long long n, GeneticCode gc, uint8_t *__restrict__ cls)
@@ -163,12 +164,14 @@ __global__ void __launch_bounds__(kOrfTileThreads) orf_scan_kernel(OrfScanArgs a
     if (threadIdx.x == 0) a.tile_cnt[tile] = total;
   } else {
     long long r = a.tile_base[tile] + wbase + incl - cnt;
+    unsigned scored = 0;
 #pragma unroll
     for (int z = 0; z < kOrfPosPerThread; ++z) {
       if (lens[z] == 0) continue;
       const int p = p0 + z, len = lens[z];
       const int start = p - 3 * len, end = p - 1;
       const bool in_context = a.complement ? ((bd.n - start + 1) < bd.C) : (end < bd.C);     // (src/p7_pipeline.c:1634-1637)
+      if (!in_context) scored += (unsigned)len;
       OrfDesc d;
       d.offset = bd.goff + start - 1;                   // index of the first codon in cls; residues follow with stride 3
       d.L = len; d.tjb_b = a.tjb_of[min(len, a.max_len)]; d.ssv_thresh = 0; d.xw_move = 0; d.vit_thresh = 0;
@@ -179,6 +182,8 @@ __global__ void __launch_bounds__(kOrfTileThreads) orf_scan_kernel(OrfScanArgs a
       a.meta[r] = m;
       ++r;
     }
+    scored = __reduce_add_sync(0xffffffffu, scored);
+    if (lane == 0 && scored) atomicAdd(a.scored, (unsigned long long)scored);
   }
 }
 

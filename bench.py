@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--search-cpu-mbp", type=float, default=4.0, help="size of the CPU-baseline sample of the search leg, Mbp")
     ap.add_argument("--search-mbp", type=float, default=1000.0,
                     help="also run the whole stage-batched bathsearch --fs pipeline (3 profiles) over a genome of this many Mbp (0 = skip)")
+    ap.add_argument("--no-filters-leg", action="store_true", help="skip the integer-filter roofline leg")
     ap.add_argument("--contexts-per-gpu", type=int, default=8, help="device contexts per GPU in the search leg")
     return ap.parse_args()
 
@@ -202,6 +203,77 @@ def run_reference(args, rank, world):
                 "windows, FTZ/DAZ per thread as impl_Init sets them); the reference binary needs Easel, which is not vendored, so it "
                 "cannot be compiled here",
     })
+
+
+STD_CODE = "KNKNTTTTRSRSIIMIQHQHPPPPRRRRLLLLEDEDAAAAGGGGVVVV*Y*YSSSS*CWCLFLF"      # NCBI table 1, codon index 16 a + 4 b + c over ACGT
+
+
+def filters_leg(ctx, model, n_nt, hbm_peak, hbm_src):
+    """north_star's second roofline: the integer filters "against integer-ALU issue rate and HBM GB/s".  The Forward leg's genome is
+    resident on the device (slot 0): six-frame translation + MSV over every ORF of the top strand in the pipeline's own call
+    (bathgpu_orfs_msv_screen, blocks of 262144 nt with 3 x max_length of context), kernel groups timed with CUDA events, then the
+    Viterbi filter over every ORF of the first blocks.  Algorithmic operation counts per DP cell as SURVEY 8(a) gives them
+    (src/impl_sse/msvfilter.c:145-148: 4 byte operations per MSV cell; src/impl_sse/vitfilter.c:145-171: 14 16-bit operations per
+    Viterbi cell) against the 16-bit lane-operation rate an in-process probe sustains (bathgpu_measure_int16_peak)."""
+    from bath_b200 import capi
+    M = model.M
+    rbv, rwv, twv = model.filter_tables()
+    ctx.load_filter_profile(model.filter_params(), rbv, rwv, twv)
+    W, Cx = 262144, 3 * model.max_length
+    blocks, pos = [], 1
+    while pos <= n_nt:
+        c = 0 if pos == 1 else min(Cx, pos - 1)
+        b1 = min(n_nt, pos + W - 1)
+        blocks.append((pos - c - 1, b1 - (pos - c) + 1, c))
+        pos = b1 + 1
+    bl = np.zeros(len(blocks), capi.block_dtype)
+    bl["goff"], bl["n"], bl["C"] = [b[0] for b in blocks], [b[1] for b in blocks], [b[2] for b in blocks]
+    maxlen = int(bl["n"].max()) // 3 + 2
+    Ls = np.arange(maxlen + 1)
+    tjb = np.zeros(maxlen + 1, np.uint8)
+    xwm = np.zeros(maxlen + 1, np.int16)
+    for L in range(1, maxlen + 1):
+        tjb[L], xwm[L] = model.orf_length_params(L)
+    tjb[0] = tjb[1]
+    p1 = (Ls.astype(np.float32) / (Ls + 1).astype(np.float32)).astype(np.float64)
+    null = np.zeros(maxlen + 1, np.float32)
+    null[1:] = (Ls[1:] * np.log(p1[1:]) + np.log(1.0 - p1[1:])).astype(np.float32)
+    aa = "ACDEFGHIKLMNPQRSTVWY"
+    gcode = np.array([27 if ch == "*" else aa.index(ch) for ch in STD_CODE], np.uint8)
+    ctx.select_slot(0)
+    best = None
+    for rep in range(4):                                         # first call allocates; best of the next three
+        per, hits, res = ctx.orfs_msv_screen(bl, 0, gcode, 20, tjb, null, 8.0)
+        ms, norf, nres = ctx.orfs_stage_breakdown()
+        if rep >= 1 and (best is None or float(ms.sum()) < float(best[0].sum())):
+            best = (ms.copy(), norf, nres)
+    ms, norf, nres = [float(v) for v in best[0]], int(best[1]), int(best[2])
+    int_peak = float(ctx.measure_int16_peak())
+    msv_cells_s = nres * M / (ms[3] * 1e-3)
+    finder_ms = float(ms[0] + ms[1] + ms[2] + ms[4])
+    finder_bytes = float(n_nt / 2 + 4.0 * n_nt + nres)                  # packed strand read, classes written once and read by the two passes and by MSV, residues of survivors aside
+    out = {"int16_peak_tera_ops": int_peak, "peak_source": "VIADDMNMX.S16x2 + VIMNMX.S16x2 probe in this process, one operation per instruction and 16-bit half (bathgpu_measure_int16_peak)",
+           "strand_nt": int(n_nt), "orfs": norf, "residues_scored": nres, "survivors": int(len(hits)),
+           "stage_ms": {"codon_classes": float(ms[0]), "orf_count_pass": float(ms[1]), "orf_emit_pass": float(ms[2]), "msv": float(ms[3]),
+                        "screen_gather": float(ms[4])},
+           "msv": {"cells_per_s": msv_cells_s, "ops_per_cell": 4, "achieved_tera_ops": msv_cells_s * 4 / 1e12,
+                   "frac_of_int16_peak": msv_cells_s * 4 / 1e12 / int_peak,
+                   "hbm": {"achieved": nres / (ms[3] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src,
+                           "note": "1 B per residue read from the class stream (stride 3) + 24 B of descriptor per ORF"}},
+           "orf_finder": {"nt_per_s": n_nt / (finder_ms * 1e-3), "hbm": {"achieved": finder_bytes / (finder_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                          "unit": "GB/s", "frac": finder_bytes / (finder_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": finder_bytes}}}
+    # Viterbi filter over every ORF of the first blocks (the pipeline runs it on the ~1 % that pass MSV + bias: too few to time)
+    nb = min(len(bl), 40)
+    per, hits, res = ctx.orfs_msv_screen(bl[:nb], 0, gcode, 20, tjb, null, -1e30)
+    d = np.zeros(len(hits), capi.orf_dtype)
+    d["offset"], d["L"] = hits["offset"], hits["n"]
+    d["tjb_b"], d["xw_move"] = tjb[np.minimum(hits["n"], maxlen)], xwm[np.minimum(hits["n"], maxlen)]
+    ctx.vit_orfs(d, max_wins=64)
+    tv = float(min((ctx.vit_orfs(d, max_wins=64), ctx.last_stage_timing()[0])[1] for _ in range(3)))
+    vit_cells_s = float(hits["n"].astype(np.int64).sum()) * M / (tv * 1e-3)
+    out["viterbi"] = {"orfs": int(len(hits)), "ms": float(tv), "cells_per_s": vit_cells_s, "ops_per_cell": 14,
+                      "achieved_tera_ops": vit_cells_s * 14 / 1e12, "frac_of_int16_peak": vit_cells_s * 14 / 1e12 / int_peak}
+    return out
 
 
 SEARCH_MODELS = (0, 1, 2)        # tRNA-synthetases.bhmm: M = 185, 192, 247
@@ -463,6 +535,19 @@ def main():
     h2d = int(dsq.nbytes + wins.nbytes)
     d2h = int(sc.nbytes + st.nbytes)
 
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+
+    # ---- the integer filters' roofline (rank 0; the strand is still resident on the device)
+    filters = None
+    if rank == 0 and not args.no_filters_leg:
+        filters = filters_leg(ctx, model, len(dsq_np) - 2, hbm_peak, hbm_src)
+
     # ---- second metric: the whole search, config 4 as written: ONE target, three profiles, blocks dealt to the N devices by one process
     # (rank 0 drives every device; the other ranks wait at the barrier with their devices idle)
     search = None
@@ -481,13 +566,6 @@ def main():
             dist.destroy_process_group()
         return
 
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     per_gpu_cells_s = cells_local * args.steps / (dev_ms * 1e-3)
     achieved_tf = FLOP_PER_CELL * per_gpu_cells_s / 1e12
     # DRAM traffic of one launch of the dominant kernel from the committed ncu --set full capture of this same workload
@@ -519,6 +597,8 @@ def main():
         "checks": {"windows": nwin, "status_ok": n_ok, "planted_homologs": nplants, "max_score_nats": float(np.max(sc)),
                    "wall_ms_timed_loop_incl_flush": wall_ms},
     }
+    if filters is not None:
+        out["roofline_filters"] = filters
     if search is not None:
         out["search"] = search
     if world == 1 and not args.no_cpu_baseline:

@@ -253,6 +253,10 @@ int bathgpu_orfs_msv_screen(bathgpu_ctx *ctx, const bathgpu_block *blocks, int n
                             int min_len, const uint8_t *tjb_of, const float *null_of, int max_len, double min_bits,
                             int64_t *norfs_per_block, int64_t *nhits, int64_t *nres);
 int bathgpu_orfs_fetch(bathgpu_ctx *ctx, bathgpu_orf_hit *hits, uint8_t *residues);
+/* Measurement aid: CUDA-event time of the kernel groups of the last bathgpu_orfs_msv_screen call -- ms[0] codon classes, [1] ORF count
+ * pass, [2] ORF emit pass, [3] MSV over every ORF, [4] F1 screen + residue gather -- with the number of ORFs found and the residues the
+ * MSV kernel scored (its DP cells = residues x M). */
+int bathgpu_orfs_stage_breakdown(bathgpu_ctx *ctx, float ms[5], int64_t *norfs, int64_t *residues_scored);
 
 /* ---- a5: the bias-composition filter ---------------------------------------------------------------------------------- */
 /* esl_hmm_Forward over the 2-state filter HMM of p7_bg_SetFilter (src/p7_bg.c:449-471), batched: what p7_bg_FilterScore computes
@@ -298,6 +302,9 @@ int bathgpu_last_stage_timing(const bathgpu_ctx *ctx, float *ms, int *launches);
 /* FP32 FMA throughput of the device (TFLOP/s, best of several launches of a register-only FFMA kernel):
  * the roofline denominator for the frameshift Forward/Backward kernels, which are FP32-pipe bound. */
 int bathgpu_measure_fp32_peak(bathgpu_ctx *ctx, double *tflops, double *sm_mhz_effective);
+/* The same for the integer filters: 16-bit lane operations per second (saturating add and max on the two halves of a register, each
+ * counted), 16 independent chains per thread. */
+int bathgpu_measure_int16_peak(bathgpu_ctx *ctx, double *tera_ops);
 
 #ifdef __cplusplus
 }
