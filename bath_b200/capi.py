@@ -20,7 +20,7 @@ EXPORTS = [
     "bathgpu_fwd_orfs", "bathgpu_fs_fwd_bck_xrows", "bathgpu_select_slot",
     "bathgpu_orf_fwd_bck_xrows", "bathgpu_orf_domains", "bathgpu_orf_fetch_domain_matrices",
     "bathgpu_orfs_msv_screen", "bathgpu_orfs_fetch", "bathgpu_revcomp_slot", "bathgpu_fs_fwd_block", "bathgpu_fs_forward_matrices",
-    "bathgpu_bias_forward", "bathgpu_orfs_stage_breakdown", "bathgpu_measure_int16_peak",
+    "bathgpu_bias_forward", "bathgpu_orfs_stage_breakdown", "bathgpu_measure_int16_peak", "bathgpu_orf_forward_matrices",
 ]
 
 
@@ -136,6 +136,8 @@ def load():
     L.bathgpu_fs_forward_matrices.argtypes = [vp, vp, C.c_int, fp, fp, fp, C.c_int64, fp, ip]
     L.bathgpu_select_slot.restype = C.c_int
     L.bathgpu_select_slot.argtypes = [vp, C.c_int]
+    L.bathgpu_orf_forward_matrices.restype = C.c_int
+    L.bathgpu_orf_forward_matrices.argtypes = [vp, vp, C.c_int, fp, fp, fp, C.c_int64, fp, ip]
     L.bathgpu_measure_int16_peak.restype = C.c_int
     L.bathgpu_measure_int16_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.bathgpu_orfs_stage_breakdown.restype = C.c_int
@@ -374,6 +376,18 @@ class Context:
 
     def revcomp_slot(self, src, dst):
         self._check(self.lib.bathgpu_revcomp_slot(self.h, int(src), int(dst)))
+
+    def orf_forward_matrices(self, regs, M, xfE=(0.5, 0.5)):
+        """bathgpu_orf_forward_matrices: per region the matrix [(L+1)][(M+1)][4] {M, D, I, 0} and the X rows [(L+1)][6]; scores; status"""
+        n = len(regs)
+        Ls = regs["L"].astype(np.int64)
+        off = np.concatenate([[0], np.cumsum(Ls + 1)])
+        mx = np.zeros((int(off[-1]), M + 1, 4), np.float32)
+        xr = np.zeros((int(off[-1]), 6), np.float32)
+        sc, st = np.empty(n, np.float32), np.empty(n, np.int32)
+        xf = np.asarray(xfE, np.float32)
+        self._check(self.lib.bathgpu_orf_forward_matrices(self.h, regs.ctypes.data, n, _f(xf), _f(mx), _f(xr), int(off[-1]), _f(sc), _i(st)))
+        return [mx[off[r]: off[r + 1]] for r in range(n)], [xr[off[r]: off[r + 1]] for r in range(n)], sc, st
 
     def measure_int16_peak(self):
         t = C.c_double(0)

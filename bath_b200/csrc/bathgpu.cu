@@ -1799,6 +1799,101 @@ extern "C" int bathgpu_orf_domains(bathgpu_ctx *ctx, const bathgpu_envelope *env
   return BATHGPU_OK;
 }
 
+// ---- f2, multi-domain regions of the standard branch: p7_Forward over a region of an ORF with the whole matrix handed back
+static cudaError_t dispatch_orf_forward_matrix(int J, const OrfDomainArgs &a, int sms, cudaStream_t s)
+{
+  cudaError_t e = cudaErrorInvalidValue;
+#define X(S) if (launch_orf_forward_matrix_##S(J, a, sms, s, &e)) return e;
+  BATHGPU_FOR_EACH_SET(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
+// stored cells -> out[(row (M+1) + k) 4 + {M, D, I, 0}] (P7_OMX cell order p7X_M, p7X_D, p7X_I; src/impl_sse/impl_sse.h:296-314,
+// un-striped); match cells are stored times Z(k) and divided back here
+__global__ void orf_export_forward_kernel(const float *__restrict__ pp, const float *__restrict__ dcell, const float *__restrict__ zinv,
+                                          int J, int M, int mpad, long long rows, float *__restrict__ out)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * (M + 1)) return;
+  const long long row = t / (M + 1);
+  const int k = (int)(t - row * (M + 1));
+  float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (k > 0) {
+    const int VEC = (J % 4 == 0) ? 4 : ((J % 2 == 0) ? 2 : 1);
+    const int kk = k - 1, lane = kk / J, j = kk % J;
+    const int p = (j / VEC) * (32 * VEC) + lane * VEC + (j % VEC);
+    const float *r = pp + (size_t)row * kPPCellsP * mpad + p;
+    c.x = r[(size_t)PPP_M * mpad] * zinv[kk];
+    c.y = dcell[(size_t)row * mpad + p];
+    c.z = r[(size_t)PPP_I * mpad];
+  }
+  reinterpret_cast<float4 *>(out)[t] = c;
+}
+
+extern "C" int bathgpu_orf_forward_matrices(bathgpu_ctx *ctx, const bathgpu_envelope *regs, int n, const float xfE[2],
+                                            float *mx, float *xrows, int64_t max_rows, float *fwdsc, int32_t *status)
+{
+  if (!ctx || !regs || n < 1 || !xfE || !mx || !xrows || !fwdsc || !status) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_orf_forward_matrices");
+  if (!orf_image(ctx))    return fail(ctx, BATHGPU_EINVAL, "no frameshift profile loaded (its amino-acid rows are the protein profile)");
+  if (ctx->S().nres == 0) return fail(ctx, BATHGPU_EINVAL, "no ORF residues uploaded");
+  int64_t total = 0;
+  for (int e = 0; e < n; ++e) {
+    if (regs[e].L < 1 || regs[e].start < 0 || regs[e].start + regs[e].L > ctx->S().nres)
+      return fail(ctx, BATHGPU_EINVAL, "region %d (offset %lld, L %d) is outside the uploaded residues (n=%lld)", e, (long long)regs[e].start, regs[e].L,
+                  (long long)ctx->S().nres);
+    total += regs[e].L + 1;
+  }
+  if (total > max_rows) return fail(ctx, BATHGPU_EINVAL, "matrix buffer too small: %lld rows needed, %lld given", (long long)total, (long long)max_rows);
+  CUDA_TRY(ctx, enter(ctx));
+  const FsProfileImage &im = *orf_image(ctx);
+  const int M = im.M, mpad = im.mpad;
+  ctx->last_ms = 0.f; ctx->last_launches = 0;
+  const size_t cap_rows = std::max<size_t>(matrix_budget() / 10 * 7 / ((size_t)kPPCellsP * mpad * 4) / 2, 8192);
+  int e0 = 0;
+  int64_t row0 = 0;
+  while (e0 < n) {
+    int e1 = e0;
+    size_t rows = 0;
+    while (e1 < n && (e1 == e0 || rows + regs[e1].L + 1 <= cap_rows)) { rows += regs[e1].L + 1; ++e1; }
+    const int m = e1 - e0;
+    std::vector<long long> xoff(m + 1, 0);
+    for (int e = 0; e < m; ++e) xoff[e + 1] = xoff[e] + regs[e0 + e].L + 1;
+    if (ctx->envs.reserve((size_t)m * sizeof(EnvelopeDesc)) != BATHGPU_OK || ctx->xoff.reserve((size_t)(m + 1) * 8) != BATHGPU_OK ||
+        reserve_matrices(ctx, rows * kPPCellsP * mpad * 4, 0) != BATHGPU_OK || ctx->ddcell.reserve(rows * mpad * 4) != BATHGPU_OK ||
+        ctx->dmxout.reserve(rows * (size_t)(M + 1) * 16) != BATHGPU_OK || ctx->dfx.reserve(rows * 24) != BATHGPU_OK ||
+        ctx->dlsf.reserve(rows * 4) != BATHGPU_OK || ctx->dfw.reserve((size_t)m * 4) != BATHGPU_OK || ctx->doasc.reserve((size_t)m * 4) != BATHGPU_OK ||
+        ctx->dstat.reserve((size_t)m * 4) != BATHGPU_OK || ctx->counter.reserve(64) != BATHGPU_OK)
+      return fail(ctx, BATHGPU_EMEM, "device allocation failed for %d regions (%zu rows, M=%d)", m, rows, M);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->envs.p, regs + e0, (size_t)m * sizeof(EnvelopeDesc), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->xoff.p, xoff.data(), (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    OrfDomainArgs a{};
+    a.emis = im.emis.as<float>(); a.amino0 = im.nrows - BATHGPU_KP; a.cellf = im.cellf5.as<float>();
+    a.residues = ctx->S().residues.as<uint8_t>(); a.envs = ctx->envs.as<EnvelopeDesc>(); a.nenv = m; a.M = M; a.mpad = mpad;
+    a.tEM = xfE[0]; a.tEL = xfE[1]; a.xoff = ctx->xoff.as<long long>();
+    a.pp = ctx->dpp.as<float>(); a.dcell = ctx->ddcell.as<float>(); a.fx = ctx->dfx.as<float>(); a.lsf = ctx->dlsf.as<float>();
+    a.fwdsc = ctx->dfw.as<float>(); a.oasc = ctx->doasc.as<float>(); a.status = ctx->dstat.as<int>(); a.counter = ctx->counter.as<int>();
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    CUDA_TRY(ctx, dispatch_orf_forward_matrix(im.J, a, ctx->prop.multiProcessorCount, ctx->stream));
+    const long long cells = (long long)rows * (M + 1);
+    orf_export_forward_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(ctx->dpp.as<float>(), ctx->ddcell.as<float>(), im.zinv.as<float>(),
+                                                                                        im.J, M, mpad, (long long)rows, ctx->dmxout.as<float>());
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(mx + (size_t)row0 * (M + 1) * 4, ctx->dmxout.p, (size_t)cells * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(xrows + (size_t)row0 * 6, ctx->dfx.p, rows * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(fwdsc + e0, ctx->dfw.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(status + e0, ctx->dstat.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_ms += ms; ctx->last_launches += 2;
+    row0 += (int64_t)rows;
+    e0 = e1;
+  }
+  return BATHGPU_OK;
+}
+
 // Test/diagnostic: matrices of envelope e of the last chunk of the last bathgpu_orf_domains call, un-permuted, in the
 // reference's cell order {M,D,I}: pp and oa [(L+1)][(M+1)][3], ppx / oax [(L+1)][6].
 extern "C" int bathgpu_orf_fetch_domain_matrices(bathgpu_ctx *ctx, int e, float *pp, float *oa, float *ppx, float *oax)

@@ -203,6 +203,17 @@ template <int J> static cudaError_t run_orf(bool full, const OrfDomainArgs &a, c
   orf_oatrace_kernel<<<(a.nenv + 3) / 4, 128, 0, s>>>(a, t);
   return cudaGetLastError();
 }
+// the Forward matrix alone, D cells kept (multi-domain regions of the standard branch: the stochastic traceback reads it)
+bool CAT(launch_orf_forward_matrix_, SETNAME)(int J, const OrfDomainArgs &a, int sms, cudaStream_t s, cudaError_t *err)
+{
+  switch (J) {
+#define X(J_) case J_: *err = cudaMemsetAsync(a.counter, 0, 4, s); if (*err != cudaSuccess) return true; \
+                       orf_forward_kernel<J_, true, true><<<grid_for(orf_forward_kernel<J_, true, true>, 32, 0, a.nenv, sms), 32, 0, s>>>(a); *err = cudaGetLastError(); return true;
+  JLIST(X)
+#undef X
+  default: return false;
+  }
+}
 bool CAT(launch_orf_domains_, SETNAME)(int J, bool full, const OrfDomainArgs &a, const TraceArgs &t, int sms, cudaStream_t s, cudaError_t *err)
 {
   switch (J) {

@@ -37,6 +37,7 @@ struct OrfDomainArgs {
   float           tEM, tEL;
   const long long *xoff;
   float          *pp;          // [rows][2][mpad]
+  float          *dcell;       // [rows][mpad]  Forward D cells (orf_forward_kernel<J, true, true> only: the stochastic trace reads them)
   float          *oa;          // [rows][3][mpad]
   float          *fx, *bx;     // X rows {E,N,J,B,C,SCALE}
   float          *ppx, *oax;
@@ -48,7 +49,7 @@ struct OrfDomainArgs {
   int             lanes_f32;   // floats per SIMD vector of the CPU build whose E-state tie-break is reproduced (4: SSE)
 };
 
-template <int J, bool FULL>
+template <int J, bool FULL, bool KEEPD = false>
 __global__ void __launch_bounds__(32) orf_forward_kernel(OrfDomainArgs a)
 {
   constexpr int VEC = VecOf<J>::V;
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(32) orf_forward_kernel(OrfDomainArgs a)
     float *fxrow = a.fx + (size_t)xo * 6;
     float *lsfrow = a.lsf + xo;
     float *pprow_lane = FULL ? a.pp + (size_t)xo * kPPCellsP * a.mpad + lane * VEC : nullptr;
+    float *drow_lane = KEEPD ? a.dcell + (size_t)xo * a.mpad + lane * VEC : nullptr;
 
     float W[J], I[J];
 #pragma unroll
@@ -85,6 +87,7 @@ __global__ void __launch_bounds__(32) orf_forward_kernel(OrfDomainArgs a)
       for (int j = 0; j < J; ++j) z[j] = 0.f;
       store_row<J, VEC>(pprow_lane + PPP_I * a.mpad, z);
       store_row<J, VEC>(pprow_lane + PPP_M * a.mpad, z);
+      if constexpr (KEEPD) store_row<J, VEC>(drow_lane, z);
     }
 
     int chunk = -64;
@@ -117,10 +120,12 @@ __global__ void __launch_bounds__(32) orf_forward_kernel(OrfDomainArgs a)
       float xB = fmaf(xJ, pmove, xN * pmove);
 
       float ov[J];
+      float dv[KEEPD ? J : 1];
 #pragma unroll
       for (int j = 0; j < J; ++j) {
         float t = fmaf(icur[j], K.im[j], m[j] * K.mm[j]);
         ov[j] = fmaf(d, K.dm[j], t);
+        if constexpr (KEEPD) dv[j] = d;
         if (j + 1 < J) d = fmaf(d, K.dd[j], av[j]);
         I[j] = fmaf(icur[j], K.ii[j], m[j] * K.mi[j]);     // I(i+1,k)
       }
@@ -136,7 +141,7 @@ __global__ void __launch_bounds__(32) orf_forward_kernel(OrfDomainArgs a)
         scale = xE;
         xN *= sf; xC *= sf; xJ *= sf; xB *= sf;
 #pragma unroll
-        for (int j = 0; j < J; ++j) { W[j] *= sf; I[j] *= sf; m[j] *= sf; icur[j] *= sf; }
+        for (int j = 0; j < J; ++j) { W[j] *= sf; I[j] *= sf; m[j] *= sf; icur[j] *= sf; if constexpr (KEEPD) dv[j] *= sf; }
         totscale += logf(xE);
         xE = 1.0f;
       }
@@ -145,6 +150,7 @@ __global__ void __launch_bounds__(32) orf_forward_kernel(OrfDomainArgs a)
         float *row = pprow_lane + (size_t)i * kPPCellsP * a.mpad;
         store_row<J, VEC>(row + PPP_I * a.mpad, icur);
         store_row<J, VEC>(row + PPP_M * a.mpad, m);
+        if constexpr (KEEPD) store_row<J, VEC>(drow_lane + (size_t)i * a.mpad, dv);
       }
       if (lane == 0) {
         float2 *x2 = reinterpret_cast<float2 *>(fxrow + (size_t)i * 6);

@@ -89,7 +89,13 @@ struct ForwardMatrix {                                            // one region 
 struct SpecialOdds { float move, loop, e_move, e_loop; };         // N/J/C -> MOVE and LOOP, E -> MOVE and LOOP of the multihit profile
 bool sample_region_segments(const ForwardMatrix &F, const float *tfv, const SpecialOdds &X, uint32_t seed, int nsamples, int ireg,
                             std::vector<Segment> &out);
-std::vector<Segment> cluster_region_segments(const std::vector<Segment> &sp, int nsamples);
+std::vector<Segment> cluster_region_segments(const std::vector<Segment> &sp, int nsamples, bool protein = false);
+// the standard-translation flavour (region_trace_ensemble, src/p7_domaindef.c:766-860): mx = [(L+1)][(M+1)][4] {M, D, I, 0} of
+// bathgpu_orf_forward_matrices, res[1..L] = the region's residues, rf = amino-acid emission odds [Kp][M+1]; besides the sampled
+// segments (ORF coordinates: ireg = first residue of the region) n2sc[1..L] receives log(mean over the samples of the per-residue
+// null2 odds), the position-specific null2 score rescore_isolated_domain_bath sums when null2_is_done
+bool sample_region_segments_protein(const ForwardMatrix &F, const float *tfv, const float *rf, const SpecialOdds &X, uint32_t seed, int nsamples,
+                                    int ireg, const uint8_t *res, std::vector<Segment> &out, std::vector<float> &n2sc);
 
 int   builder_max_length(const CoreModel &h, double emit_thresh);
 int   amino_code(char c);

@@ -1838,7 +1838,7 @@ int run_batch(bathhost_search *s)
 
     // p7_DomainDecoding (src/impl_sse/decoding.c:160-196) and the region logic of p7_domaindef_ByPosteriorHeuristics_BATH
     // (src/p7_domaindef.c:500-618); ORFs are independent here (the length model is saved and restored around each)
-    struct SEnv { int z, i, j; };
+    struct SEnv { int z, i, j; bool multi = false; std::shared_ptr<std::vector<float>> n2sc; };   // n2sc: per-ORF-position null2 scores from the trace ensemble
     std::vector<std::vector<SEnv>> env_of(nq);
     std::vector<int> nreg(nq, 0), nmulti(nq, 0);
     parallel_chunks(nq, 1, [&](size_t za, size_t zb) {
@@ -1876,13 +1876,63 @@ int run_batch(bathhost_search *s)
             nreg[z]++;
             float mx = -1.0f;                               // is_multidomain_region (:652-664)
             for (int zz = i; zz <= j; ++zz) mx = std::max(mx, std::min(etot[zz] - etot[i - 1], btot[j] - btot[zz - 1]));
-            if (mx >= rt3) nmulti[z]++;                     // stochastic clustering not restated: rescored as ONE envelope
-            env_of[z].push_back(SEnv{ (int) z, i, j });
+            if (mx >= rt3) nmulti[z]++;
+            SEnv se; se.z = (int) z; se.i = i; se.j = j; se.multi = (mx >= rt3);
+            env_of[z].push_back(se);
             i = -1; triggered = false;
           }
         }
       }
     });
+    // ---- multi-domain regions (is_multidomain_region): resolved by clustering an ensemble of stochastic tracebacks
+    // (src/p7_domaindef.c:551-600).  The Forward matrices of all flagged regions of the unit come from one device call (multihit
+    // mode at the ORF's own length model: om's length was set to the ORF's, :510, :561); sampling, null2-by-trace and clustering on
+    // the host cores (stotrace.cpp), one region per task; each cluster then takes the region's place as an envelope of its own.
+    if (BE.orf_forward_matrices) {
+      struct MReg { size_t z, e; };
+      std::vector<MReg> mregs;
+      for (size_t z = 0; z < nq; ++z) for (size_t e = 0; e < env_of[z].size(); ++e) if (env_of[z][e].multi) mregs.push_back(MReg{ z, e });
+      if (!mregs.empty()) {
+        std::vector<bathgpu_envelope> regs(mregs.size());
+        std::vector<int64_t> off(mregs.size() + 1, 0);
+        for (size_t r = 0; r < mregs.size(); ++r) {
+          const SEnv &se = env_of[mregs[r].z][mregs[r].e];
+          regs[r].start = od[mregs[r].z].offset + se.i - 1; regs[r].L = se.j - se.i + 1;
+          bathhost_length_model(od[mregs[r].z].L, 1.0f, &regs[r].pmove, &regs[r].ploop);      // p7_oprofile_ReconfigMultihit(om, saveL)
+          off[r + 1] = off[r] + regs[r].L + 1;
+        }
+        std::vector<float> mxbuf((size_t) off.back() * (M + 1) * 4), xrbuf((size_t) off.back() * 6), rsc(regs.size());
+        std::vector<int32_t> rst(regs.size());
+        const float xfEmh[2] = { 0.5f, 0.5f };
+        BE_TRY(s, BE.orf_forward_matrices(BE.ctx, regs.data(), (int) regs.size(), xfEmh, mxbuf.data(), xrbuf.data(), off.back(), rsc.data(), rst.data()),
+               "bathgpu_orf_forward_matrices");
+        std::vector<std::vector<SEnv>> repl(mregs.size());
+        const float *rf_amino = m->om3.rfv.data() + (size_t) (m->om3.nrows - kKp) * (M + 1);
+        parallel_chunks(mregs.size(), 1, [&](size_t ra, size_t rb) {
+          for (size_t r = ra; r < rb; ++r) {
+            const SEnv &se = env_of[mregs[r].z][mregs[r].e];
+            if (rst[r] != 0) continue;                       // Forward out of range: no clusters, no envelope
+            const ForwardMatrix F{ mxbuf.data() + (size_t) off[r] * (M + 1) * 4, xrbuf.data() + (size_t) off[r] * 6, M, regs[r].L };
+            const SpecialOdds X{ regs[r].pmove, regs[r].ploop, xfEmh[0], xfEmh[1] };
+            const uint8_t *rres = S.residues.data() + od[mregs[r].z].offset + se.i - 2;       // rres[p] = residue p of the region
+            std::vector<Segment> sp;
+            std::vector<float> n2r;
+            if (!sample_region_segments_protein(F, m->om3.tfv.data(), rf_amino, X, 42u, 200, se.i, rres, sp, n2r)) continue;
+            auto n2 = std::make_shared<std::vector<float>>((size_t) od[mregs[r].z].L + 2, 0.0f);
+            for (int p = 1; p <= regs[r].L; ++p) (*n2)[(size_t) (se.i + p - 1)] = n2r[(size_t) p];
+            for (const Segment &g : cluster_region_segments(sp, 200, true)) {
+              SEnv c; c.z = se.z; c.i = g.i; c.j = g.j; c.multi = false; c.n2sc = n2;
+              repl[r].push_back(c);
+            }
+          }
+        });
+        for (size_t r = mregs.size(); r-- > 0;) {              // back to front: positions in env_of[z] stay valid
+          std::vector<SEnv> &v = env_of[mregs[r].z];
+          v.erase(v.begin() + (long) mregs[r].e);
+          v.insert(v.begin() + (long) mregs[r].e, repl[r].begin(), repl[r].end());
+        }
+      }
+    }
     std::vector<SEnv> envs;
     std::vector<bathgpu_envelope> ge;
     int64_t max_steps = 0;
@@ -1947,7 +1997,8 @@ int run_batch(bathhost_search *s)
       const float aliscore = ali_score(m, dom.tr, wdsq);
       if (aliscore < 0.0f) continue;
       float domcorrection = 0.0f;                            // (:1296-1305)
-      for (int pos = i; pos <= j; ++pos) domcorrection += logf(r.null2[res_o[pos]]);
+      if (envs[e].n2sc) { for (int pos = i; pos <= j; ++pos) domcorrection += (*envs[e].n2sc)[(size_t) pos]; }   // null2_is_done (:1295)
+      else for (int pos = i; pos <= j; ++pos) domcorrection += logf(r.null2[res_o[pos]]);
       dom.domcorrection = std::max(0.f, domcorrection);
       int z1 = 0, z2 = (int) dom.tr.size() - 1;
       while (z1 < (int) dom.tr.size() && dom.tr[z1].st != TS_M) ++z1;

@@ -15,7 +15,8 @@ EXPORTS = [
     "bathhost_orf_length_params", "bathhost_model_computed_max_length",
     "bathhost_search_create", "bathhost_search_create_multi", "bathhost_search_queue", "bathhost_search_run", "bathhost_search_destroy", "bathhost_search_last_error", "bathhost_search_sequence",
     "bathhost_search_finish", "bathhost_search_nhits", "bathhost_search_get_hit", "bathhost_search_get_stats",
-    "bathhost_sample_region_segments", "bathhost_cluster_region_segments", "bathhost_search_format_tblout",
+    "bathhost_sample_region_segments", "bathhost_cluster_region_segments", "bathhost_sample_region_segments_protein",
+    "bathhost_cluster_region_segments_protein", "bathhost_search_format_tblout",
     "bathhost_calibrate", "bathhost_model_lambda", "bathhost_search_format_report", "bathhost_search_format_output", "bathhost_search_format_fstblout",
 ]
 
@@ -35,7 +36,7 @@ class FilterParams(C.Structure):
 class Backend(C.Structure):
     """bathhost_backend: the device library as a table of function pointers (include/bathhost.h)"""
     _names = ["last_error", "load_fs_profile", "load_filter_profile", "select_slot", "upload_block", "upload_orfs", "msv_orfs", "ssv_windows",
-              "vit_orfs", "fwd_orfs", "fs_fwd_windows", "fs_fwd_bck_xrows", "fs_bck_decode", "fs_domains", "fs_forward_matrices", "orf_fwd_bck_xrows", "orf_domains", "orfs_msv_screen", "orfs_fetch", "revcomp_slot", "host_alloc", "host_free", "bias_forward"]
+              "vit_orfs", "fwd_orfs", "fs_fwd_windows", "fs_fwd_bck_xrows", "fs_bck_decode", "fs_domains", "fs_forward_matrices", "orf_fwd_bck_xrows", "orf_domains", "orfs_msv_screen", "orfs_fetch", "revcomp_slot", "host_alloc", "host_free", "bias_forward", "orf_forward_matrices"]
     _fields_ = [("ctx", C.c_void_p)] + [(n, C.c_void_p) for n in _names]
 
 
@@ -413,8 +414,43 @@ def sample_region_segments(mx, xrows, tfv, odds, ireg, seed=42, nsamples=200):
     return [(g.idx, g.i, g.j, g.k, g.m, g.prob) for g in out[:n.value]]
 
 
-def cluster_region_segments(segments, nsamples=200):
+def sample_region_segments_protein(mx, xrows, tfv, rf, odds, ireg, res, seed=42, nsamples=200):
+    """bathhost_sample_region_segments_protein: (segments, n2sc[0..L]) for one region's protein Forward matrix mx [(L+1)][(M+1)][4]
+    {M, D, I, 0}; res = the region's residues (length L); rf = amino-acid emission odds [29][M+1]"""
+    import numpy as np
     L = load()
+    mx = np.ascontiguousarray(mx, np.float32); xr = np.ascontiguousarray(xrows, np.float32)
+    tf = np.ascontiguousarray(tfv, np.float32); od = np.ascontiguousarray(odds, np.float32); rfa = np.ascontiguousarray(rf, np.float32)
+    r1 = np.concatenate([[255], np.asarray(res, np.uint8), [255]]).astype(np.uint8)
+    fp = C.POINTER(C.c_float)
+    cap = nsamples * 64
+    out = (Segment * cap)()
+    n = C.c_int(0)
+    Lr = mx.shape[0] - 1
+    n2 = np.zeros(Lr + 1, np.float32)
+    f = L.bathhost_sample_region_segments_protein
+    f.restype = C.c_int
+    f.argtypes = [fp, fp, C.c_int, C.c_int, fp, fp, fp, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(Segment), C.c_int,
+                  C.POINTER(C.c_int), fp]
+    st = f(mx.ctypes.data_as(fp), xr.ctypes.data_as(fp), mx.shape[1] - 1, Lr, tf.ctypes.data_as(fp), rfa.ctypes.data_as(fp),
+           od.ctypes.data_as(fp), seed, nsamples, ireg, r1.ctypes.data_as(C.POINTER(C.c_uint8)), out, cap, C.byref(n), n2.ctypes.data_as(fp))
+    if st != 0:
+        raise RuntimeError(f"bathhost_sample_region_segments_protein: status {st}")
+    return [(g.idx, g.i, g.j, g.k, g.m, g.prob) for g in out[:n.value]], n2
+
+
+def cluster_region_segments(segments, nsamples=200, protein=False):
+    L = load()
+    if protein:
+        L.bathhost_cluster_region_segments_protein.restype = C.c_int
+        L.bathhost_cluster_region_segments_protein.argtypes = L.bathhost_cluster_region_segments.argtypes
+        sp = (Segment * max(1, len(segments)))(*[Segment(*g) for g in segments])
+        out = (Segment * 64)()
+        n = C.c_int(0)
+        st = L.bathhost_cluster_region_segments_protein(sp, len(segments), nsamples, out, 64, C.byref(n))
+        if st != 0:
+            raise RuntimeError(f"bathhost_cluster_region_segments_protein: status {st}")
+        return [(g.idx, g.i, g.j, g.k, g.m, g.prob) for g in out[:n.value]]
     sp = (Segment * max(1, len(segments)))(*[Segment(*g) for g in segments])
     out = (Segment * 64)()
     n = C.c_int(0)

@@ -289,6 +289,13 @@ int bathgpu_orf_fwd_bck_xrows(bathgpu_ctx *ctx, const bathgpu_orf *orfs, int n, 
  * coordinates (1..L) and c = 0; the caller maps them to nucleotides as p7_trace_fs_Convert does (src/p7_trace.c:405). */
 int bathgpu_orf_domains(bathgpu_ctx *ctx, const bathgpu_envelope *envs, int n, const float xfE[2],
                         bathgpu_domain_result *results, bathgpu_trace_step *traces, int64_t max_steps);
+/* p7_Forward over regions of ORFs with the whole matrix handed back, for the multi-domain branch of the standard-translation domain
+ * definition: replaces p7_Forward(orfsq->dsq+i-1, j-i+1, om, fwd, NULL) at src/p7_domaindef.c:562 for all flagged regions of a batch
+ * at once (om in multihit mode at the ORF's length: pmove / ploop of the descriptor, xfE = {0.5, 0.5}).  regs[r].start = 0-based
+ * offset of the region's first residue in the slot's residue buffer.  mx: [(L+1)][(M+1)][4] = {M, D, I, 0} per region (what P7_OMX
+ * dpf holds, un-striped), xrows: [(L+1)][6]; regions concatenated; max_rows = capacity of both in rows. */
+int bathgpu_orf_forward_matrices(bathgpu_ctx *ctx, const bathgpu_envelope *regs, int n, const float xfE[2],
+                                 float *mx, float *xrows, int64_t max_rows, float *fwdsc, int32_t *status);
 
 /* Test/diagnostic: matrices of envelope e of the last chunk of the last bathgpu_orf_domains call, cell order {M,D,I}:
  * pp and oa [(L+1)][(M+1)][3], ppx / oax [(L+1)][6].  Any pointer may be NULL. */

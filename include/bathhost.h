@@ -129,6 +129,10 @@ typedef struct {
   /* optional (may be NULL: the host library then runs the same recursion on the host cores): bathgpu_bias_forward */
   int (*bias_forward)(void *ctx, int kind, const void *items, int n, const float *tables, int ntab, float t10, float t11,
                       const uint8_t gcode[64], float *out);
+  /* optional (may be NULL: multi-domain regions of the standard branch are then rescored as one envelope and counted in
+   * stats.n_multidomain_regions only): bathgpu_orf_forward_matrices */
+  int (*orf_forward_matrices)(void *ctx, const void *regs, int n, const float xfE[2], float *mx, float *xrows, int64_t max_rows,
+                              float *fwdsc, int32_t *status);
 } bathhost_backend;
 
 /* 0 / unset fields take bathsearch's defaults (src/p7_pipeline.c:145-214; src/bathsearch.c:94) */
@@ -174,6 +178,14 @@ typedef struct { int32_t idx, i, j, k, m; float prob; } bathhost_segment;
 int bathhost_sample_region_segments(const float *mx, const float *xrows, int M, int L, const float *tfv, const float odds[4],
                                     uint32_t seed, int nsamples, int ireg, bathhost_segment *out, int max_out, int *nout);
 int bathhost_cluster_region_segments(const bathhost_segment *sp, int n, int nsamples, bathhost_segment *out, int max_out, int *nout);
+/* The standard-translation flavour (region_trace_ensemble, src/p7_domaindef.c:766-860; p7_StochasticTrace, src/impl_sse/stotrace.c;
+ * p7_Null2_ByTrace, src/impl_sse/null2.c:131-219; p7_spensemble_Cluster with the protein link rule, src/p7_spensemble.c:191-218).
+ * mx: one region of bathgpu_orf_forward_matrices' output [(L+1)][(M+1)][4] {M, D, I, 0}; rf: amino-acid emission odds [29][M+1];
+ * res[1..L]: the region's residues; n2sc[0..L] receives the per-residue null2 scores (log of the ensemble mean odds). */
+int bathhost_sample_region_segments_protein(const float *mx, const float *xrows, int M, int L, const float *tfv, const float *rf,
+                                            const float odds[4], uint32_t seed, int nsamples, int ireg, const uint8_t *res,
+                                            bathhost_segment *out, int max_out, int *nout, float *n2sc);
+int bathhost_cluster_region_segments_protein(const bathhost_segment *sp, int n, int nsamples, bathhost_segment *out, int max_out, int *nout);
 
 typedef struct bathhost_search bathhost_search;
 int  bathhost_search_create(const bathhost_model *m, const bathhost_backend *be, const bathhost_options *opt, bathhost_search **ret);

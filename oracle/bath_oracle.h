@@ -286,6 +286,12 @@ int bo_spensemble_fs_Cluster(const BO_SEGMENT *sp, int n, int nsamples, float mi
                              float min_posterior, float min_endpointp, BO_SEGMENT *out, int max_out);
 int bo_region_trace_ensemble_frameshift(const BO_FS_OPROFILE *om, const BO_MX *fwd, int ireg, int jreg, uint32_t seed, int nsamples,
                                         BO_SEGMENT *samples, int max_samples, int *ret_nsamples, BO_SEGMENT *out, int max_out);
+/* ===== stotrace.c: the standard-translation flavour (src/impl_sse/stotrace.c, null2.c:131-219, p7_domaindef.c:766-860) ===== */
+int bo_spensemble_Cluster(const BO_SEGMENT *sp, int n, int nsamples, float min_overlap, int of_smaller, int max_diagdiff,
+                          float min_posterior, float min_endpointp, BO_SEGMENT *out, int max_out);
+int bo_StochasticTrace(BO_RNG *rng, int L, const BO_OPROFILE *om, const BO_MX *ox, BO_TRACE *tr);
+int bo_region_trace_ensemble(const BO_OPROFILE *om, const uint8_t *dsq, const BO_MX *fwd, int ireg, int jreg, uint32_t seed, int nsamples,
+                             BO_SEGMENT *samples, int max_samples, int *ret_nsamples, BO_SEGMENT *out, int max_out, float *n2sc);
 
 /* ===== calibrate.c (src/evalues.c: p7_Calibrate, p7_Lambda, p7_MSVMu, p7_ViterbiMu, p7_Tau, p7_fs_Tau_3codons/_5codons) ===== */
 double bo_Lambda(const BO_HMM *hmm, const BO_BG *bg);

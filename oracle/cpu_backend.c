@@ -680,3 +680,46 @@ int bo_backend_bias_forward(void *ctx, int kind, const void *items, int n, const
   parallel_for(b, n, bias_item_fn, &j);
   return BO_OK;
 }
+
+/* ---- f2, multi-domain regions of the standard branch (bathgpu_orf_forward_matrices): p7_Forward over a region of an ORF in multihit
+ * mode at the ORF's length model, whole matrix handed back (src/p7_domaindef.c:561-562): cells {M, D, I, 0} per (row, node) */
+typedef struct { const bathgpu_envelope *e; const float *xfE; float *mx, *xr, *sc; int32_t *st; const int64_t *off; } orffm_args;
+static void orffm_item(bo_backend *b, void *arg, int i)
+{
+  orffm_args *a = arg;
+  const bathgpu_envelope *e = &a->e[i];
+  BO_OPROFILE om = *b->om;
+  int L = e->L, M = om.M, r, k;
+  uint8_t *sub = malloc((size_t) L + 2);
+  BO_MX *fwd = bo_mx_create(M, L, 3);
+  float *mx = a->mx + (size_t) a->off[i] * (M + 1) * 4, *xr = a->xr + (size_t) a->off[i] * 6;
+  sub[0] = sub[L + 1] = BO_DSQ_SENTINEL;
+  memcpy(sub + 1, b->res[b->cur] + e->start, (size_t) L);
+  om.nj = 1.0f;
+  set_length_model(&om, e->pmove, e->ploop, a->xfE);
+  a->st[i] = bo_Forward(sub, L, &om, fwd, &a->sc[i]);
+  for (r = 0; r <= L; r++) {
+    for (k = 0; k <= M; k++) {
+      float *c = mx + ((size_t) r * (M + 1) + k) * 4;
+      c[0] = fwd->dp[((size_t) r * (M + 1) + k) * 3 + BO_S_M]; c[1] = fwd->dp[((size_t) r * (M + 1) + k) * 3 + BO_S_D];
+      c[2] = fwd->dp[((size_t) r * (M + 1) + k) * 3 + BO_S_I]; c[3] = 0.0f;
+    }
+    memcpy(xr + (size_t) r * 6, fwd->xmx + (size_t) r * 6, sizeof(float) * 6);
+  }
+  bo_mx_destroy(fwd); free(sub);
+}
+int bo_backend_orf_forward_matrices(void *ctx, const void *regs, int n, const float xfE[2], float *mx, float *xrows, int64_t max_rows,
+                                    float *fwdsc, int32_t *status)
+{
+  bo_backend *b = ctx;
+  const bathgpu_envelope *e = regs;
+  int64_t *off = malloc(sizeof(int64_t) * (size_t) (n + 1));
+  orffm_args a = { e, xfE, mx, xrows, fwdsc, status, off };
+  int i;
+  off[0] = 0;
+  for (i = 0; i < n; i++) off[i + 1] = off[i] + e[i].L + 1;
+  if (off[n] > max_rows) { free(off); snprintf(b->err, sizeof b->err, "matrix buffer too small"); return BO_EINVAL; }
+  parallel_for(b, n, orffm_item, &a);
+  free(off);
+  return BO_OK;
+}

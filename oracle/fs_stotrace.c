@@ -53,7 +53,7 @@ double bo_random(BO_RNG *r)
   return (double) r->x / 4294967296.0;
 }
 
-static void fnorm(float *v, int n)
+void bo_fnorm(float *v, int n)
 {
   float sum = 0.0f, c = 0.0f, y, t;
   int   x;
@@ -62,7 +62,7 @@ static void fnorm(float *v, int n)
   else             for (x = 0; x < n; x++) v[x] = 1.0f / (float) n;
 }
 
-static int fchoose(BO_RNG *r, const float *p, int n)
+int bo_fchoose(BO_RNG *r, const float *p, int n)
 {
   double roll = bo_random(r), sum = 0.0;
   int    i;
@@ -80,8 +80,8 @@ static int select_m(BO_RNG *r, const BO_FS_OPROFILE *om, const BO_MX *ox, int i,
   path[1] = (k > 1) ? FC(ox, i, k - 1, BO_FS_M) * TF(BO_T_MM, k - 1) : 0.0f;     /* node 0 is the zero shifted in by rightshiftz */
   path[2] = (k > 1) ? FC(ox, i, k - 1, BO_FS_I) * TF(BO_T_IM, k - 1) : 0.0f;
   path[3] = (k > 1) ? FC(ox, i, k - 1, BO_FS_D) * TF(BO_T_DM, k - 1) : 0.0f;
-  fnorm(path, 4);
-  return state[fchoose(r, path, 4)];
+  bo_fnorm(path, 4);
+  return state[bo_fchoose(r, path, 4)];
 }
 
 static int select_d(BO_RNG *r, const BO_FS_OPROFILE *om, const BO_MX *ox, int i, int k)
@@ -90,8 +90,8 @@ static int select_d(BO_RNG *r, const BO_FS_OPROFILE *om, const BO_MX *ox, int i,
   float path[2];
   path[0] = (k > 1) ? FC(ox, i, k - 1, BO_FS_M) * TF(BO_T_MD, k - 1) : 0.0f;
   path[1] = (k > 1) ? FC(ox, i, k - 1, BO_FS_D) * TF(BO_T_DD, k - 1) : 0.0f;
-  fnorm(path, 2);
-  return state[fchoose(r, path, 2)];
+  bo_fnorm(path, 2);
+  return state[bo_fchoose(r, path, 2)];
 }
 
 static int select_i(BO_RNG *r, const BO_FS_OPROFILE *om, const BO_MX *ox, int i, int k)
@@ -101,8 +101,8 @@ static int select_i(BO_RNG *r, const BO_FS_OPROFILE *om, const BO_MX *ox, int i,
   if (i < 3) return -1;                     /* the reference would read before the matrix */
   path[0] = FC(ox, i - 3, k, BO_FS_M) * TF(BO_T_MI, k);
   path[1] = FC(ox, i - 3, k, BO_FS_I) * TF(BO_T_II, k);
-  fnorm(path, 2);
-  return state[fchoose(r, path, 2)];
+  bo_fnorm(path, 2);
+  return state[bo_fchoose(r, path, 2)];
 }
 
 static int select_cj(BO_RNG *r, const BO_FS_OPROFILE *om, const BO_MX *ox, int i, int cell, float loop, float e_odds, int self)
@@ -114,8 +114,8 @@ static int select_cj(BO_RNG *r, const BO_FS_OPROFILE *om, const BO_MX *ox, int i
   path[1] = XM(ox, i - 2, cell) * loop * s2;
   path[2] = XM(ox, i - 1, cell) * loop * s2 * s1;
   path[3] = XM(ox, i, BO_XC_E) * e_odds * s2 * s1 * s0;
-  fnorm(path, 4);
-  return (fchoose(r, path, 4) < 3) ? self : BO_ST_E;
+  bo_fnorm(path, 4);
+  return (bo_fchoose(r, path, 4) < 3) ? self : BO_ST_E;
 }
 
 static int select_e(BO_RNG *r, const BO_MX *ox, int i, int *ret_k)
@@ -139,8 +139,8 @@ static int select_b(BO_RNG *r, const BO_FS_OPROFILE *om, const BO_MX *ox, int i)
   float path[2];
   path[0] = XM(ox, i, BO_XC_N) * om->xf[BO_X_N][BO_O_MOVE];
   path[1] = XM(ox, i, BO_XC_J) * om->xf[BO_X_J][BO_O_MOVE];
-  fnorm(path, 2);
-  return state[fchoose(r, path, 2)];
+  bo_fnorm(path, 2);
+  return state[bo_fchoose(r, path, 2)];
 }
 
 static int select_codon_len(BO_RNG *r, const BO_MX *ox, int i, int k)
@@ -148,8 +148,8 @@ static int select_codon_len(BO_RNG *r, const BO_MX *ox, int i, int k)
   float path[5];
   int   c;
   for (c = 0; c < 5; c++) path[c] = FC(ox, i, k, BO_FS_M + 1 + c);
-  fnorm(path, 5);
-  return fchoose(r, path, 5) + 1;
+  bo_fnorm(path, 5);
+  return bo_fchoose(r, path, 5) + 1;
 }
 
 /* p7_StochasticTrace_Frameshift (stotrace_fs.c:72-128) */
@@ -207,6 +207,7 @@ int bo_trace_fs_Index(const BO_TRACE *tr, BO_SEGMENT *seg, int max_seg)
 }
 
 /* link_spsamples_fs (p7_spensemble.c:226-256) */
+static int link_protein = 0;    /* link_spsamples (p7_spensemble.c:191-218) instead of link_spsamples_fs: residue, not nucleotide, diagonals */
 static int link_fs(const BO_SEGMENT *h1, const BO_SEGMENT *h2, float min_overlap, int of_smaller, int max_diagdiff)
 {
   int nov, n, d1, d2;
@@ -218,6 +219,11 @@ static int link_fs(const BO_SEGMENT *h1, const BO_SEGMENT *h2, float min_overlap
   nov = MIN_(h1->m, h2->m) - MAX_(h1->k, h2->k);
   n   = of_smaller ? MIN_(h1->m - h1->k + 1, h2->m - h2->k + 1) : MAX_(h1->m - h1->k + 1, h2->m - h2->k + 1);
   if ((float) nov / (float) n < min_overlap) return 0;
+  if (link_protein) {
+    d1 = h1->i - h1->k; d2 = h2->i - h2->k; if (abs(d1 - d2) <= max_diagdiff) return 1;
+    d1 = h1->j - h1->m; d2 = h2->j - h2->m; if (abs(d1 - d2) <= max_diagdiff) return 1;
+    return 0;
+  }
   d1 = (h1->i / 3) - h1->k; d2 = (h2->i / 3) - h2->k; if (abs(d1 - d2) <= max_diagdiff) return 1;
   d1 = (h1->j / 3) - h1->m; d2 = (h2->j / 3) - h2->m; if (abs(d1 - d2) <= max_diagdiff) return 1;
   return 0;
@@ -325,5 +331,17 @@ int bo_region_trace_ensemble_frameshift(const BO_FS_OPROFILE *om, const BO_MX *f
   if (ret_nsamples) *ret_nsamples = n;
   nc = bo_spensemble_fs_Cluster(sp, n, nsamples, 0.8f, 1, 4, 0.25f, 0.02f, out, max_out);
   bo_trace_destroy(tr); free(sp);
+  return nc;
+}
+
+/* p7_spensemble_Cluster (p7_spensemble.c:300-440): the same procedure with the protein link rule.  Not re-entrant (tests call it
+ * from one thread). */
+int bo_spensemble_Cluster(const BO_SEGMENT *sp, int n, int nsamples, float min_overlap, int of_smaller, int max_diagdiff,
+                          float min_posterior, float min_endpointp, BO_SEGMENT *out, int max_out)
+{
+  int nc;
+  link_protein = 1;
+  nc = bo_spensemble_fs_Cluster(sp, n, nsamples, min_overlap, of_smaller, max_diagdiff, min_posterior, min_endpointp, out, max_out);
+  link_protein = 0;
   return nc;
 }
