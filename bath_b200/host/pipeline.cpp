@@ -242,6 +242,33 @@ struct HostBuf {
   ~HostBuf() { if (p) { if (release) release(p); else free(p); } }
 };
 
+// Large scratch arrays of a batch (the decoding products of every window: ~80 bytes per window row, 0.5-0.7 GB per 1 Gbp profile) come
+// from a process-wide free list instead of the heap: glibc hands freed blocks of this size back to the kernel, so every search paid
+// for mapping and zeroing them again, from all host threads at once (page-fault storms: 35 -> 175 ms on the same phase).
+class ScratchPool {
+ public:
+  static ScratchPool &get() { static ScratchPool p; return p; }
+  std::vector<float> take(size_t n)
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    size_t best = idle_.size();
+    for (size_t z = 0; z < idle_.size(); ++z) if (idle_[z].capacity() >= n && (best == idle_.size() || idle_[z].capacity() < idle_[best].capacity())) best = z;
+    std::vector<float> v;
+    if (best < idle_.size()) { v.swap(idle_[best]); idle_.erase(idle_.begin() + (long) best); }
+    return v;                                      // the caller resizes; contents are whatever the last user left
+  }
+  void give(std::vector<float> &&v)
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (v.capacity() == 0) return;
+    if (idle_.size() >= 64) { size_t small = 0; for (size_t z = 1; z < idle_.size(); ++z) if (idle_[z].capacity() < idle_[small].capacity()) small = z; idle_.erase(idle_.begin() + (long) small); }
+    idle_.push_back(std::move(v));
+  }
+ private:
+  std::mutex mu_;
+  std::vector<std::vector<float>> idle_;
+};
+
 struct SeqRef {                                  // one queued target sequence (the caller keeps dsq alive until the batch has run)
   std::string name;
   const uint8_t *dsq = nullptr;                  // 1..n with sentinels
@@ -1136,7 +1163,7 @@ int run_batch(bathhost_search *s)
     if (target <= 0) {
       static const long long env_mbp = [] { const char *e = getenv("BATHHOST_CHUNK_MBP"); return e ? atoll(e) : 0LL; }();
       target = env_mbp > 0 ? env_mbp * 1000000LL
-                           : std::max<long long>(4000000LL, std::min<long long>(32000000LL, total / (long long) (3 * s->bes.size()) + 1));
+                           : std::max<long long>(4000000LL, std::min<long long>(64000000LL, total / (long long) (2 * s->bes.size()) + 1));
     }
     for (size_t b = 0; b < nb; ++b) {
       const BlockInfo &blk = blocks[b];
@@ -1246,8 +1273,13 @@ int run_batch(bathhost_search *s)
   // arbitration between window and ORFs (:1392-1465), Forward + Backward X rows of the windows that stay (:1469-1470), and the
   // part of p7_DomainDecoding_Frameshift that does not depend on the length-model chain
   const float xfE3[2] = { m->om3.xfE_move, m->om3.xfE_loop };
-  struct Decoded { std::vector<float> btot, etot, fb, ex; };   // fb, ex: [L+1][9]
+  struct Decoded { float *btot = nullptr, *etot = nullptr, *fb = nullptr, *ex = nullptr; };   // btot, etot: [L+1]; fb, ex: [L+1][9]; views into the unit's block
   std::vector<std::vector<Decoded>> dec(units.size());
+  struct DecBlocks {                                          // one block per unit, from the process-wide pool and back to it when the batch is done
+    std::vector<std::vector<float>> v;
+    explicit DecBlocks(size_t n) : v(n) {}
+    ~DecBlocks() { for (auto &b : v) ScratchPool::get().give(std::move(b)); }
+  } dec_blocks(units.size());
   rc = for_each_backend(s, [&](int be) -> int {
     const bathhost_backend &BE = s->bes[(size_t) be];
     for (int c : chunks_of_be[(size_t) be])
@@ -1420,14 +1452,23 @@ int run_batch(bathhost_search *s)
         // the nine forward x backward products and their scale factors per row)
         std::vector<Decoded> &DV = dec[(size_t) (2 * c + sidx)];
         DV.resize(S.fsw.size());
+        {
+          std::vector<float> &blk = dec_blocks.v[(size_t) (2 * c + sidx)];
+          blk = ScratchPool::get().take(S.xoff.back() * 20);
+          blk.resize(S.xoff.back() * 20);
+          for (size_t z = 0; z < S.fsw.size(); ++z) {
+            float *base = blk.data() + S.xoff[z] * 20;
+            const size_t rows = S.xoff[z + 1] - S.xoff[z];     // Lw + 1
+            DV[z].btot = base; DV[z].etot = base + rows; DV[z].fb = base + 2 * rows; DV[z].ex = base + 11 * rows;
+          }
+        }
         parallel_chunks(S.fsw.size(), 1, [&](size_t za, size_t zb) {
           for (size_t z = za; z < zb; ++z) {
             if (S.st2[z] != 0) continue;
             const int Lw = S.dwin[S.fsw[z]].length;
             const float *xf = S.fxr + S.xoff[z] * 6, *xb = S.bxr + S.xoff[z] * 6;
             Decoded &D = DV[z];
-            D.btot.assign((size_t) Lw + 1, 0.f); D.etot.assign((size_t) Lw + 1, 0.f);
-            D.fb.assign(((size_t) Lw + 1) * 9, 0.f); D.ex.assign(((size_t) Lw + 1) * 9, 0.f);
+            memset(D.btot, 0, sizeof(float) * ((size_t) Lw + 1) * 20);
             std::vector<float> lsf((size_t) Lw + 2), lsb((size_t) Lw + 2);
             lsf[0] = logf(xf[5]);
             for (int i = 1; i <= Lw; ++i) lsf[i] = lsf[i - 1] + logf(xf[(size_t) i * 6 + 5]);
@@ -1508,7 +1549,7 @@ int run_batch(bathhost_search *s)
           const float tL = 1.0f - (2.0f + om5_nj) / ((float) om5_L + 2.0f + om5_nj);
           // mocc[i] = 1 - sum over N,J,C and the three codon offsets of fwd * bck * loop odds * scale (decoding_fs.c:309-352)
           const Decoded &D = dec[(size_t) sidx][z];
-          const std::vector<float> &btot = D.btot, &etot = D.etot;
+          const float *btot = D.btot, *etot = D.etot;
           std::vector<float> mocc((size_t) Lw + 1, 0.f);
           for (int i = 3; i <= Lw; ++i) {
             float njcp = 0.;
