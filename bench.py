@@ -57,7 +57,9 @@ def parse_args():
     ap.add_argument("--search-mbp", type=float, default=1000.0,
                     help="also run the whole stage-batched bathsearch --fs pipeline (3 profiles) over a genome of this many Mbp (0 = skip)")
     ap.add_argument("--no-filters-leg", action="store_true", help="skip the integer-filter roofline leg")
-    ap.add_argument("--contexts-per-gpu", type=int, default=8, help="device contexts per GPU in the search leg")
+    ap.add_argument("--contexts-per-gpu", type=int, default=0,
+                    help="device contexts per GPU in the search leg (0: 8 on one or two GPUs, 16 in all beyond that -- every context has a host "
+                         "thread of its own, and past ~16 of them the host side of the search is oversubscribed)")
     return ap.parse_args()
 
 
@@ -353,10 +355,10 @@ def search_leg(devices, per_gpu, mbp, cpu_mbp, with_cpu):
                    "contexts, the hit-window list / length-model chain / residue counts are kept in the reference's serial order on the "
                    "host, one merged hit list per profile; stage times in stats are summed over contexts"}
     if len(devices) > 1:                                        # the same search on one device: the tables must agree byte for byte
-        one = [capi.Context(devices[0]) for _ in range(per_gpu)]
+        one = [capi.Context(devices[0]) for _ in range(8)]       # the 1-GPU configuration of this bench
         run_search(models, pinned, gpu_ctxs=one)
         secs1, tables1, _, _ = run_search(models, pinned, gpu_ctxs=one)
-        out["one_gpu"] = {"value": total_nt * len(models) / sum(secs1) / 1e6, "seconds": sum(secs1)}
+        out["one_gpu"] = {"value": total_nt * len(models) / sum(secs1) / 1e6, "seconds": sum(secs1), "contexts_per_gpu": 8}
         out["checks"]["hits_identical_to_1gpu"] = bool(tables1 == tables)
         for c in one:
             c.close()
@@ -559,7 +561,8 @@ def main():
         barrier()
         devices = ranks.search_devices(rank, world, torch.cuda.device_count())
         if devices:
-            search = search_leg(devices, args.contexts_per_gpu, args.search_mbp, args.search_cpu_mbp, world == 1 and not args.no_cpu_baseline)
+            per_gpu = args.contexts_per_gpu if args.contexts_per_gpu > 0 else max(2, min(8, 16 // len(devices)))
+            search = search_leg(devices, per_gpu, args.search_mbp, args.search_cpu_mbp, world == 1 and not args.no_cpu_baseline)
         cpu_barrier()
 
     if rank != 0:
