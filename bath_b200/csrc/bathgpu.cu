@@ -1950,7 +1950,7 @@ extern "C" int bathgpu_bias_forward(bathgpu_ctx *ctx, int kind, const bathgpu_bi
   a.residues = S.residues.as<uint8_t>(); a.dna4 = S.dna4.as<uint32_t>(); a.out = ctx->b_out.as<float>();
   if (gcode) memcpy(a.gcode, gcode, 64);
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  const long long nthreads = (long long)n * per;
+  const long long nthreads = (long long)n * per * 32;           // a warp per item
   bias_forward_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, ctx->stream>>>(a);
   CUDA_TRY(ctx, cudaGetLastError());
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));

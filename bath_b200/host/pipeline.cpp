@@ -191,6 +191,7 @@ struct Domain {
 // one character per core trace position (five for the nucleotide line); codon[] = codon length, 0 delete, 6 stop codon
 struct AliDisplay {
   std::string model, mline, aseq, ntseq, ppline, csline, rfline;
+  std::string cigar;                 // the whole CIGAR string (bathhost_hit::cigar holds its first 1023 characters)
   std::vector<uint8_t> codon;
   int N = 0;
   void size_for(int n, bool cs, bool rf)          // all lines are written by column index: one allocation each
@@ -611,6 +612,7 @@ void summarize_alignment(const bathhost_model *m, const std::vector<bathgpu_trac
   h.shifts = shifts; h.stops = stops;
   h.pid = core.empty() ? 0.0f : ((float) exact / (float) core.size()) * 100;
   snprintf(h.cigar, sizeof h.cigar, "%s", cigar.c_str());
+  if (ad) ad->cigar = cigar;
 }
 
 // ---- a batch of target sequences, both strands, stage-batched and dealt to one or more devices ---------------------------
@@ -1163,7 +1165,7 @@ int run_batch(bathhost_search *s)
     if (target <= 0) {
       static const long long env_mbp = [] { const char *e = getenv("BATHHOST_CHUNK_MBP"); return e ? atoll(e) : 0LL; }();
       target = env_mbp > 0 ? env_mbp * 1000000LL
-                           : std::max<long long>(4000000LL, std::min<long long>(64000000LL, total / (long long) (2 * s->bes.size()) + 1));
+                           : std::max<long long>(4000000LL, std::min<long long>(128000000LL, total / (long long) s->bes.size() + 1));
     }
     for (size_t b = 0; b < nb; ++b) {
       const BlockInfo &blk = blocks[b];
@@ -2122,6 +2124,7 @@ int run_batch(bathhost_search *s)
         }
         h.pub.pid = ncore ? ((float) exact / ncore) * 100 : 0.0f;
         snprintf(h.pub.cigar, sizeof h.pub.cigar, "%s", cigar.c_str());
+        h.ad.cigar = cigar;
       }
       h.sortkey = -dom_lnP;
       S.hits_std.emplace_back(b, std::move(h));
@@ -2364,7 +2367,7 @@ extern "C" int bathhost_search_format_tblout(const bathhost_search *s, int show_
         posw, (long long) h.pub.ali_to);
     put(" %9.2g %6.1f %5.1f %5.2f", h.pub.evalue, h.pub.score, h.pub.bias, h.pub.pid);
     if (fs_pipe) put(" %7d %6d", h.pub.shifts, h.pub.stops);
-    put(" %s\n", h.pub.cigar);
+    put(" %s\n", h.ad.cigar.empty() ? h.pub.cigar : h.ad.cigar.c_str());
   }
   *needed = out.size() + 1;
   if (out.size() + 1 > cap) return buf ? BATHHOST_EINVAL : BATHHOST_OK;

@@ -158,7 +158,7 @@ typedef struct {
   double  evalue, lnP;
   float   score, bias, pre_score, envsc, oasc, pid;     /* score, bias, pre_score in bits, as the tables print them (src/p7_tophits.c:1325) */
   int32_t shifts, stops, trace_len;
-  char    cigar[1024];
+  char    cigar[1024];          /* the first 1023 characters; bathhost_search_format_tblout prints the whole string */
 } bathhost_hit;
 
 typedef struct {
