@@ -871,12 +871,13 @@ extern "C" int bathgpu_fs_fwd_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_
 // Forward parser stage
 // BATHGPU_FWD=1|3|4 forces a kernel generation for A/B runs (1: one row per block of code; 3: the row-pair schedule; 4: row pairs on
 // packed FP32, fs_parser_v4.cuh).  Unset: per node count, what measured faster on B200 (profiles/r02_forward_v3_v4.md): the packed
-// kernel from 10 nodes per lane up (M > 256: +21 % at M = 279), the scalar row-pair kernel below (equal at 6, spills at 7-8).
+// kernel at 10 nodes per lane (256 < M <= 320: +21 % at M = 279), the scalar row-pair kernel elsewhere (equal at 6 and 12, the packed one
+// spills at 7-8 and loses a third at 16: 628 vs 907 GCUPS at M = 409).
 static int fwd_version(int J)
 {
   static const int forced = [] { const char *e = getenv("BATHGPU_FWD"); int x = e ? atoi(e) : 0; return (x == 1 || x == 3 || x == 4) ? x : 0; }();
   if (forced) return forced;
-  return (J >= 10) ? 4 : 3;
+  return (J == 10) ? 4 : 3;
 }
 
 // one launch entry per kernel family and node-count set (launch.h; kernels_tu.cu)
