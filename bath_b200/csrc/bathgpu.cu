@@ -339,7 +339,8 @@ static const int kSupportedJ[] = { 1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 24, 32 };
 
 static int choose_J(int M)
 {
-  for (int J : kSupportedJ) if (32 * J >= M) return J;
+  static const int bump = [] { const char *e = getenv("BATHGPU_J_BUMP"); return e ? atoi(e) : 0; }();   // tuning: odd node counts rounded up to even
+  for (int J : kSupportedJ) if (32 * J >= M) return (bump && J >= 3 && J <= 7 && (J & 1)) ? J + 1 : J;
   return 0;
 }
 
@@ -869,13 +870,12 @@ extern "C" int bathgpu_fs_fwd_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_
 
 // ---------------------------------------------------------------------------------------------
 // Forward parser stage
-// BATHGPU_FWD=1|3|4 forces a kernel generation for A/B runs (1: one row per block of code; 3: the row-pair schedule; 4: row pairs on
-// packed FP32, fs_parser_v4.cuh).  Unset: per node count, what measured faster on B200 (profiles/r02_forward_v3_v4.md): the packed
+// BATHGPU_FWD=3|4 forces a kernel generation for A/B runs (3: the row-pair schedule; 4: row pairs on packed FP32, fs_parser_v4.cuh).  Unset: per node count, what measured faster on B200 (profiles/r02_forward_v3_v4.md): the packed
 // kernel at 10 nodes per lane (256 < M <= 320: +21 % at M = 279), the scalar row-pair kernel elsewhere (equal at 6 and 12, the packed one
 // spills at 7-8 and loses a third at 16: 628 vs 907 GCUPS at M = 409).
 static int fwd_version(int J)
 {
-  static const int forced = [] { const char *e = getenv("BATHGPU_FWD"); int x = e ? atoi(e) : 0; return (x == 1 || x == 3 || x == 4) ? x : 0; }();
+  static const int forced = [] { const char *e = getenv("BATHGPU_FWD"); int x = e ? atoi(e) : 0; return (x == 3 || x == 4) ? x : 0; }();
   if (forced) return forced;
   return (J == 10) ? 4 : 3;
 }

@@ -127,96 +127,6 @@ struct FwdConsts {
   float bs[5];
 };
 
-// One DP row of the Forward parser.  r = i + pad is the padded row number (pad rows i<0 in front so
-// that the last quad ends exactly at row L); PH = r & 3 is compile time, so ring slots are register names.
-template <int J, int VEC, int PH, bool XMX>
-__device__ __forceinline__ void fwd_row(int i, int lane, FwdState<J> &S, const FwdConsts<J> &K,
-                                        const char *__restrict__ emis_lane, unsigned rowbytes, uint32_t cw,
-                                        float ploop, float pmove, float tEL, float tEM,
-                                        float &totscale, float *__restrict__ xrow)
-{
-  constexpr int P0 = PH, P1 = (PH + 3) & 3, P2 = (PH + 2) & 3, P3 = (PH + 1) & 3;  // slots of rows i, i-1, i-2, i-3
-  float e2[J], e3[J], e4[J], m[J];
-  // cw packs the three emission-row indices of this DP row: c2 | c3 << 9 | c4 << 18
-  load_emission_row<J, VEC>(reinterpret_cast<const float *>(emis_lane + (size_t)(cw & 511u) * rowbytes), e2);
-  load_emission_row<J, VEC>(reinterpret_cast<const float *>(emis_lane + (size_t)((cw >> 9) & 511u) * rowbytes), e3);
-  load_emission_row<J, VEC>(reinterpret_cast<const float *>(emis_lane + (size_t)(cw >> 18) * rowbytes), e4);
-
-  // Mz(i,k) = Z(k) M(i,k),  M(i,k) = V(i) R2 + V(i-1) R3 + V(i-2) R4        (fwdback_fs.c:390-392)
-  // E(i)    = sum_k M(i,k) + D(i,k) = sum_k Mz(i,k)                           (:393,456-459)
-  float es0 = 0.f, es1 = 0.f;
-#pragma unroll
-  for (int j = 0; j < J; ++j) {
-    float t = S.W[P0][j] * e2[j];
-    t = fmaf(S.W[P1][j], e3[j], t);
-    t = fmaf(S.W[P2][j], e4[j], t);
-    m[j] = t;
-    if (j == 0) es0 = t * K.qm[0]; else if (j == 1) es1 = t * K.qm[1]; else if (j & 1) es1 = fmaf(t, K.qm[j], es1); else es0 = fmaf(t, K.qm[j], es0);
-  }
-  float xE = warp_allsum(J > 1 ? es0 + es1 : es0);
-
-  // D chain (:415-453), in the scaled form of FwdConsts: lane carry-out with zero carry-in, warp scan of carries,
-  // then the lane re-runs the recurrence from its true carry-in.
-  float A = 0.f;
-#pragma unroll
-  for (int j = 0; j < J; ++j) A = (j == 0) ? m[0] : fmaf(A, K.dd[j], m[j]);
-#pragma unroll
-  for (int s = 0; s < 5; ++s) {
-    float up = __shfl_up_sync(0xffffffffu, A, 1 << s);
-    A = fmaf(K.bs[s], up, A);
-  }
-  float d = __shfl_up_sync(0xffffffffu, A, 1);      // D(i, first node of this lane)
-  if (lane == 0) d = 0.f;
-
-  // specials   (:462-465; rows 0..2 hold N at 1.0, :155,279; pad rows i<0 hold everything at 0)
-  float xN = (i < 3) ? ((i >= 0) ? 1.0f : 0.0f) : S.xN[P3] * ploop;
-  float xJ = fmaf(S.xJ[P3], ploop, xE * tEL);
-  float xC = fmaf(S.xC[P3], ploop, xE * tEM);
-  float xB = fmaf(xJ, pmove, xN * pmove);
-
-  // flow into node k+1, per unit of entry odds:  O'(k) = (M tMM + I tIM + D tDM)(k) / s(k+1)
-  // W(i+2)[k+1] = B(i) + O'(k)                                                  (:383-387)
-  // I(i+3)[k]   = M(i,k) tMI + I(i,k) tII                                       (:408-409)
-  float o[J];
-#pragma unroll
-  for (int j = 0; j < J; ++j) {
-    float t = fmaf(S.I[P0][j], K.hi[j], m[j]);
-    o[j] = fmaf(d, K.dm[j], t);
-    if (j + 1 < J) d = fmaf(d, K.dd[j], m[j]);
-    S.I[P1][j] = fmaf(S.I[P0][j], K.ii[j], m[j]);               // slot (i+3)&3 == (i-1)&3
-  }
-  float oprev = __shfl_up_sync(0xffffffffu, o[J - 1], 1);
-  if (lane == 0) oprev = 0.f;
-  S.W[P2][0] = xB + oprev;
-#pragma unroll
-  for (int j = 1; j < J; ++j) S.W[P2][j] = xB + o[j - 1];
-
-  float scale = 1.0f;
-  if (xE > 1.0e4f) {             // sparse rescaling (:472-496); warp-uniform branch
-    float sf = 1.0f / xE;
-    scale = xE;
-    xN *= sf; xJ *= sf; xC *= sf; xB *= sf;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-#pragma unroll
-      for (int j = 0; j < J; ++j) { S.W[r][j] *= sf; S.I[r][j] *= sf; }
-      S.xN[r] *= sf; S.xJ[r] *= sf; S.xC[r] *= sf;
-    }
-    totscale += logf(xE);
-    xE = 1.0f;
-  }
-  S.xN[P0] = xN; S.xJ[P0] = xJ; S.xC[P0] = xC;
-
-  if constexpr (XMX) {
-    if (lane == 0 && i >= 0) {
-      float2 *x2 = reinterpret_cast<float2 *>(xrow + (size_t)i * 6);
-      x2[0] = make_float2(xE, xN);
-      x2[1] = make_float2(xJ, xB);
-      x2[2] = make_float2(xC, scale);
-    }
-  }
-}
-
 template <int J>
 __device__ __forceinline__ void load_fwd_consts(const float *__restrict__ cc, int lane, FwdConsts<J> &K)
 {
@@ -232,30 +142,6 @@ __device__ __forceinline__ void load_fwd_consts(const float *__restrict__ cc, in
   for (int s = 0; s < 5; ++s) K.bs[s] = __ldg(cc + FC_COUNT * J * kWarp + (FL_B0 + s) * kWarp + lane);
 }
 
-// One warp per block; kMinBlocks = resident warps per SM the kernel is compiled for (sets the register
-// budget: 65536 / (32 * kMinBlocks)).  Tuned on B200: occupancy beats spill-free slack up to a point.
-#ifndef BATHGPU_WARPS_J6
-#define BATHGPU_WARPS_J6 15
-#endif
-#ifndef BATHGPU_WARPS_J7
-#define BATHGPU_WARPS_J7 13
-#endif
-#ifndef BATHGPU_WARPS_J8
-#define BATHGPU_WARPS_J8 12
-#endif
-#ifndef BATHGPU_WARPS_J5
-#define BATHGPU_WARPS_J5 16
-#endif
-#ifndef BATHGPU_WARPS_J4
-#define BATHGPU_WARPS_J4 18
-#endif
-template <int J> struct FwdTune {
-  static constexpr int kThreads   = 32;
-  static constexpr int kMinBlocks = (J <= 3) ? 20 : (J == 4) ? BATHGPU_WARPS_J4 : (J == 5) ? BATHGPU_WARPS_J5 :
-                                    (J == 6) ? BATHGPU_WARPS_J6 : (J == 7) ? BATHGPU_WARPS_J7 :
-                                    (J == 8) ? BATHGPU_WARPS_J8 : 8;
-};
-
 // Codon words for 32 consecutive padded rows, one per lane: lane l handles padded row r0 + l, i.e.
 // DP row i = r0 + l - pad.  n[p] for p outside 1..L or a degenerate code is the placeholder 338
 // (fwdback_fs.c:176-178,344), which the index clamps turn into the degenerate emission rows (:347-349).
@@ -268,77 +154,6 @@ __device__ __forceinline__ uint32_t codon_word(uint32_t lo, uint32_t hi, int sh,
   w = (w < 4 && i - 1 >= 1 && i - 1 <= L) ? w : 338;
   x = (x < 4 && i     >= 1 && i     <= L) ? x : 338;
   return (uint32_t)codon2_fs3(w, x) | ((uint32_t)codon3_fs3(v, w, x) << 9) | ((uint32_t)codon4_fs3(u, v, w, x) << 18);
-}
-
-template <int J, bool XMX>
-__global__ void __launch_bounds__(FwdTune<J>::kThreads, FwdTune<J>::kMinBlocks) fs3_forward_parser_kernel(FsParserArgs a)
-{
-  constexpr int VEC = VecOf<J>::V;
-  const int lane = threadIdx.x & 31;
-
-  FwdConsts<J> K;                      // per-lane profile constants -> registers, once per warp
-  load_fwd_consts<J>(a.cellc, lane, K);
-  const char    *emis_lane = reinterpret_cast<const char *>(a.emis + lane * VEC);
-  const unsigned rowbytes  = (unsigned)a.mpad * 4u;
-
-  for (;;) {
-    int w = 0;
-    if (lane == 0) w = atomicAdd(a.counter, 1);
-    w = __shfl_sync(0xffffffffu, w, 0);
-    if (w >= a.nwin) break;
-
-    const WindowDesc wd = a.wins[w];
-    const int   L     = wd.L;
-    const float pmove = wd.pmove, ploop = wd.ploop;
-    float *xrow = nullptr;
-    if constexpr (XMX) xrow = a.xmx + (size_t)a.xoff[w] * 6;
-
-    FwdState<J> S;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-#pragma unroll
-      for (int j = 0; j < J; ++j) { S.W[r][j] = 0.f; S.I[r][j] = 0.f; }
-      S.xN[r] = 0.f; S.xJ[r] = 0.f; S.xC[r] = 0.f;
-    }
-    float totscale = 0.f;
-
-    // padded rows r = 0 .. 4*nq-1 map to DP rows i = r - pad; pad in 0..3 so that the last row is i = L
-    const int nq  = (L + 4) >> 2;                 // ceil((L+1)/4)
-    const int pad = 4 * nq - (L + 1);
-    // nibble index (in the packed block, guard word included) of n[i-3] for this lane's row of chunk 0
-    long long nib = (wd.start - 1) + (long long)(lane - pad - 3) - 1 + 8;
-    uint32_t lo = __ldg(a.dna4 + (nib >> 3)), hi = __ldg(a.dna4 + (nib >> 3) + 1);
-    int i = -pad;
-
-    for (int q0 = 0; q0 < nq; q0 += 8) {
-      const uint32_t cwl = codon_word(lo, hi, (int)(nib & 7) * 4, i + lane, L);
-      nib += 32;
-      if (q0 + 8 < nq) { lo = __ldg(a.dna4 + (nib >> 3)); hi = __ldg(a.dna4 + (nib >> 3) + 1); }   // next chunk, a chunk ahead
-      const int qn = min(8, nq - q0);
-      for (int qq = 0; qq < qn; ++qq) {
-#define BATHGPU_ROW(PH_)                                                                              \
-        {                                                                                             \
-          uint32_t cw = __shfl_sync(0xffffffffu, cwl, qq * 4 + PH_);                                  \
-          fwd_row<J, VEC, PH_, XMX>(i, lane, S, K, emis_lane, rowbytes, cw, ploop, pmove,             \
-                                    a.tEL, a.tEM, totscale, xrow);                                    \
-          ++i;                                                                                        \
-        }
-        BATHGPU_ROW(0) BATHGPU_ROW(1) BATHGPU_ROW(2) BATHGPU_ROW(3)
-#undef BATHGPU_ROW
-      }
-    }
-
-    // final score (:513-529): (C(L) + C(L-1) tCL + C(L-2) tCL) tCM; row L sits in slot 3
-    {
-      float tot = S.xC[3] + S.xC[2] * ploop + S.xC[1] * ploop;
-      int   st  = 0;
-      float sc;
-      if (isnan(tot) || isinf(tot))  { st = 16; sc = tot; }
-      else if (L > 2 && tot == 0.0f) { st = 16; sc = -INFINITY; }
-      else sc = totscale + logf(tot * pmove);
-      if (lane == 0) { a.fwdsc[w] = sc; a.status[w] = st; }
-    }
-  }
 }
 
 }  // namespace bathgpu

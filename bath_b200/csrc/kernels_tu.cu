@@ -87,12 +87,11 @@ template <int J, bool XMX> static cudaError_t run_fwd(int version, const FsParse
     else if (a.scan_steps == 3) fs3_forward_parser_kernel_v4<J, XMX, 3><<<fwd_grid(fs3_forward_parser_kernel_v4<J, XMX, 3>, J, a.nwin, sms), 32, 0, s>>>(a);
     else                        fs3_forward_parser_kernel_v4<J, XMX, 5><<<fwd_grid(fs3_forward_parser_kernel_v4<J, XMX, 5>, J, a.nwin, sms), 32, 0, s>>>(a);
   }
-  else if (version >= 3) {
+  else {                              // scalar row pairs (fs_parser_v3.cuh); the first-generation one-row kernel is gone
     if (a.scan_steps <= 2)      fs3_forward_parser_kernel_v3<J, XMX, 2><<<fwd_grid(fs3_forward_parser_kernel_v3<J, XMX, 2>, J, a.nwin, sms), 32, 0, s>>>(a);
     else if (a.scan_steps == 3) fs3_forward_parser_kernel_v3<J, XMX, 3><<<fwd_grid(fs3_forward_parser_kernel_v3<J, XMX, 3>, J, a.nwin, sms), 32, 0, s>>>(a);
     else                        fs3_forward_parser_kernel_v3<J, XMX, 5><<<fwd_grid(fs3_forward_parser_kernel_v3<J, XMX, 5>, J, a.nwin, sms), 32, 0, s>>>(a);
   }
-  else fs3_forward_parser_kernel<J, XMX><<<grid_for(fs3_forward_parser_kernel<J, XMX>, FwdTune<J>::kThreads, 0, a.nwin, sms), FwdTune<J>::kThreads, 0, s>>>(a);
   return cudaGetLastError();
 }
 bool CAT(launch_fs3_forward_, SETNAME)(int J, bool xmx, int version, const FsParserArgs &a, int sms, cudaStream_t s, cudaError_t *err)
@@ -108,7 +107,10 @@ void CAT(preload_fwd_, SETNAME)(int J)
 {
   switch (J) {
 #define X(J_) case J_: touch(fs3_forward_parser_kernel_v3<J_, false, 2>); touch(fs3_forward_parser_kernel_v3<J_, true, 2>); touch(fs3_forward_parser_kernel_v3<J_, false, 3>); \
-                       touch(fs3_forward_parser_kernel_v3<J_, true, 3>); touch(fs3_forward_parser_kernel_v3<J_, false, 5>); touch(fs3_forward_parser_kernel_v3<J_, true, 5>); break;
+                       touch(fs3_forward_parser_kernel_v3<J_, true, 3>); touch(fs3_forward_parser_kernel_v3<J_, false, 5>); touch(fs3_forward_parser_kernel_v3<J_, true, 5>); \
+                       if (J_ == 10) { touch(fs3_forward_parser_kernel_v4<J_, false, 2>); touch(fs3_forward_parser_kernel_v4<J_, true, 2>); touch(fs3_forward_parser_kernel_v4<J_, false, 3>); \
+                                       touch(fs3_forward_parser_kernel_v4<J_, true, 3>); touch(fs3_forward_parser_kernel_v4<J_, false, 5>); touch(fs3_forward_parser_kernel_v4<J_, true, 5>); } \
+                       break;
   JLIST(X)
 #undef X
   default: break;

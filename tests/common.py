@@ -16,6 +16,7 @@ AA = "ACDEFGHIKLMNPQRSTVWY"
 
 SYNTHETIC = {   # long models for the kernels' large-M instantiations: node blocks of shipped models concatenated
     "synthetic_M377.bhmm": [("tRNA-synthetases.bhmm", 0), ("tRNA-synthetases.bhmm", 1)],
+    "synthetic_M208.bhmm": [("tRNA-proteins.bhmm", 11), ("tRNA-proteins.bhmm", 1)],
     "synthetic_M624.bhmm": [("tRNA-synthetases.bhmm", 0), ("tRNA-synthetases.bhmm", 1), ("tRNA-synthetases.bhmm", 2)],
     "synthetic_M903.bhmm": [("tRNA-synthetases.bhmm", 0), ("tRNA-synthetases.bhmm", 1), ("tRNA-synthetases.bhmm", 2), ("PTHR37536.bhmm", 0)],
 }
