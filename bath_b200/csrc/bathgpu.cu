@@ -71,6 +71,7 @@ struct FsProfileImage {
   int   which = 0, M = 0, nrows = 0, J = 0, mpad = 0, scan_steps = 5;
   DevBuf emis;     // [nrows][mpad]
   DevBuf emis_bck, cellb3;   // the 3-codon Backward parser's table copy and constants (fs_backward.cuh, Bck3Consts)
+  DevBuf cellbmw;  // the same for the multi-warp Backward kernel (fs_backward_mw.cuh)
   DevBuf emis_fwd; // [nrows][mpad] the Forward parsers' copy: match->match odds folded in as well (fs_parser.cuh, FwdConsts)
   DevBuf cellc;    // forward lane constants
   DevBuf cellmw;   // the same for the multi-warp Forward kernel (J >= 16: 8 nodes per lane, J/8 warps per window)
@@ -577,6 +578,50 @@ extern "C" int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int n
       }
       b.swap(nb);
     }
+    if (which == 3 && J >= 16) {
+      // multi-warp Backward kernel (fs_backward_mw.cuh): virtual lane v = 32 w + lane owns nodes JW v + 1 .. JW v + JW
+      const int JW = kMwNodesPerLane, NW = J / JW, VL = 32 * NW;
+      std::vector<float> mw((size_t)(5 * JW + 6) * VL + 2 * NW, 0.0f);
+      std::vector<double> lp(VL, 1.0);
+      for (int v = 0; v < VL; ++v)
+        for (int j = 0; j < JW; ++j) {
+          const int k = v * JW + j + 1;
+          if (k <= M) {
+            mw[(size_t)(0 * JW + j) * VL + v] = (float)(1.0 / vmmE(k - 1));
+            mw[(size_t)(1 * JW + j) * VL + v] = (float)dd3(k);
+            mw[(size_t)(2 * JW + j) * VL + v] = (k < M) ? (float)(rE(k + 1) * T(tMD, k) / zK[k]) : 0.0f;
+            mw[(size_t)(3 * JW + j) * VL + v] = (float)(uE(k) * T(tMI, k) / zK[k]);
+            mw[(size_t)(4 * JW + j) * VL + v] = (float)T(tII, k);
+          }
+          lp[v] *= (k <= M) ? dd3(k) : 0.0;
+        }
+      for (int w = 0; w < NW; ++w) {
+        std::vector<double> bw(lp.begin() + 32 * w, lp.begin() + 32 * w + 32);
+        for (int s2 = 0; s2 < 5; ++s2) {
+          const int d = 1 << s2;
+          std::vector<double> nb(bw);
+          for (int lane = 0; lane < 32; ++lane) {
+            mw[(size_t)(5 * JW + s2) * VL + 32 * w + lane] = (lane + d <= 31) ? (float)bw[lane] : 0.0f;
+            if (lane + d <= 31) nb[lane] = bw[lane] * bw[lane + d];
+          }
+          bw.swap(nb);
+        }
+        const int k_a = 32 * w * JW + 1, k_b = 32 * (w + 1) * JW;          // first and last node of the warp
+        auto ddk = [&](int k) -> double { return (k >= 1 && k <= M) ? dd3(k) : 0.0; };
+        for (int lane = 0; lane < 31; ++lane) {                            // QU: from the first node of lane + 1 to the warp's last node but one
+          double qq = 1.0;
+          for (int k = (32 * w + lane + 1) * JW + 1; k <= k_b - 1; ++k) qq *= ddk(k);
+          mw[(size_t)(5 * JW + 5) * VL + 32 * w + lane] = (float)qq;
+        }
+        double pw = 1.0;
+        for (int k = k_a; k <= k_b - 1; ++k) pw *= ddk(k);
+        mw[(size_t)(5 * JW + 6) * VL + w] = (float)pw;
+        mw[(size_t)(5 * JW + 6) * VL + NW + w] = (float)ddk(k_b);
+      }
+      if (im.cellbmw.reserve(mw.size() * sizeof(float)) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
+      CUDA_TRY(ctx, cudaMemcpyAsync(im.cellbmw.p, mw.data(), mw.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    } else im.cellbmw.release();
     if (im.cellb3.reserve(cc.size() * sizeof(float)) != BATHGPU_OK || im.emis_bck.reserve(eb.size() * sizeof(float)) != BATHGPU_OK)
       return fail(ctx, BATHGPU_EMEM, "device allocation failed");
     CUDA_TRY(ctx, cudaMemcpyAsync(im.cellb3.p, cc.data(), cc.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
@@ -1010,7 +1055,7 @@ static int bck_decode_chunk(bathgpu_ctx *ctx, const bathgpu_window *wins, int n,
   CUDA_TRY(ctx, dispatch_fwd(true, im.J, fa, sms, ctx->stream));
 
   FsBackwardArgs ba{};
-  ba.emis = im.emis_bck.as<float>(); ba.cellb = im.cellb3.as<float>(); ba.dna4 = fa.dna4; ba.wins = fa.wins; ba.nwin = n; ba.mpad = im.mpad;
+  ba.emis = im.emis_bck.as<float>(); ba.cellb = im.cellb3.as<float>(); ba.cellbmw = im.cellbmw.as<float>(); ba.dna4 = fa.dna4; ba.wins = fa.wins; ba.nwin = n; ba.mpad = im.mpad;
   ba.tEM = xfE[0]; ba.tEL = xfE[1]; ba.fxmx = ctx->fxmx.as<float>(); ba.bxmx = ctx->bxmx.as<float>(); ba.xoff = fa.xoff;
   ba.bcksc = ctx->bcksc.as<float>(); ba.status = fa.status; ba.counter = fa.counter;
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));

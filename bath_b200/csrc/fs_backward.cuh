@@ -44,6 +44,7 @@ enum BckLaneConst { BL_B0 = 0, BL_B1, BL_B2, BL_B3, BL_B4, BL_COUNT };
 struct FsBackwardArgs {
   const float    *emis;        // the Backward parser's table copy: R[c][k] tBM(k-1) Z(k) vmm(k-1), permuted (FsProfileImage::emis_bck)
   const float    *cellb;       // Bck3Consts: [B3_COUNT][J][32] + [5][32]
+  const float    *cellbmw;     // the same for the multi-warp kernel (fs_backward_mw.cuh; J >= 16), or null
   const uint32_t *dna4;
   const WindowDesc *wins;
   int             nwin;

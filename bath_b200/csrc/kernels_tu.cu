@@ -8,6 +8,7 @@
 #include "fs_parser_v4.cuh"
 #include "fs_parser_mw.cuh"
 #include "fs_backward.cuh"
+#include "fs_backward_mw.cuh"
 #include "fs_domain.cuh"
 #include "orf_domain.cuh"
 #include "orf_filters.cuh"
@@ -119,11 +120,25 @@ void CAT(preload_fwd_, SETNAME)(int J)
 #endif
 
 #if BATHGPU_FAMILY == FAM_BCK
+// models past the one-warp kernel's register budget: J/8 warps per window (fs_backward_mw.cuh), from 16 nodes per lane up (M > 384:
+// 434 -> 475 GCUPS at M = 409, 289 -> 363 at M = 624, 202 -> 391 at M = 903).  BATHGPU_BCK_MW=0 keeps the one-warp kernel
+template <int J> static cudaError_t run_bck(const FsBackwardArgs &a, int sms, cudaStream_t s)
+{
+  if constexpr (J >= 16) {
+    static const int mw_mode = [] { const char *e = getenv("BATHGPU_BCK_MW"); return e ? atoi(e) : 1; }();
+    if (a.cellbmw && mw_mode >= 1) {
+      constexpr int NW = J / kMwNodesPerLane;
+      fs3_backward_parser_kernel_mw<NW, kMwNodesPerLane><<<grid_for(fs3_backward_parser_kernel_mw<NW, kMwNodesPerLane>, 32 * NW, 0, a.nwin, sms), 32 * NW, 0, s>>>(a);
+      return cudaGetLastError();
+    }
+  }
+  fs3_backward_parser_kernel<J><<<grid_for(fs3_backward_parser_kernel<J>, BckTune<J>::kThreads, 0, a.nwin, sms), BckTune<J>::kThreads, 0, s>>>(a);
+  return cudaGetLastError();
+}
 bool CAT(launch_fs3_backward_, SETNAME)(int J, const FsBackwardArgs &a, int sms, cudaStream_t s, cudaError_t *err)
 {
   switch (J) {
-#define X(J_) case J_: fs3_backward_parser_kernel<J_><<<grid_for(fs3_backward_parser_kernel<J_>, BckTune<J_>::kThreads, 0, a.nwin, sms), BckTune<J_>::kThreads, 0, s>>>(a); \
-                       *err = cudaGetLastError(); return true;
+#define X(J_) case J_: *err = run_bck<J_>(a, sms, s); return true;
   JLIST(X)
 #undef X
   default: return false;
@@ -132,7 +147,7 @@ bool CAT(launch_fs3_backward_, SETNAME)(int J, const FsBackwardArgs &a, int sms,
 void CAT(preload_bck_, SETNAME)(int J)
 {
   switch (J) {
-#define X(J_) case J_: touch(fs3_backward_parser_kernel<J_>); break;
+#define X(J_) case J_: touch(fs3_backward_parser_kernel<J_>); if constexpr (J_ >= 16) touch(fs3_backward_parser_kernel_mw<J_ / kMwNodesPerLane, kMwNodesPerLane>); break;
   JLIST(X)
 #undef X
   default: break;
