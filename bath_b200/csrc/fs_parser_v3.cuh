@@ -12,6 +12,13 @@
 #pragma once
 #include "fs_parser.cuh"
 
+// The E sums of a row pair reduced in one butterfly (pair_allsum: 6 shuffles for 10).  Measured on B200 per node count
+// (scripts/j_sweep.py, 16 384 windows of 1200 nt): +2.2 % at J = 3 (M = 78), +3.4 % at J = 4 (M = 116-121), +2.9 % at J = 5 (M = 131-152),
+// +4.5 % at J = 2, +1.4 % at J = 8; -1.5 % at J = 6, where the pair sits at the 128-register cap, 0 at J = 7 and 16.
+#ifndef BATHGPU_V3_JOINT_E
+#define BATHGPU_V3_JOINT_E(J) (((J) >= 2 && (J) <= 5) || (J) == 8)
+#endif
+
 namespace bathgpu {
 
 struct RowOut { float xE, xN, xJ, xC, xB, scale; };
@@ -74,6 +81,83 @@ __device__ __forceinline__ void fwd_row_compute(int i, int lane, FwdState<J> &S,
   R.xE = xE; R.xN = xN; R.xJ = xJ; R.xC = xC; R.xB = xB; R.scale = 1.0f;
 }
 
+// The row in two halves, for the joint E reduction of a row pair (fwd_row_pair): the first half ends with the lane's partial E sum
+// and the delete chain's inflow, the second starts from the reduced E.
+template <int J> struct RowMid { float m[J]; float es, d; };
+
+template <int J, int VEC, int PH, int NS>
+__device__ __forceinline__ void fwd_row_front(const FwdState<J> &S, const FwdConsts<J> &K, const char *__restrict__ emis_lane, unsigned rowbytes,
+                                              uint32_t cw, RowMid<J> &X)
+{
+  constexpr int P0 = PH, P1 = (PH + 3) & 3, P2 = (PH + 2) & 3;
+  float e2[J], e3[J], e4[J];
+  load_emission_row<J, VEC>(reinterpret_cast<const float *>(emis_lane + (size_t)(cw & 511u) * rowbytes), e2);
+  load_emission_row<J, VEC>(reinterpret_cast<const float *>(emis_lane + (size_t)((cw >> 9) & 511u) * rowbytes), e3);
+  load_emission_row<J, VEC>(reinterpret_cast<const float *>(emis_lane + (size_t)(cw >> 18) * rowbytes), e4);
+  float es0 = 0.f, es1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    float t = S.W[P2][j] * e4[j];
+    t = fmaf(S.W[P1][j], e3[j], t);
+    t = fmaf(S.W[P0][j], e2[j], t);
+    X.m[j] = t;
+    if (j == 0) es0 = t * K.qm[0]; else if (j == 1) es1 = t * K.qm[1]; else if (j & 1) es1 = fmaf(t, K.qm[j], es1); else es0 = fmaf(t, K.qm[j], es0);
+  }
+  X.es = (J > 1) ? es0 + es1 : es0;
+  float A = 0.f;
+#pragma unroll
+  for (int j = 0; j < J; ++j) A = (j == 0) ? X.m[0] : fmaf(A, K.dd[j], X.m[j]);
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    float up = __shfl_up_sync(0xffffffffu, A, 1 << s);
+    A = fmaf(K.bs[s], up, A);
+  }
+  X.d = __shfl_up_sync(0xffffffffu, A, 1);
+}
+
+template <int J, int PH, bool HEAD>
+__device__ __forceinline__ void fwd_row_back(int i, int lane, FwdState<J> &S, const FwdConsts<J> &K, const RowMid<J> &X, float xE,
+                                             float ploop, float pmove, float tEL, float tEM, RowOut &R)
+{
+  constexpr int P0 = PH, P1 = (PH + 3) & 3, P2 = (PH + 2) & 3, P3 = (PH + 1) & 3;
+  float d = X.d;
+  float xN = S.xN[P3] * ploop;
+  if constexpr (HEAD) xN = (i < 3) ? ((i >= 0) ? 1.0f : 0.0f) : xN;
+  float xJ = fmaf(S.xJ[P3], ploop, xE * tEL);
+  float xC = fmaf(S.xC[P3], ploop, xE * tEM);
+  float xB = fmaf(xJ, pmove, xN * pmove);
+  float o[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    float t = fmaf(S.I[P0][j], K.hi[j], X.m[j]);
+    o[j] = fmaf(d, K.dm[j], t);
+    if (j + 1 < J) d = fmaf(d, K.dd[j], X.m[j]);
+    S.I[P1][j] = fmaf(S.I[P0][j], K.ii[j], X.m[j]);
+  }
+  float oprev = __shfl_up_sync(0xffffffffu, o[J - 1], 1);
+  if (lane == 0) oprev = 0.f;
+  S.W[P2][0] = xB + oprev;
+#pragma unroll
+  for (int j = 1; j < J; ++j) S.W[P2][j] = xB + o[j - 1];
+  S.xN[P0] = xN; S.xJ[P0] = xJ; S.xC[P0] = xC;
+  R.xE = xE; R.xN = xN; R.xJ = xJ; R.xC = xC; R.xB = xB; R.scale = 1.0f;
+}
+
+// Both rows' E sums in one butterfly: lanes 0-15 collect row i, lanes 16-31 row i+1 (6 shuffles for the pair instead of 10); every
+// lane ends with the same bits for each sum (the halves exchange their finished sums), so the rescale test stays warp-uniform.
+__device__ __forceinline__ void pair_allsum(int lane, float a, float b, float &sa, float &sb)
+{
+  const bool lo = lane < 16;
+  float mine = (lo ? a : b) + __shfl_xor_sync(0xffffffffu, lo ? b : a, 16);
+  mine += __shfl_xor_sync(0xffffffffu, mine, 8);
+  mine += __shfl_xor_sync(0xffffffffu, mine, 4);
+  mine += __shfl_xor_sync(0xffffffffu, mine, 2);
+  mine += __shfl_xor_sync(0xffffffffu, mine, 1);
+  const float other = __shfl_xor_sync(0xffffffffu, mine, 16);
+  sa = lo ? mine : other;
+  sb = lo ? other : mine;
+}
+
 template <int J>
 __device__ __forceinline__ void scale_state(FwdState<J> &S, float sf)
 {
@@ -106,8 +190,18 @@ __device__ __forceinline__ void fwd_row_pair(int i, int lane, FwdState<J> &S, co
                                              float &totscale, float *__restrict__ xrow)
 {
   RowOut A, B;
-  fwd_row_compute<J, VEC, PH, NS, HEAD>(i, lane, S, K, emis_lane, rowbytes, cwA, ploop, pmove, tEL, tEM, A);
-  fwd_row_compute<J, VEC, PH + 1, NS, HEAD>(i + 1, lane, S, K, emis_lane, rowbytes, cwB, ploop, pmove, tEL, tEM, B);
+  if constexpr (BATHGPU_V3_JOINT_E(J)) {
+    RowMid<J> XA, XB;
+    fwd_row_front<J, VEC, PH, NS>(S, K, emis_lane, rowbytes, cwA, XA);
+    fwd_row_front<J, VEC, PH + 1, NS>(S, K, emis_lane, rowbytes, cwB, XB);
+    float xEA, xEB;
+    pair_allsum(lane, XA.es, XB.es, xEA, xEB);
+    fwd_row_back<J, PH, HEAD>(i, lane, S, K, XA, xEA, ploop, pmove, tEL, tEM, A);
+    fwd_row_back<J, PH + 1, HEAD>(i + 1, lane, S, K, XB, xEB, ploop, pmove, tEL, tEM, B);
+  } else {
+    fwd_row_compute<J, VEC, PH, NS, HEAD>(i, lane, S, K, emis_lane, rowbytes, cwA, ploop, pmove, tEL, tEM, A);
+    fwd_row_compute<J, VEC, PH + 1, NS, HEAD>(i + 1, lane, S, K, emis_lane, rowbytes, cwB, ploop, pmove, tEL, tEM, B);
+  }
   if (__builtin_expect(A.xE > 1.0e4f || B.xE > 1.0e4f, 0)) {          // rare, warp-uniform
     if (A.xE > 1.0e4f) {
       const float sf = 1.0f / A.xE;
