@@ -36,6 +36,12 @@
 #include <stdint.h>
 #include "fs_parser.cuh"
 
+// The B sums of a row pair in one butterfly (pair_allsum, fs_parser.cuh: 6 shuffles for 10).  Measured on B200 (scripts/j_sweep.py,
+// Forward with X rows + Backward, both sweeps counted): +1-2 % at every node count from 2 to 8 (M = 192: 862 -> 880 GCUPS, M = 134: 683 -> 697).
+#ifndef BATHGPU_BCK_JOINT_B
+#define BATHGPU_BCK_JOINT_B(J) ((J) <= 8)
+#endif
+
 namespace bathgpu {
 
 enum BckCellConst { BC_VMM = 0, BC_VIM, BC_VDM, BC_DD, BC_MD, BC_MI, BC_II, BC_COUNT };
@@ -134,9 +140,12 @@ struct BckRowCtx {
 // including, the rescaling.  Writes Is(i,.) and Mt(i,.) = E(i) + G into slot S0; returns the row's specials, unscaled.
 struct BckOut { float xB, xN, xJ, xC, xE; };
 
+template <int J> struct BckMid { float g[J]; float bsum; };
+
+// everything of the row that does not need B(i): emission products, the lane's share of B(i), the scaled D0 chain, G, the insert row
 template <int J, int VEC, int PH>
-__device__ __forceinline__ BckOut bck_row_core(int lane, BckState<J> &S, const Bck3Consts<J> &K,
-                                               const char *__restrict__ emis_lane, unsigned rowbytes, uint32_t cw, const BckRowCtx &R)
+__device__ __forceinline__ void bck_row_front(int lane, BckState<J> &S, const Bck3Consts<J> &K,
+                                              const char *__restrict__ emis_lane, unsigned rowbytes, uint32_t cw, BckMid<J> &X)
 {
   constexpr int S0 = PH, S2 = (PH + 2) & 3, S3 = (PH + 3) & 3;
   float e2[J], e3[J], e4[J], v[J];
@@ -154,7 +163,7 @@ __device__ __forceinline__ BckOut bck_row_core(int lane, BckState<J> &S, const B
     v[j] = t;
     if (j == 0) bs0 = t * K.qb[0]; else if (j == 1) bs1 = t * K.qb[1]; else if (j & 1) bs1 = fmaf(t, K.qb[j], bs1); else bs0 = fmaf(t, K.qb[j], bs0);
   }
-  float xB = warp_allsum(J > 1 ? bs0 + bs1 : bs0);
+  X.bsum = (J > 1) ? bs0 + bs1 : bs0;
 
   // vn(k) = v(k+1): shift down by one node
   float vn[J];
@@ -179,24 +188,36 @@ __device__ __forceinline__ BckOut bck_row_core(int lane, BckState<J> &S, const B
   if (lane == 31) d = 0.f;
 
   // G(k) = vn(k) + Is(i+3,k) mi3(k) + Ds(k+1) md3(k);  Is(i,k) = Is(i+3,k) tII(k) + vn(k)
-  float g[J];
 #pragma unroll
   for (int j = J - 1; j >= 0; --j) {
     float t = fmaf(S.I[S3][j], K.mi[j], vn[j]);
-    g[j] = fmaf(d, K.md[j], t);
+    X.g[j] = fmaf(d, K.md[j], t);
     d = fmaf(d, K.dd[j], vn[j]);
     S.I[S0][j] = fmaf(S.I[S3][j], K.ii[j], vn[j]);
   }
+}
 
-  // specials (:837-857)
+// the rest, from B(i): specials (:837-857) and Mt(i,.) = E(i) + G into slot S0; returns the row's specials, unscaled
+template <int J, int PH>
+__device__ __forceinline__ BckOut bck_row_back(BckState<J> &S, const BckMid<J> &X, float xB, const BckRowCtx &R)
+{
+  constexpr int S0 = PH, S3 = (PH + 3) & 3;
   float xC = S.xC[S3] * R.ploop;
   float xJ = fmaf(S.xJ[S3], R.ploop, xB * R.pmove);
   float xN = fmaf(S.xN[S3], R.ploop, xB * R.pmove);
   float xE = fmaf(xJ, R.tEL, xC * R.tEM);
-
 #pragma unroll
-  for (int j = 0; j < J; ++j) S.Mt[S0][j] = xE + g[j];
+  for (int j = 0; j < J; ++j) S.Mt[S0][j] = xE + X.g[j];
   return BckOut{ xB, xN, xJ, xC, xE };
+}
+
+template <int J, int VEC, int PH>
+__device__ __forceinline__ BckOut bck_row_core(int lane, BckState<J> &S, const Bck3Consts<J> &K,
+                                               const char *__restrict__ emis_lane, unsigned rowbytes, uint32_t cw, const BckRowCtx &R)
+{
+  BckMid<J> X;
+  bck_row_front<J, VEC, PH>(lane, S, K, emis_lane, rowbytes, cw, X);
+  return bck_row_back<J, PH>(S, X, warp_allsum(X.bsum), R);
 }
 
 // One Backward row.  PH = i & 3 (compile time).
@@ -286,8 +307,19 @@ __device__ __forceinline__ void bck_row_pair(int i, int lane, BckState<J> &S, co
                                              float fsA, float fsB, BckRowCtx &R, float *__restrict__ xrow)
 {
   static_assert(PH == 3 || PH == 1, "pairs start on odd phases");
-  BckOut A = bck_row_core<J, VEC, PH>(lane, S, K, emis_lane, rowbytes, cwA, R);
-  BckOut B = bck_row_core<J, VEC, PH - 1>(lane, S, K, emis_lane, rowbytes, cwB, R);
+  BckOut A, B;
+  if constexpr (BATHGPU_BCK_JOINT_B(J)) {            // both rows' B sums in one butterfly (pair_allsum, fs_parser.cuh)
+    BckMid<J> XA, XB;
+    bck_row_front<J, VEC, PH>(lane, S, K, emis_lane, rowbytes, cwA, XA);
+    bck_row_front<J, VEC, PH - 1>(lane, S, K, emis_lane, rowbytes, cwB, XB);
+    float xBA, xBB;
+    pair_allsum(lane, XA.bsum, XB.bsum, xBA, xBB);
+    A = bck_row_back<J, PH>(S, XA, xBA, R);
+    B = bck_row_back<J, PH - 1>(S, XB, xBB, R);
+  } else {
+    A = bck_row_core<J, VEC, PH>(lane, S, K, emis_lane, rowbytes, cwA, R);
+    B = bck_row_core<J, VEC, PH - 1>(lane, S, K, emis_lane, rowbytes, cwB, R);
+  }
   const int L = R.L;
   auto rescale_all = [&](float sf) {
 #pragma unroll

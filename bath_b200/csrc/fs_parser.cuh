@@ -92,6 +92,21 @@ __device__ __forceinline__ float warp_allsum(float v)
 }
 
 // fetch the 16 bits (4 nucleotides) for rows i..i+3 of a window; p0 = 0-based block index of row i
+// Two warp-wide sums in one butterfly (the E sums of a Forward row pair, the B sums of a Backward one): lanes 0-15 collect row i, lanes 16-31 row i+1 (6 shuffles for the pair instead of 10); every
+// lane ends with the same bits for each sum (the halves exchange their finished sums), so the rescale test stays warp-uniform.
+__device__ __forceinline__ void pair_allsum(int lane, float a, float b, float &sa, float &sb)
+{
+  const bool lo = lane < 16;
+  float mine = (lo ? a : b) + __shfl_xor_sync(0xffffffffu, lo ? b : a, 16);
+  mine += __shfl_xor_sync(0xffffffffu, mine, 8);
+  mine += __shfl_xor_sync(0xffffffffu, mine, 4);
+  mine += __shfl_xor_sync(0xffffffffu, mine, 2);
+  mine += __shfl_xor_sync(0xffffffffu, mine, 1);
+  const float other = __shfl_xor_sync(0xffffffffu, mine, 16);
+  sa = lo ? mine : other;
+  sb = lo ? other : mine;
+}
+
 __device__ __forceinline__ uint32_t fetch_quad(const uint32_t *__restrict__ dna4, long long p0)
 {
   long long q  = p0 + 8;                 // guard word in front

@@ -143,21 +143,6 @@ __device__ __forceinline__ void fwd_row_back(int i, int lane, FwdState<J> &S, co
   R.xE = xE; R.xN = xN; R.xJ = xJ; R.xC = xC; R.xB = xB; R.scale = 1.0f;
 }
 
-// Both rows' E sums in one butterfly: lanes 0-15 collect row i, lanes 16-31 row i+1 (6 shuffles for the pair instead of 10); every
-// lane ends with the same bits for each sum (the halves exchange their finished sums), so the rescale test stays warp-uniform.
-__device__ __forceinline__ void pair_allsum(int lane, float a, float b, float &sa, float &sb)
-{
-  const bool lo = lane < 16;
-  float mine = (lo ? a : b) + __shfl_xor_sync(0xffffffffu, lo ? b : a, 16);
-  mine += __shfl_xor_sync(0xffffffffu, mine, 8);
-  mine += __shfl_xor_sync(0xffffffffu, mine, 4);
-  mine += __shfl_xor_sync(0xffffffffu, mine, 2);
-  mine += __shfl_xor_sync(0xffffffffu, mine, 1);
-  const float other = __shfl_xor_sync(0xffffffffu, mine, 16);
-  sa = lo ? mine : other;
-  sb = lo ? other : mine;
-}
-
 template <int J>
 __device__ __forceinline__ void scale_state(FwdState<J> &S, float sf)
 {
