@@ -118,3 +118,40 @@ def test_orf_finder_argument_errors(oracle, gpu_ctx):
     with pytest.raises(capi.BathGpuError) as e:
         gpu_ctx.orfs_msv_screen(blocks, 0, np.zeros(64, np.uint8), 20, np.zeros(10, np.uint8), np.zeros(10, np.float32), 0.0)
     assert e.value.code == capi.EINVAL
+
+
+def test_orfs_spanning_many_tiles(oracle, gpu_ctx):
+    """stop-free stretches longer than the ORF pass's tile of 2048 positions (a poly-codon run, a run of N, and random DNA between them):
+    the previous stop of a frame then lies several tiles back, the path on which the kernel still walks over the class bytes"""
+    po, lib = oracle, oracle.lib()
+    from bath_b200 import capi
+    model = setup(po, gpu_ctx, "AMP_N.bhmm")
+    rng = np.random.default_rng(77)
+    n = 60000
+    dsq = common.random_dna(rng, n)
+    dsq[5001:5001 + 9000] = np.tile(np.array([2, 1, 0], np.uint8), 3000)        # GCA x 3000: no stop in any frame for 9 kb
+    dsq[20001:20001 + 7000] = 15                                                # N x 7000: every codon translates to X, no stop
+    dsq[40001:40001 + 4100] = np.tile(np.array([0, 0, 2, 1], np.uint8), 1025)   # period 4: AAG CAA GCA AGC ..., stop-free
+    gpu_ctx.upload_block(dsq)
+    blocks = np.zeros(2, capi.block_dtype)
+    blocks[0]["goff"], blocks[0]["n"], blocks[0]["C"] = 0, 33000, 0
+    blocks[1]["goff"], blocks[1]["n"], blocks[1]["C"] = 33000 - 600, n - 33000 + 600, 600
+    gcode = np.frombuffer(C.string_at(lib.bo_gencode_basic(1), 64), np.uint8)
+    tjb, null = tables(po, model, 33000 // 3 + 2)
+    for complement in (0, 1):
+        per, hits, res = gpu_ctx.orfs_msv_screen(blocks, complement, gcode, 20, tjb, null, -1e30)
+        z = 0
+        longest = 0
+        for bi in range(2):
+            want = po.find_orfs(dsq[int(blocks[bi]["goff"]):], int(blocks[bi]["n"]), gcode, 20)
+            assert per[bi] == len(want), (complement, bi, per[bi], len(want))
+            for idx, (start, end, frame, aa) in enumerate(want):
+                Cn, bn = int(blocks[bi]["C"]), int(blocks[bi]["n"])
+                if ((bn - start + 1) < Cn) if complement else (end < Cn):
+                    continue
+                h = hits[z]; z += 1
+                assert (h["block"], h["index"], h["start"], h["end"], h["frame"], h["n"]) == (bi, idx, start, end, frame, len(aa)), (bi, idx, h)
+                assert np.array_equal(res[h["offset"]: h["offset"] + h["n"]], aa)
+                longest = max(longest, len(aa))
+        assert z == len(hits)
+        assert longest > 2800                        # the 9 kb run is one ORF per frame
