@@ -30,6 +30,8 @@ typedef struct { int type, K, Kp; } ESL_ALPHABET;          /* esl_alphabet.h: on
 #define p7P_MAXCODONS5 1367                                /* src/hmmer.h:282 */
 #define p7P_MAXCODONS3 338                                 /* src/hmmer.h:283 */
 
+#define p7O_NQB(M)   (ESL_MAX(2, ((((M) - 1) / 16) + 1)))  /* src/impl_sse/impl_sse.h:24 */
+#define p7O_NQW(M)   (ESL_MAX(2, ((((M) - 1) / 8) + 1)))   /* :25 */
 #define p7O_NQF(M)   (ESL_MAX(2, ((((M) - 1) / 4) + 1)))   /* src/impl_sse/impl_sse.h:26 */
 #define p7O_NXSTATES 4                                     /* :68 */
 #define p7O_NXTRANS  2                                     /* :69 */
@@ -37,6 +39,37 @@ typedef struct { int type, K, Kp; } ESL_ALPHABET;          /* esl_alphabet.h: on
 enum p7o_xstates_e      { p7O_E = 0, p7O_N = 1, p7O_J = 2, p7O_C = 3 };                                             /* :71 */
 enum p7o_xtransitions_e { p7O_MOVE = 0, p7O_LOOP = 1 };                                                             /* :72 */
 enum p7o_tsc_e          { p7O_BM = 0, p7O_MM = 1, p7O_IM = 2, p7O_DM = 3, p7O_MD = 4, p7O_MI = 5, p7O_II = 6, p7O_DD = 7 };  /* :73 */
+
+typedef struct p7_oprofile_s {                             /* src/impl_sse/impl_sse.h:74-139 */
+  __m128i **rbv;                                           /* MSV match costs [x][q], 16 uchars per vector */
+  __m128i **sbv;
+  uint8_t   tbm_b, tec_b, tjb_b;
+  float     scale_b;
+  uint8_t   base_b, bias_b;
+  __m128i **rwv;                                           /* Viterbi match scores [x][q], 8 words per vector */
+  __m128i  *twv;                                           /* [8 * Q8] */
+  int16_t   xw[p7O_NXSTATES][p7O_NXTRANS];
+  float     scale_w;
+  int16_t   base_w, ddbound_w;
+  float     ncj_roundoff;
+  __m128  **rfv;                                           /* Forward / Backward odds [x][q], 4 floats per vector */
+  __m128   *tfv;                                           /* [8 * Q4] */
+  float     xf[p7O_NXSTATES][p7O_NXTRANS];
+  __m128i  *rbv_mem, *sbv_mem, *rwv_mem, *twv_mem;
+  __m128   *tfv_mem, *rfv_mem;
+  off_t     offs[p7_NOFFSETS];
+  off_t     roff, eoff;
+  char     *name, *acc, *desc, *rf, *mm, *cs, *consensus;
+  float     evparam[p7_NEVPARAM];
+  float     cutoff[p7_NCUTOFFS];
+  float     compo[p7_MAXABET];
+  const ESL_ALPHABET *abc;
+  int       L, M, max_length, allocM, allocQ4, allocQ8, allocQ16, mode;
+  float     nj;
+  int       clone;
+} P7_OPROFILE;
+
+#define eslENORESULT 19                                    /* easel.h */
 
 typedef struct p7_fs_oprofile_s {                          /* src/impl_sse/impl_sse.h:200-244 */
   __m128  **rfv;                                           /* [c][q], c = 0..p7P_MAXCODONS#+Kp-1, q = 0..allocQ4-1 */

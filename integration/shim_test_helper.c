@@ -66,3 +66,57 @@ void   shimtest_set_length(P7_FS_OPROFILE *om, float pmove, float ploop)      /*
   om->xf[p7O_N][p7O_MOVE] = om->xf[p7O_C][p7O_MOVE] = om->xf[p7O_J][p7O_MOVE] = pmove;
   om->xf[p7O_N][p7O_LOOP] = om->xf[p7O_C][p7O_LOOP] = om->xf[p7O_J][p7O_LOOP] = ploop;
 }
+
+/* shimtest_make_oprofile_protein stripes a protein profile's plain tables the way mf_conversion / vf_conversion / fb_conversion do
+ * (src/impl_sse/p7_oprofile.c:773-813, :826-903, :921-1000): rbv 16 bytes per vector (pad 255), rwv 8 words (pad -32768), twv
+ * interleaved per stripe with the first four blocks rotated by one node, rfv / tfv 4 floats per vector.
+ * iprm = { tbm_b, tec_b, tjb_b, base_b, bias_b, base_w, ddbound_w, xw[E][MOVE], xw[E][LOOP], xw[N][MOVE] }, fprm = { scale_b, scale_w, nj, xfE_move, xfE_loop }. */
+P7_OPROFILE *shimtest_make_oprofile_protein(int M, const uint8_t *rbv, const int16_t *rwv, const int16_t *twv, const float *rfv, const float *tfv,
+                                            const int *iprm, const float *fprm)
+{
+  P7_OPROFILE *om = calloc(1, sizeof(P7_OPROFILE));
+  const int Kp = 29, Q16 = p7O_NQB(M), Q8 = p7O_NQW(M), Q4 = p7O_NQF(M);
+  union { __m128i v; uint8_t b[16]; int16_t w[8]; } u;
+  union { __m128 v; float f[4]; } uf;
+  int x, q, z, t, j;
+  om->M = M; om->allocM = M; om->allocQ16 = Q16; om->allocQ8 = Q8; om->allocQ4 = Q4; om->abc = &shimtest_amino; om->mode = 1;
+  om->tbm_b = (uint8_t) iprm[0]; om->tec_b = (uint8_t) iprm[1]; om->tjb_b = (uint8_t) iprm[2]; om->base_b = (uint8_t) iprm[3]; om->bias_b = (uint8_t) iprm[4];
+  om->base_w = (int16_t) iprm[5]; om->ddbound_w = (int16_t) iprm[6];
+  om->xw[p7O_E][p7O_MOVE] = (int16_t) iprm[7]; om->xw[p7O_E][p7O_LOOP] = (int16_t) iprm[8]; om->xw[p7O_N][p7O_MOVE] = (int16_t) iprm[9];
+  om->scale_b = fprm[0]; om->scale_w = fprm[1]; om->nj = fprm[2]; om->xf[p7O_E][p7O_MOVE] = fprm[3]; om->xf[p7O_E][p7O_LOOP] = fprm[4];
+  om->rbv_mem = aligned_alloc(16, sizeof(__m128i) * (size_t) Kp * Q16);
+  om->rwv_mem = aligned_alloc(16, sizeof(__m128i) * (size_t) Kp * Q8);
+  om->twv_mem = aligned_alloc(16, sizeof(__m128i) * (size_t) 8 * Q8);
+  om->rfv_mem = aligned_alloc(16, sizeof(__m128) * (size_t) Kp * Q4);
+  om->tfv_mem = aligned_alloc(16, sizeof(__m128) * (size_t) 8 * Q4);
+  om->rbv = malloc(sizeof(__m128i *) * Kp); om->rwv = malloc(sizeof(__m128i *) * Kp); om->rfv = malloc(sizeof(__m128 *) * Kp);
+  om->twv = om->twv_mem; om->tfv = om->tfv_mem;
+  for (x = 0; x < Kp; x++) {
+    om->rbv[x] = om->rbv_mem + (size_t) x * Q16; om->rwv[x] = om->rwv_mem + (size_t) x * Q8; om->rfv[x] = om->rfv_mem + (size_t) x * Q4;
+    for (q = 0; q < Q16; q++) { for (z = 0; z < 16; z++) { const int k = q + 1 + z * Q16; u.b[z] = (k <= M) ? rbv[(size_t) x * (M + 1) + k] : 255; } om->rbv[x][q] = u.v; }
+    for (q = 0; q < Q8;  q++) { for (z = 0; z < 8;  z++) { const int k = q + 1 + z * Q8;  u.w[z] = (k <= M) ? rwv[(size_t) x * (M + 1) + k] : -32768; } om->rwv[x][q] = u.v; }
+    for (q = 0; q < Q4;  q++) { for (z = 0; z < 4;  z++) { const int k = q + 1 + z * Q4;  uf.f[z] = (k <= M) ? rfv[(size_t) x * (M + 1) + k] : 0.0f; } om->rfv[x][q] = uf.v; }
+  }
+  for (j = 0, q = 0; q < Q8; q++)
+    for (t = p7O_BM; t <= p7O_II; t++) {
+      const int kb = (t <= p7O_DM) ? q : q + 1;
+      for (z = 0; z < 8; z++) u.w[z] = (kb + z * Q8 < M) ? twv[(size_t) t * (M + 1) + kb + z * Q8] : -32768;
+      om->twv[j++] = u.v;
+    }
+  for (q = 0; q < Q8; q++) { for (z = 0; z < 8; z++) u.w[z] = (q + 1 + z * Q8 < M) ? twv[(size_t) p7O_DD * (M + 1) + q + 1 + z * Q8] : -32768; om->twv[j++] = u.v; }
+  for (j = 0, q = 0; q < Q4; q++)
+    for (t = p7O_BM; t <= p7O_II; t++) {
+      const int kb = (t <= p7O_DM) ? q : q + 1;
+      for (z = 0; z < 4; z++) uf.f[z] = (kb + z * Q4 < M) ? tfv[(size_t) t * (M + 1) + kb + z * Q4] : 0.0f;
+      om->tfv[j++] = uf.v;
+    }
+  for (q = 0; q < Q4; q++) { for (z = 0; z < 4; z++) uf.f[z] = (q + 1 + z * Q4 < M) ? tfv[(size_t) p7O_DD * (M + 1) + q + 1 + z * Q4] : 0.0f; om->tfv[j++] = uf.v; }
+  return om;
+}
+
+void shimtest_free_oprofile_protein(P7_OPROFILE *om)
+{
+  if (!om) return;
+  free(om->rbv_mem); free(om->rwv_mem); free(om->twv_mem); free(om->rfv_mem); free(om->tfv_mem); free(om->rbv); free(om->rwv); free(om->rfv); free(om);
+}
+void shimtest_set_orf_length(P7_OPROFILE *om, int tjb_b, int xw_move) { om->tjb_b = (uint8_t) tjb_b; om->xw[p7O_N][p7O_MOVE] = (int16_t) xw_move; }

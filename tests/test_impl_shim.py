@@ -115,3 +115,78 @@ def test_parsers_through_the_reference_signatures_match_the_oracle(oracle, hmmfi
         L.shimtest_free_omx(oxb)
     L.shimtest_free_oprofile(om)
     L.bathshim_release()
+
+
+# ---- the protein profile: un-striping of P7_OPROFILE (mf_conversion / vf_conversion / fb_conversion layouts) and the three entry points
+
+def striped_protein(L, po, model, lanes=(16, 8)):
+    """P7_OPROFILE striped from the oracle's plain tables, with its scalar parameters"""
+    rbv, rwv, twv, rfv, tfv = (np.ascontiguousarray(a) for a in model.om_tables())
+    o = model.om.contents
+    iprm = np.array([o.tbm_b, o.tec_b, o.tjb_b, o.base_b, o.bias_b, o.base_w, o.ddbound_w, o.xw[0][0], o.xw[0][1], o.xw[1][0]], np.int32)
+    fprm = np.array([o.scale_b, o.scale_w, 1.0, 0.5, 0.5], np.float32)
+    L.shimtest_make_oprofile_protein.restype = C.c_void_p
+    L.shimtest_make_oprofile_protein.argtypes = [C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_int16), C.POINTER(C.c_int16), C.POINTER(C.c_float),
+                                                 C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
+    om = L.shimtest_make_oprofile_protein(model.M, rbv.ctypes.data_as(C.POINTER(C.c_uint8)), rwv.ctypes.data_as(C.POINTER(C.c_int16)),
+                                          twv.ctypes.data_as(C.POINTER(C.c_int16)), f32p(rfv), f32p(tfv),
+                                          iprm.ctypes.data_as(C.POINTER(C.c_int32)), f32p(fprm))
+    return om, (rbv, rwv, twv, rfv, tfv)
+
+
+@pytest.mark.parametrize("hmmfile,index", [("AMP_N.bhmm", 0), ("PTH2.bhmm", 0), ("tRNA-synthetases.bhmm", 2), ("MET-ct4.bhmm", 1)])
+def test_unstriping_inverts_the_protein_profile_striping(oracle, hmmfile, index):
+    po = oracle
+    L = shim()
+    model = po.Model(common.golden(hmmfile), index)
+    M = model.M
+    om, (rbv, rwv, twv, rfv, tfv) = striped_protein(L, po, model)
+    b2, w2, t2 = np.zeros_like(rbv), np.zeros_like(rwv), np.zeros_like(twv)
+    r2, f2 = np.zeros_like(rfv), np.zeros_like(tfv)
+    L.bathshim_unstripe_oprofile.argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_int16), C.POINTER(C.c_int16), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.bathshim_unstripe_oprofile(om, b2.ctypes.data_as(C.POINTER(C.c_uint8)), w2.ctypes.data_as(C.POINTER(C.c_int16)),
+                                 t2.ctypes.data_as(C.POINTER(C.c_int16)), f32p(r2), f32p(f2))
+    L.shimtest_free_oprofile_protein.argtypes = [C.c_void_p]
+    L.shimtest_free_oprofile_protein(om)
+    assert np.array_equal(b2[:, 1:], rbv[:, 1:]) and np.array_equal(w2[:, 1:], rwv[:, 1:]) and np.array_equal(r2[:, 1:], rfv[:, 1:])
+    assert np.array_equal(t2[:4, :M], twv[:4, :M]) and np.array_equal(t2[4:, 1:M], twv[4:, 1:M])       # as for the frameshift profile: nothing for node M
+    assert np.array_equal(f2[:4, :M], tfv[:4, :M]) and np.array_equal(f2[4:, 1:M], tfv[4:, 1:M])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hmmfile,index", [("AMP_N.bhmm", 0), ("tRNA-synthetases.bhmm", 2)])
+def test_filters_through_the_reference_signatures_match_the_oracle(oracle, hmmfile, index):
+    """p7_MSVFilter / p7_ViterbiFilter bit-exact, p7_ForwardParser within 1e-3 nat, called as p7_Pipeline_BATH calls them
+    (src/p7_pipeline.c:1649, :1672, :1779) after p7_oprofile_ReconfigLength(om, L)"""
+    from test_gpu_orf_filters import make_orfs
+    po, lib = oracle, oracle.lib()
+    L = shim()
+    model = po.Model(common.golden(hmmfile), index)
+    om, _ = striped_protein(L, po, model)
+    u8p, fp = C.POINTER(C.c_uint8), C.POINTER(C.c_float)
+    for f in (L.p7_MSVFilter, L.p7_ViterbiFilter, L.p7_ForwardParser):
+        f.argtypes = [u8p, C.c_int, C.c_void_p, C.c_void_p, fp]
+    L.shimtest_set_orf_length.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    rng = np.random.default_rng(9 + index)
+    n_inf = 0
+    for s in make_orfs(rng, model, 10, 10):
+        Ls = len(s)
+        d = np.concatenate([[255], s, [255]]).astype(np.uint8)
+        lib.bo_oprofile_ReconfigLength(model.om, Ls)
+        o = model.om.contents
+        L.shimtest_set_orf_length(om, int(o.tjb_b), int(o.xw[1][0]))
+        got, want = C.c_float(), C.c_float()
+        for shim_fn, ora_fn, exact in ((L.p7_MSVFilter, lib.bo_MSVFilter, True), (L.p7_ViterbiFilter, lib.bo_ViterbiFilter, True)):
+            st = shim_fn(d.ctypes.data_as(u8p), Ls, om, None, C.byref(got))
+            ost = ora_fn(po.u8ptr(d), Ls, model.om, C.byref(want))
+            assert st == ost, (shim_fn, Ls, st, ost)
+            assert got.value == want.value or (np.isinf(got.value) and np.isinf(want.value)), (Ls, got.value, want.value)
+            n_inf += bool(np.isinf(want.value))
+        st = L.p7_ForwardParser(d.ctypes.data_as(u8p), Ls, om, None, C.byref(got))
+        ox = lib.bo_mx_create(model.M, Ls, 0)
+        ost = lib.bo_Forward(po.u8ptr(d), Ls, model.om, ox, C.byref(want))
+        lib.bo_mx_destroy(ox)
+        assert st == ost and (ost != 0 or abs(got.value - want.value) <= 1e-3), (Ls, got.value, want.value)
+    L.shimtest_free_oprofile_protein.argtypes = [C.c_void_p]
+    L.shimtest_free_oprofile_protein(om)
+    L.bathshim_release()
