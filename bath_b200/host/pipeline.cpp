@@ -2315,6 +2315,32 @@ extern "C" int bathhost_search_finish(bathhost_search *s)
   return BATHHOST_OK;
 }
 
+// Several searches (one per query profile, each with device contexts of its own) finished at the same time, one host thread each:
+// bathsearch's query loop (src/bathsearch.c:737) takes the profiles one after the other, but the searches share nothing, and run
+// together one search's serial host phases (region walk, hit list) sit under the others' device stages.  Every search gives the hit
+// list it gives alone.  Returns the first non-zero status.
+extern "C" int bathhost_search_finish_many(bathhost_search *const *ss, int n)
+{
+  if (n < 0 || (n > 0 && !ss)) return BATHHOST_EINVAL;
+  for (int k = 0; k < n; ++k) {
+    if (!ss[k]) return BATHHOST_EINVAL;
+    for (int q = 0; q < k; ++q) {
+      if (ss[q] == ss[k]) return BATHHOST_EINVAL;
+      for (const bathhost_backend &a : ss[q]->bes)          // a device context serves one search at a time
+        for (const bathhost_backend &b : ss[k]->bes)
+          if (a.ctx && a.ctx == b.ctx) return fail(ss[k], BATHHOST_EINVAL, "bathhost_search_finish_many: two searches share a device context");
+    }
+  }
+  if (n == 0) return BATHHOST_OK;
+  std::vector<int> st((size_t) n, BATHHOST_OK);
+  std::vector<std::thread> th;
+  for (int k = 1; k < n; ++k) th.emplace_back([&, k] { st[(size_t) k] = bathhost_search_finish(ss[k]); });
+  st[0] = bathhost_search_finish(ss[0]);
+  for (auto &t : th) t.join();
+  for (int k = 0; k < n; ++k) if (st[(size_t) k] != BATHHOST_OK) return st[(size_t) k];
+  return BATHHOST_OK;
+}
+
 extern "C" int bathhost_search_nhits(const bathhost_search *s) { return s ? (int) s->st.n_hits_reported : 0; }
 
 extern "C" int bathhost_search_get_hit(const bathhost_search *s, int idx, bathhost_hit *hit)

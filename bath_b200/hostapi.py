@@ -14,7 +14,7 @@ EXPORTS = [
     "bathhost_model_filter_params", "bathhost_model_rbv", "bathhost_model_rwv", "bathhost_model_twv",
     "bathhost_orf_length_params", "bathhost_model_computed_max_length",
     "bathhost_search_create", "bathhost_search_create_multi", "bathhost_search_queue", "bathhost_search_run", "bathhost_search_destroy", "bathhost_search_last_error", "bathhost_search_sequence",
-    "bathhost_search_finish", "bathhost_search_nhits", "bathhost_search_get_hit", "bathhost_search_get_stats",
+    "bathhost_search_finish", "bathhost_search_finish_many", "bathhost_search_nhits", "bathhost_search_get_hit", "bathhost_search_get_stats",
     "bathhost_sample_region_segments", "bathhost_cluster_region_segments", "bathhost_sample_region_segments_protein",
     "bathhost_cluster_region_segments_protein", "bathhost_search_format_tblout",
     "bathhost_calibrate", "bathhost_model_lambda", "bathhost_search_format_report", "bathhost_search_format_output", "bathhost_search_format_fstblout",
@@ -133,6 +133,8 @@ def load():
     L.bathhost_search_sequence.argtypes = [vp, C.c_char_p, u8p, C.c_int64]
     L.bathhost_search_finish.restype = C.c_int
     L.bathhost_search_finish.argtypes = [vp]
+    L.bathhost_search_finish_many.restype = C.c_int
+    L.bathhost_search_finish_many.argtypes = [C.POINTER(C.c_void_p), C.c_int]
     L.bathhost_search_nhits.restype = C.c_int
     L.bathhost_search_nhits.argtypes = [vp]
     L.bathhost_search_get_hit.restype = C.c_int
@@ -348,6 +350,20 @@ class Search:
             raise RuntimeError(f"bathhost_search_finish: status {st}")
         return self.hits() if fetch else int(self.lib.bathhost_search_nhits(self.h))
 
+    @staticmethod
+    def finish_many(searches):
+        """bathhost_search_finish_many: the searches (different profiles, device contexts of their own, targets already queued) run at
+        the same time, one host thread each; every search ends up as after its own finish(fetch=False)"""
+        if not searches:
+            return
+        arr = (C.c_void_p * len(searches))(*[s.h for s in searches])
+        st = searches[0].lib.bathhost_search_finish_many(arr, len(searches))
+        for s in searches:
+            s._keep = []
+        if st != OK:
+            msgs = "; ".join(s.lib.bathhost_search_last_error(s.h).decode() for s in searches)
+            raise RuntimeError(f"bathhost_search_finish_many: status {st}: {msgs}")
+
     def hits(self):
         hits = []
         for i in range(self.lib.bathhost_search_nhits(self.h)):
@@ -458,3 +474,36 @@ def cluster_region_segments(segments, nsamples=200, protein=False):
     if st != 0:
         raise RuntimeError(f"bathhost_cluster_region_segments: status {st}")
     return [(g.idx, g.i, g.j, g.k, g.m, g.prob) for g in out[:n.value]]
+
+
+def compare_tables(a, b):
+    """--tblout tables field by field: names, model and target coordinates, frameshift / stop counts and the CIGAR string must be equal;
+    the four printed floats (E-value, score, bias, percent identity) may differ by one unit of their last printed digit -- the device
+    and the CPU oracle sum the same FP32 terms in different orders, and a value on a rounding boundary of %.1f prints either way.
+    Returns (byte_identical, equivalent, lines_with_a_differing_digit)."""
+    if a == b:
+        return True, True, 0
+    la, lb = a.splitlines(), b.splitlines()
+    if len(la) != len(lb):
+        return False, False, -1
+    ndiff = 0
+    for x, y in zip(la, lb):
+        if x == y:
+            continue
+        fx, fy = x.split(), y.split()
+        if len(fx) != len(fy) or len(fx) < 18:
+            return False, False, -1
+        for i, (u, v) in enumerate(zip(fx, fy)):
+            if u == v:
+                continue
+            if i not in (11, 12, 13, 14):
+                return False, False, -1
+            fu, fv = float(u), float(v)
+            if i == 11:
+                ok = abs(fu - fv) <= 0.11 * max(abs(fu), abs(fv))           # two significant digits printed
+            else:
+                ok = abs(fu - fv) <= (0.0101 if i == 14 else 0.101)
+            if not ok:
+                return False, False, -1
+        ndiff += 1
+    return False, True, ndiff

@@ -20,8 +20,9 @@ on the DP path); the only communication is the barrier and the max-over-ranks of
 
 Second metric, "search" (BASELINE.json configs[3] as written): bathsearch --fs Mbp/s of the three profiles of
 tRNA-synthetases.bhmm against ONE synthetic genome in contigs of 1-10 Mbp with planted homologs of all three, sharded by
-blocks over the N devices by ONE process (rank 0; bathhost_search_create_multi, eight contexts per device) with one merged
-hit list per profile: strong scaling on a fixed target.  At N > 1 the same search is also run on one device and the two
+blocks over the N devices by ONE process (rank 0; bathhost_search_create_multi over 12-24 device contexts, the three profiles
+searched at the same time by bathhost_search_finish_many) with one merged hit list per profile: strong scaling on a fixed target;
+the one-profile-at-a-time order of the reference's query loop is timed beside it and must give the same tables.  At N > 1 the same search is also run on one device and the two
 tables compared byte for byte (search.checks.hits_identical_to_1gpu); at N = 1 the GPU search of the CPU-baseline prefix
 is compared with the CPU-oracle pipeline's table field by field (search.checks.hits_identical_to_cpu_prefix, rule in
 search.checks.cpu_prefix_rule; byte identity per profile beside it).
@@ -59,8 +60,8 @@ def parse_args():
                     help="also run the whole stage-batched bathsearch --fs pipeline (3 profiles) over a genome of this many Mbp (0 = skip)")
     ap.add_argument("--no-filters-leg", action="store_true", help="skip the integer-filter roofline leg")
     ap.add_argument("--contexts-per-gpu", type=int, default=0,
-                    help="device contexts per GPU in the search leg (0: 8 on one or two GPUs, 16 in all beyond that -- every context has a host "
-                         "thread of its own, and past ~16 of them the host side of the search is oversubscribed)")
+                    help="device contexts per profile and GPU in the search leg (0: 4 on one or two GPUs, 2 on four, 1 on eight -- the three "
+                         "profiles run at the same time and every context has a host thread of its own: 12-24 of them in all)")
     return ap.parse_args()
 
 
@@ -294,40 +295,12 @@ def search_target(mbp):
 
 
 def compare_tables(a, b):
-    """--tblout tables field by field: names, model and target coordinates, frameshift / stop counts and the CIGAR string must be equal;
-    the four printed floats (E-value, score, bias, percent identity) may differ by one unit of their last printed digit -- the device
-    and the CPU oracle sum the same FP32 terms in different orders, and a value on a rounding boundary of %.1f prints either way.
-    Returns (byte_identical, equivalent, lines_with_a_differing_digit)."""
-    if a == b:
-        return True, True, 0
-    la, lb = a.splitlines(), b.splitlines()
-    if len(la) != len(lb):
-        return False, False, -1
-    ndiff = 0
-    for x, y in zip(la, lb):
-        if x == y:
-            continue
-        fx, fy = x.split(), y.split()
-        if len(fx) != len(fy) or len(fx) < 18:
-            return False, False, -1
-        for i, (u, v) in enumerate(zip(fx, fy)):
-            if u == v:
-                continue
-            if i not in (11, 12, 13, 14):
-                return False, False, -1
-            fu, fv = float(u), float(v)
-            if i == 11:
-                ok = abs(fu - fv) <= 0.11 * max(abs(fu), abs(fv))           # two significant digits printed
-            else:
-                ok = abs(fu - fv) <= (0.0101 if i == 14 else 0.101)
-            if not ok:
-                return False, False, -1
-        ndiff += 1
-    return False, True, ndiff
+    from bath_b200 import hostapi
+    return hostapi.compare_tables(a, b)
 
 
 def run_search(models, contigs, gpu_ctxs=None, backends=None):
-    """every profile against the whole target: (seconds per profile, tables, stats, hit lists)"""
+    """every profile against the whole target, one profile after the other: (seconds per profile, tables, stats, hit lists)"""
     from bath_b200 import hostapi
     secs, tables, stats, hits = [], [], [], []
     for model in models:
@@ -343,6 +316,25 @@ def run_search(models, contigs, gpu_ctxs=None, backends=None):
         hits.append(h)
         search.close()
     return secs, tables, stats, hits
+
+
+def run_search_together(models, contigs, ctx_sets):
+    """the profiles of the query file searched at the same time, each over its own device contexts (bathhost_search_finish_many):
+    (seconds for all of them, tables, stats, hit lists)"""
+    from bath_b200 import hostapi
+    searches = [hostapi.Search(m, gpu_ctx=cs) for m, cs in zip(models, ctx_sets)]
+    t0 = time.perf_counter()
+    for s in searches:
+        for name, dsq in contigs:
+            s.queue_sequence(name, dsq)
+    hostapi.Search.finish_many(searches)
+    dt = time.perf_counter() - t0
+    hits = [s.hits() for s in searches]
+    tables = [s.tblout(header=False) for s in searches]
+    stats = [s.stats() for s in searches]
+    for s in searches:
+        s.close()
+    return dt, tables, stats, hits
 
 
 def recovered(hits_per_model, contigs, plants):
@@ -372,30 +364,37 @@ def search_leg(devices, per_gpu, mbp, cpu_mbp, with_cpu):
         buf[:] = dsq
         pinned.append((name, buf))
     total_nt = sum(len(d) - 2 for _, d in contigs)
-    ctxs = [capi.Context(d) for d in devices for _ in range(per_gpu)]
+    # the three profiles run at the same time, each over per_gpu contexts of its own on every device
+    sets = [[capi.Context(d) for d in devices for _ in range(per_gpu)] for _ in models]
     # one untimed pass of the three profiles (device buffers and page-locked host buffers reach their working sizes, kernels of every
     # model size get loaded: the steady state of a multi-query search); its time is reported as first_pass_seconds
     t0 = time.perf_counter()
-    run_search(models, pinned, gpu_ctxs=ctxs)
+    run_search_together(models, pinned, sets)
     cold = time.perf_counter() - t0
-    secs, tables, stats, hits = run_search(models, pinned, gpu_ctxs=ctxs)
-    dt = sum(secs)
-    out = {"metric": "bathsearch --fs Mbp/s", "value": total_nt * len(models) / dt / 1e6, "unit": "Mbp/s", "seconds": dt, "seconds_per_profile": secs,
+    dt, tables, stats, hits = run_search_together(models, pinned, sets)
+    # the reference's own order beside it: one profile after the other, every context of the first set + second set on each
+    ctxs = sets[0] + sets[1]
+    run_search(models, pinned, gpu_ctxs=ctxs)
+    secs, tables_serial, _, _ = run_search(models, pinned, gpu_ctxs=ctxs)
+    out = {"metric": "bathsearch --fs Mbp/s", "value": total_nt * len(models) / dt / 1e6, "unit": "Mbp/s", "seconds": dt,
+           "one_profile_at_a_time": {"value": total_nt * len(models) / sum(secs) / 1e6, "seconds_per_profile": secs, "contexts_per_gpu": 2 * per_gpu},
            "first_pass_seconds": cold, "target_mbp": total_nt / 1e6, "contigs": len(contigs), "profiles": [m.M for m in models],
-           "n_gpus": len(devices), "contexts_per_gpu": per_gpu, "scaling": "strong",
+           "n_gpus": len(devices), "contexts_per_gpu": per_gpu * len(models), "contexts_per_profile_per_gpu": per_gpu, "scaling": "strong",
            "hits": [len(h) for h in hits], "planted": len(plants), "planted_recovered": recovered(hits, contigs, plants),
-           "stats": stats[1], "stats_per_profile": stats, "checks": {},
-           "note": "one process drives every device (bathhost_search_create_multi): blocks of the one target are dealt to the device "
-                   "contexts, the hit-window list / length-model chain / residue counts are kept in the reference's serial order on the "
-                   "host, one merged hit list per profile; stage times in stats are summed over contexts"}
+           "stats": stats[1], "stats_per_profile": stats, "checks": {"tables_identical_to_one_profile_at_a_time": bool(tables == tables_serial)},
+           "note": "one process drives every device: the three profiles are searched at the same time (bathhost_search_finish_many, one "
+                   "search per profile over device contexts of its own on every GPU; bathhost_search_create_multi deals the blocks of the "
+                   "one target to a search's contexts); the hit-window list / length-model chain / residue counts are kept in the "
+                   "reference's serial order on the host, one merged hit list per profile; stage times in stats are summed over contexts"}
     if len(devices) > 1:                                        # the same search on one device: the tables must agree byte for byte
-        one = [capi.Context(devices[0]) for _ in range(8)]       # the 1-GPU configuration of this bench
-        run_search(models, pinned, gpu_ctxs=one)
-        secs1, tables1, _, _ = run_search(models, pinned, gpu_ctxs=one)
-        out["one_gpu"] = {"value": total_nt * len(models) / sum(secs1) / 1e6, "seconds": sum(secs1), "contexts_per_gpu": 8}
+        one = [[capi.Context(devices[0]) for _ in range(4)] for _ in models]     # the 1-GPU configuration of this bench
+        run_search_together(models, pinned, one)
+        dt1, tables1, _, _ = run_search_together(models, pinned, one)
+        out["one_gpu"] = {"value": total_nt * len(models) / dt1 / 1e6, "seconds": dt1, "contexts_per_profile_per_gpu": 4}
         out["checks"]["hits_identical_to_1gpu"] = bool(tables1 == tables)
-        for c in one:
-            c.close()
+        for cs in one:
+            for c in cs:
+                c.close()
     if with_cpu:
         # CPU baseline of this metric: the same pipeline over the CPU oracle's stage calls on a bounded prefix of the target; the GPU
         # search of the same prefix must write the same table
@@ -419,8 +418,9 @@ def search_leg(devices, per_gpu, mbp, cpu_mbp, with_cpu):
         out["checks"]["cpu_prefix_lines_differing_in_a_last_printed_digit"] = [int(c[2]) for c in cmp]
         out["checks"]["cpu_prefix_rule"] = ("hits_identical_to_cpu_prefix: same hits in the same order with equal names, coordinates, frameshift/stop "
                                             "counts and CIGAR strings; E-value, score, bias and identity equal to within one unit of the last printed digit")
-    for c in ctxs:
-        c.close()
+    for cs in sets:
+        for c in cs:
+            c.close()
     return out
 
 
@@ -617,7 +617,7 @@ def main():
         barrier()
         devices = ranks.search_devices(rank, world, torch.cuda.device_count())
         if devices:
-            per_gpu = args.contexts_per_gpu if args.contexts_per_gpu > 0 else max(2, min(8, 16 // len(devices)))
+            per_gpu = args.contexts_per_gpu if args.contexts_per_gpu > 0 else max(1, min(4, 8 // len(devices)))
             search = search_leg(devices, per_gpu, args.search_mbp, args.search_cpu_mbp, world == 1 and not args.no_cpu_baseline)
         cpu_barrier()
 

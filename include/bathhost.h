@@ -209,6 +209,11 @@ int  bathhost_search_run(bathhost_search *s);
 /* E-values over the whole search space, duplicate removal, ordering, reporting threshold.  Runs anything still queued first;
  * calling it again without new sequences changes nothing. */
 int  bathhost_search_finish(bathhost_search *s);
+/* bathhost_search_finish of n different searches at once, one host thread each (e.g. the profiles of a query file, src/bathsearch.c:737,
+ * each search created over device contexts of its own and fed the same target): the searches share nothing but the host pool, so each
+ * returns the hit list it returns alone, and one search's serial host phases run under the others' device stages.  First non-zero
+ * status, BATHHOST_EINVAL for a null or repeated search or two searches over the same device context. */
+int  bathhost_search_finish_many(bathhost_search *const *searches, int n);
 int  bathhost_search_nhits(const bathhost_search *s);
 int  bathhost_search_get_hit(const bathhost_search *s, int idx, bathhost_hit *hit);
 int  bathhost_search_get_stats(const bathhost_search *s, bathhost_stats *st);

@@ -94,3 +94,33 @@ def test_small_blocks_gpu_equals_cpu_backend(oracle, contexts):
     want = _cpu(oracle, model, targets, block_length=40_000)
     assert _run(model, targets, gpu=contexts[0], block_length=40_000) == want
     assert _run(model, targets, gpu=contexts, block_length=40_000, chunk_nt=300_000) == want
+
+
+def test_three_profiles_at_once_equal_one_after_the_other(oracle):
+    """bathhost_search_finish_many on the device: the three tRNA-synthetases profiles against the same 6 Mbp at the same time, two
+    contexts each, give the tables of the one-profile-at-a-time loop and of the CPU backend"""
+    from bath_b200 import capi, hostapi, synth
+    models = [hostapi.QueryModel(common.golden("tRNA-synthetases.bhmm"), i) for i in range(3)]
+    rng = np.random.default_rng(11)
+    contigs, _ = synth.planted_contigs(rng, 6_000_000, [m.mat() for m in models], every=25_000, fs_rates=[m.fsprob for m in models],
+                                       min_len=1_000_000, max_len=3_000_000)
+    sets = [[capi.Context(0), capi.Context(0)] for _ in models]
+    alone = [_run(m, contigs, gpu=cs) for m, cs in zip(models, sets)]
+    searches = [hostapi.Search(m, gpu_ctx=cs, chunk_nt=1_500_000) for m, cs in zip(models, sets)]
+    for s in searches:
+        for name, dsq in contigs:
+            s.queue_sequence(name, dsq)
+    hostapi.Search.finish_many(searches)
+    for s, ref, m in zip(searches, alone, models):
+        got = (s.tblout(), {k: v for k, v in s.stats().items() if k in COUNTERS})
+        assert ref[1]["n_hits_reported"] >= 60, ref[1]
+        assert got == ref
+        cpu = _cpu(oracle, m, contigs)
+        # against the CPU backend: the same hits, coordinates and CIGAR strings; a printed float may sit on a rounding boundary
+        # (here one E-value of the third profile prints 6.2e-31 / 6.3e-31: ln P differs by < 5e-4)
+        same_bytes, equivalent, ndiff = hostapi.compare_tables(got[0], cpu[0])
+        assert equivalent and ndiff <= 1 and got[1] == cpu[1]
+        s.close()
+    for cs in sets:
+        for c in cs:
+            c.close()

@@ -94,3 +94,39 @@ def test_finish_twice_changes_nothing_and_more_sequences_can_follow(oracle):
     allten = search.tblout()
     search.close()
     assert allten == _search(oracle, "2OG-FeII_Oxy_3.bhmm", targets)[0]
+
+
+def test_three_profiles_finished_at_once_equal_one_after_the_other(oracle):
+    """bathhost_search_finish_many: the query file's three profiles against the same contigs at the same time (one host thread per
+    search, two contexts each) give, search by search, the tables of the reference's one-query-at-a-time loop (src/bathsearch.c:737)"""
+    from bath_b200 import hostapi
+    models = [hostapi.QueryModel(common.golden("tRNA-synthetases.bhmm"), i) for i in range(3)]
+    rng = np.random.default_rng(7)
+    targets = []
+    for c in range(3):
+        from bath_b200 import synth
+        dsq, _ = synth.planted_genome(rng, 200_000, models[c].mat(), every=20_000, fs_rate=models[c].fsprob)
+        targets.append((f"contig{c + 1}", dsq))
+    alone = [_search(oracle, "tRNA-synthetases.bhmm", targets, index=i, block_length=60_000) for i in range(3)]
+    pairs = [[oracle.cpu_backend(2) for _ in range(2)] for _ in models]
+    searches = [hostapi.Search(m, backend=[p[0] for p in ps], block_length=60_000, chunk_nt=150_000) for m, ps in zip(models, pairs)]
+    for s in searches:
+        for name, dsq in targets:
+            s.queue_sequence(name, dsq)
+    hostapi.Search.finish_many(searches)
+    for s, ref in zip(searches, alone):
+        assert ref[1]["n_hits_reported"] >= 10
+        _same((s.tblout(), s.stats(), None), ref)
+    # a search twice, or two searches over one context, are refused
+    lib = searches[0].lib
+    import ctypes as C
+    arr = (C.c_void_p * 2)(searches[0].h, searches[0].h)
+    assert lib.bathhost_search_finish_many(arr, 2) == 11          # BATHHOST_EINVAL
+    shared = hostapi.Search(models[1], backend=[pairs[0][0][0]])
+    arr = (C.c_void_p * 2)(searches[0].h, shared.h)
+    assert lib.bathhost_search_finish_many(arr, 2) == 11
+    assert lib.bathhost_search_finish_many(None, 0) == hostapi.OK
+    shared.close()
+    for s in searches:
+        s.close()
+    del pairs
