@@ -21,6 +21,7 @@ EXPORTS = [
     "bathgpu_orf_fwd_bck_xrows", "bathgpu_orf_domains", "bathgpu_orf_fetch_domain_matrices",
     "bathgpu_orfs_msv_screen", "bathgpu_orfs_fetch", "bathgpu_revcomp_slot", "bathgpu_fs_fwd_block", "bathgpu_fs_forward_matrices",
     "bathgpu_bias_forward", "bathgpu_orfs_stage_breakdown", "bathgpu_measure_int16_peak", "bathgpu_orf_forward_matrices",
+    "bathgpu_packed4_bytes", "bathgpu_pack_dna4", "bathgpu_upload_block_packed4", "bathgpu_fs_fwd_block_packed4",
 ]
 
 
@@ -83,6 +84,12 @@ def load():
     L.bathgpu_load_fs_profile.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp, fp]
     L.bathgpu_upload_block.restype = C.c_int
     L.bathgpu_upload_block.argtypes = [vp, C.POINTER(C.c_uint8), C.c_int64]
+    L.bathgpu_packed4_bytes.restype = C.c_int64
+    L.bathgpu_packed4_bytes.argtypes = [C.c_int64]
+    L.bathgpu_pack_dna4.restype = C.c_int
+    L.bathgpu_pack_dna4.argtypes = [C.POINTER(C.c_uint8), C.c_int64, C.POINTER(C.c_uint8)]
+    L.bathgpu_upload_block_packed4.restype = C.c_int
+    L.bathgpu_upload_block_packed4.argtypes = [vp, C.POINTER(C.c_uint8), C.c_int64]
     L.bathgpu_fs_fwd_windows.restype = C.c_int
     L.bathgpu_fs_fwd_windows.argtypes = [vp, vp, C.c_int, fp, fp, ip]
     L.bathgpu_stage_windows.restype = C.c_int
@@ -132,6 +139,8 @@ def load():
     L.bathgpu_revcomp_slot.argtypes = [vp, C.c_int, C.c_int]
     L.bathgpu_fs_fwd_block.restype = C.c_int
     L.bathgpu_fs_fwd_block.argtypes = [vp, C.POINTER(C.c_uint8), C.c_int64, vp, C.c_int, fp, fp, ip]
+    L.bathgpu_fs_fwd_block_packed4.restype = C.c_int
+    L.bathgpu_fs_fwd_block_packed4.argtypes = [vp, C.POINTER(C.c_uint8), C.c_int64, vp, C.c_int, fp, fp, ip]
     L.bathgpu_fs_forward_matrices.restype = C.c_int
     L.bathgpu_fs_forward_matrices.argtypes = [vp, vp, C.c_int, fp, fp, fp, C.c_int64, fp, ip]
     L.bathgpu_select_slot.restype = C.c_int
@@ -229,6 +238,18 @@ class Context:
     def upload_block(self, dsq):
         dsq = np.ascontiguousarray(dsq, dtype=np.uint8)
         self._check(self.lib.bathgpu_upload_block(self.h, dsq.ctypes.data_as(C.POINTER(C.c_uint8)), len(dsq) - 2))
+
+    def upload_block_packed4(self, packed, n):
+        """bathgpu_upload_block_packed4: a block already packed two nucleotides per byte (pack_dna4)"""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        assert len(packed) >= (n + 1) // 2
+        self._check(self.lib.bathgpu_upload_block_packed4(self.h, packed.ctypes.data_as(C.POINTER(C.c_uint8)), n))
+
+    def fs_fwd_block_packed4_into(self, packed, n, wins, xfE, sc, st):
+        """bathgpu_fs_fwd_block_packed4: upload (half the bytes, no packing kernel) and score in one call, into caller-owned arrays"""
+        xf = np.asarray(xfE, np.float32)
+        self._check(self.lib.bathgpu_fs_fwd_block_packed4(self.h, packed.ctypes.data_as(C.POINTER(C.c_uint8)), n, wins.ctypes.data, len(wins),
+                                                          _f(xf), _f(sc), _i(st)))
 
     @staticmethod
     def make_windows(starts, lengths, nj=1.0):
@@ -480,3 +501,17 @@ class Context:
         self._check(self.lib.bathgpu_fs_domains(self.h, envs.ctypes.data, n, _f(xf), res.ctypes.data, tr.ctypes.data,
                                                 max_steps))
         return res, tr
+
+
+def pack_dna4(dsq, out=None):
+    """bathgpu_pack_dna4: ESL_DSQ bytes (sentinels at both ends) -> two nucleotides per byte, the form bathgpu_upload_block_packed4 and
+    bathgpu_fs_fwd_block_packed4 take"""
+    L = load()
+    dsq = np.ascontiguousarray(dsq, np.uint8)
+    n = len(dsq) - 2
+    if out is None:
+        out = np.empty(int(L.bathgpu_packed4_bytes(n)), np.uint8)
+    st = L.bathgpu_pack_dna4(dsq.ctypes.data_as(C.POINTER(C.c_uint8)), n, out.ctypes.data_as(C.POINTER(C.c_uint8)))
+    if st != 0:
+        raise RuntimeError(f"bathgpu_pack_dna4: status {st}")
+    return out

@@ -778,6 +778,60 @@ extern "C" int bathgpu_upload_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_
   return BATHGPU_OK;
 }
 
+// ---- host-packed blocks: two nucleotides per byte (nucleotide 2j+1 of dsq in the low nibble of byte j, 2j+2 in the high one, codes
+// above 15 stored as 15 = N), which is the device's own packed layout from word 1 on -- the block crosses the link at half the bytes
+// and needs no packing pass.
+extern "C" int64_t bathgpu_packed4_bytes(int64_t n) { return n < 0 ? 0 : (n + 1) / 2; }
+
+extern "C" int bathgpu_pack_dna4(const uint8_t *dsq, int64_t n, uint8_t *packed)
+{
+  if (!dsq || !packed || n < 1) return BATHGPU_EINVAL;
+  const uint8_t *d = dsq + 1;
+  const int64_t full = n / 2;
+  for (int64_t j = 0; j < full; ++j) {
+    const uint8_t lo = d[2 * j] > 15 ? 15 : d[2 * j], hi = d[2 * j + 1] > 15 ? 15 : d[2 * j + 1];
+    packed[j] = (uint8_t)(lo | (hi << 4));
+  }
+  if (n & 1) packed[full] = (uint8_t)((d[n - 1] > 15 ? 15 : d[n - 1]) | 0xF0);
+  return BATHGPU_OK;
+}
+
+// guard word in front, the nibbles behind nucleotide n and the 24 guard words behind the data
+__global__ void dna4_guards_kernel(uint32_t *__restrict__ out, long long n)
+{
+  const long long wl = (n + 7) / 8;                       // word of the last nucleotide
+  const int t = threadIdx.x;
+  if (t == 0) out[0] = 0xFFFFFFFFu;
+  else if (t == 1) { const int k = (int)(n - 8 * (wl - 1)); if (k < 8) out[wl] |= 0xFFFFFFFFu << (4 * k); }
+  else if (t < 26) out[wl + t - 1] = 0xFFFFFFFFu;
+}
+
+// the byte form of a packed block (ORF finder, reverse complement read bytes): bytes[1 + p] = nibble p, sentinels at both ends
+__global__ void unpack_dna4_kernel(const uint32_t *__restrict__ dna4, long long n, uint8_t *__restrict__ bytes)
+{
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  bytes[1 + p] = (uint8_t)((dna4[p / 8 + 1] >> (4 * (int)(p & 7))) & 15u);
+  if (p == 0) { bytes[0] = 255; bytes[n + 1] = 255; }
+}
+
+extern "C" int bathgpu_upload_block_packed4(bathgpu_ctx *ctx, const uint8_t *packed, int64_t n)
+{
+  if (!ctx || !packed || n < 1) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_upload_block_packed4");
+  CUDA_TRY(ctx, enter(ctx));
+  const long long nwords = (n + 8 + 7) / 8 + 24;
+  TargetSlot &S = ctx->S();
+  if (S.dna_bytes.reserve((size_t)n + 2) != BATHGPU_OK || S.dna4.reserve((size_t)nwords * 4) != BATHGPU_OK)
+    return fail(ctx, BATHGPU_EMEM, "device allocation failed for a %lld-nt block", (long long)n);
+  CUDA_TRY(ctx, cudaMemcpyAsync(S.dna4.as<uint8_t>() + 4, packed, (size_t)((n + 1) / 2), cudaMemcpyHostToDevice, ctx->stream));
+  dna4_guards_kernel<<<1, 32, 0, ctx->stream>>>(S.dna4.as<uint32_t>(), n);
+  unpack_dna4_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(S.dna4.as<uint32_t>(), n, S.dna_bytes.as<uint8_t>());
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  S.block_n = n; S.nres = 0;
+  return BATHGPU_OK;
+}
+
 // dst[1 + p] = complement of src[n - p] (Easel's DNA alphabet: A C G T - R Y M K S W H B V D N * ~)
 __global__ void revcomp_kernel(const uint8_t *__restrict__ src, long long n, uint8_t *__restrict__ dst)
 {
@@ -816,10 +870,10 @@ static cudaError_t dispatch_fwd(bool xmx, int J, const FsParserArgs &a, int sms,
 // Upload a block and score its windows in one call, with the upload hidden behind the kernel: the block crosses the link in
 // chunks on a second stream, and the windows that end inside the part already resident are scored while the rest is in flight
 // (per block the reference uploads nothing and calls p7_ForwardParser_Frameshift_3Codons window by window, src/p7_pipeline.c:1450).
-extern "C" int bathgpu_fs_fwd_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_t n, const bathgpu_window *wins, int nwin,
-                                    const float xfE[2], float *fwdsc, int32_t *status)
+static int fs_fwd_block_impl(bathgpu_ctx *ctx, const uint8_t *dsq, const uint8_t *packed, int64_t n, const bathgpu_window *wins, int nwin,
+                             const float xfE[2], float *fwdsc, int32_t *status)
 {
-  if (!ctx || !dsq || n < 1 || !wins || nwin < 1 || !xfE || !fwdsc || !status) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fs_fwd_block");
+  if (!ctx || (!dsq && !packed) || n < 1 || !wins || nwin < 1 || !xfE || !fwdsc || !status) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fs_fwd_block");
   if (!ctx->fs3.loaded) return fail(ctx, BATHGPU_EINVAL, "3-codon profile not loaded");
   for (int w = 0; w < nwin; ++w)
     if (wins[w].L < 3 || wins[w].start < 1 || wins[w].start + wins[w].L - 1 > n)
@@ -849,11 +903,20 @@ extern "C" int bathgpu_fs_fwd_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_
   cudaEvent_t *pack_ev = ctx->chunk_ev, *join_ev = ctx->chunk_ev + 8;
   for (int c = 0; c < K; ++c) {
     const long long p0 = c ? cuts[c - 1] : 0, p1 = cuts[c];                       // 0-based nucleotides [p0, p1); dsq[1 + p] is nucleotide p
-    CUDA_TRY(ctx, cudaMemcpyAsync(S.dna_bytes.as<uint8_t>() + 1 + p0, dsq + 1 + p0, (size_t)(p1 - p0), cudaMemcpyHostToDevice, ctx->copy_stream));
-    // packed word w holds nucleotides 8w-8 .. 8w-1: this chunk completes words p0/8+1 .. p1/8 (and the tail guard at the end)
-    const long long wlo = (c == 0) ? 0 : p0 / 8 + 1, whi = (p1 >= n) ? nwords : p1 / 8 + 1;
-    if (whi > wlo)
-      pack_dna4_range_kernel<<<(unsigned)((whi - wlo + 255) / 256), 256, 0, ctx->copy_stream>>>(S.dna_bytes.as<uint8_t>(), n, S.dna4.as<uint32_t>(), wlo, whi);
+    if (packed) {
+      // host-packed: bytes p0/2 .. (p1+1)/2 land in the packed words themselves (cuts are multiples of 8 except the last)
+      CUDA_TRY(ctx, cudaMemcpyAsync(S.dna4.as<uint8_t>() + 4 + p0 / 2, packed + p0 / 2, (size_t)((p1 + 1) / 2 - p0 / 2), cudaMemcpyHostToDevice, ctx->copy_stream));
+      if (p1 >= n) {
+        dna4_guards_kernel<<<1, 32, 0, ctx->copy_stream>>>(S.dna4.as<uint32_t>(), n);
+        unpack_dna4_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->copy_stream>>>(S.dna4.as<uint32_t>(), n, S.dna_bytes.as<uint8_t>());
+      } else if (c == 0) dna4_guards_kernel<<<1, 1, 0, ctx->copy_stream>>>(S.dna4.as<uint32_t>(), n);     // the front guard word (thread 0 only)
+    } else {
+      CUDA_TRY(ctx, cudaMemcpyAsync(S.dna_bytes.as<uint8_t>() + 1 + p0, dsq + 1 + p0, (size_t)(p1 - p0), cudaMemcpyHostToDevice, ctx->copy_stream));
+      // packed word w holds nucleotides 8w-8 .. 8w-1: this chunk completes words p0/8+1 .. p1/8 (and the tail guard at the end)
+      const long long wlo = (c == 0) ? 0 : p0 / 8 + 1, whi = (p1 >= n) ? nwords : p1 / 8 + 1;
+      if (whi > wlo)
+        pack_dna4_range_kernel<<<(unsigned)((whi - wlo + 255) / 256), 256, 0, ctx->copy_stream>>>(S.dna_bytes.as<uint8_t>(), n, S.dna4.as<uint32_t>(), wlo, whi);
+    }
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaEventRecord(pack_ev[c], ctx->copy_stream));
   }
@@ -911,6 +974,20 @@ extern "C" int bathgpu_fs_fwd_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_
   ctx->last_launches = launches;
   ctx->nstaged = 0;
   return BATHGPU_OK;
+}
+
+extern "C" int bathgpu_fs_fwd_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_t n, const bathgpu_window *wins, int nwin,
+                                    const float xfE[2], float *fwdsc, int32_t *status)
+{
+  if (!dsq) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fs_fwd_block");
+  return fs_fwd_block_impl(ctx, dsq, nullptr, n, wins, nwin, xfE, fwdsc, status);
+}
+
+extern "C" int bathgpu_fs_fwd_block_packed4(bathgpu_ctx *ctx, const uint8_t *packed, int64_t n, const bathgpu_window *wins, int nwin,
+                                            const float xfE[2], float *fwdsc, int32_t *status)
+{
+  if (!packed) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_fs_fwd_block_packed4");
+  return fs_fwd_block_impl(ctx, nullptr, packed, n, wins, nwin, xfE, fwdsc, status);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -417,11 +417,12 @@ struct PhaseTrace {
 
 // BE: the bathhost_backend the call goes to (a local reference at every call site)
 static const bool g_trace_calls = [] { const char *e = getenv("BATHHOST_TRACE"); return e && atoi(e) >= 2; }();   // BATHHOST_TRACE=2: slow stage calls too
+static const double g_trace_call_ms = [] { const char *e = getenv("BATHHOST_TRACE"); return e && atoi(e) >= 3 ? 0.2 : 5.0; }();   // =3: every call from 0.2 ms
 #define BE_TRY(s, call, what)                                                                   \
   do { const auto t0_ = std::chrono::steady_clock::now();                                       \
        int st_ = (call);                                                                        \
        if (g_trace_calls) { const double ms_ = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0_).count(); \
-         if (ms_ >= 5.0) fprintf(stderr, "[bathhost]   ctx %p %-28s %9.2f ms\n", BE.ctx, what, ms_); } \
+         if (ms_ >= g_trace_call_ms) fprintf(stderr, "[bathhost]   ctx %p %-28s %9.2f ms\n", BE.ctx, what, ms_); } \
        if (st_ != 0) return fail(s, st_, std::string(what) + " failed: " +                      \
        (BE.last_error ? BE.last_error(BE.ctx) : "?")); } while (0)
 

@@ -168,6 +168,14 @@ int bathgpu_select_slot(bathgpu_ctx *ctx, int slot);
 /* dsq: ESL_DSQ codes, dsq[1..n] valid (dsq[0], dsq[n+1] sentinels).  Packed to 4 bits/nt on device. */
 int bathgpu_upload_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_t n);
 
+/* Host-packed blocks ("packed 2-bit/4-bit DNA windows" at the boundary): two nucleotides per byte -- dsq[2j+1] in the low nibble of byte j,
+ * dsq[2j+2] in the high one, codes above 15 (Easel's '*' and '~') stored as 15 (N), an odd last nibble 15 -- which is the device's own
+ * layout, so the block crosses the link at half the bytes and is not packed again.  bathgpu_pack_dna4 makes that form on the host
+ * (packed: bathgpu_packed4_bytes(n) = (n+1)/2 bytes); a reader that digitises sequence files can emit it directly. */
+int64_t bathgpu_packed4_bytes(int64_t n);
+int bathgpu_pack_dna4(const uint8_t *dsq, int64_t n, uint8_t *packed);
+int bathgpu_upload_block_packed4(bathgpu_ctx *ctx, const uint8_t *packed, int64_t n);
+
 /* The reverse complement of slot src's resident sequence becomes slot dst's resident sequence (the bottom strand of a target whose
  * top strand was uploaded: bathsearch reverse-complements on the host, src/bathsearch.c:1087-1096, and would upload it again). */
 int bathgpu_revcomp_slot(bathgpu_ctx *ctx, int src, int dst);
@@ -181,6 +189,10 @@ int bathgpu_fs_fwd_windows(bathgpu_ctx *ctx, const bathgpu_window *wins, int n, 
  * link in chunks while the windows that end inside the part already resident are being scored.  Any window order. */
 int bathgpu_fs_fwd_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_t n, const bathgpu_window *wins, int nwin,
                          const float xfE[2], float *fwdsc, int32_t *status);
+
+/* bathgpu_fs_fwd_block on a host-packed block (bathgpu_pack_dna4): same chunks, half the bytes, no packing kernel. */
+int bathgpu_fs_fwd_block_packed4(bathgpu_ctx *ctx, const uint8_t *packed, int64_t n, const bathgpu_window *wins, int nwin,
+                                 const float xfE[2], float *fwdsc, int32_t *status);
 
 /* Same stage on descriptors already resident in device memory (set by
  * bathgpu_stage_windows); results stay on the device until bathgpu_fetch_scores.
