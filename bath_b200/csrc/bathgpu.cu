@@ -91,6 +91,7 @@ struct FsProfileImage {
 struct TargetSlot {          // one resident target: packed DNA + codon classes + survivor residues (e.g. one strand of one chunk of the target)
   DevBuf  dna_bytes, dna4, residues, cls;
   int64_t block_n = 0, nres = 0;
+  bool    bytes_valid = false;      // dna_bytes holds the block (a host-packed upload fills dna4 only; the byte form is made when something asks for it)
 };
 constexpr int kMaxSlots = 1 << 16;
 
@@ -100,6 +101,7 @@ struct bathgpu_ctx {
   cudaStream_t  stream = nullptr, copy_stream = nullptr, stream2 = nullptr;
   cudaEvent_t   chunk_ev[16] = {};
   cudaEvent_t   ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t   sync_ev = nullptr;                    // blocking-sync event: a host thread waiting for its stream sleeps instead of spinning
   std::string   err;
   FsProfileImage fs3, fs5;
   std::vector<std::unique_ptr<TargetSlot>> slot;      // grows on demand (bathgpu_select_slot)
@@ -171,6 +173,19 @@ static int reserve_matrices(bathgpu_ctx *ctx, size_t pp_bytes, size_t oa_bytes)
   return BATHGPU_OK;
 }
 
+// A stage call ends by waiting for its stream.  cudaStreamSynchronize spins on a core, and a search drives 12-24 contexts, one host
+// thread each, beside a host pool as wide as the machine; BATHGPU_BLOCKING_SYNC=1 makes the waiting threads sleep on a blocking-sync
+// event instead.  Measured on a 16-core B200 box (3 profiles x 1 Gbp): 4.19-4.38 Gbp/s sleeping against 4.42-4.66 spinning, and the
+// one-call Forward path from host buffers 15.8 against 15.2 ms -- the wake-up costs more than the cores it frees, so spinning stays
+// the default.
+static const bool g_blocking_sync = [] { const char *e = getenv("BATHGPU_BLOCKING_SYNC"); return e && atoi(e) != 0; }();
+static inline cudaError_t wait_stream(bathgpu_ctx *ctx)
+{
+  if (!g_blocking_sync || !ctx->sync_ev) return cudaStreamSynchronize(ctx->stream);
+  const cudaError_t e = cudaEventRecord(ctx->sync_ev, ctx->stream);
+  return e != cudaSuccess ? e : cudaEventSynchronize(ctx->sync_ev);
+}
+
 // ---------------------------------------------------------------------------------------------
 extern "C" int bathgpu_create(int device, bathgpu_ctx **ret_ctx)
 {
@@ -186,7 +201,8 @@ extern "C" int bathgpu_create(int device, bathgpu_ctx **ret_ctx)
   }
   if (ctx->prop.major < 10) { delete ctx; return BATHGPU_ENODEVICE; }   // sm_100a code only
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) {
     cudaGetLastError(); delete ctx; return BATHGPU_ECUDA;
   }
   {                                // the pool never hands memory back to the driver on its own: what one stage frees the next one reuses
@@ -209,6 +225,7 @@ extern "C" void bathgpu_destroy(bathgpu_ctx *ctx)
   cudaStreamSynchronize(ctx->stream);
   // every device buffer of the context (profile images, target slots, stage workspaces) is a DevBuf and frees itself with the context
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+  if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
   for (auto &e : ctx->o_ev) if (e) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); cudaStreamDestroy(ctx->stream2); for (auto &e : ctx->chunk_ev) if (e) cudaEventDestroy(e); }
@@ -301,7 +318,7 @@ extern "C" int bathgpu_measure_int16_peak(bathgpu_ctx *ctx, double *tera_ops)
     int16x2_probe_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->scratch.as<unsigned>(), iters, 0x00030001u, 0x00050002u);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, wait_stream(ctx));
     float ms = 0.f;
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     if (rep >= 2 && ms < best) best = ms;
@@ -323,7 +340,7 @@ extern "C" int bathgpu_measure_fp32_peak(bathgpu_ctx *ctx, double *tflops, doubl
     fp32_fma_probe_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->scratch.as<float>(), iters, 0.999f, 1e-3f);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, wait_stream(ctx));
     float ms = 0.f;
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     if (rep >= 2 && ms < best) best = ms;
@@ -414,7 +431,7 @@ extern "C" int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int n
         ef[(size_t)c * mpad + perm_index(k - 1, J)] = (float)((double)rfv[(size_t)c * ld + k] * sK[k] * zK[k] * mmK(k));
     if (im.emis_fwd.reserve(ef.size() * sizeof(float)) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
     CUDA_TRY(ctx, cudaMemcpyAsync(im.emis_fwd.p, ef.data(), ef.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, wait_stream(ctx));
     for (int lane = 0; lane < 32; ++lane) {
       double pp = 1.0, ps = 1.0;
       for (int j = 0; j < J; ++j) {
@@ -491,12 +508,12 @@ extern "C" int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int n
       if (getenv("BATHGPU_FULL_SCAN")) im.mw_scan_steps = 5;
       if (im.cellmw.reserve(mw.size() * sizeof(float)) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
       CUDA_TRY(ctx, cudaMemcpyAsync(im.cellmw.p, mw.data(), mw.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      CUDA_TRY(ctx, wait_stream(ctx));
     } else im.cellmw.release();
     if (getenv("BATHGPU_FULL_SCAN")) im.scan_steps = 5;
     if (im.cellc.reserve(cc.size() * sizeof(float)) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
     CUDA_TRY(ctx, cudaMemcpyAsync(im.cellc.p, cc.data(), cc.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, wait_stream(ctx));
   }
 
   // ---- backward constants (fs_backward.cuh)
@@ -534,7 +551,7 @@ extern "C" int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int n
     }
     if (im.cellb.reserve(cc.size() * sizeof(float)) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
     CUDA_TRY(ctx, cudaMemcpyAsync(im.cellb.p, cc.data(), cc.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, wait_stream(ctx));
   }
 
   // ---- the 3-codon Backward parser's scaled constants and table copy (fs_backward.cuh, Bck3Consts)
@@ -620,13 +637,13 @@ extern "C" int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int n
       }
       if (im.cellbmw.reserve(mw.size() * sizeof(float)) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
       CUDA_TRY(ctx, cudaMemcpyAsync(im.cellbmw.p, mw.data(), mw.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      CUDA_TRY(ctx, wait_stream(ctx));
     } else im.cellbmw.release();
     if (im.cellb3.reserve(cc.size() * sizeof(float)) != BATHGPU_OK || im.emis_bck.reserve(eb.size() * sizeof(float)) != BATHGPU_OK)
       return fail(ctx, BATHGPU_EMEM, "device allocation failed");
     CUDA_TRY(ctx, cudaMemcpyAsync(im.cellb3.p, cc.data(), cc.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(im.emis_bck.p, eb.data(), eb.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, wait_stream(ctx));
   }
 
   // ---- full-matrix Forward constants, null2 amino rows, optimal-accuracy masks, raw transitions (fs_domain.cuh)
@@ -707,12 +724,12 @@ extern "C" int bathgpu_load_fs_profile(bathgpu_ctx *ctx, int which, int M, int n
     CUDA_TRY(ctx, cudaMemcpyAsync(im.oaflags.p, fl.data(), fl.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(im.oapass.p, pass.data(), pass.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(im.tfvraw.p, tfv, (size_t)8 * ld * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, wait_stream(ctx));
   }
 
   if (im.emis.reserve(emis.size() * sizeof(float)) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
   CUDA_TRY(ctx, cudaMemcpyAsync(im.emis.p, emis.data(), emis.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, wait_stream(ctx));
   im.loaded = true;
   // CUDA loads kernels lazily: touch the ones this profile will use now, not inside the first stage call
 #define X(S) preload_fwd_##S(J); preload_bck_##S(J); preload_fs5_##S(J); preload_orf_##S(J);
@@ -773,8 +790,8 @@ extern "C" int bathgpu_upload_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_
   const long long blocks = (nwords + threads - 1) / threads;
   pack_dna4_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(ctx->S().dna_bytes.as<uint8_t>(), n, ctx->S().dna4.as<uint32_t>(), nwords);
   CUDA_TRY(ctx, cudaGetLastError());
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  ctx->S().block_n = n;
+  CUDA_TRY(ctx, wait_stream(ctx));
+  ctx->S().block_n = n; ctx->S().bytes_valid = true;
   return BATHGPU_OK;
 }
 
@@ -806,13 +823,24 @@ __global__ void dna4_guards_kernel(uint32_t *__restrict__ out, long long n)
   else if (t < 26) out[wl + t - 1] = 0xFFFFFFFFu;
 }
 
+// A host-packed chunk lands in device memory by DMA and is read by the Forward kernel from there; the byte path's packing kernel left
+// its output in L2 instead (a 100 Mbp block is 50 MB packed, L2 holds 126 MB), and the Forward kernel's first touch of a window is
+// latency-bound: 15.67 against 15.19 ms per 100 Mbp.  One prefetch per 128-byte line behind each chunk's copy puts the packed words in L2.
+__global__ void l2_prefetch_kernel(const uint8_t *__restrict__ p, long long nbytes)
+{
+  const long long line = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (line * 128 < nbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + line * 128));
+}
+
 // the byte form of a packed block (ORF finder, reverse complement read bytes): bytes[1 + p] = nibble p, sentinels at both ends
 __global__ void unpack_dna4_kernel(const uint32_t *__restrict__ dna4, long long n, uint8_t *__restrict__ bytes)
 {
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  bytes[1 + p] = (uint8_t)((dna4[p / 8 + 1] >> (4 * (int)(p & 7))) & 15u);
-  if (p == 0) { bytes[0] = 255; bytes[n + 1] = 255; }
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // packed word w + 1 holds nucleotides 8w .. 8w+7
+  if (8 * w >= n) return;
+  const uint32_t word = dna4[w + 1];
+#pragma unroll
+  for (int b = 0; b < 8; ++b) if (8 * w + b < n) bytes[1 + 8 * w + b] = (uint8_t)((word >> (4 * b)) & 15u);
+  if (w == 0) { bytes[0] = 255; bytes[n + 1] = 255; }
 }
 
 extern "C" int bathgpu_upload_block_packed4(bathgpu_ctx *ctx, const uint8_t *packed, int64_t n)
@@ -825,10 +853,9 @@ extern "C" int bathgpu_upload_block_packed4(bathgpu_ctx *ctx, const uint8_t *pac
     return fail(ctx, BATHGPU_EMEM, "device allocation failed for a %lld-nt block", (long long)n);
   CUDA_TRY(ctx, cudaMemcpyAsync(S.dna4.as<uint8_t>() + 4, packed, (size_t)((n + 1) / 2), cudaMemcpyHostToDevice, ctx->stream));
   dna4_guards_kernel<<<1, 32, 0, ctx->stream>>>(S.dna4.as<uint32_t>(), n);
-  unpack_dna4_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(S.dna4.as<uint32_t>(), n, S.dna_bytes.as<uint8_t>());
   CUDA_TRY(ctx, cudaGetLastError());
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  S.block_n = n; S.nres = 0;
+  CUDA_TRY(ctx, wait_stream(ctx));
+  S.block_n = n; S.nres = 0; S.bytes_valid = false;
   return BATHGPU_OK;
 }
 
@@ -856,11 +883,15 @@ extern "C" int bathgpu_revcomp_slot(bathgpu_ctx *ctx, int src, int dst)
   const long long nwords = (n + 8 + 7) / 8 + 24;
   if (B.dna_bytes.reserve((size_t)n + 2) != BATHGPU_OK || B.dna4.reserve((size_t)nwords * 4) != BATHGPU_OK)
     return fail(ctx, BATHGPU_EMEM, "device allocation failed for a %lld-nt block", n);
+  if (!A.bytes_valid) {                                     // host-packed upload: the byte form is made now
+    unpack_dna4_kernel<<<(unsigned)(((n + 7) / 8 + 255) / 256), 256, 0, ctx->stream>>>(A.dna4.as<uint32_t>(), n, A.dna_bytes.as<uint8_t>());
+    A.bytes_valid = true;
+  }
   revcomp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(A.dna_bytes.as<uint8_t>(), n, B.dna_bytes.as<uint8_t>());
   pack_dna4_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(B.dna_bytes.as<uint8_t>(), n, B.dna4.as<uint32_t>(), nwords);
   CUDA_TRY(ctx, cudaGetLastError());
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  B.block_n = n; B.nres = 0;
+  CUDA_TRY(ctx, wait_stream(ctx));
+  B.block_n = n; B.nres = 0; B.bytes_valid = true;
   return BATHGPU_OK;
 }
 
@@ -890,7 +921,7 @@ static int fs_fwd_block_impl(bathgpu_ctx *ctx, const uint8_t *dsq, const uint8_t
       ctx->wins.reserve((size_t)nwin * sizeof(WindowDesc)) != BATHGPU_OK || ctx->fwdsc.reserve((size_t)nwin * 4) != BATHGPU_OK ||
       ctx->status.reserve((size_t)nwin * 4) != BATHGPU_OK || ctx->counter.reserve(64) != BATHGPU_OK)
     return fail(ctx, BATHGPU_EMEM, "device allocation failed");
-  S.block_n = n; S.nres = 0;
+  S.block_n = n; S.nres = 0; S.bytes_valid = (packed == nullptr);
   // Chunks grow fourfold: scoring a chunk takes several times longer than moving it, so every later chunk arrives while the
   // one before it is being scored, and the first one is small enough that the device starts almost at once.
   long long cuts[8]; int K = 0;
@@ -906,10 +937,12 @@ static int fs_fwd_block_impl(bathgpu_ctx *ctx, const uint8_t *dsq, const uint8_t
     if (packed) {
       // host-packed: bytes p0/2 .. (p1+1)/2 land in the packed words themselves (cuts are multiples of 8 except the last)
       CUDA_TRY(ctx, cudaMemcpyAsync(S.dna4.as<uint8_t>() + 4 + p0 / 2, packed + p0 / 2, (size_t)((p1 + 1) / 2 - p0 / 2), cudaMemcpyHostToDevice, ctx->copy_stream));
-      if (p1 >= n) {
-        dna4_guards_kernel<<<1, 32, 0, ctx->copy_stream>>>(S.dna4.as<uint32_t>(), n);
-        unpack_dna4_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->copy_stream>>>(S.dna4.as<uint32_t>(), n, S.dna_bytes.as<uint8_t>());
-      } else if (c == 0) dna4_guards_kernel<<<1, 1, 0, ctx->copy_stream>>>(S.dna4.as<uint32_t>(), n);     // the front guard word (thread 0 only)
+      {
+        const long long b0 = (4 + p0 / 2) & ~127LL, b1 = 4 + (p1 + 1) / 2, lines = (b1 - b0 + 127) / 128;
+        l2_prefetch_kernel<<<(unsigned)((lines + 255) / 256), 256, 0, ctx->copy_stream>>>(S.dna4.as<uint8_t>() + b0, b1 - b0);
+      }
+      if (p1 >= n) dna4_guards_kernel<<<1, 32, 0, ctx->copy_stream>>>(S.dna4.as<uint32_t>(), n);
+      else if (c == 0) dna4_guards_kernel<<<1, 1, 0, ctx->copy_stream>>>(S.dna4.as<uint32_t>(), n);     // the front guard word (thread 0 only)
     } else {
       CUDA_TRY(ctx, cudaMemcpyAsync(S.dna_bytes.as<uint8_t>() + 1 + p0, dsq + 1 + p0, (size_t)(p1 - p0), cudaMemcpyHostToDevice, ctx->copy_stream));
       // packed word w holds nucleotides 8w-8 .. 8w-1: this chunk completes words p0/8+1 .. p1/8 (and the tail guard at the end)
@@ -967,7 +1000,7 @@ static int fs_fwd_block_impl(bathgpu_ctx *ctx, const uint8_t *dsq, const uint8_t
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(in_order ? fwdsc : sc.data(), ctx->fwdsc.p, (size_t)nwin * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(in_order ? status : st.data(), ctx->status.p, (size_t)nwin * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, wait_stream(ctx));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
   if (!in_order) for (int w = 0; w < nwin; ++w) { fwdsc[order[w]] = sc[w]; status[order[w]] = st[w]; }
   CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
@@ -1035,7 +1068,7 @@ extern "C" int bathgpu_stage_windows(bathgpu_ctx *ctx, const bathgpu_window *win
       ctx->status.reserve((size_t)n * 4) != BATHGPU_OK || ctx->counter.reserve(64) != BATHGPU_OK)
     return fail(ctx, BATHGPU_EMEM, "device allocation failed");
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->wins.p, wins, (size_t)n * sizeof(WindowDesc), cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, wait_stream(ctx));
   ctx->nstaged = n;
   return BATHGPU_OK;
 }
@@ -1058,7 +1091,7 @@ extern "C" int bathgpu_fs_fwd_staged(bathgpu_ctx *ctx, const float xfE[2])
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   CUDA_TRY(ctx, dispatch_fwd(false, im.J, a, ctx->prop.multiProcessorCount, ctx->stream));
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, wait_stream(ctx));
   CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
   ctx->last_launches = 1;
   return BATHGPU_OK;
@@ -1070,7 +1103,7 @@ extern "C" int bathgpu_fetch_scores(bathgpu_ctx *ctx, float *fwdsc, int32_t *sta
   CUDA_TRY(ctx, enter(ctx));
   if (fwdsc)  CUDA_TRY(ctx, cudaMemcpyAsync(fwdsc,  ctx->fwdsc.p,  (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (status) CUDA_TRY(ctx, cudaMemcpyAsync(status, ctx->status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, wait_stream(ctx));
   return BATHGPU_OK;
 }
 
@@ -1162,7 +1195,7 @@ static int bck_decode_chunk(bathgpu_ctx *ctx, const bathgpu_window *wins, int n,
   if (fwdsc) CUDA_TRY(ctx, cudaMemcpyAsync(fwdsc, ctx->fwdsc.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (bcksc) CUDA_TRY(ctx, cudaMemcpyAsync(bcksc, ctx->bcksc.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(status, ctx->status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, wait_stream(ctx));
   float ms = 0.f;
   CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   ctx->last_ms += ms;
@@ -1245,7 +1278,7 @@ extern "C" int bathgpu_fs_fetch_xrows(bathgpu_ctx *ctx, int which, float *out, i
   CUDA_TRY(ctx, enter(ctx));
   const DevBuf &b = which ? ctx->bxmx : ctx->fxmx;
   CUDA_TRY(ctx, cudaMemcpyAsync(out, b.p, (size_t)nrows * 24, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, wait_stream(ctx));
   return BATHGPU_OK;
 }
 
@@ -1322,7 +1355,7 @@ static int domains_chunk(bathgpu_ctx *ctx, const bathgpu_envelope *envs, int n, 
   CUDA_TRY(ctx, cudaMemcpyAsync(st.data(), ctx->dstat.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(tl.data(), ctx->dtlen.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(steps.data(), ctx->dsteps.p, steps.size() * sizeof(TraceStep), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, wait_stream(ctx));
   float ms = 0.f;
   CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   ctx->last_ms += ms;
@@ -1477,7 +1510,7 @@ extern "C" int bathgpu_fs_forward_matrices(bathgpu_ctx *ctx, const bathgpu_envel
     }
     CUDA_TRY(ctx, cudaMemcpyAsync(fwdsc + e0, ctx->dfw.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(status + e0, ctx->dstat.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, wait_stream(ctx));
     float ms = 0.f;
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms += ms; ctx->last_launches += scores_only ? 1 : 2;
@@ -1590,7 +1623,7 @@ extern "C" int bathgpu_load_filter_profile(bathgpu_ctx *ctx, const bathgpu_filte
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->f_nrb.p, hn.data(), hn.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->f_twv.p, ht.data(), ht.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->f_ddsum.p, dds.data(), dds.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, wait_stream(ctx));
   ctx->flt_loaded = true;
   preload_msv_filter(W, P); preload_vit_filter_lo(P); preload_vit_filter_hi(P);
   return BATHGPU_OK;
@@ -1602,7 +1635,7 @@ extern "C" int bathgpu_upload_orfs(bathgpu_ctx *ctx, const uint8_t *residues, in
   CUDA_TRY(ctx, enter(ctx));
   if (ctx->S().residues.reserve((size_t)n + 64) != BATHGPU_OK) return fail(ctx, BATHGPU_EMEM, "device allocation failed");
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->S().residues.p, residues, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, wait_stream(ctx));
   ctx->S().nres = n;
   return BATHGPU_OK;
 }
@@ -1658,11 +1691,11 @@ static int fetch_windows(bathgpu_ctx *ctx, bathgpu_orf_window *wins, int max_win
 {
   int nw = 0;
   CUDA_TRY(ctx, cudaMemcpyAsync(&nw, ctx->fnw.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, wait_stream(ctx));
   if (nw > max_wins) return fail(ctx, BATHGPU_EINVAL, "window buffer too small: %d windows found, room for %d", nw, max_wins);
   if (nw > 0) {
     CUDA_TRY(ctx, cudaMemcpyAsync(wins, ctx->fwins.p, (size_t)nw * sizeof(WindowRec), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, wait_stream(ctx));
     // the reference appends windows ORF by ORF in target order (src/p7_pipeline.c:1669-1680)
     std::sort(wins, wins + nw, [](const bathgpu_orf_window &x, const bathgpu_orf_window &y) {
       return x.orf != y.orf ? x.orf < y.orf : x.n < y.n; });
@@ -1676,7 +1709,7 @@ static int finish_filter(bathgpu_ctx *ctx, int n, float *sc, int32_t *status, in
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   if (sc)     CUDA_TRY(ctx, cudaMemcpyAsync(sc, ctx->fsc.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (status) CUDA_TRY(ctx, cudaMemcpyAsync(status, ctx->fst.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, wait_stream(ctx));
   CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
   ctx->last_launches = launches;
   return BATHGPU_OK;
@@ -1821,7 +1854,7 @@ static int orf_chunk(bathgpu_ctx *ctx, const EnvelopeDesc *envs, int n, const fl
   if (!full) {
     CUDA_TRY(ctx, cudaMemcpyAsync(fwd_xrows + (size_t)x_off0 * 6, ctx->dfx.p, rows * 24, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(bck_xrows + (size_t)x_off0 * 6, ctx->bxmx.p, rows * 24, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, wait_stream(ctx));
     float ms = 0.f;
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms += ms; ctx->last_launches += 2;
@@ -1835,7 +1868,7 @@ static int orf_chunk(bathgpu_ctx *ctx, const EnvelopeDesc *envs, int n, const fl
   CUDA_TRY(ctx, cudaMemcpyAsync(n2.data(), ctx->dnull2.p, (size_t)n * 29 * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(tl.data(), ctx->dtlen.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(steps.data(), ctx->dsteps.p, steps.size() * sizeof(TraceStep), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, wait_stream(ctx));
   float ms = 0.f;
   CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   ctx->last_ms += ms; ctx->last_launches += 4;
@@ -2007,7 +2040,7 @@ extern "C" int bathgpu_orf_forward_matrices(bathgpu_ctx *ctx, const bathgpu_enve
     CUDA_TRY(ctx, cudaMemcpyAsync(xrows + (size_t)row0 * 6, ctx->dfx.p, rows * 24, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(fwdsc + e0, ctx->dfw.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(status + e0, ctx->dstat.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, wait_stream(ctx));
     float ms = 0.f;
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms += ms; ctx->last_launches += 2;
@@ -2078,7 +2111,7 @@ extern "C" int bathgpu_bias_forward(bathgpu_ctx *ctx, int kind, const bathgpu_bi
   CUDA_TRY(ctx, cudaGetLastError());
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->b_out.p, (size_t)n * per * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, wait_stream(ctx));
   CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
   ctx->last_launches = 1;
   return BATHGPU_OK;
@@ -2149,7 +2182,7 @@ extern "C" int bathgpu_orfs_msv_screen(bathgpu_ctx *ctx, const bathgpu_block *bl
   CUDA_TRY(ctx, cudaEventRecord(ctx->o_ev[2], ctx->stream));
   std::vector<int> cnt((size_t)ntiles);
   CUDA_TRY(ctx, cudaMemcpyAsync(cnt.data(), ctx->o_cnt.p, (size_t)ntiles * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, wait_stream(ctx));
   std::vector<long long> base((size_t)ntiles + 1, 0), bfirst((size_t)nblocks, 0);
   for (int t = 0; t < ntiles; ++t) base[t + 1] = base[t] + cnt[t];
   for (int b = 0; b < nblocks; ++b) {
@@ -2188,7 +2221,7 @@ extern "C" int bathgpu_orfs_msv_screen(bathgpu_ctx *ctx, const bathgpu_block *bl
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   unsigned long long hc[3] = { 0, 0, 0 };
   CUDA_TRY(ctx, cudaMemcpyAsync(hc, ctx->o_counters.p, 24, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, wait_stream(ctx));
   CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
   CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->o_ms[0], ctx->o_ev[0], ctx->o_ev[1]));
   CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->o_ms[1], ctx->o_ev[1], ctx->o_ev[2]));
@@ -2219,7 +2252,7 @@ extern "C" int bathgpu_orfs_fetch(bathgpu_ctx *ctx, bathgpu_orf_hit *hits, uint8
   CUDA_TRY(ctx, enter(ctx));
   CUDA_TRY(ctx, cudaMemcpyAsync(hits, ctx->o_hits.p, (size_t)ctx->o_nhits * sizeof(OrfHit), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(residues, ctx->S().residues.p, (size_t)ctx->o_nres, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, wait_stream(ctx));
   std::sort(hits, hits + ctx->o_nhits, [](const bathgpu_orf_hit &x, const bathgpu_orf_hit &y) {
     return x.block != y.block ? x.block < y.block : x.index < y.index; });
   return BATHGPU_OK;
