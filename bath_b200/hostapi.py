@@ -477,33 +477,49 @@ def cluster_region_segments(segments, nsamples=200, protein=False):
 
 
 def compare_tables(a, b):
-    """--tblout tables field by field: names, model and target coordinates, frameshift / stop counts and the CIGAR string must be equal;
-    the four printed floats (E-value, score, bias, percent identity) may differ by one unit of their last printed digit -- the device
-    and the CPU oracle sum the same FP32 terms in different orders, and a value on a rounding boundary of %.1f prints either way.
-    Returns (byte_identical, equivalent, lines_with_a_differing_digit)."""
+    """--tblout tables hit by hit.  Hits are matched by target, query, model and target coordinates, frameshift / stop counts and
+    CIGAR string: the two tables must hold the same hits.  The four printed floats of a hit (E-value, score, bias, percent identity)
+    may differ by one unit of their last printed digit -- the device and the CPU oracle sum the same FP32 terms in different orders,
+    and a value on a rounding boundary of %.1f prints either way -- and, the table being sorted by E-value, hits whose E-values agree
+    to that precision may change places (the E-values read down the two tables must agree rank by rank).
+    Returns (byte_identical, equivalent, lines_that_differ)."""
     if a == b:
         return True, True, 0
-    la, lb = a.splitlines(), b.splitlines()
+    la = [x for x in a.splitlines() if x and not x.startswith("#")]
+    lb = [x for x in b.splitlines() if x and not x.startswith("#")]
     if len(la) != len(lb):
         return False, False, -1
+
+    def close(i, u, v):
+        fu, fv = float(u), float(v)
+        if i == 11:
+            return abs(fu - fv) <= 0.11 * max(abs(fu), abs(fv))            # two significant digits printed
+        return abs(fu - fv) <= (0.0101 if i == 14 else 0.101)
+
+    def parse(lines):
+        out = {}
+        for x in lines:
+            f = x.split()
+            if len(f) < 18:
+                return None
+            key = tuple(f[1:11]) + tuple(f[15:])
+            if key in out:
+                return None
+            out[key] = f
+        return out
+
+    da, db = parse(la), parse(lb)
+    if da is None or db is None or da.keys() != db.keys():
+        return False, False, -1
+    for key, fa in da.items():
+        fb = db[key]
+        if not all(close(i, fa[i], fb[i]) for i in (11, 12, 13, 14)):
+            return False, False, -1
     ndiff = 0
     for x, y in zip(la, lb):
-        if x == y:
-            continue
         fx, fy = x.split(), y.split()
-        if len(fx) != len(fy) or len(fx) < 18:
-            return False, False, -1
-        for i, (u, v) in enumerate(zip(fx, fy)):
-            if u == v:
-                continue
-            if i not in (11, 12, 13, 14):
+        if fx[1:] != fy[1:]:
+            ndiff += 1
+            if not close(11, fx[11], fy[11]):                                 # another hit at this rank: only among equal E-values
                 return False, False, -1
-            fu, fv = float(u), float(v)
-            if i == 11:
-                ok = abs(fu - fv) <= 0.11 * max(abs(fu), abs(fv))           # two significant digits printed
-            else:
-                ok = abs(fu - fv) <= (0.0101 if i == 14 else 0.101)
-            if not ok:
-                return False, False, -1
-        ndiff += 1
     return False, True, ndiff
