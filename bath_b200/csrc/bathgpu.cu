@@ -7,6 +7,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <math.h>
+#include <thread>
 #include <vector>
 #include <string>
 #include <algorithm>
@@ -99,6 +100,7 @@ struct bathgpu_ctx {
   int           device = 0;
   cudaDeviceProp prop{};
   cudaStream_t  stream = nullptr, copy_stream = nullptr, stream2 = nullptr;
+  cudaStream_t  bulk_stream = nullptr;                // low priority: the throughput-bound translation + MSV pass (see BulkScope)
   cudaEvent_t   chunk_ev[16] = {};
   cudaEvent_t   ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t   sync_ev = nullptr;                    // blocking-sync event: a host thread waiting for its stream sleeps instead of spinning
@@ -174,17 +176,33 @@ static int reserve_matrices(bathgpu_ctx *ctx, size_t pp_bytes, size_t oa_bytes)
 }
 
 // A stage call ends by waiting for its stream.  cudaStreamSynchronize spins on a core, and a search drives 12-24 contexts, one host
-// thread each, beside a host pool as wide as the machine; BATHGPU_BLOCKING_SYNC=1 makes the waiting threads sleep on a blocking-sync
-// event instead.  Measured on a 16-core B200 box (3 profiles x 1 Gbp): 4.19-4.38 Gbp/s sleeping against 4.42-4.66 spinning, and the
-// one-call Forward path from host buffers 15.8 against 15.2 ms -- the wake-up costs more than the cores it frees, so spinning stays
-// the default.
-static const bool g_blocking_sync = [] { const char *e = getenv("BATHGPU_BLOCKING_SYNC"); return e && atoi(e) != 0; }();
+// thread each, beside a host pool as wide as the machine.  BATHGPU_BLOCKING_SYNC=1 makes the waiting threads sleep on a blocking-sync
+// event, =2 polls and yields the core in between.  Measured on a 16-core B200 box (3 profiles x 1 Gbp): sleeping 4.19-4.38 Gbp/s against
+// 4.42-4.66 spinning, and the one-call Forward path from host buffers 15.8 against 15.2 ms; poll + yield equal to spinning within the
+// run-to-run spread (4.45-4.62).  With sleeping waits the search uses 5.1 core-seconds in 0.66 s: the host is half idle, so the waits are
+// not what limits it, and spinning stays the default.
+static const int g_sync_mode = [] { const char *e = getenv("BATHGPU_BLOCKING_SYNC"); return e ? atoi(e) : 0; }();   // 0 spin, 1 sleep, 2 poll + yield
 static inline cudaError_t wait_stream(bathgpu_ctx *ctx)
 {
-  if (!g_blocking_sync || !ctx->sync_ev) return cudaStreamSynchronize(ctx->stream);
+  if (g_sync_mode == 2) {                                    // give the core to a runnable pool worker between polls
+    for (;;) {
+      const cudaError_t q = cudaStreamQuery(ctx->stream);
+      if (q != cudaErrorNotReady) return q;
+      std::this_thread::yield();
+    }
+  }
+  if (g_sync_mode != 1 || !ctx->sync_ev) return cudaStreamSynchronize(ctx->stream);
   const cudaError_t e = cudaEventRecord(ctx->sync_ev, ctx->stream);
   return e != cudaSuccess ? e : cudaEventSynchronize(ctx->sync_ev);
 }
+
+// For the length of a call, the context's work goes to its low-priority stream (every entry point starts and ends with the
+// context's streams idle, so nothing has to be ordered between the two).
+struct BulkScope {
+  bathgpu_ctx *ctx; cudaStream_t saved;
+  explicit BulkScope(bathgpu_ctx *c) : ctx(c), saved(c->stream) { if (c->bulk_stream) c->stream = c->bulk_stream; }
+  ~BulkScope() { ctx->stream = saved; }
+};
 
 // ---------------------------------------------------------------------------------------------
 extern "C" int bathgpu_create(int device, bathgpu_ctx **ret_ctx)
@@ -200,7 +218,18 @@ extern "C" int bathgpu_create(int device, bathgpu_ctx **ret_ctx)
     cudaGetLastError(); delete ctx; return BATHGPU_ENODEVICE;
   }
   if (ctx->prop.major < 10) { delete ctx; return BATHGPU_ENODEVICE; }   // sm_100a code only
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+  // Several contexts share a device (a search drives 12-24).  Most stage calls are chains of small latency-bound kernels; the
+  // translation + MSV pass fills the device for milliseconds.  The context's own stream gets the highest priority and that pass a
+  // lowest-priority one, so another context's small kernels are placed as blocks drain instead of queueing behind the pass
+  // (BATHGPU_PRIORITIES=0: one priority).  Measured: no difference beyond the run-to-run spread on one B200 (4.37-4.59 against
+  // 4.08-4.69 Gbp/s); kept because it costs nothing and bounds the worst case.
+  int prio_lo = 0, prio_hi = 0;
+  {
+    const char *e = getenv("BATHGPU_PRIORITIES");
+    if (!(e && atoi(e) == 0) && cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) { cudaGetLastError(); prio_lo = prio_hi = 0; }
+  }
+  if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+      (prio_lo != prio_hi && cudaStreamCreateWithPriority(&ctx->bulk_stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess) ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) {
     cudaGetLastError(); delete ctx; return BATHGPU_ECUDA;
@@ -227,6 +256,7 @@ extern "C" void bathgpu_destroy(bathgpu_ctx *ctx)
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
   for (auto &e : ctx->o_ev) if (e) cudaEventDestroy(e);
+  if (ctx->bulk_stream) cudaStreamDestroy(ctx->bulk_stream);
   cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); cudaStreamDestroy(ctx->stream2); for (auto &e : ctx->chunk_ev) if (e) cudaEventDestroy(e); }
   delete ctx;
@@ -2128,6 +2158,7 @@ extern "C" int bathgpu_orfs_msv_screen(bathgpu_ctx *ctx, const bathgpu_block *bl
   if (!ctx->flt_loaded)      return fail(ctx, BATHGPU_EINVAL, "filter profile not loaded");
   TargetSlot &S = ctx->S();
   if (S.block_n == 0)        return fail(ctx, BATHGPU_EINVAL, "no block uploaded");
+  BulkScope bulk(ctx);
   static_assert(sizeof(BlockDesc) == sizeof(bathgpu_block), "block layouts must agree");
   static_assert(sizeof(OrfHit) == sizeof(bathgpu_orf_hit), "hit layouts must agree");
   std::vector<int> tile_block, tile_p0;

@@ -1210,6 +1210,8 @@ int run_batch(bathhost_search *s)
   for (size_t c = 0; c < chunks.size(); ++c) for (int b = chunks[c].blk0; b < chunks[c].blk1; ++b) chunk_of_block[(size_t) b] = (int) c;
 
   // ---- stages 1-3 per unit, device contexts side by side: upload (top) / reverse complement on the device (bottom), ORFs, filters
+  // (Letting searches that run at the same time take this phase one after the other -- it holds the throughput-bound translation + MSV
+  // pass -- was measured and lost 5-9 % on one B200: 4.07-4.39 against 4.46-4.54 Gbp/s; a search's filter phase does not fill the device.)
   int rc = for_each_backend(s, [&](int be) -> int {
     const bathhost_backend &BE = s->bes[(size_t) be];
     HostBuf stage;                                             // concatenation buffer for chunks of several sequences
