@@ -500,7 +500,7 @@ def compare_tables(a, b):
         out = {}
         for x in lines:
             f = x.split()
-            if len(f) < 18:
+            if len(f) < 16:                                                    # 18 columns with --fs (shifts, stops), 16 without
                 return None
             key = tuple(f[1:11]) + tuple(f[15:])
             if key in out:

@@ -299,12 +299,12 @@ def compare_tables(a, b):
     return hostapi.compare_tables(a, b)
 
 
-def run_search(models, contigs, gpu_ctxs=None, backends=None):
+def run_search(models, contigs, gpu_ctxs=None, backends=None, **options):
     """every profile against the whole target, one profile after the other: (seconds per profile, tables, stats, hit lists)"""
     from bath_b200 import hostapi
     secs, tables, stats, hits = [], [], [], []
     for model in models:
-        search = hostapi.Search(model, gpu_ctx=gpu_ctxs, backend=backends)
+        search = hostapi.Search(model, gpu_ctx=gpu_ctxs, backend=backends, **options)
         t0 = time.perf_counter()
         for name, dsq in contigs:
             search.queue_sequence(name, dsq)

@@ -9,15 +9,19 @@ from bath_b200 import capi
 from oracle import pyoracle as po
 
 mbp = float(sys.argv[1]) if len(sys.argv) > 1 else 100.0
+options = {}
+for a in sys.argv[2:]:                                  # e.g. std_only=1 block_length=100000
+    k, v = a.split("=")
+    options[k] = int(v)
 models, contigs, plants = bench.search_target(mbp)
 ctxs = [capi.Context(0) for _ in range(8)]
 t0 = time.perf_counter()
-gsecs, gtables, gstats, ghits = bench.run_search(models, contigs, gpu_ctxs=ctxs)
+gsecs, gtables, gstats, ghits = bench.run_search(models, contigs, gpu_ctxs=ctxs, **options)
 gdt = time.perf_counter() - t0
 po.lib(native=True)
 be, keep = po.cpu_backend(os.cpu_count() or 1)
 t0 = time.perf_counter()
-csecs, ctables, cstats, chits = bench.run_search(models, contigs, backends=be)
+csecs, ctables, cstats, chits = bench.run_search(models, contigs, backends=be, **options)
 cdt = time.perf_counter() - t0
 same = [g == c for g, c in zip(gtables, ctables)]
 cmp = [bench.compare_tables(g, c) for g, c in zip(gtables, ctables)]
@@ -41,7 +45,7 @@ for k, (g, c) in enumerate(zip(gtables, ctables)):
         open(f"gpurun_out/parity_gpu_{k}.tbl", "w").write(g)
         open(f"gpurun_out/parity_cpu_{k}.tbl", "w").write(c)
 keys = ("pos_past_msv", "pos_past_bias", "pos_past_vit", "pos_past_fwd", "n_orfs", "n_windows", "n_std_windows", "n_regions", "n_multidomain_regions", "n_envelopes", "n_hits_reported")
-print(json.dumps({"target_mbp": sum(len(d) - 2 for _, d in contigs) / 1e6, "contigs": len(contigs), "profiles": [m.M for m in models],
+print(json.dumps({"options": options, "target_mbp": sum(len(d) - 2 for _, d in contigs) / 1e6, "contigs": len(contigs), "profiles": [m.M for m in models],
                   "hits_gpu": [len(h) for h in ghits], "hits_cpu": [len(h) for h in chits], "tables_identical": same, "tables_equivalent": [c[1] for c in cmp],
                   "lines_differing_in_a_last_printed_digit": [c[2] for c in cmp],
                   "same_hit_set": same_set, "hits_at_another_rank": swapped, "max_abs_diff_score_bits": dsc, "max_abs_diff_bias_bits": dbias, "max_abs_diff_lnP": dlnp,
