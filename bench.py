@@ -415,9 +415,10 @@ def search_leg(devices, per_gpu, mbp, cpu_mbp, with_cpu):
         cmp = [compare_tables(g, c) for g, c in zip(gtables, ctables)]
         out["checks"]["hits_identical_to_cpu_prefix"] = bool(all(c[1] for c in cmp))
         out["checks"]["cpu_prefix_tables_byte_identical"] = [bool(c[0]) for c in cmp]
-        out["checks"]["cpu_prefix_lines_differing_in_a_last_printed_digit"] = [int(c[2]) for c in cmp]
-        out["checks"]["cpu_prefix_rule"] = ("hits_identical_to_cpu_prefix: same hits in the same order with equal names, coordinates, frameshift/stop "
-                                            "counts and CIGAR strings; E-value, score, bias and identity equal to within one unit of the last printed digit")
+        out["checks"]["cpu_prefix_lines_that_differ"] = [int(c[2]) for c in cmp]
+        out["checks"]["cpu_prefix_rule"] = ("hits_identical_to_cpu_prefix (hostapi.compare_tables): the same hit set -- hits matched by target, query, "
+                                            "model and target coordinates, frameshift/stop counts and CIGAR string; E-value, score, bias and identity of a "
+                                            "hit equal to within one unit of the last printed digit; rank changes only among hits whose printed E-values agree")
     for cs in sets:
         for c in cs:
             c.close()
