@@ -952,11 +952,29 @@ static int fs_fwd_block_impl(bathgpu_ctx *ctx, const uint8_t *dsq, const uint8_t
       ctx->status.reserve((size_t)nwin * 4) != BATHGPU_OK || ctx->counter.reserve(64) != BATHGPU_OK)
     return fail(ctx, BATHGPU_EMEM, "device allocation failed");
   S.block_n = n; S.nres = 0; S.bytes_valid = (packed == nullptr);
+  // windows in order of their last nucleotide ; callers that tile a block are already in order
+  static_assert(sizeof(WindowDesc) == sizeof(bathgpu_window), "descriptor layouts must agree");
+  bool in_order = true;
+  for (int w = 1; w < nwin && in_order; ++w) in_order = wins[w - 1].start + wins[w - 1].L <= wins[w].start + wins[w].L;
+  std::vector<int> order;
+  std::vector<WindowDesc> sorted;
+  std::vector<float> sc;
+  std::vector<int> st;
+  if (!in_order) {
+    order.resize((size_t)nwin); sorted.resize((size_t)nwin); sc.resize((size_t)nwin); st.resize((size_t)nwin);
+    for (int w = 0; w < nwin; ++w) order[w] = w;
+    std::sort(order.begin(), order.end(), [&](int x, int y) { return wins[x].start + wins[x].L < wins[y].start + wins[y].L; });
+    for (int w = 0; w < nwin; ++w) memcpy(&sorted[w], &wins[order[w]], sizeof(WindowDesc));
+  }
+  const WindowDesc *hw = in_order ? reinterpret_cast<const WindowDesc *>(wins) : sorted.data();
   // Chunks grow fourfold: scoring a chunk takes several times longer than moving it, so every later chunk arrives while the
   // one before it is being scored, and the first one is small enough that the device starts almost at once.
   long long cuts[8]; int K = 0;
   {
     long long first = n / 85, p = 0;
+    // the first launch should fill the device: one resident wave of windows (16 warps per SM) has to end inside the first chunk
+    const int wave = ctx->prop.multiProcessorCount * 16;
+    if (nwin > wave) first = std::min<long long>(std::max<long long>(first, hw[wave].start + hw[wave].L), std::max<long long>(first, n / 8));
     if (n < (4 << 20)) first = n;
     for (long long sz = std::max<long long>(first, 1 << 20); p < n && K < 7; sz *= 4) { p = std::min<long long>(n, (p + sz + 7) & ~7LL); cuts[K++] = p; }
     cuts[K - 1] = n;
@@ -983,21 +1001,6 @@ static int fs_fwd_block_impl(bathgpu_ctx *ctx, const uint8_t *dsq, const uint8_t
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaEventRecord(pack_ev[c], ctx->copy_stream));
   }
-  // windows in order of their last nucleotide (while the first chunks are in flight); callers that tile a block are already in order
-  static_assert(sizeof(WindowDesc) == sizeof(bathgpu_window), "descriptor layouts must agree");
-  bool in_order = true;
-  for (int w = 1; w < nwin && in_order; ++w) in_order = wins[w - 1].start + wins[w - 1].L <= wins[w].start + wins[w].L;
-  std::vector<int> order;
-  std::vector<WindowDesc> sorted;
-  std::vector<float> sc;
-  std::vector<int> st;
-  if (!in_order) {
-    order.resize((size_t)nwin); sorted.resize((size_t)nwin); sc.resize((size_t)nwin); st.resize((size_t)nwin);
-    for (int w = 0; w < nwin; ++w) order[w] = w;
-    std::sort(order.begin(), order.end(), [&](int x, int y) { return wins[x].start + wins[x].L < wins[y].start + wins[y].L; });
-    for (int w = 0; w < nwin; ++w) memcpy(&sorted[w], &wins[order[w]], sizeof(WindowDesc));
-  }
-  const WindowDesc *hw = in_order ? reinterpret_cast<const WindowDesc *>(wins) : sorted.data();
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->wins.p, hw, (size_t)nwin * sizeof(WindowDesc), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, 64, ctx->stream));
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));

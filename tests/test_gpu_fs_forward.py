@@ -101,11 +101,11 @@ def test_fused_upload_and_forward_matches_two_calls(oracle, gpu_ctx):
     from bath_b200 import capi
     model = oracle.Model(common.golden("AMP_N.bhmm"))
     rng = np.random.default_rng(17)
-    n = 9_000_000                                    # three chunks: cuts at 1 Mi and 5 Mi nucleotides
+    n = 9_000_000                                    # three chunks: cuts at n/8 = 1 125 000 and 5 625 000 nucleotides
     dsq = common.random_dna(rng, n, p_degenerate=0.001)
     gpu_ctx.load_fs_profile(3, model.rfv(3), model.tfv(3))
     starts = np.sort(rng.integers(1, n - 1500, 4000))
-    starts[:8] = [1, 2, 1_048_000, 1_048_570, 1_048_576, 5_242_880 - 700, n - 1299, n - 1200]      # around the chunk boundaries and both ends
+    starts[:10] = [1, 2, 1_124_500, 1_124_990, 1_125_000, 5_625_000 - 700, n - 1299, n - 1200, 1_048_570, 5_242_880 - 700]      # around the chunk boundaries and both ends
     lens = rng.integers(60, 1300, len(starts)); lens[7] = 1200; lens[6] = 1300
     perm = rng.permutation(len(starts))
     w = capi.Context.make_windows(starts[perm], lens[perm])

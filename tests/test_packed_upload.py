@@ -42,7 +42,7 @@ def test_packed_block_scores_equal_byte_block(oracle, gpu_ctx, n):
         lens = rng.integers(60, 1300, len(starts))
         starts[:4] = [1, 2, n - 1299, n - 1199]; lens[:4] = [900, 61, 1300, 1200]
         if n > 6_000_000:
-            starts[4:8] = [1_048_000, 1_048_570, 1_048_576, 5_242_880 - 700]
+            starts[4:10] = [1_124_500, 1_124_990, 1_125_000, 5_625_000 - 700, 1_048_570, 5_242_880 - 700]
     else:
         starts, lens = np.array([1, 2, 5]), np.array([64, 63, 60])
     perm = rng.permutation(len(starts))
