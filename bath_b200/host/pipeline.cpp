@@ -280,7 +280,6 @@ struct SeqRef {                                  // one queued target sequence (
 struct bathhost_search {
   const bathhost_model *model;
   std::vector<bathhost_backend> bes;              // device contexts the stages are dealt to (one or more per GPU)
-  HostBuf               mxbuf[2];                 // Forward matrices and X rows of multi-domain regions
   std::vector<std::unique_ptr<HostBuf[]>> be_xbuf;   // per device context: X rows of the Forward / Backward parsers (page-locked, reused from unit to unit)
   Options               opt;
   Background            bg;
@@ -1638,57 +1637,82 @@ int run_batch(bathhost_search *s)
       if (todo.empty()) break;
       if (walk_sequential) todo.resize(1);                    // test hook: one window per round from its true input = the plain sequential walk
       if (round > (int) worder.size() + 2) return fail(s, BATHHOST_EINVAL, "the region walk does not settle");
+      // Inside a piece of consecutive windows the chain is followed for real: a window starts from what its predecessor in the piece
+      // has just left, so only the first window of a piece runs on a guess (the walk is bound by reading the decoding products,
+      // 72 bytes per window row: walking nearly every window twice cost 10-34 ms per Gbp and profile).
       parallel_chunks(todo.size(), 4, [&](size_t ta, size_t tb) {
         for (size_t q = ta; q < tb; ++q) {
           const WalkItem &it = worder[todo[q]];
           WalkMemo &wm = memo[(size_t) it.u][it.z];
+          if (q > ta && todo[q] == todo[q - 1] + 1) {
+            const WalkItem &pit = worder[todo[q - 1]];
+            const WalkMemo &pm = memo[(size_t) pit.u][pit.z];
+            wm.nj_in = pm.nj_out; wm.L_in = pm.L_out;
+          }
           walk_window(it.u, it.z, wm.nj_in, wm.L_in, wm);
         }
       });
     }
+    trace.mark("  walk: rounds");
     std::vector<RegionKey> pending;
     for (const WalkItem &it : worder) { const WalkMemo &wm = memo[(size_t) it.u][it.z]; pending.insert(pending.end(), wm.pend.begin(), wm.pend.end()); }
     for (const WalkItem &it : worder) { WalkMemo &wm = memo[(size_t) it.u][it.z]; if (!wm.pend.empty()) wm.valid = false; }   // walked again once resolved
     if (pending.empty()) break;
     if (walk_pass > 64) return fail(s, BATHHOST_EINVAL, "multi-domain region resolution does not settle");
-    // ---- Forward matrices of the unresolved regions (multihit, target length saveL: :409-412), one device call per strand
+    // ---- Forward matrices of the unresolved regions (multihit, target length saveL: :409-412): one device call per unit that has any,
+    // the device contexts side by side, then every region of every unit sampled and clustered on all cores at once (regions of this
+    // kind are rare -- 10-20 per Gbp and profile -- but each costs a device call and 200 sampled traces, and they came one unit after
+    // the other: 17-36 ms of a 110-150 ms profile on eight GPUs)
     const float xfE5m[2] = { 0.5f, 0.5f };
     float mh_pmove, mh_ploop;
     bathhost_length_model(saveL, 1.0f, &mh_pmove, &mh_ploop);
-    for (size_t sidx = 0; sidx < units.size(); ++sidx) {                 // sidx: the unit (regions of this kind are rare: one device call per unit that has any)
-      if (!units[sidx]) continue;
-      Unit &S = *units[sidx];
-      const bathhost_backend &BE = s->bes[(size_t) S.be];
-      std::vector<bathgpu_envelope> regs;
-      std::vector<RegionKey> keys;
-      std::vector<int64_t> off(1, 0);
-      for (const RegionKey &k : pending) if (k.u == (int) sidx) {
-        bathgpu_envelope g;
-        g.start = S.gw[k.w].start + k.i - 1; g.L = k.j - k.i + 1; g.pmove = mh_pmove; g.ploop = mh_ploop;
-        regs.push_back(g); keys.push_back(k); off.push_back(off.back() + g.L + 1);
-      }
-      if (regs.empty()) continue;
-      float *mxbuf = s->mxbuf[0].get(BE, (size_t) off.back() * (M + 1) * 8), *xrbuf = s->mxbuf[1].get(BE, (size_t) off.back() * 6);
-      if (!mxbuf || !xrbuf) return fail(s, BATHHOST_EMEM, "host allocation failed");
-      std::vector<float> fsc(regs.size());
-      std::vector<int32_t> fst(regs.size());
-      BE_TRY(s, BE.select_slot(BE.ctx, S.slot), "bathgpu_select_slot");
-      if (!BE.fs_forward_matrices) return fail(s, BATHHOST_EINVAL, "the device library has no bathgpu_fs_forward_matrices");
-      BE_TRY(s, BE.fs_forward_matrices(BE.ctx, regs.data(), (int) regs.size(), xfE5m, mxbuf, xrbuf, off.back(), fsc.data(), fst.data()),
-             "bathgpu_fs_forward_matrices");
-      std::vector<std::vector<std::pair<int, int>>> found(regs.size());
-      const SpecialOdds X{ mh_pmove, mh_ploop, xfE5m[0], xfE5m[1] };
-      parallel_chunks(regs.size(), 1, [&](size_t ra, size_t rb) {
-        for (size_t r = ra; r < rb; ++r) {
-          if (fst[r] != 0) continue;                         // Forward out of range: no clusters (:412-413)
-          const ForwardMatrix F{ mxbuf + (size_t) off[r] * (M + 1) * 8, xrbuf + (size_t) off[r] * 6, M, regs[r].L };
-          std::vector<Segment> sp;
-          if (!sample_region_segments(F, m->om5.tfv.data(), X, kStotraceSeed, kStotraceSamples, keys[r].i, sp)) continue;
-          for (const Segment &g : cluster_region_segments(sp, kStotraceSamples)) found[r].push_back({ g.i, g.j });
-        }
-      });
-      for (size_t r = 0; r < regs.size(); ++r) resolved[keys[r]] = std::move(found[r]);
+    struct UnitRegions { std::vector<bathgpu_envelope> regs; std::vector<RegionKey> keys; std::vector<int64_t> off; std::vector<float> fsc;
+                         std::vector<int32_t> fst; HostBuf mx, xr; float *mxbuf = nullptr, *xrbuf = nullptr; };
+    std::vector<UnitRegions> ur(units.size());
+    for (const RegionKey &k : pending) {
+      Unit &S = *units[(size_t) k.u];
+      UnitRegions &R = ur[(size_t) k.u];
+      if (R.off.empty()) R.off.push_back(0);
+      bathgpu_envelope g;
+      g.start = S.gw[k.w].start + k.i - 1; g.L = k.j - k.i + 1; g.pmove = mh_pmove; g.ploop = mh_ploop;
+      R.regs.push_back(g); R.keys.push_back(k); R.off.push_back(R.off.back() + g.L + 1);
     }
+    rc = for_each_backend(s, [&](int be) -> int {
+      const bathhost_backend &BE = s->bes[(size_t) be];
+      for (size_t sidx = 0; sidx < units.size(); ++sidx) {
+        if (!units[sidx] || units[sidx]->be != be || ur[sidx].regs.empty()) continue;
+        Unit &S = *units[sidx];
+        UnitRegions &R = ur[sidx];
+        R.mxbuf = R.mx.get(BE, (size_t) R.off.back() * (M + 1) * 8); R.xrbuf = R.xr.get(BE, (size_t) R.off.back() * 6);
+        if (!R.mxbuf || !R.xrbuf) return fail(s, BATHHOST_EMEM, "host allocation failed");
+        R.fsc.resize(R.regs.size()); R.fst.resize(R.regs.size());
+        BE_TRY(s, BE.select_slot(BE.ctx, S.slot), "bathgpu_select_slot");
+        if (!BE.fs_forward_matrices) return fail(s, BATHHOST_EINVAL, "the device library has no bathgpu_fs_forward_matrices");
+        BE_TRY(s, BE.fs_forward_matrices(BE.ctx, R.regs.data(), (int) R.regs.size(), xfE5m, R.mxbuf, R.xrbuf, R.off.back(), R.fsc.data(), R.fst.data()),
+               "bathgpu_fs_forward_matrices");
+      }
+      return 0;
+    });
+    if (rc != 0) return rc;
+    trace.mark("  walk: region matrices (devices)");
+    struct RegionRef { size_t u, r; };
+    std::vector<RegionRef> all;
+    for (size_t u = 0; u < ur.size(); ++u) for (size_t r = 0; r < ur[u].regs.size(); ++r) all.push_back(RegionRef{ u, r });
+    std::vector<std::vector<std::pair<int, int>>> found(all.size());
+    const SpecialOdds X{ mh_pmove, mh_ploop, xfE5m[0], xfE5m[1] };
+    parallel_chunks(all.size(), 1, [&](size_t ra, size_t rb) {
+      for (size_t q = ra; q < rb; ++q) {
+        const UnitRegions &R = ur[all[q].u];
+        const size_t r = all[q].r;
+        if (R.fst[r] != 0) continue;                         // Forward out of range: no clusters (:412-413)
+        const ForwardMatrix F{ R.mxbuf + (size_t) R.off[r] * (M + 1) * 8, R.xrbuf + (size_t) R.off[r] * 6, M, R.regs[r].L };
+        std::vector<Segment> sp;
+        if (!sample_region_segments(F, m->om5.tfv.data(), X, kStotraceSeed, kStotraceSamples, R.keys[r].i, sp)) continue;
+        for (const Segment &g : cluster_region_segments(sp, kStotraceSamples)) found[q].push_back({ g.i, g.j });
+      }
+    });
+    for (size_t q = 0; q < all.size(); ++q) resolved[ur[all[q].u].keys[all[q].r]] = std::move(found[q]);
+    trace.mark("  walk: sampling + clustering");
   }
   s->st.n_regions = walk_regions0; s->st.n_multidomain_regions = walk_multi0;
   for (auto &U : units) { U->ge.clear(); U->envs.clear(); }
