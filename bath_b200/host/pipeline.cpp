@@ -2172,6 +2172,9 @@ int run_batch(bathhost_search *s)
   // ---- hits in the reference's order: block by block, top strand then bottom strand; counters summed over units
   {
     std::vector<size_t> pf(units.size(), 0), ps(units.size(), 0);
+    size_t more = 0;
+    for (auto &U : units) more += U->hits_fs.size() + U->hits_std.size();
+    s->hits.reserve(s->hits.size() + more);
     for (size_t b = 0; b < nb; ++b)
       for (int sidx : active) {
         const size_t u = 2 * (size_t) chunk_of_block[b] + (size_t) sidx;
@@ -2294,9 +2297,15 @@ extern "C" int bathhost_search_finish(bathhost_search *s)
     h.sortkey = -1.0 * h.pub.lnP;
     h.pub.evalue = exp(h.pub.lnP);
   }
+  // The two sorts run on an index vector and the hits are moved once at the end: a Hit carries a kilobyte of fixed-size fields
+  // (name, CIGAR), and sorting the records themselves cost 15-20 ms per profile and Gbp.
+  std::vector<uint32_t> ord(s->hits.size());
+  for (size_t z = 0; z < ord.size(); ++z) ord[z] = (uint32_t) z;
+  const std::vector<Hit> &HV = s->hits;
   // p7_tophits_SortBySeqidxAndAlipos (hit_sorter_by_seqidx_aliposition, src/p7_tophits.c:286-306): seqidx, plus strand first, then
   // the smaller coordinate ascending and the larger one descending -- start and end are swapped on the minus strand first
-  std::stable_sort(s->hits.begin(), s->hits.end(), [](const Hit &a, const Hit &b) {
+  std::stable_sort(ord.begin(), ord.end(), [&HV](uint32_t x, uint32_t y) {
+    const Hit &a = HV[x], &b = HV[y];
     if (a.pub.seqidx != b.pub.seqidx) return a.pub.seqidx < b.pub.seqidx;
     const int da = a.pub.ali_from < a.pub.ali_to ? 1 : -1, db = b.pub.ali_from < b.pub.ali_to ? 1 : -1;
     if (da != db) return da > db;
@@ -2305,10 +2314,10 @@ extern "C" int bathhost_search_finish(bathhost_search *s)
     if (as != bs) return as < bs;
     return ae > be;
   });
-  if (s->hits.size() > 1) {                                 // p7_tophits_RemoveDuplicates
+  if (ord.size() > 1) {                                     // p7_tophits_RemoveDuplicates
     size_t j = 0;
-    for (size_t i = 1; i < s->hits.size(); ++i) {
-      Hit &hj = s->hits[j], &hi = s->hits[i];
+    for (size_t i = 1; i < ord.size(); ++i) {
+      Hit &hj = s->hits[ord[j]], &hi = s->hits[ord[i]];
       long long s_j = hj.pub.ali_from, e_j = hj.pub.ali_to, s_i = hi.pub.ali_from, e_i = hi.pub.ali_to;
       const int dir_j = s_j < e_j ? 1 : -1, dir_i = s_i < e_i ? 1 : -1;
       if (dir_j == -1) std::swap(s_j, e_j);
@@ -2316,17 +2325,18 @@ extern "C" int bathhost_search_finish(bathhost_search *s)
       const long long len_j = e_j - s_j + 1, len_i = e_i - s_i + 1;
       const long long is = std::max(s_i, s_j), ie = std::min(e_i, e_j), ilen = ie - is + 1;
       const int hs = std::max(hi.pub.hmm_from, hj.pub.hmm_from), he = std::min(hi.pub.hmm_to, hj.pub.hmm_to), hlen = he - hs + 1;
-      const Hit &hp = s->hits[i - 1];
+      const Hit &hp = s->hits[ord[i - 1]];
       if (hi.pub.seqidx == hp.pub.seqidx && dir_i == dir_j && hlen > 0 &&
           ((s_i >= s_j - 3 && s_i <= s_j + 3) || (e_i >= e_j - 3 && e_i <= e_j + 3) || (ilen >= len_i * 0.95) || (ilen >= len_j * 0.95))) {
         const size_t remove = hi.pub.lnP < hj.pub.lnP ? j : i;
-        s->hits[remove].duplicate = true;
+        s->hits[ord[remove]].duplicate = true;
         j = (remove == j ? i : j);
       } else j = i;
     }
   }
   // p7_tophits_SortBySortkey: sortkey descending, then name, strand, position
-  std::stable_sort(s->hits.begin(), s->hits.end(), [](const Hit &a, const Hit &b) {
+  std::stable_sort(ord.begin(), ord.end(), [&HV](uint32_t x, uint32_t y) {
+    const Hit &a = HV[x], &b = HV[y];
     if (a.sortkey != b.sortkey) return a.sortkey > b.sortkey;
     const int c = strcmp(a.pub.name, b.pub.name);
     if (c != 0) return c < 0;
@@ -2334,6 +2344,12 @@ extern "C" int bathhost_search_finish(bathhost_search *s)
     if (da != db) return da > db;
     return a.pub.ali_from < b.pub.ali_from;
   });
+  {
+    std::vector<Hit> moved;
+    moved.reserve(s->hits.size());
+    for (uint32_t z : ord) moved.push_back(std::move(s->hits[z]));
+    s->hits.swap(moved);
+  }
   s->st.n_hits_reported = 0;
   for (Hit &h : s->hits) {
     h.reported = !h.duplicate && (exp(h.pub.lnP) <= s->opt.E);      // Z forced to 1 for reporting (src/bathsearch.c:920)
