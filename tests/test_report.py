@@ -112,3 +112,27 @@ def test_report_without_hits(oracle):
 def test_report_matches_shipped_outputs_gpu(gpu_ctx):
     from bath_b200 import hostapi
     check_all(hostapi, gpu_ctx=gpu_ctx)
+
+
+def test_compare_tables_rules():
+    """hostapi.compare_tables (used by bench.py and the large-target parity script): the same hit set by key; a printed float may move by
+    one unit of its last digit; hits may change rank only among equal printed E-values; anything else is a difference"""
+    from bath_b200 import hostapi
+    hdr = "# hit ID  target name ...\n#------- ---\n"
+    row = "{:8d} {:<20s} -  q1  PF1  185  {:3d}  183  5950093  {:8d}  {:8d}  {:>8s}  {:5.1f}  {:4.1f} 26.95  {:d}  0 {}\n"
+    a = hdr + row.format(1, "contig9", 17, 3125506, 3125006, "1.1e-23", 87.6, 0.1, 0, "501M") \
+            + row.format(2, "contig3", 2, 100, 640, "3.2e-14", 60.5, 0.6, 2, "265M2B235M2B") \
+            + row.format(3, "contig8", 8, 9000, 8452, "3.2e-14", 60.5, 0.1, 3, "363M1F48M2B4M")
+    assert hostapi.compare_tables(a, a) == (True, True, 0)
+    b = a.replace(" 87.6   0.1", " 87.6   0.2")                          # a bias digit on a rounding boundary
+    assert b != a and hostapi.compare_tables(a, b) == (False, True, 1)
+    l = a.splitlines(True)
+    swapped = "".join(l[:3] + [l[4].replace("       3 ", "       2 ", 1), l[3].replace("       2 ", "       3 ", 1)])
+    assert hostapi.compare_tables(a, swapped) == (False, True, 2)        # equal printed E-values: either order
+    assert hostapi.compare_tables(a, a.replace("3125506", "3125507"))[1] is False        # another coordinate: another hit
+    assert hostapi.compare_tables(a, a.replace("501M", "500M1I"))[1] is False
+    assert hostapi.compare_tables(a, a.replace(" 87.6 ", " 87.9 "))[1] is False          # more than one unit of the last digit
+    assert hostapi.compare_tables(a, a.replace("1.1e-23", "1.4e-23"))[1] is False
+    assert hostapi.compare_tables(a, "".join(l[:4]))[1] is False                          # a hit missing
+    worse = "".join(l[:2] + [l[3].replace("       2 ", "       1 ", 1), l[2].replace("       1 ", "       2 ", 1), l[4]])
+    assert hostapi.compare_tables(a, worse)[1] is False                                   # ranks changed across different E-values
