@@ -28,6 +28,7 @@
 #include <tuple>
 #include <string>
 #include <thread>
+#include <time.h>
 #include <vector>
 #include <memory>
 
@@ -404,13 +405,16 @@ struct StageTimer {              // adds the time since construction / last lap 
 struct PhaseTrace {
   bool on = getenv("BATHHOST_TRACE") != nullptr;
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), t = t0;
+  double cpu0 = cpu_ms();
+  static double cpu_ms() { timespec ts; clock_gettime(CLOCK_PROCESS_CPUTIME_ID, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
   void mark(const char *what)
   {
     if (!on) return;
     const auto n = std::chrono::steady_clock::now();
-    fprintf(stderr, "[bathhost] %-34s %9.2f ms (at %9.2f)\n", what, std::chrono::duration<double, std::milli>(n - t).count(),
-            std::chrono::duration<double, std::milli>(n - t0).count());
-    t = n;
+    const double c = cpu_ms();                              // CPU time of the whole process: meaningful with one search and BATHGPU_BLOCKING_SYNC=1
+    fprintf(stderr, "[bathhost] %-34s %9.2f ms (at %9.2f)  cpu %9.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count(),
+            std::chrono::duration<double, std::milli>(n - t0).count(), c - cpu0);
+    t = n; cpu0 = c;
   }
 };
 
@@ -1277,7 +1281,7 @@ int run_batch(bathhost_search *s)
   // arbitration between window and ORFs (:1392-1465), Forward + Backward X rows of the windows that stay (:1469-1470), and the
   // part of p7_DomainDecoding_Frameshift that does not depend on the length-model chain
   const float xfE3[2] = { m->om3.xfE_move, m->om3.xfE_loop };
-  struct Decoded { float *btot = nullptr, *etot = nullptr, *fb = nullptr, *ex = nullptr; };   // btot, etot: [L+1]; fb, ex: [L+1][9]; views into the unit's block
+  struct Decoded { float *btot = nullptr, *etot = nullptr, *fb = nullptr, *e0 = nullptr; };   // btot, etot, e0: [L+1]; fb: [L+1][9]; views into the unit's block
   std::vector<std::vector<Decoded>> dec(units.size());
   struct DecBlocks {                                          // one block per unit, from the process-wide pool and back to it when the batch is done
     std::vector<std::vector<float>> v;
@@ -1458,22 +1462,27 @@ int run_batch(bathhost_search *s)
         DV.resize(S.fsw.size());
         {
           std::vector<float> &blk = dec_blocks.v[(size_t) (2 * c + sidx)];
-          blk = ScratchPool::get().take(S.xoff.back() * 20);
-          blk.resize(S.xoff.back() * 20);
+          blk = ScratchPool::get().take(S.xoff.back() * 12);
+          blk.resize(S.xoff.back() * 12);
           for (size_t z = 0; z < S.fsw.size(); ++z) {
-            float *base = blk.data() + S.xoff[z] * 20;
+            float *base = blk.data() + S.xoff[z] * 12;
             const size_t rows = S.xoff[z + 1] - S.xoff[z];     // Lw + 1
-            DV[z].btot = base; DV[z].etot = base + rows; DV[z].fb = base + 2 * rows; DV[z].ex = base + 11 * rows;
+            DV[z].btot = base; DV[z].etot = base + rows; DV[z].fb = base + 2 * rows; DV[z].e0 = base + 11 * rows;
           }
         }
+        // Per row i the reference multiplies three forward x backward products per special state by the scale factors
+        // exp(lsf[i-3+o] + lsb[i+o] + liz), o = 0, 1, 2 (decoding_fs.c:309-352).  The factor of offset o at row i is the factor of offset 0
+        // at row i+o -- the same expression on the same floats -- so one exponential per row is kept (e0) and read at i, i+1, i+2; the
+        // btot / etot sums share theirs the same way (x[i] = exp(lsf[i] + lsb[i] + liz) serves etot[i] and btot[i+3]).  Entries the
+        // walk never reads (rows below 3, offsets past the window end) are left unwritten.
         parallel_chunks(S.fsw.size(), 1, [&](size_t za, size_t zb) {
+          std::vector<float> lsf, lsb, xd;
           for (size_t z = za; z < zb; ++z) {
             if (S.st2[z] != 0) continue;
             const int Lw = S.dwin[S.fsw[z]].length;
             const float *xf = S.fxr + S.xoff[z] * 6, *xb = S.bxr + S.xoff[z] * 6;
             Decoded &D = DV[z];
-            memset(D.btot, 0, sizeof(float) * ((size_t) Lw + 1) * 20);
-            std::vector<float> lsf((size_t) Lw + 2), lsb((size_t) Lw + 2);
+            lsf.resize((size_t) Lw + 2); lsb.resize((size_t) Lw + 2); xd.resize((size_t) Lw + 1);
             lsf[0] = logf(xf[5]);
             for (int i = 1; i <= Lw; ++i) lsf[i] = lsf[i - 1] + logf(xf[(size_t) i * 6 + 5]);
             lsb[Lw + 1] = 0.0f;
@@ -1482,17 +1491,17 @@ int run_batch(bathhost_search *s)
             auto F = [&](int i, int cc) { return xf[(size_t) i * 6 + cc]; };
             auto B = [&](int i, int cc) { return xb[(size_t) i * 6 + cc]; };
             static const int cells[3] = { 1, 2, 4 };          // N, J, C
+            for (int i = 0; i <= Lw; ++i) xd[i] = expf(lsf[i] + lsb[i] + liz);
+            for (int i = 0; i < 3 && i <= Lw; ++i) { D.btot[i] = 0.f; D.etot[i] = 0.f; D.e0[i] = 0.f; }
             for (int i = 3; i <= Lw; ++i) {
-              D.btot[i] = D.btot[i - 3] + F(i - 3, 3) * B(i - 3, 3) * expf(lsf[i - 3] + lsb[i - 3] + liz);
-              D.etot[i] = D.etot[i - 3] + F(i, 0) * B(i, 0) * expf(lsf[i] + lsb[i] + liz);
-              const float e0 = expf(lsf[i - 3] + lsb[i] + liz);
-              const float e1 = (i < Lw)     ? expf(lsf[i - 2] + lsb[i + 1] + liz) : 0.f;
-              const float e2 = (i < Lw - 1) ? expf(lsf[i - 1] + lsb[i + 2] + liz) : 0.f;
+              D.btot[i] = D.btot[i - 3] + F(i - 3, 3) * B(i - 3, 3) * xd[i - 3];
+              D.etot[i] = D.etot[i - 3] + F(i, 0) * B(i, 0) * xd[i];
+              D.e0[i] = expf(lsf[i - 3] + lsb[i] + liz);
               for (int cc = 0; cc < 3; ++cc) {
-                float *fb = &D.fb[(size_t) i * 9 + 3 * cc], *ex = &D.ex[(size_t) i * 9 + 3 * cc];
-                fb[0] = F(i - 3, cells[cc]) * B(i, cells[cc]); ex[0] = e0;
-                if (i < Lw)     { fb[1] = F(i - 2, cells[cc]) * B(i + 1, cells[cc]); ex[1] = e1; }
-                if (i < Lw - 1) { fb[2] = F(i - 1, cells[cc]) * B(i + 2, cells[cc]); ex[2] = e2; }
+                float *fb = &D.fb[(size_t) i * 9 + 3 * cc];
+                fb[0] = F(i - 3, cells[cc]) * B(i, cells[cc]);
+                if (i < Lw)     fb[1] = F(i - 2, cells[cc]) * B(i + 1, cells[cc]);
+                if (i < Lw - 1) fb[2] = F(i - 1, cells[cc]) * B(i + 2, cells[cc]);
               }
             }
           }
@@ -1557,11 +1566,11 @@ int run_batch(bathhost_search *s)
           std::vector<float> mocc((size_t) Lw + 1, 0.f);
           for (int i = 3; i <= Lw; ++i) {
             float njcp = 0.;
-            const float *fb = &D.fb[(size_t) i * 9], *ex = &D.ex[(size_t) i * 9];
+            const float *fb = &D.fb[(size_t) i * 9], *e0 = &D.e0[i];       // e0[o]: the scale factor of codon offset o at this row
             for (int c = 0; c < 3; ++c) {
-              njcp += fb[3 * c] * tL * ex[3 * c];
-              if (i < Lw)     njcp += fb[3 * c + 1] * tL * ex[3 * c + 1];
-              if (i < Lw - 1) njcp += fb[3 * c + 2] * tL * ex[3 * c + 2];
+              njcp += fb[3 * c] * tL * e0[0];
+              if (i < Lw)     njcp += fb[3 * c + 1] * tL * e0[1];
+              if (i < Lw - 1) njcp += fb[3 * c + 2] * tL * e0[2];
             }
             mocc[i] = 1. - njcp;
           }
@@ -1635,6 +1644,7 @@ int run_batch(bathhost_search *s)
         if (wm.valid) { nj = wm.nj_out; L = wm.L_out; } else { nj = 0.0f; L = saveL / 3; }   // first round: a guess for the successor
       }
       if (todo.empty()) break;
+      if (trace.on) fprintf(stderr, "[bathhost]   walk pass %d round %d: %zu of %zu windows\n", walk_pass, round, todo.size(), worder.size());
       if (walk_sequential) todo.resize(1);                    // test hook: one window per round from its true input = the plain sequential walk
       if (round > (int) worder.size() + 2) return fail(s, BATHHOST_EINVAL, "the region walk does not settle");
       // Inside a piece of consecutive windows the chain is followed for real: a window starts from what its predecessor in the piece
