@@ -291,6 +291,8 @@ struct bathhost_search {
   std::string           err;
   std::mutex            err_mu;
   std::vector<SeqRef>   queue;                    // sequences waiting for bathhost_search_run
+  std::vector<uint8_t>  tjb_tab;                  // per ORF length L: the MSV filter's tjb byte cost and the null1 score (they depend on
+  std::vector<float>    null_tab;                 // the profile and L only; grown to the longest block of a batch, kept across batches)
   bool                  finished = false;
   // ---- state the reference carries from one block-strand to the next, across sequences (src/bathsearch.c:817,1060-1105):
   // the hit_windows list is created once per query and never reset; by_id indexes it by ORF rank
@@ -748,14 +750,11 @@ int filter_unit(bathhost_search *s, Unit &S, const std::vector<BlockInfo> &block
     bdesc[b].goff = S.goff(blk); bdesc[b].n = (blk.n >= 15) ? blk.n : 0; bdesc[b].C = blk.C;
     maxlen = std::max(maxlen, blk.n / 3 + 1);
   }
-  // per-length integers and null1 scores depend on the ORF length only: tabulated once per strand
-  std::vector<uint8_t> tjb_of((size_t) maxlen + 1);
-  std::vector<float>   null_of((size_t) maxlen + 1);
-  tjb_of[0] = q.tjb_for_length(1); null_of[0] = 0.0f;
-  parallel_chunks((size_t) maxlen, 4096, [&](size_t a0, size_t a1) {
-    Background lbg = bg;
-    for (size_t L = a0 + 1; L <= a1; ++L) { tjb_of[L] = q.tjb_for_length((int) L); lbg.set_length((int) L); null_of[L] = lbg.null_one((int) L); }
-  });
+  // per-length integers and null1 scores depend on the ORF length only: tabulated once per search (run_batch grows the tables to the
+  // longest block before the units start)
+  const std::vector<uint8_t> &tjb_of = s->tjb_tab;
+  const std::vector<float>   &null_of = s->null_tab;
+  if ((int) tjb_of.size() < maxlen + 1) return fail(s, BATHHOST_EINVAL, "length tables shorter than the longest block");
   // the Gumbel tail is monotone: P > F1 exactly when the bit score is below x1 = invsurv(F1); the device keeps what is within a
   // margin of x1 or above it, the exact tail is evaluated here for those
   const double x1 = gumbel_invsurv(opt.F1, ev[EV_MMU], ev[EV_MLAMBDA]);
@@ -1212,6 +1211,20 @@ int run_batch(bathhost_search *s)
   std::vector<int> chunk_of_block(nb);
   for (size_t c = 0; c < chunks.size(); ++c) for (int b = chunks[c].blk0; b < chunks[c].blk1; ++b) chunk_of_block[(size_t) b] = (int) c;
 
+  {                                                           // length tables of the filters (filter_unit), up to the longest block
+    int maxlen = 1;
+    for (const BlockInfo &blk : blocks) maxlen = std::max(maxlen, blk.n / 3 + 1);
+    const size_t have = s->tjb_tab.size();
+    if (have < (size_t) maxlen + 1) {
+      s->tjb_tab.resize((size_t) maxlen + 1); s->null_tab.resize((size_t) maxlen + 1);
+      if (have == 0) { s->tjb_tab[0] = q.tjb_for_length(1); s->null_tab[0] = 0.0f; }
+      const size_t from = std::max<size_t>(have, 1);
+      parallel_chunks((size_t) maxlen + 1 - from, 4096, [&](size_t a0, size_t a1) {
+        Background lbg = bg;
+        for (size_t L = from + a0; L < from + a1; ++L) { s->tjb_tab[L] = q.tjb_for_length((int) L); lbg.set_length((int) L); s->null_tab[L] = lbg.null_one((int) L); }
+      });
+    }
+  }
   // ---- stages 1-3 per unit, device contexts side by side: upload (top) / reverse complement on the device (bottom), ORFs, filters
   // (Letting searches that run at the same time take this phase one after the other -- it holds the throughput-bound translation + MSV
   // pass -- was measured and lost 5-9 % on one B200: 4.07-4.39 against 4.46-4.54 Gbp/s; a search's filter phase does not fill the device.)
