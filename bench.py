@@ -366,17 +366,22 @@ def search_leg(devices, per_gpu, mbp, cpu_mbp, with_cpu):
     total_nt = sum(len(d) - 2 for _, d in contigs)
     # the three profiles run at the same time, each over per_gpu contexts of its own on every device
     sets = [[capi.Context(d) for d in devices for _ in range(per_gpu)] for _ in models]
-    # one untimed pass of the three profiles (device buffers and page-locked host buffers reach their working sizes, kernels of every
-    # model size get loaded: the steady state of a multi-query search); its time is reported as first_pass_seconds
+    # untimed passes of the three profiles first (device buffers and page-locked host buffers reach their working sizes, kernels of
+    # every model size get loaded: the steady state of a multi-query search); the first one's time is reported as first_pass_seconds
     t0 = time.perf_counter()
     run_search_together(models, pinned, sets)
     cold = time.perf_counter() - t0
-    dt, tables, stats, hits = run_search_together(models, pinned, sets)
+    run_search_together(models, pinned, sets)                  # second untimed pass: with the searches running at the same time, buffers change hands between passes
+    passes = []
+    for _ in range(3):                                         # three timed passes; the metric is the target searched three times / their total time
+        dt_k, tables, stats, hits = run_search_together(models, pinned, sets)
+        passes.append(dt_k)
+    dt = sum(passes) / len(passes)
     # the reference's own order beside it: one profile after the other, every context of the first set + second set on each
     ctxs = sets[0] + sets[1]
     run_search(models, pinned, gpu_ctxs=ctxs)
     secs, tables_serial, _, _ = run_search(models, pinned, gpu_ctxs=ctxs)
-    out = {"metric": "bathsearch --fs Mbp/s", "value": total_nt * len(models) / dt / 1e6, "unit": "Mbp/s", "seconds": dt,
+    out = {"metric": "bathsearch --fs Mbp/s", "value": total_nt * len(models) / dt / 1e6, "unit": "Mbp/s", "seconds": dt, "seconds_per_pass": passes,
            "one_profile_at_a_time": {"value": total_nt * len(models) / sum(secs) / 1e6, "seconds_per_profile": secs, "contexts_per_gpu": 2 * per_gpu},
            "first_pass_seconds": cold, "target_mbp": total_nt / 1e6, "contigs": len(contigs), "profiles": [m.M for m in models],
            "n_gpus": len(devices), "contexts_per_gpu": per_gpu * len(models), "contexts_per_profile_per_gpu": per_gpu, "scaling": "strong",
