@@ -22,6 +22,7 @@ EXPORTS = [
     "bathgpu_orfs_msv_screen", "bathgpu_orfs_fetch", "bathgpu_revcomp_slot", "bathgpu_fs_fwd_block", "bathgpu_fs_forward_matrices",
     "bathgpu_bias_forward", "bathgpu_orfs_stage_breakdown", "bathgpu_measure_int16_peak", "bathgpu_orf_forward_matrices",
     "bathgpu_packed4_bytes", "bathgpu_pack_dna4", "bathgpu_upload_block_packed4", "bathgpu_fs_fwd_block_packed4",
+    "bathgpu_upload_block_segments",
 ]
 
 
@@ -88,6 +89,8 @@ def load():
     L.bathgpu_packed4_bytes.argtypes = [C.c_int64]
     L.bathgpu_pack_dna4.restype = C.c_int
     L.bathgpu_pack_dna4.argtypes = [C.POINTER(C.c_uint8), C.c_int64, C.POINTER(C.c_uint8)]
+    L.bathgpu_upload_block_segments.restype = C.c_int
+    L.bathgpu_upload_block_segments.argtypes = [vp, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_int64), C.c_int]
     L.bathgpu_upload_block_packed4.restype = C.c_int
     L.bathgpu_upload_block_packed4.argtypes = [vp, C.POINTER(C.c_uint8), C.c_int64]
     L.bathgpu_fs_fwd_windows.restype = C.c_int
@@ -238,6 +241,13 @@ class Context:
     def upload_block(self, dsq):
         dsq = np.ascontiguousarray(dsq, dtype=np.uint8)
         self._check(self.lib.bathgpu_upload_block(self.h, dsq.ctypes.data_as(C.POINTER(C.c_uint8)), len(dsq) - 2))
+
+    def upload_block_segments(self, pieces):
+        """bathgpu_upload_block_segments: arrays of nucleotide codes (no sentinels) that follow one another in the resident block"""
+        pieces = [np.ascontiguousarray(p, dtype=np.uint8) for p in pieces]
+        ptrs = (C.POINTER(C.c_uint8) * len(pieces))(*[p.ctypes.data_as(C.POINTER(C.c_uint8)) for p in pieces])
+        lens = (C.c_int64 * len(pieces))(*[len(p) for p in pieces])
+        self._check(self.lib.bathgpu_upload_block_segments(self.h, ptrs, lens, len(pieces)))
 
     def upload_block_packed4(self, packed, n):
         """bathgpu_upload_block_packed4: a block already packed two nucleotides per byte (pack_dna4)"""

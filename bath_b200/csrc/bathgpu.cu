@@ -825,6 +825,34 @@ extern "C" int bathgpu_upload_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_
   return BATHGPU_OK;
 }
 
+extern "C" int bathgpu_upload_block_segments(bathgpu_ctx *ctx, const uint8_t *const *seg, const int64_t *seg_n, int nseg)
+{
+  if (!ctx || !seg || !seg_n || nseg < 1) return fail(ctx, BATHGPU_EINVAL, "bad arguments to bathgpu_upload_block_segments");
+  long long n = 0;
+  for (int g = 0; g < nseg; ++g) {
+    if (!seg[g] || seg_n[g] < 1) return fail(ctx, BATHGPU_EINVAL, "segment %d is empty", g);
+    n += seg_n[g];
+  }
+  CUDA_TRY(ctx, enter(ctx));
+  TargetSlot &S = ctx->S();
+  const long long nwords = (n + 8 + 7) / 8 + 24;
+  if (S.dna_bytes.reserve((size_t)n + 2) != BATHGPU_OK || S.dna4.reserve((size_t)nwords * 4) != BATHGPU_OK)
+    return fail(ctx, BATHGPU_EMEM, "device allocation failed for a %lld-nt block", n);
+  uint8_t *d = S.dna_bytes.as<uint8_t>();
+  CUDA_TRY(ctx, cudaMemsetAsync(d, 255, 1, ctx->stream));
+  CUDA_TRY(ctx, cudaMemsetAsync(d + n + 1, 255, 1, ctx->stream));
+  long long off = 0;
+  for (int g = 0; g < nseg; ++g) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(d + 1 + off, seg[g], (size_t)seg_n[g], cudaMemcpyHostToDevice, ctx->stream));
+    off += seg_n[g];
+  }
+  pack_dna4_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(d, n, S.dna4.as<uint32_t>(), nwords);
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, wait_stream(ctx));
+  S.block_n = n; S.nres = 0; S.bytes_valid = true;
+  return BATHGPU_OK;
+}
+
 // ---- host-packed blocks: two nucleotides per byte (nucleotide 2j+1 of dsq in the low nibble of byte j, 2j+2 in the high one, codes
 // above 15 stored as 15 = N), which is the device's own packed layout from word 1 on -- the block crosses the link at half the bytes
 // and needs no packing pass.

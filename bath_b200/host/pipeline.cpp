@@ -1239,6 +1239,11 @@ int run_batch(bathhost_search *s)
       if (ch.segs.size() == 1) {                               // the caller's buffer as it is (the byte before and the one after are not read)
         const ChunkSeg &g = ch.segs[0];
         BE_TRY(s, BE.upload_block(BE.ctx, seqs[(size_t) g.seq].dsq + (g.from - 1), ch.n), "bathgpu_upload_block");
+      } else if (BE.upload_block_segments) {                 // every piece crosses the link from the caller's buffer: no host copy of the chunk
+        std::vector<const uint8_t *> sp(ch.segs.size());
+        std::vector<int64_t> sn(ch.segs.size());
+        for (size_t g = 0; g < ch.segs.size(); ++g) { sp[g] = seqs[(size_t) ch.segs[g].seq].dsq + ch.segs[g].from; sn[g] = ch.segs[g].to - ch.segs[g].from + 1; }
+        BE_TRY(s, BE.upload_block_segments(BE.ctx, sp.data(), sn.data(), (int) sp.size()), "bathgpu_upload_block_segments");
       } else {
         uint8_t *buf = reinterpret_cast<uint8_t *>(stage.get(BE, ((size_t) ch.n + 2 + 3) / 4));
         if (!buf) return fail(s, BATHHOST_EMEM, "host allocation failed");

@@ -168,6 +168,11 @@ int bathgpu_select_slot(bathgpu_ctx *ctx, int slot);
 /* dsq: ESL_DSQ codes, dsq[1..n] valid (dsq[0], dsq[n+1] sentinels).  Packed to 4 bits/nt on device. */
 int bathgpu_upload_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_t n);
 
+/* The same block handed over as nseg pieces that follow one another on the device (seg[g]: the first nucleotide of piece g, seg_n[g]
+ * nucleotides; e.g. the sequences of a multi-FASTA target searched as one block): each piece crosses the host link from where it lies,
+ * nothing is concatenated on the host.  The resident block has n = sum of seg_n nucleotides and sentinels at both ends. */
+int bathgpu_upload_block_segments(bathgpu_ctx *ctx, const uint8_t *const *seg, const int64_t *seg_n, int nseg);
+
 /* Host-packed blocks ("packed 2-bit/4-bit DNA windows" at the boundary): two nucleotides per byte -- dsq[2j+1] in the low nibble of byte j,
  * dsq[2j+2] in the high one, codes above 15 (Easel's '*' and '~') stored as 15 (N), an odd last nibble 15 -- which is the device's own
  * layout, so the block crosses the link at half the bytes and is not packed again.  bathgpu_pack_dna4 makes that form on the host

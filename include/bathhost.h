@@ -133,6 +133,9 @@ typedef struct {
    * stats.n_multidomain_regions only): bathgpu_orf_forward_matrices */
   int (*orf_forward_matrices)(void *ctx, const void *regs, int n, const float xfE[2], float *mx, float *xrows, int64_t max_rows,
                               float *fwdsc, int32_t *status);
+  /* optional (may be NULL: a chunk made of several sequences is then concatenated in a host buffer first and goes through
+   * upload_block): bathgpu_upload_block_segments */
+  int (*upload_block_segments)(void *ctx, const uint8_t *const *seg, const int64_t *seg_n, int nseg);
 } bathhost_backend;
 
 /* 0 / unset fields take bathsearch's defaults (src/p7_pipeline.c:145-214; src/bathsearch.c:94) */

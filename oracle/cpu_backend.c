@@ -151,6 +151,22 @@ int bo_backend_upload_block(void *ctx, const uint8_t *dsq, int64_t n)
   return BO_OK;
 }
 
+/* bathgpu_upload_block_segments: the block handed over as pieces (seg[g] points at the first nucleotide of piece g) */
+int bo_backend_upload_block_segments(void *ctx, const uint8_t *const *seg, const int64_t *seg_n, int nseg)
+{
+  bo_backend *b = ctx;
+  int64_t n = 0, off = 0;
+  int g;
+  if (!seg || !seg_n || nseg < 1) return BO_EINVAL;
+  for (g = 0; g < nseg; g++) { if (!seg[g] || seg_n[g] < 1) return BO_EINVAL; n += seg_n[g]; }
+  free(b->dsq[b->cur]);
+  b->dsq[b->cur] = malloc((size_t) n + 2);
+  b->dsq[b->cur][0] = 255; b->dsq[b->cur][n + 1] = 255;
+  for (g = 0; g < nseg; g++) { memcpy(b->dsq[b->cur] + 1 + off, seg[g], (size_t) seg_n[g]); off += seg_n[g]; }
+  b->n[b->cur] = n;
+  return BO_OK;
+}
+
 int bo_backend_revcomp_slot(void *ctx, int src, int dst)
 {
   bo_backend *b = ctx;

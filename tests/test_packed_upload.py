@@ -114,3 +114,35 @@ def test_packed_block_feeds_the_orf_finder_and_revcomp(oracle, gpu_ctx, entry):
         assert np.array_equal(h0["usc"], h1["usc"])
         for a, b in zip(h0, h1):                                 # residue offsets are handed out in arrival order: compare the residues
             assert np.array_equal(r0[a["offset"]: a["offset"] + a["n"]], r1[b["offset"]: b["offset"] + b["n"]])
+
+
+@pytest.mark.gpu
+def test_segment_upload_equals_one_block(oracle, gpu_ctx):
+    """bathgpu_upload_block_segments: pieces that follow one another on the device == the concatenated block uploaded at once
+    (Forward scores of windows across the seams bit for bit; reverse complement made from it)"""
+    from bath_b200 import capi
+    model = oracle.Model(common.golden("AMP_N.bhmm"))
+    gpu_ctx.load_fs_profile(3, model.rfv(3), model.tfv(3))
+    rng = np.random.default_rng(21)
+    lens = [1, 7, 100_003, 8, 250_000, 33_333]
+    pieces = [common.random_dna(rng, n, p_degenerate=0.002)[1:-1].copy() for n in lens]
+    whole = np.concatenate([[255]] + pieces + [[255]]).astype(np.uint8)
+    n = len(whole) - 2
+    seams = np.cumsum(lens)[:-1]
+    starts = np.concatenate([rng.integers(1, n - 1300, 500), np.maximum(1, seams - 300), [1, n - 1199]])
+    w = capi.Context.make_windows(starts, np.full(len(starts), 1200))
+    gpu_ctx.select_slot(0)
+    gpu_ctx.upload_block(whole)
+    sc0, st0 = gpu_ctx.fs_fwd_windows(w)
+    gpu_ctx.revcomp_slot(0, 1); gpu_ctx.select_slot(1)
+    rc0, _ = gpu_ctx.fs_fwd_windows(w)
+    gpu_ctx.select_slot(0)
+    gpu_ctx.upload_block(np.zeros(n + 2, np.uint8))
+    gpu_ctx.upload_block_segments(pieces)
+    sc1, st1 = gpu_ctx.fs_fwd_windows(w)
+    gpu_ctx.revcomp_slot(0, 1); gpu_ctx.select_slot(1)
+    rc1, _ = gpu_ctx.fs_fwd_windows(w)
+    gpu_ctx.select_slot(0)
+    assert np.array_equal(sc0, sc1) and np.array_equal(st0, st1) and np.array_equal(rc0, rc1)
+    with pytest.raises(capi.BathGpuError):
+        gpu_ctx.upload_block_segments([pieces[0], np.zeros(0, np.uint8)])

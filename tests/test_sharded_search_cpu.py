@@ -130,3 +130,25 @@ def test_three_profiles_finished_at_once_equal_one_after_the_other(oracle):
     for s in searches:
         s.close()
     del pairs
+
+
+def test_segment_upload_equals_host_concatenation(oracle):
+    """a chunk made of several sequences: handed to the backend piece by piece (upload_block_segments) or concatenated on the host
+    first (a backend without the entry) -- the same tables"""
+    from bath_b200 import hostapi
+    targets = _targets("2OG-FeII_Oxy_3-nt-fs.fa")
+    model = hostapi.QueryModel(common.golden("2OG-FeII_Oxy_3.bhmm"))
+    out = []
+    for drop in (False, True):
+        pair = oracle.cpu_backend(2)
+        if drop:
+            pair[0].upload_block_segments = None
+        search = hostapi.Search(model, backend=pair[0], chunk_nt=10_000_000)      # all ten sequences in one chunk
+        for name, dsq in targets:
+            search.queue_sequence(name, dsq)
+        search.finish()
+        out.append((search.tblout(), search.stats()))
+        search.close()
+        del pair
+    _same(out[0], out[1])
+    assert out[0][1]["n_hits_reported"] >= 8
