@@ -293,6 +293,7 @@ struct bathhost_search {
   std::vector<SeqRef>   queue;                    // sequences waiting for bathhost_search_run
   std::vector<uint8_t>  tjb_tab;                  // per ORF length L: the MSV filter's tjb byte cost and the null1 score (they depend on
   std::vector<float>    null_tab;                 // the profile and L only; grown to the longest block of a batch, kept across batches)
+  std::vector<float>    compo_term;               // summands of the local composition per node and residue (compo_terms)
   bool                  finished = false;
   // ---- state the reference carries from one block-strand to the next, across sequences (src/bathsearch.c:817,1060-1105):
   // the hit_windows list is created once per query and never reset; by_id indexes it by ORF rank
@@ -431,21 +432,33 @@ static const double g_trace_call_ms = [] { const char *e = getenv("BATHHOST_TRAC
        if (st_ != 0) return fail(s, st_, std::string(what) + " failed: " +                      \
        (BE.last_error ? BE.last_error(BE.ctx) : "?")); } while (0)
 
-// p7_pli_ComputeLocalCompo (src/p7_pipeline.c:427-458)
-void local_compo(const bathhost_model *m, const Background &bg, int k_start, int k_end, float *compo)
+// p7_pli_ComputeLocalCompo (src/p7_pipeline.c:427-458).  The summand of node k and residue x, f[x] * exp((base_b - rbv[x][k]) / scale_b),
+// depends on the profile and the background only: compo_terms tabulates it once per search ([k][x], k = 0..M), and the sum below adds
+// the tabulated floats in the reference's order -- the same additions on the same values as recomputing 20 exponentials per node for
+// every ORF that reaches the local-composition test (which was the largest host cost of the filter phase).
+std::vector<float> compo_terms(const bathhost_model *m, const Background &bg)
 {
   const ProteinProfile &q = m->prot;
   const int M = q.M;
+  std::vector<float> term((size_t) (M + 1) * kK, 0.0f);
+  for (int k = 1; k <= M; ++k)
+    for (int x = 0; x < kK; ++x) {
+      const float log_odds = ((float) q.base_b - (float) q.rbv[(size_t) x * (M + 1) + k]) / q.scale_b;
+      term[(size_t) k * kK + x] = bg.f[x] * expf(log_odds);
+    }
+  return term;
+}
+
+void local_compo(const bathhost_model *m, const float *term, int k_start, int k_end, float *compo)
+{
+  const int M = m->prot.M;
   int k_len = k_end - k_start + 1;
   if (k_len < 20) { k_start -= (20 - k_len) / 2; k_end += (20 - k_len) / 2; }
   k_start = std::max(1, k_start);
   k_end   = std::min(M, k_end);
   for (int x = 0; x < kK; ++x) compo[x] = 0.0f;
   for (int k = k_start; k <= k_end; ++k)
-    for (int x = 0; x < kK; ++x) {
-      const float log_odds = ((float) q.base_b - (float) q.rbv[(size_t) x * (M + 1) + k]) / q.scale_b;
-      compo[x] += bg.f[x] * expf(log_odds);
-    }
+    for (int x = 0; x < kK; ++x) compo[x] += term[(size_t) k * kK + x];
   float sum = 0.0f;                                  // esl_vec_FNorm
   for (int x = 0; x < kK; ++x) sum += compo[x];
   if (sum != 0.0f) for (int x = 0; x < kK; ++x) compo[x] /= sum;
@@ -941,7 +954,7 @@ int filter_unit(bathhost_search *s, Unit &S, const std::vector<BlockInfo> &block
             k_max = std::max(k_max, wins_of[t][w].k);
             k_min = std::min(k_min, wins_of[t][w].k - wins_of[t][w].length + 1);
           }
-          local_compo(m, lbg, k_min, k_max, lcompo);
+          local_compo(m, s->compo_term.data(), k_min, k_max, lcompo);
           lbg.set_filter(M, lcompo);
           memcpy(&tables[z * 2 * kKp], &lbg.eo[0][0], sizeof(float) * 2 * kKp);
           items[z] = bathgpu_bias_item{ o.offset, o.n, (int32_t) z, Background::p1_for_length(o.n), 0 };
@@ -1211,6 +1224,7 @@ int run_batch(bathhost_search *s)
   std::vector<int> chunk_of_block(nb);
   for (size_t c = 0; c < chunks.size(); ++c) for (int b = chunks[c].blk0; b < chunks[c].blk1; ++b) chunk_of_block[(size_t) b] = (int) c;
 
+  if (s->compo_term.empty()) s->compo_term = compo_terms(m, bg);
   {                                                           // length tables of the filters (filter_unit), up to the longest block
     int maxlen = 1;
     for (const BlockInfo &blk : blocks) maxlen = std::max(maxlen, blk.n / 3 + 1);
@@ -1406,7 +1420,7 @@ int run_batch(bathhost_search *s)
               float lcompo[kK];
               for (size_t w = wa; w < wb; ++w) {
                 if (first_item[w + 1] - first_item[w] != 2) continue;
-                local_compo(m, lbg, pre[w].k_min, pre[w].k_max, lcompo);
+                local_compo(m, s->compo_term.data(), pre[w].k_min, pre[w].k_max, lcompo);
                 lbg.set_filter(M, lcompo);
                 memcpy(&tables[(size_t) items[(size_t) first_item[w] + 1].table * 2 * kKp], &lbg.eo[0][0], sizeof(float) * 2 * kKp);
               }
