@@ -407,7 +407,7 @@ def search_leg(devices, per_gpu, mbp, cpu_mbp, with_cpu):
         po.lib(native=True)
         ncpu = os.cpu_count() or 1
         sub, n = cpu_sample_contigs(contigs, cpu_mbp)
-        be, keep = po.cpu_backend(ncpu)
+        be, keep = po.cpu_backend(ncpu, simd=True)
         run_search(models[:1], sub[:1], backends=be)              # thread pool and tables warm, as the GPU arm's untimed first pass
         t0 = time.perf_counter()
         csecs, ctables, _, chits = run_search(models, sub, backends=be)
@@ -416,7 +416,7 @@ def search_leg(devices, per_gpu, mbp, cpu_mbp, with_cpu):
         _, gtables, _, _ = run_search(models, sub, gpu_ctxs=ctxs)
         out["cpu_baseline"] = {"value": n * len(models) / cdt / 1e6, "unit": "Mbp/s", "cores": ncpu, "kind": "port", "hits": [len(h) for h in chits],
                                "seconds_per_profile": csecs,
-                               "sample": f"first {n / 1e6:g} Mbp of the target ({len(sub)} contigs), 3 profiles ({cdt:.1f} s, {ncpu} threads, C oracle behind the same host pipeline)"}
+                               "sample": f"first {n / 1e6:g} Mbp of the target ({len(sub)} contigs), 3 profiles ({cdt:.1f} s, {ncpu} threads, C oracle behind the same host pipeline, its MSV / SSV screen on the AVX2 build where the host has AVX2)"}
         cmp = [compare_tables(g, c) for g, c in zip(gtables, ctables)]
         out["checks"]["hits_identical_to_cpu_prefix"] = bool(all(c[1] for c in cmp))
         out["checks"]["cpu_prefix_tables_byte_identical"] = [bool(c[0]) for c in cmp]
@@ -437,7 +437,7 @@ def search_leg_cpu(mbp, nthreads, target_mbp):
     po.lib(native=True)
     models, contigs, plants = search_target(target_mbp)
     sub, n = cpu_sample_contigs(contigs, mbp)
-    be, keep = po.cpu_backend(nthreads)
+    be, keep = po.cpu_backend(nthreads, simd=True)
     run_search(models[:1], sub[:1], backends=be)
     t0 = time.perf_counter()
     secs, tables, stats, hits = run_search(models, sub, backends=be)
@@ -445,7 +445,7 @@ def search_leg_cpu(mbp, nthreads, target_mbp):
     del keep
     return {"value": n * len(models) / dt / 1e6, "unit": "Mbp/s", "cores": nthreads, "kind": "port", "hits": [len(h) for h in hits],
             "seconds_per_profile": secs,
-            "sample": f"first {n / 1e6:g} Mbp of the target ({len(sub)} contigs), 3 profiles ({dt:.1f} s, {nthreads} threads, C oracle behind the same host pipeline)"}
+            "sample": f"first {n / 1e6:g} Mbp of the target ({len(sub)} contigs), 3 profiles ({dt:.1f} s, {nthreads} threads, C oracle behind the same host pipeline, its MSV / SSV screen on the AVX2 build where the host has AVX2)"}
 
 
 def cpu_sample_contigs(contigs, mbp):

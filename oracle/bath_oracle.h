@@ -348,6 +348,12 @@ int bo_batch_ForwardParser_3Codons(const uint8_t *dsq, const int64_t *start, con
                                    const BO_FS_OPROFILE *om, int nthreads, float *sc, int32_t *status);
 /* ===== fwd3_avx2.c: the same batch on an AVX2 + FMA build of the parser (the CPU arm of bench.py; checked against the scalar one) ===== */
 int bo_fwd3_simd_supported(void);
+/* msv_avx2.c: AVX2 build of p7_MSVFilter + SSV shortcut for the CPU arm of bench.py's search metric (bit-identical to bo_MSVFilter) */
+typedef struct bo_msv_simd_s bo_msv_simd;
+int          bo_msv_simd_supported(void);
+bo_msv_simd *bo_msv_simd_create(const BO_OPROFILE *om);
+void         bo_msv_simd_destroy(bo_msv_simd *im);
+int          bo_MSVFilter_simd(const bo_msv_simd *im, const uint8_t *dsq, int L, const BO_OPROFILE *om, float *ret_sc);
 int bo_batch_ForwardParser_3Codons_simd(const uint8_t *dsq, const int64_t *start, const int32_t *L, int n,
                                         const BO_FS_OPROFILE *om, int nthreads, float *sc, int32_t *status);
 

@@ -26,6 +26,8 @@ typedef struct {
   uint8_t       **dsq;      int64_t *n;
   uint8_t       **res;      int64_t *nres;
   bathgpu_orf_hit **hits;   int64_t *nhits;     /* per slot: survivors of the last screen */
+  int             use_simd;       /* bo_backend_set_simd: the MSV screen on the AVX2 build (msv_avx2.c; bench.py's CPU arm) */
+  bo_msv_simd    *msv_simd;
 } bo_backend;
 
 static int grow_slots(bo_backend *b, int want)
@@ -55,9 +57,20 @@ void bo_backend_destroy(bo_backend *b)
   if (!b) return;
   bo_fs_oprofile_destroy(b->om3); bo_fs_oprofile_destroy(b->om5); bo_oprofile_destroy(b->om);
   free(b->ssv_scores);
+  bo_msv_simd_destroy(b->msv_simd);
   for (s = 0; s < b->nslots; s++) { free(b->dsq[s]); free(b->res[s]); free(b->hits[s]); }
   free(b->dsq); free(b->n); free(b->res); free(b->nres); free(b->hits); free(b->nhits);
   free(b);
+}
+
+/* The MSV + SSV screen of every ORF on the AVX2 build of the same byte arithmetic (returns 1 if it is in use).  The scalar restatement
+ * stays the default: tests check the device against it; bench.py's CPU arm asks for the SIMD one. */
+int bo_backend_set_simd(bo_backend *b, int on)
+{
+  if (!b) return 0;
+  b->use_simd = on && bo_msv_simd_supported();
+  if (b->use_simd && b->om && !b->msv_simd) b->msv_simd = bo_msv_simd_create(b->om);
+  return b->use_simd;
 }
 
 const char *bo_backend_last_error(const void *ctx) { return ctx ? ((const bo_backend *) ctx)->err : "no context"; }
@@ -129,6 +142,8 @@ int bo_backend_load_filter_profile(void *ctx, const void *prm_, const uint8_t *r
   b->ssv_scores = malloc((size_t)(M + 1) * BO_KP);
   bo_oprofile_ssv_scores(om, b->ssv_scores);
   b->lanes_u8 = p->cpu_lanes_u8; b->lanes_i16 = p->cpu_lanes_i16;
+  bo_msv_simd_destroy(b->msv_simd); b->msv_simd = NULL;
+  if (b->use_simd) b->msv_simd = bo_msv_simd_create(om);
   return BO_OK;
 }
 
@@ -560,7 +575,8 @@ static void msvx_item(bo_backend *b, void *arg, int i)
   d[0] = d[L + 1] = BO_DSQ_SENTINEL;
   memcpy(d + 1, a->res + a->orfs[i].offset, (size_t) L);
   om.tjb_b = a->tjb_of[L < a->max_len ? L : a->max_len];
-  a->st[i] = bo_MSVFilter(d, L, &om, &a->usc[i]);
+  if (b->use_simd && b->msv_simd && om.M <= 1024) a->st[i] = bo_MSVFilter_simd(b->msv_simd, d, L, &om, &a->usc[i]);
+  else a->st[i] = bo_MSVFilter(d, L, &om, &a->usc[i]);
   free(d);
 }
 

@@ -367,15 +367,19 @@ def windows(wl):
     return [(wl.w[z].n, wl.w[z].k, wl.w[z].length, wl.w[z].score) for z in range(wl.count)]
 
 
-def cpu_backend(nthreads=1):
+def cpu_backend(nthreads=1, simd=False):
     """The batched stage calls of include/bathgpu.h on the CPU (oracle/cpu_backend.c), as a bathhost_backend table for the
-    host pipeline.  TESTS AND BENCH ONLY.  Returns (backend struct, keep-alive handle)."""
+    host pipeline.  TESTS AND BENCH ONLY.  Returns (backend struct, keep-alive handle).  simd=True: the MSV + SSV screen of every ORF on
+    the AVX2 build of the same byte arithmetic (msv_avx2.c), for bench.py's CPU arm; the scalar restatement is the checker."""
     from bath_b200 import hostapi
     L = lib()
     L.bo_backend_create.restype = C.c_void_p
     L.bo_backend_create.argtypes = [C.c_int]
     L.bo_backend_destroy.argtypes = [C.c_void_p]
     h = L.bo_backend_create(int(nthreads))
+    if simd:
+        L.bo_backend_set_simd.argtypes = [C.c_void_p, C.c_int]
+        L.bo_backend_set_simd(h, 1)
     be = hostapi.Backend()
     be.ctx = h
     for n in hostapi.Backend._names:
