@@ -563,21 +563,24 @@ static void xl_item(bo_backend *b, void *arg, int i)
   a->orfs[i] = NULL; a->norf[i] = 0; a->res[i] = NULL; a->nres[i] = 0;
   if (a->blk[i].n >= 3) bo_find_orfs(b->dsq[b->cur] + a->blk[i].goff, a->blk[i].n, a->gcode, a->min_len, &a->orfs[i], &a->norf[i], &a->res[i], &a->nres[i]);
 }
-typedef struct { bo_backend *b; const BO_ORF *orfs; const uint8_t *res; const uint8_t *tjb_of; int max_len; float *usc; int32_t *st; const uint8_t *dead; } msvx_args;
-static void msvx_item(bo_backend *b, void *arg, int i)
+/* MSV over every ORF of every block in ONE parallel pass (item = global ORF index; blk_of / first map it back to its block) */
+typedef struct { BO_ORF **orfs; uint8_t **res; const int *blk_of; const int64_t *first; const uint8_t *tjb_of; int max_len; float *usc; int32_t *st; const uint8_t *dead; } msvx_args;
+static void msvx_item(bo_backend *b, void *arg, int g)
 {
   msvx_args *a = arg;
   BO_OPROFILE om = *b->om;
-  int L = a->orfs[i].n;
-  uint8_t *d;
-  if (a->dead[i]) { a->usc[i] = -INFINITY; a->st[i] = 0; return; }
-  d = malloc((size_t) L + 2);
+  const int bi = a->blk_of[g], i = (int) (g - a->first[bi]);
+  const BO_ORF *o = &a->orfs[bi][i];
+  int L = o->n;
+  uint8_t stackbuf[2048], *d;
+  if (a->dead[g]) { a->usc[g] = -INFINITY; a->st[g] = 0; return; }
+  d = (L + 2 <= (int) sizeof stackbuf) ? stackbuf : malloc((size_t) L + 2);
   d[0] = d[L + 1] = BO_DSQ_SENTINEL;
-  memcpy(d + 1, a->res + a->orfs[i].offset, (size_t) L);
+  memcpy(d + 1, a->res[bi] + o->offset, (size_t) L);
   om.tjb_b = a->tjb_of[L < a->max_len ? L : a->max_len];
-  if (b->use_simd && b->msv_simd && om.M <= 1024) a->st[i] = bo_MSVFilter_simd(b->msv_simd, d, L, &om, &a->usc[i]);
-  else a->st[i] = bo_MSVFilter(d, L, &om, &a->usc[i]);
-  free(d);
+  if (b->use_simd && b->msv_simd && om.M <= 1024) a->st[g] = bo_MSVFilter_simd(b->msv_simd, d, L, &om, &a->usc[g]);
+  else a->st[g] = bo_MSVFilter(d, L, &om, &a->usc[g]);
+  if (d != stackbuf) free(d);
 }
 
 
@@ -591,38 +594,49 @@ int bo_backend_orfs_msv_screen(void *ctx, const void *blocks, int nblocks, int c
   int *norf = calloc((size_t) nblocks, sizeof(int));
   uint8_t **res = calloc((size_t) nblocks, sizeof(uint8_t *));
   int64_t *nr = calloc((size_t) nblocks, sizeof(int64_t));
+  int64_t *first = calloc((size_t) nblocks + 1, sizeof(int64_t));
   xl_args xa = { blk, complement, gcode, min_len, orfs, norf, res, nr };
-  int64_t tot_hits = 0, tot_res = 0, cap_res = 0;
+  int64_t tot_hits = 0, tot_res = 0, cap_res = 0, cap_hits = 0, N, g;
   int bi, i, s = b->cur;
+  int *blk_of; float *usc; int32_t *st; uint8_t *dead;
   parallel_for(b, nblocks, xl_item, &xa);
   free(b->hits[s]); b->hits[s] = NULL; b->nhits[s] = 0;
   free(b->res[s]); b->res[s] = NULL; b->nres[s] = 0;
-  for (bi = 0; bi < nblocks; bi++) cap_res += nr[bi];
+  for (bi = 0; bi < nblocks; bi++) { cap_res += nr[bi]; first[bi + 1] = first[bi] + norf[bi]; if (norfs_per_block) norfs_per_block[bi] = norf[bi]; }
+  N = first[nblocks];
+  if (N > 0x7fffffffLL) { snprintf(b->err, sizeof b->err, "too many ORFs in one call"); return BO_EINVAL; }
   b->res[s] = malloc((size_t) (cap_res > 0 ? cap_res : 1));
+  blk_of = malloc(sizeof(int) * (size_t) (N > 0 ? N : 1));
+  usc = malloc(sizeof(float) * (size_t) (N > 0 ? N : 1));
+  st = malloc(sizeof(int32_t) * (size_t) (N > 0 ? N : 1));
+  dead = calloc((size_t) (N > 0 ? N : 1), 1);
+  for (bi = 0; bi < nblocks; bi++)
+    for (i = 0; i < norf[bi]; i++) {
+      g = first[bi] + i;
+      blk_of[g] = bi;
+      dead[g] = complement ? ((blk[bi].n - orfs[bi][i].start + 1) < blk[bi].C) : (orfs[bi][i].end < blk[bi].C);
+    }
+  {
+    msvx_args ma = { orfs, res, blk_of, first, tjb_of, max_len, usc, st, dead };
+    parallel_for(b, (int) N, msvx_item, &ma);
+  }
   for (bi = 0; bi < nblocks; bi++) {
-    int n = norf[bi];
-    float *usc = malloc(sizeof(float) * (size_t) (n > 0 ? n : 1));
-    int32_t *st = malloc(sizeof(int32_t) * (size_t) (n > 0 ? n : 1));
-    uint8_t *dead = calloc((size_t) (n > 0 ? n : 1), 1);
-    msvx_args ma = { b, orfs[bi], res[bi], tjb_of, max_len, usc, st, dead };
-    if (norfs_per_block) norfs_per_block[bi] = n;
-    for (i = 0; i < n; i++)
-      dead[i] = complement ? ((blk[bi].n - orfs[bi][i].start + 1) < blk[bi].C) : (orfs[bi][i].end < blk[bi].C);
-    parallel_for(b, n, msvx_item, &ma);
-    for (i = 0; i < n; i++) {
+    for (i = 0; i < norf[bi]; i++) {
       int L = orfs[bi][i].n, keep;
-      if (dead[i]) continue;
-      keep = (st[i] != 0) || (((double) usc[i] - (double) null_of[L < max_len ? L : max_len]) / 0.69314718055994529 >= min_bits);
+      g = first[bi] + i;
+      if (dead[g]) continue;
+      keep = (st[g] != 0) || (((double) usc[g] - (double) null_of[L < max_len ? L : max_len]) / 0.69314718055994529 >= min_bits);
       if (!keep) continue;
-      b->hits[s] = realloc(b->hits[s], sizeof(bathgpu_orf_hit) * (size_t) (tot_hits + 1));
+      if (tot_hits == cap_hits) { cap_hits = cap_hits ? 2 * cap_hits : 1024; b->hits[s] = realloc(b->hits[s], sizeof(bathgpu_orf_hit) * (size_t) cap_hits); }
       b->hits[s][tot_hits].block = bi; b->hits[s][tot_hits].index = i; b->hits[s][tot_hits].start = orfs[bi][i].start;
       b->hits[s][tot_hits].end = orfs[bi][i].end; b->hits[s][tot_hits].n = L; b->hits[s][tot_hits].frame = orfs[bi][i].frame;
-      b->hits[s][tot_hits].offset = tot_res; b->hits[s][tot_hits].usc = usc[i]; b->hits[s][tot_hits].status = st[i];
+      b->hits[s][tot_hits].offset = tot_res; b->hits[s][tot_hits].usc = usc[g]; b->hits[s][tot_hits].status = st[g];
       memcpy(b->res[s] + tot_res, res[bi] + orfs[bi][i].offset, (size_t) L);
       tot_res += L; tot_hits++;
     }
-    free(usc); free(st); free(dead); free(orfs[bi]); free(res[bi]);
+    free(orfs[bi]); free(res[bi]);
   }
+  free(usc); free(st); free(dead); free(blk_of); free(first);
   free(orfs); free(norf); free(res); free(nr);
   b->nhits[s] = tot_hits; b->nres[s] = tot_res;
   *nhits = tot_hits; *nres = tot_res;
