@@ -230,6 +230,9 @@ using namespace bathhost;
 // grow-only host buffer for results the device writes: page-locked when the backend offers it (the copies then run at link rate)
 struct HostBuf {
   float *p = nullptr; size_t cap = 0; void (*release)(void *) = nullptr;
+  HostBuf() = default;
+  HostBuf(const HostBuf &) = delete;                   // owns its block
+  HostBuf &operator=(const HostBuf &) = delete;
   float *get(const bathhost_backend &be, size_t nfloats)
   {
     if (nfloats <= cap) return p;
