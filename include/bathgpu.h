@@ -169,7 +169,8 @@ int bathgpu_select_slot(bathgpu_ctx *ctx, int slot);
 int bathgpu_upload_block(bathgpu_ctx *ctx, const uint8_t *dsq, int64_t n);
 
 /* The same block handed over as nseg pieces that follow one another on the device (seg[g]: the first nucleotide of piece g, seg_n[g]
- * nucleotides; e.g. the sequences of a multi-FASTA target searched as one block): each piece crosses the host link from where it lies,
+ * nucleotides; e.g. the sequences of a multi-FASTA target that bathsearch reads one ESL_SQ at a time, src/bathsearch.c:1053-1113,
+ * searched as one block): each piece crosses the host link from where it lies,
  * nothing is concatenated on the host.  The resident block has n = sum of seg_n nucleotides and sentinels at both ends. */
 int bathgpu_upload_block_segments(bathgpu_ctx *ctx, const uint8_t *const *seg, const int64_t *seg_n, int nseg);
 
